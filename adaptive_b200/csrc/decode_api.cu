@@ -1,0 +1,381 @@
+// Greedy and beam decoding drivers: the whole sampler loop of
+// Encoder2Decoder.sampler (adaptive_attention.py:186-216) runs on the device, four launches
+// per step (gate GEMM, fused step kernel, vocabulary GEMM, arg-max + next-token gather) and
+// no host round trip — the arg-max feeds the next step's A operand directly.
+#include "../../include/adaptive_b200.h"
+#include "kernels.cuh"
+
+namespace aa {
+
+namespace {
+
+constexpr int START_ID = 1;  // adaptive_attention.py:188
+constexpr int END_ID = 2;    // build_vocab.py:48-51
+constexpr int MAX_BEAM = 8;
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T), 256);
+    return p;
+  }
+};
+
+struct DecodeWs {
+  float *Wcat, *P, *stat, *Acat, *Acat2, *gates, *c, *c2, *u, *logits;
+  // beam only
+  float *cum, *row_max, *row_lsum, *rec_alpha, *rec_beta;
+  int *rec_word, *rec_src, *rec_wasdone, *done;
+  size_t bytes;
+};
+
+// beam == 0: greedy layout (one row per image, no bookkeeping); beam >= 1: beam layout
+DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
+  const bool bm = beam >= 1;
+  const size_t B = d.B, R = B * (bm ? beam : 1), H = d.H, E = d.E, K = E + H;
+  const size_t L = d.T;  // max_len travels in d.T for sizing
+  Carver c(base);
+  DecodeWs w{};
+  w.Wcat = c.take<float>((size_t)5 * H * K);
+  w.P = c.take<float>(B * d.k * d.a);
+  w.stat = c.take<float>(R * 5 * H);
+  w.Acat = c.take<float>(R * K);
+  w.gates = c.take<float>(R * 5 * H);
+  w.c = c.take<float>(R * H);
+  w.u = c.take<float>(R * H);
+  w.logits = c.take<float>(R * d.Vc);
+  w.Acat2 = c.take<float>(bm ? R * K : 0);
+  w.c2 = c.take<float>(bm ? R * H : 0);
+  w.cum = c.take<float>(bm ? R : 0);
+  w.row_max = c.take<float>(bm ? R : 0);
+  w.row_lsum = c.take<float>(bm ? R : 0);
+  w.rec_alpha = c.take<float>(bm ? L * R * d.k : 0);
+  w.rec_beta = c.take<float>(bm ? L * R : 0);
+  w.rec_word = c.take<int>(bm ? L * R : 0);
+  w.rec_src = c.take<int>(bm ? L * R : 0);
+  w.rec_wasdone = c.take<int>(bm ? L * R : 0);
+  w.done = c.take<int>(bm ? R : 0);
+  w.bytes = c.off;
+  return w;
+}
+
+// Wcat [5H, E+H]: rows 0..4H = [W_ih[:, :E] | W_hh], rows 4H..5H = [W_x[:, :E] | 0]
+// (decode-mode sentinel gate has no recurrent term: h~ = 0)
+__global__ void pack_wcat_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ sen_wx,
+                                 float* __restrict__ Wcat, int H, int E) {
+  const int n = blockIdx.x;  // output row
+  const int K = E + H;
+  float* dst = Wcat + (long long)n * K;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    float v;
+    if (n < 4 * H) v = c < E ? w_ih[(long long)n * 2 * E + c] : w_hh[(long long)n * H + (c - E)];
+    else v = c < E ? sen_wx[(long long)(n - 4 * H) * 2 * E + c] : 0.f;
+    dst[c] = v;
+  }
+}
+
+// Acat[r, :E] = embed[<start>], Acat[r, E:] = h0[r / beam], c[r] = c0[r / beam]
+__global__ void init_state_kernel(const float* __restrict__ embed, const float* __restrict__ h0, const float* __restrict__ c0,
+                                  float* __restrict__ Acat, float* __restrict__ c, int H, int E, int beam) {
+  const int r = blockIdx.x;
+  const int b = r / beam;
+  const int K = E + H;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) Acat[(long long)r * K + i] = embed[(long long)START_ID * E + i];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    Acat[(long long)r * K + E + i] = h0 ? h0[(long long)b * H + i] : 0.f;
+    c[(long long)r * H + i] = c0 ? c0[(long long)b * H + i] : 0.f;
+  }
+}
+
+__global__ void expand_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int cols, int beam) {
+  const int r = blockIdx.x;
+  const int b = r / beam;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) dst[(long long)r * cols + i] = src[(long long)b * cols + i];
+}
+
+__global__ void beam_init_kernel(float* __restrict__ cum, int* __restrict__ done, int R, int beam) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  cum[r] = (r % beam == 0) ? 0.f : -INFINITY;   // only hypothesis 0 is live at step 0
+  done[r] = 0;
+}
+
+// per row: max and log-sum-exp denominator of the logits (log_softmax pieces)
+__global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ logits, int Vc, float* __restrict__ row_max,
+                                                      float* __restrict__ row_lsum) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int r = blockIdx.x;
+  const float* row = logits + (long long)r * Vc;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < Vc; i += 256) m = fmaxf(m, row[i]);
+  m = warp_max(m);
+  if (l == 0) red[w] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+    bc = t;
+  }
+  __syncthreads();
+  m = bc;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < Vc; i += 256) s += expf(row[i] - m);
+  s = warp_sum(s);
+  __syncthreads();
+  if (l == 0) red[w] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    row_max[r] = m;
+    row_lsum[r] = logf(t);
+  }
+}
+
+// One CTA per image: pick the `beam` best candidates among beam*Vc (ties -> lowest flat index),
+// then move the winners' states into the next-step buffers and record the step.
+__global__ void __launch_bounds__(256) beam_select_kernel(const float* __restrict__ logits, const float* __restrict__ row_max,
+                                                          const float* __restrict__ row_lsum, float* __restrict__ cum,
+                                                          int* __restrict__ done, int Vc, int beam, int H, int E,
+                                                          const float* __restrict__ embed, const float* __restrict__ Acat,
+                                                          const float* __restrict__ c, float* __restrict__ Acat_next,
+                                                          float* __restrict__ c_next, int* __restrict__ rec_word,
+                                                          int* __restrict__ rec_src, int* __restrict__ rec_wasdone) {
+  __shared__ float s_cum[MAX_BEAM], s_max[MAX_BEAM], s_lsum[MAX_BEAM];
+  __shared__ int s_done[MAX_BEAM];
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  __shared__ int sel_idx[MAX_BEAM];
+  __shared__ float sel_val[MAX_BEAM];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int r0 = b * beam;
+  if (tid < beam) {
+    s_cum[tid] = cum[r0 + tid];
+    s_max[tid] = row_max[r0 + tid];
+    s_lsum[tid] = row_lsum[r0 + tid];
+    s_done[tid] = done[r0 + tid];
+  }
+  __syncthreads();
+  const int total = beam * Vc;
+  for (int round = 0; round < beam; ++round) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int f = tid; f < total; f += 256) {
+      const int j = f / Vc, v = f - j * Vc;
+      float val;
+      if (s_done[j]) {
+        val = (v == END_ID) ? s_cum[j] : -INFINITY;   // frozen hypothesis: one candidate
+      } else {
+        val = s_cum[j] + ((logits[(long long)(r0 + j) * Vc + v] - s_max[j]) - s_lsum[j]);
+      }
+      bool taken = false;
+      for (int q = 0; q < round; ++q) taken |= (sel_idx[q] == f);
+      if (taken) continue;
+      if (val > best || (val == best && f < bi)) { best = val; bi = f; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (l == 0) { red_v[w] = best; red_i[w] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < 8; ++i)
+        if (red_v[i] > best || (red_v[i] == best && red_i[i] < bi)) { best = red_v[i]; bi = red_i[i]; }
+      if (bi == 0x7fffffff) {  // fewer than `beam` finite candidates: lowest untaken flat index
+        bi = 0;
+        bool again = true;
+        while (again) {
+          again = false;
+          for (int q = 0; q < round; ++q)
+            if (sel_idx[q] == bi) { ++bi; again = true; }
+        }
+        best = -INFINITY;
+      }
+      sel_idx[round] = bi;
+      sel_val[round] = best;
+    }
+    __syncthreads();
+  }
+  // commit: scores, done flags, records
+  if (tid < beam) {
+    const int f = sel_idx[tid];
+    const int src = f / Vc, word = f - src * Vc;
+    const int t_was = s_done[src];
+    cum[r0 + tid] = sel_val[tid];
+    done[r0 + tid] = t_was | (word == END_ID);
+    rec_word[r0 + tid] = word;
+    rec_src[r0 + tid] = src;
+    rec_wasdone[r0 + tid] = t_was;
+  }
+  // move state: Acat_next[slot] = [embed[word] | h[src]], c_next[slot] = c[src]
+  const int K = E + H;
+  for (int slot = 0; slot < beam; ++slot) {
+    const int f = sel_idx[slot];
+    const int src = f / Vc, word = f - src * Vc;
+    const float* a_src = Acat + (long long)(r0 + src) * K;
+    float* a_dst = Acat_next + (long long)(r0 + slot) * K;
+    for (int i = tid; i < E; i += 256) a_dst[i] = embed[(long long)word * E + i];
+    for (int i = tid; i < H; i += 256) {
+      a_dst[E + i] = a_src[E + i];
+      c_next[(long long)(r0 + slot) * H + i] = c[(long long)(r0 + src) * H + i];
+    }
+  }
+}
+
+// follow the back-pointers of the best final hypothesis (slot 0) of each image
+__global__ void beam_backtrack_kernel(const int* __restrict__ rec_word, const int* __restrict__ rec_src,
+                                      const int* __restrict__ rec_wasdone, const float* __restrict__ rec_alpha,
+                                      const float* __restrict__ rec_beta, const float* __restrict__ cum, int L, int R, int beam,
+                                      int k, long long* __restrict__ ids, float* __restrict__ attention,
+                                      float* __restrict__ Beta, float* __restrict__ score) {
+  const int b = blockIdx.x;
+  const int r0 = b * beam;
+  int slot = 0;
+  if (threadIdx.x == 0 && score) score[b] = cum[r0];
+  for (int t = L - 1; t >= 0; --t) {
+    const int src = rec_src[(long long)t * R + r0 + slot];
+    const int was = rec_wasdone[(long long)t * R + r0 + slot];
+    if (threadIdx.x == 0) {
+      ids[(long long)b * L + t] = rec_word[(long long)t * R + r0 + slot];
+      Beta[(long long)b * L + t] = was ? 0.f : rec_beta[(long long)t * R + r0 + src];
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x)
+      attention[((long long)b * L + t) * k + i] = was ? 0.f : rec_alpha[((long long)t * R + r0 + src) * k + i];
+    slot = src;
+  }
+}
+
+int check_decode(const aa_dims* d, const aa_weights* w, int max_len, int beam) {
+  AA_REQUIRE(d && w, "decode: null dims/weights");
+  AA_REQUIRE(d->B >= 0 && d->k >= 1 && d->a >= 1 && d->a <= 128 && d->Vc >= 3, "decode: bad dims");
+  AA_REQUIRE(d->H % 4 == 0 && d->E % 4 == 0 && d->H >= 4 && d->E >= 4, "decode: H and E must be multiples of 4");
+  AA_REQUIRE(max_len >= 1, "decode: max_len must be >= 1");
+  AA_REQUIRE(beam >= 1 && beam <= MAX_BEAM, "decode: beam must be in [1,%d]", MAX_BEAM);
+  AA_REQUIRE(beam <= d->Vc, "decode: beam larger than the vocabulary");
+  return AA_OK;
+}
+
+// shared prologue: weight packing, P, static gate terms, initial state
+int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const float* v_g, const float* h0, const float* c0,
+                    int beam, DecodeWs& ws, cudaStream_t st) {
+  const int B = d.B, H = d.H, E = d.E, R = B * beam, K = E + H;
+  pack_wcat_kernel<<<5 * H, 256, 0, st>>>(w.w_ih, w.w_hh, w.sen_wx, ws.Wcat, H, E);
+  AA_CHECK_LAUNCH("pack_wcat");
+  AA_TRY(gemm_nt(B * d.k, d.a, H, V, H, w.att_wv, H, ws.P, d.a, nullptr, 0, nullptr, nullptr, st));
+  // static (per image) gate terms: v_g half of x and the biases
+  float* stat_img = beam > 1 ? ws.gates : ws.stat;   // [B,5H]; `gates` is free before the first step
+  AA_TRY(gemm_nt(B, 4 * H, E, v_g, E, w.w_ih + E, 2 * E, stat_img, 5 * H, nullptr, 0, w.b_ih, w.b_hh, st));
+  AA_TRY(gemm_nt(B, H, E, v_g, E, w.sen_wx + E, 2 * E, stat_img + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
+  if (beam > 1) {
+    expand_rows_kernel<<<R, 256, 0, st>>>(stat_img, ws.stat, 5 * H, beam);
+    AA_CHECK_LAUNCH("expand_rows");
+  }
+  init_state_kernel<<<R, 256, 0, st>>>(w.embed, h0, c0, ws.Acat, ws.c, H, E, beam);
+  AA_CHECK_LAUNCH("init_state");
+  (void)K;
+  return AA_OK;
+}
+
+}  // namespace
+}  // namespace aa
+
+using namespace aa;
+
+extern "C" {
+
+size_t aa_decode_workspace_bytes(const aa_dims* d, int beam) {
+  if (!d || beam < 0) return 0;
+  return carve_decode(*d, beam, nullptr).bytes;
+}
+
+int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const float* h0,
+                     const float* c0, int max_len, int64_t* ids, float* attention, float* Beta, float* logits_out,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  AA_TRY(check_decode(d, w, max_len, 1));
+  AA_REQUIRE(V && v_g && ids && attention && Beta, "aa_greedy_decode: null pointer");
+  if (d->B == 0) return AA_OK;
+  aa_dims dd = *d;
+  dd.T = max_len;
+  if (!workspace || workspace_bytes < aa_decode_workspace_bytes(&dd, 0)) {
+    set_error("aa_greedy_decode: workspace too small (%zu < %zu)", workspace_bytes, aa_decode_workspace_bytes(&dd, 0));
+    return AA_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DecodeWs ws = carve_decode(dd, 0, workspace);
+  const int B = d->B, H = d->H, E = d->E, K = E + H, Vc = d->Vc, k = d->k, L = max_len;
+  AA_TRY(decode_prologue(dd, *w, V, v_g, h0, c0, 1, ws, st));
+  for (int t = 0; t < L; ++t) {
+    // gates = [emb(w_t) | h_{t-1}] Wcat^T + static              (LSTM + sentinel-x pre-activations)
+    AA_PROF("dec_gate_gemm", st, gemm_nt(B, 5 * H, K, ws.Acat, K, ws.Wcat, K, ws.gates, 5 * H, ws.stat, 5 * H, nullptr, nullptr, st));
+    DecodeStepArgs p{};
+    p.B = B; p.k = k; p.a = d->a; p.H = H; p.beam = 1;
+    p.gates = ws.gates; p.c = ws.c; p.h_out = ws.Acat + E; p.ld_h = K;
+    p.P = ws.P; p.V = V; p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh;
+    p.alpha = attention + (size_t)t * k; p.ld_alpha = (long long)L * k;
+    p.beta = Beta + t; p.ld_beta = L;
+    p.u = ws.u;
+    AA_PROF("dec_step_fused", st, launch_decode_step(p, st));
+    float* lg = logits_out ? logits_out + (size_t)t * B * Vc : ws.logits;
+    AA_PROF("dec_vocab_gemm", st, gemm_nt(B, Vc, H, ws.u, H, w->mlp_w, H, lg, Vc, nullptr, 0, w->mlp_b, nullptr, st));   // :132
+    AA_PROF("dec_argmax", st, launch_argmax_gather(lg, Vc, B, Vc, reinterpret_cast<long long*>(ids) + t, L, w->embed, E, ws.Acat, K, st));   // :201
+  }
+  return AA_OK;
+}
+
+int aa_beam_decode(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const float* h0, const float* c0,
+                   int beam, int max_len, int64_t* ids, float* attention, float* Beta, float* score, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  AA_TRY(check_decode(d, w, max_len, beam));
+  AA_REQUIRE(V && v_g && ids && attention && Beta, "aa_beam_decode: null pointer");
+  if (d->B == 0) return AA_OK;
+  aa_dims dd = *d;
+  dd.T = max_len;
+  if (!workspace || workspace_bytes < aa_decode_workspace_bytes(&dd, beam)) {
+    set_error("aa_beam_decode: workspace too small (%zu < %zu)", workspace_bytes, aa_decode_workspace_bytes(&dd, beam));
+    return AA_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DecodeWs ws = carve_decode(dd, beam, workspace);
+  const int B = d->B, H = d->H, E = d->E, K = E + H, Vc = d->Vc, k = d->k, L = max_len, R = B * beam;
+  AA_TRY(decode_prologue(dd, *w, V, v_g, h0, c0, beam, ws, st));
+  beam_init_kernel<<<ceil_div(R, 256), 256, 0, st>>>(ws.cum, ws.done, R, beam);
+  AA_CHECK_LAUNCH("beam_init");
+  float* Acur = ws.Acat;  float* Anext = ws.Acat2;
+  float* ccur = ws.c;     float* cnext = ws.c2;
+  for (int t = 0; t < L; ++t) {
+    AA_PROF("dec_gate_gemm", st, gemm_nt(R, 5 * H, K, Acur, K, ws.Wcat, K, ws.gates, 5 * H, ws.stat, 5 * H, nullptr, nullptr, st));
+    DecodeStepArgs p{};
+    p.B = R; p.k = k; p.a = d->a; p.H = H; p.beam = beam;
+    p.gates = ws.gates; p.c = ccur; p.h_out = Acur + E; p.ld_h = K;
+    p.P = ws.P; p.V = V; p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh;
+    p.alpha = ws.rec_alpha + (size_t)t * R * k; p.ld_alpha = k;
+    p.beta = ws.rec_beta + (size_t)t * R; p.ld_beta = 1;
+    p.u = ws.u;
+    AA_PROF("dec_step_fused", st, launch_decode_step(p, st));
+    AA_PROF("dec_vocab_gemm", st, gemm_nt(R, Vc, H, ws.u, H, w->mlp_w, H, ws.logits, Vc, nullptr, 0, w->mlp_b, nullptr, st));
+    row_lse_kernel<<<R, 256, 0, st>>>(ws.logits, Vc, ws.row_max, ws.row_lsum);
+    AA_CHECK_LAUNCH("row_lse");
+    beam_select_kernel<<<B, 256, 0, st>>>(ws.logits, ws.row_max, ws.row_lsum, ws.cum, ws.done, Vc, beam, H, E, w->embed, Acur,
+                                          ccur, Anext, cnext, ws.rec_word + (size_t)t * R, ws.rec_src + (size_t)t * R,
+                                          ws.rec_wasdone + (size_t)t * R);
+    AA_CHECK_LAUNCH("beam_select");
+    float* tmp = Acur; Acur = Anext; Anext = tmp;
+    tmp = ccur; ccur = cnext; cnext = tmp;
+  }
+  beam_backtrack_kernel<<<B, 64, 0, st>>>(ws.rec_word, ws.rec_src, ws.rec_wasdone, ws.rec_alpha, ws.rec_beta, ws.cum, L, R, beam,
+                                          k, reinterpret_cast<long long*>(ids), attention, Beta, score);
+  AA_CHECK_LAUNCH("beam_backtrack");
+  return AA_OK;
+}
+
+}  // extern "C"

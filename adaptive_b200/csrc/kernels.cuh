@@ -1,0 +1,84 @@
+// Internal launcher declarations (one per kernel family).  All launchers are asynchronous on
+// `stream`, return AA_OK / error code and never allocate.
+#pragma once
+#include "common.cuh"
+
+namespace aa {
+
+// ---- pointwise.cu ----------------------------------------------------------------------
+// x[b,t,:] = [embed[cap[b,t]] ; v_g[b]]                      (baseline_attention.py:151-154)
+int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, int B, int T, int E, int Vc,
+                   cudaStream_t s);
+// one LSTM cell update from pre-activations (gate order i,f,g,o)   (baseline_attention.py:172)
+//   pre [B,4H] row stride ld_pre; c_prev [B,H] stride ld_cprev;
+//   writes acts[b, t, 4, H] (post-activation), cells[b,t,:], hiddens[b,t,:], hs_next (= h, may be null)
+int launch_lstm_cell_fwd(const float* pre, long long ld_pre, const float* c_prev, long long ld_cprev, float* acts,
+                         long long ld_acts, float* c_out, long long ld_c, float* h_out, long long ld_h, float* hs_next,
+                         long long ld_hs, int B, int H, cudaStream_t s);
+// sentinel: g = sigmoid(pre) ; s = g * tanh(cell)                   (adaptive_attention.py:79-83)
+int launch_sentinel_fwd(const float* pre, const float* cells, float* g, float* s_out, long long n, cudaStream_t s);
+// sentinel backward: da = ds*tanh(c)*g*(1-g) ; dcell = ds*g*(1-tanh(c)^2)
+int launch_sentinel_bwd(const float* ds, const float* g, const float* cells, float* da, float* dcell, long long n,
+                        cudaStream_t s);
+// one BPTT step of the LSTM cell.  dh_attn/dhs_next/dcell are the batched (non-recurrent) contributions.
+int launch_lstm_cell_bwd(const float* dh_attn, long long ld_dh, const float* dhs_next, long long ld_dhs,
+                         const float* dh_rec, const float* dcell, long long ld_dcell, const float* dc_rec,
+                         const float* acts, long long ld_acts, const float* cells, long long ld_c, const float* c_prev,
+                         long long ld_cprev, float* dgates, long long ld_dg, float* dc_out, int B, int H,
+                         cudaStream_t s);
+// out[n] = sum_m X[m, n]   (column sums; bias gradients).  out2 (optional) receives a copy.
+int launch_colsum(const float* X, long long ldx, int M, int N, float* out, float* out2, cudaStream_t s);
+// dE[cap[row], :] += dx[row, 0:E]  (dE pre-zeroed) ; dvg[b, :] = sum_t dx[b,t,E:2E]
+int launch_embed_bwd(const long long* cap, const float* dx, float* dE, float* dvg, int B, int T, int E, int Vc,
+                     cudaStream_t s);
+int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t s);
+// row-wise arg-max of logits [B,Vc] (lowest index wins ties); writes ids_out[b*ld_ids] (int64) and, if
+// emb_dst != null, gathers embed[id] into emb_dst[b*ld_emb + 0:E] for the next decode step
+int launch_argmax_gather(const float* logits, long long ld_logits, int B, int Vc, long long* ids_out, long long ld_ids,
+                         const float* embed, int E, float* emb_dst, long long ld_emb, cudaStream_t s);
+int launch_gather_rows(const long long* ids, long long ld_ids, const float* table, int E, int Vc, float* dst, long long ld_dst,
+                       int B, cudaStream_t s);
+int launch_copy2d(float* dst, long long ld_dst, const float* src, long long ld_src, int rows, int cols, cudaStream_t s);
+// mean cross-entropy over rows + gradient: loss += -log_softmax(logits[r])[tgt[r]] / n ; dlogits = (softmax - onehot)/n
+int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
+                      long long ldd, cudaStream_t s);
+
+// ---- atten.cu --------------------------------------------------------------------------
+struct AttenFwdArgs {
+  int B, T, k, a, H;
+  const float *P, *q, *r, *s, *h, *V, *wh;   // P[B,k,a] q,r[B,T,a] s,h[B,T,H] V[B,k,H] wh[a]
+  float *alpha, *beta, *ctx, *u;            // alpha[B,T,k] beta[B,T] ctx[B,T,H] (may be null) u[B,T,H] = c_hat + h
+  float* c_hat;                             // optional [B,T,H]
+};
+int launch_atten_fwd(const AttenFwdArgs& p, cudaStream_t s);
+
+struct AttenBwdArgs {
+  int B, T, k, a, H;
+  const float *P, *q, *r, *s, *V, *wh, *alpha, *beta, *ctx;
+  const float* dchat;     // [B,T,H]
+  const float* d_alpha;   // optional [B,T,k]
+  const float* d_beta;    // optional [B,T]
+  float *ds;              // [B,T,H]  = beta * dchat         (sentinel part added later by GEMM)
+  float *dq, *dr;         // [B,T,a]  dq = sum_i dp_i + dr
+  float *dP;              // [B,k,a]  summed over t
+  float *dV;              // [B,k,H]  sum_t alpha_i dctx     (dP W_v added later by GEMM)
+  float *dwh;             // [a]      pre-zeroed, atomically accumulated
+};
+int launch_atten_bwd(const AttenBwdArgs& p, cudaStream_t s);
+
+// ---- decode.cu -------------------------------------------------------------------------
+struct DecodeStepArgs {
+  int B, k, a, H;
+  int beam;                   // rows per image (1 = greedy); V/P row = b / beam
+  const float* gates;         // [B,5H] pre-activations: i,f,g,o,sentinel
+  float* c;                   // [B,H]  in: c_{t-1}  out: c_t
+  float* h_out; long long ld_h;   // h_t destination (A-operand of the next gate GEMM)
+  const float *P, *V;         // [B/beam,k,a], [B/beam,k,H]
+  const float *Wg, *Ws, *wh;  // [a,H],[a,H],[a]
+  float* alpha; long long ld_alpha;   // alpha[b*ld_alpha + i]
+  float* beta; long long ld_beta;
+  float* u;                   // [B,H]
+};
+int launch_decode_step(const DecodeStepArgs& p, cudaStream_t s);
+
+}  // namespace aa

@@ -1,0 +1,336 @@
+// Element-wise / gather / reduction kernels of the decoder hot path (fp32).
+#include "kernels.cuh"
+
+namespace aa {
+
+namespace {
+
+constexpr int PW_THREADS = 256;
+
+__global__ void build_x_kernel(const long long* __restrict__ cap, const float* __restrict__ embed,
+                               const float* __restrict__ v_g, float* __restrict__ x, int B, int T, int E, int Vc) {
+  const int row = blockIdx.x;  // b*T + t
+  const int b = row / T;
+  long long id = cap[row];
+  id = id < 0 ? 0 : (id >= Vc ? Vc - 1 : id);
+  const float* src = embed + id * (long long)E;
+  const float* vg = v_g + (long long)b * E;
+  float* dst = x + (long long)row * 2 * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    dst[e] = __ldg(src + e);
+    dst[E + e] = __ldg(vg + e);
+  }
+}
+
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ pre, long long ld_pre, const float* __restrict__ c_prev,
+                                     long long ld_cprev, float* __restrict__ acts, long long ld_acts,
+                                     float* __restrict__ c_out, long long ld_c, float* __restrict__ h_out, long long ld_h,
+                                     float* __restrict__ hs_next, long long ld_hs, int B, int H) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  const float* p = pre + b * ld_pre;
+  const float ig = sigmoidf_acc(p[j]);
+  const float fg = sigmoidf_acc(p[H + j]);
+  const float gg = tanhf(p[2 * H + j]);
+  const float og = sigmoidf_acc(p[3 * H + j]);
+  const float c = fg * c_prev[b * ld_cprev + j] + ig * gg;
+  const float h = og * tanhf(c);
+  float* a = acts + b * ld_acts;
+  a[j] = ig; a[H + j] = fg; a[2 * H + j] = gg; a[3 * H + j] = og;
+  c_out[b * ld_c + j] = c;
+  h_out[b * ld_h + j] = h;
+  if (hs_next) hs_next[b * ld_hs + j] = h;
+}
+
+// pre and g may alias (in-place gate)
+__global__ void sentinel_fwd_kernel(const float* pre, const float* __restrict__ cells, float* g, float* __restrict__ s_out,
+                                    long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gv = sigmoidf_acc(pre[i]);
+  g[i] = gv;
+  s_out[i] = gv * tanhf(cells[i]);
+}
+
+__global__ void sentinel_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ g, const float* __restrict__ cells,
+                                    float* __restrict__ da, float* __restrict__ dcell, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = ds[i], gv = g[i], tc = tanhf(cells[i]);
+  da[i] = d * tc * gv * (1.f - gv);
+  dcell[i] = d * gv * (1.f - tc * tc);
+}
+
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_attn, long long ld_dh, const float* __restrict__ dhs_next,
+                                     long long ld_dhs, const float* __restrict__ dh_rec, const float* __restrict__ dcell,
+                                     long long ld_dcell, const float* dc_rec, const float* __restrict__ acts,
+                                     long long ld_acts, const float* __restrict__ cells, long long ld_c,
+                                     const float* __restrict__ c_prev, long long ld_cprev, float* __restrict__ dgates,
+                                     long long ld_dg, float* dc_out, int B, int H) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  float dh = dh_attn[b * ld_dh + j];
+  if (dhs_next) dh += dhs_next[b * ld_dhs + j];
+  if (dh_rec) dh += dh_rec[(long long)b * H + j];
+  const float* a = acts + b * ld_acts;
+  const float ig = a[j], fg = a[H + j], gg = a[2 * H + j], og = a[3 * H + j];
+  const float tc = tanhf(cells[b * ld_c + j]);
+  float dc = dcell[b * ld_dcell + j] + dh * og * (1.f - tc * tc);
+  if (dc_rec) dc += dc_rec[(long long)b * H + j];
+  float* dg = dgates + b * ld_dg;
+  dg[j] = dc * gg * ig * (1.f - ig);
+  dg[H + j] = dc * c_prev[b * ld_cprev + j] * fg * (1.f - fg);
+  dg[2 * H + j] = dc * ig * (1.f - gg * gg);
+  dg[3 * H + j] = dh * tc * og * (1.f - og);
+  dc_out[(long long)b * H + j] = dc * fg;
+}
+
+// block (32, 8): 32 columns per block, rows strided by 8, smem tree over y
+__global__ void colsum_kernel(const float* __restrict__ X, long long ldx, int M, int N, float* __restrict__ out,
+                              float* __restrict__ out2) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (n < N)
+    for (int m = threadIdx.y; m < M; m += 8) acc += X[(long long)m * ldx + n];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    out[n] = t;
+    if (out2) out2[n] = t;
+  }
+}
+
+__global__ void embed_scatter_kernel(const long long* __restrict__ cap, const float* __restrict__ dx, float* __restrict__ dE,
+                                     int E, int Vc) {
+  const int row = blockIdx.x;
+  long long id = cap[row];
+  id = id < 0 ? 0 : (id >= Vc ? Vc - 1 : id);
+  const float* src = dx + (long long)row * 2 * E;
+  float* dst = dE + id * (long long)E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, src[e]);
+}
+
+__global__ void dvg_kernel(const float* __restrict__ dx, float* __restrict__ dvg, int B, int T, int E) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * E) return;
+  const int b = (int)(idx / E), e = (int)(idx % E);
+  const float* p = dx + ((long long)b * T) * 2 * E + E + e;
+  float acc = 0.f;
+  for (int t = 0; t < T; ++t) acc += p[(long long)t * 2 * E];
+  dvg[idx] = acc;
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
+__global__ void copy2d_kernel(float* __restrict__ dst, long long ld_dst, const float* __restrict__ src, long long ld_src,
+                              int rows, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int r = (int)(idx / cols), c = (int)(idx % cols);
+  dst[r * ld_dst + c] = src[r * ld_src + c];
+}
+
+__global__ void gather_rows_kernel(const long long* __restrict__ ids, long long ld_ids, const float* __restrict__ table, int E,
+                                   int Vc, float* __restrict__ dst, long long ld_dst) {
+  const int b = blockIdx.x;
+  long long id = ids[b * ld_ids];
+  id = id < 0 ? 0 : (id >= Vc ? Vc - 1 : id);
+  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[b * ld_dst + e] = __ldg(table + id * E + e);
+}
+
+// One CTA per row.  Lowest index wins ties (torch.max on CPU).
+__global__ void __launch_bounds__(PW_THREADS) argmax_gather_kernel(const float* __restrict__ logits, long long ld_logits,
+                                                                   int Vc, long long* __restrict__ ids_out, long long ld_ids,
+                                                                   const float* __restrict__ embed, int E,
+                                                                   float* __restrict__ emb_dst, long long ld_emb) {
+  __shared__ float sv[PW_THREADS / 32];
+  __shared__ int si[PW_THREADS / 32];
+  __shared__ int winner;
+  const int b = blockIdx.x;
+  const float* row = logits + b * ld_logits;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int n = threadIdx.x; n < Vc; n += blockDim.x) {
+    const float v = row[n];
+    if (v > best || (v == best && n < bi)) { best = v; bi = n; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < PW_THREADS / 32; ++i)
+      if (sv[i] > best || (sv[i] == best && si[i] < bi)) { best = sv[i]; bi = si[i]; }
+    if (bi == 0x7fffffff) bi = 0;  // all-NaN row
+    winner = bi;
+    ids_out[b * ld_ids] = bi;
+  }
+  __syncthreads();
+  if (emb_dst) {
+    const float* src = embed + (long long)winner * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) emb_dst[b * ld_emb + e] = __ldg(src + e);
+  }
+}
+
+__global__ void __launch_bounds__(PW_THREADS) ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld,
+                                                                const long long* __restrict__ tgt, int n, int Vc,
+                                                                float* __restrict__ loss, float* __restrict__ dlogits,
+                                                                long long ldd) {
+  __shared__ float red[PW_THREADS / 32];
+  __shared__ float bcast;
+  const int r = blockIdx.x;
+  const float* row = logits + r * ld;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < Vc; i += blockDim.x) m = fmaxf(m, row[i]);
+  m = warp_max(m);
+  if (l == 0) red[w] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < PW_THREADS / 32; ++i) t = fmaxf(t, red[i]);
+    bcast = t;
+  }
+  __syncthreads();
+  m = bcast;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < Vc; i += blockDim.x) sum += expf(row[i] - m);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (l == 0) red[w] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < PW_THREADS / 32; ++i) t += red[i];
+    bcast = t;
+  }
+  __syncthreads();
+  sum = bcast;
+  const long long t = tgt[r];
+  const float inv_n = 1.f / (float)n;
+  if (threadIdx.x == 0) atomicAdd(loss, (logf(sum) + m - row[t]) * inv_n);
+  if (dlogits) {
+    const float inv = 1.f / sum;
+    float* d = dlogits + r * ldd;
+    for (int i = threadIdx.x; i < Vc; i += blockDim.x) {
+      float p = expf(row[i] - m) * inv;
+      if (i == t) p -= 1.f;
+      d[i] = p * inv_n;
+    }
+  }
+}
+
+inline unsigned blocks_for(long long n) { return (unsigned)((n + PW_THREADS - 1) / PW_THREADS); }
+
+}  // namespace
+
+int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, int B, int T, int E, int Vc,
+                   cudaStream_t s) {
+  if (B * T == 0) return AA_OK;
+  build_x_kernel<<<B * T, 128, 0, s>>>(cap, embed, v_g, x, B, T, E, Vc);
+  AA_CHECK_LAUNCH("build_x");
+  return AA_OK;
+}
+
+int launch_lstm_cell_fwd(const float* pre, long long ld_pre, const float* c_prev, long long ld_cprev, float* acts,
+                         long long ld_acts, float* c_out, long long ld_c, float* h_out, long long ld_h, float* hs_next,
+                         long long ld_hs, int B, int H, cudaStream_t s) {
+  lstm_cell_fwd_kernel<<<blocks_for((long long)B * H), PW_THREADS, 0, s>>>(pre, ld_pre, c_prev, ld_cprev, acts, ld_acts, c_out,
+                                                                           ld_c, h_out, ld_h, hs_next, ld_hs, B, H);
+  AA_CHECK_LAUNCH("lstm_cell_fwd");
+  return AA_OK;
+}
+
+int launch_sentinel_fwd(const float* pre, const float* cells, float* g, float* s_out, long long n, cudaStream_t s) {
+  sentinel_fwd_kernel<<<blocks_for(n), PW_THREADS, 0, s>>>(pre, cells, g, s_out, n);
+  AA_CHECK_LAUNCH("sentinel_fwd");
+  return AA_OK;
+}
+
+int launch_sentinel_bwd(const float* ds, const float* g, const float* cells, float* da, float* dcell, long long n,
+                        cudaStream_t s) {
+  sentinel_bwd_kernel<<<blocks_for(n), PW_THREADS, 0, s>>>(ds, g, cells, da, dcell, n);
+  AA_CHECK_LAUNCH("sentinel_bwd");
+  return AA_OK;
+}
+
+int launch_lstm_cell_bwd(const float* dh_attn, long long ld_dh, const float* dhs_next, long long ld_dhs,
+                         const float* dh_rec, const float* dcell, long long ld_dcell, const float* dc_rec,
+                         const float* acts, long long ld_acts, const float* cells, long long ld_c, const float* c_prev,
+                         long long ld_cprev, float* dgates, long long ld_dg, float* dc_out, int B, int H,
+                         cudaStream_t s) {
+  lstm_cell_bwd_kernel<<<blocks_for((long long)B * H), PW_THREADS, 0, s>>>(dh_attn, ld_dh, dhs_next, ld_dhs, dh_rec, dcell,
+                                                                           ld_dcell, dc_rec, acts, ld_acts, cells, ld_c,
+                                                                           c_prev, ld_cprev, dgates, ld_dg, dc_out, B, H);
+  AA_CHECK_LAUNCH("lstm_cell_bwd");
+  return AA_OK;
+}
+
+int launch_colsum(const float* X, long long ldx, int M, int N, float* out, float* out2, cudaStream_t s) {
+  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, s>>>(X, ldx, M, N, out, out2);
+  AA_CHECK_LAUNCH("colsum");
+  return AA_OK;
+}
+
+int launch_embed_bwd(const long long* cap, const float* dx, float* dE, float* dvg, int B, int T, int E, int Vc,
+                     cudaStream_t s) {
+  if (dE) {
+    embed_scatter_kernel<<<B * T, 128, 0, s>>>(cap, dx, dE, E, Vc);
+    AA_CHECK_LAUNCH("embed_scatter");
+  }
+  if (dvg) {
+    dvg_kernel<<<blocks_for((long long)B * E), PW_THREADS, 0, s>>>(dx, dvg, B, T, E);
+    AA_CHECK_LAUNCH("dvg");
+  }
+  return AA_OK;
+}
+
+int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t s) {
+  add_inplace_kernel<<<blocks_for(n), PW_THREADS, 0, s>>>(y, x, n);
+  AA_CHECK_LAUNCH("add_inplace");
+  return AA_OK;
+}
+
+int launch_argmax_gather(const float* logits, long long ld_logits, int B, int Vc, long long* ids_out, long long ld_ids,
+                         const float* embed, int E, float* emb_dst, long long ld_emb, cudaStream_t s) {
+  argmax_gather_kernel<<<B, PW_THREADS, 0, s>>>(logits, ld_logits, Vc, ids_out, ld_ids, embed, E, emb_dst, ld_emb);
+  AA_CHECK_LAUNCH("argmax_gather");
+  return AA_OK;
+}
+
+int launch_gather_rows(const long long* ids, long long ld_ids, const float* table, int E, int Vc, float* dst, long long ld_dst,
+                       int B, cudaStream_t s) {
+  gather_rows_kernel<<<B, 128, 0, s>>>(ids, ld_ids, table, E, Vc, dst, ld_dst);
+  AA_CHECK_LAUNCH("gather_rows");
+  return AA_OK;
+}
+
+int launch_copy2d(float* dst, long long ld_dst, const float* src, long long ld_src, int rows, int cols, cudaStream_t s) {
+  copy2d_kernel<<<blocks_for((long long)rows * cols), PW_THREADS, 0, s>>>(dst, ld_dst, src, ld_src, rows, cols);
+  AA_CHECK_LAUNCH("copy2d");
+  return AA_OK;
+}
+
+int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
+                      long long ldd, cudaStream_t s) {
+  if (n == 0) return AA_OK;
+  ce_fwd_bwd_kernel<<<n, PW_THREADS, 0, s>>>(logits, ld, tgt, n, Vc, loss, dlogits, ldd);
+  AA_CHECK_LAUNCH("ce_fwd_bwd");
+  return AA_OK;
+}
+
+}  // namespace aa

@@ -1,0 +1,358 @@
+"""Host-side operators over the C ABI: tensors in, tensors out, autograd wired by hand.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all arithmetic of
+the hot path runs in ``libadaptive_sm100.so``.  Every function requires CUDA tensors and
+raises otherwise — there is no CPU path (the CPU restatement lives in ``oracle/`` and is
+test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AADims, AAWeightGrads, AAWeights, KEY_TO_FIELD, WEIGHT_FIELDS, check
+
+ATT_DIM = 49
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("adaptive_b200 operators need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _states2d(st: Optional[torch.Tensor], B: int, H: int) -> Optional[torch.Tensor]:
+    """Accept [1,B,H] (nn.LSTM layout), [B,1,H] (what the reference encoder returns, Q9) or [B,H]."""
+    if st is None:
+        return None
+    if st.dim() == 3:
+        if st.shape[0] == 1 and st.shape[1] == B:
+            st = st[0]
+        elif st.shape[1] == 1 and st.shape[0] == B:
+            st = st[:, 0]
+        else:
+            raise ValueError("state of shape %s does not match batch %d" % (tuple(st.shape), B))
+    if st.shape != (B, H):
+        raise ValueError("state of shape %s, expected (%d, %d)" % (tuple(st.shape), B, H))
+    return _f32c(st)
+
+
+def make_dims(B, T, k, H, E, Vc, a=ATT_DIM) -> AADims:
+    return AADims(B=B, T=T, k=k, a=a, H=H, E=E, Vc=Vc)
+
+
+def weights_struct(w: Sequence[torch.Tensor]) -> AAWeights:
+    s = AAWeights()
+    for name, t in zip(WEIGHT_FIELDS, w):
+        setattr(s, name, t.data_ptr())
+    return s
+
+
+def ordered_weights(named: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, ...]:
+    """Order a ``{state_dict key (without 'decoder.') : tensor}`` mapping like ``aa_weights``."""
+    inv = {v: k for k, v in KEY_TO_FIELD.items()}
+    return tuple(named[inv[f]] for f in WEIGHT_FIELDS)
+
+
+def _check_weights(w: Sequence[torch.Tensor], H, E, Vc, a):
+    shapes = [(Vc, E), (4 * H, 2 * E), (4 * H, H), (4 * H,), (4 * H,), (H, 2 * E), (H, H), (a, H), (a, H), (a, H),
+              (1, a), (Vc, H), (Vc,)]
+    for name, t, s in zip(WEIGHT_FIELDS, w, shapes):
+        if tuple(t.shape) != s:
+            raise ValueError("weight %s has shape %s, expected %s" % (name, tuple(t.shape), s))
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("weight %s must be contiguous float32" % name)
+        _need_cuda(t)
+
+
+class _DecoderFn(torch.autograd.Function):
+    """``Decoder.forward`` (baseline_attention.py:148-194) + hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, V, v_g, captions, h0, c0, *w):
+        lib = _lib.load()
+        B, k, H = V.shape
+        T = captions.shape[1]
+        E = v_g.shape[1]
+        Vc = w[0].shape[0]
+        a = w[7].shape[0]
+        _check_weights(w, H, E, Vc, a)
+        dev = V.device
+        d = make_dims(B, T, k, H, E, Vc, a)
+        scores = torch.empty(B, T, Vc, device=dev, dtype=torch.float32)
+        alpha = torch.empty(B, T, k, device=dev, dtype=torch.float32)
+        beta = torch.empty(B, T, 1, device=dev, dtype=torch.float32)
+        hT = torch.empty(B, H, device=dev, dtype=torch.float32)
+        cT = torch.empty(B, H, device=dev, dtype=torch.float32)
+        nbytes = lib.aa_decoder_saved_bytes(ctypes.byref(d))
+        saved = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        ws = weights_struct(w)
+        with torch.cuda.device(dev):
+            check(lib.aa_decoder_forward(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(captions), _ptr(h0),
+                                         _ptr(c0), _ptr(scores), _ptr(alpha), _ptr(beta), _ptr(hT), _ptr(cT), _ptr(saved),
+                                         nbytes, _stream(dev)), "aa_decoder_forward")
+        ctx.dims = (B, T, k, H, E, Vc, a)
+        ctx.has_state = (h0 is not None, c0 is not None)
+        ctx.save_for_backward(V, v_g, captions, h0 if h0 is not None else V.new_empty(0),
+                              c0 if c0 is not None else V.new_empty(0), alpha, beta, saved, *w)
+        ctx.set_materialize_grads(False)
+        return scores, alpha, beta, hT, cT
+
+    @staticmethod
+    def backward(ctx, d_scores, d_alpha, d_beta, d_hT, d_cT):
+        lib = _lib.load()
+        V, v_g, captions, h0, c0, alpha, beta, saved = ctx.saved_tensors[:8]
+        w = ctx.saved_tensors[8:]
+        B, T, k, H, E, Vc, a = ctx.dims
+        h0 = h0 if ctx.has_state[0] else None
+        c0 = c0 if ctx.has_state[1] else None
+        dev = V.device
+        d = make_dims(B, T, k, H, E, Vc, a)
+        if d_scores is None:
+            d_scores = torch.zeros(B, T, Vc, device=dev, dtype=torch.float32)
+        d_scores, d_alpha, d_beta, d_hT, d_cT = (_f32c(x) for x in (d_scores, d_alpha, d_beta, d_hT, d_cT))
+        grads = [torch.empty_like(t) for t in w]
+        gs = AAWeightGrads()
+        for name, t in zip(WEIGHT_FIELDS, grads):
+            setattr(gs, name, t.data_ptr())
+        dV = torch.empty_like(V)
+        dvg = torch.empty_like(v_g)
+        dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if h0 is not None else None
+        dc0 = torch.empty(B, H, device=dev, dtype=torch.float32) if c0 is not None else None
+        sbytes = lib.aa_decoder_bwd_scratch_bytes(ctypes.byref(d))
+        scratch = torch.empty(sbytes, device=dev, dtype=torch.uint8)
+        ws = weights_struct(w)
+        with torch.cuda.device(dev):
+            check(lib.aa_decoder_backward(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(captions), _ptr(h0),
+                                          _ptr(c0), _ptr(alpha), _ptr(beta), _ptr(saved), saved.numel(), _ptr(d_scores),
+                                          _ptr(d_alpha), _ptr(d_beta), _ptr(d_hT), _ptr(d_cT), ctypes.byref(gs), _ptr(dV),
+                                          _ptr(dvg), _ptr(dh0), _ptr(dc0), _ptr(scratch), sbytes, _stream(dev)),
+                  "aa_decoder_backward")
+        return (dV, dvg, None, dh0, dc0) + tuple(grads)
+
+
+def decoder_forward(w: Sequence[torch.Tensor], V, v_g, captions, h0=None, c0=None):
+    """scores [B,T,Vc], alpha [B,T,k], beta [B,T,1], hT [B,H], cT [B,H] (differentiable)."""
+    _need_cuda(V, v_g, captions, h0, c0)
+    V, v_g = _f32c(V), _f32c(v_g)
+    B, _, H = V.shape
+    captions = captions.to(torch.int64).contiguous()
+    h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
+    return _DecoderFn.apply(V, v_g, captions, h0, c0, *w)
+
+
+class _PackRowsFn(torch.autograd.Function):
+    """``pack_padded_sequence(scores, lengths, batch_first=True).data`` (baseline_attention.py:228)."""
+
+    @staticmethod
+    def forward(ctx, scores, row_index):
+        lib = _lib.load()
+        B, T, Vc = scores.shape
+        n = row_index.numel()
+        out = torch.empty(n, Vc, device=scores.device, dtype=torch.float32)
+        with torch.cuda.device(scores.device):
+            check(lib.aa_pack_rows(_ptr(scores), Vc, _ptr(row_index), n, _ptr(out), _stream(scores.device)), "aa_pack_rows")
+        ctx.save_for_backward(row_index)
+        ctx.shape = (B, T, Vc)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        (row_index,) = ctx.saved_tensors
+        B, T, Vc = ctx.shape
+        d_out = _f32c(d_out)
+        d_scores = torch.empty(B, T, Vc, device=d_out.device, dtype=torch.float32)
+        with torch.cuda.device(d_out.device):
+            check(lib.aa_unpack_rows(_ptr(d_out), Vc, _ptr(row_index), row_index.numel(), B * T, _ptr(d_scores),
+                                     _stream(d_out.device)), "aa_unpack_rows")
+        return d_scores, None
+
+
+def packed_row_index(lengths: Sequence[int], T: int):
+    """Host logic of ``pack_padded_sequence``: time-major row order b*T+t and batch_sizes."""
+    lengths = [int(x) for x in lengths]
+    if any(lengths[i] < lengths[i + 1] for i in range(len(lengths) - 1)):
+        raise RuntimeError("`lengths` array must be sorted in decreasing order")   # torch's own error
+    if lengths and (lengths[-1] <= 0 or lengths[0] > T):
+        raise RuntimeError("lengths must be in [1, T]")
+    idx, bs = [], []
+    for t in range(lengths[0] if lengths else 0):
+        n = sum(1 for L in lengths if L > t)
+        bs.append(n)
+        idx.extend(b * T + t for b in range(n))
+    return idx, bs
+
+
+def pack_scores(scores: torch.Tensor, lengths: Sequence[int]):
+    idx, bs = packed_row_index(lengths, scores.shape[1])
+    row_index = torch.tensor(idx, dtype=torch.int64, device=scores.device)
+    data = _PackRowsFn.apply(scores, row_index)
+    return torch.nn.utils.rnn.PackedSequence(data, torch.tensor(bs, dtype=torch.int64))
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    """Mean CE over rows with the gradient produced in the same pass (train.py:63,208)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets):
+        lib = _lib.load()
+        n, Vc = logits.shape
+        loss = torch.empty((), device=logits.device, dtype=torch.float32)
+        dlog = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            check(lib.aa_cross_entropy(_ptr(logits), n, Vc, _ptr(targets), _ptr(loss), _ptr(dlog), _stream(logits.device)),
+                  "aa_cross_entropy")
+        ctx.save_for_backward(dlog)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlog,) = ctx.saved_tensors
+        return dlog * g, None
+
+
+def cross_entropy(logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    _need_cuda(logits, targets)
+    return _CrossEntropyFn.apply(_f32c(logits), targets.to(torch.int64).contiguous())
+
+
+@torch.no_grad()
+def greedy_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: int = 30, return_logits: bool = False):
+    """``Encoder2Decoder.sampler`` loop (adaptive_attention.py:186-216) on the device.
+    Returns ids [B,L] int64, attention [B,L,k], Beta [B,L,1] (+ logits [L,B,Vc])."""
+    lib = _lib.load()
+    _need_cuda(V, v_g, h0, c0)
+    V, v_g = _f32c(V), _f32c(v_g)
+    B, k, H = V.shape
+    E = v_g.shape[1]
+    Vc, a = w[0].shape[0], w[7].shape[0]
+    _check_weights(w, H, E, Vc, a)
+    h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
+    dev = V.device
+    d = make_dims(B, max_len, k, H, E, Vc, a)
+    ids = torch.empty(B, max_len, device=dev, dtype=torch.int64)
+    att = torch.empty(B, max_len, k, device=dev, dtype=torch.float32)
+    bet = torch.empty(B, max_len, 1, device=dev, dtype=torch.float32)
+    logits = torch.empty(max_len, B, Vc, device=dev, dtype=torch.float32) if return_logits else None
+    nbytes = lib.aa_decode_workspace_bytes(ctypes.byref(d), 0)
+    wsb = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    ws = weights_struct(w)
+    with torch.cuda.device(dev):
+        check(lib.aa_greedy_decode(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(h0), _ptr(c0), max_len,
+                                   _ptr(ids), _ptr(att), _ptr(bet), _ptr(logits), _ptr(wsb), nbytes, _stream(dev)),
+              "aa_greedy_decode")
+    return (ids, att, bet, logits) if return_logits else (ids, att, bet)
+
+
+@torch.no_grad()
+def beam_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, beam: int = 3, max_len: int = 20):
+    """Beam search (not in the reference; definition in oracle.beam_decode / SURVEY §8c).
+    Returns ids [B,L], attention [B,L,k], Beta [B,L,1], score [B] of the best hypothesis."""
+    lib = _lib.load()
+    _need_cuda(V, v_g, h0, c0)
+    V, v_g = _f32c(V), _f32c(v_g)
+    B, k, H = V.shape
+    E = v_g.shape[1]
+    Vc, a = w[0].shape[0], w[7].shape[0]
+    _check_weights(w, H, E, Vc, a)
+    h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
+    dev = V.device
+    d = make_dims(B, max_len, k, H, E, Vc, a)
+    ids = torch.empty(B, max_len, device=dev, dtype=torch.int64)
+    att = torch.empty(B, max_len, k, device=dev, dtype=torch.float32)
+    bet = torch.empty(B, max_len, 1, device=dev, dtype=torch.float32)
+    score = torch.empty(B, device=dev, dtype=torch.float32)
+    nbytes = lib.aa_decode_workspace_bytes(ctypes.byref(d), beam)
+    wsb = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    ws = weights_struct(w)
+    with torch.cuda.device(dev):
+        check(lib.aa_beam_decode(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(h0), _ptr(c0), beam, max_len,
+                                 _ptr(ids), _ptr(att), _ptr(bet), _ptr(score), _ptr(wsb), nbytes, _stream(dev)),
+              "aa_beam_decode")
+    return ids, att, bet, score
+
+
+# ---- sub-block operators (forward only; training goes through decoder_forward) -----------
+@torch.no_grad()
+def sentinel_forward(sen_wx, sen_wh, x_t, h_t_1, cell_t):
+    """``Sentinel.forward`` (adaptive_attention.py:75-85). x_t [B,T,2E]; h_t_1, cell_t [B,T,H]."""
+    lib = _lib.load()
+    _need_cuda(x_t, h_t_1, cell_t, sen_wx, sen_wh)
+    x_t, h_t_1, cell_t = _f32c(x_t), _f32c(h_t_1), _f32c(cell_t)
+    B, T, H = cell_t.shape
+    E = x_t.shape[2] // 2
+    d = make_dims(B, T, 1, H, E, 1)
+    gate = torch.empty_like(cell_t)
+    s = torch.empty_like(cell_t)
+    with torch.cuda.device(x_t.device):
+        check(lib.aa_sentinel_forward(ctypes.byref(d), _ptr(sen_wx), _ptr(sen_wh), _ptr(x_t), _ptr(h_t_1), _ptr(cell_t),
+                                      _ptr(gate), _ptr(s), _stream(x_t.device)), "aa_sentinel_forward")
+    return s
+
+
+@torch.no_grad()
+def atten_forward(att_wv, att_wg, att_ws, att_wh, V, h_t, s_t):
+    """``Atten.forward`` (adaptive_attention.py:26-58) -> c_hat [B,T,H], alpha [B,T,k], beta [B,T,1]."""
+    lib = _lib.load()
+    _need_cuda(V, h_t, s_t, att_wv)
+    V, h_t, s_t = _f32c(V), _f32c(h_t), _f32c(s_t)
+    B, k, H = V.shape
+    T = h_t.shape[1]
+    a = att_wv.shape[0]
+    d = make_dims(B, T, k, H, 4, 1, a)
+    dev = V.device
+    c_hat = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+    alpha = torch.empty(B, T, k, device=dev, dtype=torch.float32)
+    beta = torch.empty(B, T, 1, device=dev, dtype=torch.float32)
+    nbytes = lib.aa_atten_workspace_bytes(ctypes.byref(d))
+    wsb = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        check(lib.aa_atten_forward(ctypes.byref(d), _ptr(att_wv), _ptr(att_wg), _ptr(att_ws), _ptr(att_wh), _ptr(V),
+                                   _ptr(h_t), _ptr(s_t), _ptr(c_hat), _ptr(alpha), _ptr(beta), _ptr(wsb), nbytes,
+                                   _stream(dev)), "aa_atten_forward")
+    return c_hat, alpha, beta
+
+
+@torch.no_grad()
+def adaptive_forward(w: Sequence[torch.Tensor], x, hiddens, cells, V):
+    """``AdaptiveBlock.forward`` (adaptive_attention.py:110-134) -> scores, alpha, beta [B,T,1]."""
+    lib = _lib.load()
+    _need_cuda(x, hiddens, cells, V)
+    x, hiddens, cells, V = _f32c(x), _f32c(hiddens), _f32c(cells), _f32c(V)
+    B, k, H = V.shape
+    T = hiddens.shape[1]
+    E = x.shape[2] // 2
+    Vc, a = w[11].shape[0], w[7].shape[0]
+    d = make_dims(B, T, k, H, E, Vc, a)
+    dev = V.device
+    scores = torch.empty(B, T, Vc, device=dev, dtype=torch.float32)
+    alpha = torch.empty(B, T, k, device=dev, dtype=torch.float32)
+    beta = torch.empty(B, T, 1, device=dev, dtype=torch.float32)
+    nbytes = lib.aa_adaptive_workspace_bytes(ctypes.byref(d))
+    wsb = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    ws = weights_struct(w)
+    with torch.cuda.device(dev):
+        check(lib.aa_adaptive_forward(ctypes.byref(d), ctypes.byref(ws), _ptr(x), _ptr(hiddens), _ptr(cells), _ptr(V),
+                                      _ptr(scores), _ptr(alpha), _ptr(beta), _ptr(wsb), nbytes, _stream(dev)),
+              "aa_adaptive_forward")
+    return scores, alpha, beta

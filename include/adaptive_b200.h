@@ -1,0 +1,196 @@
+/* adaptive_b200.h — C ABI of libadaptive_sm100.so
+ *
+ * B200 (sm_100a) implementation of the caption-decoder hot path of wzn0828/Adaptive
+ * ("Knowing When to Look": LSTM step + visual sentinel + adaptive attention + vocabulary
+ * projection) for teacher-forced training (forward/backward) and greedy / beam decoding.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the PyTorch nn.Module
+ * surface.  Each entry point below names the reference code it
+ * replaces (paths relative to the reference checkout, file:line).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory,
+ *     including workspaces (sizes from the aa_*_bytes queries); nothing is allocated, freed
+ *     or retained by the library;
+ *   - all tensors are dense, row-major, contiguous, fp32 ("float") unless the name says bf16;
+ *     token ids are int64 ("long long");
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never
+ *     synchronises the device; it is safe to capture the calls into a CUDA graph;
+ *   - return value: 0 = ok, non-zero = error (AA_ERR_*); aa_last_error() returns a
+ *     thread-local message for the last failing call on the calling thread;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef ADAPTIVE_B200_H_
+#define ADAPTIVE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AA_OK 0
+#define AA_ERR_INVALID 1      /* bad argument (shape, null pointer, alignment) */
+#define AA_ERR_CUDA 2         /* a CUDA runtime call or kernel launch failed */
+#define AA_ERR_UNSUPPORTED 3  /* valid request the library has no kernel for */
+#define AA_ERR_WORKSPACE 4    /* workspace too small */
+
+/* Problem shape.  B images (rows), T teacher-forced steps, k regions per image, a = inner
+ * attention dim (49 in the reference regardless of k: adaptive_attention.py:16-19), H LSTM
+ * hidden size, E word-embedding size (LSTM input is 2E), Vc vocabulary size. */
+typedef struct aa_dims {
+  int32_t B, T, k, a, H, E, Vc;
+} aa_dims;
+
+/* Decoder parameters, named after the reference state_dict keys:
+ *   decoder.embed.weight [Vc,E]                              baseline_attention.py:137
+ *   decoder.LSTM.{weight_ih_l0 [4H,2E], weight_hh_l0 [4H,H], bias_ih_l0, bias_hh_l0 [4H]}  :140
+ *   decoder.adaptive.sentinel.{affine_x [H,2E], affine_h [H,H]}.weight   adaptive_attention.py:66-67
+ *   decoder.adaptive.atten.{affine_v, affine_g, affine_s [a,H], affine_h [1,a]}.weight      :16-19
+ *   decoder.adaptive.mlp.{weight [Vc,H], bias [Vc]}                                         :100   */
+typedef struct aa_weights {
+  const float* embed;
+  const float* w_ih;
+  const float* w_hh;
+  const float* b_ih;
+  const float* b_hh;
+  const float* sen_wx;
+  const float* sen_wh;
+  const float* att_wv;
+  const float* att_wg;
+  const float* att_ws;
+  const float* att_wh;
+  const float* mlp_w;
+  const float* mlp_b;
+} aa_weights;
+
+/* Gradients w.r.t. aa_weights, same shapes.  Every buffer is OVERWRITTEN (not accumulated). */
+typedef struct aa_weight_grads {
+  float* embed;
+  float* w_ih;
+  float* w_hh;
+  float* b_ih;
+  float* b_hh;
+  float* sen_wx;
+  float* sen_wh;
+  float* att_wv;
+  float* att_wg;
+  float* att_ws;
+  float* att_wh;
+  float* mlp_w;
+  float* mlp_b;
+} aa_weight_grads;
+
+/* ---- library ------------------------------------------------------------------------ */
+int aa_version(void);                 /* major*10000 + minor*100 + patch */
+const char* aa_last_error(void);      /* thread-local, never NULL */
+int aa_device_info(int* sm_count, int* cc_major, int* cc_minor);   /* host out-params */
+
+/* Instrumentation (host-side; no reference counterpart).  aa_launch_count: kernels launched by
+ * this library in this process so far.  aa_profile_*: when enabled, the major kernels are
+ * bracketed by cudaEvent pairs on their own stream; aa_profile_count() waits for the recorded
+ * events and returns the number of distinct kernel tags, aa_profile_get(i, ...) their totals. */
+long long aa_launch_count(void);
+int aa_profile_enable(int on);
+int aa_profile_reset(void);
+int aa_profile_count(void);
+int aa_profile_get(int i, char* name, int name_len, double* total_ms, int* launches);
+
+/* ---- stage operators (the nn.Module sub-blocks) ------------------------------------- */
+
+/* Generic fp32 contraction Y[M,N] = X[M,K] * W[N,K]^T (+ bias[N]) — nn.Linear as used at
+ * adaptive_attention.py:16-19,66-67,100.  ld* are row strides in elements. */
+int aa_linear_forward(int M, int N, int K, const float* X, int64_t ldx, const float* W, int64_t ldw,
+                      const float* bias, float* Y, int64_t ldy, void* stream);
+
+/* P = V * W_v^T, once per image (adaptive_attention.py:34, `affine_v(V)`).  V [B,k,H] -> P [B,k,a]. */
+int aa_precompute_P(const aa_dims* d, const float* V, const float* att_wv, float* P, void* stream);
+
+/* Sentinel.forward (adaptive_attention.py:75-85): s = sigmoid(x W_x^T + h_prev W_h^T) * tanh(cell).
+ * x [n,2E]; h_prev, cell [n,H] (h_prev may be NULL = zeros, the sampler case);
+ * gate_out [n,H] (optional, the sigmoid) ; s_out [n,H].  n = B*T rows. */
+int aa_sentinel_forward(const aa_dims* d, const float* sen_wx, const float* sen_wh, const float* x,
+                        const float* h_prev, const float* cell, float* gate_out, float* s_out, void* stream);
+
+/* Atten.forward (adaptive_attention.py:26-58): V [B,k,H], h_t, s_t [B,T,H] ->
+ * c_hat [B,T,H], alpha [B,T,k], beta [B,T].  workspace: aa_atten_workspace_bytes(d). */
+size_t aa_atten_workspace_bytes(const aa_dims* d);
+int aa_atten_forward(const aa_dims* d, const float* att_wv, const float* att_wg, const float* att_ws,
+                     const float* att_wh, const float* V, const float* h_t, const float* s_t, float* c_hat,
+                     float* alpha, float* beta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* AdaptiveBlock.forward (adaptive_attention.py:110-134): x [B,T,2E], hiddens, cells [B,T,H], V [B,k,H] ->
+ * scores [B,T,Vc], alpha [B,T,k], beta [B,T].  Applies the zero-h0 shift of :116-122 itself.
+ * workspace: aa_adaptive_workspace_bytes(d). */
+size_t aa_adaptive_workspace_bytes(const aa_dims* d);
+int aa_adaptive_forward(const aa_dims* d, const aa_weights* w, const float* x, const float* hiddens,
+                        const float* cells, const float* V, float* scores, float* alpha, float* beta,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- teacher-forced decoder: Decoder.forward / autograd backward -------------------- */
+
+/* Bytes of the `saved` blob written by aa_decoder_forward and read by aa_decoder_backward, and
+ * of the scratch blob aa_decoder_backward needs. */
+size_t aa_decoder_saved_bytes(const aa_dims* d);
+size_t aa_decoder_bwd_scratch_bytes(const aa_dims* d);
+
+/* Decoder.forward (baseline_attention.py:148-194 with the adaptive block of adaptive_attention.py:155).
+ *   V [B,k,H], v_g [B,E], captions [B,T] int64, h0/c0 [B,H] (NULL = zeros)
+ *   -> scores [B,T,Vc], alpha [B,T,k], beta [B,T], hT/cT [B,H].
+ * T == 1 is the sampler step (sentinel sees h~ = 0).  The `saved` blob
+ * (aa_decoder_saved_bytes) is always required: it doubles as the forward workspace. */
+int aa_decoder_forward(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g,
+                       const int64_t* captions, const float* h0, const float* c0, float* scores, float* alpha,
+                       float* beta, float* hT, float* cT, void* saved, size_t saved_bytes, void* stream);
+
+/* Gradient of  <d_scores,scores> + <d_alpha,alpha> + <d_beta,beta> + <d_hT,hT> + <d_cT,cT>
+ * (what autograd computes for the reference; formulas in SURVEY.md section 7).  d_alpha, d_beta,
+ * d_hT, d_cT may be NULL (= zero).  Outputs: all 13 parameter gradients (overwritten) and
+ * dV [B,k,H], dv_g [B,E], dh0, dc0 [B,H] (each may be NULL to skip).  d_scores is read-only. */
+int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g,
+                        const int64_t* captions, const float* h0, const float* c0, const float* alpha,
+                        const float* beta, const void* saved, size_t saved_bytes, const float* d_scores,
+                        const float* d_alpha, const float* d_beta, const float* d_hT, const float* d_cT,
+                        const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0, float* dc0,
+                        void* scratch, size_t scratch_bytes, void* stream);
+
+/* pack_padded_sequence(scores, lengths, batch_first=True).data (baseline_attention.py:228):
+ * gathers rows (b,t) with t < lengths[b] in time-major order.  row_index [n_rows] int64 holds
+ * b*T+t per packed row (host code builds it from `lengths`).  packed [n_rows,Vc]. */
+int aa_pack_rows(const float* scores, int64_t n_cols, const int64_t* row_index, int64_t n_rows, float* packed,
+                 void* stream);
+/* adjoint: d_scores[B*T, Vc] = 0 ; d_scores[row_index[r]] = d_packed[r] */
+int aa_unpack_rows(const float* d_packed, int64_t n_cols, const int64_t* row_index, int64_t n_rows, int64_t total_rows,
+                   float* d_scores, void* stream);
+
+/* Mean cross-entropy + gradient over rows (nn.CrossEntropyLoss at train.py:63,208; the step
+ * after the hot path).  loss: device scalar (overwritten); dlogits may be NULL. */
+int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, float* loss,
+                     float* dlogits, void* stream);
+
+/* ---- decoding: Encoder2Decoder.sampler -------------------------------------------- */
+
+/* Workspace for decoding d->B images for d->T (= max_len) steps: beam = 0 -> aa_greedy_decode,
+ * beam >= 1 -> aa_beam_decode with that width. */
+size_t aa_decode_workspace_bytes(const aa_dims* d, int beam);
+
+/* Greedy sampler loop (adaptive_attention.py:186-216) for B images, max_len steps, fully on the
+ * device: start id 1, arg-max of raw logits (lowest index wins ties), never stops early.
+ *   V [B,k,H], v_g [B,E], h0/c0 [B,H] -> ids [B,max_len] int64, attention [B,max_len,k],
+ *   Beta [B,max_len].  logits_out (optional, [max_len,B,Vc]) receives every step's scores. */
+int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const float* h0,
+                     const float* c0, int max_len, int64_t* ids, float* attention, float* Beta, float* logits_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Beam search (NOT in the reference; definition in SURVEY section 8c / oracle.beam_decode):
+ * returns the best hypothesis per image: ids [B,max_len], attention [B,max_len,k], Beta [B,max_len],
+ * score [B] (cumulative log-prob). */
+int aa_beam_decode(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const float* h0,
+                   const float* c0, int beam, int max_len, int64_t* ids, float* attention, float* Beta, float* score,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAPTIVE_B200_H_ */

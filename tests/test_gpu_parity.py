@@ -1,0 +1,273 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path, called through the C ABI,
+against the numpy oracle and the golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star): logits, alpha, beta and gradients within 1e-4 relative
+(max-abs error over max-abs value) on the fp32 path; greedy ids exact, near-ties logged."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from adaptive_b200 import functional as F_aa
+from adaptive_b200.synth import CFG_A, Dims, make_inputs, make_lengths, make_weights
+from oracle import adaptive_oracle as orc
+from tests.gpu_utils import dev_inputs, dev_weights, grad_key_order, near_tie_report
+from tests.helpers import GOLDEN_CASES, golden_setup, rel_err, upstream
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # fp32 path, stated by north_star
+NEAR_TIE = 1e-4     # top1-top2 logit gap below which an id flip is a logged near-tie, not a failure
+
+
+def _log_near_ties(name, near):
+    if near:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/near_ties.jsonl", "a") as f:
+            f.write(json.dumps({"test": name, "near_ties": near}) + "\n")
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_forward_backward_vs_golden(case):
+    g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
+    W = dev_weights(w, requires_grad=True)
+    V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+    scores, alpha, beta, hT, cT = F_aa.decoder_forward(W, V, v_g, cap, h0, c0)
+    tag = "f64"   # compare with the reference run in float64: the arbiter
+    sc = scores.detach().cpu().numpy()
+    if (tag + "_scores_sub") in g.files:
+        assert rel_err(sc[:, :, ::97], g[tag + "_scores_sub"]) < TOL
+        assert rel_err(sc.max(-1), g[tag + "_scores_max"]) < TOL
+    else:
+        assert rel_err(sc, g[tag + "_scores"]) < TOL
+    assert rel_err(alpha.detach().cpu().numpy(), g[tag + "_alpha"]) < TOL
+    assert rel_err(beta.detach().cpu().numpy(), g[tag + "_beta"]) < TOL
+    assert rel_err(hT.detach().cpu().numpy(), g[tag + "_hT"]) < TOL
+    assert rel_err(cT.detach().cpu().numpy(), g[tag + "_cT"]) < TOL
+
+    dS, dA, dB, dH, dC = upstream(sc.shape, tuple(alpha.shape), tuple(beta.shape), tuple(hT.shape), np.float32)
+    loss = ((scores * torch.from_numpy(dS).cuda()).sum() + (alpha * torch.from_numpy(dA).cuda()).sum()
+            + (beta * torch.from_numpy(dB).cuda()).sum() + (hT * torch.from_numpy(dH).cuda()).sum()
+            + (cT * torch.from_numpy(dC).cuda()).sum())
+    loss.backward()
+    for key, t in zip(grad_key_order(), W):
+        got = t.grad.cpu().numpy()
+        if (tag + "_grad_" + key) in g.files:
+            assert rel_err(got, g[tag + "_grad_" + key]) < TOL, key
+        else:
+            assert rel_err(got.reshape(-1)[::251], g[tag + "_grad_sub_" + key]) < TOL, key
+            nrm = np.sqrt((got.astype(np.float64) ** 2).sum())
+            assert abs(nrm - float(g[tag + "_grad_norm_" + key])) < TOL * nrm, key
+    for key, t in (("V", V), ("v_g", v_g), ("h0", h0), ("c0", c0)):
+        assert rel_err(t.grad.cpu().numpy(), g[tag + "_grad_" + key]) < TOL, key
+
+
+@pytest.mark.parametrize("B,T,dims", [(80, 18, CFG_A), (7, 1, Dims(H=64, E=32, Vc=333, k=49)),
+                                      (33, 6, Dims(H=128, E=64, Vc=1000, k=196))])
+def test_forward_backward_vs_oracle(B, T, dims):
+    """Sizes the reference fixtures do not cover (incl. BASELINE config 2's B=80) against the oracle in fp64."""
+    w = make_weights(dims, seed=5, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=6)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    i64 = {k: (v.astype(np.float64) if v.dtype != np.int64 else v) for k, v in inp.items()}
+    s_o, a_o, b_o, (h_o, c_o), cache = orc.decoder_forward(w64, i64["V"], i64["v_g"], i64["captions"], i64["h0"], i64["c0"],
+                                                           want_cache=True)
+    rng = np.random.Generator(np.random.PCG64(1))
+    dS = rng.standard_normal(s_o.shape) / s_o.shape[-1]
+    G = orc.decoder_backward(w64, cache, dS)
+    W = dev_weights(w, requires_grad=True)
+    V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+    scores, alpha, beta, hT, cT = F_aa.decoder_forward(W, V, v_g, cap, h0, c0)
+    assert rel_err(scores.detach().cpu().numpy(), s_o) < TOL
+    assert rel_err(alpha.detach().cpu().numpy(), a_o) < TOL
+    assert rel_err(beta.detach().cpu().numpy(), b_o) < TOL
+    (scores * torch.from_numpy(dS.astype(np.float32)).cuda()).sum().backward()
+    for key, t in zip(grad_key_order(), W):
+        assert rel_err(t.grad.cpu().numpy(), G[key]) < TOL, key
+    for key, t in (("V", V), ("v_g", v_g), ("h0", h0), ("c0", c0)):
+        assert rel_err(t.grad.cpu().numpy(), G[key]) < TOL, key
+
+
+def test_no_initial_state_and_state_layouts():
+    dims = Dims(H=64, E=32, Vc=200, k=49)
+    w = make_weights(dims, seed=2)
+    inp = make_inputs(dims, 4, 3, seed=3)
+    W = dev_weights(w)
+    V, v_g, h0, c0, cap = dev_inputs(inp)
+    z = np.zeros_like(inp["h0"])
+    ref = orc.decoder_forward(w, inp["V"], inp["v_g"], inp["captions"], z, z)[0]
+    got = F_aa.decoder_forward(W, V, v_g, cap, None, None)[0]
+    assert rel_err(got.cpu().numpy(), ref) < TOL
+    a = F_aa.decoder_forward(W, V, v_g, cap, h0[None], c0[None])[0]          # [1,B,H]
+    b = F_aa.decoder_forward(W, V, v_g, cap, h0[:, None], c0[:, None])[0]    # [B,1,H] (reference encoder layout, Q9)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_greedy_vs_golden(case):
+    g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
+    W = dev_weights(w)
+    V, v_g, h0, c0, cap = dev_inputs(inp)
+    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L)
+    ids, att, bet = ids.cpu().numpy(), att.cpu().numpy(), bet.cpu().numpy()
+    ref_ids, gap = g["f64_greedy_ids"], g["f64_greedy_gap"]
+    hard, near = near_tie_report(ids, ref_ids, gap, NEAR_TIE)
+    _log_near_ties("greedy_vs_golden[%s]" % case, near)
+    assert not hard, hard
+    same = (ids == ref_ids).all(1)
+    assert same.any()
+    assert rel_err(att[same], g["f64_greedy_alpha"][same]) < TOL
+    assert rel_err(bet[same], g["f64_greedy_beta"][same]) < TOL
+    # attention arg-max exact wherever the ids agree (north_star)
+    assert np.array_equal(att[same].argmax(-1), g["f64_greedy_alpha"][same].argmax(-1))
+
+
+def test_greedy_vs_oracle_batch256():
+    dims, B, L = CFG_A, 256, 20
+    w = make_weights(dims, seed=123)
+    inp = make_inputs(dims, B, 1, seed=1234)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    i64 = {k: (v.astype(np.float64) if v.dtype != np.int64 else v) for k, v in inp.items()}
+    ref_ids, ref_att, ref_bet, ref_sc = orc.greedy_decode(w64, i64["V"], i64["v_g"], i64["h0"], i64["c0"], L, want_scores=True)
+    top2 = np.sort(ref_sc, axis=-1)[..., -2:]
+    gap = top2[..., 1] - top2[..., 0]
+    W = dev_weights(w)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L)
+    ids = ids.cpu().numpy()
+    hard, near = near_tie_report(ids, ref_ids, gap, NEAR_TIE)
+    _log_near_ties("greedy_vs_oracle_batch256", near)
+    assert not hard, hard
+    same = (ids == ref_ids).all(1)
+    assert same.mean() > 0.95
+    assert rel_err(att.cpu().numpy()[same], ref_att[same]) < TOL
+    assert np.array_equal(att.cpu().numpy()[same].argmax(-1), ref_att[same].argmax(-1))
+
+
+def test_greedy_step_logits_match_decoder_step():
+    """The fused decode step must equal Decoder.forward with seq-len 1 (Q3) fed with the same tokens."""
+    dims, B, L = Dims(H=128, E=64, Vc=500, k=49), 9, 4
+    w = make_weights(dims, seed=8, bias_scale=0.1)
+    inp = make_inputs(dims, B, 1, seed=9)
+    W = dev_weights(w)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+    ids, att, bet, logits = F_aa.greedy_decode(W, V, v_g, h0, c0, L, return_logits=True)
+    tok = torch.ones(B, 1, dtype=torch.int64, device="cuda")
+    h, c = h0, c0
+    for t in range(L):
+        s1, a1, b1, h, c = F_aa.decoder_forward(W, V, v_g, tok, h, c)
+        assert rel_err(logits[t].cpu().numpy(), s1[:, 0].cpu().numpy()) < 1e-5
+        assert rel_err(att[:, t].cpu().numpy(), a1[:, 0].cpu().numpy()) < 1e-5
+        tok = ids[:, t:t + 1]
+
+
+@pytest.mark.parametrize("beam", [1, 3])
+def test_beam_vs_oracle(beam):
+    dims, B, L = Dims(H=64, E=32, Vc=300, k=49), 6, 8
+    w = make_weights(dims, seed=11, bias_scale=0.2)
+    w["adaptive.mlp.bias"][orc.END_ID] += 3.0      # make <end> likely so that frozen beams are exercised
+    inp = make_inputs(dims, B, 1, seed=12)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    i64 = {k: (v.astype(np.float64) if v.dtype != np.int64 else v) for k, v in inp.items()}
+    r_ids, r_att, r_bet, r_sc = orc.beam_decode(w64, i64["V"], i64["v_g"], i64["h0"], i64["c0"], beam, L)
+    W = dev_weights(w)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+    ids, att, bet, sc = F_aa.beam_decode(W, V, v_g, h0, c0, beam, L)
+    assert (r_ids == orc.END_ID).any()
+    assert np.array_equal(ids.cpu().numpy(), r_ids)
+    assert rel_err(sc.cpu().numpy(), r_sc) < TOL
+    assert rel_err(att.cpu().numpy(), r_att) < TOL
+    assert rel_err(bet.cpu().numpy(), r_bet) < TOL
+
+
+def test_pack_and_cross_entropy_vs_golden():
+    for case in ("tiny", "odd"):
+        g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
+        W = dev_weights(w, requires_grad=True)
+        V, v_g, h0, c0, cap = dev_inputs(inp)
+        lengths = [int(x) for x in g["lengths"]]
+        scores = F_aa.decoder_forward(W, V, v_g, cap, h0, c0)[0]
+        packed = F_aa.pack_scores(scores, lengths)
+        assert np.array_equal(packed.batch_sizes.numpy(), g["f64_packed_batch_sizes"])
+        assert rel_err(packed.data.detach().cpu().numpy(), g["f64_packed_data_sub"]) < TOL
+        tgt = torch.from_numpy(g["packed_targets"]).cuda()
+        loss = F_aa.cross_entropy(packed.data, tgt)
+        assert abs(loss.item() - float(g["f64_ce_loss"])) < 1e-4 * abs(float(g["f64_ce_loss"]))
+        loss.backward()
+        # gradient of the whole train step against the oracle
+        w64 = {k: v.astype(np.float64) for k, v in w.items()}
+        i64 = {k: (v.astype(np.float64) if v.dtype != np.int64 else v) for k, v in inp.items()}
+        s_o, _, _, _, cache = orc.decoder_forward(w64, i64["V"], i64["v_g"], i64["captions"], i64["h0"], i64["c0"], want_cache=True)
+        data, _ = orc.pack_padded(s_o, lengths)
+        _, dlog = orc.cross_entropy(data, g["packed_targets"])
+        idx, _ = F_aa.packed_row_index(lengths, T)
+        dS = np.zeros((B * T, dims.Vc))
+        dS[idx] = dlog
+        G = orc.decoder_backward(w64, cache, dS.reshape(B, T, dims.Vc))
+        for key, t in zip(grad_key_order(), W):
+            assert rel_err(t.grad.cpu().numpy(), G[key]) < TOL, key
+
+
+def test_stage_operators_vs_oracle():
+    dims, B, T = Dims(H=64, E=32, Vc=150, k=49), 5, 4
+    w = make_weights(dims, seed=21)
+    inp = make_inputs(dims, B, T, seed=22)
+    rng = np.random.Generator(np.random.PCG64(3))
+    x = rng.standard_normal((B, T, 2 * dims.E)).astype(np.float32)
+    hid = np.tanh(rng.standard_normal((B, T, dims.H))).astype(np.float32)
+    cel = rng.standard_normal((B, T, dims.H)).astype(np.float32)
+    hprev = np.tanh(rng.standard_normal((B, T, dims.H))).astype(np.float32)
+    W = dev_weights(w)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    s_ref, _ = orc.sentinel_forward(w, x, hprev, cel)
+    s = F_aa.sentinel_forward(W[5], W[6], cu(x), cu(hprev), cu(cel))
+    assert rel_err(s.cpu().numpy(), s_ref) < TOL
+    ch_ref, a_ref, b_ref, _ = orc.atten_forward(w, inp["V"], hid, s_ref)
+    ch, al, be = F_aa.atten_forward(W[7], W[8], W[9], W[10], cu(inp["V"]), cu(hid), cu(s_ref))
+    assert rel_err(ch.cpu().numpy(), ch_ref) < TOL and rel_err(al.cpu().numpy(), a_ref) < TOL and rel_err(be.cpu().numpy(), b_ref) < TOL
+    sc_ref, a2, b2, _ = orc.adaptive_forward(w, x, hid, cel, inp["V"])
+    sc, al2, be2 = F_aa.adaptive_forward(W, cu(x), cu(hid), cu(cel), cu(inp["V"]))
+    assert rel_err(sc.cpu().numpy(), sc_ref) < TOL and rel_err(al2.cpu().numpy(), a2) < TOL and rel_err(be2.cpu().numpy(), b2) < TOL
+
+
+def test_full_size_decode_properties():
+    """BASELINE config 3 size (B=4096, max_len 20): size-independent properties."""
+    dims, B, L = CFG_A, 4096, 20
+    w = make_weights(dims, seed=123)
+    inp = make_inputs(dims, B, 1, seed=1234)
+    W = dev_weights(w)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L)
+    assert ids.shape == (B, L) and int(ids.min()) >= 0 and int(ids.max()) < dims.Vc
+    assert torch.allclose(att.sum(-1), torch.ones(B, L, device="cuda"), atol=1e-5)      # k-way alpha sums to 1 (Q5)
+    assert float(bet.min()) > 0 and float(bet.max()) < 1
+    ids2, att2, bet2 = F_aa.greedy_decode(W, V, v_g, h0, c0, L)                           # deterministic
+    assert torch.equal(ids, ids2) and torch.equal(att, att2) and torch.equal(bet, bet2)
+    # images are independent: decoding a shard gives bit-identical rows (what multi-GPU sharding relies on)
+    s = slice(1000, 1512)
+    ids3, att3, _ = F_aa.greedy_decode(W, V[s].contiguous(), v_g[s].contiguous(), h0[s].contiguous(), c0[s].contiguous(), L)
+    assert torch.equal(ids3, ids[s]) and torch.equal(att3, att[s])
+    # spot-check 64 rows against the fp64 oracle
+    pick = np.arange(0, B, 64)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    r_ids, r_att, _, r_sc = orc.greedy_decode(w64, inp["V"][pick].astype(np.float64), inp["v_g"][pick].astype(np.float64),
+                                              inp["h0"][pick].astype(np.float64), inp["c0"][pick].astype(np.float64), L, want_scores=True)
+    top2 = np.sort(r_sc, axis=-1)[..., -2:]
+    hard, near = near_tie_report(ids.cpu().numpy()[pick], r_ids, top2[..., 1] - top2[..., 0], NEAR_TIE)
+    _log_near_ties("full_size_decode", near)
+    assert not hard, hard
+
+
+def test_errors_are_loud():
+    dims = Dims(H=64, E=32, Vc=100, k=49)
+    w = make_weights(dims, seed=1)
+    W = dev_weights(w)
+    inp = make_inputs(dims, 2, 2, seed=1)
+    V, v_g, h0, c0, cap = dev_inputs(inp)
+    with pytest.raises(RuntimeError):
+        F_aa.decoder_forward(W, V.cpu(), v_g, cap, h0, c0)          # no CPU path
+    with pytest.raises(ValueError):
+        F_aa.decoder_forward(W[:-1] + (W[-1][:-1],), V, v_g, cap, h0, c0)   # wrong bias shape
+    with pytest.raises(RuntimeError):
+        F_aa.pack_scores(torch.zeros(2, 2, 100, device="cuda"), [1, 2])     # unsorted lengths, torch's own error

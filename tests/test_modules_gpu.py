@@ -1,0 +1,67 @@
+"""nn.Module drop-in surface on the GPU: Encoder2Decoder.forward / .sampler against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import adaptive_b200
+from adaptive_b200.synth import Dims, make_inputs, make_lengths, make_weights
+from oracle import adaptive_oracle as orc
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class Cf:
+    adaptive_word_embed_size = 32
+    adaptive_lstm_hidden_size = 64
+    vocab_length = 120
+
+
+def _model_with(w):
+    m = adaptive_b200.Encoder2Decoder(Cf()).cuda()
+    sd = {"decoder." + k: torch.from_numpy(v) for k, v in w.items()}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing)
+    return m
+
+
+def test_e2d_forward_backward_and_sampler():
+    dims = Dims(H=64, E=32, Vc=120, k=49)
+    B, T = 6, 7
+    w = make_weights(dims, seed=31, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=32)
+    m = _model_with(w)
+    V = torch.from_numpy(inp["V"]).cuda()
+    v_g = torch.from_numpy(inp["v_g"]).cuda()
+    states = (torch.from_numpy(inp["h0"]).cuda()[:, None], torch.from_numpy(inp["c0"]).cuda()[:, None])   # [B,1,H] like the encoder
+    cap = torch.from_numpy(inp["captions"]).cuda()
+    lengths = make_lengths(B, T, seed=5)
+    packed = m((V, v_g, states), cap, lengths)
+    data_ref, bs_ref = orc.e2d_forward(w, inp["V"], inp["v_g"], inp["captions"], lengths, inp["h0"], inp["c0"])
+    assert np.array_equal(packed.batch_sizes.numpy(), bs_ref)
+    assert rel_err(packed.data.detach().cpu().numpy(), data_ref) < 1e-4
+    tgt = torch.from_numpy(orc.packed_targets(inp["captions"], lengths)).cuda()
+    loss = torch.nn.CrossEntropyLoss()(packed.data, tgt)      # the caller's own loss (train.py:63,208)
+    loss.backward()
+    total_norm = torch.nn.utils.clip_grad_norm_(m.decoder.LSTM.parameters(), 5.0)   # train.py:214
+    assert torch.isfinite(total_norm)
+    assert all(p.grad is not None for p in m.decoder.parameters())
+    ids, att, Beta = m.sampler((V, v_g, states), max_len=5)
+    r_ids, r_att, r_bet = orc.greedy_decode(w, inp["V"], inp["v_g"], inp["h0"], inp["c0"], 5)
+    assert ids.shape == (B, 5) and att.shape == (B, 5, 49) and Beta.shape == (B, 5, 1)
+    assert np.array_equal(ids.cpu().numpy(), r_ids)
+    assert rel_err(att.cpu().numpy(), r_att) < 1e-4 and rel_err(Beta.cpu().numpy(), r_bet) < 1e-4
+
+
+def test_feature_map_entry_and_decoder_states():
+    m = adaptive_b200.Encoder2Decoder(Cf()).cuda()
+    feats = torch.relu(torch.randn(3, 2048, 7, 7, device="cuda"))
+    cap = torch.randint(4, 120, (3, 4), device="cuda")
+    cap[:, 0] = 1
+    out = m(feats, cap, [3, 3, 2])
+    assert out.data.shape == (8, 120)
+    ids, att, Beta = m.sampler(feats, max_len=3)
+    assert ids.shape == (3, 3)
+    V, v_g, states = m.encoder(feats)
+    s, a, b, (hn, cn) = m.decoder(V, v_g, cap, states)
+    assert s.shape == (3, 4, 120) and b.shape == (3, 4, 1) and hn.shape == (1, 3, 64) and cn.shape == (1, 3, 64)
