@@ -203,6 +203,13 @@ def packed_row_index(lengths: Sequence[int], T: int):
     return idx, bs
 
 
+def packed_targets(captions, lengths: Sequence[int]):
+    """``pack_padded_sequence(captions[:, 1:], lengths, batch_first=True).data`` (train.py:102);
+    works on numpy arrays and torch tensors."""
+    idx, _ = packed_row_index(lengths, captions.shape[1] - 1)
+    return captions[:, 1:].reshape(-1)[idx]
+
+
 def pack_scores(scores: torch.Tensor, lengths: Sequence[int]):
     idx, bs = packed_row_index(lengths, scores.shape[1])
     row_index = torch.tensor(idx, dtype=torch.int64, device=scores.device)

@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the adaptive-attention decoder hot path (BASELINE.json metric:
+decoder tokens/sec, teacher-forced train fwd+bwd and greedy decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Headline workload (N=1): BASELINE config 2 — one training step (forward through
+``Encoder2Decoder.forward`` -> packed scores -> mean cross-entropy -> backward) at batch 80,
+49 regions, hidden 512, vocab 10k, caption length 18, synthetic features and random-init
+weights.  BASELINE config 3 (greedy sampler, batch 4096, max_len 20) is measured in the same
+run and reported under ``"decode"``.  With N > 1 (torchrun) every rank keeps the same
+per-GPU batch (weak scaling); training adds an NCCL all-reduce of the decoder gradients,
+decoding shards images with no communication.
+
+``--impl reference`` times the oracle port of the reference's CPU path (numpy, all host
+threads) on the same workload, on rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from adaptive_b200.synth import CFG_A, make_inputs, make_lengths, make_weights  # noqa: E402
+
+TRAIN_B, TRAIN_T = 80, 18          # BASELINE config 2
+DECODE_B, DECODE_L = 4096, 20      # BASELINE config 3
+METRIC = "decoder tokens/sec (train fwd+bwd)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (numpy, multi-threaded BLAS)
+# ---------------------------------------------------------------------------------------------
+def oracle_train_step_fn(B, T, dims):
+    from adaptive_b200.functional import packed_row_index
+    from oracle import adaptive_oracle as orc
+
+    w = make_weights(dims, seed=123)
+    inp = make_inputs(dims, B, T, seed=1234)
+    lengths = make_lengths(B, T, seed=1234)
+    idx, _ = packed_row_index(lengths, T)
+    tgt = orc.packed_targets(inp["captions"], lengths)
+
+    def step():
+        s, _, _, _, cache = orc.decoder_forward(w, inp["V"], inp["v_g"], inp["captions"], inp["h0"], inp["c0"], want_cache=True)
+        data, _ = orc.pack_padded(s, lengths)
+        loss, dlog = orc.cross_entropy(data, tgt)
+        dS = np.zeros((B * T, dims.Vc), dtype=np.float32)
+        dS[idx] = dlog
+        orc.decoder_backward(w, cache, dS.reshape(B, T, dims.Vc))
+        return float(loss)
+
+    return step
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    step = oracle_train_step_fn(TRAIN_B, TRAIN_T, CFG_A)
+    steps = max(1, min(args.steps, 40))
+    sec = time_cpu(step, steps, max(1, min(args.warmup, 3)))
+    v = TRAIN_B * TRAIN_T / sec
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                         "sample": "%d full steps of the same workload (B=%d, T=%d) on the numpy oracle port" % (steps, TRAIN_B, TRAIN_T)},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config(n):
+    return {"workload": "BASELINE config 2: train step fwd+CE+bwd, batch %d per GPU, 49 regions, hidden 512, embed 256, vocab 10000, "
+                        "caption len 18 (variable lengths, mean 10.5 words)" % TRAIN_B,
+            "global_batch": TRAIN_B * n, "seq_len": TRAIN_T, "parallelism": "dp%d" % n,
+            "l2": "per-step working set (weights+grads 83 MB, logits+dlogits ~110 MB, saved activations ~56 MB) exceeds the 126 MB L2; "
+                  "4 rotating input batches"}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def kernel_models(dims, B, T, decode_B):
+    """Algorithmic work per launch of each profiled kernel tag (DESIGN.md section 'Kernels')."""
+    H, E, k, a, Vc = dims.H, dims.E, dims.k, dims.a, dims.Vc
+    N = B * T
+    fl = lambda m, n, kk: 2.0 * m * n * kk
+    step_bytes = (5 * H + H) * 4 + k * H * 4 + k * a * 4 + (2 * H + H) * 4 + k * 4 + 4      # 128 588 B at cfgA
+    return {
+        "gemm_vocab_fwd": ("tensor", fl(N, Vc, H)), "gemm_vocab_dx": ("tensor", fl(N, H, Vc)), "gemm_vocab_dw": ("tensor", fl(Vc, H, N)),
+        "lstm_rec_gemm": ("tensor", fl(B, 4 * H, H)), "bptt_rec_gemm": ("tensor", fl(B, H, 4 * H)),
+        "dec_vocab_gemm": ("tensor", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tensor", fl(decode_B, 5 * H, E + H)),
+        "dec_step_fused": ("hbm", float(step_bytes) * decode_B),
+        "dec_argmax": ("hbm", float(decode_B) * Vc * 4),
+        # training attention, per launch over the whole batch: V + P + per-step rows in, u/ctx/alpha/beta out
+        "atten_fwd": ("hbm", float(B) * (k * H * 4 + k * a * 4 + T * (2 * a + 2 * H + 2 * H + k + 1) * 4)),
+        "atten_bwd": ("hbm", float(B) * (2 * k * H * 4 + 2 * k * a * 4 + T * (2 * a + 3 * H + H + k + 1 + 2 * a) * 4)),
+    }
+
+
+def rooflines(report, models, peaks):
+    out = {}
+    for tag, (ms, n) in report.items():
+        if tag not in models or n == 0 or ms <= 0:
+            out[tag] = {"ms_total": ms, "launches": n}
+            continue
+        bound, work = models[tag]
+        per = ms / n * 1e-3
+        if bound == "hbm":
+            ach, peak, unit = work / per / 1e9, peaks["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = work / per / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+        out[tag] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+                    "ms_total": ms, "launches": n, "us_per_launch": per * 1e6}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import adaptive_b200
+    from adaptive_b200 import _lib
+    from adaptive_b200 import functional as F_aa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    peaks = load_peaks()
+    dims = CFG_A
+
+    class Cf:
+        adaptive_word_embed_size, adaptive_lstm_hidden_size, vocab_length = dims.E, dims.H, dims.Vc
+
+    model = adaptive_b200.Encoder2Decoder(Cf()).to(dev)
+    w = make_weights(dims, seed=123)
+    model.load_state_dict({"decoder." + k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    params = [p for p in model.decoder.parameters()]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- training workload (headline) ----------------
+    NB = 4
+    host, devb = [], []
+    lengths = make_lengths(TRAIN_B, TRAIN_T, seed=1234)
+    for i in range(NB):
+        inp = make_inputs(dims, TRAIN_B, TRAIN_T, seed=1234 + 97 * rank + i)
+        tgt = np.ascontiguousarray(F_aa.packed_targets(inp["captions"], lengths))
+        hb = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items()}
+        hb["tgt"] = torch.from_numpy(tgt).pin_memory()
+        host.append(hb)
+        devb.append({k: v.to(dev) for k, v in hb.items()})
+    h2d_train = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        # backward-ready order: mlp first (half of the bytes), embed last; one flat bucket each
+        for p in reversed(params):
+            dist.all_reduce(p.grad)
+        for p in params:
+            p.grad.div_(world)
+
+    def train_step(b):
+        for p in params:
+            p.grad = None
+        states = (b["h0"], b["c0"])
+        packed = model((b["V"], b["v_g"], states), b["captions"], lengths)
+        loss = F_aa.cross_entropy(packed.data, b["tgt"])
+        loss.backward()
+        allreduce_grads()
+        return loss
+
+    for i in range(args.warmup):
+        train_step(devb[i % NB])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        train_step(devb[i % NB])
+    e1.record()
+    barrier()
+    train_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    train_tok = TRAIN_B * TRAIN_T * n_gpus / (train_ms * 1e-3)
+
+    # e2e: pinned host -> device copies and the loss read-back inside the timed region
+    def train_step_e2e(hb):
+        b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        return float(train_step(b).item())
+
+    for i in range(min(3, args.warmup)):
+        train_step_e2e(host[i % NB])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        train_step_e2e(host[i % NB])
+    torch.cuda.synchronize()
+    e2e_train_s = max_over_ranks((time.perf_counter() - t0)) / args.steps
+    barrier()
+
+    # per-kernel timing pass (CUDA events around the kernels, same steps; not used for `value`)
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    for i in range(args.steps):
+        train_step(devb[i % NB])
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    train_report = _lib.profile_report()
+    _lib.profile_reset()
+
+    # ---------------- decode workload (BASELINE config 3) ----------------
+    dsteps = max(2, min(args.steps, 5))
+    dinp = make_inputs(dims, DECODE_B, 1, seed=4321 + rank)
+    dhost = {k: torch.from_numpy(dinp[k]).pin_memory() for k in ("V", "v_g", "h0", "c0")}
+    ddev = {k: v.to(dev) for k, v in dhost.items()}
+    h2d_dec = sum(v.numel() * v.element_size() for v in dhost.values())
+
+    def decode_step(b):
+        return model.sampler((b["V"], b["v_g"], (b["h0"], b["c0"])), max_len=DECODE_L)
+
+    for _ in range(2):
+        decode_step(ddev)
+    barrier()
+    l0d = _lib.launch_count()
+    e0.record()
+    for _ in range(dsteps):
+        decode_step(ddev)
+    e1.record()
+    barrier()
+    dec_ms = max_over_ranks(e0.elapsed_time(e1)) / dsteps
+    dec_launches = _lib.launch_count() - l0d
+    dec_tok = DECODE_B * DECODE_L * n_gpus / (dec_ms * 1e-3)
+    t0 = time.perf_counter()
+    for _ in range(dsteps):
+        b = {k: v.to(dev, non_blocking=True) for k, v in dhost.items()}
+        ids = decode_step(b)[0].cpu()
+    torch.cuda.synchronize()
+    e2e_dec_s = max_over_ranks(time.perf_counter() - t0) / dsteps
+    d2h_dec = ids.numel() * ids.element_size()
+    barrier()
+    _lib.profile_enable(True)
+    for _ in range(dsteps):
+        decode_step(ddev)
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    dec_report = _lib.profile_report()
+    _lib.profile_reset()
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    models = kernel_models(dims, TRAIN_B, TRAIN_T, DECODE_B)
+    k_train = rooflines(train_report, models, peaks)
+    k_dec = rooflines(dec_report, models, peaks)
+    dom = max((t for t in k_train if "frac" in k_train[t]), key=lambda t: k_train[t]["ms_total"])
+    roof = {kk: k_train[dom][kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+    roof["kernel"] = dom
+    roof["peak_source"] = peaks["source"]
+    roof["share_of_step"] = k_train[dom]["ms_total"] / max(sum(v["ms_total"] for v in k_train.values()), 1e-9)
+
+    out = {
+        "metric": METRIC, "value": train_tok, "unit": "tokens/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": train_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n_gpus),
+        "clocks": clocks,
+        "e2e": {"value": TRAIN_B * TRAIN_T * n_gpus / e2e_train_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d_train,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_train_s * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "kernels": {"train": k_train, "decode": k_dec},
+        "decode": {"workload": "BASELINE config 3: greedy sampler, batch %d per GPU, max_len %d, fp32; V (411 MB) > L2" % (DECODE_B, DECODE_L),
+                   "value": dec_tok, "unit": "tokens/s", "ms_per_step": dec_ms, "steps": dsteps, "gpu_launches": int(dec_launches),
+                   "e2e": {"value": DECODE_B * DECODE_L * n_gpus / e2e_dec_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d_dec,
+                           "d2h_bytes_per_step": d2h_dec, "ms_per_step": e2e_dec_s * 1e3},
+                   "roofline_fused_step": k_dec.get("dec_step_fused")},
+    }
+    if n_gpus == 1:
+        cores = os.cpu_count() or 1
+        step = oracle_train_step_fn(TRAIN_B, TRAIN_T, dims)
+        ncpu = 20
+        sec = time_cpu(step, ncpu, 2)
+        out["cpu_baseline"] = {"value": TRAIN_B * TRAIN_T / sec, "unit": "tokens/s", "cores": cores, "kind": "port",
+                               "sample": "%d full steps of the same workload (B=%d, T=%d) on the numpy oracle port, %.1f s" %
+                                         (ncpu, TRAIN_B, TRAIN_T, sec * ncpu)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
