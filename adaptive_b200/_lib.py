@@ -16,7 +16,10 @@ P = c_void_p  # every device pointer travels as void*
 
 
 class AADims(Structure):
-    _fields_ = [(n, c_int32) for n in ("B", "T", "k", "a", "H", "E", "Vc")]
+    _fields_ = [(n, c_int32) for n in ("B", "T", "k", "a", "H", "E", "Vc", "precision")]
+
+
+PREC_FP32, PREC_BF16 = 0, 1
 
 
 WEIGHT_FIELDS = ("embed", "w_ih", "w_hh", "b_ih", "b_hh", "sen_wx", "sen_wh",
@@ -60,6 +63,8 @@ SIGNATURES = {
     "aa_profile_count": (c_int, []),
     "aa_profile_get": (c_int, [c_int, ctypes.c_char_p, c_int, POINTER(ctypes.c_double), POINTER(c_int)]),
     "aa_linear_forward": (c_int, [c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
+    "aa_gemm": (c_int, [c_int, c_int, c_int, c_int, P, c_int64, c_int, P, c_int64, c_int, P, c_int64, ctypes.c_float, P, P,
+                        c_int64, P]),
     "aa_precompute_P": (c_int, [_D, P, P, P, P]),
     "aa_sentinel_forward": (c_int, [_D, P, P, P, P, P, P, P, P]),
     "aa_atten_workspace_bytes": (c_size_t, [_D]),

@@ -106,6 +106,13 @@ __global__ void __launch_bounds__(AT_THREADS) atten_fwd_kernel(const AttenFwdArg
       if (p.ctx) *reinterpret_cast<float4*>(p.ctx + row * H + c) = acc;
       if (p.c_hat) *reinterpret_cast<float4*>(p.c_hat + row * H + c) = ch;
       if (p.u) *reinterpret_cast<float4*>(p.u + row * H + c) = make_float4(ch.x + hv.x, ch.y + hv.y, ch.z + hv.z, ch.w + hv.w);
+      if (p.u16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(ch.x + hv.x, ch.y + hv.y), hi = __floats2bfloat162_rn(ch.z + hv.z, ch.w + hv.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p.u16 + row * H + c) = pk;
+      }
     }
     __syncthreads();
   }
@@ -234,6 +241,10 @@ __global__ void __launch_bounds__(AT_THREADS) atten_bwd_kernel(const AttenBwdArg
         dwh_sent = fmaf(dzs, tr, dwh_sent);
         p.dr[row * a + j] = drj;
         p.dq[row * a + j] = dq + drj;
+        if (p.dq16) {
+          p.dr16[row * p.a_pad + j] = __float2bfloat16(drj);
+          p.dq16[row * p.a_pad + j] = __float2bfloat16(dq + drj);
+        }
       }
       __syncthreads();
     }
@@ -268,7 +279,10 @@ __global__ void __launch_bounds__(AT_THREADS) atten_bwd_kernel(const AttenBwdArg
   float* dPb = p.dP + (long long)b * k * a;
   for (int i = tid; i < k * a; i += AT_THREADS) {
     if (atomic_out) atomicAdd(dPb + i, dPs[i]);
-    else dPb[i] = dPs[i];
+    else {
+      dPb[i] = dPs[i];
+      if (p.dP16) p.dP16[((long long)b * k + i / a) * p.a_pad + (i % a)] = __float2bfloat16(dPs[i]);
+    }
   }
   // dw_h: reduce the per-warp partials, add the sentinel rows, one atomic per column
 #pragma unroll

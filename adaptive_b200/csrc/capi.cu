@@ -92,15 +92,32 @@ struct Carver {
   }
 };
 
+typedef __nv_bfloat16 bf16;
+
+struct Carver16 {   // carve helper for bf16 arrays sharing the same blob
+  Carver& c;
+  bf16* take(size_t n) { return reinterpret_cast<bf16*>(c.take((n + 1) / 2)); }
+};
+
+inline int a_pad_of(const aa_dims& d) { return (d.a + 7) / 8 * 8; }   // bf16 rows need 16-byte strides for TMA
+
+// bf16 copies of the GEMM weights (mixed-precision mode)
+struct W16 {
+  bf16 *w_ih, *w_hh, *sen_wx, *sen_wh, *att_wv, *att_wg, *att_ws, *mlp_w;
+};
+
 struct Saved {
   float *x, *xg, *acts, *cells, *hiddens, *hs_prev, *g, *s, *P, *q, *r, *ctx, *u, *zeros;
+  // bf16 mirrors (only carved when d.precision == AA_PREC_BF16)
+  bf16 *x16, *hid16, *hsprev16, *s16, *V16, *u16, *h016;
+  W16 w16;
   size_t bytes;
 };
 
 Saved carve_saved(const aa_dims& d, void* base) {
   const size_t N = (size_t)d.B * d.T, H = d.H, E = d.E;
   Carver c(base);
-  Saved s;
+  Saved s{};
   s.x = c.take(N * 2 * E);
   s.xg = c.take(N * 4 * H);
   s.acts = c.take(N * 4 * H);
@@ -115,19 +132,38 @@ Saved carve_saved(const aa_dims& d, void* base) {
   s.ctx = c.take(N * H);
   s.u = c.take(N * H);
   s.zeros = c.take((size_t)d.B * H);
+  if (d.precision == AA_PREC_BF16) {
+    Carver16 h{c};
+    s.x16 = h.take(N * 2 * E);
+    s.hid16 = h.take(N * H);
+    s.hsprev16 = h.take(N * H);
+    s.s16 = h.take(N * H);
+    s.V16 = h.take((size_t)d.B * d.k * H);
+    s.u16 = h.take(N * H);
+    s.h016 = h.take((size_t)d.B * H);
+    s.w16.w_ih = h.take(4 * H * 2 * E);
+    s.w16.w_hh = h.take(4 * H * H);
+    s.w16.sen_wx = h.take(H * 2 * E);
+    s.w16.sen_wh = h.take(H * H);
+    s.w16.att_wv = h.take((size_t)d.a * H);
+    s.w16.att_wg = h.take((size_t)d.a * H);
+    s.w16.att_ws = h.take((size_t)d.a * H);
+    s.w16.mlp_w = h.take((size_t)d.Vc * H);
+  }
   s.bytes = c.off;
   return s;
 }
 
 struct BwdScratch {
   float *du, *ds, *dq, *dr, *dP, *da, *dcell, *dhs, *dgates, *dx, *dh_rec, *dc_rec, *dV;
+  bf16 *dS16, *dq16, *dr16, *dP16, *da16, *dgates16;
   size_t bytes;
 };
 
 BwdScratch carve_bwd(const aa_dims& d, void* base) {
   const size_t N = (size_t)d.B * d.T, H = d.H, E = d.E;
   Carver c(base);
-  BwdScratch s;
+  BwdScratch s{};
   s.du = c.take(N * H);
   s.ds = c.take(N * H);
   s.dq = c.take(N * d.a);
@@ -141,8 +177,69 @@ BwdScratch carve_bwd(const aa_dims& d, void* base) {
   s.dh_rec = c.take((size_t)d.B * H);
   s.dc_rec = c.take((size_t)d.B * H);
   s.dV = c.take((size_t)d.B * d.k * H);
+  if (d.precision == AA_PREC_BF16) {
+    Carver16 h{c};
+    const size_t ap = a_pad_of(d);
+    s.dS16 = h.take(N * d.Vc);
+    s.dq16 = h.take(N * ap);
+    s.dr16 = h.take(N * ap);
+    s.dP16 = h.take((size_t)d.B * d.k * ap);
+    s.da16 = h.take(N * H);
+    s.dgates16 = h.take(N * 4 * H);
+  }
   s.bytes = c.off;
   return s;
+}
+
+// ---- precision-dispatching contractions --------------------------------------------------
+// A matrix that exists as fp32 and (in bf16 mode) as a bf16 mirror, each with its own row stride.
+struct Mat {
+  const float* f; long long ldf;
+  const bf16* h; long long ldh;
+};
+inline Mat M32(const float* f, long long ld) { return Mat{f, ld, nullptr, 0}; }
+inline Mat M2(const float* f, long long ldf, const bf16* h, long long ldh) { return Mat{f, ldf, h, ldh}; }
+
+struct Ctx {
+  int prec;
+  cudaStream_t st;
+  bool tc() const { return prec == AA_PREC_BF16; }
+};
+
+// Y[M,N] = X[M,K] W[N,K]^T (+Cin) (+b1+b2)
+int mm_nt(const Ctx& c, const char* tag, int M, int N, int K, Mat X, Mat W, float* Y, long long ldy, const float* Cin,
+          long long ldcin, const float* b1, const float* b2) {
+  ProfScope ps(tag, c.st);
+  if (!c.tc()) return gemm_nt(M, N, K, X.f, X.ldf, W.f, W.ldf, Y, ldy, Cin, ldcin, b1, b2, c.st);
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.elem_size = 2;
+  g.A = X.h; g.lda = X.ldh; g.a_mn = 0;
+  g.B = W.h; g.ldb = W.ldh; g.b_mn = 0;
+  g.D32 = Y; g.ldd32 = ldy; g.Cin = Cin; g.ldcin = ldcin; g.beta = 1.f; g.bias1 = b1; g.bias2 = b2;
+  return launch_gemm_tc(g, c.st);
+}
+// dX[M,K] = dY[M,N] W[N,K] (+Cin)
+int mm_nn(const Ctx& c, const char* tag, int M, int K, int N, Mat dY, Mat W, float* dX, long long lddx, const float* Cin,
+          long long ldcin) {
+  ProfScope ps(tag, c.st);
+  if (!c.tc()) return gemm_nn(M, K, N, dY.f, dY.ldf, W.f, W.ldf, dX, lddx, Cin, ldcin, c.st);
+  TcGemmArgs g{};
+  g.M = M; g.N = K; g.K = N; g.elem_size = 2;
+  g.A = dY.h; g.lda = dY.ldh; g.a_mn = 0;
+  g.B = W.h; g.ldb = W.ldh; g.b_mn = 1;          // W stored [N(reduction), K(out)]: MN-major B
+  g.D32 = dX; g.ldd32 = lddx; g.Cin = Cin; g.ldcin = ldcin; g.beta = 1.f;
+  return launch_gemm_tc(g, c.st);
+}
+// dW[N,K] (+)= dY[M,N]^T X[M,K]
+int mm_tn(const Ctx& c, const char* tag, int N, int K, int M, Mat dY, Mat X, float* dW, long long lddw, bool accumulate) {
+  ProfScope ps(tag, c.st);
+  if (!c.tc()) return gemm_tn(N, K, M, dY.f, dY.ldf, X.f, X.ldf, dW, lddw, accumulate, c.st);
+  TcGemmArgs g{};
+  g.M = N; g.N = K; g.K = M; g.elem_size = 2;
+  g.A = dY.h; g.lda = dY.ldh; g.a_mn = 1;        // both operands are stored reduction-major
+  g.B = X.h; g.ldb = X.ldh; g.b_mn = 1;
+  g.D32 = dW; g.ldd32 = lddw; g.Cin = accumulate ? dW : nullptr; g.ldcin = lddw; g.beta = 1.f;
+  return launch_gemm_tc(g, c.st);
 }
 
 int check_dims(const aa_dims* d, bool need_T) {
@@ -152,6 +249,10 @@ int check_dims(const aa_dims* d, bool need_T) {
   AA_REQUIRE(d->H % 4 == 0 && d->E % 4 == 0, "H and E must be multiples of 4 (H=%d, E=%d)", d->H, d->E);
   AA_REQUIRE(d->a <= 128, "attention dim a=%d exceeds 128", d->a);
   if (need_T) AA_REQUIRE(d->T >= 1, "T must be >= 1 (got %d)", d->T);
+  AA_REQUIRE(d->precision == AA_PREC_FP32 || d->precision == AA_PREC_BF16, "unknown precision %d", d->precision);
+  if (d->precision == AA_PREC_BF16)
+    AA_REQUIRE(d->H % 8 == 0 && d->E % 8 == 0 && d->Vc % 8 == 0,
+               "bf16 mode needs H, E and Vc to be multiples of 8 (16-byte bf16 rows for TMA); got H=%d E=%d Vc=%d", d->H, d->E, d->Vc);
   return AA_OK;
 }
 
@@ -172,18 +273,17 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long n_cols
 }  // namespace
 
 // attention sub-stage shared by aa_atten_forward / aa_adaptive_forward / aa_decoder_forward
-static int atten_stage(const aa_dims& d, const float* att_wv, const float* att_wg, const float* att_ws, const float* att_wh,
-                       const float* V, const float* h, const float* s, float* P, float* q, float* r, float* c_hat,
-                       float* ctx, float* u, float* alpha, float* beta, cudaStream_t st) {
+static int atten_stage(const Ctx& c, const aa_dims& d, Mat Wv, Mat Wg, Mat Ws, const float* att_wh, Mat V, Mat h, Mat s, float* P,
+                       float* q, float* r, float* c_hat, float* ctx, float* u, bf16* u16, float* alpha, float* beta) {
   const int N = d.B * d.T;
-  AA_PROF("gemm_P", st, gemm_nt(d.B * d.k, d.a, d.H, V, d.H, att_wv, d.H, P, d.a, nullptr, 0, nullptr, nullptr, st));   // :34
-  AA_PROF("gemm_qr", st, gemm_nt(N, d.a, d.H, h, d.H, att_wg, d.H, q, d.a, nullptr, 0, nullptr, nullptr, st));           // :35
-  AA_PROF("gemm_qr", st, gemm_nt(N, d.a, d.H, s, d.H, att_ws, d.H, r, d.a, q, d.a, nullptr, nullptr, st));               // :45
+  AA_TRY(mm_nt(c, "gemm_P", d.B * d.k, d.a, d.H, V, Wv, P, d.a, nullptr, 0, nullptr, nullptr));   // :34
+  AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, h, Wg, q, d.a, nullptr, 0, nullptr, nullptr));           // :35
+  AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, s, Ws, r, d.a, q, d.a, nullptr, nullptr));               // :45
   AttenFwdArgs p{};
   p.B = d.B; p.T = d.T; p.k = d.k; p.a = d.a; p.H = d.H;
-  p.P = P; p.q = q; p.r = r; p.s = s; p.h = h; p.V = V; p.wh = att_wh;
-  p.alpha = alpha; p.beta = beta; p.ctx = ctx; p.u = u; p.c_hat = c_hat;
-  AA_PROF("atten_fwd", st, launch_atten_fwd(p, st));
+  p.P = P; p.q = q; p.r = r; p.s = s.f; p.h = h.f; p.V = V.f; p.wh = att_wh;
+  p.alpha = alpha; p.beta = beta; p.ctx = ctx; p.u = u; p.c_hat = c_hat; p.u16 = u16;
+  AA_PROF("atten_fwd", c.st, launch_atten_fwd(p, c.st));
   return AA_OK;
 }
 
@@ -245,6 +345,26 @@ int aa_linear_forward(int M, int N, int K, const float* X, int64_t ldx, const fl
   return gemm_nt(M, N, K, X, ldx, W, ldw, Y, ldy, nullptr, 0, bias, nullptr, (cudaStream_t)stream);
 }
 
+int aa_gemm(int engine, int M, int N, int K, const void* A, int64_t lda, int a_kmajor, const void* B, int64_t ldb, int b_kmajor,
+            const float* C, int64_t ldc, float beta, const float* bias, float* D, int64_t ldd, void* stream) {
+  if (engine == 0) {
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K;
+    g.A = static_cast<const float*>(A); g.lda = lda; g.a_kcontig = a_kmajor;
+    g.B = static_cast<const float*>(B); g.ldb = ldb; g.b_kcontig = b_kmajor;
+    g.Cin = C; g.ldcin = ldc; g.D = D; g.ldd = ldd; g.bias1 = bias; g.alpha = 1.f; g.beta = C ? beta : 0.f; g.splitk = 1;
+    return launch_sgemm(g, (cudaStream_t)stream);
+  }
+  AA_REQUIRE(engine == 1 || engine == 2, "aa_gemm: engine must be 0 (fp32 SIMT), 1 (tcgen05 bf16) or 2 (tcgen05 tf32)");
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.a_mn = a_kmajor ? 0 : 1;
+  g.B = B; g.ldb = ldb; g.b_mn = b_kmajor ? 0 : 1;
+  g.elem_size = engine == 1 ? 2 : 4;
+  g.D32 = D; g.ldd32 = ldd; g.Cin = C; g.ldcin = ldc; g.beta = beta; g.bias1 = bias;
+  return launch_gemm_tc(g, (cudaStream_t)stream);
+}
+
 int aa_precompute_P(const aa_dims* d, const float* V, const float* att_wv, float* P, void* stream) {
   AA_TRY(check_dims(d, false));
   AA_REQUIRE(V && att_wv && P, "aa_precompute_P: null pointer");
@@ -262,7 +382,7 @@ int aa_sentinel_forward(const aa_dims* d, const float* sen_wx, const float* sen_
     AA_REQUIRE(sen_wh, "aa_sentinel_forward: sen_wh is NULL");
     AA_TRY(gemm_nt(N, d->H, d->H, h_prev, d->H, sen_wh, d->H, gate_out, d->H, gate_out, d->H, nullptr, nullptr, st));
   }
-  return launch_sentinel_fwd(gate_out, cell, gate_out, s_out, (long long)N * d->H, st);
+  return launch_sentinel_fwd(gate_out, cell, gate_out, s_out, nullptr, (long long)N * d->H, st);
 }
 
 size_t aa_atten_workspace_bytes(const aa_dims* d) {
@@ -285,8 +405,9 @@ int aa_atten_forward(const aa_dims* d, const float* att_wv, const float* att_wg,
   float* P = c.take((size_t)d->B * d->k * d->a);
   float* q = c.take(N * d->a);
   float* r = c.take(N * d->a);
-  return atten_stage(*d, att_wv, att_wg, att_ws, att_wh, V, h_t, s_t, P, q, r, c_hat, nullptr, nullptr, alpha, beta,
-                     (cudaStream_t)stream);
+  const Ctx cx{AA_PREC_FP32, (cudaStream_t)stream};
+  return atten_stage(cx, *d, M32(att_wv, d->H), M32(att_wg, d->H), M32(att_ws, d->H), att_wh, M32(V, d->H), M32(h_t, d->H),
+                     M32(s_t, d->H), P, q, r, c_hat, nullptr, nullptr, nullptr, alpha, beta);
 }
 
 size_t aa_adaptive_workspace_bytes(const aa_dims* d) {
@@ -322,9 +443,10 @@ int aa_adaptive_forward(const aa_dims* d, const aa_weights* w, const float* x, c
     AA_TRY(launch_copy2d(hs_prev + H, (long long)T * H, hiddens, (long long)T * H, d->B, (T - 1) * H, st));
     AA_TRY(gemm_nt((int)N, H, H, hs_prev, H, w->sen_wh, H, g, H, g, H, nullptr, nullptr, st));
   }
-  AA_TRY(launch_sentinel_fwd(g, cells, g, s, (long long)N * H, st));
-  AA_TRY(atten_stage(*d, w->att_wv, w->att_wg, w->att_ws, w->att_wh, V, hiddens, s, P, q, r, nullptr, nullptr, u, alpha,
-                     beta, st));
+  AA_TRY(launch_sentinel_fwd(g, cells, g, s, nullptr, (long long)N * H, st));
+  const Ctx cx{AA_PREC_FP32, st};
+  AA_TRY(atten_stage(cx, *d, M32(w->att_wv, H), M32(w->att_wg, H), M32(w->att_ws, H), w->att_wh, M32(V, H), M32(hiddens, H),
+                     M32(s, H), P, q, r, nullptr, nullptr, u, nullptr, alpha, beta));
   return gemm_nt((int)N, d->Vc, H, u, H, w->mlp_w, H, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr, st);   // :132
 }
 
@@ -348,34 +470,60 @@ int aa_decoder_forward(const aa_dims* d, const aa_weights* w, const float* V, co
   Saved sv = carve_saved(*d, saved);
   const long long* cap = reinterpret_cast<const long long*>(captions);
 
+  const Ctx cx{d->precision, st};
+  const bool tc = cx.tc();
+  const W16& h = sv.w16;
+  if (tc) {   // bf16 copies of the GEMM weights (one launch) and of V, h0
+    CastSegs cs{};
+    const float* srcs[8] = {w->w_ih, w->w_hh, w->sen_wx, w->sen_wh, w->att_wv, w->att_wg, w->att_ws, w->mlp_w};
+    bf16* dsts[8] = {h.w_ih, h.w_hh, h.sen_wx, h.sen_wh, h.att_wv, h.att_wg, h.att_ws, h.mlp_w};
+    const long long ns[8] = {4LL * H * 2 * E, 4LL * H * H, (long long)H * 2 * E, (long long)H * H, (long long)d->a * H,
+                             (long long)d->a * H, (long long)d->a * H, (long long)d->Vc * H};
+    for (int i = 0; i < 8; ++i) { cs.src[i] = srcs[i]; cs.dst[i] = dsts[i]; cs.n[i] = ns[i]; }
+    AA_PROF("cast_weights", st, launch_cast_multi(cs, 8, st));
+    AA_PROF("cast_inputs", st, launch_cast2d(V, H, sv.V16, H, (long long)B * d->k, H, st));
+    if (h0) AA_PROF("cast_inputs", st, launch_cast2d(h0, H, sv.h016, H, B, H, st));
+    else AA_CHECK_CUDA(cudaMemsetAsync(sv.h016, 0, sizeof(bf16) * (size_t)B * H, st));
+    AA_CHECK_CUDA(cudaMemset2DAsync(sv.hsprev16, (size_t)T * H * 2, 0, (size_t)H * 2, B, st));
+  }
+  const Mat Wih = M2(w->w_ih, 2 * E, h.w_ih, 2 * E), Whh = M2(w->w_hh, H, h.w_hh, H);
+  const Mat Wx = M2(w->sen_wx, 2 * E, h.sen_wx, 2 * E), Wh = M2(w->sen_wh, H, h.sen_wh, H);
+  const Mat Wv = M2(w->att_wv, H, h.att_wv, H), Wg = M2(w->att_wg, H, h.att_wg, H), Ws = M2(w->att_ws, H, h.att_ws, H);
+  const Mat Wp = M2(w->mlp_w, H, h.mlp_w, H);
+  const Mat X = M2(sv.x, 2 * E, sv.x16, 2 * E);
+
   // x = [embed(w); v_g]                                        baseline_attention.py:151-154
-  AA_TRY(launch_build_x(cap, w->embed, v_g, sv.x, B, T, E, d->Vc, st));
+  AA_TRY(launch_build_x(cap, w->embed, v_g, sv.x, sv.x16, B, T, E, d->Vc, st));
   // input halves of the LSTM gates and of the sentinel gate, batched over all T
-  AA_PROF("gemm_gates_in", st, gemm_nt(N, 4 * H, 2 * E, sv.x, 2 * E, w->w_ih, 2 * E, sv.xg, 4 * H, nullptr, 0, w->b_ih, w->b_hh, st));
-  AA_PROF("gemm_gates_in", st, gemm_nt(N, H, 2 * E, sv.x, 2 * E, w->sen_wx, 2 * E, sv.g, H, nullptr, 0, nullptr, nullptr, st));
+  AA_TRY(mm_nt(cx, "gemm_gates_in", N, 4 * H, 2 * E, X, Wih, sv.xg, 4 * H, nullptr, 0, w->b_ih, w->b_hh));
+  AA_TRY(mm_nt(cx, "gemm_gates_in", N, H, 2 * E, X, Wx, sv.g, H, nullptr, 0, nullptr, nullptr));
   if (!h0 || !c0) AA_CHECK_CUDA(cudaMemsetAsync(sv.zeros, 0, sizeof(float) * (size_t)B * H, st));
   AA_CHECK_CUDA(cudaMemset2DAsync(sv.hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, B, st));   // h~_0 = 0 (Q2)
   // recurrence                                                 baseline_attention.py:167-178
   for (int t = 0; t < T; ++t) {
-    const float* hp = t == 0 ? (h0 ? h0 : sv.zeros) : sv.hiddens + (size_t)(t - 1) * H;
-    const long long ldhp = t == 0 ? H : (long long)T * H;
+    const Mat hp = t == 0 ? M2(h0 ? h0 : sv.zeros, H, sv.h016, H)
+                          : M2(sv.hiddens + (size_t)(t - 1) * H, (long long)T * H, tc ? sv.hid16 + (size_t)(t - 1) * H : nullptr,
+                               (long long)T * H);
     const float* cp = t == 0 ? (c0 ? c0 : sv.zeros) : sv.cells + (size_t)(t - 1) * H;
     const long long ldcp = t == 0 ? H : (long long)T * H;
     float* pre = sv.xg + (size_t)t * 4 * H;
-    AA_PROF("lstm_rec_gemm", st, gemm_nt(B, 4 * H, H, hp, ldhp, w->w_hh, H, pre, (long long)T * 4 * H, pre, (long long)T * 4 * H, nullptr, nullptr, st));
-    AA_PROF("lstm_cell_fwd", st, launch_lstm_cell_fwd(pre, (long long)T * 4 * H, cp, ldcp, sv.acts + (size_t)t * 4 * H, (long long)T * 4 * H,
-                                sv.cells + (size_t)t * H, (long long)T * H, sv.hiddens + (size_t)t * H, (long long)T * H,
-                                t + 1 < T ? sv.hs_prev + (size_t)(t + 1) * H : nullptr, (long long)T * H, B, H, st));
+    AA_TRY(mm_nt(cx, "lstm_rec_gemm", B, 4 * H, H, hp, Whh, pre, (long long)T * 4 * H, pre, (long long)T * 4 * H, nullptr, nullptr));
+    AA_PROF("lstm_cell_fwd", st,
+            launch_lstm_cell_fwd(pre, (long long)T * 4 * H, cp, ldcp, sv.acts + (size_t)t * 4 * H, (long long)T * 4 * H,
+                                 sv.cells + (size_t)t * H, (long long)T * H, sv.hiddens + (size_t)t * H, (long long)T * H,
+                                 t + 1 < T ? sv.hs_prev + (size_t)(t + 1) * H : nullptr, (long long)T * H,
+                                 tc ? sv.hid16 + (size_t)t * H : nullptr, (tc && t + 1 < T) ? sv.hsprev16 + (size_t)(t + 1) * H : nullptr,
+                                 B, H, st));
   }
   if (hT) AA_TRY(launch_copy2d(hT, H, sv.hiddens + (size_t)(T - 1) * H, (long long)T * H, B, H, st));
   if (cT) AA_TRY(launch_copy2d(cT, H, sv.cells + (size_t)(T - 1) * H, (long long)T * H, B, H, st));
   // sentinel                                                   adaptive_attention.py:116-125, 75-85
-  if (T > 1) AA_TRY(gemm_nt(N, H, H, sv.hs_prev, H, w->sen_wh, H, sv.g, H, sv.g, H, nullptr, nullptr, st));
-  AA_TRY(launch_sentinel_fwd(sv.g, sv.cells, sv.g, sv.s, (long long)N * H, st));
+  if (T > 1) AA_TRY(mm_nt(cx, "gemm_sentinel_h", N, H, H, M2(sv.hs_prev, H, sv.hsprev16, H), Wh, sv.g, H, sv.g, H, nullptr, nullptr));
+  AA_TRY(launch_sentinel_fwd(sv.g, sv.cells, sv.g, sv.s, sv.s16, (long long)N * H, st));
   // attention + vocabulary projection                          adaptive_attention.py:128-132
-  AA_TRY(atten_stage(*d, w->att_wv, w->att_wg, w->att_ws, w->att_wh, V, sv.hiddens, sv.s, sv.P, sv.q, sv.r, nullptr, sv.ctx,
-                     sv.u, alpha, beta, st));
-  AA_PROF("gemm_vocab_fwd", st, gemm_nt(N, d->Vc, H, sv.u, H, w->mlp_w, H, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr, st));
+  AA_TRY(atten_stage(cx, *d, Wv, Wg, Ws, w->att_wh, M2(V, H, sv.V16, H), M2(sv.hiddens, H, sv.hid16, H), M2(sv.s, H, sv.s16, H), sv.P,
+                     sv.q, sv.r, nullptr, sv.ctx, sv.u, sv.u16, alpha, beta));
+  AA_TRY(mm_nt(cx, "gemm_vocab_fwd", N, d->Vc, H, M2(sv.u, H, sv.u16, H), Wp, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr));
   return AA_OK;
 }
 
@@ -406,9 +554,21 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
   const long long* cap = reinterpret_cast<const long long*>(captions);
   float* dVb = dV ? dV : sc.dV;
 
+  const Ctx cx{d->precision, st};
+  const bool tc = cx.tc();
+  const W16& h = sv.w16;
+  const int ap = a_pad_of(*d);
+  const Mat Whh = M2(w->w_hh, H, h.w_hh, H), Wih = M2(w->w_ih, 2 * E, h.w_ih, 2 * E);
+  const Mat Wx = M2(w->sen_wx, 2 * E, h.sen_wx, 2 * E), Wh = M2(w->sen_wh, H, h.sen_wh, H);
+  const Mat Wv = M2(w->att_wv, H, h.att_wv, H), Wg = M2(w->att_wg, H, h.att_wg, H), Ws = M2(w->att_ws, H, h.att_ws, H);
+  const Mat Wp = M2(w->mlp_w, H, h.mlp_w, H);
+  const Mat X = M2(sv.x, 2 * E, sv.x16, 2 * E);
+  if (tc) AA_PROF("cast_dscores", st, launch_cast2d(d_scores, Vc, sc.dS16, Vc, N, Vc, st));
+  const Mat dS = M2(d_scores, Vc, sc.dS16, Vc);
+
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
-  AA_PROF("gemm_vocab_dx", st, gemm_nn(N, H, Vc, d_scores, Vc, w->mlp_w, H, sc.du, H, nullptr, 0, st));
-  AA_PROF("gemm_vocab_dw", st, gemm_tn(Vc, H, N, d_scores, Vc, sv.u, H, gw->mlp_w, H, false, st));
+  AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, nullptr, 0));
+  AA_TRY(mm_tn(cx, "gemm_vocab_dw", Vc, H, N, dS, M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
   AA_PROF("colsum", st, launch_colsum(d_scores, Vc, N, Vc, gw->mlp_b, nullptr, st));
   // attention                                                   adaptive_attention.py:34-56
   AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, st));
@@ -417,20 +577,24 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
   ab.P = sv.P; ab.q = sv.q; ab.r = sv.r; ab.s = sv.s; ab.V = V; ab.wh = w->att_wh;
   ab.alpha = alpha; ab.beta = beta; ab.ctx = sv.ctx; ab.dchat = sc.du; ab.d_alpha = d_alpha; ab.d_beta = d_beta;
   ab.ds = sc.ds; ab.dq = sc.dq; ab.dr = sc.dr; ab.dP = sc.dP; ab.dV = dVb; ab.dwh = gw->att_wh;
+  ab.dq16 = tc ? sc.dq16 : nullptr; ab.dr16 = tc ? sc.dr16 : nullptr; ab.dP16 = nullptr; ab.a_pad = ap;
   AA_PROF("atten_bwd", st, launch_atten_bwd(ab, st));
-  AA_TRY(gemm_nn(N, H, a, sc.dr, a, w->att_ws, H, sc.ds, H, sc.ds, H, st));            // ds += dr W_s
-  AA_TRY(gemm_tn(a, H, N, sc.dr, a, sv.s, H, gw->att_ws, H, false, st));
-  AA_TRY(gemm_nn(N, H, a, sc.dq, a, w->att_wg, H, sc.du, H, sc.du, H, st));            // dh = du + dq W_g
-  AA_TRY(gemm_tn(a, H, N, sc.dq, a, sv.hiddens, H, gw->att_wg, H, false, st));
-  AA_TRY(gemm_nn(B * k, H, a, sc.dP, a, w->att_wv, H, dVb, H, dVb, H, st));            // dV += dP W_v
-  AA_TRY(gemm_tn(a, H, B * k, sc.dP, a, V, H, gw->att_wv, H, false, st));
+  if (tc) AA_PROF("cast_inputs", st, launch_cast2d(sc.dP, a, sc.dP16, ap, (long long)B * k, a, st));
+  const Mat dR = M2(sc.dr, a, sc.dr16, ap), dQ = M2(sc.dq, a, sc.dq16, ap), dPm = M2(sc.dP, a, sc.dP16, ap);
+  AA_TRY(mm_nn(cx, "gemm_att_dx", N, H, a, dR, Ws, sc.ds, H, sc.ds, H));                              // ds += dr W_s
+  AA_TRY(mm_tn(cx, "gemm_att_dw", a, H, N, dR, M2(sv.s, H, sv.s16, H), gw->att_ws, H, false));
+  AA_TRY(mm_nn(cx, "gemm_att_dx", N, H, a, dQ, Wg, sc.du, H, sc.du, H));                              // dh = du + dq W_g
+  AA_TRY(mm_tn(cx, "gemm_att_dw", a, H, N, dQ, M2(sv.hiddens, H, sv.hid16, H), gw->att_wg, H, false));
+  AA_TRY(mm_nn(cx, "gemm_att_dx", B * k, H, a, dPm, Wv, dVb, H, dVb, H));                             // dV += dP W_v
+  AA_TRY(mm_tn(cx, "gemm_att_dw", a, H, B * k, dPm, M2(V, H, sv.V16, H), gw->att_wv, H, false));
   // sentinel                                                    adaptive_attention.py:79-83
-  AA_TRY(launch_sentinel_bwd(sc.ds, sv.g, sv.cells, sc.da, sc.dcell, (long long)N * H, st));
-  AA_TRY(gemm_nn(N, 2 * E, H, sc.da, H, w->sen_wx, 2 * E, sc.dx, 2 * E, nullptr, 0, st));
-  AA_TRY(gemm_tn(H, 2 * E, N, sc.da, H, sv.x, 2 * E, gw->sen_wx, 2 * E, false, st));
+  AA_TRY(launch_sentinel_bwd(sc.ds, sv.g, sv.cells, sc.da, sc.dcell, tc ? sc.da16 : nullptr, (long long)N * H, st));
+  const Mat dA = M2(sc.da, H, sc.da16, H);
+  AA_TRY(mm_nn(cx, "gemm_sent_dx", N, 2 * E, H, dA, Wx, sc.dx, 2 * E, nullptr, 0));
+  AA_TRY(mm_tn(cx, "gemm_sent_dw", H, 2 * E, N, dA, X, gw->sen_wx, 2 * E, false));
   if (T > 1) {
-    AA_TRY(gemm_nn(N, H, H, sc.da, H, w->sen_wh, H, sc.dhs, H, nullptr, 0, st));
-    AA_TRY(gemm_tn(H, H, N, sc.da, H, sv.hs_prev, H, gw->sen_wh, H, false, st));
+    AA_TRY(mm_nn(cx, "gemm_sent_dx", N, H, H, dA, Wh, sc.dhs, H, nullptr, 0));
+    AA_TRY(mm_tn(cx, "gemm_sent_dw", H, H, N, dA, M2(sv.hs_prev, H, sv.hsprev16, H), gw->sen_wh, H, false));
   } else {
     AA_CHECK_CUDA(cudaMemsetAsync(gw->sen_wh, 0, sizeof(float) * (size_t)H * H, st));   // h~ = 0: no gradient (Q3)
   }
@@ -441,20 +605,27 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
     const float* dhs_next = (T > 1 && t + 1 < T) ? sc.dhs + (size_t)(t + 1) * H : nullptr;
     const float* cp = t == 0 ? (c0 ? c0 : sv.zeros) : sv.cells + (size_t)(t - 1) * H;
     const long long ldcp = t == 0 ? H : (long long)T * H;
-    AA_PROF("lstm_cell_bwd", st, launch_lstm_cell_bwd(sc.du + (size_t)t * H, (long long)T * H, dhs_next, (long long)T * H, dh_rec_in,
-                                sc.dcell + (size_t)t * H, (long long)T * H, dc_rec_in, sv.acts + (size_t)t * 4 * H,
-                                (long long)T * 4 * H, sv.cells + (size_t)t * H, (long long)T * H, cp, ldcp,
-                                sc.dgates + (size_t)t * 4 * H, (long long)T * 4 * H, sc.dc_rec, B, H, st));
-    AA_PROF("bptt_rec_gemm", st, gemm_nn(B, H, 4 * H, sc.dgates + (size_t)t * 4 * H, (long long)T * 4 * H, w->w_hh, H, sc.dh_rec, H, nullptr, 0, st));
+    AA_PROF("lstm_cell_bwd", st,
+            launch_lstm_cell_bwd(sc.du + (size_t)t * H, (long long)T * H, dhs_next, (long long)T * H, dh_rec_in,
+                                 sc.dcell + (size_t)t * H, (long long)T * H, dc_rec_in, sv.acts + (size_t)t * 4 * H,
+                                 (long long)T * 4 * H, sv.cells + (size_t)t * H, (long long)T * H, cp, ldcp,
+                                 sc.dgates + (size_t)t * 4 * H, (long long)T * 4 * H, tc ? sc.dgates16 + (size_t)t * 4 * H : nullptr,
+                                 sc.dc_rec, B, H, st));
+    AA_TRY(mm_nn(cx, "bptt_rec_gemm", B, H, 4 * H,
+                 M2(sc.dgates + (size_t)t * 4 * H, (long long)T * 4 * H, tc ? sc.dgates16 + (size_t)t * 4 * H : nullptr, (long long)T * 4 * H),
+                 Whh, sc.dh_rec, H, nullptr, 0));
   }
   if (dh0) AA_TRY(launch_copy2d(dh0, H, sc.dh_rec, H, B, H, st));
   if (dc0) AA_TRY(launch_copy2d(dc0, H, sc.dc_rec, H, B, H, st));
   // LSTM parameter gradients, batched over all steps
-  AA_PROF("gemm_lstm_dw", st, gemm_tn(4 * H, 2 * E, N, sc.dgates, 4 * H, sv.x, 2 * E, gw->w_ih, 2 * E, false, st));
-  AA_PROF("gemm_lstm_dw", st, gemm_tn(4 * H, H, N, sc.dgates, 4 * H, sv.hs_prev, H, gw->w_hh, H, false, st));   // steps t >= 1 (h~_0 rows are 0)
-  if (h0) AA_TRY(gemm_tn(4 * H, H, B, sc.dgates, (long long)T * 4 * H, h0, H, gw->w_hh, H, true, st));   // step 0
-  AA_TRY(launch_colsum(sc.dgates, 4 * H, N, 4 * H, gw->b_ih, gw->b_hh, st));
-  AA_PROF("gemm_lstm_dx", st, gemm_nn(N, 2 * E, 4 * H, sc.dgates, 4 * H, w->w_ih, 2 * E, sc.dx, 2 * E, sc.dx, 2 * E, st));   // dx += dgates W_ih
+  const Mat dG = M2(sc.dgates, 4 * H, sc.dgates16, 4 * H);
+  AA_TRY(mm_tn(cx, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, false));
+  AA_TRY(mm_tn(cx, "gemm_lstm_dw", 4 * H, H, N, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, false));   // steps t >= 1 (h~_0 rows are 0)
+  if (h0)                                                                                                      // step 0
+    AA_TRY(mm_tn(cx, "gemm_lstm_dw", 4 * H, H, B, M2(sc.dgates, (long long)T * 4 * H, sc.dgates16, (long long)T * 4 * H),
+                 M2(h0, H, sv.h016, H), gw->w_hh, H, true));
+  AA_PROF("colsum", st, launch_colsum(sc.dgates, 4 * H, N, 4 * H, gw->b_ih, gw->b_hh, st));
+  AA_TRY(mm_nn(cx, "gemm_lstm_dx", N, 2 * E, 4 * H, dG, Wih, sc.dx, 2 * E, sc.dx, 2 * E));                      // dx += dgates W_ih
   // x = [embed(w); v_g]                                         baseline_attention.py:151-154
   AA_CHECK_CUDA(cudaMemsetAsync(gw->embed, 0, sizeof(float) * (size_t)Vc * E, st));
   return launch_embed_bwd(cap, sc.dx, gw->embed, dv_g, B, T, E, Vc, st);

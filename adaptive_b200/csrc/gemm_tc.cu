@@ -1,0 +1,382 @@
+// tcgen05 GEMM for sm_100a: TMA-staged 128B-swizzled tiles in shared memory, one elected
+// thread issuing tcgen05.mma (kind::f16 for bf16, kind::tf32 for fp32 inputs), fp32
+// accumulators in tensor memory, warp-specialised (TMA producer / MMA issuer / 4 epilogue
+// warps), mbarrier pipelines.  D[M,N] = A * B^T-style contraction with either operand
+// K-major (reduction index contiguous) or MN-major (output index contiguous), so the forward
+// (X W^T), input-gradient (dY W) and weight-gradient (dY^T X) forms all run without a
+// transpose pass.
+//
+// Descriptor encodings follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction
+// descriptor" tables (same bit layout as cute::UMMA::SmemDescriptor / InstrDescriptor).
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace aa {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int TC_THREADS = 192;   // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (TMEM lane quarter = warp % 4)
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spin guard: a mis-programmed pipeline must fault (launch error) instead of hanging the GPU.
+#ifndef AA_SPIN_LIMIT_CYCLES
+#define AA_SPIN_LIMIT_CYCLES 4000000000ll   // ~2 s at 1.9 GHz
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > AA_SPIN_LIMIT_CYCLES) __trap();
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <bool TF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
+//   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
+//   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1     bits [61,64) layout = 2 (128B swizzle)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcEpilogue {
+  int M, N, K;
+  float* D32; long long ldd32;
+  __nv_bfloat16* D16; long long ldd16;
+  const float* Cin; long long ldcin; float beta;
+  const float* bias1; const float* bias2;
+};
+
+// Tile geometry (bytes): every smem row is 128 B (the swizzle span).
+//   K-major operand, R rows (M or N): one TMA box {128B/ES elements of K, R rows}      -> R*128 B
+//   MN-major operand, R columns     : R*ES/128 TMA boxes {128B/ES elements of MN, BK rows of K} -> BK*128 B each
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e) {
+  constexpr bool TF32 = (ES == 4);
+  constexpr int EPR = 128 / ES;            // elements per 128-byte smem row
+  constexpr int BK = EPR;                  // reduction elements per stage (64 bf16 / 32 tf32)
+  constexpr int UMMA_K = 32 / ES;          // 16 bf16 / 8 tf32
+  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;   // BM*BK*ES, BN*BK*ES
+  constexpr uint32_t A_BOX = A_MN ? BK * 128 : A_BYTES;        // bytes per TMA box
+  constexpr uint32_t B_BOX = B_MN ? BK * 128 : B_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = (e.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        uint8_t* a_dst = sA + s * A_BYTES;
+        uint8_t* b_dst = sB + s * B_BYTES;
+        if constexpr (A_MN) {
+#pragma unroll
+          for (int j = 0; j < (int)(A_BYTES / A_BOX); ++j) tma_load_2d(a_dst + j * A_BOX, &tmA, m0 + j * EPR, kb * BK, &full_bar[s]);
+        } else {
+          tma_load_2d(a_dst, &tmA, kb * BK, m0, &full_bar[s]);
+        }
+        if constexpr (B_MN) {
+#pragma unroll
+          for (int j = 0; j < (int)(B_BYTES / B_BOX); ++j) tma_load_2d(b_dst + j * B_BOX, &tmB, n0 + j * EPR, kb * BK, &full_bar[s]);
+        } else {
+          tma_load_2d(b_dst, &tmB, kb * BK, n0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A/B format (bf16 = 1, tf32 = 2) at bits 7-9 / 10-12,
+      // A/B major at bits 15/16 (0 = K, 1 = MN), N>>3 at bits 17-22, M>>4 at bits 24-28
+      constexpr uint32_t fmt = TF32 ? 2u : 1u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
+        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major : LBO unused (1), SBO = 8 rows * 128 B; advance 32 B per UMMA_K inside the swizzle atom
+          // MN-major: LBO = bytes between 128B-wide MN chunks (one TMA box), SBO = 8 k-rows * 128 B;
+          //           advance UMMA_K k-rows * 128 B
+          const uint64_t da = A_MN ? make_smem_desc(a_addr + k * UMMA_K * 128, A_BOX, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(b_addr + k * UMMA_K * 128, B_BOX, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
+          tc_mma<TF32>(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);   // frees the smem stage when these MMAs have read it
+      }
+      tc_commit(tmem_full);         // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < e.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= e.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const bool full = nb + 32 <= e.N;
+      if (e.bias1 || e.bias2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nb + j < e.N) v[j] += (e.bias1 ? __ldg(e.bias1 + nb + j) : 0.f) + (e.bias2 ? __ldg(e.bias2 + nb + j) : 0.f);
+      }
+      if (e.Cin) {
+        const float* cp = e.Cin + (long long)row * e.ldcin + nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nb + j < e.N) v[j] += e.beta * cp[j];
+      }
+      if (e.D32) {
+        float* dp = e.D32 + (long long)row * e.ldd32 + nb;
+        if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < e.N) dp[j] = v[j];
+        }
+      }
+      if (e.D16) {
+        __nv_bfloat16* dp = e.D16 + (long long)row * e.ldd16 + nb;
+        if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(dp + j) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < e.N) dp[j] = __float2bfloat16(v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D tensor map over a row-major [rows, cols] array (cols contiguous, row stride ld elements):
+// box = {128 bytes of the contiguous dim, box_rows}, 128B swizzle, zero fill out of bounds.
+int make_map(CUtensorMap* map, const void* base, int es, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return AA_ERR_CUDA;
+  }
+  AA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tcgen05 GEMM: operand base must be 16-byte aligned");
+  AA_REQUIRE((ld * es) % 16 == 0, "tcgen05 GEMM: operand row stride must be a multiple of 16 bytes (ld=%lld, es=%d)", ld, es);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)(ld * es)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld es=%d)", (int)r, rows, cols, ld, es);
+    return AA_ERR_CUDA;
+  }
+  return AA_OK;
+}
+
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN>
+int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
+  constexpr int BK = 128 / ES;
+  CUtensorMap tmA, tmB;
+  // K-major operand: array [R, K] (K contiguous), box {BK, tile rows}; MN-major: array [K, R] (R contiguous), box {128B of R, BK rows}
+  if (A_MN) AA_TRY(make_map(&tmA, g.A, ES, g.K, g.M, g.lda, BK));
+  else      AA_TRY(make_map(&tmA, g.A, ES, g.M, g.K, g.lda, BM));
+  if (B_MN) AA_TRY(make_map(&tmB, g.B, ES, g.K, g.N, g.ldb, BK));
+  else      AA_TRY(make_map(&tmB, g.B, ES, g.N, g.K, g.ldb, BN));
+  TcEpilogue e{};
+  e.M = g.M; e.N = g.N; e.K = g.K;
+  e.D32 = g.D32; e.ldd32 = g.ldd32; e.D16 = g.D16; e.ldd16 = g.ldd16;
+  e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
+  constexpr size_t smem = (size_t)STAGES * (BM * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e);
+  AA_CHECK_LAUNCH("gemm_tc_kernel");
+  return AA_OK;
+}
+
+template <int BN, int ES, int STAGES>
+int launch_major(const TcGemmArgs& g, cudaStream_t st) {
+  if (!g.a_mn && !g.b_mn) return launch_cfg<BN, ES, STAGES, false, false>(g, st);
+  if (!g.a_mn && g.b_mn) return launch_cfg<BN, ES, STAGES, false, true>(g, st);
+  if (g.a_mn && !g.b_mn) return launch_cfg<BN, ES, STAGES, true, false>(g, st);
+  return launch_cfg<BN, ES, STAGES, true, true>(g, st);
+}
+
+template <int ES>
+int launch_es(const TcGemmArgs& g, cudaStream_t st) {
+  // pick BN so that the grid covers the SMs when the problem allows it
+  const long long sms = num_sms();
+  const long long mt = ceil_div(g.M, BM);
+  if (mt * ceil_div(g.N, 128) >= sms || g.N > 2048) return launch_major<128, ES, 3>(g, st);
+  if (mt * ceil_div(g.N, 64) >= sms || g.N > 512 || (g.b_mn && ES == 2)) return launch_major<64, ES, 4>(g, st);
+  return launch_major<32, ES, 4>(g, st);   // (an MN-major bf16 B tile needs >= 64 columns: one 128-byte swizzle row)
+}
+
+}  // namespace
+
+int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return AA_OK;
+  AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16), "tcgen05 GEMM: bad arguments");
+  AA_REQUIRE(g.elem_size == 2 || g.elem_size == 4, "tcgen05 GEMM: element size must be 2 (bf16) or 4 (tf32)");
+  if (g.elem_size == 4 && (g.a_mn || g.b_mn)) {
+    // 32-bit MN-major operands need the SWIZZLE_128B_BASE32B layout; only the forward (K-major) form is built
+    set_error("tcgen05 GEMM: tf32 operands must be K-major");
+    return AA_ERR_UNSUPPORTED;
+  }
+  return g.elem_size == 2 ? launch_es<2>(g, st) : launch_es<4>(g, st);
+}
+
+}  // namespace aa

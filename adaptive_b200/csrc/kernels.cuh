@@ -7,25 +7,27 @@ namespace aa {
 
 // ---- pointwise.cu ----------------------------------------------------------------------
 // x[b,t,:] = [embed[cap[b,t]] ; v_g[b]]                      (baseline_attention.py:151-154)
-int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, int B, int T, int E, int Vc,
-                   cudaStream_t s);
+// (every *16 argument is an optional bf16 mirror of the fp32 output, same strides; null in fp32 mode)
+int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, __nv_bfloat16* x16, int B, int T, int E,
+                   int Vc, cudaStream_t s);
 // one LSTM cell update from pre-activations (gate order i,f,g,o)   (baseline_attention.py:172)
 //   pre [B,4H] row stride ld_pre; c_prev [B,H] stride ld_cprev;
 //   writes acts[b, t, 4, H] (post-activation), cells[b,t,:], hiddens[b,t,:], hs_next (= h, may be null)
 int launch_lstm_cell_fwd(const float* pre, long long ld_pre, const float* c_prev, long long ld_cprev, float* acts,
                          long long ld_acts, float* c_out, long long ld_c, float* h_out, long long ld_h, float* hs_next,
-                         long long ld_hs, int B, int H, cudaStream_t s);
+                         long long ld_hs, __nv_bfloat16* h16, __nv_bfloat16* hs_next16, int B, int H, cudaStream_t s);
 // sentinel: g = sigmoid(pre) ; s = g * tanh(cell)                   (adaptive_attention.py:79-83)
-int launch_sentinel_fwd(const float* pre, const float* cells, float* g, float* s_out, long long n, cudaStream_t s);
-// sentinel backward: da = ds*tanh(c)*g*(1-g) ; dcell = ds*g*(1-tanh(c)^2)
-int launch_sentinel_bwd(const float* ds, const float* g, const float* cells, float* da, float* dcell, long long n,
+int launch_sentinel_fwd(const float* pre, const float* cells, float* g, float* s_out, __nv_bfloat16* s16, long long n,
                         cudaStream_t s);
+// sentinel backward: da = ds*tanh(c)*g*(1-g) ; dcell = ds*g*(1-tanh(c)^2)
+int launch_sentinel_bwd(const float* ds, const float* g, const float* cells, float* da, float* dcell, __nv_bfloat16* da16,
+                        long long n, cudaStream_t s);
 // one BPTT step of the LSTM cell.  dh_attn/dhs_next/dcell are the batched (non-recurrent) contributions.
 int launch_lstm_cell_bwd(const float* dh_attn, long long ld_dh, const float* dhs_next, long long ld_dhs,
                          const float* dh_rec, const float* dcell, long long ld_dcell, const float* dc_rec,
                          const float* acts, long long ld_acts, const float* cells, long long ld_c, const float* c_prev,
-                         long long ld_cprev, float* dgates, long long ld_dg, float* dc_out, int B, int H,
-                         cudaStream_t s);
+                         long long ld_cprev, float* dgates, long long ld_dg, __nv_bfloat16* dgates16, float* dc_out, int B,
+                         int H, cudaStream_t s);
 // out[n] = sum_m X[m, n]   (column sums; bias gradients).  out2 (optional) receives a copy.
 int launch_colsum(const float* X, long long ldx, int M, int N, float* out, float* out2, cudaStream_t s);
 // dE[cap[row], :] += dx[row, 0:E]  (dE pre-zeroed) ; dvg[b, :] = sum_t dx[b,t,E:2E]
@@ -39,9 +41,34 @@ int launch_argmax_gather(const float* logits, long long ld_logits, int B, int Vc
 int launch_gather_rows(const long long* ids, long long ld_ids, const float* table, int E, int Vc, float* dst, long long ld_dst,
                        int B, cudaStream_t s);
 int launch_copy2d(float* dst, long long ld_dst, const float* src, long long ld_src, int rows, int cols, cudaStream_t s);
+// fp32 -> bf16 casts: 2-D with row strides, and a one-launch multi-segment cast (weights)
+int launch_cast2d(const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst, long long rows, int cols,
+                  cudaStream_t s);
+struct CastSegs {
+  const float* src[8];
+  __nv_bfloat16* dst[8];
+  long long n[8];
+};
+int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s);
 // mean cross-entropy over rows + gradient: loss += -log_softmax(logits[r])[tgt[r]] / n ; dlogits = (softmax - onehot)/n
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
                       long long ldd, cudaStream_t s);
+
+// ---- gemm_tc.cu (tcgen05 + TMA) ------------------------------------------------------------
+// D[m,n] = sum_k A(m,k) B(n,k) (+ beta*Cin + bias1[n] + bias2[n]); bf16 (elem_size 2) or tf32 (4) inputs,
+// fp32 accumulation.  a_mn/b_mn = 0: operand stored [rows, K] with K contiguous (K-major);
+// = 1: stored [K, rows] with rows contiguous (MN-major).  Output fp32 (D32) and/or bf16 (D16).
+struct TcGemmArgs {
+  int M, N, K;
+  const void* A; long long lda; int a_mn;
+  const void* B; long long ldb; int b_mn;
+  int elem_size;
+  float* D32; long long ldd32;
+  __nv_bfloat16* D16; long long ldd16;
+  const float* Cin; long long ldcin; float beta;
+  const float* bias1; const float* bias2;
+};
+int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
 
 // ---- atten.cu --------------------------------------------------------------------------
 struct AttenFwdArgs {
@@ -49,6 +76,7 @@ struct AttenFwdArgs {
   const float *P, *q, *r, *s, *h, *V, *wh;   // P[B,k,a] q,r[B,T,a] s,h[B,T,H] V[B,k,H] wh[a]
   float *alpha, *beta, *ctx, *u;            // alpha[B,T,k] beta[B,T] ctx[B,T,H] (may be null) u[B,T,H] = c_hat + h
   float* c_hat;                             // optional [B,T,H]
+  __nv_bfloat16* u16;                       // optional bf16 mirror of u
 };
 int launch_atten_fwd(const AttenFwdArgs& p, cudaStream_t s);
 
@@ -63,6 +91,8 @@ struct AttenBwdArgs {
   float *dP;              // [B,k,a]  summed over t
   float *dV;              // [B,k,H]  sum_t alpha_i dctx     (dP W_v added later by GEMM)
   float *dwh;             // [a]      pre-zeroed, atomically accumulated
+  __nv_bfloat16 *dq16, *dr16, *dP16;   // optional bf16 mirrors with row stride a_pad (dP16 only when not split over T)
+  int a_pad;
 };
 int launch_atten_bwd(const AttenBwdArgs& p, cudaStream_t s);
 

@@ -7,8 +7,11 @@ namespace {
 
 constexpr int PW_THREADS = 256;
 
+typedef __nv_bfloat16 bf16;
+
 __global__ void build_x_kernel(const long long* __restrict__ cap, const float* __restrict__ embed,
-                               const float* __restrict__ v_g, float* __restrict__ x, int B, int T, int E, int Vc) {
+                               const float* __restrict__ v_g, float* __restrict__ x, bf16* __restrict__ x16, int B, int T, int E,
+                               int Vc) {
   const int row = blockIdx.x;  // b*T + t
   const int b = row / T;
   long long id = cap[row];
@@ -17,15 +20,21 @@ __global__ void build_x_kernel(const long long* __restrict__ cap, const float* _
   const float* vg = v_g + (long long)b * E;
   float* dst = x + (long long)row * 2 * E;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    dst[e] = __ldg(src + e);
-    dst[E + e] = __ldg(vg + e);
+    const float a = __ldg(src + e), b2 = __ldg(vg + e);
+    dst[e] = a;
+    dst[E + e] = b2;
+    if (x16) {
+      x16[(long long)row * 2 * E + e] = __float2bfloat16(a);
+      x16[(long long)row * 2 * E + E + e] = __float2bfloat16(b2);
+    }
   }
 }
 
 __global__ void lstm_cell_fwd_kernel(const float* __restrict__ pre, long long ld_pre, const float* __restrict__ c_prev,
                                      long long ld_cprev, float* __restrict__ acts, long long ld_acts,
                                      float* __restrict__ c_out, long long ld_c, float* __restrict__ h_out, long long ld_h,
-                                     float* __restrict__ hs_next, long long ld_hs, int B, int H) {
+                                     float* __restrict__ hs_next, long long ld_hs, bf16* __restrict__ h16,
+                                     bf16* __restrict__ hs_next16, int B, int H) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H) return;
   const int b = (int)(idx / H), j = (int)(idx % H);
@@ -41,24 +50,30 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ pre, long long ld
   c_out[b * ld_c + j] = c;
   h_out[b * ld_h + j] = h;
   if (hs_next) hs_next[b * ld_hs + j] = h;
+  if (h16) h16[b * ld_h + j] = __float2bfloat16(h);               // bf16 mirrors share the fp32 strides
+  if (hs_next16) hs_next16[b * ld_hs + j] = __float2bfloat16(h);
 }
 
 // pre and g may alias (in-place gate)
 __global__ void sentinel_fwd_kernel(const float* pre, const float* __restrict__ cells, float* g, float* __restrict__ s_out,
-                                    long long n) {
+                                    bf16* __restrict__ s16, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gv = sigmoidf_acc(pre[i]);
   g[i] = gv;
-  s_out[i] = gv * tanhf(cells[i]);
+  const float sv = gv * tanhf(cells[i]);
+  s_out[i] = sv;
+  if (s16) s16[i] = __float2bfloat16(sv);
 }
 
 __global__ void sentinel_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ g, const float* __restrict__ cells,
-                                    float* __restrict__ da, float* __restrict__ dcell, long long n) {
+                                    float* __restrict__ da, float* __restrict__ dcell, bf16* __restrict__ da16, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float d = ds[i], gv = g[i], tc = tanhf(cells[i]);
-  da[i] = d * tc * gv * (1.f - gv);
+  const float dav = d * tc * gv * (1.f - gv);
+  da[i] = dav;
+  if (da16) da16[i] = __float2bfloat16(dav);
   dcell[i] = d * gv * (1.f - tc * tc);
 }
 
@@ -67,7 +82,7 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_attn, long lon
                                      long long ld_dcell, const float* dc_rec, const float* __restrict__ acts,
                                      long long ld_acts, const float* __restrict__ cells, long long ld_c,
                                      const float* __restrict__ c_prev, long long ld_cprev, float* __restrict__ dgates,
-                                     long long ld_dg, float* dc_out, int B, int H) {
+                                     long long ld_dg, bf16* __restrict__ dgates16, float* dc_out, int B, int H) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H) return;
   const int b = (int)(idx / H), j = (int)(idx % H);
@@ -80,10 +95,14 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_attn, long lon
   float dc = dcell[b * ld_dcell + j] + dh * og * (1.f - tc * tc);
   if (dc_rec) dc += dc_rec[(long long)b * H + j];
   float* dg = dgates + b * ld_dg;
-  dg[j] = dc * gg * ig * (1.f - ig);
-  dg[H + j] = dc * c_prev[b * ld_cprev + j] * fg * (1.f - fg);
-  dg[2 * H + j] = dc * ig * (1.f - gg * gg);
-  dg[3 * H + j] = dh * tc * og * (1.f - og);
+  const float d0 = dc * gg * ig * (1.f - ig), d1 = dc * c_prev[b * ld_cprev + j] * fg * (1.f - fg);
+  const float d2 = dc * ig * (1.f - gg * gg), d3 = dh * tc * og * (1.f - og);
+  dg[j] = d0; dg[H + j] = d1; dg[2 * H + j] = d2; dg[3 * H + j] = d3;
+  if (dgates16) {
+    bf16* dg16 = dgates16 + b * ld_dg;
+    dg16[j] = __float2bfloat16(d0); dg16[H + j] = __float2bfloat16(d1);
+    dg16[2 * H + j] = __float2bfloat16(d2); dg16[3 * H + j] = __float2bfloat16(d3);
+  }
   dc_out[(long long)b * H + j] = dc * fg;
 }
 
@@ -234,36 +253,65 @@ __global__ void __launch_bounds__(PW_THREADS) ce_fwd_bwd_kernel(const float* __r
   }
 }
 
+// fp32 -> bf16, 2-D with independent row strides (also used for the zero-padded a -> a_pad copies)
+__global__ void cast2d_kernel(const float* __restrict__ src, long long ld_src, bf16* __restrict__ dst, long long ld_dst, long long rows,
+                              int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const long long r = idx / cols;
+  const int c = (int)(idx % cols);
+  dst[r * ld_dst + c] = __float2bfloat16(src[r * ld_src + c]);
+}
+
+__global__ void cast_multi_kernel(const CastSegs segs) {
+  const int sidx = blockIdx.y;
+  const float* __restrict__ src = segs.src[sidx];
+  bf16* __restrict__ dst = segs.dst[sidx];
+  const long long n = segs.n[sidx];
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = pk;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16(src[i]);
+}
+
 inline unsigned blocks_for(long long n) { return (unsigned)((n + PW_THREADS - 1) / PW_THREADS); }
 
 }  // namespace
 
-int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, int B, int T, int E, int Vc,
-                   cudaStream_t s) {
+int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, __nv_bfloat16* x16, int B, int T, int E,
+                   int Vc, cudaStream_t s) {
   if (B * T == 0) return AA_OK;
-  build_x_kernel<<<B * T, 128, 0, s>>>(cap, embed, v_g, x, B, T, E, Vc);
+  build_x_kernel<<<B * T, 128, 0, s>>>(cap, embed, v_g, x, x16, B, T, E, Vc);
   AA_CHECK_LAUNCH("build_x");
   return AA_OK;
 }
 
 int launch_lstm_cell_fwd(const float* pre, long long ld_pre, const float* c_prev, long long ld_cprev, float* acts,
                          long long ld_acts, float* c_out, long long ld_c, float* h_out, long long ld_h, float* hs_next,
-                         long long ld_hs, int B, int H, cudaStream_t s) {
+                         long long ld_hs, __nv_bfloat16* h16, __nv_bfloat16* hs_next16, int B, int H, cudaStream_t s) {
   lstm_cell_fwd_kernel<<<blocks_for((long long)B * H), PW_THREADS, 0, s>>>(pre, ld_pre, c_prev, ld_cprev, acts, ld_acts, c_out,
-                                                                           ld_c, h_out, ld_h, hs_next, ld_hs, B, H);
+                                                                           ld_c, h_out, ld_h, hs_next, ld_hs, h16, hs_next16, B, H);
   AA_CHECK_LAUNCH("lstm_cell_fwd");
   return AA_OK;
 }
 
-int launch_sentinel_fwd(const float* pre, const float* cells, float* g, float* s_out, long long n, cudaStream_t s) {
-  sentinel_fwd_kernel<<<blocks_for(n), PW_THREADS, 0, s>>>(pre, cells, g, s_out, n);
+int launch_sentinel_fwd(const float* pre, const float* cells, float* g, float* s_out, __nv_bfloat16* s16, long long n,
+                        cudaStream_t s) {
+  sentinel_fwd_kernel<<<blocks_for(n), PW_THREADS, 0, s>>>(pre, cells, g, s_out, s16, n);
   AA_CHECK_LAUNCH("sentinel_fwd");
   return AA_OK;
 }
 
-int launch_sentinel_bwd(const float* ds, const float* g, const float* cells, float* da, float* dcell, long long n,
-                        cudaStream_t s) {
-  sentinel_bwd_kernel<<<blocks_for(n), PW_THREADS, 0, s>>>(ds, g, cells, da, dcell, n);
+int launch_sentinel_bwd(const float* ds, const float* g, const float* cells, float* da, float* dcell, __nv_bfloat16* da16,
+                        long long n, cudaStream_t s) {
+  sentinel_bwd_kernel<<<blocks_for(n), PW_THREADS, 0, s>>>(ds, g, cells, da, dcell, da16, n);
   AA_CHECK_LAUNCH("sentinel_bwd");
   return AA_OK;
 }
@@ -271,11 +319,11 @@ int launch_sentinel_bwd(const float* ds, const float* g, const float* cells, flo
 int launch_lstm_cell_bwd(const float* dh_attn, long long ld_dh, const float* dhs_next, long long ld_dhs,
                          const float* dh_rec, const float* dcell, long long ld_dcell, const float* dc_rec,
                          const float* acts, long long ld_acts, const float* cells, long long ld_c, const float* c_prev,
-                         long long ld_cprev, float* dgates, long long ld_dg, float* dc_out, int B, int H,
-                         cudaStream_t s) {
+                         long long ld_cprev, float* dgates, long long ld_dg, __nv_bfloat16* dgates16, float* dc_out, int B,
+                         int H, cudaStream_t s) {
   lstm_cell_bwd_kernel<<<blocks_for((long long)B * H), PW_THREADS, 0, s>>>(dh_attn, ld_dh, dhs_next, ld_dhs, dh_rec, dcell,
                                                                            ld_dcell, dc_rec, acts, ld_acts, cells, ld_c,
-                                                                           c_prev, ld_cprev, dgates, ld_dg, dc_out, B, H);
+                                                                           c_prev, ld_cprev, dgates, ld_dg, dgates16, dc_out, B, H);
   AA_CHECK_LAUNCH("lstm_cell_bwd");
   return AA_OK;
 }
@@ -322,6 +370,21 @@ int launch_gather_rows(const long long* ids, long long ld_ids, const float* tabl
 int launch_copy2d(float* dst, long long ld_dst, const float* src, long long ld_src, int rows, int cols, cudaStream_t s) {
   copy2d_kernel<<<blocks_for((long long)rows * cols), PW_THREADS, 0, s>>>(dst, ld_dst, src, ld_src, rows, cols);
   AA_CHECK_LAUNCH("copy2d");
+  return AA_OK;
+}
+
+int launch_cast2d(const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst, long long rows, int cols,
+                  cudaStream_t s) {
+  if (rows * cols == 0) return AA_OK;
+  cast2d_kernel<<<blocks_for(rows * cols), PW_THREADS, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
+  AA_CHECK_LAUNCH("cast2d");
+  return AA_OK;
+}
+
+int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s) {
+  if (nsegs == 0) return AA_OK;
+  cast_multi_kernel<<<dim3(64, nsegs), PW_THREADS, 0, s>>>(segs);
+  AA_CHECK_LAUNCH("cast_multi");
   return AA_OK;
 }
 

@@ -56,8 +56,11 @@ def _states2d(st: Optional[torch.Tensor], B: int, H: int) -> Optional[torch.Tens
     return _f32c(st)
 
 
-def make_dims(B, T, k, H, E, Vc, a=ATT_DIM) -> AADims:
-    return AADims(B=B, T=T, k=k, a=a, H=H, E=E, Vc=Vc)
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+
+def make_dims(B, T, k, H, E, Vc, a=ATT_DIM, precision=_lib.PREC_FP32) -> AADims:
+    return AADims(B=B, T=T, k=k, a=a, H=H, E=E, Vc=Vc, precision=precision)
 
 
 def weights_struct(w: Sequence[torch.Tensor]) -> AAWeights:
@@ -88,7 +91,7 @@ class _DecoderFn(torch.autograd.Function):
     """``Decoder.forward`` (baseline_attention.py:148-194) + hand-written backward."""
 
     @staticmethod
-    def forward(ctx, V, v_g, captions, h0, c0, *w):
+    def forward(ctx, prec, V, v_g, captions, h0, c0, *w):
         lib = _lib.load()
         B, k, H = V.shape
         T = captions.shape[1]
@@ -97,7 +100,7 @@ class _DecoderFn(torch.autograd.Function):
         a = w[7].shape[0]
         _check_weights(w, H, E, Vc, a)
         dev = V.device
-        d = make_dims(B, T, k, H, E, Vc, a)
+        d = make_dims(B, T, k, H, E, Vc, a, prec)
         scores = torch.empty(B, T, Vc, device=dev, dtype=torch.float32)
         alpha = torch.empty(B, T, k, device=dev, dtype=torch.float32)
         beta = torch.empty(B, T, 1, device=dev, dtype=torch.float32)
@@ -110,7 +113,7 @@ class _DecoderFn(torch.autograd.Function):
             check(lib.aa_decoder_forward(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(captions), _ptr(h0),
                                          _ptr(c0), _ptr(scores), _ptr(alpha), _ptr(beta), _ptr(hT), _ptr(cT), _ptr(saved),
                                          nbytes, _stream(dev)), "aa_decoder_forward")
-        ctx.dims = (B, T, k, H, E, Vc, a)
+        ctx.dims = (B, T, k, H, E, Vc, a, prec)
         ctx.has_state = (h0 is not None, c0 is not None)
         ctx.save_for_backward(V, v_g, captions, h0 if h0 is not None else V.new_empty(0),
                               c0 if c0 is not None else V.new_empty(0), alpha, beta, saved, *w)
@@ -122,11 +125,11 @@ class _DecoderFn(torch.autograd.Function):
         lib = _lib.load()
         V, v_g, captions, h0, c0, alpha, beta, saved = ctx.saved_tensors[:8]
         w = ctx.saved_tensors[8:]
-        B, T, k, H, E, Vc, a = ctx.dims
+        B, T, k, H, E, Vc, a, prec = ctx.dims
         h0 = h0 if ctx.has_state[0] else None
         c0 = c0 if ctx.has_state[1] else None
         dev = V.device
-        d = make_dims(B, T, k, H, E, Vc, a)
+        d = make_dims(B, T, k, H, E, Vc, a, prec)
         if d_scores is None:
             d_scores = torch.zeros(B, T, Vc, device=dev, dtype=torch.float32)
         d_scores, d_alpha, d_beta, d_hT, d_cT = (_f32c(x) for x in (d_scores, d_alpha, d_beta, d_hT, d_cT))
@@ -147,17 +150,18 @@ class _DecoderFn(torch.autograd.Function):
                                           _ptr(d_alpha), _ptr(d_beta), _ptr(d_hT), _ptr(d_cT), ctypes.byref(gs), _ptr(dV),
                                           _ptr(dvg), _ptr(dh0), _ptr(dc0), _ptr(scratch), sbytes, _stream(dev)),
                   "aa_decoder_backward")
-        return (dV, dvg, None, dh0, dc0) + tuple(grads)
+        return (None, dV, dvg, None, dh0, dc0) + tuple(grads)
 
 
-def decoder_forward(w: Sequence[torch.Tensor], V, v_g, captions, h0=None, c0=None):
-    """scores [B,T,Vc], alpha [B,T,k], beta [B,T,1], hT [B,H], cT [B,H] (differentiable)."""
+def decoder_forward(w: Sequence[torch.Tensor], V, v_g, captions, h0=None, c0=None, precision: str = "fp32"):
+    """scores [B,T,Vc], alpha [B,T,k], beta [B,T,1], hT [B,H], cT [B,H] (differentiable).
+    ``precision``: "fp32" (exact, the parity path) or "bf16" (tcgen05 tensor cores, fp32 accumulate)."""
     _need_cuda(V, v_g, captions, h0, c0)
     V, v_g = _f32c(V), _f32c(v_g)
     B, _, H = V.shape
     captions = captions.to(torch.int64).contiguous()
     h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
-    return _DecoderFn.apply(V, v_g, captions, h0, c0, *w)
+    return _DecoderFn.apply(PRECISIONS[precision], V, v_g, captions, h0, c0, *w)
 
 
 class _PackRowsFn(torch.autograd.Function):

@@ -137,6 +137,8 @@ class Decoder(nn.Module):
         self.LSTM = nn.LSTM(embed_size * 2, hidden_size, 1, batch_first=True)
         _lstm_init(self.LSTM)
         self.adaptive = AdaptiveBlock(embed_size, hidden_size, vocab_size, cf)
+        # "fp32": exact path (parity with the reference); "bf16": tensor-core mixed precision for training
+        self.precision = getattr(cf, "precision", "fp32") if cf is not None else "fp32"
 
     def weights(self):
         return self.adaptive._weights13(self.embed, self.LSTM)
@@ -146,7 +148,7 @@ class Decoder(nn.Module):
         h0 = c0 = None
         if states is not None:
             h0, c0 = states
-        scores, alpha, beta, hT, cT = F_aa.decoder_forward(self.weights(), V, v_g, captions, h0, c0)
+        scores, alpha, beta, hT, cT = F_aa.decoder_forward(self.weights(), V, v_g, captions, h0, c0, self.precision)
         return scores, alpha, beta, (hT.unsqueeze(0), cT.unsqueeze(0))
 
 

@@ -39,8 +39,12 @@ extern "C" {
 /* Problem shape.  B images (rows), T teacher-forced steps, k regions per image, a = inner
  * attention dim (49 in the reference regardless of k: adaptive_attention.py:16-19), H LSTM
  * hidden size, E word-embedding size (LSTM input is 2E), Vc vocabulary size. */
+#define AA_PREC_FP32 0   /* exact fp32 everywhere (SIMT contractions): the parity path */
+#define AA_PREC_BF16 1   /* mixed precision: bf16 operands on tcgen05 tensor cores, fp32 accumulation,
+                            fp32 master weights / state / softmax / gradients (teacher-forced path only) */
 typedef struct aa_dims {
   int32_t B, T, k, a, H, E, Vc;
+  int32_t precision;   /* AA_PREC_* */
 } aa_dims;
 
 /* Decoder parameters, named after the reference state_dict keys:
@@ -103,6 +107,17 @@ int aa_profile_get(int i, char* name, int name_len, double* total_ms, int* launc
  * adaptive_attention.py:16-19,66-67,100.  ld* are row strides in elements. */
 int aa_linear_forward(int M, int N, int K, const float* X, int64_t ldx, const float* W, int64_t ldw,
                       const float* bias, float* Y, int64_t ldy, void* stream);
+
+/* The contraction engines themselves (every nn.Linear / bmm of the path is one of these):
+ *   D[M,N] = sum_k A(m,k) B(n,k) + beta*C[M,N] + bias[N]
+ * engine 0: exact fp32 SIMT (A, B float);  1: tcgen05 kind::f16 (A, B bf16, fp32 accumulate);
+ * 2: tcgen05 kind::tf32 (A, B float read as tf32, fp32 accumulate).
+ * a_kmajor != 0: A stored [M,K] (K contiguous, row stride lda); == 0: stored [K,M] (M contiguous).
+ * b_kmajor != 0: B stored [N,K] (the nn.Linear weight layout); == 0: stored [K,N].
+ * C, bias may be NULL.  tcgen05 engines need 16-byte aligned bases and row strides. */
+int aa_gemm(int engine, int M, int N, int K, const void* A, int64_t lda, int a_kmajor, const void* B, int64_t ldb,
+            int b_kmajor, const float* C, int64_t ldc, float beta, const float* bias, float* D, int64_t ldd,
+            void* stream);
 
 /* P = V * W_v^T, once per image (adaptive_attention.py:34, `affine_v(V)`).  V [B,k,H] -> P [B,k,a]. */
 int aa_precompute_P(const aa_dims* d, const float* V, const float* att_wv, float* P, void* stream);

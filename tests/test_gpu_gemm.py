@@ -1,0 +1,87 @@
+"""The contraction engines through the C ABI (aa_gemm): fp32 SIMT (exact), tcgen05 bf16 and
+tcgen05 tf32, all four operand layouts, ragged shapes -- against torch float64 matmul on the
+same (already rounded) inputs."""
+import ctypes
+
+import pytest
+import torch
+
+from adaptive_b200 import _lib
+from adaptive_b200.functional import _ptr, _stream
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 128, 64), (80, 2048, 512), (1440, 49, 512), (1360, 10000, 512), (49, 512, 3920), (257, 96, 40), (4096, 520, 776)]
+
+
+def _run(engine, M, N, K, a_k, b_k, with_c, with_bias, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dt = torch.bfloat16 if engine == 1 else torch.float32
+    A = torch.randn((M, K) if a_k else (K, M), generator=g, device="cuda").to(dt)
+    B = torch.randn((N, K) if b_k else (K, N), generator=g, device="cuda").to(dt)
+    C = torch.randn(M, N, generator=g, device="cuda") if with_c else None
+    bias = torch.randn(N, generator=g, device="cuda") if with_bias else None
+    D = torch.full((M, N), float("nan"), device="cuda")
+    lib = _lib.load()
+    rc = lib.aa_gemm(engine, M, N, K, _ptr(A), A.stride(0), 1 if a_k else 0, _ptr(B), B.stride(0), 1 if b_k else 0, _ptr(C), N, 0.5,
+                     _ptr(bias), _ptr(D), N, _stream(D.device))
+    _lib.check(rc, "aa_gemm")
+    torch.cuda.synchronize()
+    Ad = A.double() if a_k else A.double().t()
+    Bd = B.double() if b_k else B.double().t()
+    ref = Ad @ Bd.t()
+    if with_c:
+        ref = ref + 0.5 * C.double()
+    if with_bias:
+        ref = ref + bias.double()
+    return D, ref
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("a_k,b_k", [(1, 1), (1, 0), (0, 0), (0, 1)])
+def test_simt_fp32(M, N, K, a_k, b_k):
+    D, ref = _run(0, M, N, K, a_k, b_k, True, True)
+    assert torch.isfinite(D).all()
+    assert float((D.double() - ref).abs().max() / ref.abs().max()) < 1e-5     # fp32 accumulation over K up to 3920
+
+
+def _aligned(M, N, K, a_k, b_k, es):
+    # TMA needs 16-byte row strides: the contiguous extent of each operand must be a multiple of 16/es
+    q = 16 // es
+    return ((K if a_k else M) % q == 0) and ((K if b_k else N) % q == 0)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("a_k,b_k", [(1, 1), (1, 0), (0, 0), (0, 1)])
+def test_tcgen05_bf16(M, N, K, a_k, b_k):
+    if not _aligned(M, N, K, a_k, b_k, 2):
+        pytest.skip("operand row stride not 16-byte aligned")
+    D, ref = _run(1, M, N, K, a_k, b_k, True, True)
+    assert torch.isfinite(D).all()
+    # inputs are exact bf16; products exact in fp32; only the fp32 accumulation order differs
+    assert float((D.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_tcgen05_tf32(M, N, K):
+    a_k = b_k = 1      # the tf32 engine serves the forward (K-major) form only
+    D, ref = _run(2, M, N, K, a_k, b_k, False, True)
+    assert torch.isfinite(D).all()
+    assert float((D.double() - ref).abs().max() / ref.abs().max()) < 2e-3      # tf32: 10-bit mantissa inputs
+
+
+def test_tcgen05_tf32_rejects_mn_major():
+    lib = _lib.load()
+    A = torch.randn(64, 64, device="cuda")
+    D = torch.empty(64, 64, device="cuda")
+    rc = lib.aa_gemm(2, 64, 64, 64, _ptr(A), 64, 0, _ptr(A), 64, 1, None, 0, 0.0, None, _ptr(D), 64, _stream(D.device))
+    assert rc == 3 and b"K-major" in lib.aa_last_error()
+
+
+def test_tcgen05_rejects_misaligned():
+    lib = _lib.load()
+    A = torch.randn(64, 66, device="cuda").bfloat16()[:, :65]
+    B = torch.randn(64, 65, device="cuda").bfloat16()
+    D = torch.empty(64, 64, device="cuda")
+    rc = lib.aa_gemm(1, 64, 64, 65, _ptr(A), 65, 1, _ptr(B), 65, 1, None, 0, 0.0, None, _ptr(D), 64, _stream(D.device))
+    assert rc != 0 and b"16 bytes" in lib.aa_last_error()

@@ -89,6 +89,36 @@ def test_forward_backward_vs_oracle(B, T, dims):
         assert rel_err(t.grad.cpu().numpy(), G[key]) < TOL, key
 
 
+BF16_TOL = 2e-2     # bf16 path, stated by north_star
+
+
+@pytest.mark.parametrize("B,T,dims", [(80, 18, CFG_A), (5, 3, Dims(H=64, E=32, Vc=200, k=49)),
+                                      (33, 6, Dims(H=128, E=64, Vc=1000, k=196)), (7, 1, Dims(H=64, E=32, Vc=336, k=49))])
+def test_bf16_forward_backward_vs_oracle(B, T, dims):
+    """Mixed-precision (tcgen05 bf16) training path against the fp64 oracle, 2e-2 relative."""
+    w = make_weights(dims, seed=5, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=6)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    i64 = {k: (v.astype(np.float64) if v.dtype != np.int64 else v) for k, v in inp.items()}
+    s_o, a_o, b_o, (h_o, c_o), cache = orc.decoder_forward(w64, i64["V"], i64["v_g"], i64["captions"], i64["h0"], i64["c0"],
+                                                           want_cache=True)
+    rng = np.random.Generator(np.random.PCG64(1))
+    dS = rng.standard_normal(s_o.shape) / s_o.shape[-1]
+    G = orc.decoder_backward(w64, cache, dS)
+    W = dev_weights(w, requires_grad=True)
+    V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+    scores, alpha, beta, hT, cT = F_aa.decoder_forward(W, V, v_g, cap, h0, c0, precision="bf16")
+    errs = {"scores": rel_err(scores.detach().cpu().numpy(), s_o), "alpha": rel_err(alpha.detach().cpu().numpy(), a_o),
+            "beta": rel_err(beta.detach().cpu().numpy(), b_o), "hT": rel_err(hT.detach().cpu().numpy(), h_o)}
+    (scores * torch.from_numpy(dS.astype(np.float32)).cuda()).sum().backward()
+    for key, t in zip(grad_key_order(), W):
+        errs["d" + key] = rel_err(t.grad.cpu().numpy(), G[key])
+    for key, t in (("V", V), ("v_g", v_g), ("h0", h0), ("c0", c0)):
+        errs["d" + key] = rel_err(t.grad.cpu().numpy(), G[key])
+    bad = {k: v for k, v in errs.items() if not v < BF16_TOL}
+    assert not bad, (bad, errs)
+
+
 def test_no_initial_state_and_state_layouts():
     dims = Dims(H=64, E=32, Vc=200, k=49)
     w = make_weights(dims, seed=2)
