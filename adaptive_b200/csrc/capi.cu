@@ -109,7 +109,8 @@ struct W16 {
 struct Saved {
   float *x, *xg, *acts, *cells, *hiddens, *hs_prev, *g, *s, *P, *q, *r, *ctx, *u, *zeros;
   // bf16 mirrors (only carved when d.precision == AA_PREC_BF16)
-  bf16 *x16, *hid16, *hsprev16, *s16, *V16, *u16, *h016;
+  bf16 *x16, *hid16, *hsprev16, *s16, *V16, *u16, *h016, *whh_pack16;
+  unsigned* counters;
   W16 w16;
   size_t bytes;
 };
@@ -149,6 +150,8 @@ Saved carve_saved(const aa_dims& d, void* base) {
     s.w16.att_wg = h.take((size_t)d.a * H);
     s.w16.att_ws = h.take((size_t)d.a * H);
     s.w16.mlp_w = h.take((size_t)d.Vc * H);
+    s.whh_pack16 = h.take(4 * H * H);
+    s.counters = reinterpret_cast<unsigned*>(c.take(64));
   }
   s.bytes = c.off;
   return s;
@@ -156,7 +159,8 @@ Saved carve_saved(const aa_dims& d, void* base) {
 
 struct BwdScratch {
   float *du, *ds, *dq, *dr, *dP, *da, *dcell, *dhs, *dgates, *dx, *dh_rec, *dc_rec, *dV;
-  bf16 *dS16, *dq16, *dr16, *dP16, *da16, *dgates16;
+  bf16 *dS16, *dq16, *dr16, *dP16, *da16, *dgates16, *whhT16;
+  unsigned* counters;
   size_t bytes;
 };
 
@@ -186,6 +190,8 @@ BwdScratch carve_bwd(const aa_dims& d, void* base) {
     s.dP16 = h.take((size_t)d.B * d.k * ap);
     s.da16 = h.take(N * H);
     s.dgates16 = h.take(N * 4 * H);
+    s.whhT16 = h.take(4 * H * H);
+    s.counters = reinterpret_cast<unsigned*>(c.take(64));
   }
   s.bytes = c.off;
   return s;
@@ -500,7 +506,15 @@ int aa_decoder_forward(const aa_dims* d, const aa_weights* w, const float* V, co
   if (!h0 || !c0) AA_CHECK_CUDA(cudaMemsetAsync(sv.zeros, 0, sizeof(float) * (size_t)B * H, st));
   AA_CHECK_CUDA(cudaMemset2DAsync(sv.hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, B, st));   // h~_0 = 0 (Q2)
   // recurrence                                                 baseline_attention.py:167-178
-  for (int t = 0; t < T; ++t) {
+  const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
+  if (seq) {   // all T steps in one cooperative launch (lstm_seq.cu)
+    LstmSeqFwd ls{};
+    ls.B = B; ls.T = T; ls.H = H; ls.w_hh = w->w_hh; ls.xg = sv.xg; ls.c0 = c0; ls.h016 = sv.h016;
+    ls.hiddens = sv.hiddens; ls.cells = sv.cells; ls.acts = sv.acts; ls.hs_prev = sv.hs_prev;
+    ls.hid16 = sv.hid16; ls.hsprev16 = sv.hsprev16; ls.whh_packed16 = sv.whh_pack16; ls.counters = sv.counters;
+    AA_PROF("lstm_seq_fwd", st, launch_lstm_seq_fwd(ls, st));
+  }
+  for (int t = 0; t < T && !seq; ++t) {
     const Mat hp = t == 0 ? M2(h0 ? h0 : sv.zeros, H, sv.h016, H)
                           : M2(sv.hiddens + (size_t)(t - 1) * H, (long long)T * H, tc ? sv.hid16 + (size_t)(t - 1) * H : nullptr,
                                (long long)T * H);
@@ -563,13 +577,13 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
   const Mat Wv = M2(w->att_wv, H, h.att_wv, H), Wg = M2(w->att_wg, H, h.att_wg, H), Ws = M2(w->att_ws, H, h.att_ws, H);
   const Mat Wp = M2(w->mlp_w, H, h.mlp_w, H);
   const Mat X = M2(sv.x, 2 * E, sv.x16, 2 * E);
-  if (tc) AA_PROF("cast_dscores", st, launch_cast2d(d_scores, Vc, sc.dS16, Vc, N, Vc, st));
+  // db_p = column sums of dS, fused with the bf16 cast of dS                     adaptive_attention.py:132
+  AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, N, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
   const Mat dS = M2(d_scores, Vc, sc.dS16, Vc);
 
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
   AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, nullptr, 0));
   AA_TRY(mm_tn(cx, "gemm_vocab_dw", Vc, H, N, dS, M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
-  AA_PROF("colsum", st, launch_colsum(d_scores, Vc, N, Vc, gw->mlp_b, nullptr, st));
   // attention                                                   adaptive_attention.py:34-56
   AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, st));
   AttenBwdArgs ab{};
@@ -599,7 +613,16 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
     AA_CHECK_CUDA(cudaMemsetAsync(gw->sen_wh, 0, sizeof(float) * (size_t)H * H, st));   // h~ = 0: no gradient (Q3)
   }
   // BPTT                                                        baseline_attention.py:167-178
-  for (int t = T - 1; t >= 0; --t) {
+  const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
+  if (seq) {
+    LstmSeqBwd ls{};
+    ls.B = B; ls.T = T; ls.H = H; ls.w_hh = w->w_hh;
+    ls.dh_attn = sc.du; ls.dhs = T > 1 ? sc.dhs : nullptr; ls.dcell = sc.dcell; ls.d_hT = d_hT; ls.d_cT = d_cT;
+    ls.acts = sv.acts; ls.cells = sv.cells; ls.c0 = c0; ls.dgates = sc.dgates; ls.dgates16 = sc.dgates16;
+    ls.dh0 = dh0; ls.dc0 = dc0; ls.whhT16 = sc.whhT16; ls.counters = sc.counters;
+    AA_PROF("lstm_seq_bwd", st, launch_lstm_seq_bwd(ls, st));
+  }
+  for (int t = T - 1; t >= 0 && !seq; --t) {
     const float* dh_rec_in = t == T - 1 ? d_hT : sc.dh_rec;
     const float* dc_rec_in = t == T - 1 ? d_cT : sc.dc_rec;
     const float* dhs_next = (T > 1 && t + 1 < T) ? sc.dhs + (size_t)(t + 1) * H : nullptr;
@@ -615,8 +638,8 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
                  M2(sc.dgates + (size_t)t * 4 * H, (long long)T * 4 * H, tc ? sc.dgates16 + (size_t)t * 4 * H : nullptr, (long long)T * 4 * H),
                  Whh, sc.dh_rec, H, nullptr, 0));
   }
-  if (dh0) AA_TRY(launch_copy2d(dh0, H, sc.dh_rec, H, B, H, st));
-  if (dc0) AA_TRY(launch_copy2d(dc0, H, sc.dc_rec, H, B, H, st));
+  if (dh0 && !seq) AA_TRY(launch_copy2d(dh0, H, sc.dh_rec, H, B, H, st));
+  if (dc0 && !seq) AA_TRY(launch_copy2d(dc0, H, sc.dc_rec, H, B, H, st));
   // LSTM parameter gradients, batched over all steps
   const Mat dG = M2(sc.dgates, 4 * H, sc.dgates16, 4 * H);
   AA_TRY(mm_tn(cx, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, false));

@@ -8,101 +8,60 @@
 //
 // Descriptor encodings follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction
 // descriptor" tables (same bit layout as cute::UMMA::SmemDescriptor / InstrDescriptor).
-#include <cuda.h>
-
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace aa {
 
 namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// 2-D tensor map over a row-major [rows, cols] array (cols contiguous, row stride ld elements):
+// box = {128 bytes of the contiguous dim, box_rows}, 128B swizzle, zero fill out of bounds.
+int make_map(CUtensorMap* map, const void* base, int es, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return AA_ERR_CUDA;
+  }
+  AA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tcgen05 GEMM: operand base must be 16-byte aligned");
+  AA_REQUIRE((ld * es) % 16 == 0, "tcgen05 GEMM: operand row stride must be a multiple of 16 bytes (ld=%lld, es=%d)", ld, es);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)(ld * es)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld es=%d)", (int)r, rows, cols, ld, es);
+    return AA_ERR_CUDA;
+  }
+  return AA_OK;
+}
+
+namespace {
+
+using namespace tc;
 
 constexpr int BM = 128;
 constexpr int TC_THREADS = 192;   // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (TMEM lane quarter = warp % 4)
-
-// ---- PTX wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Spin guard: a mis-programmed pipeline must fault (launch error) instead of hanging the GPU.
-#ifndef AA_SPIN_LIMIT_CYCLES
-#define AA_SPIN_LIMIT_CYCLES 4000000000ll   // ~2 s at 1.9 GHz
-#endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  long long t0 = 0;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!done) {
-      if (t0 == 0) t0 = clock64();
-      else if (clock64() - t0 > AA_SPIN_LIMIT_CYCLES) __trap();
-    }
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <bool TF32>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (TF32) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell)
-//   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
-//   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1     bits [61,64) layout = 2 (128B swizzle)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 struct TcEpilogue {
   int M, N, K;
@@ -214,62 +173,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_commit(tmem_full);         // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> (smem transpose) -> coalesced global stores =====
+    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns); storing that directly
+    // touches 32 different 128-byte lines per instruction.  Each warp transposes its 32x32 chunk through a
+    // private smem tile (row stride 36 floats: conflict-free float4 writes and reads) so that one store
+    // instruction writes 4 complete 128-byte row segments: lane -> (row it*4 + lane/8, columns 4*(lane%8)..+3).
     const int q = warp & 3;         // TMEM lane quarter this warp may access
+    constexpr int TS = 36;
+    float* tbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15) + (warp - 2) * (32 * TS);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < e.M;
+    const int row0 = m0 + q * 32;
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       const int nb = n0 + c * 32;
-      if (!row_ok || nb >= e.N) continue;
-      float v[32];
+      if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const bool full = nb + 32 <= e.N;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(&tbuf[lane * TS + j]) =
+            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      __syncwarp();
+      const int n = nb + c4;
+      float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
       if (e.bias1 || e.bias2) {
+        float bb[4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || nb + j < e.N) v[j] += (e.bias1 ? __ldg(e.bias1 + nb + j) : 0.f) + (e.bias2 ? __ldg(e.bias2 + nb + j) : 0.f);
+        for (int j = 0; j < 4; ++j)
+          bb[j] = (n + j < e.N) ? (e.bias1 ? __ldg(e.bias1 + n + j) : 0.f) + (e.bias2 ? __ldg(e.bias2 + n + j) : 0.f) : 0.f;
+        badd = make_float4(bb[0], bb[1], bb[2], bb[3]);
       }
+      const bool vec32 = (n + 3 < e.N) && ((e.ldd32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D32) & 15) == 0);
+      const bool vecc = (n + 3 < e.N) && ((e.ldcin & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Cin) & 15) == 0);
+      const bool vec16 = (n + 3 < e.N) && ((e.ldd16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D16) & 7) == 0);
+      float4 cin[8];
       if (e.Cin) {
-        const float* cp = e.Cin + (long long)row * e.ldcin + nb;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || nb + j < e.N) v[j] += e.beta * cp[j];
-      }
-      if (e.D32) {
-        float* dp = e.D32 + (long long)row * e.ldd32 + nb;
-        if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < e.N) dp[j] = v[j];
-        }
-      }
-      if (e.D16) {
-        __nv_bfloat16* dp = e.D16 + (long long)row * e.ldd16 + nb;
-        if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(dp + j) = pk;
+        for (int it = 0; it < 8; ++it) {
+          const long long row = row0 + it * 4 + rsub;
+          cin[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < e.M && n < e.N) {
+            const float* cp = e.Cin + row * e.ldcin + n;
+            if (vecc) cin[it] = *reinterpret_cast<const float4*>(cp);
+            else {
+              cin[it].x = cp[0];
+              if (n + 1 < e.N) cin[it].y = cp[1];
+              if (n + 2 < e.N) cin[it].z = cp[2];
+              if (n + 3 < e.N) cin[it].w = cp[3];
+            }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < e.N) dp[j] = __float2bfloat16(v[j]);
         }
       }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long row = row0 + it * 4 + rsub;
+        float4 v = *reinterpret_cast<const float4*>(&tbuf[(it * 4 + rsub) * TS + c4]);
+        v.x += badd.x; v.y += badd.y; v.z += badd.z; v.w += badd.w;
+        if (e.Cin) { v.x += e.beta * cin[it].x; v.y += e.beta * cin[it].y; v.z += e.beta * cin[it].z; v.w += e.beta * cin[it].w; }
+        if (row < e.M && n < e.N) {
+          if (e.D32) {
+            float* dp = e.D32 + row * e.ldd32 + n;
+            if (vec32) *reinterpret_cast<float4*>(dp) = v;
+            else {
+              dp[0] = v.x;
+              if (n + 1 < e.N) dp[1] = v.y;
+              if (n + 2 < e.N) dp[2] = v.z;
+              if (n + 3 < e.N) dp[3] = v.w;
+            }
+          }
+          if (e.D16) {
+            __nv_bfloat16* dp = e.D16 + row * e.ldd16 + n;
+            if (vec16) {
+              __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&a);
+              pk.y = *reinterpret_cast<uint32_t*>(&b);
+              *reinterpret_cast<uint2*>(dp) = pk;
+            } else {
+              dp[0] = __float2bfloat16(v.x);
+              if (n + 1 < e.N) dp[1] = __float2bfloat16(v.y);
+              if (n + 2 < e.N) dp[2] = __float2bfloat16(v.z);
+              if (n + 3 < e.N) dp[3] = __float2bfloat16(v.w);
+            }
+          }
+        }
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -281,46 +272,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- host side ---------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D tensor map over a row-major [rows, cols] array (cols contiguous, row stride ld elements):
-// box = {128 bytes of the contiguous dim, box_rows}, 128B swizzle, zero fill out of bounds.
-int make_map(CUtensorMap* map, const void* base, int es, long long rows, long long cols, long long ld, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled is not available from this driver");
-    return AA_ERR_CUDA;
-  }
-  AA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tcgen05 GEMM: operand base must be 16-byte aligned");
-  AA_REQUIRE((ld * es) % 16 == 0, "tcgen05 GEMM: operand row stride must be a multiple of 16 bytes (ld=%lld, es=%d)", ld, es);
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)(ld * es)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim,
-                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld es=%d)", (int)r, rows, cols, ld, es);
-    return AA_ERR_CUDA;
-  }
-  return AA_OK;
-}
-
 template <int BN, int ES, int STAGES, bool A_MN, bool B_MN>
 int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int BK = 128 / ES;
@@ -334,7 +285,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   e.M = g.M; e.N = g.N; e.K = g.K;
   e.D32 = g.D32; e.ldd32 = g.ldd32; e.D16 = g.D16; e.ldd16 = g.ldd16;
   e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
-  constexpr size_t smem = (size_t)STAGES * (BM * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 32 + 4 * 32 * 36 * 4 + 1024;
   auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {

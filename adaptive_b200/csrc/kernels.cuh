@@ -30,6 +30,9 @@ int launch_lstm_cell_bwd(const float* dh_attn, long long ld_dh, const float* dhs
                          int H, cudaStream_t s);
 // out[n] = sum_m X[m, n]   (column sums; bias gradients).  out2 (optional) receives a copy.
 int launch_colsum(const float* X, long long ldx, int M, int N, float* out, float* out2, cudaStream_t s);
+// same, and writes the bf16 mirror X16 (row stride ld16) of X in the same pass when X16 != null
+int launch_colsum_cast(const float* X, long long ldx, int M, int N, float* out, float* out2, __nv_bfloat16* X16, long long ld16,
+                       cudaStream_t s);
 // dE[cap[row], :] += dx[row, 0:E]  (dE pre-zeroed) ; dvg[b, :] = sum_t dx[b,t,E:2E]
 int launch_embed_bwd(const long long* cap, const float* dx, float* dE, float* dvg, int B, int T, int E, int Vc,
                      cudaStream_t s);
@@ -69,6 +72,32 @@ struct TcGemmArgs {
   const float* bias1; const float* bias2;
 };
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
+
+// ---- lstm_seq.cu (persistent recurrence, bf16 tensor-core mode) -----------------------------
+// true when the one-launch recurrence kernels can run this shape (H % 64 == 0 and the CTAs fit the chip)
+bool lstm_seq_supported(int B, int H, int* units_fwd);
+struct LstmSeqFwd {
+  int B, T, H;
+  const float* w_hh;                  // [4H,H] fp32 master weights (re-packed to bf16 inside)
+  const float* xg;                    // [B,T,4H] input-half gate pre-activations incl. biases
+  const float* c0;                    // [B,H] or null
+  const __nv_bfloat16* h016;          // [B,H] bf16 initial hidden state
+  float *hiddens, *cells, *acts, *hs_prev;
+  __nv_bfloat16 *hid16, *hsprev16;
+  __nv_bfloat16* whh_packed16;        // scratch [4H*H]
+  unsigned* counters;                 // scratch [ceil(B/128)]
+};
+int launch_lstm_seq_fwd(const LstmSeqFwd& p, cudaStream_t s);
+struct LstmSeqBwd {
+  int B, T, H;
+  const float* w_hh;
+  const float *dh_attn, *dhs, *dcell, *d_hT, *d_cT, *acts, *cells, *c0;
+  float* dgates; __nv_bfloat16* dgates16;
+  float *dh0, *dc0;
+  __nv_bfloat16* whhT16;              // scratch [H*4H]
+  unsigned* counters;
+};
+int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t s);
 
 // ---- atten.cu --------------------------------------------------------------------------
 struct AttenFwdArgs {

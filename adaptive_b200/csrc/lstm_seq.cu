@@ -1,0 +1,523 @@
+// Persistent LSTM recurrence kernels (bf16 tensor-core mode): all T steps of the forward
+// recurrence (baseline_attention.py:167-178) and of its BPTT run inside ONE cooperative launch
+// each, instead of 2 launches per step.
+//
+//  * every CTA keeps its slice of W_hh resident in shared memory (TMA-loaded once) for all steps;
+//  * per step it TMA-streams the previous state (h_{t-1}, resp. dgates_{t+1}) from L2 through an
+//    mbarrier ring, runs the slice GEMM on tcgen05 (fp32 accumulator in TMEM), and applies the LSTM
+//    cell (resp. its gradient) in the epilogue warps straight out of tensor memory, with the cell
+//    state c (resp. dc) living in registers across all steps;
+//  * steps are separated by a release/acquire grid barrier per 128-row group (rows are independent
+//    sequences), so the launch must be cooperative (all CTAs co-resident).
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace aa {
+
+namespace {
+
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int SEQ_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int SEQ_STAGES = 4;
+constexpr uint32_t A_STAGE_BYTES = 128 * 128;   // 128 rows x 64 bf16
+
+__device__ __forceinline__ void grid_barrier_wait(const unsigned* counter, unsigned target) {
+  long long t0 = 0;
+  while (ld_acquire_gpu(counter) < target) {
+    __nanosleep(40);
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > AA_SPIN_LIMIT_CYCLES) __trap();
+  }
+}
+
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// packed 4 x bf16 store
+__device__ __forceinline__ void st_bf16x4(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+struct SeqFwdArgs {
+  int B, T, H;
+  const float* xg;   // [B,T,4H] input-half gate pre-activations incl. both biases
+  const float* c0;   // [B,H] or null
+  float *hiddens, *cells, *acts, *hs_prev;   // [B,T,H] [B,T,H] [B,T,4,H] [B,T,H]
+  bf16 *hid16, *hsprev16;                    // bf16 mirrors
+  unsigned* counters;                        // [row groups], zeroed by the launcher
+};
+
+// U hidden units per CTA -> UMMA N = 4U gate columns, packed unit-major: column n = u*4 + g.
+template <int U>
+__global__ void __launch_bounds__(SEQ_THREADS, 1)
+lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH0,
+                    const __grid_constant__ CUtensorMap tmH, const SeqFwdArgs a) {
+  constexpr int N = 4 * U;
+  constexpr int TCOLS = N < 32 ? 32 : N;
+  constexpr int CH = N < 32 ? N : 32;           // TMEM columns per epilogue chunk
+  constexpr int UC = CH / 4;                    // units per chunk
+  constexpr uint32_t W_KB_BYTES = N * 128;      // one 64-wide k-block of the weight slice
+  const int KB = a.H / 64;
+  const int C = gridDim.x;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                        // [STAGES][16 KB]
+  uint8_t* sW = smem + SEQ_STAGES * A_STAGE_BYTES;           // [KB][N*128]  (N*128 is a multiple of 1024 for N >= 8... see launcher)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)KB * W_KB_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + SEQ_STAGES;
+  uint64_t* w_full = bars + 2 * SEQ_STAGES;
+  uint64_t* tmem_full = w_full + 1;
+  uint64_t* tmem_empty = w_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x, rg = blockIdx.y;
+  const int m0 = rg * 128;
+  const unsigned* counter = a.counters + rg;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SEQ_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(w_full, 1);
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weight slice: rows [c*N, (c+1)*N) of the packed W_hh, all k-blocks
+      mbar_expect_tx(w_full, (uint32_t)KB * W_KB_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + (size_t)kb * W_KB_BYTES, &tmW, kb * 64, c * N, w_full);
+      int it = 0;
+      for (int t = 0; t < a.T; ++t) {
+        if (t > 0) {
+          grid_barrier_wait(counter, (unsigned)t * C);   // every CTA of this row group has published h_{t-1}
+          fence_proxy_async();
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % SEQ_STAGES;
+          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES);
+          if (t == 0) tma_load_2d(sA + s * A_STAGE_BYTES, &tmH0, kb * 64, m0, &full_bar[s]);
+          else        tma_load_2d(sA + s * A_STAGE_BYTES, &tmH, (t - 1) * a.H + kb * 64, m0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(w_full, 0);
+      int it = 0;
+      for (int t = 0; t < a.T; ++t) {
+        mbar_wait(tmem_empty, (t & 1) ^ 1);      // epilogue has drained the previous step's accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % SEQ_STAGES;
+          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sW + (size_t)kb * W_KB_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma<false>(tmem_base, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(tmem_full);
+      }
+    }
+  } else {
+    // ===== epilogue warps: LSTM cell out of tensor memory; thread = batch row, cell state in registers =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool valid = row < a.B;
+    const int H = a.H, T = a.T;
+    const int j0 = c * U;                        // first hidden unit of this CTA
+    float creg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) creg[u] = (valid && a.c0) ? a.c0[(long long)row * H + j0 + u] : 0.f;
+    for (int t = 0; t < T; ++t) {
+      const long long bt = (long long)row * T + t;
+      mbar_wait(tmem_full, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < N / CH; ++ch) {
+        // input-half pre-activations for this chunk's units (independent of the MMA)
+        float4 x4[4][UC / 4];
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int v = 0; v < UC / 4; ++v)
+              x4[g][v] = *reinterpret_cast<const float4*>(a.xg + bt * 4 * H + (long long)g * H + j0 + ch * UC + v * 4);
+        }
+        uint32_t r[CH];
+        tmem_ld<CH>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CH), r);
+        if (ch == N / CH - 1) {                  // accumulator fully read: hand TMEM back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        if (valid) {
+#pragma unroll
+          for (int v = 0; v < UC / 4; ++v) {
+            float hn[4], cn[4], ig[4], fg[4], gg[4], og[4];
+            const float xi[4] = {x4[0][v].x, x4[0][v].y, x4[0][v].z, x4[0][v].w};
+            const float xf[4] = {x4[1][v].x, x4[1][v].y, x4[1][v].z, x4[1][v].w};
+            const float xc[4] = {x4[2][v].x, x4[2][v].y, x4[2][v].z, x4[2][v].w};
+            const float xo[4] = {x4[3][v].x, x4[3][v].y, x4[3][v].z, x4[3][v].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int ul = v * 4 + e;          // unit within chunk; TMEM column = ul*4 + gate
+              const int u = ch * UC + ul;
+              ig[e] = sigmoidf_acc(__uint_as_float(r[ul * 4 + 0]) + xi[e]);
+              fg[e] = sigmoidf_acc(__uint_as_float(r[ul * 4 + 1]) + xf[e]);
+              gg[e] = tanhf(__uint_as_float(r[ul * 4 + 2]) + xc[e]);
+              og[e] = sigmoidf_acc(__uint_as_float(r[ul * 4 + 3]) + xo[e]);
+              cn[e] = fg[e] * creg[u] + ig[e] * gg[e];
+              creg[u] = cn[e];
+              hn[e] = og[e] * tanhf(cn[e]);
+            }
+            const int j = j0 + ch * UC + v * 4;
+            *reinterpret_cast<float4*>(a.hiddens + bt * H + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(a.cells + bt * H + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            st_bf16x4(a.hid16 + bt * H + j, hn[0], hn[1], hn[2], hn[3]);
+            float* ac = a.acts + bt * 4 * H + j;
+            *reinterpret_cast<float4*>(ac) = make_float4(ig[0], ig[1], ig[2], ig[3]);
+            *reinterpret_cast<float4*>(ac + H) = make_float4(fg[0], fg[1], fg[2], fg[3]);
+            *reinterpret_cast<float4*>(ac + 2 * H) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+            *reinterpret_cast<float4*>(ac + 3 * H) = make_float4(og[0], og[1], og[2], og[3]);
+            if (t + 1 < T) {
+              *reinterpret_cast<float4*>(a.hs_prev + (bt + 1) * H + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+              st_bf16x4(a.hsprev16 + (bt + 1) * H + j, hn[0], hn[1], hn[2], hn[3]);
+            }
+          }
+        }
+      }
+      // publish h_t: generic-proxy stores -> visible at gpu scope -> one release-arrive per CTA
+      __threadfence();
+      fence_proxy_async();
+      epilogue_bar();
+      if (warp == 2 && lane == 0 && t + 1 < T) red_release_gpu_add(a.counters + rg, 1u);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TCOLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BPTT
+// ---------------------------------------------------------------------------------------------
+struct SeqBwdArgs {
+  int B, T, H;
+  const float *dh_attn, *dhs, *dcell;     // [B,T,H]: batched (non-recurrent) gradient contributions; dhs may be null (T == 1)
+  const float *d_hT, *d_cT;               // [B,H] or null
+  const float *acts, *cells, *c0;         // saved forward state; c0 may be null (zeros)
+  float* dgates; bf16* dgates16;          // [B,T,4H]
+  float *dh0, *dc0;                       // [B,H] (may be null)
+  unsigned* counters;
+};
+
+// 16 hidden units per CTA: dh_rec[:, j-slice] = dgates_{t+1} [B,4H] * W_hh[:, j-slice]  (K = 4H)
+__global__ void __launch_bounds__(SEQ_THREADS, 1)
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, const SeqBwdArgs a) {
+  constexpr int U = 16, N = 16, TCOLS = 32;
+  constexpr uint32_t W_KB_BYTES = N * 128;
+  const int KB = 4 * a.H / 64;
+  const int C = gridDim.x;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + SEQ_STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)KB * W_KB_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + SEQ_STAGES;
+  uint64_t* w_full = bars + 2 * SEQ_STAGES;
+  uint64_t* tmem_full = w_full + 1;
+  uint64_t* tmem_empty = w_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x, rg = blockIdx.y;
+  const int m0 = rg * 128;
+  const int T = a.T, H = a.H;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SEQ_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(w_full, 1);
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // GEMM i (i = 1..T) consumes dgates of step t = T - i and produces dh_rec for step t - 1 (dh0 when t == 0).
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)KB * W_KB_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + (size_t)kb * W_KB_BYTES, &tmWT, kb * 64, c * U, w_full);
+      int it = 0;
+      for (int i = 1; i <= T; ++i) {
+        const int t = T - i;
+        grid_barrier_wait(a.counters + rg, (unsigned)i * C);     // dgates_t complete in this row group
+        fence_proxy_async();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % SEQ_STAGES;
+          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES);
+          tma_load_2d(sA + s * A_STAGE_BYTES, &tmG, t * 4 * H + kb * 64, m0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(w_full, 0);
+      int it = 0;
+      for (int i = 1; i <= T; ++i) {
+        mbar_wait(tmem_empty, ((i - 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % SEQ_STAGES;
+          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sW + (size_t)kb * W_KB_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma<false>(tmem_base, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(tmem_full);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool valid = row < a.B;
+    const int j0 = c * U;
+    float dcreg[U];     // dc flowing from step t+1 into step t
+    float dhrec[U];     // dh flowing from step t+1 into step t
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      dcreg[u] = (valid && a.d_cT) ? a.d_cT[(long long)row * H + j0 + u] : 0.f;
+      dhrec[u] = (valid && a.d_hT) ? a.d_hT[(long long)row * H + j0 + u] : 0.f;
+    }
+    for (int i = 0; i <= T; ++i) {
+      const int t = T - 1 - i;
+      if (i >= 1) {
+        mbar_wait(tmem_full, (i - 1) & 1);
+        tc_fence_after();
+        uint32_t r[16];
+        tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16), r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+#pragma unroll
+        for (int u = 0; u < U; ++u) dhrec[u] = __uint_as_float(r[u]);
+      }
+      if (t < 0) break;
+      if (valid) {
+        const long long bt = (long long)row * T + t;
+#pragma unroll
+        for (int v = 0; v < U / 4; ++v) {
+          const int j = j0 + v * 4;
+          const float4 dha = *reinterpret_cast<const float4*>(a.dh_attn + bt * H + j);
+          float4 dhs = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.dhs && t + 1 < T) dhs = *reinterpret_cast<const float4*>(a.dhs + (bt + 1) * H + j);
+          const float4 dcl = *reinterpret_cast<const float4*>(a.dcell + bt * H + j);
+          const float* ac = a.acts + bt * 4 * H + j;
+          const float4 ig4 = *reinterpret_cast<const float4*>(ac), fg4 = *reinterpret_cast<const float4*>(ac + H);
+          const float4 gg4 = *reinterpret_cast<const float4*>(ac + 2 * H), og4 = *reinterpret_cast<const float4*>(ac + 3 * H);
+          const float4 ce4 = *reinterpret_cast<const float4*>(a.cells + bt * H + j);
+          float4 cp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t > 0) cp4 = *reinterpret_cast<const float4*>(a.cells + (bt - 1) * H + j);
+          else if (a.c0) cp4 = *reinterpret_cast<const float4*>(a.c0 + (long long)row * H + j);
+          const float dhav[4] = {dha.x + dhs.x, dha.y + dhs.y, dha.z + dhs.z, dha.w + dhs.w};
+          const float dclv[4] = {dcl.x, dcl.y, dcl.z, dcl.w};
+          const float igv[4] = {ig4.x, ig4.y, ig4.z, ig4.w}, fgv[4] = {fg4.x, fg4.y, fg4.z, fg4.w};
+          const float ggv[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, ogv[4] = {og4.x, og4.y, og4.z, og4.w};
+          const float cev[4] = {ce4.x, ce4.y, ce4.z, ce4.w}, cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+          float d0[4], d1[4], d2[4], d3[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int u = v * 4 + e;
+            const float dh = dhav[e] + dhrec[u];
+            const float tcv = tanhf(cev[e]);
+            const float dc = dclv[e] + dcreg[u] + dh * ogv[e] * (1.f - tcv * tcv);
+            d0[e] = dc * ggv[e] * igv[e] * (1.f - igv[e]);
+            d1[e] = dc * cpv[e] * fgv[e] * (1.f - fgv[e]);
+            d2[e] = dc * igv[e] * (1.f - ggv[e] * ggv[e]);
+            d3[e] = dh * tcv * ogv[e] * (1.f - ogv[e]);
+            dcreg[u] = dc * fgv[e];
+          }
+          float* dg = a.dgates + bt * 4 * H + j;
+          bf16* dg16 = a.dgates16 + bt * 4 * H + j;
+          *reinterpret_cast<float4*>(dg) = make_float4(d0[0], d0[1], d0[2], d0[3]);
+          *reinterpret_cast<float4*>(dg + H) = make_float4(d1[0], d1[1], d1[2], d1[3]);
+          *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+          *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(d3[0], d3[1], d3[2], d3[3]);
+          st_bf16x4(dg16, d0[0], d0[1], d0[2], d0[3]);
+          st_bf16x4(dg16 + H, d1[0], d1[1], d1[2], d1[3]);
+          st_bf16x4(dg16 + 2 * H, d2[0], d2[1], d2[2], d2[3]);
+          st_bf16x4(dg16 + 3 * H, d3[0], d3[1], d3[2], d3[3]);
+        }
+      }
+      __threadfence();
+      fence_proxy_async();
+      epilogue_bar();
+      if (warp == 2 && lane == 0) red_release_gpu_add(a.counters + rg, 1u);
+    }
+    // after the last GEMM: dhrec = dgates_0 W_hh = dh0 ; dcreg = dc0
+    if (valid) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (a.dh0) a.dh0[(long long)row * H + j0 + u] = dhrec[u];
+        if (a.dc0) a.dc0[(long long)row * H + j0 + u] = dcreg[u];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TCOLS) : "memory");
+  }
+}
+
+// ---- weight re-layouts (fp32 master -> bf16 operand) -----------------------------------------
+// forward: Wp[(c*4U + u*4 + g), k] = W_hh[g*H + c*U + u, k]
+__global__ void pack_whh_fwd_kernel(const float* __restrict__ w_hh, bf16* __restrict__ wp, int H, int U) {
+  const int n = blockIdx.x;                 // packed row
+  const int c = n / (4 * U), rem = n % (4 * U), u = rem / 4, g = rem % 4;
+  const float* src = w_hh + ((long long)g * H + c * U + u) * H;
+  bf16* dst = wp + (long long)n * H;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) dst[k] = __float2bfloat16(src[k]);
+}
+// backward: WT[j, n] = W_hh[n, j]   ([H, 4H] bf16), 32x32 smem tiles
+__global__ void transpose_whh_kernel(const float* __restrict__ w_hh, bf16* __restrict__ wt, int H) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = w_hh[(long long)(n0 + r) * H + j0 + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) wt[(long long)(j0 + r) * 4 * H + n0 + threadIdx.x] = __float2bfloat16(tile[threadIdx.x][r]);
+}
+
+template <int U>
+int launch_fwd_u(const LstmSeqFwd& p, int C, int RG, cudaStream_t st) {
+  constexpr int N = 4 * U;
+  const int H = p.H, KB = H / 64;
+  pack_whh_fwd_kernel<<<4 * H, 128, 0, st>>>(p.w_hh, p.whh_packed16, H, U);
+  AA_CHECK_LAUNCH("pack_whh_fwd");
+  AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
+  CUtensorMap tmW, tmH0, tmH;
+  AA_TRY(make_map(&tmW, p.whh_packed16, 2, 4LL * H, H, H, N));
+  AA_TRY(make_map(&tmH0, p.h016, 2, p.B, H, H, 128));
+  AA_TRY(make_map(&tmH, p.hid16, 2, p.B, (long long)p.T * H, (long long)p.T * H, 128));
+  SeqFwdArgs a{};
+  a.B = p.B; a.T = p.T; a.H = H; a.xg = p.xg; a.c0 = p.c0;
+  a.hiddens = p.hiddens; a.cells = p.cells; a.acts = p.acts; a.hs_prev = p.hs_prev; a.hid16 = p.hid16; a.hsprev16 = p.hsprev16;
+  a.counters = p.counters;
+  const size_t smem = (size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)KB * N * 128 + 16 * 8 + 16 + 1024;
+  auto kern = lstm_seq_fwd_kernel<U>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  void* args[] = {(void*)&tmW, (void*)&tmH0, (void*)&tmH, (void*)&a};
+  AA_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(C, RG), dim3(SEQ_THREADS), args, smem, st));
+  count_launch();
+  return AA_OK;
+}
+
+}  // namespace
+
+bool lstm_seq_supported(int B, int H, int* units_fwd) {
+  if (H % 64 != 0 || H < 64 || B < 1) return false;
+  const int RG = ceil_div(B, 128);
+  const int sms = num_sms();
+  if ((H / 16) * RG > sms) return false;                         // backward: 16 units per CTA
+  if ((size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)(4 * H / 64) * 16 * 128 > 200 * 1024) return false;
+  for (int U : {4, 8, 16, 32}) {
+    if (H % U) continue;
+    const size_t smem = (size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)(H / 64) * 4 * U * 128;
+    if ((H / U) * RG <= sms && smem <= 200 * 1024) {
+      if (units_fwd) *units_fwd = U;
+      return true;
+    }
+  }
+  return false;
+}
+
+int launch_lstm_seq_fwd(const LstmSeqFwd& p, cudaStream_t st) {
+  int U = 0;
+  AA_REQUIRE(lstm_seq_supported(p.B, p.H, &U), "lstm_seq_fwd: unsupported shape B=%d H=%d", p.B, p.H);
+  const int C = p.H / U, RG = ceil_div(p.B, 128);
+  switch (U) {
+    case 4: return launch_fwd_u<4>(p, C, RG, st);
+    case 8: return launch_fwd_u<8>(p, C, RG, st);
+    case 16: return launch_fwd_u<16>(p, C, RG, st);
+    default: return launch_fwd_u<32>(p, C, RG, st);
+  }
+}
+
+int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
+  AA_REQUIRE(lstm_seq_supported(p.B, p.H, nullptr), "lstm_seq_bwd: unsupported shape B=%d H=%d", p.B, p.H);
+  const int H = p.H, KB = 4 * H / 64, C = H / 16, RG = ceil_div(p.B, 128);
+  transpose_whh_kernel<<<dim3(4 * H / 32, H / 32), dim3(32, 8), 0, st>>>(p.w_hh, p.whhT16, H);
+  AA_CHECK_LAUNCH("transpose_whh");
+  AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
+  CUtensorMap tmWT, tmG;
+  AA_TRY(make_map(&tmWT, p.whhT16, 2, H, 4LL * H, 4LL * H, 16));
+  AA_TRY(make_map(&tmG, p.dgates16, 2, p.B, (long long)p.T * 4 * H, (long long)p.T * 4 * H, 128));
+  SeqBwdArgs a{};
+  a.B = p.B; a.T = p.T; a.H = H;
+  a.dh_attn = p.dh_attn; a.dhs = p.dhs; a.dcell = p.dcell; a.d_hT = p.d_hT; a.d_cT = p.d_cT;
+  a.acts = p.acts; a.cells = p.cells; a.c0 = p.c0; a.dgates = p.dgates; a.dgates16 = p.dgates16; a.dh0 = p.dh0; a.dc0 = p.dc0;
+  a.counters = p.counters;
+  const size_t smem = (size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)KB * 16 * 128 + 16 * 8 + 16 + 1024;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    AA_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  void* args[] = {(void*)&tmWT, (void*)&tmG, (void*)&a};
+  AA_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lstm_seq_bwd_kernel, dim3(C, RG), dim3(SEQ_THREADS), args, smem, st));
+  count_launch();
+  return AA_OK;
+}
+
+}  // namespace aa

@@ -106,25 +106,6 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh_attn, long lon
   dc_out[(long long)b * H + j] = dc * fg;
 }
 
-// block (32, 8): 32 columns per block, rows strided by 8, smem tree over y
-__global__ void colsum_kernel(const float* __restrict__ X, long long ldx, int M, int N, float* __restrict__ out,
-                              float* __restrict__ out2) {
-  __shared__ float red[8][33];
-  const int n = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.f;
-  if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) acc += X[(long long)m * ldx + n];
-  red[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float t = 0.f;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
-    out[n] = t;
-    if (out2) out2[n] = t;
-  }
-}
-
 __global__ void embed_scatter_kernel(const long long* __restrict__ cap, const float* __restrict__ dx, float* __restrict__ dE,
                                      int E, int Vc) {
   const int row = blockIdx.x;
@@ -263,6 +244,57 @@ __global__ void cast2d_kernel(const float* __restrict__ src, long long ld_src, b
   dst[r * ld_dst + c] = __float2bfloat16(src[r * ld_src + c]);
 }
 
+// out[n] += sum_m X[m,n] over this block's row chunk (out pre-zeroed); optionally writes the bf16 mirror of X.
+// block (32,8): 128 columns x RB rows per block, float4 per thread.
+constexpr int CS_RB = 64;
+__global__ void colsum_cast_kernel(const float* __restrict__ X, long long ldx, int M, int N, float* __restrict__ out,
+                                   float* __restrict__ out2, bf16* __restrict__ X16, long long ld16) {
+  __shared__ float4 red[8][32];
+  const int c = blockIdx.x * 128 + threadIdx.x * 4;
+  const int r_begin = blockIdx.y * CS_RB, r_end = min(M, r_begin + CS_RB);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < N) {
+    const bool vec = (c + 3 < N) && ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    for (int m = r_begin + threadIdx.y; m < r_end; m += 8) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* p = X + (long long)m * ldx + c;
+      if (vec) v = *reinterpret_cast<const float4*>(p);
+      else { v.x = p[0]; if (c + 1 < N) v.y = p[1]; if (c + 2 < N) v.z = p[2]; if (c + 3 < N) v.w = p[3]; }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (X16) {
+        bf16* q = X16 + (long long)m * ld16 + c;
+        if (vec && ((ld16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(X16) & 7) == 0)) {
+          __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&a);
+          pk.y = *reinterpret_cast<uint32_t*>(&b);
+          *reinterpret_cast<uint2*>(q) = pk;
+        } else {
+          q[0] = __float2bfloat16(v.x);
+          if (c + 1 < N) q[1] = __float2bfloat16(v.y);
+          if (c + 2 < N) q[2] = __float2bfloat16(v.z);
+          if (c + 3 < N) q[3] = __float2bfloat16(v.w);
+        }
+      }
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) {
+      const float4 u = red[y][threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+    for (int j = 0; j < 4 && c + j < N; ++j) {
+      atomicAdd(out + c + j, tv[j]);
+      if (out2) atomicAdd(out2 + c + j, tv[j]);
+    }
+  }
+}
+
 __global__ void cast_multi_kernel(const CastSegs segs) {
   const int sidx = blockIdx.y;
   const float* __restrict__ src = segs.src[sidx];
@@ -329,8 +361,17 @@ int launch_lstm_cell_bwd(const float* dh_attn, long long ld_dh, const float* dhs
 }
 
 int launch_colsum(const float* X, long long ldx, int M, int N, float* out, float* out2, cudaStream_t s) {
-  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, s>>>(X, ldx, M, N, out, out2);
-  AA_CHECK_LAUNCH("colsum");
+  return launch_colsum_cast(X, ldx, M, N, out, out2, nullptr, 0, s);
+}
+
+int launch_colsum_cast(const float* X, long long ldx, int M, int N, float* out, float* out2, __nv_bfloat16* X16, long long ld16,
+                       cudaStream_t s) {
+  if (N == 0) return AA_OK;
+  AA_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
+  if (out2) AA_CHECK_CUDA(cudaMemsetAsync(out2, 0, sizeof(float) * N, s));
+  if (M == 0) return AA_OK;
+  colsum_cast_kernel<<<dim3(ceil_div(N, 128), ceil_div(M, CS_RB)), dim3(32, 8), 0, s>>>(X, ldx, M, N, out, out2, X16, ld16);
+  AA_CHECK_LAUNCH("colsum_cast");
   return AA_OK;
 }
 
@@ -376,6 +417,11 @@ int launch_copy2d(float* dst, long long ld_dst, const float* src, long long ld_s
 int launch_cast2d(const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst, long long rows, int cols,
                   cudaStream_t s) {
   if (rows * cols == 0) return AA_OK;
+  if (ld_src == cols && ld_dst == cols) {   // contiguous: vectorised 1-D path
+    CastSegs cs{};
+    cs.src[0] = src; cs.dst[0] = dst; cs.n[0] = rows * cols;
+    return launch_cast_multi(cs, 1, s);
+  }
   cast2d_kernel<<<blocks_for(rows * cols), PW_THREADS, 0, s>>>(src, ld_src, dst, ld_dst, rows, cols);
   AA_CHECK_LAUNCH("cast2d");
   return AA_OK;
@@ -383,7 +429,11 @@ int launch_cast2d(const float* src, long long ld_src, __nv_bfloat16* dst, long l
 
 int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s) {
   if (nsegs == 0) return AA_OK;
-  cast_multi_kernel<<<dim3(64, nsegs), PW_THREADS, 0, s>>>(segs);
+  long long nmax = 0;
+  for (int i = 0; i < nsegs; ++i) nmax = segs.n[i] > nmax ? segs.n[i] : nmax;
+  long long nb = (nmax / 4 + PW_THREADS * 4 - 1) / (PW_THREADS * 4);   // ~4 float4 per thread
+  nb = nb < 1 ? 1 : (nb > 1184 ? 1184 : nb);
+  cast_multi_kernel<<<dim3((unsigned)nb, nsegs), PW_THREADS, 0, s>>>(segs);
   AA_CHECK_LAUNCH("cast_multi");
   return AA_OK;
 }

@@ -214,11 +214,22 @@ def packed_targets(captions, lengths: Sequence[int]):
     return captions[:, 1:].reshape(-1)[idx]
 
 
+_ROW_INDEX_CACHE: Dict[tuple, tuple] = {}
+
+
 def pack_scores(scores: torch.Tensor, lengths: Sequence[int]):
-    idx, bs = packed_row_index(lengths, scores.shape[1])
-    row_index = torch.tensor(idx, dtype=torch.int64, device=scores.device)
-    data = _PackRowsFn.apply(scores, row_index)
-    return torch.nn.utils.rnn.PackedSequence(data, torch.tensor(bs, dtype=torch.int64))
+    # the device copy of the row index is cached per (lengths, T, device): repeated shapes cost no
+    # host->device copy, which also keeps the call capturable into a CUDA graph
+    key = (tuple(int(x) for x in lengths), scores.shape[1], scores.device.index)
+    hit = _ROW_INDEX_CACHE.get(key)
+    if hit is None:
+        idx, bs = packed_row_index(lengths, scores.shape[1])
+        hit = (torch.tensor(idx, dtype=torch.int64, device=scores.device), torch.tensor(bs, dtype=torch.int64))
+        if len(_ROW_INDEX_CACHE) > 256:
+            _ROW_INDEX_CACHE.clear()
+        _ROW_INDEX_CACHE[key] = hit
+    data = _PackRowsFn.apply(scores, hit[0])
+    return torch.nn.utils.rnn.PackedSequence(data, hit[1])
 
 
 class _CrossEntropyFn(torch.autograd.Function):
