@@ -76,7 +76,10 @@ struct TcEpilogue {
 //   MN-major operand, R columns     : R*ES/128 TMA boxes {128B/ES elements of MN, BK rows of K} -> BK*128 B each
 template <int BN, int ES, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m,
+               int num_tiles) {
+  // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so neighbouring CTAs share the
+  // B/weight tile in L2).  Two TMEM accumulators: the epilogue of tile i overlaps the TMA/MMA of tile i+1.
   constexpr bool TF32 = (ES == 4);
   constexpr int EPR = 128 / ES;            // elements per 128-byte smem row
   constexpr int BK = EPR;                  // reduction elements per stage (64 bf16 / 32 tf32)
@@ -84,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;   // BM*BK*ES, BN*BK*ES
   constexpr uint32_t A_BOX = A_MN ? BK * 128 : A_BYTES;        // bytes per TMA box
   constexpr uint32_t B_BOX = B_MN ? BK * 128 : B_BYTES;
+  constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -91,11 +95,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb = (e.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -107,12 +111,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);    // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
-                 : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -123,24 +129,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-        uint8_t* a_dst = sA + s * A_BYTES;
-        uint8_t* b_dst = sB + s * B_BYTES;
-        if constexpr (A_MN) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          uint8_t* a_dst = sA + s * A_BYTES;
+          uint8_t* b_dst = sB + s * B_BYTES;
+          if constexpr (A_MN) {
 #pragma unroll
-          for (int j = 0; j < (int)(A_BYTES / A_BOX); ++j) tma_load_2d(a_dst + j * A_BOX, &tmA, m0 + j * EPR, kb * BK, &full_bar[s]);
-        } else {
-          tma_load_2d(a_dst, &tmA, kb * BK, m0, &full_bar[s]);
-        }
-        if constexpr (B_MN) {
+            for (int j = 0; j < (int)(A_BYTES / A_BOX); ++j) tma_load_2d(a_dst + j * A_BOX, &tmA, m0 + j * EPR, kb * BK, &full_bar[s]);
+          } else {
+            tma_load_2d(a_dst, &tmA, kb * BK, m0, &full_bar[s]);
+          }
+          if constexpr (B_MN) {
 #pragma unroll
-          for (int j = 0; j < (int)(B_BYTES / B_BOX); ++j) tma_load_2d(b_dst + j * B_BOX, &tmB, n0 + j * EPR, kb * BK, &full_bar[s]);
-        } else {
-          tma_load_2d(b_dst, &tmB, kb * BK, n0, &full_bar[s]);
+            for (int j = 0; j < (int)(B_BYTES / B_BOX); ++j) tma_load_2d(b_dst + j * B_BOX, &tmB, n0 + j * EPR, kb * BK, &full_bar[s]);
+          } else {
+            tma_load_2d(b_dst, &tmB, kb * BK, n0, &full_bar[s]);
+          }
         }
       }
     }
@@ -152,25 +162,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t fmt = TF32 ? 2u : 1u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major : LBO unused (1), SBO = 8 rows * 128 B; advance 32 B per UMMA_K inside the swizzle atom
-          // MN-major: LBO = bytes between 128B-wide MN chunks (one TMA box), SBO = 8 k-rows * 128 B;
-          //           advance UMMA_K k-rows * 128 B
-          const uint64_t da = A_MN ? make_smem_desc(a_addr + k * UMMA_K * 128, A_BOX, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_smem_desc(b_addr + k * UMMA_K * 128, B_BOX, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
-          tc_mma<TF32>(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major : LBO unused (1), SBO = 8 rows * 128 B; advance 32 B per UMMA_K inside the swizzle atom
+            // MN-major: LBO = bytes between 128B-wide MN chunks (one TMA box), SBO = 8 k-rows * 128 B;
+            //           advance UMMA_K k-rows * 128 B
+            const uint64_t da = A_MN ? make_smem_desc(a_addr + k * UMMA_K * 128, A_BOX, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * UMMA_K * 128, B_BOX, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
+            tc_mma<TF32>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);   // frees the smem stage when these MMAs have read it
         }
-        tc_commit(&empty_bar[s]);   // frees the smem stage when these MMAs have read it
+        tc_commit(&tmem_full[acc]);   // accumulator complete
       }
-      tc_commit(tmem_full);         // accumulator complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (smem transpose) -> coalesced global stores =====
@@ -181,97 +198,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;         // TMEM lane quarter this warp may access
     constexpr int TS = 36;
     float* tbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15) + (warp - 2) * (32 * TS);
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int row0 = m0 + q * 32;
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int acc = lt & 1;
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const int row0 = m0 + q * 32;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      const int nb = n0 + c * 32;
-      if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        if (c == BN / 32 - 1) {     // whole accumulator read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const int nb = n0 + c * 32;
+        if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(&tbuf[lane * TS + j]) =
-            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-      __syncwarp();
-      const int n = nb + c4;
-      float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e.bias1 || e.bias2) {
-        float bb[4];
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(&tbuf[lane * TS + j]) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int n = nb + c4;
+        float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias1 || e.bias2) {
+          float bb[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          bb[j] = (n + j < e.N) ? (e.bias1 ? __ldg(e.bias1 + n + j) : 0.f) + (e.bias2 ? __ldg(e.bias2 + n + j) : 0.f) : 0.f;
-        badd = make_float4(bb[0], bb[1], bb[2], bb[3]);
-      }
-      const bool vec32 = (n + 3 < e.N) && ((e.ldd32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D32) & 15) == 0);
-      const bool vecc = (n + 3 < e.N) && ((e.ldcin & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Cin) & 15) == 0);
-      const bool vec16 = (n + 3 < e.N) && ((e.ldd16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D16) & 7) == 0);
-      float4 cin[8];
-      if (e.Cin) {
+          for (int j = 0; j < 4; ++j)
+            bb[j] = (n + j < e.N) ? (e.bias1 ? __ldg(e.bias1 + n + j) : 0.f) + (e.bias2 ? __ldg(e.bias2 + n + j) : 0.f) : 0.f;
+          badd = make_float4(bb[0], bb[1], bb[2], bb[3]);
+        }
+        const bool vec32 = (n + 3 < e.N) && ((e.ldd32 & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D32) & 15) == 0);
+        const bool vecc = (n + 3 < e.N) && ((e.ldcin & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Cin) & 15) == 0);
+        const bool vec16 = (n + 3 < e.N) && ((e.ldd16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D16) & 7) == 0);
+        float4 cin[8];
+        if (e.Cin) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const long long row = row0 + it * 4 + rsub;
-          cin[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const long long row = row0 + i8 * 4 + rsub;
+            cin[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < e.M && n < e.N) {
+              const float* cp = e.Cin + row * e.ldcin + n;
+              if (vecc) cin[i8] = *reinterpret_cast<const float4*>(cp);
+              else {
+                cin[i8].x = cp[0];
+                if (n + 1 < e.N) cin[i8].y = cp[1];
+                if (n + 2 < e.N) cin[i8].z = cp[2];
+                if (n + 3 < e.N) cin[i8].w = cp[3];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i8 = 0; i8 < 8; ++i8) {
+          const long long row = row0 + i8 * 4 + rsub;
+          float4 v = *reinterpret_cast<const float4*>(&tbuf[(i8 * 4 + rsub) * TS + c4]);
+          v.x += badd.x; v.y += badd.y; v.z += badd.z; v.w += badd.w;
+          if (e.Cin) { v.x += e.beta * cin[i8].x; v.y += e.beta * cin[i8].y; v.z += e.beta * cin[i8].z; v.w += e.beta * cin[i8].w; }
           if (row < e.M && n < e.N) {
-            const float* cp = e.Cin + row * e.ldcin + n;
-            if (vecc) cin[it] = *reinterpret_cast<const float4*>(cp);
-            else {
-              cin[it].x = cp[0];
-              if (n + 1 < e.N) cin[it].y = cp[1];
-              if (n + 2 < e.N) cin[it].z = cp[2];
-              if (n + 3 < e.N) cin[it].w = cp[3];
+            if (e.D32) {
+              float* dp = e.D32 + row * e.ldd32 + n;
+              if (vec32) *reinterpret_cast<float4*>(dp) = v;
+              else {
+                dp[0] = v.x;
+                if (n + 1 < e.N) dp[1] = v.y;
+                if (n + 2 < e.N) dp[2] = v.z;
+                if (n + 3 < e.N) dp[3] = v.w;
+              }
+            }
+            if (e.D16) {
+              __nv_bfloat16* dp = e.D16 + row * e.ldd16 + n;
+              if (vec16) {
+                __nv_bfloat162 a2 = __floats2bfloat162_rn(v.x, v.y), b2 = __floats2bfloat162_rn(v.z, v.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&a2);
+                pk.y = *reinterpret_cast<uint32_t*>(&b2);
+                *reinterpret_cast<uint2*>(dp) = pk;
+              } else {
+                dp[0] = __float2bfloat16(v.x);
+                if (n + 1 < e.N) dp[1] = __float2bfloat16(v.y);
+                if (n + 2 < e.N) dp[2] = __float2bfloat16(v.z);
+                if (n + 3 < e.N) dp[3] = __float2bfloat16(v.w);
+              }
             }
           }
         }
+        __syncwarp();
       }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const long long row = row0 + it * 4 + rsub;
-        float4 v = *reinterpret_cast<const float4*>(&tbuf[(it * 4 + rsub) * TS + c4]);
-        v.x += badd.x; v.y += badd.y; v.z += badd.z; v.w += badd.w;
-        if (e.Cin) { v.x += e.beta * cin[it].x; v.y += e.beta * cin[it].y; v.z += e.beta * cin[it].z; v.w += e.beta * cin[it].w; }
-        if (row < e.M && n < e.N) {
-          if (e.D32) {
-            float* dp = e.D32 + row * e.ldd32 + n;
-            if (vec32) *reinterpret_cast<float4*>(dp) = v;
-            else {
-              dp[0] = v.x;
-              if (n + 1 < e.N) dp[1] = v.y;
-              if (n + 2 < e.N) dp[2] = v.z;
-              if (n + 3 < e.N) dp[3] = v.w;
-            }
-          }
-          if (e.D16) {
-            __nv_bfloat16* dp = e.D16 + row * e.ldd16 + n;
-            if (vec16) {
-              __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&a);
-              pk.y = *reinterpret_cast<uint32_t*>(&b);
-              *reinterpret_cast<uint2*>(dp) = pk;
-            } else {
-              dp[0] = __float2bfloat16(v.x);
-              if (n + 1 < e.N) dp[1] = __float2bfloat16(v.y);
-              if (n + 2 < e.N) dp[2] = __float2bfloat16(v.z);
-              if (n + 3 < e.N) dp[3] = __float2bfloat16(v.w);
-            }
-          }
-        }
-      }
-      __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
   }
 }
 
-// ---- host side ---------------------------------------------------------------------------
 template <int BN, int ES, int STAGES, bool A_MN, bool B_MN>
 int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int BK = 128 / ES;
@@ -285,15 +311,17 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   e.M = g.M; e.N = g.N; e.K = g.K;
   e.D32 = g.D32; e.ldd32 = g.ldd32; e.D16 = g.D16; e.ldd16 = g.ldd16;
   e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
-  constexpr size_t smem = (size_t)STAGES * (BM * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 32 + 4 * 32 * 36 * 4 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + 4 * 32 * 36 * 4 + 1024;
   auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
-  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e);
+  const int tiles_m = ceil_div(g.M, BM), tiles_n = ceil_div(g.N, BN);
+  const int num_tiles = tiles_m * tiles_n;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();     // persistent: one CTA per SM
+  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e, tiles_m, num_tiles);
   AA_CHECK_LAUNCH("gemm_tc_kernel");
   return AA_OK;
 }
@@ -311,9 +339,9 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
   // pick BN so that the grid covers the SMs when the problem allows it
   const long long sms = num_sms();
   const long long mt = ceil_div(g.M, BM);
-  if (mt * ceil_div(g.N, 128) >= sms || g.N > 2048) return launch_major<128, ES, 3>(g, st);
-  if (mt * ceil_div(g.N, 64) >= sms || g.N > 512 || (g.b_mn && ES == 2)) return launch_major<64, ES, 4>(g, st);
-  return launch_major<32, ES, 4>(g, st);   // (an MN-major bf16 B tile needs >= 64 columns: one 128-byte swizzle row)
+  if (mt * ceil_div(g.N, 128) >= sms || g.N > 2048) return launch_major<128, ES, 5>(g, st);
+  if (mt * ceil_div(g.N, 64) >= sms || g.N > 512 || (g.b_mn && ES == 2)) return launch_major<64, ES, 6>(g, st);
+  return launch_major<32, ES, 6>(g, st);   // (an MN-major bf16 B tile needs >= 64 columns: one 128-byte swizzle row)
 }
 
 }  // namespace

@@ -19,20 +19,22 @@ namespace {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
-constexpr int SEQ_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int SEQ_STAGES = 4;
+constexpr int SEQ_THREADS = 192;      // forward: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int BWD_THREADS = 576;      // backward: warp 0 TMA, warp 1 MMA, warps 2-17 epilogue (4 units each)
+constexpr int MAX_STAGES = 8;
+constexpr size_t SEQ_SMEM_BUDGET = 200 * 1024;
 constexpr uint32_t A_STAGE_BYTES = 128 * 128;   // 128 rows x 64 bf16
 
 __device__ __forceinline__ void grid_barrier_wait(const unsigned* counter, unsigned target) {
   long long t0 = 0;
   while (ld_acquire_gpu(counter) < target) {
-    __nanosleep(40);
     if (t0 == 0) t0 = clock64();
     else if (clock64() - t0 > AA_SPIN_LIMIT_CYCLES) __trap();
   }
 }
 
-__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // packed 4 x bf16 store
 __device__ __forceinline__ void st_bf16x4(bf16* p, float a, float b, float c, float d) {
@@ -50,6 +52,7 @@ struct SeqFwdArgs {
   float *hiddens, *cells, *acts, *hs_prev;   // [B,T,H] [B,T,H] [B,T,4,H] [B,T,H]
   bf16 *hid16, *hsprev16;                    // bf16 mirrors
   unsigned* counters;                        // [row groups], zeroed by the launcher
+  int stages;                                // depth of the h_{t-1} TMA ring (<= MAX_STAGES)
 };
 
 // U hidden units per CTA -> UMMA N = 4U gate columns, packed unit-major: column n = u*4 + g.
@@ -67,12 +70,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int STAGES = a.stages;
   uint8_t* sA = smem;                                        // [STAGES][16 KB]
-  uint8_t* sW = smem + SEQ_STAGES * A_STAGE_BYTES;           // [KB][N*128]  (N*128 is a multiple of 1024 for N >= 8... see launcher)
+  uint8_t* sW = smem + (size_t)STAGES * A_STAGE_BYTES;       // [KB][N*128]  (N*128 is a multiple of 1024 for N >= 8)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)KB * W_KB_BYTES);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + SEQ_STAGES;
-  uint64_t* w_full = bars + 2 * SEQ_STAGES;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* w_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_full = w_full + 1;
   uint64_t* tmem_empty = w_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
@@ -83,7 +87,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const unsigned* counter = a.counters + rg;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < SEQ_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(w_full, 1);
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 4);
@@ -110,8 +114,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           fence_proxy_async();
         }
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % SEQ_STAGES;
-          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], A_STAGE_BYTES);
           if (t == 0) tma_load_2d(sA + s * A_STAGE_BYTES, &tmH0, kb * 64, m0, &full_bar[s]);
@@ -128,8 +132,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         mbar_wait(tmem_empty, (t & 1) ^ 1);      // epilogue has drained the previous step's accumulator
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % SEQ_STAGES;
-          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
@@ -155,13 +159,20 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     for (int u = 0; u < U; ++u) creg[u] = (valid && a.c0) ? a.c0[(long long)row * H + j0 + u] : 0.f;
     for (int t = 0; t < T; ++t) {
       const long long bt = (long long)row * T + t;
+      // input-half pre-activations of the first chunk: independent of the MMA, fetched while it runs
+      float4 x4[4][UC / 4];
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int v = 0; v < UC / 4; ++v)
+            x4[g][v] = *reinterpret_cast<const float4*>(a.xg + bt * 4 * H + (long long)g * H + j0 + v * 4);
+      }
       mbar_wait(tmem_full, t & 1);
       tc_fence_after();
 #pragma unroll
       for (int ch = 0; ch < N / CH; ++ch) {
-        // input-half pre-activations for this chunk's units (independent of the MMA)
-        float4 x4[4][UC / 4];
-        if (valid) {
+        if (ch > 0 && valid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -211,11 +222,15 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           }
         }
       }
-      // publish h_t: generic-proxy stores -> visible at gpu scope -> one release-arrive per CTA
-      __threadfence();
+      // publish h_t (cooperative-groups grid-sync pattern): every writer orders its generic-proxy stores
+      // before later async-proxy (TMA) reads, the epilogue warps meet, one thread fences at gpu scope and
+      // release-arrives on the row group's counter
       fence_proxy_async();
-      epilogue_bar();
-      if (warp == 2 && lane == 0 && t + 1 < T) red_release_gpu_add(a.counters + rg, 1u);
+      epilogue_bar<128>();
+      if (warp == 2 && lane == 0 && t + 1 < T) {
+        __threadfence();
+        red_release_gpu_add(a.counters + rg, 1u);
+      }
     }
   }
   tc_fence_before();
@@ -237,24 +252,28 @@ struct SeqBwdArgs {
   float* dgates; bf16* dgates16;          // [B,T,4H]
   float *dh0, *dc0;                       // [B,H] (may be null)
   unsigned* counters;
+  int stages;
 };
 
-// 16 hidden units per CTA: dh_rec[:, j-slice] = dgates_{t+1} [B,4H] * W_hh[:, j-slice]  (K = 4H)
-__global__ void __launch_bounds__(SEQ_THREADS, 1)
+// 16 hidden units per CTA: dh_rec[:, j-slice] = dgates_{t+1} [B,4H] * W_hh[:, j-slice]  (K = 4H).
+// 16 epilogue warps: warp -> (TMEM lane quarter = warp % 4, column group = (warp-2)/4), i.e. each thread owns
+// one batch row and 4 hidden units, so that all of a step's operand loads are in flight at once.
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, const SeqBwdArgs a) {
   constexpr int U = 16, N = 16, TCOLS = 32;
   constexpr uint32_t W_KB_BYTES = N * 128;
   const int KB = 4 * a.H / 64;
   const int C = gridDim.x;
+  const int STAGES = a.stages;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sW = smem + SEQ_STAGES * A_STAGE_BYTES;
+  uint8_t* sW = smem + (size_t)STAGES * A_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)KB * W_KB_BYTES);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + SEQ_STAGES;
-  uint64_t* w_full = bars + 2 * SEQ_STAGES;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* w_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_full = w_full + 1;
   uint64_t* tmem_empty = w_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
@@ -265,10 +284,10 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
   const int T = a.T, H = a.H;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < SEQ_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(w_full, 1);
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -291,8 +310,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
         grid_barrier_wait(a.counters + rg, (unsigned)i * C);     // dgates_t complete in this row group
         fence_proxy_async();
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % SEQ_STAGES;
-          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], A_STAGE_BYTES);
           tma_load_2d(sA + s * A_STAGE_BYTES, &tmG, t * 4 * H + kb * 64, m0, &full_bar[s]);
@@ -308,8 +327,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
         mbar_wait(tmem_empty, ((i - 1) & 1) ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % SEQ_STAGES;
-          const uint32_t ph = (it / SEQ_STAGES) & 1;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
@@ -325,88 +344,89 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
     }
   } else {
     const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;            // column group: units cg*4 .. cg*4+3 of this CTA's 16
     const int row = m0 + q * 32 + lane;
     const bool valid = row < a.B;
-    const int j0 = c * U;
-    float dcreg[U];     // dc flowing from step t+1 into step t
-    float dhrec[U];     // dh flowing from step t+1 into step t
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      dcreg[u] = (valid && a.d_cT) ? a.d_cT[(long long)row * H + j0 + u] : 0.f;
-      dhrec[u] = (valid && a.d_hT) ? a.d_hT[(long long)row * H + j0 + u] : 0.f;
+    const int j = c * U + cg * 4;              // first of this thread's 4 hidden units
+    float dcreg[4], dhrec[4];                  // dc / dh flowing from step t+1 into step t
+    {
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 c4 = (valid && a.d_cT) ? *reinterpret_cast<const float4*>(a.d_cT + (long long)row * H + j) : z;
+      const float4 h4 = (valid && a.d_hT) ? *reinterpret_cast<const float4*>(a.d_hT + (long long)row * H + j) : z;
+      dcreg[0] = c4.x; dcreg[1] = c4.y; dcreg[2] = c4.z; dcreg[3] = c4.w;
+      dhrec[0] = h4.x; dhrec[1] = h4.y; dhrec[2] = h4.z; dhrec[3] = h4.w;
     }
     for (int i = 0; i <= T; ++i) {
       const int t = T - 1 - i;
+      // operands of step t that do not depend on the recurrence: issue the loads before waiting for the MMA
+      float4 dha, dhs4, dcl, ig4, fg4, gg4, og4, ce4, cp4;
+      dha = dhs4 = dcl = ig4 = fg4 = gg4 = og4 = ce4 = cp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const long long bt = (long long)row * T + (t < 0 ? 0 : t);
+      if (valid && t >= 0) {
+        dha = *reinterpret_cast<const float4*>(a.dh_attn + bt * H + j);
+        if (a.dhs && t + 1 < T) dhs4 = *reinterpret_cast<const float4*>(a.dhs + (bt + 1) * H + j);
+        dcl = *reinterpret_cast<const float4*>(a.dcell + bt * H + j);
+        const float* ac = a.acts + bt * 4 * H + j;
+        ig4 = *reinterpret_cast<const float4*>(ac);
+        fg4 = *reinterpret_cast<const float4*>(ac + H);
+        gg4 = *reinterpret_cast<const float4*>(ac + 2 * H);
+        og4 = *reinterpret_cast<const float4*>(ac + 3 * H);
+        ce4 = *reinterpret_cast<const float4*>(a.cells + bt * H + j);
+        if (t > 0) cp4 = *reinterpret_cast<const float4*>(a.cells + (bt - 1) * H + j);
+        else if (a.c0) cp4 = *reinterpret_cast<const float4*>(a.c0 + (long long)row * H + j);
+      }
       if (i >= 1) {
         mbar_wait(tmem_full, (i - 1) & 1);
         tc_fence_after();
-        uint32_t r[16];
-        tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16), r);
+        uint32_t r[4];
+        tmem_ld<4>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 4), r);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty);
 #pragma unroll
-        for (int u = 0; u < U; ++u) dhrec[u] = __uint_as_float(r[u]);
+        for (int u = 0; u < 4; ++u) dhrec[u] = __uint_as_float(r[u]);
       }
       if (t < 0) break;
       if (valid) {
-        const long long bt = (long long)row * T + t;
+        const float dhav[4] = {dha.x + dhs4.x, dha.y + dhs4.y, dha.z + dhs4.z, dha.w + dhs4.w};
+        const float dclv[4] = {dcl.x, dcl.y, dcl.z, dcl.w};
+        const float igv[4] = {ig4.x, ig4.y, ig4.z, ig4.w}, fgv[4] = {fg4.x, fg4.y, fg4.z, fg4.w};
+        const float ggv[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, ogv[4] = {og4.x, og4.y, og4.z, og4.w};
+        const float cev[4] = {ce4.x, ce4.y, ce4.z, ce4.w}, cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+        float d0[4], d1[4], d2[4], d3[4];
 #pragma unroll
-        for (int v = 0; v < U / 4; ++v) {
-          const int j = j0 + v * 4;
-          const float4 dha = *reinterpret_cast<const float4*>(a.dh_attn + bt * H + j);
-          float4 dhs = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.dhs && t + 1 < T) dhs = *reinterpret_cast<const float4*>(a.dhs + (bt + 1) * H + j);
-          const float4 dcl = *reinterpret_cast<const float4*>(a.dcell + bt * H + j);
-          const float* ac = a.acts + bt * 4 * H + j;
-          const float4 ig4 = *reinterpret_cast<const float4*>(ac), fg4 = *reinterpret_cast<const float4*>(ac + H);
-          const float4 gg4 = *reinterpret_cast<const float4*>(ac + 2 * H), og4 = *reinterpret_cast<const float4*>(ac + 3 * H);
-          const float4 ce4 = *reinterpret_cast<const float4*>(a.cells + bt * H + j);
-          float4 cp4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (t > 0) cp4 = *reinterpret_cast<const float4*>(a.cells + (bt - 1) * H + j);
-          else if (a.c0) cp4 = *reinterpret_cast<const float4*>(a.c0 + (long long)row * H + j);
-          const float dhav[4] = {dha.x + dhs.x, dha.y + dhs.y, dha.z + dhs.z, dha.w + dhs.w};
-          const float dclv[4] = {dcl.x, dcl.y, dcl.z, dcl.w};
-          const float igv[4] = {ig4.x, ig4.y, ig4.z, ig4.w}, fgv[4] = {fg4.x, fg4.y, fg4.z, fg4.w};
-          const float ggv[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, ogv[4] = {og4.x, og4.y, og4.z, og4.w};
-          const float cev[4] = {ce4.x, ce4.y, ce4.z, ce4.w}, cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
-          float d0[4], d1[4], d2[4], d3[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int u = v * 4 + e;
-            const float dh = dhav[e] + dhrec[u];
-            const float tcv = tanhf(cev[e]);
-            const float dc = dclv[e] + dcreg[u] + dh * ogv[e] * (1.f - tcv * tcv);
-            d0[e] = dc * ggv[e] * igv[e] * (1.f - igv[e]);
-            d1[e] = dc * cpv[e] * fgv[e] * (1.f - fgv[e]);
-            d2[e] = dc * igv[e] * (1.f - ggv[e] * ggv[e]);
-            d3[e] = dh * tcv * ogv[e] * (1.f - ogv[e]);
-            dcreg[u] = dc * fgv[e];
-          }
-          float* dg = a.dgates + bt * 4 * H + j;
-          bf16* dg16 = a.dgates16 + bt * 4 * H + j;
-          *reinterpret_cast<float4*>(dg) = make_float4(d0[0], d0[1], d0[2], d0[3]);
-          *reinterpret_cast<float4*>(dg + H) = make_float4(d1[0], d1[1], d1[2], d1[3]);
-          *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(d2[0], d2[1], d2[2], d2[3]);
-          *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(d3[0], d3[1], d3[2], d3[3]);
-          st_bf16x4(dg16, d0[0], d0[1], d0[2], d0[3]);
-          st_bf16x4(dg16 + H, d1[0], d1[1], d1[2], d1[3]);
-          st_bf16x4(dg16 + 2 * H, d2[0], d2[1], d2[2], d2[3]);
-          st_bf16x4(dg16 + 3 * H, d3[0], d3[1], d3[2], d3[3]);
+        for (int e = 0; e < 4; ++e) {
+          const float dh = dhav[e] + dhrec[e];
+          const float tcv = tanhf(cev[e]);
+          const float dc = dclv[e] + dcreg[e] + dh * ogv[e] * (1.f - tcv * tcv);
+          d0[e] = dc * ggv[e] * igv[e] * (1.f - igv[e]);
+          d1[e] = dc * cpv[e] * fgv[e] * (1.f - fgv[e]);
+          d2[e] = dc * igv[e] * (1.f - ggv[e] * ggv[e]);
+          d3[e] = dh * tcv * ogv[e] * (1.f - ogv[e]);
+          dcreg[e] = dc * fgv[e];
         }
+        float* dg = a.dgates + bt * 4 * H + j;
+        bf16* dg16 = a.dgates16 + bt * 4 * H + j;
+        *reinterpret_cast<float4*>(dg) = make_float4(d0[0], d0[1], d0[2], d0[3]);
+        *reinterpret_cast<float4*>(dg + H) = make_float4(d1[0], d1[1], d1[2], d1[3]);
+        *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+        *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(d3[0], d3[1], d3[2], d3[3]);
+        st_bf16x4(dg16, d0[0], d0[1], d0[2], d0[3]);
+        st_bf16x4(dg16 + H, d1[0], d1[1], d1[2], d1[3]);
+        st_bf16x4(dg16 + 2 * H, d2[0], d2[1], d2[2], d2[3]);
+        st_bf16x4(dg16 + 3 * H, d3[0], d3[1], d3[2], d3[3]);
       }
-      __threadfence();
       fence_proxy_async();
-      epilogue_bar();
-      if (warp == 2 && lane == 0) red_release_gpu_add(a.counters + rg, 1u);
+      epilogue_bar<512>();
+      if (warp == 2 && lane == 0) {
+        __threadfence();
+        red_release_gpu_add(a.counters + rg, 1u);
+      }
     }
     // after the last GEMM: dhrec = dgates_0 W_hh = dh0 ; dcreg = dc0
     if (valid) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (a.dh0) a.dh0[(long long)row * H + j0 + u] = dhrec[u];
-        if (a.dc0) a.dc0[(long long)row * H + j0 + u] = dcreg[u];
-      }
+      if (a.dh0) *reinterpret_cast<float4*>(a.dh0 + (long long)row * H + j) = make_float4(dhrec[0], dhrec[1], dhrec[2], dhrec[3]);
+      if (a.dc0) *reinterpret_cast<float4*>(a.dc0 + (long long)row * H + j) = make_float4(dcreg[0], dcreg[1], dcreg[2], dcreg[3]);
     }
   }
   tc_fence_before();
@@ -435,6 +455,13 @@ __global__ void transpose_whh_kernel(const float* __restrict__ w_hh, bf16* __res
   for (int r = threadIdx.y; r < 32; r += 8) wt[(long long)(j0 + r) * 4 * H + n0 + threadIdx.x] = __float2bfloat16(tile[threadIdx.x][r]);
 }
 
+// depth of the activation ring: as deep as shared memory allows next to the resident weight slice
+inline int seq_stages(size_t w_bytes) {
+  if (w_bytes + 2 * A_STAGE_BYTES > SEQ_SMEM_BUDGET) return 0;
+  size_t n = (SEQ_SMEM_BUDGET - w_bytes) / A_STAGE_BYTES;
+  return (int)(n > MAX_STAGES ? MAX_STAGES : n);
+}
+
 template <int U>
 int launch_fwd_u(const LstmSeqFwd& p, int C, int RG, cudaStream_t st) {
   constexpr int N = 4 * U;
@@ -450,7 +477,8 @@ int launch_fwd_u(const LstmSeqFwd& p, int C, int RG, cudaStream_t st) {
   a.B = p.B; a.T = p.T; a.H = H; a.xg = p.xg; a.c0 = p.c0;
   a.hiddens = p.hiddens; a.cells = p.cells; a.acts = p.acts; a.hs_prev = p.hs_prev; a.hid16 = p.hid16; a.hsprev16 = p.hsprev16;
   a.counters = p.counters;
-  const size_t smem = (size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)KB * N * 128 + 16 * 8 + 16 + 1024;
+  a.stages = seq_stages((size_t)KB * N * 128);
+  const size_t smem = (size_t)a.stages * A_STAGE_BYTES + (size_t)KB * N * 128 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
   auto kern = lstm_seq_fwd_kernel<U>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -470,11 +498,10 @@ bool lstm_seq_supported(int B, int H, int* units_fwd) {
   const int RG = ceil_div(B, 128);
   const int sms = num_sms();
   if ((H / 16) * RG > sms) return false;                         // backward: 16 units per CTA
-  if ((size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)(4 * H / 64) * 16 * 128 > 200 * 1024) return false;
+  if (seq_stages((size_t)(4 * H / 64) * 16 * 128) < 2) return false;
   for (int U : {4, 8, 16, 32}) {
     if (H % U) continue;
-    const size_t smem = (size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)(H / 64) * 4 * U * 128;
-    if ((H / U) * RG <= sms && smem <= 200 * 1024) {
+    if ((H / U) * RG <= sms && seq_stages((size_t)(H / 64) * 4 * U * 128) >= 2) {
       if (units_fwd) *units_fwd = U;
       return true;
     }
@@ -508,14 +535,15 @@ int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
   a.dh_attn = p.dh_attn; a.dhs = p.dhs; a.dcell = p.dcell; a.d_hT = p.d_hT; a.d_cT = p.d_cT;
   a.acts = p.acts; a.cells = p.cells; a.c0 = p.c0; a.dgates = p.dgates; a.dgates16 = p.dgates16; a.dh0 = p.dh0; a.dc0 = p.dc0;
   a.counters = p.counters;
-  const size_t smem = (size_t)SEQ_STAGES * A_STAGE_BYTES + (size_t)KB * 16 * 128 + 16 * 8 + 16 + 1024;
+  a.stages = seq_stages((size_t)KB * 16 * 128);
+  const size_t smem = (size_t)a.stages * A_STAGE_BYTES + (size_t)KB * 16 * 128 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   void* args[] = {(void*)&tmWT, (void*)&tmG, (void*)&a};
-  AA_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lstm_seq_bwd_kernel, dim3(C, RG), dim3(SEQ_THREADS), args, smem, st));
+  AA_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lstm_seq_bwd_kernel, dim3(C, RG), dim3(BWD_THREADS), args, smem, st));
   count_launch();
   return AA_OK;
 }
