@@ -335,6 +335,8 @@ int aa_profile_get(int i, char* name, int name_len, double* total_ms, int* launc
   return AA_OK;
 }
 
+int aa_debug_set_trace_buffer(void* dev_ptr) { return set_seq_trace_buffer(dev_ptr); }
+
 int aa_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   AA_CHECK_CUDA(cudaGetDevice(&dev));

@@ -25,6 +25,18 @@ constexpr int MAX_STAGES = 8;
 constexpr size_t SEQ_SMEM_BUDGET = 200 * 1024;
 constexpr uint32_t A_STAGE_BYTES = 128 * 128;   // 128 rows x 64 bf16
 
+// Optional per-step timeline of CTA (0,0) (diagnostics: aa_debug_set_trace_buffer): 8 x uint64 globaltimer
+// stamps per step -- 0 barrier passed, 1 TMA issued, 2 first stage landed, 3 MMA committed, 4 accumulator
+// observed, 5 cell math + stores issued, 6 epilogue warps met, 7 arrive published.
+__device__ unsigned long long* g_seq_trace = nullptr;
+__device__ __forceinline__ void trace(int step, int ev) {
+  if (g_seq_trace && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_seq_trace[step * 8 + ev] = t;
+  }
+}
+
 __device__ __forceinline__ void grid_barrier_wait(const unsigned* counter, unsigned target) {
   long long t0 = 0;
   while (ld_acquire_gpu(counter) < target) {
@@ -53,6 +65,7 @@ struct SeqFwdArgs {
   bf16 *hid16, *hsprev16;                    // bf16 mirrors
   unsigned* counters;                        // [row groups], zeroed by the launcher
   int stages;                                // depth of the h_{t-1} TMA ring (<= MAX_STAGES)
+  int box_rows;                              // rows per TMA box (batch rows of a group rounded up to 8)
 };
 
 // U hidden units per CTA -> UMMA N = 4U gate columns, packed unit-major: column n = u*4 + g.
@@ -113,20 +126,23 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           grid_barrier_wait(counter, (unsigned)t * C);   // every CTA of this row group has published h_{t-1}
           fence_proxy_async();
         }
+        trace(t, 0);
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES);
+          mbar_expect_tx(&full_bar[s], (uint32_t)a.box_rows * 128u);
           if (t == 0) tma_load_2d(sA + s * A_STAGE_BYTES, &tmH0, kb * 64, m0, &full_bar[s]);
           else        tma_load_2d(sA + s * A_STAGE_BYTES, &tmH, (t - 1) * a.H + kb * 64, m0, &full_bar[s]);
         }
+        trace(t, 1);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(w_full, 0);
+      const uint64_t desc0 = make_smem_desc(0, 16, 1024);
       int it = 0;
       for (int t = 0; t < a.T; ++t) {
         mbar_wait(tmem_empty, (t & 1) ^ 1);      // epilogue has drained the previous step's accumulator
@@ -135,16 +151,17 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
+          if (kb == 0) trace(t, 2);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sW + (size_t)kb * W_KB_BYTES);
+          // descriptors differ only in the start-address field (bits 0-13, 16-byte units): +2 per 32-byte k-step
+          const uint64_t da = desc0 + ((smem_u32(sA + s * A_STAGE_BYTES)) >> 4);
+          const uint64_t db = desc0 + ((smem_u32(sW + (size_t)kb * W_KB_BYTES)) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma<false>(tmem_base, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma<false>(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[s]);
         }
         tc_commit(tmem_full);
+        trace(t, 3);
       }
     }
   } else {
@@ -159,6 +176,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     for (int u = 0; u < U; ++u) creg[u] = (valid && a.c0) ? a.c0[(long long)row * H + j0 + u] : 0.f;
     for (int t = 0; t < T; ++t) {
       const long long bt = (long long)row * T + t;
+      float hn[U], ig[U], fg[U], gg[U], og[U];
       // input-half pre-activations of the first chunk: independent of the MMA, fetched while it runs
       float4 x4[4][UC / 4];
       if (valid) {
@@ -169,6 +187,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             x4[g][v] = *reinterpret_cast<const float4*>(a.xg + bt * 4 * H + (long long)g * H + j0 + v * 4);
       }
       mbar_wait(tmem_full, t & 1);
+      if (threadIdx.x == 64) trace(t, 4);
       tc_fence_after();
 #pragma unroll
       for (int ch = 0; ch < N / CH; ++ch) {
@@ -189,7 +208,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (valid) {
 #pragma unroll
           for (int v = 0; v < UC / 4; ++v) {
-            float hn[4], cn[4], ig[4], fg[4], gg[4], og[4];
             const float xi[4] = {x4[0][v].x, x4[0][v].y, x4[0][v].z, x4[0][v].w};
             const float xf[4] = {x4[1][v].x, x4[1][v].y, x4[1][v].z, x4[1][v].w};
             const float xc[4] = {x4[2][v].x, x4[2][v].y, x4[2][v].z, x4[2][v].w};
@@ -198,39 +216,47 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             for (int e = 0; e < 4; ++e) {
               const int ul = v * 4 + e;          // unit within chunk; TMEM column = ul*4 + gate
               const int u = ch * UC + ul;
-              ig[e] = sigmoidf_acc(__uint_as_float(r[ul * 4 + 0]) + xi[e]);
-              fg[e] = sigmoidf_acc(__uint_as_float(r[ul * 4 + 1]) + xf[e]);
-              gg[e] = tanhf(__uint_as_float(r[ul * 4 + 2]) + xc[e]);
-              og[e] = sigmoidf_acc(__uint_as_float(r[ul * 4 + 3]) + xo[e]);
-              cn[e] = fg[e] * creg[u] + ig[e] * gg[e];
-              creg[u] = cn[e];
-              hn[e] = og[e] * tanhf(cn[e]);
+              ig[u] = sigmoidf_fast(__uint_as_float(r[ul * 4 + 0]) + xi[e]);
+              fg[u] = sigmoidf_fast(__uint_as_float(r[ul * 4 + 1]) + xf[e]);
+              gg[u] = tanhf_fast(__uint_as_float(r[ul * 4 + 2]) + xc[e]);
+              og[u] = sigmoidf_fast(__uint_as_float(r[ul * 4 + 3]) + xo[e]);
+              creg[u] = fg[u] * creg[u] + ig[u] * gg[u];
+              hn[u] = og[u] * tanhf_fast(creg[u]);
             }
-            const int j = j0 + ch * UC + v * 4;
-            *reinterpret_cast<float4*>(a.hiddens + bt * H + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(a.cells + bt * H + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            st_bf16x4(a.hid16 + bt * H + j, hn[0], hn[1], hn[2], hn[3]);
-            float* ac = a.acts + bt * 4 * H + j;
-            *reinterpret_cast<float4*>(ac) = make_float4(ig[0], ig[1], ig[2], ig[3]);
-            *reinterpret_cast<float4*>(ac + H) = make_float4(fg[0], fg[1], fg[2], fg[3]);
-            *reinterpret_cast<float4*>(ac + 2 * H) = make_float4(gg[0], gg[1], gg[2], gg[3]);
-            *reinterpret_cast<float4*>(ac + 3 * H) = make_float4(og[0], og[1], og[2], og[3]);
-            if (t + 1 < T) {
-              *reinterpret_cast<float4*>(a.hs_prev + (bt + 1) * H + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-              st_bf16x4(a.hsprev16 + (bt + 1) * H + j, hn[0], hn[1], hn[2], hn[3]);
-            }
+            // only the bf16 h_t feeds the next step: store it first, everything else after the arrive
+            st_bf16x4(a.hid16 + bt * H + j0 + ch * UC + v * 4, hn[ch * UC + v * 4], hn[ch * UC + v * 4 + 1], hn[ch * UC + v * 4 + 2],
+                      hn[ch * UC + v * 4 + 3]);
           }
         }
       }
-      // publish h_t (cooperative-groups grid-sync pattern): every writer orders its generic-proxy stores
-      // before later async-proxy (TMA) reads, the epilogue warps meet, one thread fences at gpu scope and
-      // release-arrives on the row group's counter
-      fence_proxy_async();
+      // publish h_t (cooperative-groups grid-sync pattern): the epilogue warps meet, one thread fences at gpu
+      // scope (cumulative over the stores it observed through the barrier) and release-arrives on the row
+      // group's counter; the consumer side acquires and issues fence.proxy.async before its TMA loads
+      if (threadIdx.x == 64) trace(t, 5);
       epilogue_bar<128>();
+      if (threadIdx.x == 64) trace(t, 6);
       if (warp == 2 && lane == 0 && t + 1 < T) {
         __threadfence();
         red_release_gpu_add(a.counters + rg, 1u);
       }
+      if (valid) {   // the remaining outputs are only read after the kernel: off the critical path
+#pragma unroll
+        for (int u = 0; u < U; u += 4) {
+          const int j = j0 + u;
+          *reinterpret_cast<float4*>(a.hiddens + bt * H + j) = make_float4(hn[u], hn[u + 1], hn[u + 2], hn[u + 3]);
+          *reinterpret_cast<float4*>(a.cells + bt * H + j) = make_float4(creg[u], creg[u + 1], creg[u + 2], creg[u + 3]);
+          float* ac = a.acts + bt * 4 * H + j;
+          *reinterpret_cast<float4*>(ac) = make_float4(ig[u], ig[u + 1], ig[u + 2], ig[u + 3]);
+          *reinterpret_cast<float4*>(ac + H) = make_float4(fg[u], fg[u + 1], fg[u + 2], fg[u + 3]);
+          *reinterpret_cast<float4*>(ac + 2 * H) = make_float4(gg[u], gg[u + 1], gg[u + 2], gg[u + 3]);
+          *reinterpret_cast<float4*>(ac + 3 * H) = make_float4(og[u], og[u + 1], og[u + 2], og[u + 3]);
+          if (t + 1 < T) {
+            *reinterpret_cast<float4*>(a.hs_prev + (bt + 1) * H + j) = make_float4(hn[u], hn[u + 1], hn[u + 2], hn[u + 3]);
+            st_bf16x4(a.hsprev16 + (bt + 1) * H + j, hn[u], hn[u + 1], hn[u + 2], hn[u + 3]);
+          }
+        }
+      }
+      if (threadIdx.x == 64) trace(t, 7);
     }
   }
   tc_fence_before();
@@ -253,6 +279,7 @@ struct SeqBwdArgs {
   float *dh0, *dc0;                       // [B,H] (may be null)
   unsigned* counters;
   int stages;
+  int box_rows;
 };
 
 // 16 hidden units per CTA: dh_rec[:, j-slice] = dgates_{t+1} [B,4H] * W_hh[:, j-slice]  (K = 4H).
@@ -309,19 +336,22 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
         const int t = T - i;
         grid_barrier_wait(a.counters + rg, (unsigned)i * C);     // dgates_t complete in this row group
         fence_proxy_async();
+        trace(i, 0);
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES);
+          mbar_expect_tx(&full_bar[s], (uint32_t)a.box_rows * 128u);
           tma_load_2d(sA + s * A_STAGE_BYTES, &tmG, t * 4 * H + kb * 64, m0, &full_bar[s]);
         }
+        trace(i, 1);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(w_full, 0);
+      const uint64_t desc0 = make_smem_desc(0, 16, 1024);
       int it = 0;
       for (int i = 1; i <= T; ++i) {
         mbar_wait(tmem_empty, ((i - 1) & 1) ^ 1);
@@ -330,16 +360,17 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
+          if (kb == 0) trace(i, 2);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sW + (size_t)kb * W_KB_BYTES);
+          // descriptors differ only in the start-address field (bits 0-13, 16-byte units): +2 per 32-byte k-step
+          const uint64_t da = desc0 + ((smem_u32(sA + s * A_STAGE_BYTES)) >> 4);
+          const uint64_t db = desc0 + ((smem_u32(sW + (size_t)kb * W_KB_BYTES)) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma<false>(tmem_base, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma<false>(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[s]);
         }
         tc_commit(tmem_full);
+        trace(i, 3);
       }
     }
   } else {
@@ -377,6 +408,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
       }
       if (i >= 1) {
         mbar_wait(tmem_full, (i - 1) & 1);
+        if (threadIdx.x == 64) trace(i, 4);
         tc_fence_after();
         uint32_t r[4];
         tmem_ld<4>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 4), r);
@@ -397,7 +429,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float dh = dhav[e] + dhrec[e];
-          const float tcv = tanhf(cev[e]);
+          const float tcv = tanhf_fast(cev[e]);
           const float dc = dclv[e] + dcreg[e] + dh * ogv[e] * (1.f - tcv * tcv);
           d0[e] = dc * ggv[e] * igv[e] * (1.f - igv[e]);
           d1[e] = dc * cpv[e] * fgv[e] * (1.f - fgv[e]);
@@ -416,12 +448,14 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
         st_bf16x4(dg16 + 2 * H, d2[0], d2[1], d2[2], d2[3]);
         st_bf16x4(dg16 + 3 * H, d3[0], d3[1], d3[2], d3[3]);
       }
-      fence_proxy_async();
+      if (threadIdx.x == 64) trace(i, 5);
       epilogue_bar<512>();
+      if (threadIdx.x == 64) trace(i, 6);
       if (warp == 2 && lane == 0) {
         __threadfence();
         red_release_gpu_add(a.counters + rg, 1u);
       }
+      if (threadIdx.x == 64) trace(i, 7);
     }
     // after the last GEMM: dhrec = dgates_0 W_hh = dh0 ; dcreg = dc0
     if (valid) {
@@ -471,13 +505,15 @@ int launch_fwd_u(const LstmSeqFwd& p, int C, int RG, cudaStream_t st) {
   AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
   CUtensorMap tmW, tmH0, tmH;
   AA_TRY(make_map(&tmW, p.whh_packed16, 2, 4LL * H, H, H, N));
-  AA_TRY(make_map(&tmH0, p.h016, 2, p.B, H, H, 128));
-  AA_TRY(make_map(&tmH, p.hid16, 2, p.B, (long long)p.T * H, (long long)p.T * H, 128));
+  const int box_rows = (p.B >= 128 ? 128 : (p.B + 7) / 8 * 8);   // rows beyond the batch are never loaded
+  AA_TRY(make_map(&tmH0, p.h016, 2, p.B, H, H, box_rows));
+  AA_TRY(make_map(&tmH, p.hid16, 2, p.B, (long long)p.T * H, (long long)p.T * H, box_rows));
   SeqFwdArgs a{};
   a.B = p.B; a.T = p.T; a.H = H; a.xg = p.xg; a.c0 = p.c0;
   a.hiddens = p.hiddens; a.cells = p.cells; a.acts = p.acts; a.hs_prev = p.hs_prev; a.hid16 = p.hid16; a.hsprev16 = p.hsprev16;
   a.counters = p.counters;
   a.stages = seq_stages((size_t)KB * N * 128);
+  a.box_rows = box_rows;
   const size_t smem = (size_t)a.stages * A_STAGE_BYTES + (size_t)KB * N * 128 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
   auto kern = lstm_seq_fwd_kernel<U>;
   static size_t attr_smem = 0;
@@ -492,6 +528,12 @@ int launch_fwd_u(const LstmSeqFwd& p, int C, int RG, cudaStream_t st) {
 }
 
 }  // namespace
+
+int set_seq_trace_buffer(void* dev_ptr) {
+  unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+  AA_CHECK_CUDA(cudaMemcpyToSymbol(g_seq_trace, &p, sizeof(p)));
+  return AA_OK;
+}
 
 bool lstm_seq_supported(int B, int H, int* units_fwd) {
   if (H % 64 != 0 || H < 64 || B < 1) return false;
@@ -529,13 +571,15 @@ int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
   AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
   CUtensorMap tmWT, tmG;
   AA_TRY(make_map(&tmWT, p.whhT16, 2, H, 4LL * H, 4LL * H, 16));
-  AA_TRY(make_map(&tmG, p.dgates16, 2, p.B, (long long)p.T * 4 * H, (long long)p.T * 4 * H, 128));
+  const int box_rows = (p.B >= 128 ? 128 : (p.B + 7) / 8 * 8);
+  AA_TRY(make_map(&tmG, p.dgates16, 2, p.B, (long long)p.T * 4 * H, (long long)p.T * 4 * H, box_rows));
   SeqBwdArgs a{};
   a.B = p.B; a.T = p.T; a.H = H;
   a.dh_attn = p.dh_attn; a.dhs = p.dhs; a.dcell = p.dcell; a.d_hT = p.d_hT; a.d_cT = p.d_cT;
   a.acts = p.acts; a.cells = p.cells; a.c0 = p.c0; a.dgates = p.dgates; a.dgates16 = p.dgates16; a.dh0 = p.dh0; a.dc0 = p.dc0;
   a.counters = p.counters;
   a.stages = seq_stages((size_t)KB * 16 * 128);
+  a.box_rows = box_rows;
   const size_t smem = (size_t)a.stages * A_STAGE_BYTES + (size_t)KB * 16 * 128 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {

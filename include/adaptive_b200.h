@@ -100,6 +100,9 @@ int aa_profile_enable(int on);
 int aa_profile_reset(void);
 int aa_profile_count(void);
 int aa_profile_get(int i, char* name, int name_len, double* total_ms, int* launches);
+/* Diagnostics: device buffer [steps][8] of uint64 %globaltimer stamps written by CTA (0,0) of the persistent
+ * LSTM kernels (see lstm_seq.cu); NULL switches tracing off. */
+int aa_debug_set_trace_buffer(void* dev_ptr);
 
 /* ---- stage operators (the nn.Module sub-blocks) ------------------------------------- */
 
