@@ -173,6 +173,32 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
                         const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0, float* dc0,
                         void* scratch, size_t scratch_bytes, void* stream);
 
+/* Data-parallel hook (the reference's multi-GPU scheme is nn.DataParallel's reduce_add_coalesced after
+ * backward, baseline_attention.py:184-187; here: one process per GPU, NCCL all-reduce overlapped with the
+ * rest of the backward).  The parameter gradients become final in four buckets, in this order:
+ *   AA_BUCKET_MLP      mlp_w, mlp_b                                      (first: half of all gradient bytes)
+ *   AA_BUCKET_ATTEN    att_wv, att_wg, att_ws, att_wh, sen_wx, sen_wh
+ *   AA_BUCKET_LSTM     w_ih, w_hh, b_ih, b_hh
+ *   AA_BUCKET_EMBED    embed                                             (last)
+ * aa_decoder_backward_hooked is aa_decoder_backward plus: as soon as the last kernel writing a bucket has been
+ * enqueued, it records ready_events[bucket] (cudaEvent_t passed as void*, may be NULL to skip recording) on the
+ * stream that kernel ran on and calls on_ready(bucket, user) on the calling host thread, so that the caller
+ * can make a communication stream wait on the event and launch the bucket's all-reduce while the remaining
+ * backward kernels are still running.  on_ready may be NULL. */
+#define AA_BUCKET_MLP 0
+#define AA_BUCKET_ATTEN 1
+#define AA_BUCKET_LSTM 2
+#define AA_BUCKET_EMBED 3
+#define AA_NUM_BUCKETS 4
+typedef void (*aa_grad_ready_fn)(int bucket, void* user);
+int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g,
+                               const int64_t* captions, const float* h0, const float* c0, const float* alpha,
+                               const float* beta, const void* saved, size_t saved_bytes, const float* d_scores,
+                               const float* d_alpha, const float* d_beta, const float* d_hT, const float* d_cT,
+                               const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0, float* dc0,
+                               void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
+                               aa_grad_ready_fn on_ready, void* user);
+
 /* pack_padded_sequence(scores, lengths, batch_first=True).data (baseline_attention.py:228):
  * gathers rows (b,t) with t < lengths[b] in time-major order.  row_index [n_rows] int64 holds
  * b*T+t per packed row (host code builds it from `lengths`).  packed [n_rows,Vc]. */
