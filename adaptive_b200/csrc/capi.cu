@@ -1,6 +1,7 @@
 // extern "C" boundary of libadaptive_sm100.so (see include/adaptive_b200.h) and the host-side
 // orchestration of the teacher-forced forward/backward.  Decoding lives in decode_api.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -33,6 +34,52 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// ---- side stream (fork/join inside one call) -------------------------------------------------
+// The backward has work that is off the critical path (every weight-gradient contraction, dV, the sentinel's
+// dx): it runs on a library-owned non-blocking stream, forked from / joined back into the caller's stream with
+// events, so the call still looks like ONE stream-ordered operation to the caller (and captures into a CUDA
+// graph as a fork/join).  One side stream + event pool per (host thread, device), created lazily -- the first
+// call on a thread must therefore not be made under stream capture (same rule as the one-time
+// cudaFuncSetAttribute calls of the kernels).  AA_NO_SIDE_STREAM=1 serialises everything on the caller's stream.
+namespace {
+constexpr int SIDE_EVENTS = 12;
+struct SideCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[SIDE_EVENTS] = {};
+  bool ready = false;
+};
+thread_local SideCtx g_side[16];
+int g_side_disabled = -1;
+}  // namespace
+
+static int get_side(SideCtx** out) {
+  *out = nullptr;
+  if (g_side_disabled < 0) {
+    const char* e = getenv("AA_NO_SIDE_STREAM");
+    g_side_disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (g_side_disabled) return AA_OK;
+  int dev = 0;
+  AA_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return AA_OK;
+  SideCtx& c = g_side[dev];
+  if (!c.ready) {
+    AA_CHECK_CUDA(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    for (int i = 0; i < SIDE_EVENTS; ++i) AA_CHECK_CUDA(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
+    c.ready = true;
+  }
+  *out = &c;
+  return AA_OK;
+}
+
+// `to` waits for everything enqueued on `from` so far (event slot i of the pool)
+static int stream_dep(SideCtx* sc, int i, cudaStream_t from, cudaStream_t to) {
+  if (!sc || from == to) return AA_OK;
+  AA_CHECK_CUDA(cudaEventRecord(sc->ev[i], from));
+  AA_CHECK_CUDA(cudaStreamWaitEvent(to, sc->ev[i], 0));
+  return AA_OK;
 }
 
 // ---- instrumentation -------------------------------------------------------------------
@@ -543,11 +590,12 @@ int aa_decoder_forward(const aa_dims* d, const aa_weights* w, const float* V, co
   return AA_OK;
 }
 
-int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
-                        const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
-                        size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
-                        const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
-                        float* dc0, void* scratch, size_t scratch_bytes, void* stream) {
+static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                                 const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
+                                 size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
+                                 const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
+                                 float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
+                                 aa_grad_ready_fn on_ready, void* user) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && alpha && beta && d_scores && gw, "aa_decoder_backward: null pointer");
   AA_REQUIRE(gw->embed && gw->w_ih && gw->w_hh && gw->b_ih && gw->b_hh && gw->sen_wx && gw->sen_wh && gw->att_wv &&
@@ -570,7 +618,23 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
   const long long* cap = reinterpret_cast<const long long*>(captions);
   float* dVb = dV ? dV : sc.dV;
 
+  // Two lanes.  `cx` (the caller's stream) carries the critical path
+  //   dS -> du -> attention backward -> ds/dh -> sentinel backward -> dhs -> BPTT -> dx -> embedding scatter;
+  // `cs` (the library's side stream) carries everything nothing else waits for: the 11 weight-gradient
+  // contractions, dV += dP W_v and the sentinel's dx.  While the BPTT kernel (H/16 CTAs) walks its T dependent
+  // steps the rest of the chip works through the side lane.
+  SideCtx* side = nullptr;
+  AA_TRY(get_side(&side));
   const Ctx cx{d->precision, st};
+  const Ctx cs{d->precision, side ? side->side : st};
+  const cudaStream_t sd = cs.st;
+  int evi = 0;
+  auto to_side = [&]() { return stream_dep(side, evi++, st, sd); };   // side lane waits for the main lane so far
+  auto bucket_ready = [&](int bucket, cudaStream_t on) -> int {
+    if (ready_events && ready_events[bucket]) AA_CHECK_CUDA(cudaEventRecord((cudaEvent_t)ready_events[bucket], on));
+    if (on_ready) on_ready(bucket, user);
+    return AA_OK;
+  };
   const bool tc = cx.tc();
   const W16& h = sv.w16;
   const int ap = a_pad_of(*d);
@@ -584,8 +648,10 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
   const Mat dS = M2(d_scores, Vc, sc.dS16, Vc);
 
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
+  AA_TRY(to_side());
+  AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, N, dS, M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
+  AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));
   AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, nullptr, 0));
-  AA_TRY(mm_tn(cx, "gemm_vocab_dw", Vc, H, N, dS, M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
   // attention                                                   adaptive_attention.py:34-56
   AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, st));
   AttenBwdArgs ab{};
@@ -595,25 +661,30 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
   ab.ds = sc.ds; ab.dq = sc.dq; ab.dr = sc.dr; ab.dP = sc.dP; ab.dV = dVb; ab.dwh = gw->att_wh;
   ab.dq16 = tc ? sc.dq16 : nullptr; ab.dr16 = tc ? sc.dr16 : nullptr; ab.dP16 = nullptr; ab.a_pad = ap;
   AA_PROF("atten_bwd", st, launch_atten_bwd(ab, st));
-  if (tc) AA_PROF("cast_inputs", st, launch_cast2d(sc.dP, a, sc.dP16, ap, (long long)B * k, a, st));
   const Mat dR = M2(sc.dr, a, sc.dr16, ap), dQ = M2(sc.dq, a, sc.dq16, ap), dPm = M2(sc.dP, a, sc.dP16, ap);
+  AA_TRY(to_side());
+  AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, N, dR, M2(sv.s, H, sv.s16, H), gw->att_ws, H, false));
+  AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, N, dQ, M2(sv.hiddens, H, sv.hid16, H), gw->att_wg, H, false));
+  if (tc) AA_PROF("cast_inputs", sd, launch_cast2d(sc.dP, a, sc.dP16, ap, (long long)B * k, a, sd));
+  AA_TRY(mm_nn(cs, "gemm_att_dx", B * k, H, a, dPm, Wv, dVb, H, dVb, H));                             // dV += dP W_v
+  AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, B * k, dPm, M2(V, H, sv.V16, H), gw->att_wv, H, false));
   AA_TRY(mm_nn(cx, "gemm_att_dx", N, H, a, dR, Ws, sc.ds, H, sc.ds, H));                              // ds += dr W_s
-  AA_TRY(mm_tn(cx, "gemm_att_dw", a, H, N, dR, M2(sv.s, H, sv.s16, H), gw->att_ws, H, false));
   AA_TRY(mm_nn(cx, "gemm_att_dx", N, H, a, dQ, Wg, sc.du, H, sc.du, H));                              // dh = du + dq W_g
-  AA_TRY(mm_tn(cx, "gemm_att_dw", a, H, N, dQ, M2(sv.hiddens, H, sv.hid16, H), gw->att_wg, H, false));
-  AA_TRY(mm_nn(cx, "gemm_att_dx", B * k, H, a, dPm, Wv, dVb, H, dVb, H));                             // dV += dP W_v
-  AA_TRY(mm_tn(cx, "gemm_att_dw", a, H, B * k, dPm, M2(V, H, sv.V16, H), gw->att_wv, H, false));
   // sentinel                                                    adaptive_attention.py:79-83
   AA_TRY(launch_sentinel_bwd(sc.ds, sv.g, sv.cells, sc.da, sc.dcell, tc ? sc.da16 : nullptr, (long long)N * H, st));
   const Mat dA = M2(sc.da, H, sc.da16, H);
-  AA_TRY(mm_nn(cx, "gemm_sent_dx", N, 2 * E, H, dA, Wx, sc.dx, 2 * E, nullptr, 0));
-  AA_TRY(mm_tn(cx, "gemm_sent_dw", H, 2 * E, N, dA, X, gw->sen_wx, 2 * E, false));
+  AA_TRY(to_side());
+  AA_TRY(mm_nn(cs, "gemm_sent_dx", N, 2 * E, H, dA, Wx, sc.dx, 2 * E, nullptr, 0));
+  const int ev_dx = evi++;
+  if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_dx], sd));
+  AA_TRY(mm_tn(cs, "gemm_sent_dw", H, 2 * E, N, dA, X, gw->sen_wx, 2 * E, false));
   if (T > 1) {
     AA_TRY(mm_nn(cx, "gemm_sent_dx", N, H, H, dA, Wh, sc.dhs, H, nullptr, 0));
-    AA_TRY(mm_tn(cx, "gemm_sent_dw", H, H, N, dA, M2(sv.hs_prev, H, sv.hsprev16, H), gw->sen_wh, H, false));
+    AA_TRY(mm_tn(cs, "gemm_sent_dw", H, H, N, dA, M2(sv.hs_prev, H, sv.hsprev16, H), gw->sen_wh, H, false));
   } else {
-    AA_CHECK_CUDA(cudaMemsetAsync(gw->sen_wh, 0, sizeof(float) * (size_t)H * H, st));   // h~ = 0: no gradient (Q3)
+    AA_CHECK_CUDA(cudaMemsetAsync(gw->sen_wh, 0, sizeof(float) * (size_t)H * H, sd));   // h~ = 0: no gradient (Q3)
   }
+  AA_TRY(bucket_ready(AA_BUCKET_ATTEN, sd));   // (att_wh was finished by atten_bwd, which the side lane has waited for)
   // BPTT                                                        baseline_attention.py:167-178
   const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
   if (seq) {
@@ -644,16 +715,41 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
   if (dc0 && !seq) AA_TRY(launch_copy2d(dc0, H, sc.dc_rec, H, B, H, st));
   // LSTM parameter gradients, batched over all steps
   const Mat dG = M2(sc.dgates, 4 * H, sc.dgates16, 4 * H);
-  AA_TRY(mm_tn(cx, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, false));
-  AA_TRY(mm_tn(cx, "gemm_lstm_dw", 4 * H, H, N, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, false));   // steps t >= 1 (h~_0 rows are 0)
+  AA_TRY(to_side());
+  AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, false));
+  AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, H, N, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, false));   // steps t >= 1 (h~_0 rows are 0)
   if (h0)                                                                                                      // step 0
-    AA_TRY(mm_tn(cx, "gemm_lstm_dw", 4 * H, H, B, M2(sc.dgates, (long long)T * 4 * H, sc.dgates16, (long long)T * 4 * H),
+    AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, H, B, M2(sc.dgates, (long long)T * 4 * H, sc.dgates16, (long long)T * 4 * H),
                  M2(h0, H, sv.h016, H), gw->w_hh, H, true));
-  AA_PROF("colsum", st, launch_colsum(sc.dgates, 4 * H, N, 4 * H, gw->b_ih, gw->b_hh, st));
-  AA_TRY(mm_nn(cx, "gemm_lstm_dx", N, 2 * E, 4 * H, dG, Wih, sc.dx, 2 * E, sc.dx, 2 * E));                      // dx += dgates W_ih
+  AA_PROF("colsum", sd, launch_colsum(sc.dgates, 4 * H, N, 4 * H, gw->b_ih, gw->b_hh, sd));
+  AA_TRY(bucket_ready(AA_BUCKET_LSTM, sd));
+  // dx += dgates W_ih needs the sentinel's dx from the side lane
+  if (side) AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_dx], 0));
+  AA_TRY(mm_nn(cx, "gemm_lstm_dx", N, 2 * E, 4 * H, dG, Wih, sc.dx, 2 * E, sc.dx, 2 * E));
   // x = [embed(w); v_g]                                         baseline_attention.py:151-154
   AA_CHECK_CUDA(cudaMemsetAsync(gw->embed, 0, sizeof(float) * (size_t)Vc * E, st));
-  return launch_embed_bwd(cap, sc.dx, gw->embed, dv_g, B, T, E, Vc, st);
+  AA_TRY(launch_embed_bwd(cap, sc.dx, gw->embed, dv_g, B, T, E, Vc, st));
+  AA_TRY(bucket_ready(AA_BUCKET_EMBED, st));
+  return stream_dep(side, evi++, sd, st);   // join: the call is complete, in stream order, when `stream` says so
+}
+
+int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                        const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
+                        size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
+                        const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
+                        float* dc0, void* scratch, size_t scratch_bytes, void* stream) {
+  return decoder_backward_impl(d, w, V, v_g, captions, h0, c0, alpha, beta, saved, saved_bytes, d_scores, d_alpha, d_beta, d_hT,
+                               d_cT, gw, dV, dv_g, dh0, dc0, scratch, scratch_bytes, stream, nullptr, nullptr, nullptr);
+}
+
+int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                               const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
+                               size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
+                               const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
+                               float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
+                               aa_grad_ready_fn on_ready, void* user) {
+  return decoder_backward_impl(d, w, V, v_g, captions, h0, c0, alpha, beta, saved, saved_bytes, d_scores, d_alpha, d_beta, d_hT,
+                               d_cT, gw, dV, dv_g, dh0, dc0, scratch, scratch_bytes, stream, ready_events, on_ready, user);
 }
 
 int aa_pack_rows(const float* scores, int64_t n_cols, const int64_t* row_index, int64_t n_rows, float* packed, void* stream) {
@@ -677,14 +773,19 @@ int aa_unpack_rows(const float* d_packed, int64_t n_cols, const int64_t* row_ind
   return AA_OK;
 }
 
-int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, float* loss, float* dlogits,
-                     void* stream) {
+int aa_cross_entropy_denom(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom, float* loss,
+                           float* dlogits, void* stream) {
   AA_REQUIRE(loss, "aa_cross_entropy: loss is NULL");
   AA_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
   if (n_rows == 0) return AA_OK;
   AA_REQUIRE(logits && targets, "aa_cross_entropy: null pointer");
-  return launch_ce_fwd_bwd(logits, Vc, reinterpret_cast<const long long*>(targets), (int)n_rows, (int)Vc, loss, dlogits, Vc,
+  return launch_ce_fwd_bwd(logits, Vc, reinterpret_cast<const long long*>(targets), (int)n_rows, (int)Vc, loss, dlogits, Vc, denom,
                            (cudaStream_t)stream);
+}
+
+int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, float* loss, float* dlogits,
+                     void* stream) {
+  return aa_cross_entropy_denom(logits, n_rows, Vc, targets, n_rows, loss, dlogits, stream);
 }
 
 }  // extern "C"

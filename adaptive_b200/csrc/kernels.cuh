@@ -53,9 +53,10 @@ struct CastSegs {
   long long n[8];
 };
 int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s);
-// mean cross-entropy over rows + gradient: loss += -log_softmax(logits[r])[tgt[r]] / n ; dlogits = (softmax - onehot)/n
+// mean cross-entropy over rows + gradient: loss += -log_softmax(logits[r])[tgt[r]] / denom ; dlogits = (softmax - onehot)/denom
+// (denom <= 0: the row count n)
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
-                      long long ldd, cudaStream_t s);
+                      long long ldd, long long denom, cudaStream_t s);
 
 // ---- gemm_tc.cu (tcgen05 + TMA) ------------------------------------------------------------
 // D[m,n] = sum_k A(m,k) B(n,k) (+ beta*Cin + bias1[n] + bias2[n]); bf16 (elem_size 2) or tf32 (4) inputs,

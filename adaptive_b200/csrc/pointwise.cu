@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(PW_THREADS) argmax_gather_kernel(const float* 
 __global__ void __launch_bounds__(PW_THREADS) ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld,
                                                                 const long long* __restrict__ tgt, int n, int Vc,
                                                                 float* __restrict__ loss, float* __restrict__ dlogits,
-                                                                long long ldd) {
+                                                                long long ldd, float inv_n) {
   __shared__ float red[PW_THREADS / 32];
   __shared__ float bcast;
   const int r = blockIdx.x;
@@ -221,7 +221,6 @@ __global__ void __launch_bounds__(PW_THREADS) ce_fwd_bwd_kernel(const float* __r
   __syncthreads();
   sum = bcast;
   const long long t = tgt[r];
-  const float inv_n = 1.f / (float)n;
   if (threadIdx.x == 0) atomicAdd(loss, (logf(sum) + m - row[t]) * inv_n);
   if (dlogits) {
     const float inv = 1.f / sum;
@@ -439,9 +438,9 @@ int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s) {
 }
 
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
-                      long long ldd, cudaStream_t s) {
+                      long long ldd, long long denom, cudaStream_t s) {
   if (n == 0) return AA_OK;
-  ce_fwd_bwd_kernel<<<n, PW_THREADS, 0, s>>>(logits, ld, tgt, n, Vc, loss, dlogits, ldd);
+  ce_fwd_bwd_kernel<<<n, PW_THREADS, 0, s>>>(logits, ld, tgt, n, Vc, loss, dlogits, ldd, 1.f / (float)(denom > 0 ? denom : n));
   AA_CHECK_LAUNCH("ce_fwd_bwd");
   return AA_OK;
 }

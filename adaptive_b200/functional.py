@@ -217,19 +217,26 @@ def packed_targets(captions, lengths: Sequence[int]):
 _ROW_INDEX_CACHE: Dict[tuple, tuple] = {}
 
 
-def pack_scores(scores: torch.Tensor, lengths: Sequence[int]):
-    # the device copy of the row index is cached per (lengths, T, device): repeated shapes cost no
-    # host->device copy, which also keeps the call capturable into a CUDA graph
-    key = (tuple(int(x) for x in lengths), scores.shape[1], scores.device.index)
+def cached_row_index(lengths: Sequence[int], T: int, device):
+    """(device row index b*T+t of every packed row, host batch_sizes).  The device copy is cached per
+    (lengths, T, device): repeated shapes cost no host->device copy, which also keeps the callers
+    capturable into a CUDA graph."""
+    device = torch.device(device)
+    key = (tuple(int(x) for x in lengths), int(T), device.type, device.index)
     hit = _ROW_INDEX_CACHE.get(key)
     if hit is None:
-        idx, bs = packed_row_index(lengths, scores.shape[1])
-        hit = (torch.tensor(idx, dtype=torch.int64, device=scores.device), torch.tensor(bs, dtype=torch.int64))
+        idx, bs = packed_row_index(lengths, T)
+        hit = (torch.tensor(idx, dtype=torch.int64, device=device), torch.tensor(bs, dtype=torch.int64))
         if len(_ROW_INDEX_CACHE) > 256:
             _ROW_INDEX_CACHE.clear()
         _ROW_INDEX_CACHE[key] = hit
-    data = _PackRowsFn.apply(scores, hit[0])
-    return torch.nn.utils.rnn.PackedSequence(data, hit[1])
+    return hit
+
+
+def pack_scores(scores: torch.Tensor, lengths: Sequence[int]):
+    row_index, batch_sizes = cached_row_index(lengths, scores.shape[1], scores.device)
+    data = _PackRowsFn.apply(scores, row_index)
+    return torch.nn.utils.rnn.PackedSequence(data, batch_sizes)
 
 
 class _CrossEntropyFn(torch.autograd.Function):

@@ -1,0 +1,322 @@
+"""Multi-GPU drivers: one process per GPU (``torchrun``), ``torch.distributed`` for the plumbing.
+
+The reference's only multi-GPU scheme is ``nn.DataParallel`` around the encoder and the adaptive
+block (``baseline_attention.py:184-187,215-218``; ``adaptive_attention.py:178-181``): single
+process, parameters re-broadcast on every forward, logits gathered to GPU 0, the LSTM loop not
+parallelised at all.  It is not reproduced.  Here:
+
+* **decoding** shards the images into contiguous ranges, one per rank, with *no* data-path
+  collective (images are independent; beams never cross images).  Gathering the ids at the end
+  is control plane.
+* **training** is data parallel over the batch: weights replicated, one exchange step — a
+  sum all-reduce of the 13 decoder gradients.  The gradients live in four flat buckets in the
+  order in which the hand-written backward finishes them (``AA_BUCKET_*`` in
+  ``include/adaptive_b200.h``: mlp -> attention/sentinel -> LSTM -> embedding);
+  ``aa_decoder_backward_hooked`` reports each bucket as soon as its last kernel is enqueued and
+  the bucket's all-reduce starts on the communication stream while the rest of the backward
+  (notably the whole BPTT) is still running.  The loss and its gradient are normalised by the
+  GLOBAL packed-token count, so the reduced gradients equal those of the reference's
+  single-process mean cross-entropy (``train.py:63,208``) on the concatenated batch.
+
+Everything that does not touch the device (sharding arithmetic, bucket layout, the reducer) works
+with the ``gloo`` backend on CPU tensors and is tested that way (``tests/test_parallel_cpu.py``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._lib import WEIGHT_FIELDS
+
+# gradient buckets in backward-ready order (must match AA_BUCKET_* in include/adaptive_b200.h)
+BUCKETS: Tuple[Tuple[str, ...], ...] = (
+    ("mlp_w", "mlp_b"),
+    ("att_wv", "att_wg", "att_ws", "att_wh", "sen_wx", "sen_wh"),
+    ("w_ih", "w_hh", "b_ih", "b_hh"),
+    ("embed",),
+)
+BUCKET_OF: Dict[str, int] = {f: b for b, fs in enumerate(BUCKETS) for f in fs}
+assert sorted(BUCKET_OF) == sorted(WEIGHT_FIELDS)
+
+
+# ---------------------------------------------------------------------------------------------
+# sharding arithmetic (decode)
+# ---------------------------------------------------------------------------------------------
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous near-equal split of ``n`` images: the first ``n % world`` ranks get one more."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_encoded(encoded, rank: int, world: int):
+    """Slice an encoded batch ``(V, v_g, (h0, c0))`` to this rank's image range.
+    States may be ``[1,B,H]`` (nn.LSTM layout), ``[B,1,H]`` (what the reference encoder returns) or ``[B,H]``."""
+    V, v_g, states = encoded
+    B = V.shape[0]
+    lo, hi = shard_range(B, rank, world)
+
+    def cut(s):
+        if s is None:
+            return None
+        if s.dim() == 3 and s.shape[0] == 1 and s.shape[1] == B:
+            return s[:, lo:hi]
+        return s[lo:hi]
+
+    st = None if states is None else tuple(cut(s) for s in states)
+    return V[lo:hi], v_g[lo:hi], st
+
+
+def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Concatenate every rank's rows in rank order (ranges from ``shard_range``): the end-of-decode
+    collection of ids.  Uneven shards are padded to the largest one for the all_gather."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    most = max(hi - lo for lo, hi in sizes)
+    pad = local.new_zeros((most,) + tuple(local.shape[1:]))
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+
+
+def sharded_sampler(model, encoded, max_len: int = 30, beam: int = 0, gather: bool = False, group=None):
+    """``Encoder2Decoder.sampler`` over this rank's contiguous image range (no collective on the
+    data path).  Returns the local ``(ids, attention, Beta)``; with ``gather=True`` the ids of
+    all ranks, in image order, instead of the local ones."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_total = encoded[0].shape[0]
+    local = shard_encoded(encoded, rank, world)
+    out = model.beam_sampler(local, beam=beam, max_len=max_len) if beam >= 1 else model.sampler(local, max_len=max_len)
+    if gather:
+        return (gather_rows(out[0], n_total, group),) + tuple(out[1:])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient buckets + reducer (training)
+# ---------------------------------------------------------------------------------------------
+class GradBuckets:
+    """One flat fp32 buffer per bucket with a view per parameter (``aa_weights`` field order)."""
+
+    def __init__(self, shapes: Dict[str, Sequence[int]], device, dtype=torch.float32):
+        self.flat: List[torch.Tensor] = []
+        self.views: Dict[str, torch.Tensor] = {}
+        for fields in BUCKETS:
+            sizes = [int(torch.Size(shapes[f]).numel()) for f in fields]
+            # 64-element (256 B) alignment of every view: the kernels store 128-bit vectors
+            offs, total = [], 0
+            for n in sizes:
+                offs.append(total)
+                total += (n + 63) // 64 * 64
+            buf = torch.zeros(total, device=device, dtype=dtype)
+            self.flat.append(buf)
+            for f, o, n in zip(fields, offs, sizes):
+                self.views[f] = buf[o:o + n].view(*shapes[f])
+
+    def ordered(self) -> Tuple[torch.Tensor, ...]:
+        return tuple(self.views[f] for f in WEIGHT_FIELDS)
+
+    def nbytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self.flat)
+
+
+class BucketReducer:
+    """Sum all-reduce of the buckets, each started as soon as it is reported ready.
+
+    On CUDA the collective is issued under ``comm_stream`` after that stream has been made to
+    wait for ``ready_event`` (recorded by the backward on whichever of its lanes finished the
+    bucket), so it overlaps the remaining backward kernels; ``finish`` makes the caller's
+    current stream wait for all of them.  On CPU (gloo) it degenerates to async all-reduces."""
+
+    def __init__(self, buckets: GradBuckets, group=None, average: bool = False):
+        self.buckets, self.group, self.average = buckets, group, average
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cuda = buckets.flat[0].is_cuda
+        self.works: List = []
+        self.order: List[int] = []
+        if self.cuda:
+            self.comm_stream = torch.cuda.Stream(device=buckets.flat[0].device)
+            self.events = [torch.cuda.Event() for _ in BUCKETS]
+            for e in self.events:      # the raw cudaEvent_t exists only after a first record
+                e.record()
+        else:
+            self.comm_stream, self.events = None, [None] * len(BUCKETS)
+
+    def event_handles(self):
+        """``void* ready_events[AA_NUM_BUCKETS]`` for ``aa_decoder_backward_hooked`` (CUDA only)."""
+        arr = (ctypes.c_void_p * len(BUCKETS))()
+        for i, e in enumerate(self.events):
+            arr[i] = e.cuda_event
+        return arr
+
+    def start(self):
+        self.works, self.order = [], []
+
+    def on_ready(self, bucket: int):
+        self.order.append(bucket)
+        if self.world == 1:
+            return
+        flat = self.buckets.flat[bucket]
+        if self.cuda:
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(self.events[bucket])
+                self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        if self.cuda and self.world > 1:
+            with torch.cuda.stream(self.comm_stream):
+                for w in self.works:
+                    w.wait()                      # comm_stream waits for NCCL's stream
+                if self.average:
+                    for flat in self.buckets.flat:
+                        flat.div_(self.world)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            for w in self.works:
+                w.wait()
+            if self.average and self.world > 1:
+                for flat in self.buckets.flat:
+                    flat.div_(self.world)
+        self.works = []
+
+
+_COUNT_CACHE: Dict[tuple, int] = {}
+
+
+def global_token_count(lengths: Sequence[int], group=None) -> int:
+    """Sum over ranks of this rank's packed-row count ``sum(lengths)`` (cached per lengths tuple, so
+    a steady-state training loop does no host-side collective)."""
+    n_local = int(sum(int(x) for x in lengths))
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return n_local
+    key = (tuple(int(x) for x in lengths), id(group))
+    hit = _COUNT_CACHE.get(key)
+    if hit is None:
+        counts: List[Optional[int]] = [None] * dist.get_world_size(group)
+        dist.all_gather_object(counts, n_local, group=group)
+        hit = int(sum(counts))
+        if len(_COUNT_CACHE) > 256:
+            _COUNT_CACHE.clear()
+        _COUNT_CACHE[key] = hit
+    return hit
+
+
+class DataParallelTrainer:
+    """Data-parallel training step of the decoder over the C ABI, no autograd in the loop.
+
+    ``step(encoded, captions, lengths, targets) -> loss`` runs forward -> packed rows -> cross-entropy
+    (global-count normalised) -> hooked backward with bucketed, overlapped all-reduce, and leaves
+    the reduced gradients in ``p.grad`` of ``model.decoder``'s parameters (views of the flat
+    buckets; the caller's optimizer / ``clip_grad_norm_(model.decoder.LSTM.parameters(), 5)`` of
+    ``train.py:213-214`` work on them as usual).  ``loss`` is the global mean CE (device scalar).
+    With one process it is simply the fused single-GPU training step."""
+
+    def __init__(self, model, group=None, overlap: bool = True):
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.model, self.group, self.overlap = model, group, overlap
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.weights = model.decoder.weights()
+        dev = self.weights[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("DataParallelTrainer needs the decoder on a CUDA device (no CPU fallback)")
+        self.device = dev
+        self.buckets = GradBuckets({f: tuple(t.shape) for f, t in zip(WEIGHT_FIELDS, self.weights)}, dev)
+        self.reducer = BucketReducer(self.buckets, group)
+        for p, g in zip(self.weights, self.buckets.ordered()):
+            p.grad = g
+        self._cb_type = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)
+        self._cb = self._cb_type(lambda bucket, _user: self.reducer.on_ready(int(bucket)))
+        self._bufs: Dict[tuple, dict] = {}
+
+    def _buffers(self, B, T, k, H, E, Vc, a, n_rows, prec):
+        from . import functional as F_aa
+
+        key = (B, T, k, n_rows, prec)
+        hit = self._bufs.get(key)
+        if hit is None:
+            dev = self.device
+            d = F_aa.make_dims(B, T, k, H, E, Vc, a, prec)
+            f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+            u8 = lambda n: torch.empty(n, device=dev, dtype=torch.uint8)
+            hit = {
+                "d": d, "scores": f32(B, T, Vc), "alpha": f32(B, T, k), "beta": f32(B, T, 1), "hT": f32(B, H), "cT": f32(B, H),
+                "saved": u8(self.lib.aa_decoder_saved_bytes(ctypes.byref(d))),
+                "scratch": u8(self.lib.aa_decoder_bwd_scratch_bytes(ctypes.byref(d))),
+                "packed": f32(n_rows, Vc), "dpacked": f32(n_rows, Vc), "dscores": f32(B, T, Vc),
+                "loss": torch.zeros((), device=dev, dtype=torch.float32), "dV": f32(B, k, H), "dvg": f32(B, E),
+                "dh0": f32(B, H), "dc0": f32(B, H),
+            }
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            self._bufs[key] = hit
+        return hit
+
+    def step(self, encoded, captions: torch.Tensor, lengths: Sequence[int], targets: torch.Tensor) -> torch.Tensor:
+        from . import functional as F_aa
+        from ._lib import AAWeightGrads, check
+
+        lib = self.lib
+        V, v_g, states = encoded
+        V, v_g = F_aa._f32c(V), F_aa._f32c(v_g)
+        B, k, H = V.shape
+        E, T = v_g.shape[1], captions.shape[1]
+        w = self.weights
+        Vc, a = w[0].shape[0], w[7].shape[0]
+        h0 = c0 = None
+        if states is not None:
+            h0, c0 = F_aa._states2d(states[0], B, H), F_aa._states2d(states[1], B, H)
+        captions = captions.to(torch.int64).contiguous()
+        targets = targets.to(torch.int64).contiguous()
+        prec = F_aa.PRECISIONS[self.model.decoder.precision]
+        row_index, _ = F_aa.cached_row_index(lengths, T, self.device)
+        n_rows = row_index.numel()
+        denom = global_token_count(lengths, self.group)
+        b = self._buffers(B, T, k, H, E, Vc, a, n_rows, prec)
+        d, st, P = b["d"], F_aa._stream(self.device), F_aa._ptr
+        ws = F_aa.weights_struct(w)
+        gs = AAWeightGrads()
+        for name, t in zip(WEIGHT_FIELDS, self.buckets.ordered()):
+            setattr(gs, name, t.data_ptr())
+        with torch.cuda.device(self.device):
+            check(lib.aa_decoder_forward(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(b["scores"]),
+                                         P(b["alpha"]), P(b["beta"]), P(b["hT"]), P(b["cT"]), P(b["saved"]), b["saved"].numel(), st),
+                  "aa_decoder_forward")
+            check(lib.aa_pack_rows(P(b["scores"]), Vc, P(row_index), n_rows, P(b["packed"]), st), "aa_pack_rows")
+            check(lib.aa_cross_entropy_denom(P(b["packed"]), n_rows, Vc, P(targets), denom, P(b["loss"]), P(b["dpacked"]), st),
+                  "aa_cross_entropy_denom")
+            check(lib.aa_unpack_rows(P(b["dpacked"]), Vc, P(row_index), n_rows, B * T, P(b["dscores"]), st), "aa_unpack_rows")
+            self.reducer.start()
+            hooked = self.overlap and self.world > 1
+            check(lib.aa_decoder_backward_hooked(
+                ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(b["alpha"]), P(b["beta"]), P(b["saved"]),
+                b["saved"].numel(), P(b["dscores"]), None, None, None, None, ctypes.byref(gs), P(b["dV"]), P(b["dvg"]),
+                P(b["dh0"]) if h0 is not None else None, P(b["dc0"]) if c0 is not None else None, P(b["scratch"]),
+                b["scratch"].numel(), st, self.reducer.event_handles() if hooked else None,
+                ctypes.cast(self._cb, ctypes.c_void_p) if hooked else None, None), "aa_decoder_backward_hooked")
+            if self.world > 1 and not hooked:          # non-overlapped variant: same buckets, after the backward
+                for i in range(len(BUCKETS)):
+                    self.reducer.events[i].record()
+                    self.reducer.on_ready(i)
+            self.reducer.finish()
+            loss = b["loss"]
+            if self.world > 1:
+                loss = loss.clone()
+                dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        for p, g in zip(self.weights, self.buckets.ordered()):
+            p.grad = g
+        self.input_grads = {"V": b["dV"], "v_g": b["dvg"], "h0": b["dh0"] if h0 is not None else None,
+                            "c0": b["dc0"] if c0 is not None else None}
+        return loss

@@ -212,6 +212,11 @@ int aa_unpack_rows(const float* d_packed, int64_t n_cols, const int64_t* row_ind
  * after the hot path).  loss: device scalar (overwritten); dlogits may be NULL. */
 int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, float* loss,
                      float* dlogits, void* stream);
+/* Same with an explicit denominator: loss = sum_r nll_r / denom, dlogits = (softmax - onehot) / denom.  Data-parallel
+ * training passes the GLOBAL packed-row count so that the all-reduced (summed) gradients equal the reference's
+ * single-process mean (train.py:63,208). */
+int aa_cross_entropy_denom(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom,
+                           float* loss, float* dlogits, void* stream);
 
 /* ---- decoding: Encoder2Decoder.sampler -------------------------------------------- */
 
