@@ -19,7 +19,7 @@ class AADims(Structure):
     _fields_ = [(n, c_int32) for n in ("B", "T", "k", "a", "H", "E", "Vc", "precision")]
 
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32X3 = 0, 1, 2
 
 
 WEIGHT_FIELDS = ("embed", "w_ih", "w_hh", "b_ih", "b_hh", "sen_wx", "sen_wh",
@@ -66,6 +66,8 @@ SIGNATURES = {
     "aa_linear_forward": (c_int, [c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "aa_gemm": (c_int, [c_int, c_int, c_int, c_int, P, c_int64, c_int, P, c_int64, c_int, P, c_int64, ctypes.c_float, P, P,
                         c_int64, P]),
+    "aa_split_tf32": (c_int, [P, c_int64, c_int64, c_int, P, c_int, P]),
+    "aa_gemm_split3": (c_int, [c_int, c_int, c_int, P, P, P, P, c_int64, P]),
     "aa_precompute_P": (c_int, [_D, P, P, P, P]),
     "aa_sentinel_forward": (c_int, [_D, P, P, P, P, P, P, P, P]),
     "aa_atten_workspace_bytes": (c_size_t, [_D]),

@@ -420,6 +420,20 @@ int aa_gemm(int engine, int M, int N, int K, const void* A, int64_t lda, int a_k
   return launch_gemm_tc(g, (cudaStream_t)stream);
 }
 
+int aa_split_tf32(const float* src, int64_t ld_src, int64_t rows, int cols, float* dst, int Kp, void* stream) {
+  AA_REQUIRE(src && dst && rows >= 0 && cols >= 1, "aa_split_tf32: bad argument");
+  return launch_split_tf32(src, ld_src, rows, cols, dst, Kp, (cudaStream_t)stream);
+}
+
+int aa_gemm_split3(int M, int N, int Kp, const float* A_split, const float* B_split, const float* bias, float* D, int64_t ldd,
+                   void* stream) {
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = Kp; g.elem_size = 4; g.split3 = 1;
+  g.A = A_split; g.lda = 2LL * Kp; g.B = B_split; g.ldb = 2LL * Kp;
+  g.D32 = D; g.ldd32 = ldd; g.bias1 = bias; g.beta = 0.f;
+  return launch_gemm_tc(g, (cudaStream_t)stream);
+}
+
 int aa_precompute_P(const aa_dims* d, const float* V, const float* att_wv, float* P, void* stream) {
   AA_TRY(check_dims(d, false));
   AA_REQUIRE(V && att_wv && P, "aa_precompute_P: null pointer");

@@ -56,7 +56,14 @@ __global__ void __launch_bounds__(DS_THREADS) decode_step_kernel(const DecodeSte
       AA_CELL(x) AA_CELL(y) AA_CELL(z) AA_CELL(w)
 #undef AA_CELL
       *reinterpret_cast<float4*>(p.c + b * H + c) = cn;
-      *reinterpret_cast<float4*>(p.h_out + b * p.ld_h + c) = hn;
+      if (p.split) {
+        float4 hi, lo;
+        split_tf32(hn.x, hi.x, lo.x); split_tf32(hn.y, hi.y, lo.y); split_tf32(hn.z, hi.z, lo.z); split_tf32(hn.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(p.h_out + b * p.ld_h + c) = hi;
+        *reinterpret_cast<float4*>(p.h_out + b * p.ld_h + p.h_lo_off + c) = lo;
+      } else {
+        *reinterpret_cast<float4*>(p.h_out + b * p.ld_h + c) = hn;
+      }
       *reinterpret_cast<float4*>(hs + g * H + c) = hn;
       *reinterpret_cast<float4*>(ss + g * H + c) = sn;
     }
@@ -164,17 +171,242 @@ __global__ void __launch_bounds__(DS_THREADS) decode_step_kernel(const DecodeSte
       o.y = beta * sv.y + (1.f - beta) * acc.y + hv.y;
       o.z = beta * sv.z + (1.f - beta) * acc.z + hv.z;
       o.w = beta * sv.w + (1.f - beta) * acc.w + hv.w;
-      *reinterpret_cast<float4*>(p.u + b * H + c) = o;
+      float* ur = p.u + b * (p.ld_u ? p.ld_u : (long long)H) + c;
+      if (p.split) {
+        float4 hi, lo;
+        split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(ur) = hi;
+        *reinterpret_cast<float4*>(ur + p.u_lo_off) = lo;
+      } else {
+        *reinterpret_cast<float4*>(ur) = o;
+      }
     }
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core decode pipeline (AA_PREC_TF32X3): the per-step work is cut where the data dependencies are
+//   gate GEMM -> dec_cell_kernel -> q/r GEMM -> dec_atten_kernel -> vocabulary GEMM (+ arg-max)
+// so that W_g / W_s run on tcgen05 like the gate and vocabulary contractions, and the attention kernel is a pure
+// stream over V with no block-level synchronisation.
+// ---------------------------------------------------------------------------------------------
+
+// LSTM pointwise + sentinel gate (baseline_attention.py:172, adaptive_attention.py:79-83 with h~ = 0, Q3).
+// Writes c in place, h and s as tf32 (hi, lo) pairs into the A-operand rows [emb | h | s] and as plain fp32 [h | s].
+__global__ void __launch_bounds__(256) dec_cell_kernel(const DecodeCellArgs p) {
+  const int H = p.H, H4 = H / 4;
+  const long long total = (long long)p.R * H4;
+  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long long)gridDim.x * blockDim.x) {
+    const long long r = item / H4;
+    const int c = (int)(item % H4) * 4;
+    const float* pre = p.gates + r * 5 * H;
+    const float4 pi = ldg4_stream(pre + c);
+    const float4 pf = ldg4_stream(pre + H + c);
+    const float4 pg = ldg4_stream(pre + 2 * H + c);
+    const float4 po = ldg4_stream(pre + 3 * H + c);
+    const float4 ps = ldg4_stream(pre + 4 * H + c);
+    const float4 cp = *reinterpret_cast<const float4*>(p.c + r * H + c);
+    float4 cn, hn, sn;
+#define AA_CELL(X)                                                               \
+  {                                                                              \
+    const float cc = sigmoidf_acc(pf.X) * cp.X + sigmoidf_acc(pi.X) * tanhf(pg.X); \
+    const float tc = tanhf(cc);                                                  \
+    cn.X = cc;                                                                   \
+    hn.X = sigmoidf_acc(po.X) * tc;                                              \
+    sn.X = sigmoidf_acc(ps.X) * tc;                                              \
+  }
+    AA_CELL(x) AA_CELL(y) AA_CELL(z) AA_CELL(w)
+#undef AA_CELL
+    *reinterpret_cast<float4*>(p.c + r * H + c) = cn;
+    *reinterpret_cast<float4*>(p.hs + r * 2 * H + c) = hn;
+    *reinterpret_cast<float4*>(p.hs + r * 2 * H + H + c) = sn;
+    float4 hi, lo;
+    float* arow = p.A + r * p.ldA;
+    split_tf32(hn.x, hi.x, lo.x); split_tf32(hn.y, hi.y, lo.y); split_tf32(hn.z, hi.z, lo.z); split_tf32(hn.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(arow + p.h_off + c) = hi;
+    *reinterpret_cast<float4*>(arow + p.lo_off + p.h_off + c) = lo;
+    split_tf32(sn.x, hi.x, lo.x); split_tf32(sn.y, hi.y, lo.y); split_tf32(sn.z, hi.z, lo.z); split_tf32(sn.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(arow + p.h_off + H + c) = hi;
+    *reinterpret_cast<float4*>(arow + p.lo_off + p.h_off + H + c) = lo;
+  }
+}
+
+// Scores + tanh + k-way / (k+1)-way softmax + beta-gated context + (c_hat + h): ONE WARP PER ROW, no __syncthreads.
+//   z_i = w_h . tanh(P_i + q)  (lanes over the attention dim, coalesced P rows, warp-shuffle sums)
+//   alpha, beta: warp-shuffle max / sum
+//   ctx = sum_i alpha_i V_i: each lane owns 4*NCH columns, V rows streamed with 128-bit coalesced loads
+//   (R rows in flight per lane), read exactly once (L1::no_allocate)
+// HBM-bound on V (k*H*4 bytes per image and step).
+constexpr int DA_WARPS = 8;
+template <int NCH, int RU>
+__global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAttenArgs p) {
+  extern __shared__ float da_sm[];
+  const int k = p.k, a = p.a, H = p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* zs = da_sm + (size_t)warp * (k + 1);    // this warp's scores, then alphas
+  const int j0 = lane, j1 = lane + 32, j2 = lane + 64, j3 = lane + 96;       // a <= 128
+  const float w0 = j0 < a ? p.wh[j0] : 0.f, w1 = j1 < a ? p.wh[j1] : 0.f, w2 = j2 < a ? p.wh[j2] : 0.f, w3 = j3 < a ? p.wh[j3] : 0.f;
+  for (long long r = (long long)blockIdx.x * DA_WARPS + warp; r < p.R; r += (long long)gridDim.x * DA_WARPS) {
+    const long long b = r / p.beam;
+    const float* qr = p.qr + r * 2 * a;
+    const float q0 = j0 < a ? qr[j0] : 0.f, q1 = j1 < a ? qr[j1] : 0.f, q2 = j2 < a ? qr[j2] : 0.f, q3 = j3 < a ? qr[j3] : 0.f;
+    // ---- scores ----
+    const float* Pb = p.P + b * k * a;
+    for (int i0 = 0; i0 < k; i0 += 4) {
+      float acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u] = 0.f;
+        if (i0 + u < k) {
+          const float* prow = Pb + (long long)(i0 + u) * a;
+          if (j0 < a) acc[u] = w0 * tanhf(__ldg(prow + j0) + q0);
+          if (j1 < a) acc[u] = fmaf(w1, tanhf(__ldg(prow + j1) + q1), acc[u]);
+          if (j2 < a) acc[u] = fmaf(w2, tanhf(__ldg(prow + j2) + q2), acc[u]);
+          if (j3 < a) acc[u] = fmaf(w3, tanhf(__ldg(prow + j3) + q3), acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float z = warp_sum(acc[u]);
+        if (lane == u && i0 + u < k) zs[i0 + u] = z;
+      }
+    }
+    {   // sentinel score z_s = w_h . tanh(r)
+      float acc = 0.f;
+      if (j0 < a) acc = w0 * tanhf(qr[a + j0]);
+      if (j1 < a) acc = fmaf(w1, tanhf(qr[a + j1]), acc);
+      if (j2 < a) acc = fmaf(w2, tanhf(qr[a + j2]), acc);
+      if (j3 < a) acc = fmaf(w3, tanhf(qr[a + j3]), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) zs[k] = acc;
+    }
+    __syncwarp();
+    // ---- softmaxes (adaptive_attention.py:39,51) ----
+    float m = -INFINITY;
+    for (int i = lane; i < k; i += 32) m = fmaxf(m, zs[i]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int i = lane; i < k; i += 32) sum += expf(zs[i] - m);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    const float zsent = zs[k];
+    const float m1 = fmaxf(m, zsent);
+    float sum1 = 0.f;
+    for (int i = lane; i < k; i += 32) sum1 += expf(zs[i] - m1);
+    sum1 = warp_sum(sum1);
+    const float es = expf(zsent - m1);
+    const float beta = es / (sum1 + es);
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+      const float al = expf(zs[i] - m) * inv;
+      zs[i] = al;
+      p.alpha[r * p.ld_alpha + i] = al;
+    }
+    if (lane == 0) p.beta[r * p.ld_beta] = beta;
+    __syncwarp();
+    // ---- context over V, c_hat, u = c_hat + h ----
+    const float* Vb = p.V + b * k * H;
+    float4 acc[NCH];
+#pragma unroll
+    for (int n = 0; n < NCH; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = 0;
+    for (; i + RU <= k; i += RU) {
+      float4 v[RU][NCH];
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+#pragma unroll
+        for (int n = 0; n < NCH; ++n) {
+          const int c = lane * 4 + n * 128;
+          v[u][n] = c < H ? ldg4_stream(Vb + (long long)(i + u) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const float al = zs[i + u];
+#pragma unroll
+        for (int n = 0; n < NCH; ++n) {
+          acc[n].x = fmaf(al, v[u][n].x, acc[n].x); acc[n].y = fmaf(al, v[u][n].y, acc[n].y);
+          acc[n].z = fmaf(al, v[u][n].z, acc[n].z); acc[n].w = fmaf(al, v[u][n].w, acc[n].w);
+        }
+      }
+    }
+    for (; i < k; ++i) {
+      const float al = zs[i];
+#pragma unroll
+      for (int n = 0; n < NCH; ++n) {
+        const int c = lane * 4 + n * 128;
+        if (c < H) {
+          const float4 v = ldg4_stream(Vb + (long long)i * H + c);
+          acc[n].x = fmaf(al, v.x, acc[n].x); acc[n].y = fmaf(al, v.y, acc[n].y);
+          acc[n].z = fmaf(al, v.z, acc[n].z); acc[n].w = fmaf(al, v.w, acc[n].w);
+        }
+      }
+    }
+    const float* hs = p.hs + r * 2 * H;
+    float* urow = p.u + r * p.ld_u;
+#pragma unroll
+    for (int n = 0; n < NCH; ++n) {
+      const int c = lane * 4 + n * 128;
+      if (c < H) {
+        const float4 hv = *reinterpret_cast<const float4*>(hs + c);
+        const float4 sv = *reinterpret_cast<const float4*>(hs + H + c);
+        float4 o;
+        o.x = beta * sv.x + (1.f - beta) * acc[n].x + hv.x;
+        o.y = beta * sv.y + (1.f - beta) * acc[n].y + hv.y;
+        o.z = beta * sv.z + (1.f - beta) * acc[n].z + hv.z;
+        o.w = beta * sv.w + (1.f - beta) * acc[n].w + hv.w;
+        float4 hi, lo;
+        split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(urow + c) = hi;
+        *reinterpret_cast<float4*>(urow + p.u_lo_off + c) = lo;
+      }
+    }
+    __syncwarp();   // zs is reused by this warp's next row
+  }
+}
+
+template <int NCH, int RU>
+int launch_da(const DecodeAttenArgs& p, cudaStream_t s) {
+  const size_t smem = sizeof(float) * DA_WARPS * (size_t)(p.k + 1);
+  auto kern = dec_atten_kernel<NCH, RU>;
+  int occ = 1;
+  AA_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DA_WARPS * 32, smem));
+  if (occ < 1) occ = 1;
+  const long long blocks = (p.R + DA_WARPS - 1) / DA_WARPS;
+  const long long cap = (long long)num_sms() * occ;
+  kern<<<(unsigned)(blocks < cap ? blocks : cap), DA_WARPS * 32, smem, s>>>(p);
+  AA_CHECK_LAUNCH("dec_atten");
+  return AA_OK;
+}
+
 }  // namespace
+
+int launch_decode_cell(const DecodeCellArgs& p, cudaStream_t s) {
+  AA_REQUIRE(p.H % 4 == 0 && p.ldA % 4 == 0 && p.h_off % 4 == 0 && p.lo_off % 4 == 0, "decode_cell: H, ldA and the offsets must be multiples of 4");
+  if (p.R == 0) return AA_OK;
+  const long long total = (long long)p.R * (p.H / 4);
+  const long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  dec_cell_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(p);
+  AA_CHECK_LAUNCH("dec_cell");
+  return AA_OK;
+}
+
+int launch_decode_atten(const DecodeAttenArgs& p, cudaStream_t s) {
+  AA_REQUIRE(p.H % 4 == 0 && p.H <= 1024, "decode_atten: H must be a multiple of 4 and <= 1024 (got %d)", p.H);
+  AA_REQUIRE(p.a <= 128 && p.k >= 1 && p.k <= 4096, "decode_atten: need a <= 128 and 1 <= k <= 4096");
+  AA_REQUIRE(p.beam >= 1 && p.ld_u % 4 == 0 && p.u_lo_off % 4 == 0, "decode_atten: bad beam / u layout");
+  if (p.R == 0) return AA_OK;
+  if (p.H <= 128) return launch_da<1, 8>(p, s);
+  if (p.H <= 256) return launch_da<2, 8>(p, s);
+  if (p.H <= 512) return launch_da<4, 4>(p, s);
+  return launch_da<8, 2>(p, s);
+}
 
 int launch_decode_step(const DecodeStepArgs& p, cudaStream_t s) {
   AA_REQUIRE(p.H % 4 == 0, "decode_step: H must be a multiple of 4 (got %d)", p.H);
   AA_REQUIRE(p.beam >= 1, "decode_step: beam must be >= 1");
-  AA_REQUIRE(p.ld_h % 4 == 0, "decode_step: ld_h must be a multiple of 4");
+  AA_REQUIRE(p.ld_h % 4 == 0 && p.ld_u % 4 == 0 && p.h_lo_off % 4 == 0 && p.u_lo_off % 4 == 0,
+             "decode_step: row strides and lo offsets must be multiples of 4");
   if (p.B == 0) return AA_OK;
   const size_t smem = sizeof(float) * ((size_t)2 * G * p.H + 2 * G * p.a + G * (p.k + 1) + G * p.k + p.a + G);
   AA_REQUIRE(smem <= 200 * 1024, "decode_step: H=%d k=%d too large for shared memory", p.H, p.k);

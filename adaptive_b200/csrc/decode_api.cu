@@ -27,6 +27,11 @@ struct Carver {
 
 struct DecodeWs {
   float *Wcat, *P, *stat, *Acat, *Acat2, *gates, *c, *c2, *u, *logits;
+  // AA_PREC_TF32X3: the A/B operands of the two per-step contractions are stored as tf32 (hi | lo) row pairs
+  // rows of the A operand: [emb (E) | h (H) | s (H)] hi half, padded to `lo` columns, then the lo half; the gate GEMM
+  // reads the [emb | h] window, the q/r GEMM the [h | s] window.  W2 = [[W_g, 0], [W_g, W_s]] gives [q | r] in one GEMM.
+  float *Wp_s, *pmax, *W2, *hs, *qr; int* pidx;
+  int split, bm, K, Kp, lo, K2p, Hp, ldA, ldU, tiles_n;
   // beam only
   float *cum, *row_max, *row_lsum, *rec_alpha, *rec_beta;
   int *rec_word, *rec_src, *rec_wasdone, *done;
@@ -40,15 +45,31 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   const size_t L = d.T;  // max_len travels in d.T for sizing
   Carver c(base);
   DecodeWs w{};
-  w.Wcat = c.take<float>((size_t)5 * H * K);
+  w.split = d.precision == AA_PREC_TF32X3;
+  w.bm = bm ? 1 : 0;
+  w.K = (int)K;
+  w.Kp = (int)((K + 31) / 32 * 32);
+  w.Hp = (int)((H + 31) / 32 * 32);
+  w.K2p = (int)((2 * H + 31) / 32 * 32);
+  w.lo = (int)((E + 2 * H + 31) / 32 * 32);
+  w.ldA = w.split ? 2 * w.lo : (int)K;
+  w.ldU = w.split ? 2 * w.Hp : (int)H;
+  w.tiles_n = ceil_div(d.Vc, gemm_tc_argmax_tile_n(d.Vc));
+  w.Wcat = c.take<float>((size_t)5 * H * (w.split ? 2 * w.Kp : (int)K));
+  w.W2 = c.take<float>(w.split ? (size_t)2 * d.a * 2 * w.K2p : 0);
+  w.hs = c.take<float>(w.split ? R * 2 * H : 0);
+  w.qr = c.take<float>(w.split ? R * 2 * d.a : 0);
   w.P = c.take<float>(B * d.k * d.a);
   w.stat = c.take<float>(R * 5 * H);
-  w.Acat = c.take<float>(R * K);
+  w.Acat = c.take<float>(R * w.ldA);
   w.gates = c.take<float>(R * 5 * H);
   w.c = c.take<float>(R * H);
-  w.u = c.take<float>(R * H);
-  w.logits = c.take<float>(R * d.Vc);
-  w.Acat2 = c.take<float>(bm ? R * K : 0);
+  w.u = c.take<float>(R * w.ldU);
+  w.logits = c.take<float>((w.split && !bm) ? 0 : R * d.Vc);     // split greedy never materialises the logits
+  w.Wp_s = c.take<float>(w.split ? (size_t)d.Vc * 2 * w.Hp : 0);
+  w.pmax = c.take<float>((w.split && !bm) ? R * w.tiles_n : 0);
+  w.pidx = c.take<int>((w.split && !bm) ? R * w.tiles_n : 0);
+  w.Acat2 = c.take<float>(bm ? R * w.ldA : 0);
   w.c2 = c.take<float>(bm ? R * H : 0);
   w.cum = c.take<float>(bm ? R : 0);
   w.row_max = c.take<float>(bm ? R : 0);
@@ -65,30 +86,64 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
 
 // Wcat [5H, E+H]: rows 0..4H = [W_ih[:, :E] | W_hh], rows 4H..5H = [W_x[:, :E] | 0]
 // (decode-mode sentinel gate has no recurrent term: h~ = 0)
+// split != 0: row = [tf32 hi (Kp, zero padded) | lo (Kp)], row stride ld = 2*Kp; else plain fp32, ld = K
 __global__ void pack_wcat_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ sen_wx,
-                                 float* __restrict__ Wcat, int H, int E) {
+                                 float* __restrict__ Wcat, int H, int E, int split, int Kp, int ld) {
   const int n = blockIdx.x;  // output row
   const int K = E + H;
-  float* dst = Wcat + (long long)n * K;
-  for (int c = threadIdx.x; c < K; c += blockDim.x) {
-    float v;
-    if (n < 4 * H) v = c < E ? w_ih[(long long)n * 2 * E + c] : w_hh[(long long)n * H + (c - E)];
-    else v = c < E ? sen_wx[(long long)(n - 4 * H) * 2 * E + c] : 0.f;
-    dst[c] = v;
+  float* dst = Wcat + (long long)n * ld;
+  for (int c = threadIdx.x; c < (split ? Kp : K); c += blockDim.x) {
+    float v = 0.f;
+    if (c < K) {
+      if (n < 4 * H) v = c < E ? w_ih[(long long)n * 2 * E + c] : w_hh[(long long)n * H + (c - E)];
+      else v = c < E ? sen_wx[(long long)(n - 4 * H) * 2 * E + c] : 0.f;
+    }
+    if (split) {
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      dst[c] = hi;
+      dst[Kp + c] = lo;
+    } else {
+      dst[c] = v;
+    }
   }
 }
 
 // Acat[r, :E] = embed[<start>], Acat[r, E:] = h0[r / beam], c[r] = c0[r / beam]
+// W2 [2a, 2*K2p] (tf32 hi | lo): row j < a = [W_g[j] | 0], row a + j = [W_g[j] | W_s[j]]  ->  [h | s] W2^T = [q | s W_s^T + q]
+__global__ void pack_wqr_kernel(const float* __restrict__ Wg, const float* __restrict__ Ws, float* __restrict__ W2, int a, int H, int K2p) {
+  const int n = blockIdx.x;
+  const int j = n < a ? n : n - a;
+  float* dst = W2 + (long long)n * 2 * K2p;
+  for (int c = threadIdx.x; c < K2p; c += blockDim.x) {
+    float v = 0.f;
+    if (c < H) v = Wg[(long long)j * H + c];
+    else if (c < 2 * H && n >= a) v = Ws[(long long)j * H + (c - H)];
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    dst[c] = hi;
+    dst[K2p + c] = lo;
+  }
+}
+
+// (split layout: hi at column j, lo at column Kp + j of the row -- Kp here is the row's lo offset; pads are pre-zeroed)
 __global__ void init_state_kernel(const float* __restrict__ embed, const float* __restrict__ h0, const float* __restrict__ c0,
-                                  float* __restrict__ Acat, float* __restrict__ c, int H, int E, int beam) {
+                                  float* __restrict__ Acat, float* __restrict__ c, int H, int E, int beam, int split, int Kp, int ld) {
   const int r = blockIdx.x;
   const int b = r / beam;
-  const int K = E + H;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) Acat[(long long)r * K + i] = embed[(long long)START_ID * E + i];
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    Acat[(long long)r * K + E + i] = h0 ? h0[(long long)b * H + i] : 0.f;
-    c[(long long)r * H + i] = c0 ? c0[(long long)b * H + i] : 0.f;
+  float* row = Acat + (long long)r * ld;
+  for (int i = threadIdx.x; i < E + H; i += blockDim.x) {
+    const float v = i < E ? embed[(long long)START_ID * E + i] : (h0 ? h0[(long long)b * H + (i - E)] : 0.f);
+    if (split) {
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      row[i] = hi;
+      row[Kp + i] = lo;
+    } else {
+      row[i] = v;
+    }
   }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) c[(long long)r * H + i] = c0 ? c0[(long long)b * H + i] : 0.f;
 }
 
 __global__ void expand_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int cols, int beam) {
@@ -146,7 +201,8 @@ __global__ void __launch_bounds__(256) beam_select_kernel(const float* __restric
                                                           const float* __restrict__ embed, const float* __restrict__ Acat,
                                                           const float* __restrict__ c, float* __restrict__ Acat_next,
                                                           float* __restrict__ c_next, int* __restrict__ rec_word,
-                                                          int* __restrict__ rec_src, int* __restrict__ rec_wasdone) {
+                                                          int* __restrict__ rec_src, int* __restrict__ rec_wasdone, int split,
+                                                          int Kp, int ldA) {
   __shared__ float s_cum[MAX_BEAM], s_max[MAX_BEAM], s_lsum[MAX_BEAM];
   __shared__ int s_done[MAX_BEAM];
   __shared__ float red_v[8];
@@ -218,15 +274,25 @@ __global__ void __launch_bounds__(256) beam_select_kernel(const float* __restric
     rec_wasdone[r0 + tid] = t_was;
   }
   // move state: Acat_next[slot] = [embed[word] | h[src]], c_next[slot] = c[src]
-  const int K = E + H;
   for (int slot = 0; slot < beam; ++slot) {
     const int f = sel_idx[slot];
     const int src = f / Vc, word = f - src * Vc;
-    const float* a_src = Acat + (long long)(r0 + src) * K;
-    float* a_dst = Acat_next + (long long)(r0 + slot) * K;
-    for (int i = tid; i < E; i += 256) a_dst[i] = embed[(long long)word * E + i];
+    const float* a_src = Acat + (long long)(r0 + src) * ldA;
+    float* a_dst = Acat_next + (long long)(r0 + slot) * ldA;
+    for (int i = tid; i < E; i += 256) {
+      const float x = embed[(long long)word * E + i];
+      if (split) {
+        float hi, lo;
+        split_tf32(x, hi, lo);
+        a_dst[i] = hi;
+        a_dst[Kp + i] = lo;
+      } else {
+        a_dst[i] = x;
+      }
+    }
     for (int i = tid; i < H; i += 256) {
       a_dst[E + i] = a_src[E + i];
+      if (split) a_dst[Kp + E + i] = a_src[Kp + E + i];
       c_next[(long long)(r0 + slot) * H + i] = c[(long long)(r0 + src) * H + i];
     }
   }
@@ -262,15 +328,43 @@ int check_decode(const aa_dims* d, const aa_weights* w, int max_len, int beam) {
   AA_REQUIRE(max_len >= 1, "decode: max_len must be >= 1");
   AA_REQUIRE(beam >= 1 && beam <= MAX_BEAM, "decode: beam must be in [1,%d]", MAX_BEAM);
   AA_REQUIRE(beam <= d->Vc, "decode: beam larger than the vocabulary");
+  AA_REQUIRE(d->precision == AA_PREC_FP32 || d->precision == AA_PREC_TF32X3,
+             "decode: precision must be AA_PREC_FP32 (SIMT) or AA_PREC_TF32X3 (tensor cores), got %d", d->precision);
   return AA_OK;
+}
+
+// One per-step contraction D[M,N] = A W^T (+Cin) (+bias): exact-fp32 SIMT, or 3xTF32 on tcgen05 over pre-split operands
+// (then optionally with the fused arg-max partials instead of / next to D).
+// (split: A is a column window starting at A of rows of lda floats whose lo half sits lo_a columns further; W rows are
+// [hi (Kp) | lo (Kp)])
+int dec_gemm(const DecodeWs& ws, int M, int N, int K, int Kp, const float* A, long long lda, int lo_a, long long a_cols, const float* W,
+             long long ldw, float* D, long long ldd, const float* Cin, long long ldcin, const float* bias, float* pmax, int* pidx,
+             cudaStream_t st) {
+  if (!ws.split) return gemm_nt(M, N, K, A, lda, W, ldw, D, ldd, Cin, ldcin, bias, nullptr, st);
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = Kp; g.elem_size = 4; g.split3 = 1;
+  g.A = A; g.lda = lda; g.lo_a = lo_a; g.a_cols = a_cols; g.B = W; g.ldb = ldw;
+  g.D32 = D; g.ldd32 = ldd; g.Cin = Cin; g.ldcin = ldcin; g.beta = 1.f; g.bias1 = bias;
+  g.pmax = pmax; g.pidx = pidx;
+  return launch_gemm_tc(g, st);
 }
 
 // shared prologue: weight packing, P, static gate terms, initial state
 int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const float* v_g, const float* h0, const float* c0,
                     int beam, DecodeWs& ws, cudaStream_t st) {
   const int B = d.B, H = d.H, E = d.E, R = B * beam, K = E + H;
-  pack_wcat_kernel<<<5 * H, 256, 0, st>>>(w.w_ih, w.w_hh, w.sen_wx, ws.Wcat, H, E);
+  pack_wcat_kernel<<<5 * H, 256, 0, st>>>(w.w_ih, w.w_hh, w.sen_wx, ws.Wcat, H, E, ws.split, ws.Kp, ws.split ? 2 * ws.Kp : K);
   AA_CHECK_LAUNCH("pack_wcat");
+  if (ws.split) {
+    AA_TRY(launch_split_tf32(w.mlp_w, H, d.Vc, H, ws.Wp_s, ws.Hp, st));
+    pack_wqr_kernel<<<2 * d.a, 256, 0, st>>>(w.att_wg, w.att_ws, ws.W2, d.a, H, ws.K2p);
+    AA_CHECK_LAUNCH("pack_wqr");
+    // the operand windows read past the columns they need (up to a multiple of 32, against zero weight columns):
+    // everything they can touch must be finite from the start, and the pad columns stay zero for the whole decode
+    AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat, 0, sizeof(float) * (size_t)R * ws.ldA, st));
+    if (ws.bm) AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat2, 0, sizeof(float) * (size_t)R * ws.ldA, st));
+    if (ws.Hp != H) AA_CHECK_CUDA(cudaMemsetAsync(ws.u, 0, sizeof(float) * (size_t)R * ws.ldU, st));
+  }
   AA_TRY(gemm_nt(B * d.k, d.a, H, V, H, w.att_wv, H, ws.P, d.a, nullptr, 0, nullptr, nullptr, st));
   // static (per image) gate terms: v_g half of x and the biases
   float* stat_img = beam > 1 ? ws.gates : ws.stat;   // [B,5H]; `gates` is free before the first step
@@ -280,9 +374,41 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
     expand_rows_kernel<<<R, 256, 0, st>>>(stat_img, ws.stat, 5 * H, beam);
     AA_CHECK_LAUNCH("expand_rows");
   }
-  init_state_kernel<<<R, 256, 0, st>>>(w.embed, h0, c0, ws.Acat, ws.c, H, E, beam);
+  init_state_kernel<<<R, 256, 0, st>>>(w.embed, h0, c0, ws.Acat, ws.c, H, E, beam, ws.split, ws.lo, ws.ldA);
   AA_CHECK_LAUNCH("init_state");
   (void)K;
+  return AA_OK;
+}
+
+// One decode step up to u = c_hat + h for R rows (R = B * beam) whose A operand is `Acur` and cell state `ccur`.
+int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, const float* V, float* Acur, float* ccur, int R, int beam,
+                     float* alpha, long long ld_alpha, float* beta, long long ld_beta, cudaStream_t st) {
+  const int H = d.H, E = d.E, K = E + H;
+  // gates = [emb(w_t) | h_{t-1}] Wcat^T + static              (LSTM + sentinel-x pre-activations)
+  AA_PROF("dec_gate_gemm", st, dec_gemm(ws, R, 5 * H, K, ws.Kp, Acur, ws.ldA, ws.lo, ws.ldA, ws.Wcat, ws.split ? 2 * ws.Kp : K, ws.gates,
+                                        5 * H, ws.stat, 5 * H, nullptr, nullptr, nullptr, st));
+  if (!ws.split) {   // exact-fp32 path: one fused kernel incl. the q/r mat-vecs
+    DecodeStepArgs p{};
+    p.B = R; p.k = d.k; p.a = d.a; p.H = H; p.beam = beam;
+    p.gates = ws.gates; p.c = ccur; p.h_out = Acur + E; p.ld_h = ws.ldA;
+    p.P = ws.P; p.V = V; p.Wg = w.att_wg; p.Ws = w.att_ws; p.wh = w.att_wh;
+    p.alpha = alpha; p.ld_alpha = ld_alpha; p.beta = beta; p.ld_beta = ld_beta;
+    p.u = ws.u; p.ld_u = ws.ldU;
+    AA_PROF("dec_step_fused", st, launch_decode_step(p, st));
+    return AA_OK;
+  }
+  DecodeCellArgs cp{};
+  cp.R = R; cp.H = H; cp.gates = ws.gates; cp.c = ccur; cp.hs = ws.hs; cp.A = Acur; cp.ldA = ws.ldA; cp.h_off = E; cp.lo_off = ws.lo;
+  AA_PROF("dec_cell", st, launch_decode_cell(cp, st));
+  // [q | r] = [h | s] W2^T                                                              adaptive_attention.py:35,45
+  AA_PROF("dec_qr_gemm", st, dec_gemm(ws, R, 2 * d.a, 2 * H, ws.K2p, Acur + E, ws.ldA, ws.lo, ws.ldA - E, ws.W2, 2 * ws.K2p, ws.qr,
+                                      2 * d.a, nullptr, 0, nullptr, nullptr, nullptr, st));
+  DecodeAttenArgs ap{};
+  ap.R = R; ap.k = d.k; ap.a = d.a; ap.H = H; ap.beam = beam;
+  ap.qr = ws.qr; ap.hs = ws.hs; ap.P = ws.P; ap.V = V; ap.wh = w.att_wh;
+  ap.alpha = alpha; ap.ld_alpha = ld_alpha; ap.beta = beta; ap.ld_beta = ld_beta;
+  ap.u = ws.u; ap.ld_u = ws.ldU; ap.u_lo_off = ws.Hp;
+  AA_PROF("dec_step_fused", st, launch_decode_atten(ap, st));
   return AA_OK;
 }
 
@@ -314,20 +440,23 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
   DecodeWs ws = carve_decode(dd, 0, workspace);
   const int B = d->B, H = d->H, E = d->E, K = E + H, Vc = d->Vc, k = d->k, L = max_len;
   AA_TRY(decode_prologue(dd, *w, V, v_g, h0, c0, 1, ws, st));
+  const float* Wp = ws.split ? ws.Wp_s : w->mlp_w;
   for (int t = 0; t < L; ++t) {
-    // gates = [emb(w_t) | h_{t-1}] Wcat^T + static              (LSTM + sentinel-x pre-activations)
-    AA_PROF("dec_gate_gemm", st, gemm_nt(B, 5 * H, K, ws.Acat, K, ws.Wcat, K, ws.gates, 5 * H, ws.stat, 5 * H, nullptr, nullptr, st));
-    DecodeStepArgs p{};
-    p.B = B; p.k = k; p.a = d->a; p.H = H; p.beam = 1;
-    p.gates = ws.gates; p.c = ws.c; p.h_out = ws.Acat + E; p.ld_h = K;
-    p.P = ws.P; p.V = V; p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh;
-    p.alpha = attention + (size_t)t * k; p.ld_alpha = (long long)L * k;
-    p.beta = Beta + t; p.ld_beta = L;
-    p.u = ws.u;
-    AA_PROF("dec_step_fused", st, launch_decode_step(p, st));
-    float* lg = logits_out ? logits_out + (size_t)t * B * Vc : ws.logits;
-    AA_PROF("dec_vocab_gemm", st, gemm_nt(B, Vc, H, ws.u, H, w->mlp_w, H, lg, Vc, nullptr, 0, w->mlp_b, nullptr, st));   // :132
-    AA_PROF("dec_argmax", st, launch_argmax_gather(lg, Vc, B, Vc, reinterpret_cast<long long*>(ids) + t, L, w->embed, E, ws.Acat, K, st));   // :201
+    AA_TRY(decode_step_body(dd, *w, ws, V, ws.Acat, ws.c, B, 1, attention + (size_t)t * k, (long long)L * k, Beta + t, L, st));
+    long long* ids_t = reinterpret_cast<long long*>(ids) + t;
+    if (ws.split) {
+      // logits = u W_p^T + b_p on tensor cores; the epilogue keeps a per-(row, column tile) arg-max, so the [B,Vc]
+      // logits never touch HBM unless the caller asked for them                                          :132, :201
+      float* lg = logits_out ? logits_out + (size_t)t * B * Vc : nullptr;
+      AA_PROF("dec_vocab_gemm", st, dec_gemm(ws, B, Vc, H, ws.Hp, ws.u, ws.ldU, ws.Hp, ws.ldU, Wp, 2 * ws.Hp, lg, Vc, nullptr, 0, w->mlp_b,
+                                             ws.pmax, ws.pidx, st));
+      AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles_n, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,
+                                                       ws.lo, st));
+    } else {
+      float* lg = logits_out ? logits_out + (size_t)t * B * Vc : ws.logits;
+      AA_PROF("dec_vocab_gemm", st, gemm_nt(B, Vc, H, ws.u, H, w->mlp_w, H, lg, Vc, nullptr, 0, w->mlp_b, nullptr, st));   // :132
+      AA_PROF("dec_argmax", st, launch_argmax_gather(lg, Vc, B, Vc, ids_t, L, w->embed, E, ws.Acat, K, st));                // :201
+    }
   }
   return AA_OK;
 }
@@ -346,28 +475,21 @@ int aa_beam_decode(const aa_dims* d, const aa_weights* w, const float* V, const 
   }
   cudaStream_t st = (cudaStream_t)stream;
   DecodeWs ws = carve_decode(dd, beam, workspace);
-  const int B = d->B, H = d->H, E = d->E, K = E + H, Vc = d->Vc, k = d->k, L = max_len, R = B * beam;
+  const int B = d->B, H = d->H, E = d->E, Vc = d->Vc, k = d->k, L = max_len, R = B * beam;
   AA_TRY(decode_prologue(dd, *w, V, v_g, h0, c0, beam, ws, st));
   beam_init_kernel<<<ceil_div(R, 256), 256, 0, st>>>(ws.cum, ws.done, R, beam);
   AA_CHECK_LAUNCH("beam_init");
   float* Acur = ws.Acat;  float* Anext = ws.Acat2;
   float* ccur = ws.c;     float* cnext = ws.c2;
   for (int t = 0; t < L; ++t) {
-    AA_PROF("dec_gate_gemm", st, gemm_nt(R, 5 * H, K, Acur, K, ws.Wcat, K, ws.gates, 5 * H, ws.stat, 5 * H, nullptr, nullptr, st));
-    DecodeStepArgs p{};
-    p.B = R; p.k = k; p.a = d->a; p.H = H; p.beam = beam;
-    p.gates = ws.gates; p.c = ccur; p.h_out = Acur + E; p.ld_h = K;
-    p.P = ws.P; p.V = V; p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh;
-    p.alpha = ws.rec_alpha + (size_t)t * R * k; p.ld_alpha = k;
-    p.beta = ws.rec_beta + (size_t)t * R; p.ld_beta = 1;
-    p.u = ws.u;
-    AA_PROF("dec_step_fused", st, launch_decode_step(p, st));
-    AA_PROF("dec_vocab_gemm", st, gemm_nt(R, Vc, H, ws.u, H, w->mlp_w, H, ws.logits, Vc, nullptr, 0, w->mlp_b, nullptr, st));
+    AA_TRY(decode_step_body(dd, *w, ws, V, Acur, ccur, R, beam, ws.rec_alpha + (size_t)t * R * k, k, ws.rec_beta + (size_t)t * R, 1, st));
+    AA_PROF("dec_vocab_gemm", st, dec_gemm(ws, R, Vc, H, ws.Hp, ws.u, ws.ldU, ws.Hp, ws.ldU, ws.split ? ws.Wp_s : w->mlp_w,
+                                           ws.split ? 2 * ws.Hp : H, ws.logits, Vc, nullptr, 0, w->mlp_b, nullptr, nullptr, st));
     row_lse_kernel<<<R, 256, 0, st>>>(ws.logits, Vc, ws.row_max, ws.row_lsum);
     AA_CHECK_LAUNCH("row_lse");
     beam_select_kernel<<<B, 256, 0, st>>>(ws.logits, ws.row_max, ws.row_lsum, ws.cum, ws.done, Vc, beam, H, E, w->embed, Acur,
                                           ccur, Anext, cnext, ws.rec_word + (size_t)t * R, ws.rec_src + (size_t)t * R,
-                                          ws.rec_wasdone + (size_t)t * R);
+                                          ws.rec_wasdone + (size_t)t * R, ws.split, ws.lo, ws.ldA);
     AA_CHECK_LAUNCH("beam_select");
     float* tmp = Acur; Acur = Anext; Anext = tmp;
     tmp = ccur; ccur = cnext; cnext = tmp;

@@ -69,12 +69,20 @@ struct TcEpilogue {
   __nv_bfloat16* D16; long long ldd16;
   const float* Cin; long long ldcin; float beta;
   const float* bias1; const float* bias2;
+  float* pmax; int* pidx; int tiles_n;      // optional per-(row, n-tile) arg-max partials of D (bias included)
+  int lo_a, lo_b;                           // split mode: column offset of the lo half inside a row of A / B
 };
 
 // Tile geometry (bytes): every smem row is 128 B (the swizzle span).
 //   K-major operand, R rows (M or N): one TMA box {128B/ES elements of K, R rows}      -> R*128 B
 //   MN-major operand, R columns     : R*ES/128 TMA boxes {128B/ES elements of MN, BK rows of K} -> BK*128 B each
-template <int BN, int ES, int STAGES, bool A_MN, bool B_MN>
+//
+// SPLIT (fp32-accurate "3xTF32"): the operands arrive pre-split as [rows, 2*K] = [hi | lo] with hi = tf32(x),
+// lo = tf32(x - hi); a stage holds the four sub-tiles A_hi, A_lo, B_hi, B_lo and every k-step issues
+// lo*hi + hi*lo + hi*hi into the same fp32 accumulator (the lo*lo term, ~2^-22 relative, is dropped).  Loading
+// each sub-tile once and using it in two products gives 1.5x the arithmetic intensity against L2 of a plain
+// 3K-long tf32 contraction.
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m,
                int num_tiles) {
@@ -85,6 +93,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int BK = EPR;                  // reduction elements per stage (64 bf16 / 32 tf32)
   constexpr int UMMA_K = 32 / ES;          // 16 bf16 / 8 tf32
   constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;   // BM*BK*ES, BN*BK*ES
+  constexpr uint32_t A_STAGE = SPLIT ? 2 * A_BYTES : A_BYTES, B_STAGE = SPLIT ? 2 * B_BYTES : B_BYTES;
+  static_assert(!SPLIT || (ES == 4 && !A_MN && !B_MN), "split mode: K-major fp32 operands only");
   constexpr uint32_t A_BOX = A_MN ? BK * 128 : A_BYTES;        // bytes per TMA box
   constexpr uint32_t B_BOX = B_MN ? BK * 128 : B_BYTES;
   constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -92,8 +102,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
@@ -136,9 +146,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-          uint8_t* a_dst = sA + s * A_BYTES;
-          uint8_t* b_dst = sB + s * B_BYTES;
+          mbar_expect_tx(&full_bar[s], A_STAGE + B_STAGE);
+          uint8_t* a_dst = sA + s * A_STAGE;
+          uint8_t* b_dst = sB + s * B_STAGE;
+          if constexpr (SPLIT) {      // hi halves at column kb*BK, lo halves at column K + kb*BK of the same arrays
+            tma_load_2d(a_dst, &tmA, kb * BK, m0, &full_bar[s]);
+            tma_load_2d(a_dst + A_BYTES, &tmA, e.lo_a + kb * BK, m0, &full_bar[s]);
+            tma_load_2d(b_dst, &tmB, kb * BK, n0, &full_bar[s]);
+            tma_load_2d(b_dst + B_BYTES, &tmB, e.lo_b + kb * BK, n0, &full_bar[s]);
+            continue;
+          }
           if constexpr (A_MN) {
 #pragma unroll
             for (int j = 0; j < (int)(A_BYTES / A_BOX); ++j) tma_load_2d(a_dst + j * A_BOX, &tmA, m0 + j * EPR, kb * BK, &full_bar[s]);
@@ -173,10 +190,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
+            if constexpr (SPLIT) {
+              const uint64_t ah = make_smem_desc(a_addr + k * 32, 16, 1024), al = make_smem_desc(a_addr + A_BYTES + k * 32, 16, 1024);
+              const uint64_t bh = make_smem_desc(b_addr + k * 32, 16, 1024), bl = make_smem_desc(b_addr + B_BYTES + k * 32, 16, 1024);
+              tc_mma<true>(tmem_d, al, bh, idesc, (kb | k) != 0 ? 1u : 0u);
+              tc_mma<true>(tmem_d, ah, bl, idesc, 1u);
+              tc_mma<true>(tmem_d, ah, bh, idesc, 1u);
+              continue;
+            }
             // K-major : LBO unused (1), SBO = 8 rows * 128 B; advance 32 B per UMMA_K inside the swizzle atom
             // MN-major: LBO = bytes between 128B-wide MN chunks (one TMA box), SBO = 8 k-rows * 128 B;
             //           advance UMMA_K k-rows * 128 B
@@ -206,6 +231,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
       const int row0 = m0 + q * 32;
+      float best = -INFINITY;     // this thread's row (row0 + lane): running arg-max over the tile's columns
+      int best_i = 0x7fffffff;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -217,6 +244,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int nb = n0 + c * 32;
         if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
+        if (e.pmax) {               // ascending column scan with a strict compare: the lowest index wins ties
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j < e.N) {
+              const float v = __uint_as_float(r[j]) + (e.bias1 ? __ldg(e.bias1 + nb + j) : 0.f) + (e.bias2 ? __ldg(e.bias2 + nb + j) : 0.f);
+              if (v > best) { best = v; best_i = nb + j; }
+            }
+          }
+          if (!e.D32 && !e.D16) continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(&tbuf[lane * TS + j]) =
@@ -288,6 +325,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
+      if (e.pmax && row0 + lane < e.M) {
+        const long long o = (long long)(row0 + lane) * e.tiles_n + tile / tiles_m;
+        e.pmax[o] = best;
+        e.pidx[o] = best_i;
+      }
     }
   }
   tc_fence_before();
@@ -298,27 +340,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, int ES, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT = false>
 int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int BK = 128 / ES;
   CUtensorMap tmA, tmB;
   // K-major operand: array [R, K] (K contiguous), box {BK, tile rows}; MN-major: array [K, R] (R contiguous), box {128B of R, BK rows}
+  // split operands: a row holds [hi (>= K columns) ... lo (>= K columns) ...]; the map spans what the row has left
+  // from the operand's base column on (columns past it are zero-filled by TMA, never wrapped into the next row)
+  const int lo_a = g.lo_a ? g.lo_a : g.K, lo_b = g.lo_b ? g.lo_b : g.K;
+  const long long acols = SPLIT ? (g.a_cols ? g.a_cols : (long long)lo_a + g.K) : g.K;
+  const long long bcols = SPLIT ? (g.b_cols ? g.b_cols : (long long)lo_b + g.K) : g.K;
   if (A_MN) AA_TRY(make_map(&tmA, g.A, ES, g.K, g.M, g.lda, BK));
-  else      AA_TRY(make_map(&tmA, g.A, ES, g.M, g.K, g.lda, BM));
+  else      AA_TRY(make_map(&tmA, g.A, ES, g.M, acols, g.lda, BM));
   if (B_MN) AA_TRY(make_map(&tmB, g.B, ES, g.K, g.N, g.ldb, BK));
-  else      AA_TRY(make_map(&tmB, g.B, ES, g.N, g.K, g.ldb, BN));
+  else      AA_TRY(make_map(&tmB, g.B, ES, g.N, bcols, g.ldb, BN));
+  const int tiles_m = ceil_div(g.M, BM), tiles_n = ceil_div(g.N, BN);
   TcEpilogue e{};
   e.M = g.M; e.N = g.N; e.K = g.K;
   e.D32 = g.D32; e.ldd32 = g.ldd32; e.D16 = g.D16; e.ldd16 = g.ldd16;
   e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
-  constexpr size_t smem = (size_t)STAGES * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + 4 * 32 * 36 * 4 + 1024;
-  auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN>;
+  e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = tiles_n; e.lo_a = lo_a; e.lo_b = lo_b;
+  constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + 4 * 32 * 36 * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "tile configuration exceeds shared memory");
+  auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN, SPLIT>;
   static bool attr_done = false;
   if (!attr_done) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int tiles_m = ceil_div(g.M, BM), tiles_n = ceil_div(g.N, BN);
   const int num_tiles = tiles_m * tiles_n;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();     // persistent: one CTA per SM
   kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e, tiles_m, num_tiles);
@@ -346,10 +395,20 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
+int gemm_tc_argmax_tile_n(int N) { return N > 64 ? 128 : 64; }
+
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AA_OK;
-  AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16), "tcgen05 GEMM: bad arguments");
+  AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16 || g.pmax), "tcgen05 GEMM: bad arguments");
   AA_REQUIRE(g.elem_size == 2 || g.elem_size == 4, "tcgen05 GEMM: element size must be 2 (bf16) or 4 (tf32)");
+  AA_REQUIRE(!g.pmax || (g.pidx && g.split3 && !g.Cin), "tcgen05 GEMM: arg-max partials need pidx, split mode and no C input");
+  if (g.split3) {
+    AA_REQUIRE(g.elem_size == 4 && !g.a_mn && !g.b_mn, "tcgen05 GEMM: split (3xTF32) mode needs K-major fp32 operands");
+    AA_REQUIRE(g.K % 32 == 0, "tcgen05 GEMM: split mode needs K (per half) padded to a multiple of 32 (got %d)", g.K);
+    // the arg-max partial layout [M, ceil(N / tile_n)] is part of the contract: tile_n = gemm_tc_argmax_tile_n(N)
+    if (g.N > 64) return launch_cfg<128, 4, 3, false, false, true>(g, st);
+    return launch_cfg<64, 4, 4, false, false, true>(g, st);
+  }
   if (g.elem_size == 4 && (g.a_mn || g.b_mn)) {
     // 32-bit MN-major operands need the SWIZZLE_128B_BASE32B layout; only the forward (K-major) form is built
     set_error("tcgen05 GEMM: tf32 operands must be K-major");

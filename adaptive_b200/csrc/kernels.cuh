@@ -41,6 +41,12 @@ int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t s);
 // emb_dst != null, gathers embed[id] into emb_dst[b*ld_emb + 0:E] for the next decode step
 int launch_argmax_gather(const float* logits, long long ld_logits, int B, int Vc, long long* ids_out, long long ld_ids,
                          const float* embed, int E, float* emb_dst, long long ld_emb, cudaStream_t s);
+// reduce the vocabulary GEMM's arg-max partials [B, tiles_n] to ids and gather embed[id] into the next A operand
+// (split != 0: as tf32 hi at [0,E) and lo at [lo_off, lo_off+E) of the destination row)
+int launch_argmax_finalize(const float* pmax, const int* pidx, int tiles_n, int B, long long* ids_out, long long ld_ids,
+                           const float* embed, int E, float* emb_dst, long long ld_emb, int split, long long lo_off, cudaStream_t s);
+// dst [rows, 2*Kp] = [tf32 hi | lo] of src [rows, cols] (zero padded to Kp, a multiple of 32)
+int launch_split_tf32(const float* src, long long ld_src, long long rows, int cols, float* dst, int Kp, cudaStream_t s);
 int launch_gather_rows(const long long* ids, long long ld_ids, const float* table, int E, int Vc, float* dst, long long ld_dst,
                        int B, cudaStream_t s);
 int launch_copy2d(float* dst, long long ld_dst, const float* src, long long ld_src, int rows, int cols, cudaStream_t s);
@@ -71,8 +77,19 @@ struct TcGemmArgs {
   __nv_bfloat16* D16; long long ldd16;
   const float* Cin; long long ldcin; float beta;
   const float* bias1; const float* bias2;
+  // split3 != 0: fp32-accurate "3xTF32" mode.  A is [M, 2K], B is [N, 2K], each row = [hi | lo] with
+  // hi = tf32(x), lo = tf32(x - hi) (see launch_split_tf32), K = padded length of one half (multiple of 32).
+  int split3;
+  // split3 only, all optional (0 = default): column offset of the lo half inside a row (default K) and number of
+  // valid columns of a row counted from the operand's base pointer (default lo + K) -- lets an operand be a column
+  // window of a wider split row, e.g. [emb | h | s] rows serving both the gate and the q/r contraction
+  int lo_a, lo_b; long long a_cols, b_cols;
+  // optional (split3 only): per-(row, n-tile) arg-max partials of D incl. bias, layout [M, ceil(N / tile_n)] with
+  // tile_n = gemm_tc_argmax_tile_n(N); D32/D16 may then both be null (the logits are never written).
+  float* pmax; int* pidx;
 };
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
+int gemm_tc_argmax_tile_n(int N);
 
 // ---- lstm_seq.cu (persistent recurrence, bf16 tensor-core mode) -----------------------------
 // true when the one-launch recurrence kernels can run this shape (H % 64 == 0 and the CTAs fit the chip)
@@ -138,8 +155,33 @@ struct DecodeStepArgs {
   const float *Wg, *Ws, *wh;  // [a,H],[a,H],[a]
   float* alpha; long long ld_alpha;   // alpha[b*ld_alpha + i]
   float* beta; long long ld_beta;
-  float* u;                   // [B,H]
+  float* u; long long ld_u;   // u = c_hat + h, row stride ld_u (0 = H)
+  // split != 0: h and u are written as tf32 (hi, lo) pairs for the 3xTF32 tensor-core contractions: hi at the
+  // plain position, lo at +h_lo_off / +u_lo_off in the same row
+  int split; long long h_lo_off, u_lo_off;
 };
 int launch_decode_step(const DecodeStepArgs& p, cudaStream_t s);
+
+// tensor-core decode pipeline (AA_PREC_TF32X3): LSTM pointwise + sentinel gate ...
+struct DecodeCellArgs {
+  int R, H;
+  const float* gates;         // [R,5H] pre-activations: i,f,g,o,sentinel
+  float* c;                   // [R,H] in/out
+  float* hs;                  // [R,2H] fp32 [h_t | s_t]
+  float* A; long long ldA;    // A-operand rows: h (hi) at [h_off, h_off+H), s (hi) at [h_off+H, h_off+2H), lo halves at +lo_off
+  long long h_off, lo_off;
+};
+int launch_decode_cell(const DecodeCellArgs& p, cudaStream_t s);
+// ... and the attention stream: scores + both softmaxes + beta-gated context + (c_hat + h), one warp per row
+struct DecodeAttenArgs {
+  int R, k, a, H, beam;       // R rows; V/P row = r / beam
+  const float* qr;            // [R,2a] = [q | r]   (q = h W_g^T, r = s W_s^T + q)
+  const float* hs;            // [R,2H] = [h | s]
+  const float *P, *V, *wh;    // [R/beam,k,a], [R/beam,k,H], [a]
+  float* alpha; long long ld_alpha;
+  float* beta; long long ld_beta;
+  float* u; long long ld_u, u_lo_off;    // u = c_hat + h as tf32 (hi, lo): hi at [0,H), lo at [u_lo_off, u_lo_off+H)
+};
+int launch_decode_atten(const DecodeAttenArgs& p, cudaStream_t s);
 
 }  // namespace aa

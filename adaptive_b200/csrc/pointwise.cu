@@ -186,6 +186,63 @@ __global__ void __launch_bounds__(PW_THREADS) argmax_gather_kernel(const float* 
   }
 }
 
+// Final reduction of the vocabulary GEMM's per-(row, n-tile) arg-max partials (gemm_tc.cu epilogue) + gather of the
+// winner's embedding into the next step's A operand.  One warp per row; partial j covers columns [j*tile_n, ...), so
+// comparing (value, index) with "greater, or equal and lower index" keeps torch.max's lowest-index tie-break (Q12).
+// emb_dst row layout: split != 0 -> hi at [0,E), lo at [lo_off, lo_off+E); else plain fp32 at [0,E).
+__global__ void __launch_bounds__(PW_THREADS) argmax_finalize_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx,
+                                                                     int tiles_n, int B, long long* __restrict__ ids_out,
+                                                                     long long ld_ids, const float* __restrict__ embed, int E,
+                                                                     float* __restrict__ emb_dst, long long ld_emb, int split,
+                                                                     long long lo_off) {
+  const int b = blockIdx.x * (PW_THREADS / 32) + (threadIdx.x >> 5);
+  const int l = threadIdx.x & 31;
+  if (b >= B) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = l; j < tiles_n; j += 32) {
+    const float v = pmax[(long long)b * tiles_n + j];
+    const int i = pidx[(long long)b * tiles_n + j];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (bi == 0x7fffffff) bi = 0;  // all-NaN row
+  if (l == 0) ids_out[b * ld_ids] = bi;
+  if (emb_dst) {
+    const float* src = embed + (long long)bi * E;
+    float* dst = emb_dst + b * ld_emb;
+    for (int e = l; e < E; e += 32) {
+      const float x = __ldg(src + e);
+      if (split) {
+        float hi, lo;
+        split_tf32(x, hi, lo);
+        dst[e] = hi;
+        dst[lo_off + e] = lo;
+      } else {
+        dst[e] = x;
+      }
+    }
+  }
+}
+
+// dst[r, 0:Kp] = tf32 hi of src[r, 0:cols] (zero padded), dst[r, Kp:2Kp] = lo
+__global__ void __launch_bounds__(PW_THREADS) split_tf32_kernel(const float* __restrict__ src, long long ld_src, long long rows, int cols,
+                                                                float* __restrict__ dst, int Kp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Kp) return;
+  const long long r = idx / Kp;
+  const int c = (int)(idx % Kp);
+  float hi = 0.f, lo = 0.f;
+  if (c < cols) split_tf32(src[r * ld_src + c], hi, lo);
+  dst[r * 2 * Kp + c] = hi;
+  dst[r * 2 * Kp + Kp + c] = lo;
+}
+
 __global__ void __launch_bounds__(PW_THREADS) ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld,
                                                                 const long long* __restrict__ tgt, int n, int Vc,
                                                                 float* __restrict__ loss, float* __restrict__ dlogits,
@@ -397,6 +454,23 @@ int launch_argmax_gather(const float* logits, long long ld_logits, int B, int Vc
                          const float* embed, int E, float* emb_dst, long long ld_emb, cudaStream_t s) {
   argmax_gather_kernel<<<B, PW_THREADS, 0, s>>>(logits, ld_logits, Vc, ids_out, ld_ids, embed, E, emb_dst, ld_emb);
   AA_CHECK_LAUNCH("argmax_gather");
+  return AA_OK;
+}
+
+int launch_argmax_finalize(const float* pmax, const int* pidx, int tiles_n, int B, long long* ids_out, long long ld_ids,
+                           const float* embed, int E, float* emb_dst, long long ld_emb, int split, long long lo_off, cudaStream_t s) {
+  if (B == 0) return AA_OK;
+  argmax_finalize_kernel<<<ceil_div(B, PW_THREADS / 32), PW_THREADS, 0, s>>>(pmax, pidx, tiles_n, B, ids_out, ld_ids, embed, E, emb_dst,
+                                                                             ld_emb, split, lo_off);
+  AA_CHECK_LAUNCH("argmax_finalize");
+  return AA_OK;
+}
+
+int launch_split_tf32(const float* src, long long ld_src, long long rows, int cols, float* dst, int Kp, cudaStream_t s) {
+  if (rows == 0) return AA_OK;
+  AA_REQUIRE(Kp >= cols && Kp % 32 == 0, "split_tf32: Kp=%d must be a multiple of 32 and >= cols=%d", Kp, cols);
+  split_tf32_kernel<<<blocks_for(rows * Kp), PW_THREADS, 0, s>>>(src, ld_src, rows, cols, dst, Kp);
+  AA_CHECK_LAUNCH("split_tf32");
   return AA_OK;
 }
 

@@ -57,6 +57,8 @@ def _states2d(st: Optional[torch.Tensor], B: int, H: int) -> Optional[torch.Tens
 
 
 PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+# decoding: "fp32" = exact SIMT contractions; "tf32x3" = tcgen05 tensor cores over (hi, lo)-split fp32 operands
+DECODE_PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3}
 
 
 def make_dims(B, T, k, H, E, Vc, a=ATT_DIM, precision=_lib.PREC_FP32) -> AADims:
@@ -266,9 +268,11 @@ def cross_entropy(logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
-def greedy_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: int = 30, return_logits: bool = False):
+def greedy_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: int = 30, return_logits: bool = False,
+                  precision: str = "tf32x3"):
     """``Encoder2Decoder.sampler`` loop (adaptive_attention.py:186-216) on the device.
-    Returns ids [B,L] int64, attention [B,L,k], Beta [B,L,1] (+ logits [L,B,Vc])."""
+    Returns ids [B,L] int64, attention [B,L,k], Beta [B,L,1] (+ logits [L,B,Vc]).
+    ``precision``: "tf32x3" (per-step contractions on tensor cores, fp32-accurate) or "fp32" (exact SIMT)."""
     lib = _lib.load()
     _need_cuda(V, v_g, h0, c0)
     V, v_g = _f32c(V), _f32c(v_g)
@@ -278,7 +282,7 @@ def greedy_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: 
     _check_weights(w, H, E, Vc, a)
     h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
     dev = V.device
-    d = make_dims(B, max_len, k, H, E, Vc, a)
+    d = make_dims(B, max_len, k, H, E, Vc, a, DECODE_PRECISIONS[precision])
     ids = torch.empty(B, max_len, device=dev, dtype=torch.int64)
     att = torch.empty(B, max_len, k, device=dev, dtype=torch.float32)
     bet = torch.empty(B, max_len, 1, device=dev, dtype=torch.float32)
@@ -294,7 +298,8 @@ def greedy_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: 
 
 
 @torch.no_grad()
-def beam_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, beam: int = 3, max_len: int = 20):
+def beam_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, beam: int = 3, max_len: int = 20,
+                precision: str = "tf32x3"):
     """Beam search (not in the reference; definition in oracle.beam_decode / SURVEY §8c).
     Returns ids [B,L], attention [B,L,k], Beta [B,L,1], score [B] of the best hypothesis."""
     lib = _lib.load()
@@ -306,7 +311,7 @@ def beam_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, beam: int =
     _check_weights(w, H, E, Vc, a)
     h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
     dev = V.device
-    d = make_dims(B, max_len, k, H, E, Vc, a)
+    d = make_dims(B, max_len, k, H, E, Vc, a, DECODE_PRECISIONS[precision])
     ids = torch.empty(B, max_len, device=dev, dtype=torch.int64)
     att = torch.empty(B, max_len, k, device=dev, dtype=torch.float32)
     bet = torch.empty(B, max_len, 1, device=dev, dtype=torch.float32)

@@ -139,6 +139,8 @@ class Decoder(nn.Module):
         self.adaptive = AdaptiveBlock(embed_size, hidden_size, vocab_size, cf)
         # "fp32": exact path (parity with the reference); "bf16": tensor-core mixed precision for training
         self.precision = getattr(cf, "precision", "fp32") if cf is not None else "fp32"
+        # decoding: "tf32x3" = per-step contractions on tensor cores (fp32-accurate 3xTF32), "fp32" = exact SIMT
+        self.decode_precision = getattr(cf, "decode_precision", "tf32x3") if cf is not None else "tf32x3"
 
     def weights(self):
         return self.adaptive._weights13(self.embed, self.LSTM)
@@ -216,10 +218,10 @@ class Encoder2Decoder(nn.Module):
         """Greedy search -> sampled_ids [B,max_len], attention [B,max_len,k], Beta [B,max_len,1]."""
         V, v_g, states = self._encode(images)
         h0, c0 = states if states is not None else (None, None)
-        return F_aa.greedy_decode(self.decoder.weights(), V, v_g, h0, c0, max_len)
+        return F_aa.greedy_decode(self.decoder.weights(), V, v_g, h0, c0, max_len, precision=self.decoder.decode_precision)
 
     def beam_sampler(self, images, beam=3, max_len=20):
         """Beam search (extension; the reference only has a TODO for it, `for_wzn:3`)."""
         V, v_g, states = self._encode(images)
         h0, c0 = states if states is not None else (None, None)
-        return F_aa.beam_decode(self.decoder.weights(), V, v_g, h0, c0, beam, max_len)
+        return F_aa.beam_decode(self.decoder.weights(), V, v_g, h0, c0, beam, max_len, precision=self.decoder.decode_precision)

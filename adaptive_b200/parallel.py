@@ -320,3 +320,39 @@ class DataParallelTrainer:
         self.input_grads = {"V": b["dV"], "v_g": b["dvg"], "h0": b["dh0"] if h0 is not None else None,
                             "c0": b["dc0"] if c0 is not None else None}
         return loss
+
+
+class GraphedDPStep:
+    """``DataParallelTrainer.step`` captured once as a CUDA graph (forward, loss, hooked backward and the
+    bucketed NCCL all-reduces on their communication stream) and replayed per batch.  Shapes, caption lengths
+    and parameter tensors are frozen at capture; inputs are copied into static buffers before each replay.
+    Every rank must construct it at the same point (capture issues the same collectives on all ranks)."""
+
+    KEYS = ("V", "v_g", "h0", "c0", "captions", "tgt")
+
+    def __init__(self, trainer: DataParallelTrainer, example: Dict[str, torch.Tensor], lengths: Sequence[int], warmup: int = 3):
+        self.trainer = trainer
+        self.lengths = [int(x) for x in lengths]
+        self.static = {k: example[k].clone() for k in self.KEYS}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # one-time initialisation (attributes, side streams, NCCL) outside the capture
+                self._eager()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+
+    def _eager(self):
+        b = self.static
+        return self.trainer.step((b["V"], b["v_g"], (b["h0"], b["c0"])), b["captions"], self.lengths, b["tgt"])
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        for k in self.KEYS:
+            if batch[k] is not self.static[k]:
+                self.static[k].copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.loss

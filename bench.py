@@ -166,17 +166,33 @@ def kernel_models(dims, B, T, decode_B):
     H, E, k, a, Vc = dims.H, dims.E, dims.k, dims.a, dims.Vc
     N = B * T
     fl = lambda m, n, kk: 2.0 * m * n * kk
-    step_bytes = (5 * H + H) * 4 + k * H * 4 + k * a * 4 + (2 * H + H) * 4 + k * 4 + 4      # 128 588 B at cfgA
+    # attention stream kernel of the tensor-core decode pipeline, per (row, step): reads V, P, [h|s], [q|r]; writes u, alpha, beta
+    step_bytes = k * H * 4 + k * a * 4 + 2 * H * 4 + 2 * a * 4 + H * 4 + k * 4 + 4          # 116 692 B at cfgA
+    cell_bytes = (5 * H + H) * 4 + (H + 2 * H) * 4                                          # gates, c in; c, h, s out
     return {
+        "lstm_seq_fwd": ("tensor", fl(B, 4 * H, H) * T), "lstm_seq_bwd": ("tensor", fl(B, H, 4 * H) * T),
+        "dec_cell": ("hbm", float(cell_bytes) * decode_B), "dec_qr_gemm": ("tf32x3", fl(decode_B, 2 * a, 2 * H)),
         "gemm_vocab_fwd": ("tensor", fl(N, Vc, H)), "gemm_vocab_dx": ("tensor", fl(N, H, Vc)), "gemm_vocab_dw": ("tensor", fl(Vc, H, N)),
         "lstm_rec_gemm": ("tensor", fl(B, 4 * H, H)), "bptt_rec_gemm": ("tensor", fl(B, H, 4 * H)),
-        "dec_vocab_gemm": ("tensor", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tensor", fl(decode_B, 5 * H, E + H)),
+        "dec_vocab_gemm": ("tf32x3", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tf32x3", fl(decode_B, 5 * H, E + H)),
         "dec_step_fused": ("hbm", float(step_bytes) * decode_B),
-        "dec_argmax": ("hbm", float(decode_B) * Vc * 4),
+        "dec_argmax": ("hbm", float(decode_B) * ((Vc + 127) // 128) * 8),      # reduction of the GEMM epilogue's partials
         # training attention, per launch over the whole batch: V + P + per-step rows in, u/ctx/alpha/beta out
         "atten_fwd": ("hbm", float(B) * (k * H * 4 + k * a * 4 + T * (2 * a + 2 * H + 2 * H + k + 1) * 4)),
         "atten_bwd": ("hbm", float(B) * (2 * k * H * 4 + 2 * k * a * 4 + T * (2 * a + 3 * H + H + k + 1 + 2 * a) * 4)),
     }
+
+
+def load_traffic():
+    """dram bytes per launch of the profiled kernels, from the committed `ncu --set full` captures (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return {k: v["dram_bytes_per_launch"] for k, v in json.load(open(p)).items() if isinstance(v, dict)}
+    except (OSError, ValueError, KeyError):
+        return {}
+
+
+TRAFFIC = load_traffic()
 
 
 def rooflines(report, models, peaks):
@@ -187,12 +203,20 @@ def rooflines(report, models, peaks):
             continue
         bound, work = models[tag]
         per = ms / n * 1e-3
+        extra = {}
         if bound == "hbm":
             ach, peak, unit = work / per / 1e9, peaks["hbm_gbs"], "GB/s"
+        elif bound == "tf32x3":
+            # fp32-accurate contraction executed as three tf32 tensor-core products: the tensor pipe does 3x the
+            # algorithmic flops; there is no measured tf32 peak, so half of the measured bf16 peak (the nominal ratio) is used
+            bound = "tensor"
+            ach, peak, unit = 3.0 * work / per / 1e12, peaks["bf16_tflops"] / 2.0, "TFLOP/s"
+            extra = {"engine": "tcgen05 kind::tf32 x3 (hi/lo split)", "algorithmic_tflops": work / per / 1e12,
+                     "peak_note": "tf32 peak taken as measured bf16 peak / 2"}
         else:
             ach, peak, unit = work / per / 1e12, peaks["bf16_tflops"], "TFLOP/s"
-        out[tag] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
-                    "ms_total": ms, "launches": n, "us_per_launch": per * 1e6}
+        out[tag] = dict({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": TRAFFIC.get(tag),
+                         "ms_total": ms, "launches": n, "us_per_launch": per * 1e6}, **extra)
     return out
 
 
@@ -253,15 +277,6 @@ def run_ours(args):
         devb.append({k: v.to(dev) for k, v in hb.items()})
     h2d_train = sum(v.numel() * v.element_size() for v in host[0].values())
 
-    def allreduce_grads():
-        if world == 1:
-            return
-        # backward-ready order: mlp first (half of the bytes), embed last; one flat bucket each
-        for p in reversed(params):
-            dist.all_reduce(p.grad)
-        for p in params:
-            p.grad.div_(world)
-
     def train_step_eager(b):
         for p in params:
             p.grad = None
@@ -277,12 +292,40 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - l0
 
-    stepper = GraphedTrainStep(model, devb[0], lengths) if args.graph else None
+    dp_mode = None
+    if world == 1:
+        stepper = GraphedTrainStep(model, devb[0], lengths) if args.graph else None
 
-    def train_step(b):
-        loss = stepper(b) if stepper is not None else train_step_eager(b)
-        allreduce_grads()
-        return loss
+        def train_step(b):
+            return stepper(b) if stepper is not None else train_step_eager(b)
+    else:
+        # data parallel: C-ABI forward / loss / hooked backward with the four gradient buckets all-reduced (NCCL, sum) on a
+        # communication stream as soon as each is final, overlapping the rest of the backward; loss and gradients are
+        # normalised by the GLOBAL packed-token count (adaptive_b200/parallel.py)
+        from adaptive_b200.parallel import DataParallelTrainer, GraphedDPStep
+
+        trainer = DataParallelTrainer(model, overlap=bool(args.overlap))
+
+        def dp_eager(b):
+            return trainer.step((b["V"], b["v_g"], (b["h0"], b["c0"])), b["captions"], lengths, b["tgt"])
+
+        stepper = None
+        dp_mode = "eager"
+        if args.graph:
+            ok = torch.ones(1, device=dev)
+            try:
+                stepper = GraphedDPStep(trainer, devb[0], lengths)
+            except Exception as e:      # capture of the NCCL collectives refused: fall back to eager launches on every rank
+                sys.stderr.write("rank %d: CUDA-graph capture of the data-parallel step failed (%s); running eagerly\n" % (rank, e))
+                ok.zero_()
+                stepper = None
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 1:
+                stepper = None
+            dp_mode = "graph" if stepper is not None else "eager"
+
+        def train_step(b):
+            return stepper(b) if stepper is not None else dp_eager(b)
 
     for i in range(args.warmup):
         train_step(devb[i % NB])
@@ -380,13 +423,19 @@ def run_ours(args):
     dom = max((t for t in k_train if "frac" in k_train[t]), key=lambda t: k_train[t]["ms_total"])
     roof = {kk: k_train[dom][kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roof["kernel"] = dom
+    if dom.startswith("lstm_seq"):
+        roof["note"] = ("latency-bound: %d dependent recurrence steps of a [%d x %d] x [%d x %d] contraction inside one cooperative launch; "
+                        "the HBM-bound kernels of this step and of decoding are listed under kernels" %
+                        (TRAIN_T, TRAIN_B, 4 * dims.H, 4 * dims.H, dims.H))
     roof["peak_source"] = peaks["source"]
     roof["share_of_step"] = k_train[dom]["ms_total"] / max(sum(v["ms_total"] for v in k_train.values()), 1e-9)
 
     out = {
         "metric": METRIC, "value": train_tok, "unit": "tokens/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": train_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": dict(workload_config(n_gpus), cuda_graph=bool(args.graph)),
+        "config": dict(workload_config(n_gpus), cuda_graph=bool(stepper is not None),
+                       **({"dp": "4 gradient buckets, NCCL sum all-reduce %s the backward (%s launches)" %
+                           ("overlapped with" if args.overlap else "after", dp_mode)} if world > 1 else {})),
         "clocks": clocks,
         "e2e": {"value": TRAIN_B * TRAIN_T * n_gpus / e2e_train_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d_train,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_train_s * 1e3},
@@ -397,6 +446,7 @@ def run_ours(args):
                    "value": dec_tok, "unit": "tokens/s", "ms_per_step": dec_ms, "steps": dsteps, "gpu_launches": int(dec_launches),
                    "e2e": {"value": DECODE_B * DECODE_L * n_gpus / e2e_dec_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d_dec,
                            "d2h_bytes_per_step": d2h_dec, "ms_per_step": e2e_dec_s * 1e3},
+                   "precision": model.decoder.decode_precision,
                    "roofline_fused_step": k_dec.get("dec_step_fused")},
     }
     if n_gpus == 1:
@@ -420,6 +470,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="training path: bf16 tensor cores (BASELINE config 2) or exact fp32")
     ap.add_argument("--graph", type=int, default=1, help="replay the training step as one CUDA graph (1) or launch eagerly (0)")
+    ap.add_argument("--overlap", type=int, default=1, help="N>1: start each gradient bucket's all-reduce as soon as the backward finishes it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -42,6 +42,8 @@ extern "C" {
 #define AA_PREC_FP32 0   /* exact fp32 everywhere (SIMT contractions): the parity path */
 #define AA_PREC_BF16 1   /* mixed precision: bf16 operands on tcgen05 tensor cores, fp32 accumulation,
                             fp32 master weights / state / softmax / gradients (teacher-forced path only) */
+#define AA_PREC_TF32X3 2 /* decoding: the per-step contractions run on tcgen05 as 3xTF32 over (hi, lo)-split fp32 operands
+                            (fp32-accurate to ~1e-6 relative; fp32 accumulate); everything else exact fp32 */
 typedef struct aa_dims {
   int32_t B, T, k, a, H, E, Vc;
   int32_t precision;   /* AA_PREC_* */
@@ -121,6 +123,13 @@ int aa_linear_forward(int M, int N, int K, const float* X, int64_t ldx, const fl
 int aa_gemm(int engine, int M, int N, int K, const void* A, int64_t lda, int a_kmajor, const void* B, int64_t ldb,
             int b_kmajor, const float* C, int64_t ldc, float beta, const float* bias, float* D, int64_t ldd,
             void* stream);
+
+/* fp32-accurate tensor-core contraction ("3xTF32"): operands pre-split by aa_split_tf32 into rows of 2*Kp floats
+ * [tf32 hi (cols zero-padded to Kp) | lo], Kp a multiple of 32.  D[M,N] = A B^T (+ bias[N]); lo*lo terms are dropped
+ * (relative error ~1e-6, fp32 accumulation).  This is the engine of the two per-step contractions of decoding. */
+int aa_split_tf32(const float* src, int64_t ld_src, int64_t rows, int cols, float* dst, int Kp, void* stream);
+int aa_gemm_split3(int M, int N, int Kp, const float* A_split, const float* B_split, const float* bias, float* D,
+                   int64_t ldd, void* stream);
 
 /* P = V * W_v^T, once per image (adaptive_attention.py:34, `affine_v(V)`).  V [B,k,H] -> P [B,k,a]. */
 int aa_precompute_P(const aa_dims* d, const float* V, const float* att_wv, float* P, void* stream);

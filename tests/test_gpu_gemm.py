@@ -85,3 +85,38 @@ def test_tcgen05_rejects_misaligned():
     D = torch.empty(64, 64, device="cuda")
     rc = lib.aa_gemm(1, 64, 64, 65, _ptr(A), 65, 1, _ptr(B), 65, 1, None, 0, 0.0, None, _ptr(D), 64, _stream(D.device))
     assert rc != 0 and b"16 bytes" in lib.aa_last_error()
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES + [(4096, 10000, 512), (300, 49, 100), (64, 2560, 776)])
+def test_tcgen05_split3_is_fp32_accurate(M, N, K):
+    """3xTF32 over (hi, lo)-split operands: fp32-level accuracy (the engine of the decode contractions)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, generator=g, device="cuda")
+    B = torch.randn(N, K, generator=g, device="cuda")
+    bias = torch.randn(N, generator=g, device="cuda")
+    Kp = (K + 31) // 32 * 32
+    As = torch.full((M, 2 * Kp), float("nan"), device="cuda")
+    Bs = torch.full((N, 2 * Kp), float("nan"), device="cuda")
+    D = torch.full((M, N), float("nan"), device="cuda")
+    lib = _lib.load()
+    st = _stream(D.device)
+    _lib.check(lib.aa_split_tf32(_ptr(A), K, M, K, _ptr(As), Kp, st), "aa_split_tf32")
+    _lib.check(lib.aa_split_tf32(_ptr(B), K, N, K, _ptr(Bs), Kp, st), "aa_split_tf32")
+    _lib.check(lib.aa_gemm_split3(M, N, Kp, _ptr(As), _ptr(Bs), _ptr(bias), _ptr(D), N, st), "aa_gemm_split3")
+    torch.cuda.synchronize()
+    # the split itself: hi has 13 zero low mantissa bits, hi + lo reproduces x to ~2^-22, pads are zero
+    hi, lo = As[:, :K], As[:, Kp:Kp + K]
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert float(((hi.double() + lo.double()) - A.double()).abs().max()) <= 2.0 ** -21 * float(A.abs().max())
+    if Kp > K:
+        assert float(As[:, K:Kp].abs().max()) == 0 and float(As[:, Kp + K:].abs().max()) == 0
+    ref = A.double() @ B.double().t() + bias.double()
+    err = float((D.double() - ref).abs().max() / ref.abs().max())
+    simt = torch.empty(M, N, device="cuda")
+    _lib.check(lib.aa_gemm(0, M, N, K, _ptr(A), K, 1, _ptr(B), K, 1, None, N, 0.0, _ptr(bias), _ptr(simt), N, st), "aa_gemm")
+    err_simt = float((simt.double() - ref).abs().max() / ref.abs().max())
+    assert torch.isfinite(D).all()
+    # single-pass tf32 is ~1e-3, fp32 SIMT ~1e-6.  3xTF32 measures 3.6e-6 at K=512 and 2.9e-5 at K=3920 on B200: the tensor
+    # core adds into its fp32 accumulator with truncation, so the error grows linearly with the number of accumulation
+    # steps (3 per 8 elements of K) instead of with its square root.  The decode contractions have K <= 1536.
+    assert err < 1e-5 * max(1.0, K / 1024), (err, err_simt)

@@ -134,16 +134,20 @@ def test_no_initial_state_and_state_layouts():
     assert torch.equal(a, b)
 
 
+DECODE_PRECISIONS = ("fp32", "tf32x3")     # exact SIMT contractions / 3xTF32 on tcgen05 (the sampler's default)
+
+
+@pytest.mark.parametrize("prec", DECODE_PRECISIONS)
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_greedy_vs_golden(case):
+def test_greedy_vs_golden(case, prec):
     g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
     W = dev_weights(w)
     V, v_g, h0, c0, cap = dev_inputs(inp)
-    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L)
+    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision=prec)
     ids, att, bet = ids.cpu().numpy(), att.cpu().numpy(), bet.cpu().numpy()
     ref_ids, gap = g["f64_greedy_ids"], g["f64_greedy_gap"]
     hard, near = near_tie_report(ids, ref_ids, gap, NEAR_TIE)
-    _log_near_ties("greedy_vs_golden[%s]" % case, near)
+    _log_near_ties("greedy_vs_golden[%s,%s]" % (case, prec), near)
     assert not hard, hard
     same = (ids == ref_ids).all(1)
     assert same.any()
@@ -153,7 +157,8 @@ def test_greedy_vs_golden(case):
     assert np.array_equal(att[same].argmax(-1), g["f64_greedy_alpha"][same].argmax(-1))
 
 
-def test_greedy_vs_oracle_batch256():
+@pytest.mark.parametrize("prec", DECODE_PRECISIONS)
+def test_greedy_vs_oracle_batch256(prec):
     dims, B, L = CFG_A, 256, 20
     w = make_weights(dims, seed=123)
     inp = make_inputs(dims, B, 1, seed=1234)
@@ -164,10 +169,10 @@ def test_greedy_vs_oracle_batch256():
     gap = top2[..., 1] - top2[..., 0]
     W = dev_weights(w)
     V, v_g, h0, c0, _ = dev_inputs(inp)
-    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L)
+    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision=prec)
     ids = ids.cpu().numpy()
     hard, near = near_tie_report(ids, ref_ids, gap, NEAR_TIE)
-    _log_near_ties("greedy_vs_oracle_batch256", near)
+    _log_near_ties("greedy_vs_oracle_batch256[%s]" % prec, near)
     assert not hard, hard
     same = (ids == ref_ids).all(1)
     assert same.mean() > 0.95
@@ -175,25 +180,30 @@ def test_greedy_vs_oracle_batch256():
     assert np.array_equal(att.cpu().numpy()[same].argmax(-1), ref_att[same].argmax(-1))
 
 
-def test_greedy_step_logits_match_decoder_step():
+@pytest.mark.parametrize("prec", DECODE_PRECISIONS)
+def test_greedy_step_logits_match_decoder_step(prec):
     """The fused decode step must equal Decoder.forward with seq-len 1 (Q3) fed with the same tokens."""
     dims, B, L = Dims(H=128, E=64, Vc=500, k=49), 9, 4
     w = make_weights(dims, seed=8, bias_scale=0.1)
     inp = make_inputs(dims, B, 1, seed=9)
     W = dev_weights(w)
     V, v_g, h0, c0, _ = dev_inputs(inp)
-    ids, att, bet, logits = F_aa.greedy_decode(W, V, v_g, h0, c0, L, return_logits=True)
+    ids, att, bet, logits = F_aa.greedy_decode(W, V, v_g, h0, c0, L, return_logits=True, precision=prec)
+    tol = 1e-5 if prec == "fp32" else 2e-5        # 3xTF32 drops the lo*lo products (~2^-22 relative each)
     tok = torch.ones(B, 1, dtype=torch.int64, device="cuda")
     h, c = h0, c0
     for t in range(L):
         s1, a1, b1, h, c = F_aa.decoder_forward(W, V, v_g, tok, h, c)
-        assert rel_err(logits[t].cpu().numpy(), s1[:, 0].cpu().numpy()) < 1e-5
-        assert rel_err(att[:, t].cpu().numpy(), a1[:, 0].cpu().numpy()) < 1e-5
+        assert rel_err(logits[t].cpu().numpy(), s1[:, 0].cpu().numpy()) < tol
+        assert rel_err(att[:, t].cpu().numpy(), a1[:, 0].cpu().numpy()) < tol
+        # the fused arg-max of the vocabulary GEMM's epilogue == arg-max of the logits it would have written
+        assert torch.equal(ids[:, t], logits[t].argmax(-1))
         tok = ids[:, t:t + 1]
 
 
+@pytest.mark.parametrize("prec", DECODE_PRECISIONS)
 @pytest.mark.parametrize("beam", [1, 3])
-def test_beam_vs_oracle(beam):
+def test_beam_vs_oracle(beam, prec):
     dims, B, L = Dims(H=64, E=32, Vc=300, k=49), 6, 8
     w = make_weights(dims, seed=11, bias_scale=0.2)
     w["adaptive.mlp.bias"][orc.END_ID] += 3.0      # make <end> likely so that frozen beams are exercised
@@ -203,7 +213,7 @@ def test_beam_vs_oracle(beam):
     r_ids, r_att, r_bet, r_sc = orc.beam_decode(w64, i64["V"], i64["v_g"], i64["h0"], i64["c0"], beam, L)
     W = dev_weights(w)
     V, v_g, h0, c0, _ = dev_inputs(inp)
-    ids, att, bet, sc = F_aa.beam_decode(W, V, v_g, h0, c0, beam, L)
+    ids, att, bet, sc = F_aa.beam_decode(W, V, v_g, h0, c0, beam, L, precision=prec)
     assert (r_ids == orc.END_ID).any()
     assert np.array_equal(ids.cpu().numpy(), r_ids)
     assert rel_err(sc.cpu().numpy(), r_sc) < TOL
@@ -261,22 +271,24 @@ def test_stage_operators_vs_oracle():
     assert rel_err(sc.cpu().numpy(), sc_ref) < TOL and rel_err(al2.cpu().numpy(), a2) < TOL and rel_err(be2.cpu().numpy(), b2) < TOL
 
 
-def test_full_size_decode_properties():
+@pytest.mark.parametrize("prec", DECODE_PRECISIONS)
+def test_full_size_decode_properties(prec):
     """BASELINE config 3 size (B=4096, max_len 20): size-independent properties."""
     dims, B, L = CFG_A, 4096, 20
     w = make_weights(dims, seed=123)
     inp = make_inputs(dims, B, 1, seed=1234)
     W = dev_weights(w)
     V, v_g, h0, c0, _ = dev_inputs(inp)
-    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L)
+    ids, att, bet = F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision=prec)
     assert ids.shape == (B, L) and int(ids.min()) >= 0 and int(ids.max()) < dims.Vc
     assert torch.allclose(att.sum(-1), torch.ones(B, L, device="cuda"), atol=1e-5)      # k-way alpha sums to 1 (Q5)
     assert float(bet.min()) > 0 and float(bet.max()) < 1
-    ids2, att2, bet2 = F_aa.greedy_decode(W, V, v_g, h0, c0, L)                           # deterministic
+    ids2, att2, bet2 = F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision=prec)           # deterministic
     assert torch.equal(ids, ids2) and torch.equal(att, att2) and torch.equal(bet, bet2)
     # images are independent: decoding a shard gives bit-identical rows (what multi-GPU sharding relies on)
     s = slice(1000, 1512)
-    ids3, att3, _ = F_aa.greedy_decode(W, V[s].contiguous(), v_g[s].contiguous(), h0[s].contiguous(), c0[s].contiguous(), L)
+    ids3, att3, _ = F_aa.greedy_decode(W, V[s].contiguous(), v_g[s].contiguous(), h0[s].contiguous(), c0[s].contiguous(), L,
+                                       precision=prec)
     assert torch.equal(ids3, ids[s]) and torch.equal(att3, att[s])
     # spot-check 64 rows against the fp64 oracle
     pick = np.arange(0, B, 64)
@@ -285,7 +297,7 @@ def test_full_size_decode_properties():
                                               inp["h0"][pick].astype(np.float64), inp["c0"][pick].astype(np.float64), L, want_scores=True)
     top2 = np.sort(r_sc, axis=-1)[..., -2:]
     hard, near = near_tie_report(ids.cpu().numpy()[pick], r_ids, top2[..., 1] - top2[..., 0], NEAR_TIE)
-    _log_near_ties("full_size_decode", near)
+    _log_near_ties("full_size_decode[%s]" % prec, near)
     assert not hard, hard
 
 

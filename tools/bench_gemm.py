@@ -42,6 +42,27 @@ def main():
             t = sorted(ts[2:])[len(ts[2:]) // 2] * 1e-3
             print(json.dumps({"shape": name, "M": M, "N": N, "K": K, "engine": ["fp32_simt", "tc_bf16", "tc_tf32"][engine], "us": t * 1e6,
                               "tflops": 2.0 * M * N * K / t / 1e12}))
+        if ak and bk and not wc:          # fp32-accurate 3xTF32 over pre-split operands (the decode engine)
+            Kp = (K + 31) // 32 * 32
+            A = torch.randn(M, K, device="cuda")
+            B = torch.randn(N, K, device="cuda")
+            As, Bs = torch.empty(M, 2 * Kp, device="cuda"), torch.empty(N, 2 * Kp, device="cuda")
+            D = torch.empty(M, N, device="cuda")
+            st = _stream(D.device)
+            _lib.check(lib.aa_split_tf32(_ptr(A), K, M, K, _ptr(As), Kp, st), "split")
+            _lib.check(lib.aa_split_tf32(_ptr(B), K, N, K, _ptr(Bs), Kp, st), "split")
+            ts = []
+            for i in range(8):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(lib.aa_gemm_split3(M, N, Kp, _ptr(As), _ptr(Bs), None, _ptr(D), N, st), "aa_gemm_split3")
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = sorted(ts[2:])[len(ts[2:]) // 2] * 1e-3
+            print(json.dumps({"shape": name, "M": M, "N": N, "K": K, "engine": "tc_tf32x3", "us": t * 1e6,
+                              "tflops": 2.0 * M * N * K / t / 1e12, "tensor_tflops": 6.0 * M * N * Kp / t / 1e12}))
 
 
 if __name__ == "__main__":
