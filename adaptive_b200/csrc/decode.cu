@@ -5,6 +5,7 @@
 // 26-58, 132).  HBM-bound: per image and step it streams V (k*H*4 B) once plus ~26 KB of
 // state; see DESIGN.md for the byte accounting.
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace aa {
 
@@ -248,21 +249,21 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
   const float w0 = j0 < a ? p.wh[j0] : 0.f, w1 = j1 < a ? p.wh[j1] : 0.f, w2 = j2 < a ? p.wh[j2] : 0.f, w3 = j3 < a ? p.wh[j3] : 0.f;
   for (long long r = (long long)blockIdx.x * DA_WARPS + warp; r < p.R; r += (long long)gridDim.x * DA_WARPS) {
     const long long b = r / p.beam;
-    const float* qr = p.qr + r * 2 * a;
+    const float* qr = p.qr + r * p.ld_qr;
     const float q0 = j0 < a ? qr[j0] : 0.f, q1 = j1 < a ? qr[j1] : 0.f, q2 = j2 < a ? qr[j2] : 0.f, q3 = j3 < a ? qr[j3] : 0.f;
     // ---- scores ----
-    const float* Pb = p.P + b * k * a;
+    const float* Pb = p.P + b * k * p.ldP;
     for (int i0 = 0; i0 < k; i0 += 4) {
       float acc[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         acc[u] = 0.f;
         if (i0 + u < k) {
-          const float* prow = Pb + (long long)(i0 + u) * a;
-          if (j0 < a) acc[u] = w0 * tanhf(__ldg(prow + j0) + q0);
-          if (j1 < a) acc[u] = fmaf(w1, tanhf(__ldg(prow + j1) + q1), acc[u]);
-          if (j2 < a) acc[u] = fmaf(w2, tanhf(__ldg(prow + j2) + q2), acc[u]);
-          if (j3 < a) acc[u] = fmaf(w3, tanhf(__ldg(prow + j3) + q3), acc[u]);
+          const float* prow = Pb + (long long)(i0 + u) * p.ldP;
+          if (j0 < a) acc[u] = w0 * tanhf_fast(__ldg(prow + j0) + q0);
+          if (j1 < a) acc[u] = fmaf(w1, tanhf_fast(__ldg(prow + j1) + q1), acc[u]);
+          if (j2 < a) acc[u] = fmaf(w2, tanhf_fast(__ldg(prow + j2) + q2), acc[u]);
+          if (j3 < a) acc[u] = fmaf(w3, tanhf_fast(__ldg(prow + j3) + q3), acc[u]);
         }
       }
 #pragma unroll
@@ -273,10 +274,10 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
     }
     {   // sentinel score z_s = w_h . tanh(r)
       float acc = 0.f;
-      if (j0 < a) acc = w0 * tanhf(qr[a + j0]);
-      if (j1 < a) acc = fmaf(w1, tanhf(qr[a + j1]), acc);
-      if (j2 < a) acc = fmaf(w2, tanhf(qr[a + j2]), acc);
-      if (j3 < a) acc = fmaf(w3, tanhf(qr[a + j3]), acc);
+      if (j0 < a) acc = w0 * tanhf_fast(qr[a + j0]);
+      if (j1 < a) acc = fmaf(w1, tanhf_fast(qr[a + j1]), acc);
+      if (j2 < a) acc = fmaf(w2, tanhf_fast(qr[a + j2]), acc);
+      if (j3 < a) acc = fmaf(w3, tanhf_fast(qr[a + j3]), acc);
       acc = warp_sum(acc);
       if (lane == 0) zs[k] = acc;
     }
@@ -364,6 +365,315 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same attention step as dec_atten_kernel, restructured as a bulk-copy pipeline (the default whenever the operand
+// layout allows 16-byte bulk copies):
+//   * one persistent CTA per SM; work item = one image (all of its beam rows, NB at a time, share one pass over V);
+//   * a producer warp streams V[b] (k*H*4 contiguous bytes) through an S-stage shared-memory ring with
+//     cp.async.bulk + mbarrier complete_tx, L2 evict-first (V is read once per step and is far larger than L2), and
+//     the small per-item operands (P[b], the rows' [q | r] and [h | s]) through a 3-slot side buffer.  It runs up to a
+//     full ring ahead of the consumers, across item boundaries, so HBM never waits for the score / softmax phases --
+//     this is what the register-staged kernel above cannot do (its loads of V only start once alpha is known, and ncu
+//     shows it issue-latency bound at ~1 IPC per SM: r01_v7 capture);
+//   * two consumer groups of 8 warps take alternate items, so one group's score phase (MUFU) overlaps the other's
+//     context phase (LDS + FMA).  Per item: scores (4 threads per (row, region), interleaved over the attention dim,
+//     two shuffles), softmaxes (warp per row), context sum_i alpha_i V_i straight out of the ring (thread = one float4
+//     column x one region residue class), beta gate and the tf32 (hi, lo) split of u = c_hat + h.
+// HBM-bound on V; the V bytes in flight per SM are the ring size (>= 100 KB), not registers x occupancy.
+constexpr int DT_CG = 2;                  // consumer groups
+constexpr int DT_GT = 256;                // threads per consumer group
+constexpr int DT_GW = DT_GT / 32;
+constexpr int DT_THREADS = DT_CG * DT_GT + 32;   // + producer warp
+constexpr int DT_MAXS = 16;
+constexpr int DT_AUX = 3;                 // side-buffer slots: items n, n+1 in work, n+2 loading
+constexpr size_t DT_SMEM_BUDGET = 220 * 1024;
+constexpr uint32_t DT_STAGE_TARGET = 16 * 1024;
+
+struct DaTmaCfg {
+  int S, rps, nchunks, G, nvec;
+  uint32_t stage_bytes, aux_stride, p_bytes, qr_off, hs_off;
+  uint32_t off_aux, off_wh, off_grp, grp_stride, off_als, off_bts, off_red, off_bar;   // byte offsets (128-byte aligned base)
+};
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   tc::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void group_bar(int cg) { asm volatile("bar.sync %0, %1;" ::"r"(cg + 1), "n"(DT_GT) : "memory"); }
+
+template <int NB>
+__global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const DecodeAttenArgs p, const DaTmaCfg cf) {
+  using namespace tc;
+  extern __shared__ uint8_t dt_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dt_raw) + 127) & ~(uintptr_t)127);
+  uint8_t* ring = sm;
+  uint8_t* auxb = sm + cf.off_aux;
+  float* whs = reinterpret_cast<float*>(sm + cf.off_wh);
+  uint64_t* fullV = reinterpret_cast<uint64_t*>(sm + cf.off_bar);
+  uint64_t* emptyV = fullV + DT_MAXS;
+  uint64_t* fullA = emptyV + DT_MAXS;
+  uint64_t* emptyA = fullA + DT_AUX;
+
+  const int k = p.k, a = p.a, H = p.H, S = cf.S;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int groups = (p.beam + NB - 1) / NB;
+  const long long nitems = (long long)(p.R / p.beam) * groups;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&fullV[s], 1); mbar_init(&emptyV[s], DT_GW); }
+    for (int s = 0; s < DT_AUX; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], DT_GW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = tid; j < a; j += DT_THREADS) whs[j] = p.wh[j];
+  __syncthreads();
+
+  if (warp == DT_CG * DT_GW) {
+    // ===== producer =====
+    if (lane == 0) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      int s = 0;
+      uint32_t ph = 0;
+      int n = 0;
+      for (long long item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+        const long long b = item / groups;
+        const int g = (int)(item % groups);
+        const int nrows = min(NB, p.beam - g * NB);
+        const long long r0 = b * p.beam + (long long)g * NB;
+        const int slot = n % DT_AUX;
+        mbar_wait(&emptyA[slot], ((n / DT_AUX) & 1) ^ 1);
+        uint8_t* aux = auxb + (size_t)slot * cf.aux_stride;
+        const uint32_t qb = (uint32_t)nrows * (uint32_t)p.ld_qr * 4u, hb = (uint32_t)nrows * 2u * (uint32_t)H * 4u;
+        mbar_expect_tx(&fullA[slot], cf.p_bytes + qb + hb);
+        bulk_g2s(aux, p.P + b * k * p.ldP, cf.p_bytes, &fullA[slot]);
+        bulk_g2s(aux + cf.qr_off, p.qr + r0 * p.ld_qr, qb, &fullA[slot]);
+        bulk_g2s(aux + cf.hs_off, p.hs + r0 * 2 * H, hb, &fullA[slot]);
+        const float* Vb = p.V + b * k * H;
+        for (int c = 0; c < cf.nchunks; ++c) {
+          const int nreg = min(cf.rps, k - c * cf.rps);
+          const uint32_t bytes = (uint32_t)nreg * (uint32_t)H * 4u;
+          mbar_wait(&emptyV[s], ph ^ 1);
+          mbar_expect_tx(&fullV[s], bytes);
+          bulk_g2s_hint(ring + (size_t)s * cf.stage_bytes, Vb + (long long)c * cf.rps * H, bytes, &fullV[s], pol);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers: group cg takes the CTA's items n = cg, cg + DT_CG, ... =====
+  const int cg = warp / DT_GW;
+  const int gt = tid - cg * DT_GT;            // thread within the group
+  const int gw = gt >> 5;                     // warp within the group
+  float* zs = reinterpret_cast<float*>(sm + cf.off_grp + (size_t)cg * cf.grp_stride);   // [NB][k+1]
+  float* als = reinterpret_cast<float*>(sm + cf.off_grp + (size_t)cg * cf.grp_stride + cf.off_als);   // [NB][k]
+  float* bts = reinterpret_cast<float*>(sm + cf.off_grp + (size_t)cg * cf.grp_stride + cf.off_bts);   // [NB]
+  float* red = reinterpret_cast<float*>(sm + cf.off_grp + (size_t)cg * cf.grp_stride + cf.off_red);   // [G-1][NB][H]
+  const int nvec = cf.nvec, G = cf.G;
+  const bool act = gt < G * nvec;
+  const int vec = gt % nvec, grp = gt / nvec;
+  const int sub = gt & 3;
+  for (int n = cg;; n += DT_CG) {
+    const long long item = blockIdx.x + (long long)n * gridDim.x;
+    if (item >= nitems) break;
+    const long long b = item / groups;
+    const int g = (int)(item % groups);
+    const int nrows = min(NB, p.beam - g * NB);
+    const long long r0 = b * p.beam + (long long)g * NB;
+    const int slot = n % DT_AUX;
+    const uint8_t* aux = auxb + (size_t)slot * cf.aux_stride;
+    const float* Ps = reinterpret_cast<const float*>(aux);
+    const float* qs = reinterpret_cast<const float*>(aux + cf.qr_off);
+    const float* hss = reinterpret_cast<const float*>(aux + cf.hs_off);
+    mbar_wait(&fullA[slot], (n / DT_AUX) & 1);
+    // ---- scores: unit = (row j, region i), i == k the sentinel; 4 threads per unit over the attention dim ----
+    const int units = nrows * (k + 1);
+    for (int ub = 0; ub < units; ub += DT_GT / 4) {
+      const int unit = ub + (gt >> 2);
+      float acc = 0.f;
+      if (unit < units) {
+        const int j = unit / (k + 1), i = unit - j * (k + 1);
+        const float* qrow = qs + j * p.ld_qr;
+        if (i < k) {          // z_i = w_h . tanh(P_i + q)                                adaptive_attention.py:37-38
+          const float* prow = Ps + (long long)i * p.ldP;
+#pragma unroll 4
+          for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanhf_fast(prow[jj] + qrow[jj]), acc);
+        } else {              // z_s = w_h . tanh(r)                                      adaptive_attention.py:46-47
+          const float* rrow = qrow + a;
+#pragma unroll 4
+          for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanhf_fast(rrow[jj]), acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (sub == 0 && unit < units) zs[unit] = acc;
+    }
+    group_bar(cg);
+    // ---- softmaxes (adaptive_attention.py:39,51): warp j owns row j ----
+    for (int j = gw; j < nrows; j += DT_GW) {
+      const float* z = zs + j * (k + 1);
+      const long long r = r0 + j;
+      float m = -INFINITY;
+      for (int i = lane; i < k; i += 32) m = fmaxf(m, z[i]);
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int i = lane; i < k; i += 32) sum += expf(z[i] - m);
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      const float zsent = z[k];
+      const float m1 = fmaxf(m, zsent);
+      float sum1 = 0.f;
+      for (int i = lane; i < k; i += 32) sum1 += expf(z[i] - m1);
+      sum1 = warp_sum(sum1);
+      const float es = expf(zsent - m1);
+      const float beta = es / (sum1 + es);
+      for (int i = lane; i < k; i += 32) {
+        const float al = expf(z[i] - m) * inv;
+        als[j * k + i] = al;
+        p.alpha[r * p.ld_alpha + i] = al;
+      }
+      if (lane == 0) {
+        bts[j] = beta;
+        p.beta[r * p.ld_beta] = beta;
+      }
+    }
+    group_bar(cg);
+    // ---- context out of the ring ----
+    float4 acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int it0 = n * cf.nchunks;
+    int s = it0 % S;
+    uint32_t ph = (uint32_t)(it0 / S) & 1u;
+    for (int c = 0; c < cf.nchunks; ++c) {
+      const int i0 = c * cf.rps;
+      const int nreg = min(cf.rps, k - i0);
+      mbar_wait(&fullV[s], ph);
+      if (act) {
+        const float* vs = reinterpret_cast<const float*>(ring + (size_t)s * cf.stage_bytes) + vec * 4;
+        int first = grp - i0 % G;
+        if (first < 0) first += G;
+#pragma unroll 4
+        for (int i = first; i < nreg; i += G) {
+          const float4 v = *reinterpret_cast<const float4*>(vs + (size_t)i * H);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            if (j < nrows) {
+              const float al = als[j * k + i0 + i];
+              acc[j].x = fmaf(al, v.x, acc[j].x); acc[j].y = fmaf(al, v.y, acc[j].y);
+              acc[j].z = fmaf(al, v.z, acc[j].z); acc[j].w = fmaf(al, v.w, acc[j].w);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&emptyV[s]);
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+    if (act && grp > 0) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (j < nrows) *reinterpret_cast<float4*>(red + ((size_t)(grp - 1) * NB + j) * H + vec * 4) = acc[j];
+    }
+    group_bar(cg);   // partial sums visible; also: every read of zs / als of this item is done
+    if (act && grp == 0) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < nrows) {
+          float4 t = acc[j];
+          for (int gg = 1; gg < G; ++gg) {
+            const float4 o = *reinterpret_cast<const float4*>(red + ((size_t)(gg - 1) * NB + j) * H + vec * 4);
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+          }
+          const float beta = bts[j];
+          const float4 hv = *reinterpret_cast<const float4*>(hss + (size_t)j * 2 * H + vec * 4);
+          const float4 sv = *reinterpret_cast<const float4*>(hss + (size_t)j * 2 * H + H + vec * 4);
+          float4 o;
+          o.x = beta * sv.x + (1.f - beta) * t.x + hv.x;
+          o.y = beta * sv.y + (1.f - beta) * t.y + hv.y;
+          o.z = beta * sv.z + (1.f - beta) * t.z + hv.z;
+          o.w = beta * sv.w + (1.f - beta) * t.w + hv.w;
+          float4 hi, lo;
+          split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
+          float* urow = p.u + (r0 + j) * p.ld_u + vec * 4;
+          *reinterpret_cast<float4*>(urow) = hi;
+          *reinterpret_cast<float4*>(urow + p.u_lo_off) = lo;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&emptyA[slot]);   // this warp is done with the item's P / qr / hs
+  }
+}
+
+// shared-memory plan of the pipeline for one shape; false when the shape does not fit (the caller falls back)
+bool plan_da_tma(const DecodeAttenArgs& p, int NB, DaTmaCfg& cf, size_t& smem) {
+  const int k = p.k, H = p.H;
+  const uint32_t row_bytes = (uint32_t)H * 4u;
+  int max_rps = (int)(DT_STAGE_TARGET / row_bytes);
+  if (max_rps < 1) max_rps = 1;
+  if (max_rps > k) max_rps = k;
+  cf.nchunks = ceil_div(k, max_rps);
+  cf.rps = ceil_div(k, cf.nchunks);
+  cf.nchunks = ceil_div(k, cf.rps);
+  cf.stage_bytes = (uint32_t)align_up((size_t)cf.rps * row_bytes, 128);
+  cf.nvec = H / 4;
+  cf.G = DT_GT / cf.nvec;
+  if (cf.G < 1) return false;                     // H > 1024
+  if (cf.G > k) cf.G = k;
+  cf.p_bytes = (uint32_t)k * (uint32_t)p.ldP * 4u;
+  cf.qr_off = (uint32_t)align_up(cf.p_bytes, 128);
+  cf.hs_off = cf.qr_off + (uint32_t)align_up((size_t)NB * p.ld_qr * 4, 128);
+  cf.aux_stride = cf.hs_off + (uint32_t)align_up((size_t)NB * 2 * H * 4, 128);
+  const size_t wh_bytes = align_up(sizeof(float) * (size_t)p.a, 16);
+  const size_t g_zs = align_up(sizeof(float) * NB * (size_t)(k + 1), 16);
+  const size_t g_als = align_up(sizeof(float) * NB * (size_t)k, 16);
+  const size_t g_bts = 16 * ((NB + 3) / 4);
+  const size_t g_red = sizeof(float) * (size_t)(cf.G - 1) * NB * H;
+  const size_t g_all = align_up(g_zs + g_als + g_bts + g_red, 16);
+  const size_t bars = sizeof(uint64_t) * (2 * DT_MAXS + 2 * DT_AUX);
+  const size_t fixed = DT_AUX * (size_t)cf.aux_stride + wh_bytes + DT_CG * g_all + bars + 128 /* base alignment */;
+  if (fixed + 3 * (size_t)cf.stage_bytes > DT_SMEM_BUDGET) return false;
+  size_t S = (DT_SMEM_BUDGET - fixed) / cf.stage_bytes;
+  if (S > (size_t)DT_MAXS) S = DT_MAXS;
+  cf.S = (int)S;
+  cf.off_aux = (uint32_t)(S * cf.stage_bytes);
+  cf.off_wh = cf.off_aux + DT_AUX * cf.aux_stride;
+  cf.off_grp = cf.off_wh + (uint32_t)wh_bytes;
+  cf.grp_stride = (uint32_t)g_all;
+  cf.off_als = (uint32_t)g_zs;
+  cf.off_bts = cf.off_als + (uint32_t)g_als;
+  cf.off_red = cf.off_bts + (uint32_t)g_bts;
+  cf.off_bar = (uint32_t)align_up(cf.off_grp + DT_CG * g_all, 8);
+  smem = cf.off_bar + bars + 128;
+  return true;
+}
+
+template <int NB>
+int launch_da_tma(const DecodeAttenArgs& p, const DaTmaCfg& cf, size_t smem, cudaStream_t s) {
+  auto kern = dec_atten_tma_kernel<NB>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int groups = (p.beam + NB - 1) / NB;
+  const long long items = (long long)(p.R / p.beam) * groups;
+  const int sms = num_sms();
+  kern<<<(unsigned)(items < sms ? items : sms), DT_THREADS, smem, s>>>(p, cf);
+  AA_CHECK_LAUNCH("dec_atten_tma");
+  return AA_OK;
+}
+
 template <int NCH, int RU>
 int launch_da(const DecodeAttenArgs& p, cudaStream_t s) {
   const size_t smem = sizeof(float) * DA_WARPS * (size_t)(p.k + 1);
@@ -395,7 +705,25 @@ int launch_decode_atten(const DecodeAttenArgs& p, cudaStream_t s) {
   AA_REQUIRE(p.H % 4 == 0 && p.H <= 1024, "decode_atten: H must be a multiple of 4 and <= 1024 (got %d)", p.H);
   AA_REQUIRE(p.a <= 128 && p.k >= 1 && p.k <= 4096, "decode_atten: need a <= 128 and 1 <= k <= 4096");
   AA_REQUIRE(p.beam >= 1 && p.ld_u % 4 == 0 && p.u_lo_off % 4 == 0, "decode_atten: bad beam / u layout");
+  AA_REQUIRE(p.ldP >= p.a && p.ld_qr >= 2 * p.a && p.R % p.beam == 0, "decode_atten: bad P / qr strides or R not a multiple of beam");
   if (p.R == 0) return AA_OK;
+  // bulk-copy pipeline whenever every streamed operand is 16-byte addressable and the shape fits shared memory
+  const bool aligned = p.ldP % 4 == 0 && p.ld_qr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.V) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p.P) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.qr) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(p.hs) & 15) == 0 && !p.force_simple;
+  if (aligned) {
+    const int NB = p.beam >= 4 ? 4 : p.beam;
+    DaTmaCfg cf{};
+    size_t smem = 0;
+    if (plan_da_tma(p, NB, cf, smem)) {
+      switch (NB) {
+        case 1: return launch_da_tma<1>(p, cf, smem, s);
+        case 2: return launch_da_tma<2>(p, cf, smem, s);
+        case 3: return launch_da_tma<3>(p, cf, smem, s);
+        default: return launch_da_tma<4>(p, cf, smem, s);
+      }
+    }
+  }
   if (p.H <= 128) return launch_da<1, 8>(p, s);
   if (p.H <= 256) return launch_da<2, 8>(p, s);
   if (p.H <= 512) return launch_da<4, 4>(p, s);

@@ -12,6 +12,7 @@ namespace {
 constexpr int START_ID = 1;  // adaptive_attention.py:188
 constexpr int END_ID = 2;    // build_vocab.py:48-51
 constexpr int MAX_BEAM = 8;
+int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
 
 struct Carver {
   char* base;
@@ -32,6 +33,7 @@ struct DecodeWs {
   // reads the [emb | h] window, the q/r GEMM the [h | s] window.  W2 = [[W_g, 0], [W_g, W_s]] gives [q | r] in one GEMM.
   float *Wp_s, *pmax, *W2, *hs, *qr; int* pidx;
   int split, bm, K, Kp, lo, K2p, Hp, ldA, ldU, tiles_n;
+  int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
   // beam only
   float *cum, *row_max, *row_lsum, *rec_alpha, *rec_beta;
   int *rec_word, *rec_src, *rec_wasdone, *done;
@@ -55,11 +57,13 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.ldA = w.split ? 2 * w.lo : (int)K;
   w.ldU = w.split ? 2 * w.Hp : (int)H;
   w.tiles_n = ceil_div(d.Vc, gemm_tc_argmax_tile_n(d.Vc));
+  w.ldP = w.split ? (d.a + 3) / 4 * 4 : d.a;
+  w.ld_qr = (2 * d.a + 3) / 4 * 4;
   w.Wcat = c.take<float>((size_t)5 * H * (w.split ? 2 * w.Kp : (int)K));
   w.W2 = c.take<float>(w.split ? (size_t)2 * d.a * 2 * w.K2p : 0);
   w.hs = c.take<float>(w.split ? R * 2 * H : 0);
-  w.qr = c.take<float>(w.split ? R * 2 * d.a : 0);
-  w.P = c.take<float>(B * d.k * d.a);
+  w.qr = c.take<float>(w.split ? R * w.ld_qr : 0);
+  w.P = c.take<float>(B * d.k * w.ldP);
   w.stat = c.take<float>(R * 5 * H);
   w.Acat = c.take<float>(R * w.ldA);
   w.gates = c.take<float>(R * 5 * H);
@@ -365,7 +369,11 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
     if (ws.bm) AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat2, 0, sizeof(float) * (size_t)R * ws.ldA, st));
     if (ws.Hp != H) AA_CHECK_CUDA(cudaMemsetAsync(ws.u, 0, sizeof(float) * (size_t)R * ws.ldU, st));
   }
-  AA_TRY(gemm_nt(B * d.k, d.a, H, V, H, w.att_wv, H, ws.P, d.a, nullptr, 0, nullptr, nullptr, st));
+  if (ws.split && (ws.ldP != d.a || ws.ld_qr != 2 * d.a)) {   // pad columns are streamed into shared memory with their rows (never read): keep them finite
+    AA_CHECK_CUDA(cudaMemsetAsync(ws.P, 0, sizeof(float) * (size_t)B * d.k * ws.ldP, st));
+    AA_CHECK_CUDA(cudaMemsetAsync(ws.qr, 0, sizeof(float) * (size_t)R * ws.ld_qr, st));
+  }
+  AA_TRY(gemm_nt(B * d.k, d.a, H, V, H, w.att_wv, H, ws.P, ws.ldP, nullptr, 0, nullptr, nullptr, st));
   // static (per image) gate terms: v_g half of x and the biases
   float* stat_img = beam > 1 ? ws.gates : ws.stat;   // [B,5H]; `gates` is free before the first step
   AA_TRY(gemm_nt(B, 4 * H, E, v_g, E, w.w_ih + E, 2 * E, stat_img, 5 * H, nullptr, 0, w.b_ih, w.b_hh, st));
@@ -402,10 +410,11 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
   AA_PROF("dec_cell", st, launch_decode_cell(cp, st));
   // [q | r] = [h | s] W2^T                                                              adaptive_attention.py:35,45
   AA_PROF("dec_qr_gemm", st, dec_gemm(ws, R, 2 * d.a, 2 * H, ws.K2p, Acur + E, ws.ldA, ws.lo, ws.ldA - E, ws.W2, 2 * ws.K2p, ws.qr,
-                                      2 * d.a, nullptr, 0, nullptr, nullptr, nullptr, st));
+                                      ws.ld_qr, nullptr, 0, nullptr, nullptr, nullptr, st));
   DecodeAttenArgs ap{};
   ap.R = R; ap.k = d.k; ap.a = d.a; ap.H = H; ap.beam = beam;
-  ap.qr = ws.qr; ap.hs = ws.hs; ap.P = ws.P; ap.V = V; ap.wh = w.att_wh;
+  ap.qr = ws.qr; ap.ld_qr = ws.ld_qr; ap.hs = ws.hs; ap.P = ws.P; ap.ldP = ws.ldP; ap.V = V; ap.wh = w.att_wh;
+  ap.force_simple = g_force_simple_atten;
   ap.alpha = alpha; ap.ld_alpha = ld_alpha; ap.beta = beta; ap.ld_beta = ld_beta;
   ap.u = ws.u; ap.ld_u = ws.ldU; ap.u_lo_off = ws.Hp;
   AA_PROF("dec_step_fused", st, launch_decode_atten(ap, st));
@@ -418,6 +427,11 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
 using namespace aa;
 
 extern "C" {
+
+int aa_debug_set_decode_atten_simple(int on) {
+  g_force_simple_atten = on ? 1 : 0;
+  return AA_OK;
+}
 
 size_t aa_decode_workspace_bytes(const aa_dims* d, int beam) {
   if (!d || beam < 0) return 0;

@@ -175,9 +175,11 @@ int launch_decode_cell(const DecodeCellArgs& p, cudaStream_t s);
 // ... and the attention stream: scores + both softmaxes + beta-gated context + (c_hat + h), one warp per row
 struct DecodeAttenArgs {
   int R, k, a, H, beam;       // R rows; V/P row = r / beam
-  const float* qr;            // [R,2a] = [q | r]   (q = h W_g^T, r = s W_s^T + q)
+  const float* qr; long long ld_qr;   // [R, ld_qr >= 2a] = [q | r]   (q = h W_g^T, r = s W_s^T + q)
   const float* hs;            // [R,2H] = [h | s]
-  const float *P, *V, *wh;    // [R/beam,k,a], [R/beam,k,H], [a]
+  const float *P, *V, *wh;    // [R/beam,k,ldP >= a], [R/beam,k,H], [a]
+  long long ldP;              // row stride of P (a multiple of 4 enables the bulk-copy pipeline)
+  int force_simple;           // != 0: always take the register-staged kernel (tests)
   float* alpha; long long ld_alpha;
   float* beta; long long ld_beta;
   float* u; long long ld_u, u_lo_off;    // u = c_hat + h as tf32 (hi, lo): hi at [0,H), lo at [u_lo_off, u_lo_off+H)

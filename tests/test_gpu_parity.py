@@ -221,6 +221,58 @@ def test_beam_vs_oracle(beam, prec):
     assert rel_err(bet.cpu().numpy(), r_bet) < TOL
 
 
+@pytest.mark.parametrize("dims,B,beam,L", [
+    (Dims(H=512, E=256, Vc=600, k=49), 300, 1, 3),      # cfgA shape: 2 region groups, 7 chunks of 7 regions, > 148 images
+    (Dims(H=1024, E=512, Vc=400, k=196), 9, 1, 2),      # cfgB shape: 1 group, 49 chunks, large P side slot
+    (Dims(H=128, E=64, Vc=300, k=49), 160, 3, 3),       # beam rows share one pass over V (NB = 3), 8 region groups
+    (Dims(H=64, E=32, Vc=300, k=10), 5, 5, 3),          # beam 5 = one group of 4 rows + one of 1; G capped by k
+    (Dims(H=36, E=20, Vc=200, k=3, a=8), 3, 2, 2),      # a % 4 == 0 (unpadded strides), idle consumer threads
+    (Dims(H=100, E=28, Vc=200, k=33, a=127), 4, 1, 2),  # 4 lane slots over the attention dim, odd everything
+])
+def test_decode_attention_pipeline_vs_simple_kernel_and_oracle(dims, B, beam, L):
+    """The bulk-copy (cp.async.bulk + mbarrier ring) attention kernel against the register-staged kernel it replaces
+    (same ids, alpha/beta to rounding) and against the fp64 oracle."""
+    from adaptive_b200 import _lib
+    lib = _lib.load()
+    w = make_weights(dims, seed=21, bias_scale=0.1)
+    inp = make_inputs(dims, B, 1, seed=22)
+    W = dev_weights(w)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+
+    def run():
+        if beam == 1:
+            return F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision="tf32x3")
+        return F_aa.beam_decode(W, V, v_g, h0, c0, beam, L, precision="tf32x3")[:3]
+
+    ids, att, bet = run()
+    try:
+        lib.aa_debug_set_decode_atten_simple(1)
+        ids_s, att_s, bet_s = run()
+    finally:
+        lib.aa_debug_set_decode_atten_simple(0)
+    torch.cuda.synchronize()
+    assert torch.equal(ids, ids_s)
+    assert rel_err(att.cpu().numpy(), att_s.cpu().numpy()) < 1e-6
+    assert rel_err(bet.cpu().numpy(), bet_s.cpu().numpy()) < 1e-6
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    i64 = {k: (v.astype(np.float64) if v.dtype != np.int64 else v) for k, v in inp.items()}
+    if beam == 1:
+        r_ids, r_att, r_bet, r_sc = orc.greedy_decode(w64, i64["V"], i64["v_g"], i64["h0"], i64["c0"], L, want_scores=True)
+        top2 = np.sort(r_sc, axis=-1)[..., -2:]
+        hard, near = near_tie_report(ids.cpu().numpy(), r_ids, top2[..., 1] - top2[..., 0], NEAR_TIE)
+        assert not hard, hard
+        same = (ids.cpu().numpy() == r_ids).all(1)
+        assert same.mean() > 0.9
+        assert rel_err(att.cpu().numpy()[same], r_att[same]) < TOL
+        assert rel_err(bet.cpu().numpy()[same], r_bet[same]) < TOL
+    else:
+        r_ids, r_att, r_bet, _ = orc.beam_decode(w64, i64["V"], i64["v_g"], i64["h0"], i64["c0"], beam, L)
+        same = (ids.cpu().numpy() == r_ids).all(1)
+        assert same.mean() > 0.9            # beam ties between near-equal hypotheses may legitimately flip
+        assert rel_err(att.cpu().numpy()[same], r_att[same]) < TOL
+        assert rel_err(bet.cpu().numpy()[same], r_bet[same]) < TOL
+
+
 def test_pack_and_cross_entropy_vs_golden():
     for case in ("tiny", "odd"):
         g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
