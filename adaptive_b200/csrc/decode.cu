@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(256) dec_cell_kernel(const DecodeCellArgs p) {
 //   ctx = sum_i alpha_i V_i: each lane owns 4*NCH columns, V rows streamed with 128-bit coalesced loads
 //   (R rows in flight per lane), read exactly once (L1::no_allocate)
 // HBM-bound on V (k*H*4 bytes per image and step).
+__device__ __forceinline__ float tanh_mufu(float x);
 constexpr int DA_WARPS = 8;
 template <int NCH, int RU>
 __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAttenArgs p) {
@@ -260,10 +261,10 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
         acc[u] = 0.f;
         if (i0 + u < k) {
           const float* prow = Pb + (long long)(i0 + u) * p.ldP;
-          if (j0 < a) acc[u] = w0 * tanhf_fast(__ldg(prow + j0) + q0);
-          if (j1 < a) acc[u] = fmaf(w1, tanhf_fast(__ldg(prow + j1) + q1), acc[u]);
-          if (j2 < a) acc[u] = fmaf(w2, tanhf_fast(__ldg(prow + j2) + q2), acc[u]);
-          if (j3 < a) acc[u] = fmaf(w3, tanhf_fast(__ldg(prow + j3) + q3), acc[u]);
+          if (j0 < a) acc[u] = w0 * tanh_mufu(__ldg(prow + j0) + q0);
+          if (j1 < a) acc[u] = fmaf(w1, tanh_mufu(__ldg(prow + j1) + q1), acc[u]);
+          if (j2 < a) acc[u] = fmaf(w2, tanh_mufu(__ldg(prow + j2) + q2), acc[u]);
+          if (j3 < a) acc[u] = fmaf(w3, tanh_mufu(__ldg(prow + j3) + q3), acc[u]);
         }
       }
 #pragma unroll
@@ -274,10 +275,10 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
     }
     {   // sentinel score z_s = w_h . tanh(r)
       float acc = 0.f;
-      if (j0 < a) acc = w0 * tanhf_fast(qr[a + j0]);
-      if (j1 < a) acc = fmaf(w1, tanhf_fast(qr[a + j1]), acc);
-      if (j2 < a) acc = fmaf(w2, tanhf_fast(qr[a + j2]), acc);
-      if (j3 < a) acc = fmaf(w3, tanhf_fast(qr[a + j3]), acc);
+      if (j0 < a) acc = w0 * tanh_mufu(qr[a + j0]);
+      if (j1 < a) acc = fmaf(w1, tanh_mufu(qr[a + j1]), acc);
+      if (j2 < a) acc = fmaf(w2, tanh_mufu(qr[a + j2]), acc);
+      if (j3 < a) acc = fmaf(w3, tanh_mufu(qr[a + j3]), acc);
       acc = warp_sum(acc);
       if (lane == 0) zs[k] = acc;
     }
@@ -407,13 +408,36 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
                "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)), "l"(policy)
                : "memory");
 }
+// tanh from two MUFU ops, 5 instructions: 1 - 2 / (1 + 2^(2x log2 e)); abs error ~1e-7, saturates correctly at +-inf
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+// mbarrier wait without the clock64 guard of tc::mbar_wait (the pipeline's consumers poll often): traps after ~2^28 polls
+__device__ __forceinline__ void mbar_wait_lite(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = tc::smem_u32(bar);
+  uint32_t done, polls = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++polls > (1u << 28)) __trap();
+  } while (!done);
+}
 __device__ __forceinline__ void group_bar(int cg) { asm volatile("bar.sync %0, %1;" ::"r"(cg + 1), "n"(DT_GT) : "memory"); }
 
 template <int NB>
 __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const DecodeAttenArgs p, const DaTmaCfg cf) {
   using namespace tc;
   extern __shared__ uint8_t dt_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dt_raw) + 127) & ~(uintptr_t)127);
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS instead of generic LD/ST)
+  uint8_t* sm = dt_raw + ((128u - (smem_u32(dt_raw) & 127u)) & 127u);
   uint8_t* ring = sm;
   uint8_t* auxb = sm + cf.off_aux;
   float* whs = reinterpret_cast<float*>(sm + cf.off_wh);
@@ -482,6 +506,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
   const bool act = gt < G * nvec;
   const int vec = gt % nvec, grp = gt / nvec;
   const int sub = gt & 3;
+  const int vcol = vec * 4, GH = G * H, rps_mod = cf.rps % G;
   for (int n = cg;; n += DT_CG) {
     const long long item = blockIdx.x + (long long)n * gridDim.x;
     if (item >= nitems) break;
@@ -494,7 +519,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
     const float* Ps = reinterpret_cast<const float*>(aux);
     const float* qs = reinterpret_cast<const float*>(aux + cf.qr_off);
     const float* hss = reinterpret_cast<const float*>(aux + cf.hs_off);
-    mbar_wait(&fullA[slot], (n / DT_AUX) & 1);
+    mbar_wait_lite(&fullA[slot], (n / DT_AUX) & 1);
     // ---- scores: unit = (row j, region i), i == k the sentinel; 4 threads per unit over the attention dim ----
     const int units = nrows * (k + 1);
     for (int ub = 0; ub < units; ub += DT_GT / 4) {
@@ -506,11 +531,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
         if (i < k) {          // z_i = w_h . tanh(P_i + q)                                adaptive_attention.py:37-38
           const float* prow = Ps + (long long)i * p.ldP;
 #pragma unroll 4
-          for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanhf_fast(prow[jj] + qrow[jj]), acc);
+          for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanh_mufu(prow[jj] + qrow[jj]), acc);
         } else {              // z_s = w_h . tanh(r)                                      adaptive_attention.py:46-47
           const float* rrow = qrow + a;
 #pragma unroll 4
-          for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanhf_fast(rrow[jj]), acc);
+          for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanh_mufu(rrow[jj]), acc);
         }
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -554,21 +579,23 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
     const int it0 = n * cf.nchunks;
     int s = it0 % S;
     uint32_t ph = (uint32_t)(it0 / S) & 1u;
+    const uint8_t* stage = ring + (size_t)s * cf.stage_bytes;
+    int resid = 0;                              // (c * rps) % G: this thread takes the regions with global index == grp (mod G)
     for (int c = 0; c < cf.nchunks; ++c) {
       const int i0 = c * cf.rps;
       const int nreg = min(cf.rps, k - i0);
-      mbar_wait(&fullV[s], ph);
+      mbar_wait_lite(&fullV[s], ph);
       if (act) {
-        const float* vs = reinterpret_cast<const float*>(ring + (size_t)s * cf.stage_bytes) + vec * 4;
-        int first = grp - i0 % G;
+        int first = grp - resid;
         if (first < 0) first += G;
-#pragma unroll 4
-        for (int i = first; i < nreg; i += G) {
-          const float4 v = *reinterpret_cast<const float4*>(vs + (size_t)i * H);
+        const float* vp = reinterpret_cast<const float*>(stage) + vcol + first * H;
+        const float* ap = als + i0 + first;
+        for (int i = first; i < nreg; i += G, vp += GH, ap += G) {
+          const float4 v = *reinterpret_cast<const float4*>(vp);
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
-            if (j < nrows) {
-              const float al = als[j * k + i0 + i];
+            if (NB == 1 || j < nrows) {
+              const float al = ap[j * k];
               acc[j].x = fmaf(al, v.x, acc[j].x); acc[j].y = fmaf(al, v.y, acc[j].y);
               acc[j].z = fmaf(al, v.z, acc[j].z); acc[j].w = fmaf(al, v.w, acc[j].w);
             }
@@ -577,7 +604,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&emptyV[s]);
-      if (++s == S) { s = 0; ph ^= 1; }
+      resid += rps_mod;
+      if (resid >= G) resid -= G;
+      stage += cf.stage_bytes;
+      if (++s == S) { s = 0; ph ^= 1; stage = ring; }
     }
     if (act && grp > 0) {
 #pragma unroll

@@ -100,7 +100,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
@@ -222,7 +222,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // instruction writes 4 complete 128-byte row segments: lane -> (row it*4 + lane/8, columns 4*(lane%8)..+3).
     const int q = warp & 3;         // TMEM lane quarter this warp may access
     constexpr int TS = 36;
-    float* tbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15) + (warp - 2) * (32 * TS);
+    // (16-byte aligned by offset arithmetic on the __shared__ pointer: keeps STS/LDS instead of generic ST/LD)
+    uint8_t* tb0 = reinterpret_cast<uint8_t*>(tmem_slot + 1);
+    float* tbuf = reinterpret_cast<float*>(tb0 + ((16u - (smem_u32(tb0) & 15u)) & 15u)) + (warp - 2) * (32 * TS);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {

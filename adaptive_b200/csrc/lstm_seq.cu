@@ -82,7 +82,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const int C = gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS)
   const int STAGES = a.stages;
   uint8_t* sA = smem;                                        // [STAGES][16 KB]
   uint8_t* sW = smem + (size_t)STAGES * A_STAGE_BYTES;       // [KB][N*128]  (N*128 is a multiple of 1024 for N >= 8)
@@ -294,7 +294,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
   const int STAGES = a.stages;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS)
   uint8_t* sA = smem;
   uint8_t* sW = smem + (size_t)STAGES * A_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)KB * W_KB_BYTES);
