@@ -61,7 +61,11 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int TC_THREADS = 192;   // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (TMEM lane quarter = warp % 4)
+// warp 0: TMA, warp 1: MMA, warps 2..: epilogue (TMEM lane quarter = warp % 4).  EW epilogue warps = EW/4 "parts" per
+// lane quarter, each part draining a contiguous range of the tile's 32-column chunks: with 4 warps the TMEM -> smem
+// transpose -> global chain of one warp per quarter bounded the K=512 contractions (1.4 TB/s of output at 148 SMs).
+constexpr int epi_warps(bool split) { return split ? 4 : 8; }   // (split stages leave no room for 8 transpose tiles)
+constexpr int tc_threads(bool split) { return 64 + 32 * epi_warps(split); }
 
 struct TcEpilogue {
   int M, N, K;
@@ -83,7 +87,7 @@ struct TcEpilogue {
 // each sub-tile once and using it in two products gives 1.5x the arithmetic intensity against L2 of a plain
 // 3K-long tf32 contraction.
 template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(SPLIT), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m,
                int num_tiles) {
   // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so neighbouring CTAs share the
@@ -98,6 +102,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t A_BOX = A_MN ? BK * 128 : A_BYTES;        // bytes per TMA box
   constexpr uint32_t B_BOX = B_MN ? BK * 128 : B_BYTES;
   constexpr uint32_t TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int EW = epi_warps(SPLIT);
+  constexpr int NCH = BN / 32;                               // 32-column chunks per tile
+  constexpr int NPARTS = (EW / 4) < NCH ? (EW / 4) : NCH;    // parts with work (a 32-wide tile has one chunk)
+  constexpr int CPP = NCH / NPARTS;                          // chunks per part
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS)
@@ -123,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);    // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], EW);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,8 +180,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the warp stays converged, one elected lane issues (see tc::elect_one) =====
+    {
       // instruction descriptor: D=f32 (bits 4-5 = 1), A/B format (bf16 = 1, tf32 = 2) at bits 7-9 / 10-12,
       // A/B major at bits 15/16 (0 = K, 1 = MN), N>>3 at bits 17-22, M>>4 at bits 24-28
       constexpr uint32_t fmt = TF32 ? 2u : 1u;
@@ -192,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
           const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             if constexpr (SPLIT) {
@@ -210,8 +219,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_mma<TF32>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty_bar[s]);   // frees the smem stage when these MMAs have read it
+          }
+          __syncwarp();
         }
-        tc_commit(&tmem_full[acc]);   // accumulator complete
+        if (elect_one()) tc_commit(&tmem_full[acc]);   // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -226,6 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* tb0 = reinterpret_cast<uint8_t*>(tmem_slot + 1);
     float* tbuf = reinterpret_cast<float*>(tb0 + ((16u - (smem_u32(tb0) & 15u)) & 15u)) + (warp - 2) * (32 * TS);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const int part = (warp - 2) >> 2;      // which contiguous chunk range of the tile this warp drains
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
@@ -235,11 +248,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row0 = m0 + q * 32;
       float best = -INFINITY;     // this thread's row (row0 + lane): running arg-max over the tile's columns
       int best_i = 0x7fffffff;
+      if (part >= NPARTS) {         // nothing to drain for this warp in a narrow tile: just release the accumulator
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = part * CPP; c < (part + 1) * CPP; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        if (c == BN / 32 - 1) {     // whole accumulator read: hand it back to the MMA warp
+        if (c == (part + 1) * CPP - 1) {     // this warp's share of the accumulator is read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -327,8 +344,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
-      if (e.pmax && row0 + lane < e.M) {
-        const long long o = (long long)(row0 + lane) * e.tiles_n + tile / tiles_m;
+      // partial index = first column of this part / (CPP * 32): the layout [M, ceil(N / gemm_tc_argmax_tile_n(N))]
+      if (e.pmax && row0 + lane < e.M && n0 + part * CPP * 32 < e.N) {
+        const long long o = (long long)(row0 + lane) * e.tiles_n + (long long)(tile / tiles_m) * NPARTS + part;
         e.pmax[o] = best;
         e.pidx[o] = best_i;
       }
@@ -361,8 +379,10 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   e.M = g.M; e.N = g.N; e.K = g.K;
   e.D32 = g.D32; e.ldd32 = g.ldd32; e.D16 = g.D16; e.ldd16 = g.ldd16;
   e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
-  e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = tiles_n; e.lo_a = lo_a; e.lo_b = lo_b;
-  constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + 4 * 32 * 36 * 4 + 1024;
+  constexpr int EW = epi_warps(SPLIT);
+  constexpr int NPARTS = (EW / 4) < (BN / 32) ? (EW / 4) : (BN / 32);
+  e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
+  constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN, SPLIT>;
   static bool attr_done = false;
@@ -372,7 +392,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   }
   const int num_tiles = tiles_m * tiles_n;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();     // persistent: one CTA per SM
-  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e, tiles_m, num_tiles);
+  kern<<<grid, tc_threads(SPLIT), smem, st>>>(tmA, tmB, e, tiles_m, num_tiles);
   AA_CHECK_LAUNCH("gemm_tc_kernel");
   return AA_OK;
 }

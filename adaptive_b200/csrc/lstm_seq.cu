@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(SEQ_THREADS, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH0,
                     const __grid_constant__ CUtensorMap tmH, const SeqFwdArgs a) {
   constexpr int N = 4 * U;
-  constexpr int TCOLS = N < 32 ? 32 : N;
+  // Back-to-back tcgen05.mma into the SAME accumulator serialise on the accumulate dependency (~180 cycles each,
+  // measured: 32 dependent N=16 MMAs took 3 us); with the k-steps spread round-robin over NACC accumulators (summed in
+  // the epilogue) the pipe is bound by the A-operand read instead.
+  constexpr int NACC = N <= 32 ? 4 : 2;
+  constexpr int TCOLS = N * NACC < 32 ? 32 : N * NACC;
   constexpr int CH = N < 32 ? N : 32;           // TMEM columns per epilogue chunk
   constexpr int UC = CH / 4;                    // units per chunk
   constexpr uint32_t W_KB_BYTES = N * 128;      // one 64-wide k-block of the weight slice
@@ -124,7 +128,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       for (int t = 0; t < a.T; ++t) {
         if (t > 0) {
           grid_barrier_wait(counter, (unsigned)t * C);   // every CTA of this row group has published h_{t-1}
-          fence_proxy_async();
+          fence_proxy_async_global();
         }
         trace(t, 0);
         for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -139,7 +143,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the MMA warp stays converged; one elected lane issues (see tc::elect_one)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(w_full, 0);
       const uint64_t desc0 = make_smem_desc(0, 16, 1024);
@@ -151,17 +155,22 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
-          if (kb == 0) trace(t, 2);
+          if (kb == 0 && lane == 0) trace(t, 2);
           tc_fence_after();
           // descriptors differ only in the start-address field (bits 0-13, 16-byte units): +2 per 32-byte k-step
           const uint64_t da = desc0 + ((smem_u32(sA + s * A_STAGE_BYTES)) >> 4);
           const uint64_t db = desc0 + ((smem_u32(sW + (size_t)kb * W_KB_BYTES)) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma<false>(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(&empty_bar[s]);
+            for (int k = 0; k < 4; ++k)    // k-step j = kb*4 + k -> accumulator j % NACC (NACC divides 4 or is 4)
+              tc_mma<false>(tmem_base + (uint32_t)((k % NACC) * N), da + 2 * k, db + 2 * k, idesc, (kb * 4 + k) >= NACC ? 1u : 0u);
+            tc_commit(&empty_bar[s]);
+          }
+          __syncwarp();
         }
-        tc_commit(tmem_full);
-        trace(t, 3);
+        if (elect_one()) tc_commit(tmem_full);
+        __syncwarp();
+        if (lane == 0) trace(t, 3);
       }
     }
   } else {
@@ -200,6 +209,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         }
         uint32_t r[CH];
         tmem_ld<CH>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * CH), r);
+#pragma unroll
+        for (int ai = 1; ai < NACC; ++ai) {      // sum the partial accumulators
+          uint32_t r2[CH];
+          tmem_ld<CH>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * N + ch * CH), r2);
+#pragma unroll
+          for (int e = 0; e < CH; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+        }
         if (ch == N / CH - 1) {                  // accumulator fully read: hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -235,10 +251,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       if (threadIdx.x == 64) trace(t, 5);
       epilogue_bar<128>();
       if (threadIdx.x == 64) trace(t, 6);
-      if (warp == 2 && lane == 0 && t + 1 < T) {
-        __threadfence();
-        red_release_gpu_add(a.counters + rg, 1u);
-      }
+      // (red.release.gpu is cumulative over the stores observed through the barrier: no separate __threadfence)
+      if (warp == 2 && lane == 0 && t + 1 < T) red_release_gpu_add(a.counters + rg, 1u);
       if (valid) {   // the remaining outputs are only read after the kernel: off the critical path
 #pragma unroll
         for (int u = 0; u < U; u += 4) {
@@ -285,18 +299,37 @@ struct SeqBwdArgs {
 // 16 hidden units per CTA: dh_rec[:, j-slice] = dgates_{t+1} [B,4H] * W_hh[:, j-slice]  (K = 4H).
 // 16 epilogue warps: warp -> (TMEM lane quarter = warp % 4, column group = (warp-2)/4), i.e. each thread owns
 // one batch row and 4 hidden units, so that all of a step's operand loads are in flight at once.
+// The same 512 threads also FEED the contraction: per step every CTA needs the whole dgates_t block
+// ([rows, 4H] bf16, 320 KB at B=80 / H=512).  A one-thread TMA producer tops out at ~48 B/clk per SM on this
+// access pattern (tools/tma_probe.cu: 3.6 us per step, and 12 us inside the kernel), cooperative 16-byte
+// cp.async.cg copies into the 128B-swizzled K-major layout run as deep as the ring (slots - 1 super-stages of 2
+// k-blocks in flight), completion counted by the slot's mbarrier (cp.async.mbarrier.arrive.noinc).
+constexpr int SS_KB = 2;                                   // k-blocks per super-stage
+constexpr uint32_t SS_BYTES = SS_KB * A_STAGE_BYTES;       // 32 KB
+constexpr int BWD_LOADERS = BWD_THREADS - 64;              // 512
+constexpr int BWD_LPT = (128 * 8 * SS_KB) / BWD_LOADERS;   // 16-byte chunks per thread and super-stage at 128 rows (4)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (does not add to the pending count)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmG, const SeqBwdArgs a) {
-  constexpr int U = 16, N = 16, TCOLS = 32;
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a) {
+  constexpr int U = 16, N = 16, NACC = 8, TCOLS = N * NACC;   // NACC partial accumulators: see lstm_seq_fwd_kernel
   constexpr uint32_t W_KB_BYTES = N * 128;
   const int KB = 4 * a.H / 64;
+  const int NSS = KB / SS_KB;                 // super-stages per step (KB is a multiple of 4)
   const int C = gridDim.x;
-  const int STAGES = a.stages;
+  const int NSLOT = a.stages;                 // ring slots of SS_BYTES
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS)
   uint8_t* sA = smem;
-  uint8_t* sW = smem + (size_t)STAGES * A_STAGE_BYTES;
+  uint8_t* sW = smem + (size_t)NSLOT * SS_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)KB * W_KB_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
@@ -311,7 +344,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
   const int T = a.T, H = a.H;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&full_bar[s], BWD_LOADERS); mbar_init(&empty_bar[s], 1); }
     mbar_init(w_full, 1);
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 16);
@@ -328,27 +361,12 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
 
   // GEMM i (i = 1..T) consumes dgates of step t = T - i and produces dh_rec for step t - 1 (dh0 when t == 0).
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0) {   // resident weight slice: rows [c*U, (c+1)*U) of W_hh^T, all k-blocks
       mbar_expect_tx(w_full, (uint32_t)KB * W_KB_BYTES);
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + (size_t)kb * W_KB_BYTES, &tmWT, kb * 64, c * U, w_full);
-      int it = 0;
-      for (int i = 1; i <= T; ++i) {
-        const int t = T - i;
-        grid_barrier_wait(a.counters + rg, (unsigned)i * C);     // dgates_t complete in this row group
-        fence_proxy_async();
-        trace(i, 0);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], (uint32_t)a.box_rows * 128u);
-          tma_load_2d(sA + s * A_STAGE_BYTES, &tmG, t * 4 * H + kb * 64, m0, &full_bar[s]);
-        }
-        trace(i, 1);
-      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the MMA warp stays converged; one elected lane issues (see tc::elect_one)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(w_full, 0);
       const uint64_t desc0 = make_smem_desc(0, 16, 1024);
@@ -356,21 +374,31 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
       for (int i = 1; i <= T; ++i) {
         mbar_wait(tmem_empty, ((i - 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int ss = 0; ss < NSS; ++ss, ++it) {
+          const int s = it % NSLOT;
+          const uint32_t ph = (it / NSLOT) & 1;
           mbar_wait(&full_bar[s], ph);
-          if (kb == 0) trace(i, 2);
+          if (ss == 0 && lane == 0) trace(i, 2);
+          fence_proxy_async_smem(); // generic-proxy (cp.async) writes -> async-proxy (tcgen05.mma) reads, on the consumer side
           tc_fence_after();
-          // descriptors differ only in the start-address field (bits 0-13, 16-byte units): +2 per 32-byte k-step
-          const uint64_t da = desc0 + ((smem_u32(sA + s * A_STAGE_BYTES)) >> 4);
-          const uint64_t db = desc0 + ((smem_u32(sW + (size_t)kb * W_KB_BYTES)) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma<false>(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int kl = 0; kl < SS_KB; ++kl) {
+            const int kb = ss * SS_KB + kl;
+            // descriptors differ only in the start-address field (bits 0-13, 16-byte units): +2 per 32-byte k-step
+            const uint64_t da = desc0 + ((smem_u32(sA + (size_t)s * SS_BYTES + kl * A_STAGE_BYTES)) >> 4);
+            const uint64_t db = desc0 + ((smem_u32(sW + (size_t)kb * W_KB_BYTES)) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // k-step j = kb*4 + k -> accumulator j % 8 = kl*4 + k (SS_KB == 2, kb = ss*2 + kl)
+              tc_mma<false>(tmem_base + (uint32_t)((kl * 4 + k) * N), da + 2 * k, db + 2 * k, idesc, ss != 0 ? 1u : 0u);
+          }
           tc_commit(&empty_bar[s]);
+          }
+          __syncwarp();
         }
-        tc_commit(tmem_full);
-        trace(i, 3);
+        if (elect_one()) tc_commit(tmem_full);
+        __syncwarp();
+        if (lane == 0) trace(i, 3);
       }
     }
   } else {
@@ -379,6 +407,22 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
     const int row = m0 + q * 32 + lane;
     const bool valid = row < a.B;
     const int j = c * U + cg * 4;              // first of this thread's 4 hidden units
+    // ---- loader role: this thread's 16-byte chunks of a super-stage (fixed for the whole kernel) ----
+    const int tl = threadIdx.x - 64;           // 0..511
+    const int rows = min(128, a.B - m0);
+    const int per_kb = rows * 8;
+    uint32_t ld_dst[BWD_LPT];                  // byte offset inside a ring slot (128B swizzle: chunk ^= row & 7)
+    long long ld_src[BWD_LPT];                 // element offset from dgates16 + step/super-stage base; < 0: none
+#pragma unroll
+    for (int m = 0; m < BWD_LPT; ++m) {
+      const int qi = tl + m * BWD_LOADERS;
+      const int kl = qi / per_kb, rem = qi - kl * per_kb;
+      const int r = rem >> 3, ch = rem & 7;
+      ld_src[m] = kl < SS_KB ? (long long)(m0 + r) * T * 4 * H + kl * 64 + ch * 8 : -1;
+      ld_dst[m] = (uint32_t)(kl * A_STAGE_BYTES + r * 128 + ((ch ^ (r & 7)) << 4));
+    }
+    const uint32_t sA_u32 = smem_u32(sA);
+    int it_issue = 0;                          // super-stages issued so far (all steps)
     float dcreg[4], dhrec[4];                  // dc / dh flowing from step t+1 into step t
     {
       float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -407,25 +451,52 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
         else if (a.c0) cp4 = *reinterpret_cast<const float4*>(a.c0 + (long long)row * H + j);
       }
       if (i >= 1) {
+        // ---- feed GEMM i: dgates of step T - i, complete in this row group once the counter says so ----
+        if (threadIdx.x == 64) {
+          grid_barrier_wait(a.counters + rg, (unsigned)i * C);
+          trace(i, 0);
+        }
+        epilogue_bar<BWD_LOADERS>();
+        const __nv_bfloat16* src0 = a.dgates16 + (long long)(T - i) * 4 * H;
+        for (int ss = 0; ss < NSS; ++ss, ++it_issue) {
+          const int s = it_issue % NSLOT;
+          mbar_wait(&empty_bar[s], ((it_issue / NSLOT) & 1) ^ 1);
+          const uint32_t dst0 = sA_u32 + (uint32_t)s * SS_BYTES;
+          const __nv_bfloat16* src = src0 + ss * (SS_KB * 64);
+#pragma unroll
+          for (int m = 0; m < BWD_LPT; ++m)
+            if (ld_src[m] >= 0) cp_async16(dst0 + ld_dst[m], src + ld_src[m]);
+          // completion of this thread's copies is counted by the slot's mbarrier itself (no wait, no fence here: a
+          // writer-side fence.proxy.async would drain the younger copies and serialise the pipeline)
+          cp_async_arrive_noinc(&full_bar[s]);
+        }
+        if (threadIdx.x == 64) trace(i, 1);
+
         mbar_wait(tmem_full, (i - 1) & 1);
         if (threadIdx.x == 64) trace(i, 4);
         tc_fence_after();
-        uint32_t r[4];
-        tmem_ld<4>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 4), r);
+        uint32_t r[NACC][4];
+#pragma unroll
+        for (int ai = 0; ai < NACC; ++ai) tmem_ld<4>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * N + cg * 4), r[ai]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) dhrec[u] = __uint_as_float(r[u]);
+        for (int u = 0; u < 4; ++u) {
+          float acc = __uint_as_float(r[0][u]);
+#pragma unroll
+          for (int ai = 1; ai < NACC; ++ai) acc += __uint_as_float(r[ai][u]);
+          dhrec[u] = acc;
+        }
       }
       if (t < 0) break;
+      float d0[4], d1[4], d2[4], d3[4];
       if (valid) {
         const float dhav[4] = {dha.x + dhs4.x, dha.y + dhs4.y, dha.z + dhs4.z, dha.w + dhs4.w};
         const float dclv[4] = {dcl.x, dcl.y, dcl.z, dcl.w};
         const float igv[4] = {ig4.x, ig4.y, ig4.z, ig4.w}, fgv[4] = {fg4.x, fg4.y, fg4.z, fg4.w};
         const float ggv[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, ogv[4] = {og4.x, og4.y, og4.z, og4.w};
         const float cev[4] = {ce4.x, ce4.y, ce4.z, ce4.w}, cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
-        float d0[4], d1[4], d2[4], d3[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float dh = dhav[e] + dhrec[e];
@@ -437,25 +508,26 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_const
           d3[e] = dh * tcv * ogv[e] * (1.f - ogv[e]);
           dcreg[e] = dc * fgv[e];
         }
-        float* dg = a.dgates + bt * 4 * H + j;
+        // only the bf16 mirror feeds the next step's contraction: store it first, the fp32 copy after the arrive
         bf16* dg16 = a.dgates16 + bt * 4 * H + j;
-        *reinterpret_cast<float4*>(dg) = make_float4(d0[0], d0[1], d0[2], d0[3]);
-        *reinterpret_cast<float4*>(dg + H) = make_float4(d1[0], d1[1], d1[2], d1[3]);
-        *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(d2[0], d2[1], d2[2], d2[3]);
-        *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(d3[0], d3[1], d3[2], d3[3]);
         st_bf16x4(dg16, d0[0], d0[1], d0[2], d0[3]);
         st_bf16x4(dg16 + H, d1[0], d1[1], d1[2], d1[3]);
         st_bf16x4(dg16 + 2 * H, d2[0], d2[1], d2[2], d2[3]);
         st_bf16x4(dg16 + 3 * H, d3[0], d3[1], d3[2], d3[3]);
       }
       if (threadIdx.x == 64) trace(i, 5);
-      epilogue_bar<512>();
+      epilogue_bar<BWD_LOADERS>();
       if (threadIdx.x == 64) trace(i, 6);
-      if (warp == 2 && lane == 0) {
-        __threadfence();
-        red_release_gpu_add(a.counters + rg, 1u);
-      }
+      // red.release.gpu is cumulative over the stores observed through the barrier: no separate fence
+      if (warp == 2 && lane == 0) red_release_gpu_add(a.counters + rg, 1u);
       if (threadIdx.x == 64) trace(i, 7);
+      if (valid) {
+        float* dg = a.dgates + bt * 4 * H + j;
+        *reinterpret_cast<float4*>(dg) = make_float4(d0[0], d0[1], d0[2], d0[3]);
+        *reinterpret_cast<float4*>(dg + H) = make_float4(d1[0], d1[1], d1[2], d1[3]);
+        *reinterpret_cast<float4*>(dg + 2 * H) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+        *reinterpret_cast<float4*>(dg + 3 * H) = make_float4(d3[0], d3[1], d3[2], d3[3]);
+      }
     }
     // after the last GEMM: dhrec = dgates_0 W_hh = dh0 ; dcreg = dc0
     if (valid) {
@@ -493,6 +565,13 @@ __global__ void transpose_whh_kernel(const float* __restrict__ w_hh, bf16* __res
 inline int seq_stages(size_t w_bytes) {
   if (w_bytes + 2 * A_STAGE_BYTES > SEQ_SMEM_BUDGET) return 0;
   size_t n = (SEQ_SMEM_BUDGET - w_bytes) / A_STAGE_BYTES;
+  return (int)(n > MAX_STAGES ? MAX_STAGES : n);
+}
+
+// backward: ring slots of one super-stage (SS_BYTES) next to the resident W_hh^T slice (works from 2)
+inline int bwd_slots(size_t w_bytes) {
+  if (w_bytes + 2 * SS_BYTES > SEQ_SMEM_BUDGET) return 0;
+  size_t n = (SEQ_SMEM_BUDGET - w_bytes) / SS_BYTES;
   return (int)(n > MAX_STAGES ? MAX_STAGES : n);
 }
 
@@ -540,7 +619,7 @@ bool lstm_seq_supported(int B, int H, int* units_fwd) {
   const int RG = ceil_div(B, 128);
   const int sms = num_sms();
   if ((H / 16) * RG > sms) return false;                         // backward: 16 units per CTA
-  if (seq_stages((size_t)(4 * H / 64) * 16 * 128) < 2) return false;
+  if (bwd_slots((size_t)(4 * H / 64) * 16 * 128) < 2) return false;
   for (int U : {4, 8, 16, 32}) {
     if (H % U) continue;
     if ((H / U) * RG <= sms && seq_stages((size_t)(H / 64) * 4 * U * 128) >= 2) {
@@ -569,24 +648,22 @@ int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
   transpose_whh_kernel<<<dim3(4 * H / 32, H / 32), dim3(32, 8), 0, st>>>(p.w_hh, p.whhT16, H);
   AA_CHECK_LAUNCH("transpose_whh");
   AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
-  CUtensorMap tmWT, tmG;
+  CUtensorMap tmWT;
   AA_TRY(make_map(&tmWT, p.whhT16, 2, H, 4LL * H, 4LL * H, 16));
-  const int box_rows = (p.B >= 128 ? 128 : (p.B + 7) / 8 * 8);
-  AA_TRY(make_map(&tmG, p.dgates16, 2, p.B, (long long)p.T * 4 * H, (long long)p.T * 4 * H, box_rows));
   SeqBwdArgs a{};
   a.B = p.B; a.T = p.T; a.H = H;
   a.dh_attn = p.dh_attn; a.dhs = p.dhs; a.dcell = p.dcell; a.d_hT = p.d_hT; a.d_cT = p.d_cT;
   a.acts = p.acts; a.cells = p.cells; a.c0 = p.c0; a.dgates = p.dgates; a.dgates16 = p.dgates16; a.dh0 = p.dh0; a.dc0 = p.dc0;
   a.counters = p.counters;
-  a.stages = seq_stages((size_t)KB * 16 * 128);
-  a.box_rows = box_rows;
-  const size_t smem = (size_t)a.stages * A_STAGE_BYTES + (size_t)KB * 16 * 128 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
+  a.stages = bwd_slots((size_t)KB * 16 * 128);
+  a.box_rows = 0;
+  const size_t smem = (size_t)a.stages * SS_BYTES + (size_t)KB * 16 * 128 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  void* args[] = {(void*)&tmWT, (void*)&tmG, (void*)&a};
+  void* args[] = {(void*)&tmWT, (void*)&a};
   AA_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lstm_seq_bwd_kernel, dim3(C, RG), dim3(BWD_THREADS), args, smem, st));
   count_launch();
   return AA_OK;

@@ -48,6 +48,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// One lane of a CONVERGED warp (the same lane every time for a full mask).  The MMA warp must run its loop converged and
+// issue under this predicate: with `if (lane == 0)` control flow the compiler cannot prove the tcgen05 operands uniform and
+// wraps every tcgen05.mma in an R2UR + ELECT + branch sequence that costs ~180 cycles per instruction (tools/mma_probe.cu:
+// 178.7 vs 103.2 cycles per MMA at N <= 128, 179 vs 128 at N = 256), i.e. the issue rate, not the tensor pipe, bounds it.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -126,7 +135,10 @@ __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes -> async-proxy (TMA / tcgen05) reads.  The unqualified form compiles to MEMBAR.ALL.CTA +
+// MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC: name the state space so that only the needed part is paid for.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
