@@ -220,6 +220,37 @@ def rooflines(report, models, peaks):
     return out
 
 
+_T0 = time.time()
+
+
+def stage(msg):
+    """Progress line on stderr (rank-tagged) and a re-armed watchdog: a stage that takes longer than AA_BENCH_STAGE_TIMEOUT
+    seconds (default 240) dumps every thread's Python stack and exits non-zero instead of hanging the launcher."""
+    import faulthandler
+
+    sys.stderr.write("[bench rank %s +%.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() - _T0, msg))
+    sys.stderr.flush()
+    faulthandler.cancel_dump_traceback_later()
+    faulthandler.dump_traceback_later(float(os.environ.get("AA_BENCH_STAGE_TIMEOUT", "240")), exit=True)
+
+
+def leave(world):
+    """End of a rank's run: flush what was printed, then (N > 1) leave without tearing NCCL down.
+    ``destroy_process_group()`` after CUDA-graph-captured collectives blocked forever on the 2-GPU box (every stage done, the
+    JSON line still in the stdout buffer); a finished benchmark process has nothing left to release that process exit does
+    not release, so the ranks synchronise their devices and exit 0 directly."""
+    import faulthandler
+
+    faulthandler.cancel_dump_traceback_later()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        import torch
+
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -235,7 +266,10 @@ def run_ours(args):
         raise RuntimeError("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    stage("init (world %d)" % world)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     peaks = load_peaks()
@@ -286,12 +320,14 @@ def run_ours(args):
         loss.backward()
         return loss
 
+    stage("first eager training step")
     # one eager step: counts the kernels of a step (graph replays bypass the library's launch counter)
     l0 = _lib.launch_count()
     train_step_eager(devb[0])
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - l0
 
+    stage("building the stepper (graph=%d)" % args.graph)
     dp_mode = None
     if world == 1:
         stepper = GraphedTrainStep(model, devb[0], lengths) if args.graph else None
@@ -327,9 +363,11 @@ def run_ours(args):
         def train_step(b):
             return stepper(b) if stepper is not None else dp_eager(b)
 
+    stage("training warm-up")
     for i in range(args.warmup):
         train_step(devb[i % NB])
     barrier()
+    stage("training timed region")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -345,6 +383,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     train_tok = TRAIN_B * TRAIN_T * n_gpus / (train_ms * 1e-3)
 
+    stage("training e2e")
     # e2e: pinned host -> device copies and the loss read-back inside the timed region
     def train_step_e2e(hb):
         if stepper is not None:
@@ -362,6 +401,7 @@ def run_ours(args):
     e2e_train_s = max_over_ranks((time.perf_counter() - t0)) / args.steps
     barrier()
 
+    stage("per-kernel timing pass")
     # per-kernel timing pass (CUDA events around the kernels, same steps; not used for `value`)
     _lib.profile_reset()
     _lib.profile_enable(True)
@@ -372,6 +412,7 @@ def run_ours(args):
     train_report = _lib.profile_report()
     _lib.profile_reset()
 
+    stage("decode")
     # ---------------- decode workload (BASELINE config 3) ----------------
     dsteps = max(2, min(args.steps, 5))
     dinp = make_inputs(dims, DECODE_B, 1, seed=4321 + rank)
@@ -410,11 +451,11 @@ def run_ours(args):
     dec_report = _lib.profile_report()
     _lib.profile_reset()
 
+    stage("report")
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world)
         return
 
     models = kernel_models(dims, TRAIN_B, TRAIN_T, DECODE_B)
@@ -458,8 +499,7 @@ def run_ours(args):
                                "sample": "%d full steps of the same workload (B=%d, T=%d) on the numpy oracle port, %.1f s" %
                                          (ncpu, TRAIN_B, TRAIN_T, sec * ncpu)}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    leave(world)
 
 
 def main():
