@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 
 namespace aa {
+extern int g_atten_sequential;
 
 static thread_local char g_err[512] = "";
 
@@ -345,6 +346,11 @@ static int atten_stage(const Ctx& c, const aa_dims& d, Mat Wv, Mat Wg, Mat Ws, c
 using namespace aa;
 
 extern "C" {
+
+int aa_debug_set_atten_sequential(int on) {
+  aa::g_atten_sequential = on ? 1 : 0;
+  return AA_OK;
+}
 
 int aa_version(void) { return 100; /* 0.1.0 */ }
 

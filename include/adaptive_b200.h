@@ -108,6 +108,8 @@ int aa_debug_set_trace_buffer(void* dev_ptr);
 /* Diagnostics: on != 0 makes the tensor-core decode pipeline use the register-staged attention kernel instead of the
  * bulk-copy (cp.async.bulk + mbarrier ring) one; both compute the same step (tests compare them). */
 int aa_debug_set_decode_atten_simple(int on);
+/* Diagnostics: on != 0 makes the training attention use the step-by-step kernels instead of the step-parallel ones. */
+int aa_debug_set_atten_sequential(int on);
 
 /* ---- stage operators (the nn.Module sub-blocks) ------------------------------------- */
 

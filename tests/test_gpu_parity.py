@@ -273,6 +273,41 @@ def test_decode_attention_pipeline_vs_simple_kernel_and_oracle(dims, B, beam, L)
         assert rel_err(bet.cpu().numpy()[same], r_bet[same]) < TOL
 
 
+@pytest.mark.parametrize("B,T,dims", [(80, 18, CFG_A), (3, 7, Dims(H=1024, E=64, Vc=300, k=196)), (150, 5, Dims(H=64, E=32, Vc=200, k=10)),
+                                      (5, 23, Dims(H=100, E=28, Vc=200, k=33, a=127)), (2, 45, Dims(H=36, E=20, Vc=100, k=3, a=8))])
+def test_step_parallel_attention_vs_sequential_kernels(B, T, dims):
+    """Training attention: the step-parallel kernels (one CTA per image, every phase over all steps) against the
+    step-by-step kernels they replace -- forward outputs and every gradient, fp32 path."""
+    from adaptive_b200 import _lib
+    lib = _lib.load()
+    w = make_weights(dims, seed=31, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=32)
+    rng = np.random.Generator(np.random.PCG64(3))
+    dS = torch.from_numpy((rng.standard_normal((B, T, dims.Vc)) / dims.Vc).astype(np.float32)).cuda()
+
+    def run():
+        W = dev_weights(w, requires_grad=True)
+        V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+        scores, alpha, beta, hT, cT = F_aa.decoder_forward(W, V, v_g, cap, h0, c0)
+        (scores * dS).sum().backward()
+        torch.cuda.synchronize()
+        outs = {"scores": scores, "alpha": alpha, "beta": beta}
+        for key, t in zip(grad_key_order(), W):
+            outs["d" + key] = t.grad
+        for key, t in (("V", V), ("v_g", v_g), ("h0", h0), ("c0", c0)):
+            outs["d" + key] = t.grad
+        return {k: v.detach().cpu().numpy() for k, v in outs.items()}
+
+    new = run()
+    try:
+        lib.aa_debug_set_atten_sequential(1)
+        old = run()
+    finally:
+        lib.aa_debug_set_atten_sequential(0)
+    bad = {k: rel_err(new[k], old[k]) for k in new if not rel_err(new[k], old[k]) < 2e-5}
+    assert not bad, bad
+
+
 def test_pack_and_cross_entropy_vs_golden():
     for case in ("tiny", "odd"):
         g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
