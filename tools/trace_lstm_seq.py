@@ -18,6 +18,8 @@ W = dev_weights(w, requires_grad=True)
 V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
 lib = _lib.load()
 names = ["bar_passed", "tma_issued", "stage0_landed", "mma_commit", "acc_seen", "cell_done", "warps_met", "published"]
+# (cluster kernels: 0 step start, 1 MMAs issued, 2 accumulator seen, 3 cell math done, 4 barrier "MMAs done" passed,
+#  5 slice delivered + arrive, 6 outputs stored)
 for it in range(3):
     buf = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
     _lib.check(lib.aa_debug_set_trace_buffer(F_aa._ptr(buf)), "trace")
