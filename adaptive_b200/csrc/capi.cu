@@ -347,6 +347,8 @@ using namespace aa;
 
 extern "C" {
 
+int aa_debug_set_bptt_ksplit(int ks) { return aa::set_bptt_ksplit_max(ks); }
+
 int aa_debug_set_atten_sequential(int on) {
   aa::g_atten_sequential = on ? 1 : 0;
   return AA_OK;

@@ -116,7 +116,8 @@ struct LstmSeqBwd {
   unsigned* counters;
 };
 int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t s);
-int set_seq_trace_buffer(void* dev_ptr);   // diagnostics: [steps][8] uint64 globaltimer stamps of CTA (0,0); null = off
+int set_seq_trace_buffer(void* dev_ptr);
+int set_bptt_ksplit_max(int ks);   // diagnostics: cap on the K-split (cluster size) of the BPTT kernel; 1 = no cluster   // diagnostics: [steps][8] uint64 globaltimer stamps of CTA (0,0); null = off
 
 // ---- atten.cu --------------------------------------------------------------------------
 struct AttenFwdArgs {

@@ -317,37 +317,86 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- cluster helpers (K-split of the backward contraction) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// release-arrive (cluster scope) on an mbarrier that lives in a peer CTA's shared memory
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire: the data guarded by the barrier was written by peer CTAs
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > AA_SPIN_LIMIT_CYCLES) __trap();
+    }
+  } while (!done);
+}
+
+// KS = K-split: a cluster of KS CTAs shares one 16-unit output slice, CTA rank kq contracts the K range
+// [kq*4H/KS, (kq+1)*4H/KS) (its own quarter of dgates_t and of the W_hh^T slice), the fp32 partials are exchanged through
+// distributed shared memory (one 16-byte store per thread to the CTA that owns the thread's 4 units, completion counted
+// by an mbarrier in the owner) and rank r finishes the units of column groups cg % KS == r.  A tcgen05.mma with M = 128
+// operands from shared memory costs ~103 cycles whatever N is (tools/mma_probe.cu), so the 4H/16 k-steps of this
+// contraction bound the step; the split divides them (and the operand bytes each CTA pulls from L2) by KS.
+template <int KS>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a) {
   constexpr int U = 16, N = 16, NACC = 8, TCOLS = N * NACC;   // NACC partial accumulators: see lstm_seq_fwd_kernel
   constexpr uint32_t W_KB_BYTES = N * 128;
-  const int KB = 4 * a.H / 64;
-  const int NSS = KB / SS_KB;                 // super-stages per step (KB is a multiple of 4)
-  const int C = gridDim.x;
+  const int KB = 4 * a.H / 64 / KS;           // k-blocks of this CTA's K range
+  const int NSS = KB / SS_KB;                 // super-stages per step
+  const int CT = gridDim.x;                   // CTAs per row group (all of them publish every step)
   const int NSLOT = a.stages;                 // ring slots of SS_BYTES
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS/STS)
   uint8_t* sA = smem;
   uint8_t* sW = smem + (size_t)NSLOT * SS_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)KB * W_KB_BYTES);
+  float* recv = reinterpret_cast<float*>(sW + (size_t)KB * W_KB_BYTES);          // [KS src][4 cg][128 rows][4] fp32 partials from the peers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(recv) + (KS > 1 ? (size_t)KS * 4 * 128 * 16 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* w_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_full = w_full + 1;
   uint64_t* tmem_empty = w_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 3);
+  uint64_t* recv_bar = w_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x, rg = blockIdx.y;
+  const int kq = KS > 1 ? (int)cluster_ctarank() : 0;
+  const int c = blockIdx.x / KS, rg = blockIdx.y;
   const int m0 = rg * 128;
   const int T = a.T, H = a.H;
+  const int kcol0 = kq * (4 * H / KS);        // first gate column of this CTA's K range
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&full_bar[s], BWD_LOADERS); mbar_init(&empty_bar[s], 1); }
     mbar_init(w_full, 1);
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 16);
+    mbar_init(recv_bar, KS > 1 ? (KS - 1) * (4 / KS) * 4 : 1);   // one arrive per sending warp: (KS-1) peers x owned column groups x 4 lane quarters
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -361,9 +410,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
 
   // GEMM i (i = 1..T) consumes dgates of step t = T - i and produces dh_rec for step t - 1 (dh0 when t == 0).
   if (warp == 0) {
-    if (lane == 0) {   // resident weight slice: rows [c*U, (c+1)*U) of W_hh^T, all k-blocks
+    if (lane == 0) {   // resident weight slice: rows [c*U, (c+1)*U) of W_hh^T, this CTA's k-blocks
       mbar_expect_tx(w_full, (uint32_t)KB * W_KB_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + (size_t)kb * W_KB_BYTES, &tmWT, kb * 64, c * U, w_full);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + (size_t)kb * W_KB_BYTES, &tmWT, kcol0 + kb * 64, c * U, w_full);
     }
   } else if (warp == 1) {
     {   // the MMA warp stays converged; one elected lane issues (see tc::elect_one)
@@ -403,8 +452,10 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
     }
   } else {
     const int q = warp & 3;
-    const int cg = (warp - 2) >> 2;            // column group: units cg*4 .. cg*4+3 of this CTA's 16
-    const int row = m0 + q * 32 + lane;
+    const int cg = (warp - 2) >> 2;            // column group: units cg*4 .. cg*4+3 of this slice's 16
+    const bool owner = (cg % KS) == kq;        // this CTA finishes these 4 units (cell gradient, stores)
+    const int rloc = q * 32 + lane;
+    const int row = m0 + rloc;
     const bool valid = row < a.B;
     const int j = c * U + cg * 4;              // first of this thread's 4 hidden units
     // ---- loader role: this thread's 16-byte chunks of a super-stage (fixed for the whole kernel) ----
@@ -422,12 +473,18 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
       ld_dst[m] = (uint32_t)(kl * A_STAGE_BYTES + r * 128 + ((ch ^ (r & 7)) << 4));
     }
     const uint32_t sA_u32 = smem_u32(sA);
+    // where this thread's partial goes when another CTA owns its units: recv[src = kq][cg][rloc] in CTA (cg % KS)
+    uint32_t send_addr = 0, send_bar = 0;
+    if (KS > 1 && !owner) {
+      send_addr = mapa_u32(smem_u32(recv) + (uint32_t)(((kq * 4 + cg) * 128 + rloc) * 16), (uint32_t)(cg % KS));
+      send_bar = mapa_u32(smem_u32(recv_bar), (uint32_t)(cg % KS));
+    }
     int it_issue = 0;                          // super-stages issued so far (all steps)
     float dcreg[4], dhrec[4];                  // dc / dh flowing from step t+1 into step t
     {
       float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 c4 = (valid && a.d_cT) ? *reinterpret_cast<const float4*>(a.d_cT + (long long)row * H + j) : z;
-      const float4 h4 = (valid && a.d_hT) ? *reinterpret_cast<const float4*>(a.d_hT + (long long)row * H + j) : z;
+      const float4 c4 = (owner && valid && a.d_cT) ? *reinterpret_cast<const float4*>(a.d_cT + (long long)row * H + j) : z;
+      const float4 h4 = (owner && valid && a.d_hT) ? *reinterpret_cast<const float4*>(a.d_hT + (long long)row * H + j) : z;
       dcreg[0] = c4.x; dcreg[1] = c4.y; dcreg[2] = c4.z; dcreg[3] = c4.w;
       dhrec[0] = h4.x; dhrec[1] = h4.y; dhrec[2] = h4.z; dhrec[3] = h4.w;
     }
@@ -437,7 +494,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
       float4 dha, dhs4, dcl, ig4, fg4, gg4, og4, ce4, cp4;
       dha = dhs4 = dcl = ig4 = fg4 = gg4 = og4 = ce4 = cp4 = make_float4(0.f, 0.f, 0.f, 0.f);
       const long long bt = (long long)row * T + (t < 0 ? 0 : t);
-      if (valid && t >= 0) {
+      if (owner && valid && t >= 0) {
         dha = *reinterpret_cast<const float4*>(a.dh_attn + bt * H + j);
         if (a.dhs && t + 1 < T) dhs4 = *reinterpret_cast<const float4*>(a.dhs + (bt + 1) * H + j);
         dcl = *reinterpret_cast<const float4*>(a.dcell + bt * H + j);
@@ -451,13 +508,13 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
         else if (a.c0) cp4 = *reinterpret_cast<const float4*>(a.c0 + (long long)row * H + j);
       }
       if (i >= 1) {
-        // ---- feed GEMM i: dgates of step T - i, complete in this row group once the counter says so ----
+        // ---- feed GEMM i: this CTA's K range of dgates of step T - i, complete once the counter says so ----
         if (threadIdx.x == 64) {
-          grid_barrier_wait(a.counters + rg, (unsigned)i * C);
+          grid_barrier_wait(a.counters + rg, (unsigned)i * CT);
           trace(i, 0);
         }
         epilogue_bar<BWD_LOADERS>();
-        const __nv_bfloat16* src0 = a.dgates16 + (long long)(T - i) * 4 * H;
+        const __nv_bfloat16* src0 = a.dgates16 + (long long)(T - i) * 4 * H + kcol0;
         for (int ss = 0; ss < NSS; ++ss, ++it_issue) {
           const int s = it_issue % NSLOT;
           mbar_wait(&empty_bar[s], ((it_issue / NSLOT) & 1) ^ 1);
@@ -481,17 +538,36 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty);
+        float part[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float acc = __uint_as_float(r[0][u]);
 #pragma unroll
           for (int ai = 1; ai < NACC; ++ai) acc += __uint_as_float(r[ai][u]);
-          dhrec[u] = acc;
+          part[u] = acc;
         }
+        if (KS > 1) {
+          if (!owner) {        // hand the partial to the CTA that owns these units
+            st_cluster_f4(send_addr, part[0], part[1], part[2], part[3]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(send_bar);
+          } else {             // gather the peers' partials of this thread's units
+            mbar_wait_cluster(recv_bar, (i - 1) & 1);
+#pragma unroll
+            for (int src = 0; src < KS; ++src) {
+              if (src != kq) {
+                const float4 o = *reinterpret_cast<const float4*>(recv + ((src * 4 + cg) * 128 + rloc) * 4);
+                part[0] += o.x; part[1] += o.y; part[2] += o.z; part[3] += o.w;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dhrec[u] = part[u];
       }
       if (t < 0) break;
       float d0[4], d1[4], d2[4], d3[4];
-      if (valid) {
+      if (owner && valid) {
         const float dhav[4] = {dha.x + dhs4.x, dha.y + dhs4.y, dha.z + dhs4.z, dha.w + dhs4.w};
         const float dclv[4] = {dcl.x, dcl.y, dcl.z, dcl.w};
         const float igv[4] = {ig4.x, ig4.y, ig4.z, ig4.w}, fgv[4] = {fg4.x, fg4.y, fg4.z, fg4.w};
@@ -521,7 +597,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
       // red.release.gpu is cumulative over the stores observed through the barrier: no separate fence
       if (warp == 2 && lane == 0) red_release_gpu_add(a.counters + rg, 1u);
       if (threadIdx.x == 64) trace(i, 7);
-      if (valid) {
+      if (owner && valid) {
         float* dg = a.dgates + bt * 4 * H + j;
         *reinterpret_cast<float4*>(dg) = make_float4(d0[0], d0[1], d0[2], d0[3]);
         *reinterpret_cast<float4*>(dg + H) = make_float4(d1[0], d1[1], d1[2], d1[3]);
@@ -530,7 +606,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
       }
     }
     // after the last GEMM: dhrec = dgates_0 W_hh = dh0 ; dcreg = dc0
-    if (valid) {
+    if (owner && valid) {
       if (a.dh0) *reinterpret_cast<float4*>(a.dh0 + (long long)row * H + j) = make_float4(dhrec[0], dhrec[1], dhrec[2], dhrec[3]);
       if (a.dc0) *reinterpret_cast<float4*>(a.dc0 + (long long)row * H + j) = make_float4(dcreg[0], dcreg[1], dcreg[2], dcreg[3]);
     }
@@ -540,6 +616,9 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const SeqBwdArgs a
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TCOLS) : "memory");
+  }
+  if (KS > 1) {   // no CTA of the cluster may exit while a peer could still address its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
@@ -642,12 +721,9 @@ int launch_lstm_seq_fwd(const LstmSeqFwd& p, cudaStream_t st) {
   }
 }
 
-int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
-  AA_REQUIRE(lstm_seq_supported(p.B, p.H, nullptr), "lstm_seq_bwd: unsupported shape B=%d H=%d", p.B, p.H);
-  const int H = p.H, KB = 4 * H / 64, C = H / 16, RG = ceil_div(p.B, 128);
-  transpose_whh_kernel<<<dim3(4 * H / 32, H / 32), dim3(32, 8), 0, st>>>(p.w_hh, p.whhT16, H);
-  AA_CHECK_LAUNCH("transpose_whh");
-  AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
+template <int KS>
+int launch_bwd_ks(const LstmSeqBwd& p, cudaStream_t st) {
+  const int H = p.H, KB = 4 * H / 64 / KS, C = H / 16, RG = ceil_div(p.B, 128);
   CUtensorMap tmWT;
   AA_TRY(make_map(&tmWT, p.whhT16, 2, H, 4LL * H, 4LL * H, 16));
   SeqBwdArgs a{};
@@ -655,17 +731,66 @@ int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
   a.dh_attn = p.dh_attn; a.dhs = p.dhs; a.dcell = p.dcell; a.d_hT = p.d_hT; a.d_cT = p.d_cT;
   a.acts = p.acts; a.cells = p.cells; a.c0 = p.c0; a.dgates = p.dgates; a.dgates16 = p.dgates16; a.dh0 = p.dh0; a.dc0 = p.dc0;
   a.counters = p.counters;
-  a.stages = bwd_slots((size_t)KB * 16 * 128);
+  const size_t fixed = (size_t)KB * 16 * 128 + (KS > 1 ? (size_t)KS * 4 * 128 * 16 : 0);
+  a.stages = bwd_slots(fixed);
+  if (a.stages > KB / SS_KB * 2) a.stages = KB / SS_KB * 2 > 2 ? KB / SS_KB * 2 : 2;   // no point in more than two steps' worth of slots
   a.box_rows = 0;
-  const size_t smem = (size_t)a.stages * SS_BYTES + (size_t)KB * 16 * 128 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)a.stages * SS_BYTES + fixed + (2 * MAX_STAGES + 5) * 8 + 16 + 1024;
+  auto kern = lstm_seq_bwd_kernel<KS>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    AA_CHECK_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   void* args[] = {(void*)&tmWT, (void*)&a};
-  AA_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)lstm_seq_bwd_kernel, dim3(C, RG), dim3(BWD_THREADS), args, smem, st));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(C * KS, RG);
+  cfg.blockDim = dim3(BWD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;      // the grid barrier needs every CTA resident
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = KS;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = KS > 1 ? 2 : 1;
+  AA_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kern, args));
   count_launch();
+  return AA_OK;
+}
+
+// K-split of the backward contraction (cluster size): as wide as the chip and the shape allow
+int bwd_ksplit(int B, int H) {
+  const int C = H / 16, RG = ceil_div(B, 128), sms = num_sms();
+  for (int ks : {4, 2}) {
+    if ((4 * H / 64) % (ks * SS_KB) != 0) continue;
+    if (C * ks * RG > sms) continue;
+    const size_t fixed = (size_t)(4 * H / 64 / ks) * 16 * 128 + (size_t)ks * 4 * 128 * 16;
+    if (bwd_slots(fixed) >= 2) return ks;
+  }
+  return 1;
+}
+
+int g_bwd_ksplit_max = 4;   // diagnostics (aa_debug_set_bptt_ksplit): cap on the K-split
+
+int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
+  AA_REQUIRE(lstm_seq_supported(p.B, p.H, nullptr), "lstm_seq_bwd: unsupported shape B=%d H=%d", p.B, p.H);
+  const int H = p.H, RG = ceil_div(p.B, 128);
+  transpose_whh_kernel<<<dim3(4 * H / 32, H / 32), dim3(32, 8), 0, st>>>(p.w_hh, p.whhT16, H);
+  AA_CHECK_LAUNCH("transpose_whh");
+  AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
+  int ks = bwd_ksplit(p.B, H);
+  if (ks > g_bwd_ksplit_max) ks = g_bwd_ksplit_max;
+  if (ks == 4) return launch_bwd_ks<4>(p, st);
+  if (ks == 2) return launch_bwd_ks<2>(p, st);
+  return launch_bwd_ks<1>(p, st);
+}
+
+int set_bptt_ksplit_max(int ks) {
+  g_bwd_ksplit_max = ks < 1 ? 1 : ks;
   return AA_OK;
 }
 

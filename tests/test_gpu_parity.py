@@ -308,6 +308,38 @@ def test_step_parallel_attention_vs_sequential_kernels(B, T, dims):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("B,T,dims", [(80, 18, CFG_A), (130, 4, Dims(H=128, E=64, Vc=304, k=49)), (9, 6, Dims(H=256, E=64, Vc=304, k=20))])
+def test_bptt_cluster_ksplit_matches_single_cta(B, T, dims):
+    """Persistent BPTT kernel: the K-split over a thread-block cluster (partials exchanged through distributed shared
+    memory) against the same kernel without the split -- identical bf16 operands, only the fp32 summation order differs."""
+    from adaptive_b200 import _lib
+    lib = _lib.load()
+    w = make_weights(dims, seed=41, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=42)
+    rng = np.random.Generator(np.random.PCG64(4))
+    dS = torch.from_numpy((rng.standard_normal((B, T, dims.Vc)) / dims.Vc).astype(np.float32)).cuda()
+
+    def run():
+        W = dev_weights(w, requires_grad=True)
+        V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+        scores = F_aa.decoder_forward(W, V, v_g, cap, h0, c0, precision="bf16")[0]
+        (scores * dS).sum().backward()
+        torch.cuda.synchronize()
+        outs = {"d" + key: t.grad for key, t in zip(grad_key_order(), W)}
+        outs.update({"dh0": h0.grad, "dc0": c0.grad, "dv_g": v_g.grad})
+        return {k: v.detach().cpu().numpy() for k, v in outs.items()}
+
+    split = run()
+    try:
+        lib.aa_debug_set_bptt_ksplit(1)
+        single = run()
+    finally:
+        lib.aa_debug_set_bptt_ksplit(4)
+    # bf16 rounding of dgates amplifies last-bit differences of the fp32 partial sums: 1e-3 of the largest entry
+    bad = {k: rel_err(split[k], single[k]) for k in split if not rel_err(split[k], single[k]) < 1e-3}
+    assert not bad, bad
+
+
 def test_pack_and_cross_entropy_vs_golden():
     for case in ("tiny", "odd"):
         g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
