@@ -84,6 +84,9 @@ SIGNATURES = {
                                     c_size_t, P]),
     "aa_decoder_backward_hooked": (c_int, [_D, _W, P, P, P, P, P, P, P, P, c_size_t, P, P, P, P, P, _G, P, P, P, P, P,
                                            c_size_t, P, POINTER(c_void_p), c_void_p, c_void_p]),
+    "aa_decoder_forward_packed": (c_int, [_D, _W, P, P, P, P, P, P, c_int64, P, P, P, P, P, P, c_size_t, P]),
+    "aa_decoder_backward_packed": (c_int, [_D, _W, P, P, P, P, P, P, P, P, c_size_t, P, c_int64, P, P, P, P, P, _G, P, P, P, P, P,
+                                           c_size_t, P, POINTER(c_void_p), c_void_p, c_void_p]),
     "aa_pack_rows": (c_int, [P, c_int64, P, c_int64, P, P]),
     "aa_unpack_rows": (c_int, [P, c_int64, P, c_int64, c_int64, P, P]),
     "aa_cross_entropy": (c_int, [P, c_int64, c_int64, P, P, P, P]),

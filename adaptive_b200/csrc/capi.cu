@@ -156,8 +156,9 @@ struct W16 {
 
 struct Saved {
   float *x, *xg, *acts, *cells, *hiddens, *hs_prev, *g, *s, *P, *q, *r, *ctx, *u, *zeros;
+  float* up;      // rows of u in packed order (packed entry points only)
   // bf16 mirrors (only carved when d.precision == AA_PREC_BF16)
-  bf16 *x16, *hid16, *hsprev16, *s16, *V16, *u16, *h016, *whh_pack16;
+  bf16 *x16, *hid16, *hsprev16, *s16, *V16, *u16, *h016, *whh_pack16, *up16;
   unsigned* counters;
   W16 w16;
   size_t bytes;
@@ -181,8 +182,10 @@ Saved carve_saved(const aa_dims& d, void* base) {
   s.ctx = c.take(N * H);
   s.u = c.take(N * H);
   s.zeros = c.take((size_t)d.B * H);
+  s.up = c.take(N * H);
   if (d.precision == AA_PREC_BF16) {
     Carver16 h{c};
+    s.up16 = h.take(N * H);
     s.x16 = h.take(N * 2 * E);
     s.hid16 = h.take(N * H);
     s.hsprev16 = h.take(N * H);
@@ -206,6 +209,7 @@ Saved carve_saved(const aa_dims& d, void* base) {
 }
 
 struct BwdScratch {
+  float* dup;     // du rows in packed order (packed entry points only)
   float *du, *ds, *dq, *dr, *dP, *da, *dcell, *dhs, *dgates, *dx, *dh_rec, *dc_rec, *dV;
   bf16 *dS16, *dq16, *dr16, *dP16, *da16, *dgates16, *whhT16;
   unsigned* counters;
@@ -229,6 +233,7 @@ BwdScratch carve_bwd(const aa_dims& d, void* base) {
   s.dh_rec = c.take((size_t)d.B * H);
   s.dc_rec = c.take((size_t)d.B * H);
   s.dV = c.take((size_t)d.B * d.k * H);
+  s.dup = c.take(N * H);
   if (d.precision == AA_PREC_BF16) {
     Carver16 h{c};
     const size_t ap = a_pad_of(d);
@@ -308,6 +313,16 @@ int check_dims(const aa_dims* d, bool need_T) {
     AA_REQUIRE(d->H % 8 == 0 && d->E % 8 == 0 && d->Vc % 8 == 0,
                "bf16 mode needs H, E and Vc to be multiples of 8 (16-byte bf16 rows for TMA); got H=%d E=%d Vc=%d", d->H, d->E, d->Vc);
   return AA_OK;
+}
+
+// dst[r, :] = src[row_index[r], :] (fp32 and, optionally, the bf16 mirror in the same launch); cols % 4 == 0
+__global__ void gather_rows2_kernel(const float* __restrict__ src, const bf16* __restrict__ src16, const long long* __restrict__ row_index,
+                                    int cols, float* __restrict__ dst, bf16* __restrict__ dst16) {
+  const long long r = blockIdx.x, sr = row_index[r];
+  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+    *reinterpret_cast<float4*>(dst + r * cols + c) = *reinterpret_cast<const float4*>(src + sr * cols + c);
+    if (src16) *reinterpret_cast<uint2*>(dst16 + r * cols + c) = *reinterpret_cast<const uint2*>(src16 + sr * cols + c);
+  }
 }
 
 __global__ void pack_rows_kernel(const float* __restrict__ src, long long n_cols, const long long* __restrict__ row_index,
@@ -530,9 +545,9 @@ int aa_adaptive_forward(const aa_dims* d, const aa_weights* w, const float* x, c
 size_t aa_decoder_saved_bytes(const aa_dims* d) { return d ? carve_saved(*d, nullptr).bytes : 0; }
 size_t aa_decoder_bwd_scratch_bytes(const aa_dims* d) { return d ? carve_bwd(*d, nullptr).bytes : 0; }
 
-int aa_decoder_forward(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
-                       const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
-                       void* saved, size_t saved_bytes, void* stream) {
+static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                                const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
+                                void* saved, size_t saved_bytes, void* stream, const int64_t* row_index, int64_t n_rows) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && scores && alpha && beta, "aa_decoder_forward: null pointer");
   if (d->B == 0) return AA_OK;
@@ -608,8 +623,31 @@ int aa_decoder_forward(const aa_dims* d, const aa_weights* w, const float* V, co
   // attention + vocabulary projection                          adaptive_attention.py:128-132
   AA_TRY(atten_stage(cx, *d, Wv, Wg, Ws, w->att_wh, M2(V, H, sv.V16, H), M2(sv.hiddens, H, sv.hid16, H), M2(sv.s, H, sv.s16, H), sv.P,
                      sv.q, sv.r, nullptr, sv.ctx, sv.u, sv.u16, alpha, beta));
+  if (row_index) {   // only the rows pack_padded_sequence keeps, already in packed order (baseline_attention.py:228, Q13)
+    if (n_rows == 0) return AA_OK;
+    gather_rows2_kernel<<<(unsigned)n_rows, 128, 0, st>>>(sv.u, tc ? sv.u16 : nullptr, reinterpret_cast<const long long*>(row_index), H,
+                                                          sv.up, tc ? sv.up16 : nullptr);
+    AA_CHECK_LAUNCH("gather_rows2");
+    AA_TRY(mm_nt(cx, "gemm_vocab_fwd", (int)n_rows, d->Vc, H, M2(sv.up, H, sv.up16, H), Wp, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr));
+    return AA_OK;
+  }
   AA_TRY(mm_nt(cx, "gemm_vocab_fwd", N, d->Vc, H, M2(sv.u, H, sv.u16, H), Wp, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr));
   return AA_OK;
+}
+
+int aa_decoder_forward(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                       const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
+                       void* saved, size_t saved_bytes, void* stream) {
+  return decoder_forward_impl(d, w, V, v_g, captions, h0, c0, scores, alpha, beta, hT, cT, saved, saved_bytes, stream, nullptr, 0);
+}
+
+int aa_decoder_forward_packed(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                              const float* h0, const float* c0, const int64_t* row_index, int64_t n_rows, float* scores_packed,
+                              float* alpha, float* beta, float* hT, float* cT, void* saved, size_t saved_bytes, void* stream) {
+  AA_REQUIRE(row_index && d && n_rows >= 0 && n_rows <= (int64_t)d->B * d->T, "aa_decoder_forward_packed: bad row index / count");
+  AA_REQUIRE(d->H % 4 == 0, "aa_decoder_forward_packed: H must be a multiple of 4");
+  return decoder_forward_impl(d, w, V, v_g, captions, h0, c0, scores_packed, alpha, beta, hT, cT, saved, saved_bytes, stream, row_index,
+                              n_rows);
 }
 
 static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
@@ -617,7 +655,7 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
                                  size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
                                  const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
                                  float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
-                                 aa_grad_ready_fn on_ready, void* user) {
+                                 aa_grad_ready_fn on_ready, void* user, const int64_t* row_index = nullptr, int64_t n_rows = 0) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && alpha && beta && d_scores && gw, "aa_decoder_backward: null pointer");
   AA_REQUIRE(gw->embed && gw->w_ih && gw->w_hh && gw->b_ih && gw->b_hh && gw->sen_wx && gw->sen_wh && gw->att_wv &&
@@ -666,14 +704,27 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
   const Mat Wp = M2(w->mlp_w, H, h.mlp_w, H);
   const Mat X = M2(sv.x, 2 * E, sv.x16, 2 * E);
   // db_p = column sums of dS, fused with the bf16 cast of dS                     adaptive_attention.py:132
-  AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, N, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
+  // (packed entry point: d_scores holds the NR = n_rows packed rows only; the other positions have no gradient)
+  const int NR = row_index ? (int)n_rows : N;
+  if (NR > 0) AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
+  else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_b, 0, sizeof(float) * Vc, st));
   const Mat dS = M2(d_scores, Vc, sc.dS16, Vc);
 
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
   AA_TRY(to_side());
-  AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, N, dS, M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
+  if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
+  else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
   AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));
-  AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, nullptr, 0));
+  if (row_index) {   // du rows of the packed positions, scattered back to [B,T,H] (zero elsewhere)
+    AA_CHECK_CUDA(cudaMemsetAsync(sc.du, 0, sizeof(float) * (size_t)N * H, st));
+    if (NR > 0) {
+      AA_TRY(mm_nn(cx, "gemm_vocab_dx", NR, H, Vc, dS, Wp, sc.dup, H, nullptr, 0));
+      pack_rows_kernel<<<(unsigned)NR, 128, 0, st>>>(sc.dup, H, reinterpret_cast<const long long*>(row_index), sc.du, 0);
+      AA_CHECK_LAUNCH("scatter_rows");
+    }
+  } else {
+    AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, nullptr, 0));
+  }
   // attention                                                   adaptive_attention.py:34-56
   AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, st));
   AttenBwdArgs ab{};
@@ -772,6 +823,18 @@ int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const floa
                                aa_grad_ready_fn on_ready, void* user) {
   return decoder_backward_impl(d, w, V, v_g, captions, h0, c0, alpha, beta, saved, saved_bytes, d_scores, d_alpha, d_beta, d_hT,
                                d_cT, gw, dV, dv_g, dh0, dc0, scratch, scratch_bytes, stream, ready_events, on_ready, user);
+}
+
+int aa_decoder_backward_packed(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                               const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
+                               size_t saved_bytes, const int64_t* row_index, int64_t n_rows, const float* d_scores_packed,
+                               const float* d_alpha, const float* d_beta, const float* d_hT, const float* d_cT,
+                               const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0, float* dc0, void* scratch,
+                               size_t scratch_bytes, void* stream, void* const* ready_events, aa_grad_ready_fn on_ready, void* user) {
+  AA_REQUIRE(row_index && d && n_rows >= 0 && n_rows <= (int64_t)d->B * d->T, "aa_decoder_backward_packed: bad row index / count");
+  return decoder_backward_impl(d, w, V, v_g, captions, h0, c0, alpha, beta, saved, saved_bytes, d_scores_packed, d_alpha, d_beta, d_hT,
+                               d_cT, gw, dV, dv_g, dh0, dc0, scratch, scratch_bytes, stream, ready_events, on_ready, user, row_index,
+                               n_rows);
 }
 
 int aa_pack_rows(const float* scores, int64_t n_cols, const int64_t* row_index, int64_t n_rows, float* packed, void* stream) {

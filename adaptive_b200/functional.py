@@ -166,6 +166,90 @@ def decoder_forward(w: Sequence[torch.Tensor], V, v_g, captions, h0=None, c0=Non
     return _DecoderFn.apply(PRECISIONS[precision], V, v_g, captions, h0, c0, *w)
 
 
+class _DecoderPackedFn(torch.autograd.Function):
+    """``Encoder2Decoder.forward`` body (baseline_attention.py:219-230): ``Decoder.forward`` followed by
+    ``pack_padded_sequence(scores, lengths, batch_first=True).data``, with the vocabulary projection computed for the packed
+    rows only (the reference computes all B*T rows and drops the rest, Q13) -- same values, same order."""
+
+    @staticmethod
+    def forward(ctx, prec, V, v_g, captions, h0, c0, row_index, *w):
+        lib = _lib.load()
+        B, k, H = V.shape
+        T = captions.shape[1]
+        E = v_g.shape[1]
+        Vc = w[0].shape[0]
+        a = w[7].shape[0]
+        _check_weights(w, H, E, Vc, a)
+        dev = V.device
+        n = row_index.numel()
+        d = make_dims(B, T, k, H, E, Vc, a, prec)
+        packed = torch.empty(n, Vc, device=dev, dtype=torch.float32)
+        alpha = torch.empty(B, T, k, device=dev, dtype=torch.float32)
+        beta = torch.empty(B, T, 1, device=dev, dtype=torch.float32)
+        hT = torch.empty(B, H, device=dev, dtype=torch.float32)
+        cT = torch.empty(B, H, device=dev, dtype=torch.float32)
+        nbytes = lib.aa_decoder_saved_bytes(ctypes.byref(d))
+        saved = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        ws = weights_struct(w)
+        with torch.cuda.device(dev):
+            check(lib.aa_decoder_forward_packed(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(captions), _ptr(h0),
+                                                _ptr(c0), _ptr(row_index), n, _ptr(packed), _ptr(alpha), _ptr(beta), _ptr(hT), _ptr(cT),
+                                                _ptr(saved), nbytes, _stream(dev)), "aa_decoder_forward_packed")
+        ctx.dims = (B, T, k, H, E, Vc, a, prec)
+        ctx.has_state = (h0 is not None, c0 is not None)
+        ctx.save_for_backward(V, v_g, captions, h0 if h0 is not None else V.new_empty(0),
+                              c0 if c0 is not None else V.new_empty(0), alpha, beta, saved, row_index, *w)
+        ctx.set_materialize_grads(False)
+        return packed, alpha, beta, hT, cT
+
+    @staticmethod
+    def backward(ctx, d_packed, d_alpha, d_beta, d_hT, d_cT):
+        lib = _lib.load()
+        V, v_g, captions, h0, c0, alpha, beta, saved, row_index = ctx.saved_tensors[:9]
+        w = ctx.saved_tensors[9:]
+        B, T, k, H, E, Vc, a, prec = ctx.dims
+        h0 = h0 if ctx.has_state[0] else None
+        c0 = c0 if ctx.has_state[1] else None
+        dev = V.device
+        n = row_index.numel()
+        d = make_dims(B, T, k, H, E, Vc, a, prec)
+        if d_packed is None:
+            d_packed = torch.zeros(n, Vc, device=dev, dtype=torch.float32)
+        d_packed, d_alpha, d_beta, d_hT, d_cT = (_f32c(x) for x in (d_packed, d_alpha, d_beta, d_hT, d_cT))
+        grads = [torch.empty_like(t) for t in w]
+        gs = AAWeightGrads()
+        for name, t in zip(WEIGHT_FIELDS, grads):
+            setattr(gs, name, t.data_ptr())
+        dV = torch.empty_like(V)
+        dvg = torch.empty_like(v_g)
+        dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if h0 is not None else None
+        dc0 = torch.empty(B, H, device=dev, dtype=torch.float32) if c0 is not None else None
+        sbytes = lib.aa_decoder_bwd_scratch_bytes(ctypes.byref(d))
+        scratch = torch.empty(sbytes, device=dev, dtype=torch.uint8)
+        ws = weights_struct(w)
+        with torch.cuda.device(dev):
+            check(lib.aa_decoder_backward_packed(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(captions), _ptr(h0),
+                                                 _ptr(c0), _ptr(alpha), _ptr(beta), _ptr(saved), saved.numel(), _ptr(row_index), n,
+                                                 _ptr(d_packed), _ptr(d_alpha), _ptr(d_beta), _ptr(d_hT), _ptr(d_cT), ctypes.byref(gs),
+                                                 _ptr(dV), _ptr(dvg), _ptr(dh0), _ptr(dc0), _ptr(scratch), sbytes, _stream(dev), None, None,
+                                                 None), "aa_decoder_backward_packed")
+        return (None, dV, dvg, None, dh0, dc0, None) + tuple(grads)
+
+
+def decoder_forward_packed(w: Sequence[torch.Tensor], V, v_g, captions, lengths: Sequence[int], h0=None, c0=None,
+                           precision: str = "fp32"):
+    """-> (PackedSequence of scores over the valid positions, alpha [B,T,k], beta [B,T,1], hT, cT), differentiable.
+    Equal to ``pack_scores(decoder_forward(...)[0], lengths)`` without ever computing the discarded rows."""
+    _need_cuda(V, v_g, captions, h0, c0)
+    V, v_g = _f32c(V), _f32c(v_g)
+    B, _, H = V.shape
+    captions = captions.to(torch.int64).contiguous()
+    h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
+    row_index, batch_sizes = cached_row_index(lengths, captions.shape[1], V.device)
+    data, alpha, beta, hT, cT = _DecoderPackedFn.apply(PRECISIONS[precision], V, v_g, captions, h0, c0, row_index, *w)
+    return torch.nn.utils.rnn.PackedSequence(data, batch_sizes), alpha, beta, hT, cT
+
+
 class _PackRowsFn(torch.autograd.Function):
     """``pack_padded_sequence(scores, lengths, batch_first=True).data`` (baseline_attention.py:228)."""
 

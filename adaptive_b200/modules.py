@@ -200,6 +200,7 @@ class Encoder2Decoder(nn.Module):
         cf = cf if cf is not None else _Cfg()
         self.encoder = AttentiveCNN(cf.adaptive_word_embed_size, cf.adaptive_lstm_hidden_size, cf)
         self.decoder = Decoder(cf.adaptive_word_embed_size, cf.vocab_length, cf.adaptive_lstm_hidden_size, cf)
+        self.fused_pack = True
 
     def _encode(self, images):
         if isinstance(images, (tuple, list)):
@@ -211,6 +212,12 @@ class Encoder2Decoder(nn.Module):
         """-> PackedSequence of scores over the valid positions (lengths already minus one,
         sorted descending), time-major like ``pack_padded_sequence(..., batch_first=True)``."""
         V, v_g, states = self._encode(images)
+        h0, c0 = states if states is not None else (None, None)
+        # Decoder.forward + pack_padded_sequence (baseline_attention.py:219-230) in one operator: the vocabulary projection
+        # is only computed for the rows the packing keeps (identical values and order; `fused_pack = False` takes the
+        # two-step route `pack_scores(self.decoder(...)[0], lengths)`)
+        if self.fused_pack and V.shape[2] % 4 == 0:
+            return F_aa.decoder_forward_packed(self.decoder.weights(), V, v_g, captions, lengths, h0, c0, self.decoder.precision)[0]
         scores = self.decoder(V, v_g, captions, states)[0]
         return F_aa.pack_scores(scores, lengths)
 

@@ -252,10 +252,10 @@ class DataParallelTrainer:
             f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
             u8 = lambda n: torch.empty(n, device=dev, dtype=torch.uint8)
             hit = {
-                "d": d, "scores": f32(B, T, Vc), "alpha": f32(B, T, k), "beta": f32(B, T, 1), "hT": f32(B, H), "cT": f32(B, H),
+                "d": d, "alpha": f32(B, T, k), "beta": f32(B, T, 1), "hT": f32(B, H), "cT": f32(B, H),
                 "saved": u8(self.lib.aa_decoder_saved_bytes(ctypes.byref(d))),
                 "scratch": u8(self.lib.aa_decoder_bwd_scratch_bytes(ctypes.byref(d))),
-                "packed": f32(n_rows, Vc), "dpacked": f32(n_rows, Vc), "dscores": f32(B, T, Vc),
+                "packed": f32(n_rows, Vc), "dpacked": f32(n_rows, Vc),
                 "loss": torch.zeros((), device=dev, dtype=torch.float32), "dV": f32(B, k, H), "dvg": f32(B, E),
                 "dh0": f32(B, H), "dc0": f32(B, H),
             }
@@ -291,21 +291,20 @@ class DataParallelTrainer:
         for name, t in zip(WEIGHT_FIELDS, self.buckets.ordered()):
             setattr(gs, name, t.data_ptr())
         with torch.cuda.device(self.device):
-            check(lib.aa_decoder_forward(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(b["scores"]),
-                                         P(b["alpha"]), P(b["beta"]), P(b["hT"]), P(b["cT"]), P(b["saved"]), b["saved"].numel(), st),
-                  "aa_decoder_forward")
-            check(lib.aa_pack_rows(P(b["scores"]), Vc, P(row_index), n_rows, P(b["packed"]), st), "aa_pack_rows")
+            # forward over the packed rows only (pack_padded_sequence fused, Q13), loss + its gradient in one pass, backward
+            check(lib.aa_decoder_forward_packed(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(row_index),
+                                                n_rows, P(b["packed"]), P(b["alpha"]), P(b["beta"]), P(b["hT"]), P(b["cT"]), P(b["saved"]),
+                                                b["saved"].numel(), st), "aa_decoder_forward_packed")
             check(lib.aa_cross_entropy_denom(P(b["packed"]), n_rows, Vc, P(targets), denom, P(b["loss"]), P(b["dpacked"]), st),
                   "aa_cross_entropy_denom")
-            check(lib.aa_unpack_rows(P(b["dpacked"]), Vc, P(row_index), n_rows, B * T, P(b["dscores"]), st), "aa_unpack_rows")
             self.reducer.start()
             hooked = self.overlap and self.world > 1
-            check(lib.aa_decoder_backward_hooked(
+            check(lib.aa_decoder_backward_packed(
                 ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(b["alpha"]), P(b["beta"]), P(b["saved"]),
-                b["saved"].numel(), P(b["dscores"]), None, None, None, None, ctypes.byref(gs), P(b["dV"]), P(b["dvg"]),
-                P(b["dh0"]) if h0 is not None else None, P(b["dc0"]) if c0 is not None else None, P(b["scratch"]),
+                b["saved"].numel(), P(row_index), n_rows, P(b["dpacked"]), None, None, None, None, ctypes.byref(gs), P(b["dV"]),
+                P(b["dvg"]), P(b["dh0"]) if h0 is not None else None, P(b["dc0"]) if c0 is not None else None, P(b["scratch"]),
                 b["scratch"].numel(), st, self.reducer.event_handles() if hooked else None,
-                ctypes.cast(self._cb, ctypes.c_void_p) if hooked else None, None), "aa_decoder_backward_hooked")
+                ctypes.cast(self._cb, ctypes.c_void_p) if hooked else None, None), "aa_decoder_backward_packed")
             if self.world > 1 and not hooked:          # non-overlapped variant: same buckets, after the backward
                 for i in range(len(BUCKETS)):
                     self.reducer.events[i].record()

@@ -215,6 +215,23 @@ int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const floa
                                void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
                                aa_grad_ready_fn on_ready, void* user);
 
+/* Packed variants of aa_decoder_forward / aa_decoder_backward for Encoder2Decoder.forward (baseline_attention.py:206-230):
+ * the reference projects all B*T positions onto the vocabulary and then keeps, through pack_padded_sequence (:228), only the
+ * n_rows positions inside each caption's length.  Here the projection (and, in the backward, its three contractions, the bias
+ * gradient and the bf16 cast) runs over those rows only, directly in packed time-major order.  row_index [n_rows] (device,
+ * int64) = b*T+t of every packed row (aa host logic: functional.packed_row_index); scores_packed / d_scores_packed are
+ * [n_rows, Vc].  Everything else as in the unpacked entry points; ready_events / on_ready / user as in
+ * aa_decoder_backward_hooked (all may be NULL). */
+int aa_decoder_forward_packed(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                              const float* h0, const float* c0, const int64_t* row_index, int64_t n_rows, float* scores_packed,
+                              float* alpha, float* beta, float* hT, float* cT, void* saved, size_t saved_bytes, void* stream);
+int aa_decoder_backward_packed(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                               const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
+                               size_t saved_bytes, const int64_t* row_index, int64_t n_rows, const float* d_scores_packed,
+                               const float* d_alpha, const float* d_beta, const float* d_hT, const float* d_cT,
+                               const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0, float* dc0, void* scratch,
+                               size_t scratch_bytes, void* stream, void* const* ready_events, aa_grad_ready_fn on_ready, void* user);
+
 /* pack_padded_sequence(scores, lengths, batch_first=True).data (baseline_attention.py:228):
  * gathers rows (b,t) with t < lengths[b] in time-major order.  row_index [n_rows] int64 holds
  * b*T+t per packed row (host code builds it from `lengths`).  packed [n_rows,Vc]. */

@@ -340,6 +340,40 @@ def test_bptt_cluster_ksplit_matches_single_cta(B, T, dims):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-6), ("bf16", 2e-3)])
+def test_packed_forward_backward_equals_pack_of_full(prec, tol):
+    """Encoder2Decoder.forward with the fused packing (vocabulary projection over the kept rows only) against
+    pack_padded_sequence of the full Decoder.forward: same PackedSequence, same gradients."""
+    dims, B, T = Dims(H=128, E=64, Vc=504, k=49), 11, 9
+    w = make_weights(dims, seed=51, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=52)
+    lengths = make_lengths(B, T, seed=53)
+    n = int(sum(lengths))
+    rng = np.random.Generator(np.random.PCG64(5))
+    dP = torch.from_numpy((rng.standard_normal((n, dims.Vc)) / dims.Vc).astype(np.float32)).cuda()
+
+    def run(fused):
+        W = dev_weights(w, requires_grad=True)
+        V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+        if fused:
+            packed = F_aa.decoder_forward_packed(W, V, v_g, cap, lengths, h0, c0, precision=prec)[0]
+        else:
+            packed = F_aa.pack_scores(F_aa.decoder_forward(W, V, v_g, cap, h0, c0, precision=prec)[0], lengths)
+        (packed.data * dP).sum().backward()
+        torch.cuda.synchronize()
+        outs = {"data": packed.data, "batch_sizes": packed.batch_sizes.float()}
+        for key, t in zip(grad_key_order(), W):
+            outs["d" + key] = t.grad
+        for key, t in (("V", V), ("v_g", v_g), ("h0", h0), ("c0", c0)):
+            outs["d" + key] = t.grad
+        return {k: v.detach().cpu().numpy() for k, v in outs.items()}
+
+    a, b = run(True), run(False)
+    assert a["data"].shape == (n, dims.Vc)
+    bad = {k: rel_err(a[k], b[k]) for k in a if not rel_err(a[k], b[k]) <= tol}
+    assert not bad, bad
+
+
 def test_pack_and_cross_entropy_vs_golden():
     for case in ("tiny", "odd"):
         g, dims, B, T, L, w, inp = golden_setup(case, np.float32)
