@@ -384,21 +384,18 @@ def run_ours(args):
     train_tok = TRAIN_B * TRAIN_T * n_gpus / (train_ms * 1e-3)
 
     stage("training e2e")
-    # e2e: pinned host -> device copies and the loss read-back inside the timed region
-    def train_step_e2e(hb):
-        if stepper is not None:
-            return float(train_step(hb).item())          # H2D copies go straight into the graph's static buffers
-        b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        return float(train_step(b).item())
+    # e2e: through adaptive_b200.pipeline.HostPipeline (the loop a caller runs): every step's inputs are copied from pinned
+    # host memory and its loss is read back, inside the timed region; the copy of batch i+1 overlaps step i
+    from adaptive_b200.pipeline import HostPipeline
 
-    for i in range(min(3, args.warmup)):
-        train_step_e2e(host[i % NB])
+    pipe = HostPipeline(lambda b: train_step(b), host[0], dev)
+    pipe.run(host[i % NB] for i in range(min(3, args.warmup)))
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        train_step_e2e(host[i % NB])
+    losses = pipe.run(host[i % NB] for i in range(args.steps))
     torch.cuda.synchronize()
     e2e_train_s = max_over_ranks((time.perf_counter() - t0)) / args.steps
+    assert len(losses) == args.steps and all(np.isfinite(float(x)) for x in losses)
     barrier()
 
     stage("per-kernel timing pass")
@@ -435,12 +432,14 @@ def run_ours(args):
     dec_ms = max_over_ranks(e0.elapsed_time(e1)) / dsteps
     dec_launches = _lib.launch_count() - l0d
     dec_tok = DECODE_B * DECODE_L * n_gpus / (dec_ms * 1e-3)
+    dpipe = HostPipeline(lambda b: decode_step(b)[0], dhost, dev)
+    dpipe.run(dhost for _ in range(2))
+    barrier()
     t0 = time.perf_counter()
-    for _ in range(dsteps):
-        b = {k: v.to(dev, non_blocking=True) for k, v in dhost.items()}
-        ids = decode_step(b)[0].cpu()
+    all_ids = dpipe.run(dhost for _ in range(dsteps))
     torch.cuda.synchronize()
     e2e_dec_s = max_over_ranks(time.perf_counter() - t0) / dsteps
+    ids = all_ids[-1]
     d2h_dec = ids.numel() * ids.element_size()
     barrier()
     _lib.profile_enable(True)

@@ -65,3 +65,27 @@ def test_feature_map_entry_and_decoder_states():
     V, v_g, states = m.encoder(feats)
     s, a, b, (hn, cn) = m.decoder(V, v_g, cap, states)
     assert s.shape == (3, 4, 120) and b.shape == (3, 4, 1) and hn.shape == (1, 3, 64) and cn.shape == (1, 3, 64)
+
+
+def test_host_pipeline_matches_sequential_loop():
+    """HostPipeline (double-buffered H2D upload, results read one step late) returns, per batch, exactly what the plain
+    copy -> step -> read loop returns."""
+    import torch
+    from adaptive_b200.pipeline import HostPipeline
+
+    torch.manual_seed(0)
+    batches = [{"x": torch.randn(64, 33).pin_memory(), "y": torch.randint(0, 9, (64,)).pin_memory()} for _ in range(7)]
+    w = torch.randn(33, 5, device="cuda")
+    static_out = torch.empty(5, device="cuda")
+
+    def step(b):                 # returns a tensor it overwrites on the next call, like a CUDA graph's static output
+        static_out.copy_(((b["x"] @ w) * b["y"].float().unsqueeze(1)).sum(0))
+        return static_out
+
+    want = [step({k: v.cuda() for k, v in hb.items()}).cpu().clone() for hb in batches]
+    pipe = HostPipeline(step, batches[0], "cuda")
+    got = pipe.run(iter(batches))
+    assert len(got) == len(want)
+    for g, wv in zip(got, want):
+        assert torch.equal(g, wv)
+    assert pipe.h2d_bytes == 64 * 33 * 4 + 64 * 8 and pipe.d2h_bytes == 20
