@@ -9,6 +9,8 @@
 //    state c (resp. dc) living in registers across all steps;
 //  * steps are separated by a release/acquire grid barrier per 128-row group (rows are independent
 //    sequences), so the launch must be cooperative (all CTAs co-resident).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
@@ -748,16 +750,37 @@ int launch_bwd_ks(const LstmSeqBwd& p, cudaStream_t st) {
   cfg.blockDim = dim3(BWD_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeCooperative;      // the grid barrier needs every CTA resident
-  at[0].val.cooperative = 1;
-  at[1].id = cudaLaunchAttributeClusterDimension;
-  at[1].val.clusterDim.x = KS;
-  at[1].val.clusterDim.y = 1;
-  at[1].val.clusterDim.z = 1;
+  // The grid barrier needs every CTA resident.  Without clusters that is what a cooperative launch checks; with clusters the
+  // residency check is cudaOccupancyMaxActiveClusters below (Nsight Compute cannot replay a launch that is both cooperative
+  // and clustered: "LaunchFailed"), the launch itself is a plain cluster launch.
+  cudaLaunchAttribute at[1];
+  if (KS > 1) {
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = KS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+  } else {
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = KS > 1 ? 2 : 1;
-  AA_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kern, args));
+  cfg.numAttrs = 1;
+  if (KS > 1) {   // clusters are placed inside one GPC: ask the runtime how many fit at once (varies with floor-sweeping / profilers)
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kern, &cfg) != cudaSuccess || max_clusters < C * RG) {
+      cudaGetLastError();
+      return AA_ERR_UNSUPPORTED;
+    }
+  }
+  const cudaError_t le = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+  if (le != cudaSuccess) {
+    if (KS > 1) {          // a refused cluster launch (e.g. under a profiler that cannot replay cooperative cluster grids) is not
+      cudaGetLastError();  // fatal: the caller retries without the K-split
+      return AA_ERR_UNSUPPORTED;
+    }
+    set_error("cudaLaunchKernelExC(lstm_seq_bwd) failed: %s", cudaGetErrorString(le));
+    return AA_ERR_CUDA;
+  }
   count_launch();
   return AA_OK;
 }
@@ -784,9 +807,16 @@ int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t st) {
   AA_CHECK_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(unsigned) * RG, st));
   int ks = bwd_ksplit(p.B, H);
   if (ks > g_bwd_ksplit_max) ks = g_bwd_ksplit_max;
-  if (ks == 4) return launch_bwd_ks<4>(p, st);
-  if (ks == 2) return launch_bwd_ks<2>(p, st);
-  return launch_bwd_ks<1>(p, st);
+  static const int env_cap = [] {   // AA_BPTT_KSPLIT=1 in the environment: never use the cluster variant
+    const char* e = getenv("AA_BPTT_KSPLIT");
+    return e ? atoi(e) : 4;
+  }();
+  if (ks > env_cap) ks = env_cap < 1 ? 1 : env_cap;
+  int rc = AA_ERR_UNSUPPORTED;
+  if (ks == 4) rc = launch_bwd_ks<4>(p, st);
+  else if (ks == 2) rc = launch_bwd_ks<2>(p, st);
+  if (rc == AA_ERR_UNSUPPORTED) rc = launch_bwd_ks<1>(p, st);
+  return rc;
 }
 
 int set_bptt_ksplit_max(int ks) {

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from adaptive_b200 import functional as F_aa
-from adaptive_b200.synth import CFG_A, Dims, make_inputs, make_lengths, make_weights
+from adaptive_b200.synth import CFG_A, CFG_B, Dims, make_inputs, make_lengths, make_weights
 from oracle import adaptive_oracle as orc
 from tests.gpu_utils import dev_inputs, dev_weights, grad_key_order, near_tie_report
 from tests.helpers import GOLDEN_CASES, golden_setup, rel_err, upstream
@@ -452,6 +452,62 @@ def test_full_size_decode_properties(prec):
     hard, near = near_tie_report(ids.cpu().numpy()[pick], r_ids, top2[..., 1] - top2[..., 0], NEAR_TIE)
     _log_near_ties("full_size_decode[%s]" % prec, near)
     assert not hard, hard
+
+
+def test_cfgB_shape_training_vs_oracle_and_full_batch_properties():
+    """BASELINE config 5 shapes (H=1024, E=512, k=196, Vc=20000, T=18): the bf16 training path against the fp64 oracle on
+    a batch the oracle finishes in seconds, then the full per-GPU batch (256) through size-independent properties:
+    alpha sums to 1, beta in (0,1), finite gradients, rows independent (a slice of the batch gives the same rows up to rounding), and
+    the gradient is linear in the upstream gradient."""
+    dims, T = CFG_B, 18
+    w = make_weights(dims, seed=61, bias_scale=0.1)
+    W = dev_weights(w, requires_grad=True)
+    # ---- oracle comparison at B = 6 ----
+    B = 6
+    inp = make_inputs(dims, B, T, seed=62)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    i64 = {k: (v.astype(np.float64) if v.dtype != np.int64 else v) for k, v in inp.items()}
+    s_o, a_o, b_o, _, cache = orc.decoder_forward(w64, i64["V"], i64["v_g"], i64["captions"], i64["h0"], i64["c0"], want_cache=True)
+    rng = np.random.Generator(np.random.PCG64(6))
+    dS = rng.standard_normal(s_o.shape) / s_o.shape[-1]
+    G = orc.decoder_backward(w64, cache, dS)
+    V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+    scores, alpha, beta, hT, cT = F_aa.decoder_forward(W, V, v_g, cap, h0, c0, precision="bf16")
+    (scores * torch.from_numpy(dS.astype(np.float32)).cuda()).sum().backward()
+    errs = {"scores": rel_err(scores.detach().cpu().numpy(), s_o), "alpha": rel_err(alpha.detach().cpu().numpy(), a_o),
+            "beta": rel_err(beta.detach().cpu().numpy(), b_o)}
+    for key, t in zip(grad_key_order(), W):
+        errs["d" + key] = rel_err(t.grad.cpu().numpy(), G[key])
+    errs["dV"] = rel_err(V.grad.cpu().numpy(), G["V"])
+    bad = {k: v for k, v in errs.items() if not v < BF16_TOL}
+    assert not bad, (bad, errs)
+    # ---- full per-GPU batch: properties ----
+    B = 256
+    inp = make_inputs(dims, B, T, seed=63)
+    V, v_g, h0, c0, cap = dev_inputs(inp)
+    Wd = tuple(t.detach().requires_grad_(True) for t in W)
+    dSg = torch.randn(B, T, 64, device="cuda") / dims.Vc      # upstream gradient on the first 64 vocabulary columns only (memory)
+
+    def fb(scale, sl=slice(None)):
+        for t in Wd:
+            t.grad = None
+        sc, al, be, _, _ = F_aa.decoder_forward(Wd, V[sl].contiguous(), v_g[sl].contiguous(), cap[sl].contiguous(), h0[sl].contiguous(),
+                                                c0[sl].contiguous(), precision="bf16")
+        (sc[..., :64] * (scale * dSg[sl])).sum().backward()
+        torch.cuda.synchronize()
+        return sc.detach(), al.detach(), be.detach(), [t.grad.clone() for t in Wd]
+
+    sc1, al1, be1, g1 = fb(1.0)
+    assert torch.allclose(al1.sum(-1), torch.ones(B, T, device="cuda"), atol=1e-5)
+    assert float(be1.min()) > 0 and float(be1.max()) < 1
+    assert all(bool(torch.isfinite(g).all()) for g in g1)
+    # rows are independent sequences (not bit-identical: the recurrence kernel picks its units-per-CTA, hence the order of
+    # its partial fp32 accumulators, from the batch size; bf16 operand rounding then moves the last bits)
+    sc2, al2, _, _ = fb(1.0, slice(100, 164))
+    assert rel_err(sc2.cpu().numpy(), sc1[100:164].cpu().numpy()) < 5e-3 and rel_err(al2.cpu().numpy(), al1[100:164].cpu().numpy()) < 5e-3
+    _, _, _, g2 = fb(2.0)                                     # backward is linear in the upstream gradient
+    for a, b in zip(g1, g2):
+        assert rel_err((2 * a).cpu().numpy(), b.cpu().numpy()) < 2e-3
 
 
 def test_errors_are_loud():
