@@ -65,6 +65,7 @@ SIGNATURES = {
     "aa_debug_set_trace_buffer": (c_int, [P]),
     "aa_debug_set_decode_atten_simple": (c_int, [c_int]),
     "aa_debug_set_atten_sequential": (c_int, [c_int]),
+    "aa_debug_set_gemm_splitk": (c_int, [c_int]),
     "aa_debug_set_bptt_ksplit": (c_int, [c_int]),
     "aa_linear_forward": (c_int, [c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "aa_gemm": (c_int, [c_int, c_int, c_int, c_int, P, c_int64, c_int, P, c_int64, c_int, P, c_int64, ctypes.c_float, P, P,

@@ -61,6 +61,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;
+int g_tc_splitk = 1;   // diagnostics (aa_debug_set_gemm_splitk)
 // warp 0: TMA, warp 1: MMA, warps 2..: epilogue (TMEM lane quarter = warp % 4).  EW epilogue warps = EW/4 "parts" per
 // lane quarter, each part draining a contiguous range of the tile's 32-column chunks: with 4 warps the TMEM -> smem
 // transpose -> global chain of one warp per quarter bounded the K=512 contractions (1.4 TB/s of output at 148 SMs).
@@ -75,6 +76,7 @@ struct TcEpilogue {
   const float* bias1; const float* bias2;
   float* pmax; int* pidx; int tiles_n;      // optional per-(row, n-tile) arg-max partials of D (bias included)
   int lo_a, lo_b;                           // split mode: column offset of the lo half inside a row of A / B
+  int ksplit, kb_per;                       // split-K: work unit = (tile, K range of kb_per k-blocks); partial tiles are added with red.global.add
 };
 
 // Tile geometry (bytes): every smem row is 128 B (the swizzle span).
@@ -89,7 +91,7 @@ struct TcEpilogue {
 template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT>
 __global__ void __launch_bounds__(tc_threads(SPLIT), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m,
-               int num_tiles) {
+               int num_tiles, int num_units) {
   // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so neighbouring CTAs share the
   // B/weight tile in L2).  Two TMEM accumulators: the epilogue of tile i overlaps the TMA/MMA of tile i+1.
   constexpr bool TF32 = (ES == 4);
@@ -148,9 +150,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit % num_tiles, sp = unit / num_tiles;
         const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int kb0 = sp * e.kb_per, kb1 = min(nkb, kb0 + e.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -188,12 +192,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++lt) {
+        const int kb0 = (unit / num_tiles) * e.kb_per, kb1 = min(nkb, kb0 + e.kb_per);
         const int acc = lt & 1;
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -206,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if constexpr (SPLIT) {
               const uint64_t ah = make_smem_desc(a_addr + k * 32, 16, 1024), al = make_smem_desc(a_addr + A_BYTES + k * 32, 16, 1024);
               const uint64_t bh = make_smem_desc(b_addr + k * 32, 16, 1024), bl = make_smem_desc(b_addr + B_BYTES + k * 32, 16, 1024);
-              tc_mma<true>(tmem_d, al, bh, idesc, (kb | k) != 0 ? 1u : 0u);
+              tc_mma<true>(tmem_d, al, bh, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
               tc_mma<true>(tmem_d, ah, bl, idesc, 1u);
               tc_mma<true>(tmem_d, ah, bh, idesc, 1u);
               continue;
@@ -216,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             //           advance UMMA_K k-rows * 128 B
             const uint64_t da = A_MN ? make_smem_desc(a_addr + k * UMMA_K * 128, A_BOX, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(b_addr + k * UMMA_K * 128, B_BOX, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
-            tc_mma<TF32>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma<TF32>(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty_bar[s]);   // frees the smem stage when these MMAs have read it
           }
@@ -240,7 +245,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     const int part = (warp - 2) >> 2;      // which contiguous chunk range of the tile this warp drains
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    const bool ks_atomic = e.ksplit > 1;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++lt) {
+      const int tile = unit % num_tiles;
+      const bool first_split = unit < num_tiles;     // bias and the C input are added by the K range 0 only
       const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
       const int acc = lt & 1;
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
@@ -280,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         const int n = nb + c4;
         float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias1 || e.bias2) {
+        if ((e.bias1 || e.bias2) && first_split) {
           float bb[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -291,7 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool vecc = (n + 3 < e.N) && ((e.ldcin & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Cin) & 15) == 0);
         const bool vec16 = (n + 3 < e.N) && ((e.ldd16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.D16) & 7) == 0);
         float4 cin[8];
-        if (e.Cin) {
+        const bool use_cin = e.Cin && first_split && !(ks_atomic && e.Cin == e.D32);   // in-place accumulate: the adds land on C itself
+        if (use_cin) {
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const long long row = row0 + i8 * 4 + rsub;
@@ -313,9 +322,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const long long row = row0 + i8 * 4 + rsub;
           float4 v = *reinterpret_cast<const float4*>(&tbuf[(i8 * 4 + rsub) * TS + c4]);
           v.x += badd.x; v.y += badd.y; v.z += badd.z; v.w += badd.w;
-          if (e.Cin) { v.x += e.beta * cin[i8].x; v.y += e.beta * cin[i8].y; v.z += e.beta * cin[i8].z; v.w += e.beta * cin[i8].w; }
+          if (use_cin) { v.x += e.beta * cin[i8].x; v.y += e.beta * cin[i8].y; v.z += e.beta * cin[i8].z; v.w += e.beta * cin[i8].w; }
           if (row < e.M && n < e.N) {
-            if (e.D32) {
+            if (e.D32 && ks_atomic) {       // split-K: accumulate this K range's partial tile
+              float* dp = e.D32 + row * e.ldd32 + n;
+              if (vec32) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+              else {
+                atomicAdd(dp, v.x);
+                if (n + 1 < e.N) atomicAdd(dp + 1, v.y);
+                if (n + 2 < e.N) atomicAdd(dp + 2, v.z);
+                if (n + 3 < e.N) atomicAdd(dp + 3, v.w);
+              }
+            } else if (e.D32) {
               float* dp = e.D32 + row * e.ldd32 + n;
               if (vec32) *reinterpret_cast<float4*>(dp) = v;
               else {
@@ -391,8 +409,24 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
     attr_done = true;
   }
   const int num_tiles = tiles_m * tiles_n;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();     // persistent: one CTA per SM
-  kern<<<grid, tc_threads(SPLIT), smem, st>>>(tmA, tmB, e, tiles_m, num_tiles);
+  // Split-K.  One tcgen05.mma with M = 128 costs ~103 cycles for any N <= 128 (tools/mma_probe.cu), so a contraction is
+  // cheapest with wide tiles; when wide tiles leave most SMs idle (small M*N, long K: the dX / dW contractions) the K range
+  // is cut instead and the partial tiles are summed with vector red.global.add.  Needs a plain fp32 output.
+  constexpr int BKk = 128 / ES;
+  const int nkb = ceil_div(g.K, BKk);
+  int ksplit = 1;
+  if (!SPLIT && g.D32 && !g.D16 && !g.pmax && g_tc_splitk) {
+    const int sms = num_sms();
+    while (ksplit < 16 && num_tiles * (ksplit + 1) <= sms && nkb / (ksplit + 1) >= 4) ++ksplit;
+  }
+  e.kb_per = ceil_div(nkb, ksplit);
+  ksplit = ceil_div(nkb, e.kb_per);            // no empty K ranges
+  e.ksplit = ksplit;
+  if (ksplit > 1 && !(g.Cin == g.D32 && g.beta == 1.f))   // (in-place accumulate adds onto C itself: nothing to clear)
+    AA_CHECK_CUDA(cudaMemset2DAsync(g.D32, sizeof(float) * (size_t)g.ldd32, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
+  const int num_units = num_tiles * ksplit;
+  const int grid = num_units < num_sms() ? num_units : num_sms();     // persistent: one CTA per SM
+  kern<<<grid, tc_threads(SPLIT), smem, st>>>(tmA, tmB, e, tiles_m, num_tiles, num_units);
   AA_CHECK_LAUNCH("gemm_tc_kernel");
   return AA_OK;
 }
@@ -410,12 +444,20 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
   // pick BN so that the grid covers the SMs when the problem allows it
   const long long sms = num_sms();
   const long long mt = ceil_div(g.M, BM);
-  if (mt * ceil_div(g.N, 128) >= sms || g.N > 2048) return launch_major<128, ES, 5>(g, st);
-  if (mt * ceil_div(g.N, 64) >= sms || g.N > 512 || (g.b_mn && ES == 2)) return launch_major<64, ES, 6>(g, st);
-  return launch_major<32, ES, 6>(g, st);   // (an MN-major bf16 B tile needs >= 64 columns: one 128-byte swizzle row)
+  const bool can_splitk = g_tc_splitk && g.D32 && !g.D16 && !g.pmax && ceil_div(g.K, 128 / ES) >= 8;
+  // widest tile the problem fills: the per-MMA cost does not depend on N, and split-K covers the SMs when it applies
+  if (g.N > 64 && (can_splitk || mt * ceil_div(g.N, 128) >= sms || g.N > 2048)) return launch_major<128, ES, 5>(g, st);
+  if (g.N > 32 && (can_splitk || mt * ceil_div(g.N, 64) >= sms || g.N > 512 || (g.b_mn && ES == 2))) return launch_major<64, ES, 6>(g, st);
+  if (g.b_mn && ES == 2) return launch_major<64, ES, 6>(g, st);   // (an MN-major bf16 B tile needs >= 64 columns: one 128-byte swizzle row)
+  return launch_major<32, ES, 6>(g, st);
 }
 
 }  // namespace
+
+int set_gemm_splitk(int on) {
+  g_tc_splitk = on ? 1 : 0;
+  return AA_OK;
+}
 
 int gemm_tc_argmax_tile_n(int N) { return N > 64 ? 128 : 64; }
 

@@ -90,6 +90,7 @@ struct TcGemmArgs {
 };
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
 int gemm_tc_argmax_tile_n(int N);
+int set_gemm_splitk(int on);   // diagnostics: 0 = never split K (deterministic summation order)
 
 // ---- lstm_seq.cu (persistent recurrence, bf16 tensor-core mode) -----------------------------
 // true when the one-launch recurrence kernels can run this shape (H % 64 == 0 and the CTAs fit the chip)

@@ -110,6 +110,9 @@ int aa_debug_set_trace_buffer(void* dev_ptr);
 int aa_debug_set_decode_atten_simple(int on);
 /* Diagnostics: on != 0 makes the training attention use the step-by-step kernels instead of the step-parallel ones. */
 int aa_debug_set_atten_sequential(int on);
+/* Diagnostics: on == 0 stops the tcgen05 GEMM from splitting K (partial tiles summed with red.global.add, i.e. a
+ * run-to-run varying fp32 summation order in the affected gradients); default on. */
+int aa_debug_set_gemm_splitk(int on);
 /* Diagnostics: cap on the K-split (thread-block cluster size 1, 2 or 4) of the persistent BPTT kernel. */
 int aa_debug_set_bptt_ksplit(int ks);
 
