@@ -99,7 +99,7 @@ def run_reference(args):
                          "sample": "%d full steps of the same workload (B=%d, T=%d) on the numpy oracle port" % (steps, TRAIN_B, TRAIN_T)},
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def workload_config(n):
@@ -497,11 +497,31 @@ def run_ours(args):
         out["cpu_baseline"] = {"value": TRAIN_B * TRAIN_T / sec, "unit": "tokens/s", "cores": cores, "kind": "port",
                                "sample": "%d full steps of the same workload (B=%d, T=%d) on the numpy oracle port, %.1f s" %
                                          (ncpu, TRAIN_B, TRAIN_T, sec * ncpu)}
-    print(json.dumps(out))
+    emit(out)
     leave(world)
 
 
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to stdout whatever
+    NCCL_DEBUG_FILE says), so the real stdout is kept on a private descriptor for the JSON line and fd 1 is pointed at stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
