@@ -73,12 +73,17 @@ def oracle_train_step_fn(B, T, dims):
 
 
 def time_cpu(step, steps, warmup):
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    return (time.perf_counter() - t0) / steps
+    """Seconds per step with the BLAS pool at every host core (torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would otherwise pin the numpy port to one thread)."""
+    from threadpoolctl import threadpool_limits
+
+    with threadpool_limits(limits=os.cpu_count() or 1):
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        return (time.perf_counter() - t0) / steps
 
 
 def run_reference(args):
