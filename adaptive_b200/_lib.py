@@ -88,6 +88,8 @@ SIGNATURES = {
     "aa_decoder_forward_packed": (c_int, [_D, _W, P, P, P, P, P, P, c_int64, P, P, P, P, P, P, c_size_t, P]),
     "aa_decoder_backward_packed": (c_int, [_D, _W, P, P, P, P, P, P, P, P, c_size_t, P, c_int64, P, P, P, P, P, _G, P, P, P, P, P,
                                            c_size_t, P, POINTER(c_void_p), c_void_p, c_void_p]),
+    "aa_clip_adam_step": (c_int, [P, c_int, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                  ctypes.c_float, c_int, P, P, P]),
     "aa_pack_rows": (c_int, [P, c_int64, P, c_int64, P, P]),
     "aa_unpack_rows": (c_int, [P, c_int64, P, c_int64, c_int64, P, P]),
     "aa_cross_entropy": (c_int, [P, c_int64, c_int64, P, P, P, P]),

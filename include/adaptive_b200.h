@@ -218,6 +218,25 @@ int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const floa
                                void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
                                aa_grad_ready_fn on_ready, void* user);
 
+/* ---- optimizer step next to the path --------------------------------------------------------------
+ * clip_grad_norm_(model.decoder.LSTM.parameters(), clip_max_norm) (train.py:213-214) followed by torch.optim.Adam's update
+ * (model_factory.py:69-77; defaults of the reference: lr 1e-3, betas 0.8 / 0.999, eps 1e-8, weight_decay 0) over up to
+ * AA_OPT_MAX_TENSORS parameter tensors in two launches.  clip[i] != 0 marks the tensors of the clipped group (the LSTM's
+ * four); their gradients enter Adam scaled by min(1, max_norm / (norm + 1e-6)) and are rewritten in place only when
+ * write_clipped_grads != 0.  step counts from 1.  scratch: one device float; norm_out (optional): the group's norm. */
+#define AA_OPT_MAX_TENSORS 24
+typedef struct aa_opt_tensors {
+  float* param[AA_OPT_MAX_TENSORS];
+  float* grad[AA_OPT_MAX_TENSORS];
+  float* m[AA_OPT_MAX_TENSORS];
+  float* v[AA_OPT_MAX_TENSORS];
+  long long n[AA_OPT_MAX_TENSORS];
+  int clip[AA_OPT_MAX_TENSORS];
+} aa_opt_tensors;
+int aa_clip_adam_step(const aa_opt_tensors* t, int n_tensors, int step, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, float clip_max_norm, int write_clipped_grads, float* scratch, float* norm_out,
+                      void* stream);
+
 /* Packed variants of aa_decoder_forward / aa_decoder_backward for Encoder2Decoder.forward (baseline_attention.py:206-230):
  * the reference projects all B*T positions onto the vocabulary and then keeps, through pack_padded_sequence (:228), only the
  * n_rows positions inside each caption's length.  Here the projection (and, in the backward, its three contractions, the bias

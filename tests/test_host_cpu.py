@@ -85,3 +85,19 @@ def test_synth_is_reproducible_and_shaped():
     assert inp["V"].min() >= 0 and np.abs(inp["h0"]).max() <= 1
     ls = make_lengths(80, 18)
     assert ls == sorted(ls, reverse=True) and ls[0] == 17 and min(ls) >= 6
+
+
+def test_ids_to_captions_and_vocabulary_format():
+    """tools/utils.py:180-195 semantics: cut at the first <end>, keep everything before it (incl. <start>/<unk>/<pad>), one
+    record per image; Vocabulary ids of the specials as in build_vocab.py:48-51."""
+    from adaptive_b200.postprocess import Vocabulary, caption_results, ids_to_captions
+
+    vocab = Vocabulary(["a", "dog", "runs"])
+    assert [vocab(w) for w in ("<pad>", "<start>", "<end>", "<unk>", "a", "dog", "runs", "zebra")] == [0, 1, 2, 3, 4, 5, 6, 3]
+    assert len(vocab) == 7 and vocab.idx2word[5] == "dog"
+    ids = np.array([[4, 5, 6, 2, 4, 4], [2, 4, 5, 6, 4, 4], [4, 3, 6, 6, 6, 6]])
+    assert ids_to_captions(ids, vocab) == ["a dog runs", "", "a <unk> runs runs runs runs"]
+    res = caption_results([11, 12, 13], ids, vocab)
+    assert res[0] == {"image_id": 11, "caption": "a dog runs"} and [r["image_id"] for r in res] == [11, 12, 13]
+    with pytest.raises(ValueError):
+        caption_results([1, 2], ids, vocab)

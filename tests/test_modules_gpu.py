@@ -89,3 +89,39 @@ def test_host_pipeline_matches_sequential_loop():
     for g, wv in zip(got, want):
         assert torch.equal(g, wv)
     assert pipe.h2d_bytes == 64 * 33 * 4 + 64 * 8 and pipe.d2h_bytes == 20
+
+
+def test_fused_clip_adam_matches_torch_clip_and_adam():
+    """aa_clip_adam_step == clip_grad_norm_(LSTM params, 5) + torch.optim.Adam(lr 1e-3, betas (0.8, 0.999), weight_decay 0) of
+    the reference (train.py:213-214, model_factory.py:69-77, cfg_wzn.py:47-51), over several steps, with and without the clip
+    being active; with weight decay the update of elements where g + wd*p cancels is ill-conditioned (it is ~lr*sign), so that
+    variant is compared on the well-conditioned elements only."""
+    import torch
+    from adaptive_b200.optim import FusedClipAdam
+
+    shapes = [(300, 40), (2048, 96), (2048,), (17,), (5, 7, 3)]
+    clip_idx = [1, 2]
+    for wd in (0.0, 0.01):
+        torch.manual_seed(1)
+        ours = [torch.randn(s, device="cuda") for s in shapes]
+        ref = [p.clone().requires_grad_(True) for p in ours]
+        opt_ref = torch.optim.Adam(ref, lr=1e-3, betas=(0.8, 0.999), weight_decay=wd)
+        opt = FusedClipAdam(ours, clip_params=[ours[i] for i in clip_idx], lr=1e-3, betas=(0.8, 0.999), weight_decay=wd, max_norm=5.0)
+        for step in range(4):
+            scale = 10.0 if step % 2 == 0 else 0.001          # clip active / inactive
+            grads = [torch.randn(s, device="cuda") * scale for s in shapes]
+            for p, r, g in zip(ours, ref, grads):
+                p.grad = g.clone()
+                r.grad = g.clone()
+            want_norm = torch.nn.utils.clip_grad_norm_([ref[i] for i in clip_idx], 5.0)
+            opt_ref.step()
+            opt.step()
+            torch.cuda.synchronize()
+            assert abs(float(opt.grad_norm) - float(want_norm)) <= 1e-4 * float(want_norm)
+            for i, (p, r) in enumerate(zip(ours, ref)):
+                assert torch.allclose(p.grad, r.grad, rtol=1e-6, atol=1e-9), (step, i)     # clipped gradients written back like torch
+                diff = (p - r.detach()).abs()
+                if wd == 0.0:
+                    assert float(diff.max()) <= 1e-6, (step, i, float(diff.max()))
+                else:
+                    assert float(diff.max()) <= 2e-5 and float(diff.median()) <= 2e-7, (step, i, float(diff.max()), float(diff.median()))
