@@ -411,16 +411,23 @@ __global__ void __launch_bounds__(TP_THREADS) atten_fwd_tpar_kernel(const AttenF
     float4 acc[TT];
 #pragma unroll
     for (int m = 0; m < TT; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int i = 0; i < k; ++i) {
-      const float4 v = ldg4(Vb + (long long)i * H);
+    constexpr int VB = 7;    // V rows in flight per thread (global-load latency, not bandwidth, bounds this phase)
+    for (int i0 = 0; i0 < k; i0 += VB) {
+      float4 v[VB];
 #pragma unroll
-      for (int m = 0; m < TT; ++m) {
-        const int tl = tg + ngrp * m;
-        if (tl < TC) {
-          const float al = als[tl * k + i];
-          acc[m].x = fmaf(al, v.x, acc[m].x); acc[m].y = fmaf(al, v.y, acc[m].y);
-          acc[m].z = fmaf(al, v.z, acc[m].z); acc[m].w = fmaf(al, v.w, acc[m].w);
+      for (int u = 0; u < VB; ++u) v[u] = i0 + u < k ? ldg4(Vb + (long long)(i0 + u) * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < VB; ++u) {
+        if (i0 + u < k) {
+#pragma unroll
+          for (int m = 0; m < TT; ++m) {
+            const int tl = tg + ngrp * m;
+            if (tl < TC) {
+              const float al = als[tl * k + i0 + u];
+              acc[m].x = fmaf(al, v[u].x, acc[m].x); acc[m].y = fmaf(al, v[u].y, acc[m].y);
+              acc[m].z = fmaf(al, v[u].z, acc[m].z); acc[m].w = fmaf(al, v[u].w, acc[m].w);
+            }
+          }
         }
       }
     }

@@ -344,10 +344,10 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long n_cols
 // attention sub-stage shared by aa_atten_forward / aa_adaptive_forward / aa_decoder_forward
 static int atten_stage(const Ctx& c, const aa_dims& d, Mat Wv, Mat Wg, Mat Ws, const float* att_wh, Mat V, Mat h, Mat s, float* P,
                        float* q, float* r, float* c_hat, float* ctx, float* u, bf16* u16, float* alpha, float* beta,
-                       bool have_P = false) {
+                       bool have_P = false, bool have_q = false) {
   const int N = d.B * d.T;
   if (!have_P) AA_TRY(mm_nt(c, "gemm_P", d.B * d.k, d.a, d.H, V, Wv, P, d.a, nullptr, 0, nullptr, nullptr));   // :34
-  AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, h, Wg, q, d.a, nullptr, 0, nullptr, nullptr));           // :35
+  if (!have_q) AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, h, Wg, q, d.a, nullptr, 0, nullptr, nullptr));           // :35
   AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, s, Ws, r, d.a, q, d.a, nullptr, nullptr));               // :45
   AttenFwdArgs p{};
   p.B = d.B; p.T = d.T; p.k = d.k; p.a = d.a; p.H = d.H;
@@ -628,12 +628,16 @@ static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const flo
   if (hT) AA_TRY(launch_copy2d(hT, H, sv.hiddens + (size_t)(T - 1) * H, (long long)T * H, B, H, st));
   if (cT) AA_TRY(launch_copy2d(cT, H, sv.cells + (size_t)(T - 1) * H, (long long)T * H, B, H, st));
   AA_TRY(stream_dep(side, SIDE_EVENTS - 1, cs.st, st));       // main lane joins the side lane
+  // q = h W_g^T only needs the hidden states: it runs on the side lane next to the sentinel's recurrent half
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
+  AA_TRY(mm_nt(cs, "gemm_qr", N, d->a, H, M2(sv.hiddens, H, sv.hid16, H), Wg, sv.q, d->a, nullptr, 0, nullptr, nullptr));   // :35
   // sentinel                                                   adaptive_attention.py:116-125, 75-85
   if (T > 1) AA_TRY(mm_nt(cx, "gemm_sentinel_h", N, H, H, M2(sv.hs_prev, H, sv.hsprev16, H), Wh, sv.g, H, sv.g, H, nullptr, nullptr));
   AA_TRY(launch_sentinel_fwd(sv.g, sv.cells, sv.g, sv.s, sv.s16, (long long)N * H, st));
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 1, cs.st, st));       // q is ready
   // attention + vocabulary projection                          adaptive_attention.py:128-132
   AA_TRY(atten_stage(cx, *d, Wv, Wg, Ws, w->att_wh, M2(V, H, sv.V16, H), M2(sv.hiddens, H, sv.hid16, H), M2(sv.s, H, sv.s16, H), sv.P,
-                     sv.q, sv.r, nullptr, sv.ctx, sv.u, sv.u16, alpha, beta, /*have_P=*/true));
+                     sv.q, sv.r, nullptr, sv.ctx, sv.u, sv.u16, alpha, beta, /*have_P=*/true, /*have_q=*/true));
   if (row_index) {   // only the rows pack_padded_sequence keeps, already in packed order (baseline_attention.py:228, Q13)
     if (n_rows == 0) return AA_OK;
     gather_rows2_kernel<<<(unsigned)n_rows, 128, 0, st>>>(sv.u, tc ? sv.u16 : nullptr, reinterpret_cast<const long long*>(row_index), H,

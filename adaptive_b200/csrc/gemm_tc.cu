@@ -470,6 +470,8 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
     AA_REQUIRE(g.elem_size == 4 && !g.a_mn && !g.b_mn, "tcgen05 GEMM: split (3xTF32) mode needs K-major fp32 operands");
     AA_REQUIRE(g.K % 32 == 0, "tcgen05 GEMM: split mode needs K (per half) padded to a multiple of 32 (got %d)", g.K);
     // the arg-max partial layout [M, ceil(N / tile_n)] is part of the contract: tile_n = gemm_tc_argmax_tile_n(N)
+    // (256-column tiles -- 128 cycles per MMA for twice the columns -- were measured SLOWER here: only two 96 KB stages fit
+    //  and the TMA feed, ~50 B/clk per SM, becomes the bound: vocabulary GEMM 224 us against 205 us, r01_v33)
     if (g.N > 64) return launch_cfg<128, 4, 3, false, false, true>(g, st);
     return launch_cfg<64, 4, 4, false, false, true>(g, st);
   }
