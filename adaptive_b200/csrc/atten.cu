@@ -463,26 +463,31 @@ __global__ void __launch_bounds__(TP_THREADS) atten_fwd_tpar_kernel(const AttenF
 //   NV = float4 chunks of 128 columns a lane holds of one V row (H <= 128 * NV), RI = regions per thread in the score
 //   backward (k <= (TP_THREADS / a) * RI)
 template <int NV, int RI>
-__global__ void __launch_bounds__(TP_THREADS) atten_bwd_tpar_kernel(const AttenBwdArgs p) {
+__global__ void __launch_bounds__(TP_THREADS) atten_bwd_tpar_kernel(const AttenBwdArgs p, int t_per_cta) {
   extern __shared__ __align__(16) float sm[];
-  const int k = p.k, a = p.a, H = p.H, T = p.T;
+  const int k = p.k, a = p.a, H = p.H;
+  // this CTA's steps [t_begin, t_begin + T); with more than one CTA per image dV, dP are accumulated with atomics
+  const int t_begin = blockIdx.y * t_per_cta;
+  const int T = min(p.T, t_begin + t_per_cta) - t_begin;
+  const bool atomic_out = gridDim.y > 1;
+  const int TS = t_per_cta;              // shared-memory strides are sized for the largest chunk
   float* dcs = sm;                       // [T*H]   dctx_t = (1-beta_t) dc_hat_t          (16-byte aligned rows)
-  float* Ps = dcs + (size_t)T * H;       // [k*a]
+  float* Ps = dcs + (size_t)TS * H;      // [k*a]
   float* whs = Ps + k * a;               // [a]
   float* qs = whs + a;                   // [T*a]
-  float* rs = qs + T * a;                // [T*a]
-  float* als = rs + T * a;               // [T*k]
-  float* dzs = als + T * k;              // [T*k]   d_alpha, then dz
-  float* dqs = dzs + T * k;              // [T*a]   sum_i dp_i (shared-memory atomics)
-  float* drs = dqs + T * a;              // [T*a]
-  float* dwhs = drs + T * a;             // [a]
+  float* rs = qs + TS * a;               // [T*a]
+  float* als = rs + TS * a;              // [T*k]
+  float* dzs = als + TS * k;             // [T*k]   d_alpha, then dz
+  float* dqs = dzs + TS * k;             // [T*a]   sum_i dp_i (shared-memory atomics)
+  float* drs = dqs + TS * a;             // [T*a]
+  float* dwhs = drs + TS * a;            // [a]
   float* bts = dwhs + a;                 // [T]
-  float* dbs = bts + T;                  // [T]     dbeta
-  float* dzsent = dbs + T;               // [T]
+  float* dbs = bts + TS;                 // [T]     dbeta
+  float* dzsent = dbs + TS;              // [T]
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long row0 = (long long)b * T;
+  const long long row0 = (long long)b * p.T + t_begin;
   const float* Pb = p.P + (long long)b * k * a;
   for (int i = tid; i < k * a; i += TP_THREADS) Ps[i] = Pb[i];
   for (int j = tid; j < a; j += TP_THREADS) { whs[j] = p.wh[j]; dwhs[j] = 0.f; }
@@ -594,8 +599,11 @@ __global__ void __launch_bounds__(TP_THREADS) atten_bwd_tpar_kernel(const AttenB
       for (int ii = 0; ii < RI; ++ii) {
         const int i = g + ii * NG;
         if (i < k) {
-          dPb[i * a + j] = dP[ii];
-          if (p.dP16) p.dP16[((long long)b * k + i) * p.a_pad + j] = __float2bfloat16(dP[ii]);
+          if (atomic_out) atomicAdd(dPb + i * a + j, dP[ii]);
+          else {
+            dPb[i * a + j] = dP[ii];
+            if (p.dP16) p.dP16[((long long)b * k + i) * p.a_pad + j] = __float2bfloat16(dP[ii]);
+          }
         }
       }
     }
@@ -617,7 +625,8 @@ __global__ void __launch_bounds__(TP_THREADS) atten_bwd_tpar_kernel(const AttenB
           acc.x = fmaf(al, d.x, acc.x); acc.y = fmaf(al, d.y, acc.y);
           acc.z = fmaf(al, d.z, acc.z); acc.w = fmaf(al, d.w, acc.w);
         }
-        *reinterpret_cast<float4*>(dVb + (long long)i * H) = acc;
+        if (atomic_out) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dVb + (long long)i * H), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+        else *reinterpret_cast<float4*>(dVb + (long long)i * H) = acc;
       }
     }
   }
@@ -639,8 +648,8 @@ __global__ void __launch_bounds__(TP_THREADS) atten_bwd_tpar_kernel(const AttenB
 size_t fwd_tpar_smem(const AttenFwdArgs& p, int t_per) {
   return sizeof(float) * ((size_t)p.k * p.a + p.a + (size_t)t_per * (2 * p.a + (p.k + 1) + p.k + 1) + 4);
 }
-size_t bwd_tpar_smem(const AttenBwdArgs& p) {
-  return sizeof(float) * ((size_t)p.T * p.H + (size_t)p.k * p.a + 2 * p.a + (size_t)p.T * (4 * p.a + 2 * p.k + 3) + 4);
+size_t bwd_tpar_smem(const AttenBwdArgs& p, int t_per) {
+  return sizeof(float) * ((size_t)t_per * p.H + (size_t)p.k * p.a + 2 * p.a + (size_t)t_per * (4 * p.a + 2 * p.k + 3) + 4);
 }
 
 template <int TT>
@@ -657,14 +666,19 @@ int launch_fwd_tpar(const AttenFwdArgs& p, int t_per, size_t smem, cudaStream_t 
 }
 
 template <int NV, int RI>
-int launch_bwd_tpar(const AttenBwdArgs& p, size_t smem, cudaStream_t s) {
+int launch_bwd_tpar(const AttenBwdArgs& p, int t_per, size_t smem, cudaStream_t s) {
   auto kern = atten_bwd_tpar_kernel<NV, RI>;
   static size_t attr = 0;
   if (smem > attr) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  kern<<<p.B, TP_THREADS, smem, s>>>(p);
+  const int ny = ceil_div(p.T, t_per);
+  if (ny > 1) {   // several CTAs per image: dV / dP are accumulated
+    AA_CHECK_CUDA(cudaMemsetAsync(p.dV, 0, sizeof(float) * (size_t)p.B * p.k * p.H, s));
+    AA_CHECK_CUDA(cudaMemsetAsync(p.dP, 0, sizeof(float) * (size_t)p.B * p.k * p.a, s));
+  }
+  kern<<<dim3(p.B, ny), TP_THREADS, smem, s>>>(p, t_per);
   AA_CHECK_LAUNCH("atten_bwd_tpar");
   return AA_OK;
 }
@@ -679,8 +693,20 @@ int launch_atten_fwd(const AttenFwdArgs& p, cudaStream_t s) {
   if (!g_atten_sequential && p.H <= 2048 && TP_THREADS / (p.H / 4) >= 1) {
     const int ngrp = TP_THREADS / (p.H / 4);
     int t_per = p.T < ngrp * 10 ? p.T : ngrp * 10;
-    // few images: split the steps over more CTAs so that the grid still covers the chip
-    while (t_per > 1 && (long long)p.B * ceil_div(p.T, t_per) < num_sms() && t_per > ngrp) t_per = ceil_div(t_per, 2);
+    // few images: split the steps over more CTAs, aiming at one full wave of two co-resident CTAs per SM
+    {
+      const long long slots = 2LL * num_sms();
+      int best = t_per;
+      double best_cost = 1e30;
+      for (int y = 1; y <= p.T; ++y) {
+        const int tp = ceil_div(p.T, y);
+        if (tp > ngrp * 10) continue;
+        const long long ctas = (long long)p.B * ceil_div(p.T, tp);
+        const double cost = (double)((ctas + slots - 1) / slots) * (1.5 + tp) * (ctas > num_sms() ? 1.25 : 1.0);
+        if (cost < best_cost) { best_cost = cost; best = tp; }
+      }
+      t_per = best;
+    }
     while (t_per > 1 && fwd_tpar_smem(p, t_per) > 160 * 1024) --t_per;
     const size_t smem_tp = fwd_tpar_smem(p, t_per);
     if (smem_tp <= 160 * 1024) {
@@ -713,13 +739,18 @@ int launch_atten_bwd(const AttenBwdArgs& p, cudaStream_t s) {
   AA_REQUIRE(p.a <= 32 * MAXJ, "atten_bwd: attention dim a=%d exceeds %d", p.a, 32 * MAXJ);
   if (p.B == 0 || p.T == 0) return AA_OK;
   // step-parallel kernel: one CTA per image with every step inside (dV / dP written once, no atomics)
-  if (!g_atten_sequential && p.H <= 1024 && p.a <= TP_THREADS && bwd_tpar_smem(p) <= 200 * 1024) {
+  if (!g_atten_sequential && p.H <= 1024 && p.a <= TP_THREADS) {
+    // steps per CTA: all of them when the images alone cover the chip, else split (dV / dP then go through atomics);
+    // shrink further until the chunk fits shared memory
+    int t_per = p.T;
+    if ((long long)p.B * 4 < 3LL * num_sms() && p.T > 1) t_per = ceil_div(p.T, (int)((2 * num_sms()) / p.B));   // ~two CTAs per SM
+    while (t_per > 1 && bwd_tpar_smem(p, t_per) > 100 * 1024) --t_per;     // (<= 100 KB: two CTAs per SM)
     const int ri = ceil_div(p.k, TP_THREADS / p.a);
-    const size_t smem_tp = bwd_tpar_smem(p);
-    if (ri <= 24) {
+    const size_t smem_tp = bwd_tpar_smem(p, t_per);
+    if (ri <= 24 && smem_tp <= 200 * 1024) {
       const bool wide = p.H > 512;
-      if (ri <= 6) return wide ? launch_bwd_tpar<8, 6>(p, smem_tp, s) : launch_bwd_tpar<4, 6>(p, smem_tp, s);
-      return wide ? launch_bwd_tpar<8, 24>(p, smem_tp, s) : launch_bwd_tpar<4, 24>(p, smem_tp, s);
+      if (ri <= 6) return wide ? launch_bwd_tpar<8, 6>(p, t_per, smem_tp, s) : launch_bwd_tpar<4, 6>(p, t_per, smem_tp, s);
+      return wide ? launch_bwd_tpar<8, 24>(p, t_per, smem_tp, s) : launch_bwd_tpar<4, 24>(p, t_per, smem_tp, s);
     }
   }
   static bool attr_done = false;
