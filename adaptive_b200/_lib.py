@@ -67,6 +67,7 @@ SIGNATURES = {
     "aa_debug_set_atten_sequential": (c_int, [c_int]),
     "aa_debug_set_gemm_splitk": (c_int, [c_int]),
     "aa_debug_set_bptt_ksplit": (c_int, [c_int]),
+    "aa_debug_set_lstm_cluster": (c_int, [c_int, c_int]),
     "aa_linear_forward": (c_int, [c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "aa_gemm": (c_int, [c_int, c_int, c_int, c_int, P, c_int64, c_int, P, c_int64, c_int, P, c_int64, ctypes.c_float, P, P,
                         c_int64, P]),

@@ -408,7 +408,12 @@ int aa_profile_get(int i, char* name, int name_len, double* total_ms, int* launc
   return AA_OK;
 }
 
-int aa_debug_set_trace_buffer(void* dev_ptr) { return set_seq_trace_buffer(dev_ptr); }
+int aa_debug_set_trace_buffer(void* dev_ptr) {
+  AA_TRY(set_clk_trace_buffer(dev_ptr));
+  return set_seq_trace_buffer(dev_ptr);
+}
+
+int aa_debug_set_lstm_cluster(int on, int nacc) { return aa::set_lstm_cluster(on, nacc); }
 
 int aa_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
@@ -608,7 +613,13 @@ static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const flo
     ls.B = B; ls.T = T; ls.H = H; ls.w_hh = w->w_hh; ls.xg = sv.xg; ls.c0 = c0; ls.h016 = sv.h016;
     ls.hiddens = sv.hiddens; ls.cells = sv.cells; ls.acts = sv.acts; ls.hs_prev = sv.hs_prev;
     ls.hid16 = sv.hid16; ls.hsprev16 = sv.hsprev16; ls.whh_packed16 = sv.whh_pack16; ls.counters = sv.counters;
-    AA_PROF("lstm_seq_fwd", st, launch_lstm_seq_fwd(ls, st));
+    ls.whh16 = h.w_hh;
+    {   // cluster kernels (weights in tensor memory) where the shape allows, else the grid-barrier kernel
+      aa::ProfScope ps("lstm_seq_fwd", st);
+      int rc = launch_lstm_cluster_fwd(ls, st);
+      if (rc == AA_ERR_UNSUPPORTED) rc = launch_lstm_seq_fwd(ls, st);
+      if (rc != AA_OK) return rc;
+    }
   }
   for (int t = 0; t < T && !seq; ++t) {
     const Mat hp = t == 0 ? M2(h0 ? h0 : sv.zeros, H, sv.h016, H)
@@ -781,7 +792,13 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
     ls.dh_attn = sc.du; ls.dhs = T > 1 ? sc.dhs : nullptr; ls.dcell = sc.dcell; ls.d_hT = d_hT; ls.d_cT = d_cT;
     ls.acts = sv.acts; ls.cells = sv.cells; ls.c0 = c0; ls.dgates = sc.dgates; ls.dgates16 = sc.dgates16;
     ls.dh0 = dh0; ls.dc0 = dc0; ls.whhT16 = sc.whhT16; ls.counters = sc.counters;
-    AA_PROF("lstm_seq_bwd", st, launch_lstm_seq_bwd(ls, st));
+    ls.whh16 = sv.w16.w_hh;
+    {
+      aa::ProfScope ps("lstm_seq_bwd", st);
+      int rc = launch_lstm_cluster_bwd(ls, st);
+      if (rc == AA_ERR_UNSUPPORTED) rc = launch_lstm_seq_bwd(ls, st);
+      if (rc != AA_OK) return rc;
+    }
   }
   for (int t = T - 1; t >= 0 && !seq; --t) {
     const float* dh_rec_in = t == T - 1 ? d_hT : sc.dh_rec;

@@ -105,6 +105,7 @@ struct LstmSeqFwd {
   __nv_bfloat16 *hid16, *hsprev16;
   __nv_bfloat16* whh_packed16;        // scratch [4H*H]
   unsigned* counters;                 // scratch [ceil(B/128)]
+  const __nv_bfloat16* whh16;         // optional: plain bf16 copy of w_hh [4H,H] (operand of the cluster kernels)
 };
 int launch_lstm_seq_fwd(const LstmSeqFwd& p, cudaStream_t s);
 struct LstmSeqBwd {
@@ -115,10 +116,19 @@ struct LstmSeqBwd {
   float *dh0, *dc0;
   __nv_bfloat16* whhT16;              // scratch [H*4H]
   unsigned* counters;
+  const __nv_bfloat16* whh16;         // optional: plain bf16 copy of w_hh [4H,H] (operand of the cluster kernels)
 };
 int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t s);
 int set_seq_trace_buffer(void* dev_ptr);
 int set_bptt_ksplit_max(int ks);   // diagnostics: cap on the K-split (cluster size) of the BPTT kernel; 1 = no cluster   // diagnostics: [steps][8] uint64 globaltimer stamps of CTA (0,0); null = off
+
+// ---- lstm_cluster.cu (same recurrences inside thread-block clusters, weights in tensor memory; H in {128,256,512}) ----
+// Both return AA_ERR_UNSUPPORTED when the shape / device cannot run them: the caller then takes the lstm_seq.cu kernels.
+bool lstm_cluster_supported(int B, int H);
+int launch_lstm_cluster_fwd(const LstmSeqFwd& p, cudaStream_t s);
+int launch_lstm_cluster_bwd(const LstmSeqBwd& p, cudaStream_t s);
+int set_clk_trace_buffer(void* dev_ptr);
+int set_lstm_cluster(int on, int nacc);   // diagnostics: on = 0 never takes the cluster kernels; nacc = accumulators of the forward chain
 
 // ---- atten.cu --------------------------------------------------------------------------
 struct AttenFwdArgs {

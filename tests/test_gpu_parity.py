@@ -340,6 +340,59 @@ def test_bptt_cluster_ksplit_matches_single_cta(B, T, dims):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("nacc", [1, 4])
+@pytest.mark.parametrize("B,T,dims,states", [
+    (80, 18, CFG_A, True),                                   # BASELINE config 2: 8 clusters x 10 rows
+    (200, 5, CFG_A, True),                                   # more clusters than can be resident at once (waves), ragged last group
+    (3, 7, Dims(H=128, E=64, Vc=304, k=49), False),          # cluster of 4, no initial state, fewer rows than one quad
+    (37, 6, Dims(H=256, E=64, Vc=304, k=20), True),          # cluster of 8, two M-blocks
+    (1, 1, Dims(H=512, E=64, Vc=304, k=20), True),           # a single step
+])
+def test_cluster_recurrence_matches_grid_barrier_kernels(B, T, dims, states, nacc):
+    """bf16 recurrences: the cluster kernels (weights in tensor memory, h_t / partial dh exchanged through distributed shared
+    memory; lstm_cluster.cu) against the grid-barrier kernels (lstm_seq.cu) -- same bf16 operands, same fp32 accumulation,
+    only the summation order and the transposed tile orientation differ."""
+    from adaptive_b200 import _lib
+    lib = _lib.load()
+    w = make_weights(dims, seed=61, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=62)
+    rng = np.random.Generator(np.random.PCG64(6))
+    dS = torch.from_numpy((rng.standard_normal((B, T, dims.Vc)) / dims.Vc).astype(np.float32)).cuda()
+
+    def run():
+        W = dev_weights(w, requires_grad=True)
+        V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
+        if not states:
+            h0 = c0 = None
+        scores, alpha, beta, hT, cT = F_aa.decoder_forward(W, V, v_g, cap, h0, c0, precision="bf16")
+        ((scores * dS).sum() + 0.3 * hT.sum() - 0.2 * cT.sum()).backward()
+        torch.cuda.synchronize()
+        outs = {"scores": scores, "alpha": alpha, "beta": beta, "hT": hT, "cT": cT}
+        outs.update({"d" + key: t.grad for key, t in zip(grad_key_order(), W)})
+        outs.update({"dV": V.grad, "dv_g": v_g.grad})
+        if states:
+            outs.update({"dh0": h0.grad, "dc0": c0.grad})
+        return {k: v.detach().cpu().numpy() for k, v in outs.items()}
+
+    try:
+        lib.aa_debug_set_lstm_cluster(1, nacc)
+        n0 = lib.aa_launch_count()
+        new = run()
+        n_new = lib.aa_launch_count() - n0
+        lib.aa_debug_set_lstm_cluster(0, 1)
+        n0 = lib.aa_launch_count()
+        old = run()
+        n_old = lib.aa_launch_count() - n0
+    finally:
+        lib.aa_debug_set_lstm_cluster(1, 1)
+    # the cluster path needs neither the packed nor the transposed weight copy: two launches fewer
+    assert n_new == n_old - 2, (n_new, n_old)
+    # bf16 rounding of h_t / dgates_t (2^-9 relative) amplifies last-bit differences of the fp32 sums: one flipped rounding
+    # moves an operand element by 4e-3 of its value; measured worst case 1.3e-3 of the largest entry
+    bad = {k: rel_err(new[k], old[k]) for k in new if not rel_err(new[k], old[k]) < 3e-3}
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("prec,tol", [("fp32", 1e-6), ("bf16", 2e-3)])
 def test_packed_forward_backward_equals_pack_of_full(prec, tol):
     """Encoder2Decoder.forward with the fused packing (vocabulary projection over the kept rows only) against

@@ -17,9 +17,13 @@ inp = make_inputs(CFG_A, B, T)
 W = dev_weights(w, requires_grad=True)
 V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=True)
 lib = _lib.load()
+import os  # noqa: E402
+if "AA_TRACE_NACC" in os.environ:   # accumulators of the forward cluster kernel's MMA chain (1, 2 or 4)
+    _lib.check(lib.aa_debug_set_lstm_cluster(1, int(os.environ["AA_TRACE_NACC"])), "nacc")
 names = ["bar_passed", "tma_issued", "stage0_landed", "mma_commit", "acc_seen", "cell_done", "warps_met", "published"]
-# (cluster kernels: 0 step start, 1 MMAs issued, 2 accumulator seen, 3 cell math done, 4 barrier "MMAs done" passed,
-#  5 slice delivered + arrive, 6 outputs stored)
+# cluster kernels (lstm_cluster.cu, the default where H in {128,256,512}): 0 operand complete (MMA warp), 1 MMAs issued,
+#  2 accumulator seen, 3 activations staged, 4 cell done (fwd) / dgates staged (bwd), 5 slice delivered / partials sent,
+#  6 partials received (bwd), 7 outputs stored.  AA_LSTM_CLUSTER=0 in the environment traces the grid-barrier kernels.
 for it in range(3):
     buf = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
     _lib.check(lib.aa_debug_set_trace_buffer(F_aa._ptr(buf)), "trace")
