@@ -130,14 +130,15 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
                "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
                : "memory");
 }
-// K-major operand without swizzle ("interleaved" canonical layout): 8-row x 16-byte core matrices, lbo = byte distance of
-// the two core matrices of one MMA along K, sbo = byte distance of 8-row groups
-__device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// K-major operand with the 64-byte swizzle: rows of 64 B (32 bf16), 16-byte chunk index ^= (row >> 1) & 3, 8-row groups
+// sbo bytes apart (512 when dense); layout type 4
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)1 << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -177,11 +178,14 @@ struct ClFwdArgs {
   bf16 *hid16, *hsprev16;
 };
 
-// Operand layout of h_{t-1} in shared memory (no swizzle): [slice c of 32 units][16-byte chunk ch of 8 units (4)][row (16)][16 B],
-// so that the slice CTA c produces is one contiguous 1 KB block (4 x 256 B) in every receiver: it is delivered with bulk
-// shared->shared::cluster copies whose bytes the receiver's mbarrier counts -- no per-thread remote stores, no release fence
-// waiting for their acknowledgements, and the data arrives through the async proxy the tensor core reads with.
-constexpr uint32_t SLICE_BYTES = 4 * NB * 16;   // 1 KB
+// Operand layout of h_{t-1} in shared memory: [slice c of 32 units][row (16)][64 B] with the 64-byte swizzle (a row of the
+// K-major operand is exactly one CTA's 32 units), so that the slice CTA c produces is one contiguous block in every
+// receiver: it is delivered with ONE bulk shared->shared::cluster copy per peer whose bytes the receiver's mbarrier counts --
+// no per-thread remote stores, no release fence waiting for their acknowledgements, and the data arrives through the async
+// proxy the tensor core reads with.  (A layout without swizzle is contiguous too, but its MMAs ran at 1.8 us per 32 against
+// 1.15 us with the 128-byte swizzle: profiles/r01_v36_lstm_trace.txt vs r01_v38_lstm_trace.txt.)
+constexpr uint32_t SLICE_BYTES = NB * 64;       // 1 KB
+__device__ __forceinline__ uint32_t sw64_off(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 template <int NACC>
 __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ClFwdArgs a) {
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
   const uint32_t c = cluster_ctarank();
   const int m0 = blockIdx.y * a.rpg;
   const int rows = min(a.rpg, a.B - m0);
-  const uint32_t step_bytes = (uint32_t)(CL * 4 * rows * 16);        // what one step delivers into this CTA
+  const uint32_t step_bytes = (uint32_t)(CL * rows * 64);            // what one step delivers into this CTA
 
   if (warp == 4 && lane == 0) {
     mbar_init(w_full, 1);
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
   for (int i = threadIdx.x; i < rows * (H / 8); i += CLK_THREADS) {
     const int r = i / (H / 8), cc = i - r * (H / 8);               // cc = 16-byte chunk (8 units) of row r
     const uint4 v = *reinterpret_cast<const uint4*>(a.h016 + (long long)(m0 + r) * H + cc * 8);
-    sts128(sB + (uint32_t)(cc >> 2) * SLICE_BYTES + (uint32_t)(cc & 3) * (NB * 16) + (uint32_t)r * 16u, v);
+    sts128(sB + (uint32_t)(cc >> 2) * SLICE_BYTES + sw64_off(r, cc & 3), v);
   }
   tc_fence_before();
   __syncthreads();
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
 
   if (warp == 4) {
     // ===== MMA issuer (converged warp, one elected lane) =====
-    const uint64_t desc0 = make_smem_desc_noswz(0, NB * 16, 128);
+    const uint64_t desc0 = make_smem_desc_sw64(0, 512);
     fence_proxy_async_smem();                    // h_0 was written with st.shared (generic proxy)
     for (int t = 0; t < T; ++t) {
       const uint32_t p = (uint32_t)t & 1u;
@@ -269,10 +273,10 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
       tc_fence_after();
       if (elect_one()) {
         if (t + 1 < T) mbar_expect_tx(&full[p ^ 1u], step_bytes);            // arm the buffer h_t will be delivered into
-        for (int ks = 0; ks < 4 * KB; ++ks) {     // k-step = 16 units = chunks 2*(ks&1), +1 of slice ks/2
-          // (inside a cluster the shared-window address of ranks >= 1 carries the rank above bit 18: keep the 14-bit field clean,
-          //  the bits above it are the leading byte offset, which this layout -- unlike the swizzled ones -- uses)
-          const uint64_t db = desc0 + (((sB + (p * CL + (uint32_t)(ks >> 1)) * SLICE_BYTES + (uint32_t)(ks & 1) * (2 * NB * 16)) & 0x3FFFFu) >> 4);
+        for (int ks = 0; ks < 4 * KB; ++ks) {     // k-step = 16 units = half a row (32 B) of slice ks/2
+          // (inside a cluster the shared-window address of ranks >= 1 carries the rank in its upper bits: keep the 14-bit
+          //  start-address field clean)
+          const uint64_t db = desc0 + (((sB + (p * CL + (uint32_t)(ks >> 1)) * SLICE_BYTES + (uint32_t)(ks & 1) * 32u) & 0x3FFFFu) >> 4);
           tc_mma_ts(tmem_base + D_COL + (uint32_t)((ks % NACC) * NB), tmem_base + (uint32_t)(ks * 8), db, IDESC, ks >= NACC ? 1u : 0u);
         }
         tc_commit(tmem_full);
@@ -339,19 +343,18 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
           const float og = lds_f32(sAct + (uint32_t)(((3 * NB + b) * 32 + u) * 4));
           creg[i] = fg * creg[i] + ig * gg;
           hv[i] = og * tanhf_fast(creg[i]);
-          sts_u16(stage + (uint32_t)((u >> 3) * (NB * 16) + b * 16 + (u & 7) * 2), bf16_bits(hv[i]));
+          sts_u16(stage + sw64_off(b, u >> 3) + (uint32_t)((u & 7) * 2), bf16_bits(hv[i]));
         }
       }
       if (t + 1 < T) {
         fence_proxy_async_smem();                // the staged slice is read by the bulk-copy engine (async proxy)
         named_bar<128>(1);
         if (threadIdx.x == 0) cl_trace(t, 4);
-        // this CTA's slice of h_t into every CTA's operand buffer of the other parity: one copy per (peer, chunk)
-        if ((int)threadIdx.x < CL * 4) {
-          const uint32_t peer = threadIdx.x >> 2, ch = threadIdx.x & 3;
+        // this CTA's slice of h_t into every CTA's operand buffer of the other parity: one copy per peer
+        if ((int)threadIdx.x < CL) {
+          const uint32_t peer = threadIdx.x;
           const uint32_t pn = ((uint32_t)t + 1u) & 1u;
-          bulk_copy_to_peer(mapa_u32(sB + (pn * CL + c) * SLICE_BYTES + ch * (NB * 16), peer), stage + ch * (NB * 16), (uint32_t)rows * 16u,
-                            mapa_u32(smem_u32(&full[pn]), peer));
+          bulk_copy_to_peer(mapa_u32(sB + (pn * CL + c) * SLICE_BYTES, peer), stage, (uint32_t)rows * 64u, mapa_u32(smem_u32(&full[pn]), peer));
         }
       } else {
         named_bar<128>(1);                       // (sAct is rewritten by the next step: keep the step structure)
@@ -645,7 +648,7 @@ inline size_t bwd_smem(int H, int RP) {
 }
 
 int g_lstm_cluster = 1;    // diagnostics (aa_debug_set_lstm_cluster): 0 = always take the grid-barrier kernels of lstm_seq.cu
-int g_lstm_cluster_nacc = 1;
+int g_lstm_cluster_nacc = 4;
 
 // Plain cluster launch; co-residency of a cluster is the hardware's business, clusters are independent of each other.
 int launch_clk(const void* kern, int CL, int groups, size_t smem, cudaStream_t st, void** args, bool query_only, int* max_clusters) {
@@ -720,7 +723,7 @@ int set_clk_trace_buffer(void* dev_ptr) {
 
 int set_lstm_cluster(int on, int nacc) {
   g_lstm_cluster = on ? 1 : 0;
-  g_lstm_cluster_nacc = nacc == 4 ? 4 : nacc == 2 ? 2 : 1;
+  g_lstm_cluster_nacc = nacc == 1 ? 1 : nacc == 2 ? 2 : 4;   // (anything else: the default)
   return AA_OK;
 }
 

@@ -117,7 +117,7 @@ int aa_debug_set_gemm_splitk(int on);
 int aa_debug_set_bptt_ksplit(int ks);
 /* Diagnostics: on == 0 makes the bf16 recurrences always take the grid-barrier kernels (lstm_seq.cu) instead of the
  * cluster kernels with the weights in tensor memory (lstm_cluster.cu); nacc in {1,2,4} = partial accumulators the
- * forward cluster kernel spreads its MMA chain over.  Default: on, 1. */
+ * forward cluster kernel spreads its MMA chain over (anything else: the default, 4).  Default: on. */
 int aa_debug_set_lstm_cluster(int on, int nacc);
 
 /* ---- stage operators (the nn.Module sub-blocks) ------------------------------------- */

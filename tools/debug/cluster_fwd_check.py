@@ -17,14 +17,14 @@ for B, T in ((80, 1), (80, 2), (80, 3), (80, 18), (5, 4)):
     inp = make_inputs(CFG_A, B, T, seed=62)
     out = {}
     for mode in (1, 0):
-        lib.aa_debug_set_lstm_cluster(mode, 1)
+        lib.aa_debug_set_lstm_cluster(mode, 0)
         W = dev_weights(w, requires_grad=False)
         V, v_g, h0, c0, cap = dev_inputs(inp, requires_grad=False)
         with torch.no_grad():
             scores, alpha, beta, hT, cT = F_aa.decoder_forward(W, V, v_g, cap, h0, c0, precision="bf16")
         torch.cuda.synchronize()
         out[mode] = (hT.cpu().numpy(), cT.cpu().numpy(), scores.cpu().numpy())
-    lib.aa_debug_set_lstm_cluster(1, 1)
+    lib.aa_debug_set_lstm_cluster(1, 0)
     h1, c1, s1 = out[1]
     h0_, c0_, s0 = out[0]
     bad = ~np.isfinite(h1)
