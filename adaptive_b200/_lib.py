@@ -94,6 +94,8 @@ SIGNATURES = {
     "aa_pack_rows": (c_int, [P, c_int64, P, c_int64, P, P]),
     "aa_unpack_rows": (c_int, [P, c_int64, P, c_int64, c_int64, P, P]),
     "aa_cross_entropy": (c_int, [P, c_int64, c_int64, P, P, P, P]),
+    "aa_scale_unless_one": (c_int, [P, P, c_int64, P]),
+    "aa_copy_multi": (c_int, [c_int, P, P, P, P]),
     "aa_cross_entropy_denom": (c_int, [P, c_int64, c_int64, P, c_int64, P, P, P]),
     "aa_decode_workspace_bytes": (c_size_t, [_D, c_int]),
     "aa_greedy_decode": (c_int, [_D, _W, P, P, P, P, c_int, P, P, P, P, P, c_size_t, P]),

@@ -674,7 +674,7 @@ int launch_bwd_tpar(const AttenBwdArgs& p, int t_per, size_t smem, cudaStream_t 
     attr = smem;
   }
   const int ny = ceil_div(p.T, t_per);
-  if (ny > 1) {   // several CTAs per image: dV / dP are accumulated
+  if (ny > 1 && !p.prezeroed) {   // several CTAs per image: dV / dP are accumulated
     AA_CHECK_CUDA(cudaMemsetAsync(p.dV, 0, sizeof(float) * (size_t)p.B * p.k * p.H, s));
     AA_CHECK_CUDA(cudaMemsetAsync(p.dP, 0, sizeof(float) * (size_t)p.B * p.k * p.a, s));
   }
@@ -771,7 +771,7 @@ int launch_atten_bwd(const AttenBwdArgs& p, cudaStream_t s) {
   while (TC > 1 && bytes(TC) > budget) --TC;
   AA_REQUIRE(bytes(TC) <= budget, "atten_bwd: k=%d a=%d H=%d does not fit shared memory", p.k, p.a, p.H);
   const int atomic_out = ny > 1 ? 1 : 0;
-  if (atomic_out) {
+  if (atomic_out && !p.prezeroed) {
     AA_CHECK_CUDA(cudaMemsetAsync(p.dV, 0, sizeof(float) * (size_t)p.B * p.k * p.H, s));
     AA_CHECK_CUDA(cudaMemsetAsync(p.dP, 0, sizeof(float) * (size_t)p.B * p.k * p.a, s));
   }

@@ -41,13 +41,13 @@ int num_sms() {
 // The backward has work that is off the critical path (every weight-gradient contraction, dV, the sentinel's
 // dx): it runs on a library-owned non-blocking stream, forked from / joined back into the caller's stream with
 // events, so the call still looks like ONE stream-ordered operation to the caller (and captures into a CUDA
-// graph as a fork/join).  One side stream + event pool per (host thread, device), created lazily -- the first
+// graph as a fork/join).  Three side lanes + event pool per (host thread, device), created lazily -- the first
 // call on a thread must therefore not be made under stream capture (same rule as the one-time
 // cudaFuncSetAttribute calls of the kernels).  AA_NO_SIDE_STREAM=1 serialises everything on the caller's stream.
 namespace {
-constexpr int SIDE_EVENTS = 12;
+constexpr int SIDE_EVENTS = 32;
 struct SideCtx {
-  cudaStream_t side = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;   // lanes A, B, C
   cudaEvent_t ev[SIDE_EVENTS] = {};
   bool ready = false;
 };
@@ -68,6 +68,8 @@ static int get_side(SideCtx** out) {
   SideCtx& c = g_side[dev];
   if (!c.ready) {
     AA_CHECK_CUDA(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    AA_CHECK_CUDA(cudaStreamCreateWithFlags(&c.side2, cudaStreamNonBlocking));
+    AA_CHECK_CUDA(cudaStreamCreateWithFlags(&c.side3, cudaStreamNonBlocking));
     for (int i = 0; i < SIDE_EVENTS; ++i) AA_CHECK_CUDA(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
     c.ready = true;
   }
@@ -573,15 +575,23 @@ static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const flo
   const Ctx cx{d->precision, st};
   const bool tc = cx.tc();
   const W16& h = sv.w16;
-  if (tc) {   // bf16 copies of the GEMM weights (one launch) and of V, h0
-    CastSegs cs{};
+  // Side lane, forked at once: what the recurrence does not need -- the bf16 copies of every weight but the LSTM's and of V,
+  // P = V W_v^T and the sentinel gate's input half -- runs next to the main lane's casts, gate GEMM and recurrence.
+  SideCtx* side = nullptr;
+  AA_TRY(get_side(&side));
+  const Ctx cs{d->precision, side ? side->side : st};
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
+  if (tc) {   // bf16 copies of the GEMM weights and of V, h0
     const float* srcs[8] = {w->w_ih, w->w_hh, w->sen_wx, w->sen_wh, w->att_wv, w->att_wg, w->att_ws, w->mlp_w};
     bf16* dsts[8] = {h.w_ih, h.w_hh, h.sen_wx, h.sen_wh, h.att_wv, h.att_wg, h.att_ws, h.mlp_w};
     const long long ns[8] = {4LL * H * 2 * E, 4LL * H * H, (long long)H * 2 * E, (long long)H * H, (long long)d->a * H,
                              (long long)d->a * H, (long long)d->a * H, (long long)d->Vc * H};
-    for (int i = 0; i < 8; ++i) { cs.src[i] = srcs[i]; cs.dst[i] = dsts[i]; cs.n[i] = ns[i]; }
-    AA_PROF("cast_weights", st, launch_cast_multi(cs, 8, st));
-    AA_PROF("cast_inputs", st, launch_cast2d(V, H, sv.V16, H, (long long)B * d->k, H, st));
+    CastSegs c_main{}, c_side{};
+    for (int i = 0; i < 2; ++i) { c_main.src[i] = srcs[i]; c_main.dst[i] = dsts[i]; c_main.n[i] = ns[i]; }
+    for (int i = 2; i < 8; ++i) { c_side.src[i - 2] = srcs[i]; c_side.dst[i - 2] = dsts[i]; c_side.n[i - 2] = ns[i]; }
+    AA_PROF("cast_weights", st, launch_cast_multi(c_main, 2, st));
+    AA_PROF("cast_weights", cs.st, launch_cast_multi(c_side, 6, cs.st));
+    AA_PROF("cast_inputs", cs.st, launch_cast2d(V, H, sv.V16, H, (long long)B * d->k, H, cs.st));
     if (h0) AA_PROF("cast_inputs", st, launch_cast2d(h0, H, sv.h016, H, B, H, st));
     else AA_CHECK_CUDA(cudaMemsetAsync(sv.h016, 0, sizeof(bf16) * (size_t)B * H, st));
     AA_CHECK_CUDA(cudaMemset2DAsync(sv.hsprev16, (size_t)T * H * 2, 0, (size_t)H * 2, B, st));
@@ -594,16 +604,11 @@ static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const flo
 
   // x = [embed(w); v_g]                                        baseline_attention.py:151-154
   AA_TRY(launch_build_x(cap, w->embed, v_g, sv.x, sv.x16, B, T, E, d->Vc, st));
-  // input halves of the LSTM gates and of the sentinel gate, batched over all T
-  AA_TRY(mm_nt(cx, "gemm_gates_in", N, 4 * H, 2 * E, X, Wih, sv.xg, 4 * H, nullptr, 0, w->b_ih, w->b_hh));
-  // Side lane: what the recurrence does not need -- the sentinel gate's input half and P = V W_v^T -- runs next to the
-  // persistent LSTM kernel (128 CTAs, latency-bound) instead of before / after it.
-  SideCtx* side = nullptr;
-  AA_TRY(get_side(&side));
-  const Ctx cs{d->precision, side ? side->side : st};
-  AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
-  AA_TRY(mm_nt(cs, "gemm_gates_in", N, H, 2 * E, X, Wx, sv.g, H, nullptr, 0, nullptr, nullptr));
   AA_TRY(mm_nt(cs, "gemm_P", B * d->k, d->a, H, M2(V, H, sv.V16, H), Wv, sv.P, d->a, nullptr, 0, nullptr, nullptr));   // :34
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 3, st, cs.st));       // (x is built)
+  // input halves of the LSTM gates (main lane) and of the sentinel gate (side lane), batched over all T
+  AA_TRY(mm_nt(cx, "gemm_gates_in", N, 4 * H, 2 * E, X, Wih, sv.xg, 4 * H, nullptr, 0, w->b_ih, w->b_hh));
+  AA_TRY(mm_nt(cs, "gemm_gates_in", N, H, 2 * E, X, Wx, sv.g, H, nullptr, 0, nullptr, nullptr));
   if (!h0 || !c0) AA_CHECK_CUDA(cudaMemsetAsync(sv.zeros, 0, sizeof(float) * (size_t)B * H, st));
   AA_CHECK_CUDA(cudaMemset2DAsync(sv.hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, B, st));   // h~_0 = 0 (Q2)
   // recurrence                                                 baseline_attention.py:167-178
@@ -704,18 +709,21 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
   const long long* cap = reinterpret_cast<const long long*>(captions);
   float* dVb = dV ? dV : sc.dV;
 
-  // Two lanes.  `cx` (the caller's stream) carries the critical path
-  //   dS -> du -> attention backward -> ds/dh -> sentinel backward -> dhs -> BPTT -> dx -> embedding scatter;
-  // `cs` (the library's side stream) carries everything nothing else waits for: the 11 weight-gradient
-  // contractions, dV += dP W_v and the sentinel's dx.  While the BPTT kernel (H/16 CTAs) walks its T dependent
-  // steps the rest of the chip works through the side lane.
+  // Four lanes.  `cx` (the caller's stream) carries the critical path
+  //   dS -> du -> attention backward -> ds -> sentinel backward -> dhs -> BPTT -> dx -> embedding scatter;
+  // the library's side lanes A, B (and C for the bias sums) carry everything nothing on that path waits for: the 11
+  // weight-gradient contractions, dV += dP W_v, dh = du + dq W_g (only the BPTT needs it) and the sentinel's dx.  One
+  // side lane serialised those ~14 small contractions and finished ~60 us after the main lane (profiles/r01_v40_bench.json:
+  // the side lane's kernels sum to more than the main lane's); small contractions leave most SMs idle, so independent
+  // ones now run next to each other.
   SideCtx* side = nullptr;
   AA_TRY(get_side(&side));
   const Ctx cx{d->precision, st};
-  const Ctx cs{d->precision, side ? side->side : st};
-  const cudaStream_t sd = cs.st;
+  const cudaStream_t sd = side ? side->side : st, sb = side ? side->side2 : st, sl = side ? side->side3 : st;
+  const Ctx cs{d->precision, sd}, cb{d->precision, sb};
   int evi = 0;
-  auto to_side = [&]() { return stream_dep(side, evi++, st, sd); };   // side lane waits for the main lane so far
+  auto dep = [&](cudaStream_t from, cudaStream_t to) { return stream_dep(side, evi++, from, to); };   // `to` waits for `from` so far
+  auto to_side = [&]() { return dep(st, sd); };
   auto bucket_ready = [&](int bucket, cudaStream_t on) -> int {
     if (ready_events && ready_events[bucket]) AA_CHECK_CUDA(cudaEventRecord((cudaEvent_t)ready_events[bucket], on));
     if (on_ready) on_ready(bucket, user);
@@ -729,6 +737,14 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
   const Mat Wv = M2(w->att_wv, H, h.att_wv, H), Wg = M2(w->att_wg, H, h.att_wg, H), Ws = M2(w->att_ws, H, h.att_ws, H);
   const Mat Wp = M2(w->mlp_w, H, h.mlp_w, H);
   const Mat X = M2(sv.x, 2 * E, sv.x16, 2 * E);
+  // zero-fills of everything that is accumulated into later (du, dV, dP, att_wh and the 10 MB embedding gradient) run on lane C
+  // now, next to the first contractions, instead of as memset nodes in front of their consumers on the critical path
+  AA_TRY(dep(st, sl));
+  if (row_index) AA_CHECK_CUDA(cudaMemsetAsync(sc.du, 0, sizeof(float) * (size_t)N * H, sl));
+  AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, sl));
+  AA_CHECK_CUDA(cudaMemsetAsync(dVb, 0, sizeof(float) * (size_t)B * k * H, sl));
+  AA_CHECK_CUDA(cudaMemsetAsync(sc.dP, 0, sizeof(float) * (size_t)B * k * a, sl));
+  AA_CHECK_CUDA(cudaMemsetAsync(gw->embed, 0, sizeof(float) * (size_t)Vc * E, sl));
   // db_p = column sums of dS, fused with the bf16 cast of dS                     adaptive_attention.py:132
   // (packed entry point: d_scores holds the NR = n_rows packed rows only; the other positions have no gradient)
   const int NR = row_index ? (int)n_rows : N;
@@ -737,53 +753,60 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
   const Mat dS = M2(d_scores, Vc, sc.dS16, Vc);
 
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
+  // (du is on the critical path: its contraction is enqueued before the weight gradient's so that it gets the SMs first)
   AA_TRY(to_side());
-  if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
-  else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
-  AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));
   if (row_index) {   // du rows of the packed positions, scattered back to [B,T,H] (zero elsewhere)
-    AA_CHECK_CUDA(cudaMemsetAsync(sc.du, 0, sizeof(float) * (size_t)N * H, st));
-    if (NR > 0) {
-      AA_TRY(mm_nn(cx, "gemm_vocab_dx", NR, H, Vc, dS, Wp, sc.dup, H, nullptr, 0));
-      pack_rows_kernel<<<(unsigned)NR, 128, 0, st>>>(sc.dup, H, reinterpret_cast<const long long*>(row_index), sc.du, 0);
-      AA_CHECK_LAUNCH("scatter_rows");
-    }
+    if (NR > 0) AA_TRY(mm_nn(cx, "gemm_vocab_dx", NR, H, Vc, dS, Wp, sc.dup, H, nullptr, 0));
   } else {
     AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, nullptr, 0));
   }
+  if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
+  else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
+  AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));
+  AA_TRY(dep(sl, st));                                         // the zero-fills are done
+  if (row_index && NR > 0) {
+    pack_rows_kernel<<<(unsigned)NR, 128, 0, st>>>(sc.dup, H, reinterpret_cast<const long long*>(row_index), sc.du, 0);
+    AA_CHECK_LAUNCH("scatter_rows");
+  }
   // attention                                                   adaptive_attention.py:34-56
-  AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, st));
   AttenBwdArgs ab{};
   ab.B = B; ab.T = T; ab.k = k; ab.a = a; ab.H = H;
   ab.P = sv.P; ab.q = sv.q; ab.r = sv.r; ab.s = sv.s; ab.V = V; ab.wh = w->att_wh;
   ab.alpha = alpha; ab.beta = beta; ab.ctx = sv.ctx; ab.dchat = sc.du; ab.d_alpha = d_alpha; ab.d_beta = d_beta;
   ab.ds = sc.ds; ab.dq = sc.dq; ab.dr = sc.dr; ab.dP = sc.dP; ab.dV = dVb; ab.dwh = gw->att_wh;
   ab.dq16 = tc ? sc.dq16 : nullptr; ab.dr16 = tc ? sc.dr16 : nullptr; ab.dP16 = nullptr; ab.a_pad = ap;
+  ab.prezeroed = 1;
   AA_PROF("atten_bwd", st, launch_atten_bwd(ab, st));
   const Mat dR = M2(sc.dr, a, sc.dr16, ap), dQ = M2(sc.dq, a, sc.dq16, ap), dPm = M2(sc.dP, a, sc.dP16, ap);
   AA_TRY(to_side());
+  AA_TRY(dep(st, sb));
+  AA_TRY(mm_nn(cb, "gemm_att_dx", N, H, a, dQ, Wg, sc.du, H, sc.du, H));                              // dh = du + dq W_g  (lane B)
+  const int ev_du = evi++;
+  if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_du], sb));
   AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, N, dR, M2(sv.s, H, sv.s16, H), gw->att_ws, H, false));
   AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, N, dQ, M2(sv.hiddens, H, sv.hid16, H), gw->att_wg, H, false));
-  if (tc) AA_PROF("cast_inputs", sd, launch_cast2d(sc.dP, a, sc.dP16, ap, (long long)B * k, a, sd));
-  AA_TRY(mm_nn(cs, "gemm_att_dx", B * k, H, a, dPm, Wv, dVb, H, dVb, H));                             // dV += dP W_v
-  AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, B * k, dPm, M2(V, H, sv.V16, H), gw->att_wv, H, false));
+  if (tc) AA_PROF("cast_inputs", sb, launch_cast2d(sc.dP, a, sc.dP16, ap, (long long)B * k, a, sb));
+  AA_TRY(mm_nn(cb, "gemm_att_dx", B * k, H, a, dPm, Wv, dVb, H, dVb, H));                             // dV += dP W_v
+  AA_TRY(mm_tn(cb, "gemm_att_dw", a, H, B * k, dPm, M2(V, H, sv.V16, H), gw->att_wv, H, false));
   AA_TRY(mm_nn(cx, "gemm_att_dx", N, H, a, dR, Ws, sc.ds, H, sc.ds, H));                              // ds += dr W_s
-  AA_TRY(mm_nn(cx, "gemm_att_dx", N, H, a, dQ, Wg, sc.du, H, sc.du, H));                              // dh = du + dq W_g
   // sentinel                                                    adaptive_attention.py:79-83
   AA_TRY(launch_sentinel_bwd(sc.ds, sv.g, sv.cells, sc.da, sc.dcell, tc ? sc.da16 : nullptr, (long long)N * H, st));
   const Mat dA = M2(sc.da, H, sc.da16, H);
   AA_TRY(to_side());
+  AA_TRY(dep(st, sb));
   AA_TRY(mm_nn(cs, "gemm_sent_dx", N, 2 * E, H, dA, Wx, sc.dx, 2 * E, nullptr, 0));
   const int ev_dx = evi++;
   if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_dx], sd));
   AA_TRY(mm_tn(cs, "gemm_sent_dw", H, 2 * E, N, dA, X, gw->sen_wx, 2 * E, false));
   if (T > 1) {
     AA_TRY(mm_nn(cx, "gemm_sent_dx", N, H, H, dA, Wh, sc.dhs, H, nullptr, 0));
-    AA_TRY(mm_tn(cs, "gemm_sent_dw", H, H, N, dA, M2(sv.hs_prev, H, sv.hsprev16, H), gw->sen_wh, H, false));
+    AA_TRY(mm_tn(cb, "gemm_sent_dw", H, H, N, dA, M2(sv.hs_prev, H, sv.hsprev16, H), gw->sen_wh, H, false));
   } else {
-    AA_CHECK_CUDA(cudaMemsetAsync(gw->sen_wh, 0, sizeof(float) * (size_t)H * H, sd));   // h~ = 0: no gradient (Q3)
+    AA_CHECK_CUDA(cudaMemsetAsync(gw->sen_wh, 0, sizeof(float) * (size_t)H * H, sb));   // h~ = 0: no gradient (Q3)
   }
-  AA_TRY(bucket_ready(AA_BUCKET_ATTEN, sd));   // (att_wh was finished by atten_bwd, which the side lane has waited for)
+  AA_TRY(dep(sb, sd));
+  AA_TRY(bucket_ready(AA_BUCKET_ATTEN, sd));   // (att_wh was finished by atten_bwd, which the side lanes have waited for)
+  if (side) AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_du], 0));   // the BPTT reads dh
   // BPTT                                                        baseline_attention.py:167-178
   const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
   if (seq) {
@@ -818,24 +841,27 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
   }
   if (dh0 && !seq) AA_TRY(launch_copy2d(dh0, H, sc.dh_rec, H, B, H, st));
   if (dc0 && !seq) AA_TRY(launch_copy2d(dc0, H, sc.dc_rec, H, B, H, st));
-  // LSTM parameter gradients, batched over all steps
+  // LSTM parameter gradients, batched over all steps: one lane each
   const Mat dG = M2(sc.dgates, 4 * H, sc.dgates16, 4 * H);
   AA_TRY(to_side());
+  AA_TRY(dep(st, sb));
+  AA_TRY(dep(st, sl));
   AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, false));
-  AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, H, N, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, false));   // steps t >= 1 (h~_0 rows are 0)
+  AA_TRY(mm_tn(cb, "gemm_lstm_dw", 4 * H, H, N, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, false));   // steps t >= 1 (h~_0 rows are 0)
   if (h0)                                                                                                      // step 0
-    AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, H, B, M2(sc.dgates, (long long)T * 4 * H, sc.dgates16, (long long)T * 4 * H),
+    AA_TRY(mm_tn(cb, "gemm_lstm_dw", 4 * H, H, B, M2(sc.dgates, (long long)T * 4 * H, sc.dgates16, (long long)T * 4 * H),
                  M2(h0, H, sv.h016, H), gw->w_hh, H, true));
-  AA_PROF("colsum", sd, launch_colsum(sc.dgates, 4 * H, N, 4 * H, gw->b_ih, gw->b_hh, sd));
+  AA_PROF("colsum", sl, launch_colsum(sc.dgates, 4 * H, N, 4 * H, gw->b_ih, gw->b_hh, sl));
+  AA_TRY(dep(sb, sd));
+  AA_TRY(dep(sl, sd));
   AA_TRY(bucket_ready(AA_BUCKET_LSTM, sd));
   // dx += dgates W_ih needs the sentinel's dx from the side lane
   if (side) AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_dx], 0));
   AA_TRY(mm_nn(cx, "gemm_lstm_dx", N, 2 * E, 4 * H, dG, Wih, sc.dx, 2 * E, sc.dx, 2 * E));
-  // x = [embed(w); v_g]                                         baseline_attention.py:151-154
-  AA_CHECK_CUDA(cudaMemsetAsync(gw->embed, 0, sizeof(float) * (size_t)Vc * E, st));
+  // x = [embed(w); v_g]                                         baseline_attention.py:151-154   (gw->embed was zero-filled on lane C)
   AA_TRY(launch_embed_bwd(cap, sc.dx, gw->embed, dv_g, B, T, E, Vc, st));
   AA_TRY(bucket_ready(AA_BUCKET_EMBED, st));
-  return stream_dep(side, evi++, sd, st);   // join: the call is complete, in stream order, when `stream` says so
+  return dep(sd, st);   // join (lane A has joined B and C): the call is complete, in stream order, when `stream` says so
 }
 
 int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
@@ -903,6 +929,21 @@ int aa_cross_entropy_denom(const float* logits, int64_t n_rows, int64_t Vc, cons
 int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, float* loss, float* dlogits,
                      void* stream) {
   return aa_cross_entropy_denom(logits, n_rows, Vc, targets, n_rows, loss, dlogits, stream);
+}
+
+int aa_scale_unless_one(float* x, const float* g, int64_t n, void* stream) {
+  AA_REQUIRE(n >= 0 && (n == 0 || (x && g)), "aa_scale_unless_one: bad argument");
+  return launch_scale_unless_one(x, g, (long long)n, (cudaStream_t)stream);
+}
+
+int aa_copy_multi(int n_segments, const void* const* src, void* const* dst, const int64_t* bytes, void* stream) {
+  AA_REQUIRE(n_segments >= 0 && n_segments <= 8 && (n_segments == 0 || (src && dst && bytes)), "aa_copy_multi: bad argument");
+  long long b[8];
+  for (int i = 0; i < n_segments; ++i) {
+    AA_REQUIRE(bytes[i] >= 0 && (bytes[i] == 0 || (src[i] && dst[i])), "aa_copy_multi: bad segment %d", i);
+    b[i] = (long long)bytes[i];
+  }
+  return launch_copy_multi(n_segments, src, dst, b, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -64,6 +64,11 @@ int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s);
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
                       long long ldd, long long denom, cudaStream_t s);
 
+// x[0:n] *= *g unless *g == 1 (device scalar)
+int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s);
+// up to 8 device-to-device copies in one launch
+int launch_copy_multi(int nsegs, const void* const* src, void* const* dst, const long long* bytes, cudaStream_t s);
+
 // ---- gemm_tc.cu (tcgen05 + TMA) ------------------------------------------------------------
 // D[m,n] = sum_k A(m,k) B(n,k) (+ beta*Cin + bias1[n] + bias2[n]); bf16 (elem_size 2) or tf32 (4) inputs,
 // fp32 accumulation.  a_mn/b_mn = 0: operand stored [rows, K] with K contiguous (K-major);
@@ -153,6 +158,7 @@ struct AttenBwdArgs {
   float *dwh;             // [a]      pre-zeroed, atomically accumulated
   __nv_bfloat16 *dq16, *dr16, *dP16;   // optional bf16 mirrors with row stride a_pad (dP16 only when not split over T)
   int a_pad;
+  int prezeroed;          // != 0: the caller has already zero-filled dV and dP (off the critical path)
 };
 int launch_atten_bwd(const AttenBwdArgs& p, cudaStream_t s);
 

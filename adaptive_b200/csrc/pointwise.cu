@@ -290,6 +290,105 @@ __global__ void __launch_bounds__(PW_THREADS) ce_fwd_bwd_kernel(const float* __r
   }
 }
 
+// Same result with the row held in registers: one read of the logits, one exp per element, one write of the gradient
+// (the kernel above reads every row three times and evaluates exp twice per element: 36.7 us for 840 x 10000 inside the
+// training step, profiles/r01_v42_timeline.txt; 67 MB of traffic is ~11 us of HBM time).  Needs Vc % 4 == 0, 16-byte
+// aligned rows and Vc <= 4 * NT * Q4.
+template <int NT, int Q4>
+__global__ void __launch_bounds__(NT) ce_fwd_bwd_reg_kernel(const float* __restrict__ logits, long long ld,
+                                                            const long long* __restrict__ tgt, int Vc, float* __restrict__ loss,
+                                                            float* __restrict__ dlogits, long long ldd, float inv_n) {
+  __shared__ float red[NT / 32];
+  __shared__ float bcast[2];
+  const int r = blockIdx.x;
+  const float4* row = reinterpret_cast<const float4*>(logits + r * ld);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int n4 = Vc >> 2;
+  float4 v[Q4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < Q4; ++q) {
+    const int i = q * NT + threadIdx.x;
+    v[q] = i < n4 ? ldg4_stream(reinterpret_cast<const float*>(row + i)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    m = fmaxf(fmaxf(m, fmaxf(v[q].x, v[q].y)), fmaxf(v[q].z, v[q].w));
+  }
+  m = warp_max(m);
+  if (l == 0) red[w] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < NT / 32; ++i) t = fmaxf(t, red[i]);
+    bcast[0] = t;
+  }
+  __syncthreads();
+  m = bcast[0];
+  const long long t = tgt[r];
+  float sum = 0.f, xt = 0.f;
+#pragma unroll
+  for (int q = 0; q < Q4; ++q) {
+    const int i = q * NT + threadIdx.x;
+    if (i == (int)(t >> 2)) xt = (t & 3) == 0 ? v[q].x : (t & 3) == 1 ? v[q].y : (t & 3) == 2 ? v[q].z : v[q].w;
+    v[q].x = expf(v[q].x - m); v[q].y = expf(v[q].y - m); v[q].z = expf(v[q].z - m); v[q].w = expf(v[q].w - m);   // (exp(-inf) = 0 past the row)
+    sum += (v[q].x + v[q].y) + (v[q].z + v[q].w);
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (l == 0) red[w] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s2 = 0.f;
+    for (int i = 0; i < NT / 32; ++i) s2 += red[i];
+    bcast[1] = s2;
+  }
+  __syncthreads();
+  sum = bcast[1];
+  if ((int)(t >> 2) % NT == (int)threadIdx.x && (t >> 2) < n4) atomicAdd(loss, (logf(sum) + m - xt) * inv_n);   // the thread that held x_t
+  if (dlogits) {
+    const float sc = inv_n / sum;
+    float4* d = reinterpret_cast<float4*>(dlogits + r * ldd);
+#pragma unroll
+    for (int q = 0; q < Q4; ++q) {
+      const int i = q * NT + threadIdx.x;
+      if (i < n4) {
+        float4 p = make_float4(v[q].x * sc, v[q].y * sc, v[q].z * sc, v[q].w * sc);
+        if (i == (int)(t >> 2)) {
+          if ((t & 3) == 0) p.x -= inv_n; else if ((t & 3) == 1) p.y -= inv_n; else if ((t & 3) == 2) p.z -= inv_n; else p.w -= inv_n;
+        }
+        d[i] = p;
+      }
+    }
+  }
+}
+
+// x *= *g unless *g == 1 (the upstream gradient of a loss that is the root of the backward pass): every CTA reads the device
+// scalar and leaves at once in the common case instead of a full read-modify-write pass over x
+__global__ void scale_unless_one_kernel(float* __restrict__ x, const float* __restrict__ g, long long n) {
+  const float s = *g;
+  if (s == 1.0f) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= s;
+}
+
+// up to 8 device-to-device copies in one launch (the step's input tensors into a CUDA graph's static buffers)
+struct CopySegs {
+  const void* src[8];
+  void* dst[8];
+  long long bytes[8];
+};
+__global__ void copy_multi_kernel(const CopySegs segs) {
+  const int sidx = blockIdx.y;
+  const char* src = static_cast<const char*>(segs.src[sidx]);
+  char* dst = static_cast<char*>(segs.dst[sidx]);
+  const long long n = segs.bytes[sidx];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const long long n16 = n >> 4;
+    for (long long i = tid; i < n16; i += nth) reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    for (long long i = (n16 << 4) + tid; i < n; i += nth) dst[i] = src[i];
+  } else {
+    for (long long i = tid; i < n; i += nth) dst[i] = src[i];
+  }
+}
+
 // fp32 -> bf16, 2-D with independent row strides (also used for the zero-padded a -> a_pad copies)
 __global__ void cast2d_kernel(const float* __restrict__ src, long long ld_src, bf16* __restrict__ dst, long long ld_dst, long long rows,
                               int cols) {
@@ -514,8 +613,40 @@ int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s) {
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
                       long long ldd, long long denom, cudaStream_t s) {
   if (n == 0) return AA_OK;
-  ce_fwd_bwd_kernel<<<n, PW_THREADS, 0, s>>>(logits, ld, tgt, n, Vc, loss, dlogits, ldd, 1.f / (float)(denom > 0 ? denom : n));
+  const float inv_n = 1.f / (float)(denom > 0 ? denom : n);
+  const bool vec = Vc % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0;
+  const int n4 = Vc / 4;
+  if (vec && n4 <= 256 * 4) ce_fwd_bwd_reg_kernel<256, 4><<<n, 256, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
+  else if (vec && n4 <= 256 * 10) ce_fwd_bwd_reg_kernel<256, 10><<<n, 256, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
+  else if (vec && n4 <= 512 * 10) ce_fwd_bwd_reg_kernel<512, 10><<<n, 512, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
+  else if (vec && n4 <= 1024 * 12) ce_fwd_bwd_reg_kernel<1024, 12><<<n, 1024, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
+  else ce_fwd_bwd_kernel<<<n, PW_THREADS, 0, s>>>(logits, ld, tgt, n, Vc, loss, dlogits, ldd, inv_n);
   AA_CHECK_LAUNCH("ce_fwd_bwd");
+  return AA_OK;
+}
+
+int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s) {
+  if (n == 0) return AA_OK;
+  long long nb = (n + PW_THREADS * 8 - 1) / (PW_THREADS * 8);
+  nb = nb > 1184 ? 1184 : nb;
+  scale_unless_one_kernel<<<(unsigned)nb, PW_THREADS, 0, s>>>(x, g, n);
+  AA_CHECK_LAUNCH("scale_unless_one");
+  return AA_OK;
+}
+
+int launch_copy_multi(int nsegs, const void* const* src, void* const* dst, const long long* bytes, cudaStream_t s) {
+  AA_REQUIRE(nsegs >= 0 && nsegs <= 8, "copy_multi: at most 8 segments (got %d)", nsegs);
+  if (nsegs == 0) return AA_OK;
+  CopySegs segs{};
+  long long nmax = 0;
+  for (int i = 0; i < nsegs; ++i) {
+    segs.src[i] = src[i]; segs.dst[i] = dst[i]; segs.bytes[i] = bytes[i];
+    nmax = bytes[i] > nmax ? bytes[i] : nmax;
+  }
+  long long nb = (nmax / 16 + PW_THREADS * 4 - 1) / (PW_THREADS * 4);   // ~4 uint4 per thread of the largest segment
+  nb = nb < 1 ? 1 : (nb > 592 ? 592 : nb);
+  copy_multi_kernel<<<dim3((unsigned)nb, nsegs), PW_THREADS, 0, s>>>(segs);
+  AA_CHECK_LAUNCH("copy_multi");
   return AA_OK;
 }
 

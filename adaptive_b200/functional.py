@@ -343,7 +343,30 @@ class _CrossEntropyFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dlog,) = ctx.saved_tensors
-        return dlog * g, None
+        # upstream gradient: a device scalar, 1 when the loss is the root (train.py:210).  dlog is this function's own buffer
+        # and is consumed once, so it is scaled in place, and only when g != 1 (decided on the device: no host sync)
+        g = g.to(torch.float32).contiguous()
+        with torch.cuda.device(dlog.device):
+            check(_lib.load().aa_scale_unless_one(_ptr(dlog), _ptr(g), dlog.numel(), _stream(dlog.device)), "aa_scale_unless_one")
+        return dlog, None
+
+
+def copy_multi(dsts: Sequence[torch.Tensor], srcs: Sequence[torch.Tensor]) -> None:
+    """dst[i].copy_(src[i]) for up to 8 contiguous same-shaped device tensor pairs per launch (one kernel instead of one
+    memcpy node each)."""
+    pairs = [(d, s) for d, s in zip(dsts, srcs) if d is not s and d.numel() > 0]
+    for d, s in pairs:
+        if not (d.is_cuda and s.is_cuda and d.is_contiguous() and s.is_contiguous() and d.dtype == s.dtype and d.shape == s.shape):
+            raise ValueError("copy_multi: contiguous CUDA tensors of equal shape and dtype expected")
+    lib = _lib.load()
+    for i in range(0, len(pairs), 8):
+        grp = pairs[i:i + 8]
+        n = len(grp)
+        src = (ctypes.c_void_p * n)(*[s.data_ptr() for _, s in grp])
+        dst = (ctypes.c_void_p * n)(*[d.data_ptr() for d, _ in grp])
+        nbytes = (ctypes.c_int64 * n)(*[d.numel() * d.element_size() for d, _ in grp])
+        with torch.cuda.device(grp[0][0].device):
+            check(lib.aa_copy_multi(n, src, dst, nbytes, _stream(grp[0][0].device)), "aa_copy_multi")
 
 
 def cross_entropy(logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:

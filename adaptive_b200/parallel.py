@@ -350,8 +350,8 @@ class GraphedDPStep:
         return self.trainer.step((b["V"], b["v_g"], (b["h0"], b["c0"])), b["captions"], self.lengths, b["tgt"])
 
     def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        for k in self.KEYS:
-            if batch[k] is not self.static[k]:
-                self.static[k].copy_(batch[k], non_blocking=True)
+        from . import functional as F_aa
+
+        F_aa.copy_multi([self.static[k] for k in self.KEYS], [batch[k] for k in self.KEYS])   # one launch for the six inputs
         self.graph.replay()
         return self.loss

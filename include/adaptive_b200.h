@@ -277,6 +277,13 @@ int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int6
 int aa_cross_entropy_denom(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom,
                            float* loss, float* dlogits, void* stream);
 
+/* x[0:n] *= *g unless *g == 1 -- the backward of the loss above when it is not the root of the backward pass
+ * (torch.autograd hands the upstream gradient as a device scalar; `loss.backward()` at train.py:210 passes 1). */
+int aa_scale_unless_one(float* x, const float* g, int64_t n, void* stream);
+/* Up to 8 device-to-device copies in one launch (host-side plumbing with no reference counterpart: a step's input tensors
+ * into the static buffers of a captured CUDA graph; six separate copies cost 27 us of a 500 us step). */
+int aa_copy_multi(int n_segments, const void* const* src, void* const* dst, const int64_t* bytes, void* stream);
+
 /* ---- decoding: Encoder2Decoder.sampler -------------------------------------------- */
 
 /* Workspace for decoding d->B images for d->T (= max_len) steps: beam = 0 -> aa_greedy_decode,
