@@ -44,10 +44,15 @@ int num_sms() {
 // graph as a fork/join).  Three side lanes + event pool per (host thread, device), created lazily -- the first
 // call on a thread must therefore not be made under stream capture (same rule as the one-time
 // cudaFuncSetAttribute calls of the kernels).  AA_NO_SIDE_STREAM=1 serialises everything on the caller's stream.
+// The critical path of the training forward / backward itself runs on a library-owned stream of the HIGHEST priority
+// (forked from and joined into the caller's stream like the side lanes): when a side-lane contraction and a critical one
+// become ready together, the block scheduler hands free SMs to the critical one first (the caller's stream usually has the
+// lowest priority, like the side lanes; profiles/r01_v43_timeline.txt shows du = dS W_p waiting 14 us behind dW_p).
 namespace {
 constexpr int SIDE_EVENTS = 32;
 struct SideCtx {
-  cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;   // lanes A, B, C
+  cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;   // lanes A, B, C (lowest priority)
+  cudaStream_t crit = nullptr;                                     // the critical path of a call (highest priority)
   cudaEvent_t ev[SIDE_EVENTS] = {};
   bool ready = false;
 };
@@ -67,9 +72,12 @@ static int get_side(SideCtx** out) {
   if (dev < 0 || dev >= 16) return AA_OK;
   SideCtx& c = g_side[dev];
   if (!c.ready) {
-    AA_CHECK_CUDA(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
-    AA_CHECK_CUDA(cudaStreamCreateWithFlags(&c.side2, cudaStreamNonBlocking));
-    AA_CHECK_CUDA(cudaStreamCreateWithFlags(&c.side3, cudaStreamNonBlocking));
+    int prio_least = 0, prio_greatest = 0;
+    AA_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, prio_least));
+    AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, prio_least));
+    AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.side3, cudaStreamNonBlocking, prio_least));
+    AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.crit, cudaStreamNonBlocking, prio_greatest));
     for (int i = 0; i < SIDE_EVENTS; ++i) AA_CHECK_CUDA(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
     c.ready = true;
   }
@@ -555,9 +563,27 @@ int aa_adaptive_forward(const aa_dims* d, const aa_weights* w, const float* x, c
 size_t aa_decoder_saved_bytes(const aa_dims* d) { return d ? carve_saved(*d, nullptr).bytes : 0; }
 size_t aa_decoder_bwd_scratch_bytes(const aa_dims* d) { return d ? carve_bwd(*d, nullptr).bytes : 0; }
 
+static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                                const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
+                                void* saved, size_t saved_bytes, void* stream, SideCtx* side, const int64_t* row_index, int64_t n_rows);
+
+// fork the call's critical lane from the caller's stream, run the body on it, join every lane back
 static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
                                 const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
                                 void* saved, size_t saved_bytes, void* stream, const int64_t* row_index, int64_t n_rows) {
+  SideCtx* side = nullptr;
+  AA_TRY(get_side(&side));
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStream_t st = side ? side->crit : caller;
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 4, caller, st));
+  AA_TRY(decoder_forward_body(d, w, V, v_g, captions, h0, c0, scores, alpha, beta, hT, cT, saved, saved_bytes, (void*)st, side, row_index, n_rows));
+  if (side) AA_TRY(stream_dep(side, SIDE_EVENTS - 5, side->side2, st));   // (hT / cT copies)
+  return stream_dep(side, SIDE_EVENTS - 6, st, caller);
+}
+
+static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                                const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
+                                void* saved, size_t saved_bytes, void* stream, SideCtx* side, const int64_t* row_index, int64_t n_rows) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && scores && alpha && beta, "aa_decoder_forward: null pointer");
   if (d->B == 0) return AA_OK;
@@ -577,8 +603,6 @@ static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const flo
   const W16& h = sv.w16;
   // Side lane, forked at once: what the recurrence does not need -- the bf16 copies of every weight but the LSTM's and of V,
   // P = V W_v^T and the sentinel gate's input half -- runs next to the main lane's casts, gate GEMM and recurrence.
-  SideCtx* side = nullptr;
-  AA_TRY(get_side(&side));
   const Ctx cs{d->precision, side ? side->side : st};
   AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
   if (tc) {   // bf16 copies of the GEMM weights and of V, h0
@@ -641,8 +665,12 @@ static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const flo
                                  tc ? sv.hid16 + (size_t)t * H : nullptr, (tc && t + 1 < T) ? sv.hsprev16 + (size_t)(t + 1) * H : nullptr,
                                  B, H, st));
   }
-  if (hT) AA_TRY(launch_copy2d(hT, H, sv.hiddens + (size_t)(T - 1) * H, (long long)T * H, B, H, st));
-  if (cT) AA_TRY(launch_copy2d(cT, H, sv.cells + (size_t)(T - 1) * H, (long long)T * H, B, H, st));
+  {   // final states out: nothing downstream reads them, lane B (joined by the caller of this body)
+    const cudaStream_t so = side ? side->side2 : st;
+    AA_TRY(stream_dep(side, SIDE_EVENTS - 7, st, so));
+    if (hT) AA_TRY(launch_copy2d(hT, H, sv.hiddens + (size_t)(T - 1) * H, (long long)T * H, B, H, so));
+    if (cT) AA_TRY(launch_copy2d(cT, H, sv.cells + (size_t)(T - 1) * H, (long long)T * H, B, H, so));
+  }
   AA_TRY(stream_dep(side, SIDE_EVENTS - 1, cs.st, st));       // main lane joins the side lane
   // q = h W_g^T only needs the hidden states: it runs on the side lane next to the sentinel's recurrent half
   AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
@@ -681,12 +709,35 @@ int aa_decoder_forward_packed(const aa_dims* d, const aa_weights* w, const float
                               n_rows);
 }
 
+static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                                 const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
+                                 size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
+                                 const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
+                                 float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
+                                 aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows);
+
 static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
                                  const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
                                  size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
                                  const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
                                  float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
                                  aa_grad_ready_fn on_ready, void* user, const int64_t* row_index = nullptr, int64_t n_rows = 0) {
+  SideCtx* side = nullptr;
+  AA_TRY(get_side(&side));
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStream_t st = side ? side->crit : caller;
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 4, caller, st));
+  AA_TRY(decoder_backward_body(d, w, V, v_g, captions, h0, c0, alpha, beta, saved, saved_bytes, d_scores, d_alpha, d_beta, d_hT, d_cT, gw, dV,
+                               dv_g, dh0, dc0, scratch, scratch_bytes, (void*)st, ready_events, on_ready, user, side, row_index, n_rows));
+  return stream_dep(side, SIDE_EVENTS - 6, st, caller);
+}
+
+static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                                 const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
+                                 size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
+                                 const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
+                                 float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
+                                 aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && alpha && beta && d_scores && gw, "aa_decoder_backward: null pointer");
   AA_REQUIRE(gw->embed && gw->w_ih && gw->w_hh && gw->b_ih && gw->b_hh && gw->sen_wx && gw->sen_wh && gw->att_wv &&
@@ -716,8 +767,6 @@ static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const fl
   // side lane serialised those ~14 small contractions and finished ~60 us after the main lane (profiles/r01_v40_bench.json:
   // the side lane's kernels sum to more than the main lane's); small contractions leave most SMs idle, so independent
   // ones now run next to each other.
-  SideCtx* side = nullptr;
-  AA_TRY(get_side(&side));
   const Ctx cx{d->precision, st};
   const cudaStream_t sd = side ? side->side : st, sb = side ? side->side2 : st, sl = side ? side->side3 : st;
   const Ctx cs{d->precision, sd}, cb{d->precision, sb};

@@ -415,7 +415,9 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int BKk = 128 / ES;
   const int nkb = ceil_div(g.K, BKk);
   int ksplit = 1;
-  if (!SPLIT && g.D32 && !g.D16 && !g.pmax && g_tc_splitk) {
+  // (a split needs the output zero-filled first: a memset node and its dependency edge cost ~2-3 us inside a graph, more than the
+  //  ~0.9 us that halving an 8-k-block chain saves -- K <= 8 k-blocks is never split)
+  if (!SPLIT && g.D32 && !g.D16 && !g.pmax && g_tc_splitk && nkb > 8) {
     const int sms = num_sms();
     while (ksplit < 16 && num_tiles * (ksplit + 1) <= sms && nkb / (ksplit + 1) >= 4) ++ksplit;
   }

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
   const int m0 = blockIdx.y * a.rpg;
   const int rows = min(a.rpg, a.B - m0);
   const uint32_t step_bytes = (uint32_t)(CL * rows * 64);            // what one step delivers into this CTA
+  if (threadIdx.x == 0) cl_trace(40, 0);                             // (row 40 of the trace: kernel entry, prologue done, loop done, exit)
 
   if (warp == 4 && lane == 0) {
     mbar_init(w_full, 1);
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) cl_trace(40, 1);
 
   if (warp == 4) {
     // ===== MMA issuer (converged warp, one elected lane) =====
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
       }
     }
   }
+  if (threadIdx.x == 0) cl_trace(40, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
   cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
+  if (threadIdx.x == 0) cl_trace(40, 3);
 }
 
 // =============================================================================================================
@@ -404,6 +408,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_bwd_kernel(const __gr
   const int m0 = blockIdx.y * a.rpg;
   const int rows = min(a.rpg, a.B - m0);
   const int rows4 = (a.rpg + 3) / 4 * 4;                            // floats staged per (destination, unit)
+  if (threadIdx.x == 0) cl_trace(40, 0);
 
   if (warp == 4 && lane == 0) {
     mbar_init(w_full, 1);
@@ -457,6 +462,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_bwd_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   cluster_sync_all();   // every CTA is done with its weight tiles: their bytes may now receive partials; barriers are initialised
+  if (threadIdx.x == 0) cl_trace(40, 1);
 
   // GEMM i (i = 1..T) consumes dgates of step T - i and yields dh_rec for step T - i - 1 (dh0 when i == T).
   if (warp == 4) {
@@ -597,6 +603,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_bwd_kernel(const __gr
       }
     }
   }
+  if (threadIdx.x == 0) cl_trace(40, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
@@ -604,6 +611,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_bwd_kernel(const __gr
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
   cluster_sync_all();
+  if (threadIdx.x == 0) cl_trace(40, 3);
 }
 
 // floats per (source, unit) row of the partials buffer: >= the rows sent, an odd number of 16-byte quads so that the

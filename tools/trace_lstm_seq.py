@@ -49,3 +49,6 @@ for label, tr, rng in (("forward", fwd, range(0, T)), ("backward", bwd, range(0,
         per = int(base - prev) if prev is not None else 0
         prev = base
         print("%4d " % s + " ".join("%13d" % x for x in rel) + "   period=%d" % per)
+    k = tr[40]
+    if k[0] > 0:   # cluster kernels: whole-kernel stamps of CTA (0,0)
+        print("kernel: entry 0, prologue done +%d ns, loop done +%d ns, exit +%d ns" % (k[1] - k[0], k[2] - k[0], k[3] - k[0]))
