@@ -198,7 +198,7 @@ Saved carve_saved(const aa_dims& d, void* base) {
     s.up16 = h.take(N * H);
     s.x16 = h.take(N * 2 * E);
     s.hid16 = h.take(N * H);
-    s.hsprev16 = h.take(N * H);
+    s.hsprev16 = h.take(N * H + (size_t)d.B * H);   // (+ B rows: h0, the K-tail of the dW_hh contraction)
     s.s16 = h.take(N * H);
     s.V16 = h.take((size_t)d.B * d.k * H);
     s.u16 = h.take(N * H);
@@ -252,7 +252,7 @@ BwdScratch carve_bwd(const aa_dims& d, void* base) {
     s.dr16 = h.take(N * ap);
     s.dP16 = h.take((size_t)d.B * d.k * ap);
     s.da16 = h.take(N * H);
-    s.dgates16 = h.take(N * 4 * H);
+    s.dgates16 = h.take(N * 4 * H + (size_t)d.B * 4 * H);   // (+ B rows: dgates of step 0, the K-tail of the dW_hh contraction)
     s.whhT16 = h.take(4 * H * H);
     s.counters = reinterpret_cast<unsigned*>(c.take(64));
   }
@@ -789,14 +789,23 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   // zero-fills of everything that is accumulated into later (du, dV, dP, att_wh and the 10 MB embedding gradient) run on lane C
   // now, next to the first contractions, instead of as memset nodes in front of their consumers on the critical path
   AA_TRY(dep(st, sl));
+  const int NR = row_index ? (int)n_rows : N;
+  const bool pre_dx = tc && NR > 0;     // du's contraction adds onto a zero-filled output: no memset node in front of it
+  if (pre_dx) AA_CHECK_CUDA(cudaMemsetAsync(row_index ? sc.dup : sc.du, 0, sizeof(float) * (size_t)NR * H, sl));
+  const int ev_dup = evi++;
+  if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_dup], sl));
   if (row_index) AA_CHECK_CUDA(cudaMemsetAsync(sc.du, 0, sizeof(float) * (size_t)N * H, sl));
   AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, sl));
   AA_CHECK_CUDA(cudaMemsetAsync(dVb, 0, sizeof(float) * (size_t)B * k * H, sl));
   AA_CHECK_CUDA(cudaMemsetAsync(sc.dP, 0, sizeof(float) * (size_t)B * k * a, sl));
   AA_CHECK_CUDA(cudaMemsetAsync(gw->embed, 0, sizeof(float) * (size_t)Vc * E, sl));
+  if (tc) {   // the LSTM weight gradients are accumulated onto zeros as well (their split-K zero-fills sat on the tail after the BPTT)
+    AA_CHECK_CUDA(cudaMemsetAsync(gw->w_ih, 0, sizeof(float) * (size_t)4 * H * 2 * E, sl));
+    AA_CHECK_CUDA(cudaMemsetAsync(gw->w_hh, 0, sizeof(float) * (size_t)4 * H * H, sl));
+    if (h0) AA_CHECK_CUDA(cudaMemcpyAsync(sv.hsprev16 + (size_t)N * H, sv.h016, sizeof(bf16) * (size_t)B * H, cudaMemcpyDeviceToDevice, sl));
+  }
   // db_p = column sums of dS, fused with the bf16 cast of dS                     adaptive_attention.py:132
   // (packed entry point: d_scores holds the NR = n_rows packed rows only; the other positions have no gradient)
-  const int NR = row_index ? (int)n_rows : N;
   if (NR > 0) AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
   else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_b, 0, sizeof(float) * Vc, st));
   const Mat dS = M2(d_scores, Vc, sc.dS16, Vc);
@@ -804,10 +813,11 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
   // (du is on the critical path: its contraction is enqueued before the weight gradient's so that it gets the SMs first)
   AA_TRY(to_side());
+  if (side && pre_dx) AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_dup], 0));
   if (row_index) {   // du rows of the packed positions, scattered back to [B,T,H] (zero elsewhere)
-    if (NR > 0) AA_TRY(mm_nn(cx, "gemm_vocab_dx", NR, H, Vc, dS, Wp, sc.dup, H, nullptr, 0));
+    if (NR > 0) AA_TRY(mm_nn(cx, "gemm_vocab_dx", NR, H, Vc, dS, Wp, sc.dup, H, pre_dx ? sc.dup : nullptr, H));
   } else {
-    AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, nullptr, 0));
+    AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, pre_dx ? sc.du : nullptr, H));
   }
   if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
   else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
@@ -895,11 +905,24 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   AA_TRY(to_side());
   AA_TRY(dep(st, sb));
   AA_TRY(dep(st, sl));
-  AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, false));
-  AA_TRY(mm_tn(cb, "gemm_lstm_dw", 4 * H, H, N, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, false));   // steps t >= 1 (h~_0 rows are 0)
-  if (h0)                                                                                                      // step 0
-    AA_TRY(mm_tn(cb, "gemm_lstm_dw", 4 * H, H, B, M2(sc.dgates, (long long)T * 4 * H, sc.dgates16, (long long)T * 4 * H),
-                 M2(h0, H, sv.h016, H), gw->w_hh, H, true));
+  if (tc) {
+    // (outputs zero-filled on lane C at the start: accumulate, no memset nodes here.)  The step-0 term dgates_0^T h0 of dW_hh
+    // rides along as B extra K rows: h0 behind the rows of h~ and the step-0 rows of dgates behind the rows of dgates
+    AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, true));
+    int Kh = N;
+    if (h0) {
+      AA_CHECK_CUDA(cudaMemcpy2DAsync(sc.dgates16 + (size_t)N * 4 * H, sizeof(bf16) * (size_t)4 * H, sc.dgates16, sizeof(bf16) * (size_t)T * 4 * H,
+                                      sizeof(bf16) * (size_t)4 * H, (size_t)B, cudaMemcpyDeviceToDevice, sb));
+      Kh = N + B;
+    }
+    AA_TRY(mm_tn(cb, "gemm_lstm_dw", 4 * H, H, Kh, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, true));
+  } else {
+    AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, false));
+    AA_TRY(mm_tn(cb, "gemm_lstm_dw", 4 * H, H, N, dG, M2(sv.hs_prev, H, sv.hsprev16, H), gw->w_hh, H, false));   // steps t >= 1 (h~_0 rows are 0)
+    if (h0)                                                                                                      // step 0
+      AA_TRY(mm_tn(cb, "gemm_lstm_dw", 4 * H, H, B, M2(sc.dgates, (long long)T * 4 * H, sc.dgates16, (long long)T * 4 * H),
+                   M2(h0, H, sv.h016, H), gw->w_hh, H, true));
+  }
   AA_PROF("colsum", sl, launch_colsum(sc.dgates, 4 * H, N, 4 * H, gw->b_ih, gw->b_hh, sl));
   AA_TRY(dep(sb, sd));
   AA_TRY(dep(sl, sd));
