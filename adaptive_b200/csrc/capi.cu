@@ -53,6 +53,7 @@ constexpr int SIDE_EVENTS = 32;
 struct SideCtx {
   cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr;   // lanes A, B, C (lowest priority)
   cudaStream_t crit = nullptr;                                     // the critical path of a call (highest priority)
+  cudaStream_t zero = nullptr;                                     // zero-fills the critical path will wait for (highest priority)
   cudaEvent_t ev[SIDE_EVENTS] = {};
   bool ready = false;
 };
@@ -78,6 +79,7 @@ static int get_side(SideCtx** out) {
     AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, prio_least));
     AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.side3, cudaStreamNonBlocking, prio_least));
     AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.crit, cudaStreamNonBlocking, prio_greatest));
+    AA_CHECK_CUDA(cudaStreamCreateWithPriority(&c.zero, cudaStreamNonBlocking, prio_greatest));
     for (int i = 0; i < SIDE_EVENTS; ++i) AA_CHECK_CUDA(cudaEventCreateWithFlags(&c.ev[i], cudaEventDisableTiming));
     c.ready = true;
   }
@@ -617,9 +619,16 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
     AA_PROF("cast_weights", cs.st, launch_cast_multi(c_side, 6, cs.st));
     AA_PROF("cast_inputs", cs.st, launch_cast2d(V, H, sv.V16, H, (long long)B * d->k, H, cs.st));
     if (h0) AA_PROF("cast_inputs", st, launch_cast2d(h0, H, sv.h016, H, B, H, st));
-    else AA_CHECK_CUDA(cudaMemsetAsync(sv.h016, 0, sizeof(bf16) * (size_t)B * H, st));
-    AA_CHECK_CUDA(cudaMemset2DAsync(sv.hsprev16, (size_t)T * H * 2, 0, (size_t)H * 2, B, st));
   }
+  // zero-fills (h~_0 = 0 rows, absent initial states): lane B, joined in front of the recurrence
+  const cudaStream_t so = side ? side->side2 : st;
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 8, st, so));
+  if (tc) {
+    if (!h0) AA_CHECK_CUDA(cudaMemsetAsync(sv.h016, 0, sizeof(bf16) * (size_t)B * H, so));
+    AA_CHECK_CUDA(cudaMemset2DAsync(sv.hsprev16, (size_t)T * H * 2, 0, (size_t)H * 2, B, so));
+  }
+  if (!h0 || !c0) AA_CHECK_CUDA(cudaMemsetAsync(sv.zeros, 0, sizeof(float) * (size_t)B * H, so));
+  AA_CHECK_CUDA(cudaMemset2DAsync(sv.hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, B, so));   // h~_0 = 0 (Q2)
   const Mat Wih = M2(w->w_ih, 2 * E, h.w_ih, 2 * E), Whh = M2(w->w_hh, H, h.w_hh, H);
   const Mat Wx = M2(w->sen_wx, 2 * E, h.sen_wx, 2 * E), Wh = M2(w->sen_wh, H, h.sen_wh, H);
   const Mat Wv = M2(w->att_wv, H, h.att_wv, H), Wg = M2(w->att_wg, H, h.att_wg, H), Ws = M2(w->att_ws, H, h.att_ws, H);
@@ -633,8 +642,7 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
   // input halves of the LSTM gates (main lane) and of the sentinel gate (side lane), batched over all T
   AA_TRY(mm_nt(cx, "gemm_gates_in", N, 4 * H, 2 * E, X, Wih, sv.xg, 4 * H, nullptr, 0, w->b_ih, w->b_hh));
   AA_TRY(mm_nt(cs, "gemm_gates_in", N, H, 2 * E, X, Wx, sv.g, H, nullptr, 0, nullptr, nullptr));
-  if (!h0 || !c0) AA_CHECK_CUDA(cudaMemsetAsync(sv.zeros, 0, sizeof(float) * (size_t)B * H, st));
-  AA_CHECK_CUDA(cudaMemset2DAsync(sv.hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, B, st));   // h~_0 = 0 (Q2)
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 9, so, st));          // (zero-fills done)
   // recurrence                                                 baseline_attention.py:167-178
   const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
   if (seq) {   // all T steps in one cooperative launch (lstm_seq.cu)
@@ -666,7 +674,6 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
                                  B, H, st));
   }
   {   // final states out: nothing downstream reads them, lane B (joined by the caller of this body)
-    const cudaStream_t so = side ? side->side2 : st;
     AA_TRY(stream_dep(side, SIDE_EVENTS - 7, st, so));
     if (hT) AA_TRY(launch_copy2d(hT, H, sv.hiddens + (size_t)(T - 1) * H, (long long)T * H, B, H, so));
     if (cT) AA_TRY(launch_copy2d(cT, H, sv.cells + (size_t)(T - 1) * H, (long long)T * H, B, H, so));
@@ -786,24 +793,31 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   const Mat Wv = M2(w->att_wv, H, h.att_wv, H), Wg = M2(w->att_wg, H, h.att_wg, H), Ws = M2(w->att_ws, H, h.att_ws, H);
   const Mat Wp = M2(w->mlp_w, H, h.mlp_w, H);
   const Mat X = M2(sv.x, 2 * E, sv.x16, 2 * E);
-  // zero-fills of everything that is accumulated into later (du, dV, dP, att_wh and the 10 MB embedding gradient) run on lane C
-  // now, next to the first contractions, instead of as memset nodes in front of their consumers on the critical path
-  AA_TRY(dep(st, sl));
+  // Zero-fills of everything that is accumulated into later run next to the first kernels of the critical lane instead of as
+  // memset nodes in front of their consumers.  What the critical lane waits for soon (du, dV, dP, att_wh) goes to a lane of its
+  // own priority: on a low-priority lane these small kernels queued behind the pending CTAs of the first weight-gradient
+  // contraction and held the attention backward up for 24 us (profiles/r01_v45_timeline.txt).  The rest (embedding and LSTM
+  // weight gradients, the h0 rows of the dW_hh operand) is only needed after the BPTT: lane C.
+  const cudaStream_t sz = side ? side->zero : st;
+  AA_TRY(dep(st, sz));
   const int NR = row_index ? (int)n_rows : N;
   const bool pre_dx = tc && NR > 0;     // du's contraction adds onto a zero-filled output: no memset node in front of it
-  if (pre_dx) AA_CHECK_CUDA(cudaMemsetAsync(row_index ? sc.dup : sc.du, 0, sizeof(float) * (size_t)NR * H, sl));
-  const int ev_dup = evi++;
-  if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_dup], sl));
-  if (row_index) AA_CHECK_CUDA(cudaMemsetAsync(sc.du, 0, sizeof(float) * (size_t)N * H, sl));
-  AA_CHECK_CUDA(cudaMemsetAsync(gw->att_wh, 0, sizeof(float) * a, sl));
-  AA_CHECK_CUDA(cudaMemsetAsync(dVb, 0, sizeof(float) * (size_t)B * k * H, sl));
-  AA_CHECK_CUDA(cudaMemsetAsync(sc.dP, 0, sizeof(float) * (size_t)B * k * a, sl));
-  AA_CHECK_CUDA(cudaMemsetAsync(gw->embed, 0, sizeof(float) * (size_t)Vc * E, sl));
-  if (tc) {   // the LSTM weight gradients are accumulated onto zeros as well (their split-K zero-fills sat on the tail after the BPTT)
-    AA_CHECK_CUDA(cudaMemsetAsync(gw->w_ih, 0, sizeof(float) * (size_t)4 * H * 2 * E, sl));
-    AA_CHECK_CUDA(cudaMemsetAsync(gw->w_hh, 0, sizeof(float) * (size_t)4 * H * H, sl));
-    if (h0) AA_CHECK_CUDA(cudaMemcpyAsync(sv.hsprev16 + (size_t)N * H, sv.h016, sizeof(bf16) * (size_t)B * H, cudaMemcpyDeviceToDevice, sl));
+  {   // ONE kernel per group (memset nodes carry no priority and are dispatched one by one)
+    void* zp[5] = {pre_dx ? (void*)(row_index ? sc.dup : sc.du) : nullptr, row_index ? (void*)sc.du : nullptr, (void*)gw->att_wh, (void*)sc.dP,
+                   (void*)dVb};
+    const long long zb[5] = {(long long)sizeof(float) * NR * H, (long long)sizeof(float) * N * H, (long long)sizeof(float) * a,
+                             (long long)sizeof(float) * B * k * a, (long long)sizeof(float) * B * k * H};
+    AA_TRY(launch_zero_multi(5, zp, zb, sz));
   }
+  AA_TRY(dep(st, sl));
+  {
+    void* zp[3] = {(void*)gw->embed, tc ? (void*)gw->w_ih : nullptr, tc ? (void*)gw->w_hh : nullptr};
+    const long long zb[3] = {(long long)sizeof(float) * Vc * E, (long long)sizeof(float) * 4 * H * 2 * E, (long long)sizeof(float) * 4 * H * H};
+    AA_TRY(launch_zero_multi(3, zp, zb, sl));
+    if (tc && h0) AA_CHECK_CUDA(cudaMemcpyAsync(sv.hsprev16 + (size_t)N * H, sv.h016, sizeof(bf16) * (size_t)B * H, cudaMemcpyDeviceToDevice, sl));
+  }
+  const int ev_late = evi++;
+  if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_late], sl));
   // db_p = column sums of dS, fused with the bf16 cast of dS                     adaptive_attention.py:132
   // (packed entry point: d_scores holds the NR = n_rows packed rows only; the other positions have no gradient)
   if (NR > 0) AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
@@ -813,7 +827,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
   // (du is on the critical path: its contraction is enqueued before the weight gradient's so that it gets the SMs first)
   AA_TRY(to_side());
-  if (side && pre_dx) AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_dup], 0));
+  AA_TRY(dep(sz, st));                                         // the zero-fills of du, dV, dP, att_wh are done
   if (row_index) {   // du rows of the packed positions, scattered back to [B,T,H] (zero elsewhere)
     if (NR > 0) AA_TRY(mm_nn(cx, "gemm_vocab_dx", NR, H, Vc, dS, Wp, sc.dup, H, pre_dx ? sc.dup : nullptr, H));
   } else {
@@ -822,7 +836,6 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
   else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
   AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));
-  AA_TRY(dep(sl, st));                                         // the zero-fills are done
   if (row_index && NR > 0) {
     pack_rows_kernel<<<(unsigned)NR, 128, 0, st>>>(sc.dup, H, reinterpret_cast<const long long*>(row_index), sc.du, 0);
     AA_CHECK_LAUNCH("scatter_rows");
@@ -905,6 +918,11 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   AA_TRY(to_side());
   AA_TRY(dep(st, sb));
   AA_TRY(dep(st, sl));
+  if (side) {   // (the late zero-fills of lane C)
+    AA_CHECK_CUDA(cudaStreamWaitEvent(sd, side->ev[ev_late], 0));
+    AA_CHECK_CUDA(cudaStreamWaitEvent(sb, side->ev[ev_late], 0));
+    AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_late], 0));
+  }
   if (tc) {
     // (outputs zero-filled on lane C at the start: accumulate, no memset nodes here.)  The step-0 term dgates_0^T h0 of dW_hh
     // rides along as B extra K rows: h0 behind the rows of h~ and the step-0 rows of dgates behind the rows of dgates

@@ -66,6 +66,8 @@ int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, i
 
 // x[0:n] *= *g unless *g == 1 (device scalar)
 int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s);
+// zero-fill of up to 8 buffers in one launch (null / empty entries are skipped)
+int launch_zero_multi(int nsegs, void* const* dst, const long long* bytes, cudaStream_t s);
 // up to 8 device-to-device copies in one launch
 int launch_copy_multi(int nsegs, const void* const* src, void* const* dst, const long long* bytes, cudaStream_t s);
 

@@ -625,6 +625,42 @@ int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, i
   return AA_OK;
 }
 
+// zero-fill of up to 8 buffers in one launch (16-byte vector stores where the buffer allows)
+namespace {
+__global__ void zero_multi_kernel(const CopySegs segs) {
+  const int sidx = blockIdx.y;
+  char* dst = static_cast<char*>(segs.dst[sidx]);
+  const long long n = segs.bytes[sidx];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const long long n16 = n >> 4;
+    for (long long i = tid; i < n16; i += nth) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
+    for (long long i = (n16 << 4) + tid; i < n; i += nth) dst[i] = 0;
+  } else {
+    for (long long i = tid; i < n; i += nth) dst[i] = 0;
+  }
+}
+}  // namespace
+
+int launch_zero_multi(int nsegs, void* const* dst, const long long* bytes, cudaStream_t s) {
+  AA_REQUIRE(nsegs >= 0 && nsegs <= 8, "zero_multi: at most 8 segments (got %d)", nsegs);
+  CopySegs segs{};
+  long long nmax = 0;
+  int n = 0;
+  for (int i = 0; i < nsegs; ++i) {
+    if (!dst[i] || bytes[i] <= 0) continue;
+    segs.dst[n] = dst[i]; segs.bytes[n] = bytes[i];
+    nmax = bytes[i] > nmax ? bytes[i] : nmax;
+    ++n;
+  }
+  if (n == 0) return AA_OK;
+  long long nb = (nmax / 16 + PW_THREADS * 4 - 1) / (PW_THREADS * 4);
+  nb = nb < 1 ? 1 : (nb > 296 ? 296 : nb);
+  zero_multi_kernel<<<dim3((unsigned)nb, n), PW_THREADS, 0, s>>>(segs);
+  AA_CHECK_LAUNCH("zero_multi");
+  return AA_OK;
+}
+
 int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s) {
   if (n == 0) return AA_OK;
   long long nb = (n + PW_THREADS * 8 - 1) / (PW_THREADS * 8);
