@@ -105,22 +105,33 @@ def sharded_sampler(model, encoded, max_len: int = 30, beam: int = 0, gather: bo
 # gradient buckets + reducer (training)
 # ---------------------------------------------------------------------------------------------
 class GradBuckets:
-    """One flat fp32 buffer per bucket with a view per parameter (``aa_weights`` field order)."""
+    """One flat fp32 buffer per bucket with a view per parameter (``aa_weights`` field order).
+
+    The buckets are carved out of ONE allocation, in bucket order, followed by a slot for the loss scalar: the last two
+    buckets (LSTM and embedding, final within a few microseconds of each other at the end of the backward) and the loss are
+    then one contiguous range, ``tail``, and go through one collective instead of three -- each NCCL all-reduce of the
+    captured step costs ~45 us whatever its size (``profiles/r01_v47_timeline_n2.txt``)."""
 
     def __init__(self, shapes: Dict[str, Sequence[int]], device, dtype=torch.float32):
         self.flat: List[torch.Tensor] = []
         self.views: Dict[str, torch.Tensor] = {}
+        layout, total = [], 0
         for fields in BUCKETS:
             sizes = [int(torch.Size(shapes[f]).numel()) for f in fields]
             # 64-element (256 B) alignment of every view: the kernels store 128-bit vectors
-            offs, total = [], 0
+            offs, start = [], total
             for n in sizes:
                 offs.append(total)
                 total += (n + 63) // 64 * 64
-            buf = torch.zeros(total, device=device, dtype=dtype)
-            self.flat.append(buf)
+            layout.append((fields, sizes, offs, start, total))
+        self.all = torch.zeros(total + 64, device=device, dtype=dtype)
+        for fields, sizes, offs, start, end in layout:
+            self.flat.append(self.all[start:end])
             for f, o, n in zip(fields, offs, sizes):
-                self.views[f] = buf[o:o + n].view(*shapes[f])
+                self.views[f] = self.all[o:o + n].view(*shapes[f])
+        self.loss = self.all[total:total + 1].view(())           # summed over ranks together with ``tail``
+        self.tail_first = len(BUCKETS) - 2                        # first bucket of the merged range
+        self.tail = self.all[layout[self.tail_first][3]:total + 64]
 
     def ordered(self) -> Tuple[torch.Tensor, ...]:
         return tuple(self.views[f] for f in WEIGHT_FIELDS)
@@ -160,20 +171,34 @@ class BucketReducer:
 
     def start(self):
         self.works, self.order = [], []
+        self._deferred: List[int] = []
+
+    def _all_reduce(self, flat: torch.Tensor, buckets: Sequence[int]):
+        if self.cuda:
+            with torch.cuda.stream(self.comm_stream):
+                for b in buckets:
+                    self.comm_stream.wait_event(self.events[b])
+                self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def on_ready(self, bucket: int):
         self.order.append(bucket)
         if self.world == 1:
             return
-        flat = self.buckets.flat[bucket]
-        if self.cuda:
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(self.events[bucket])
-                self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        last = len(BUCKETS) - 1
+        if bucket == self.buckets.tail_first:        # reduced together with the last bucket and the loss slot
+            self._deferred.append(bucket)
+        elif bucket == last and self._deferred == [self.buckets.tail_first]:
+            self._deferred = []
+            self._all_reduce(self.buckets.tail, (self.buckets.tail_first, last))
         else:
-            self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._all_reduce(self.buckets.flat[bucket], (bucket,))
 
     def finish(self):
+        for b in getattr(self, "_deferred", []):       # (a deferred bucket whose partner never came)
+            self._all_reduce(self.buckets.flat[b], (b,))
+        self._deferred = []
         if self.cuda and self.world > 1:
             with torch.cuda.stream(self.comm_stream):
                 for w in self.works:
@@ -256,7 +281,7 @@ class DataParallelTrainer:
                 "saved": u8(self.lib.aa_decoder_saved_bytes(ctypes.byref(d))),
                 "scratch": u8(self.lib.aa_decoder_bwd_scratch_bytes(ctypes.byref(d))),
                 "packed": f32(n_rows, Vc), "dpacked": f32(n_rows, Vc),
-                "loss": torch.zeros((), device=dev, dtype=torch.float32), "dV": f32(B, k, H), "dvg": f32(B, E),
+                "loss": self.buckets.loss, "dV": f32(B, k, H), "dvg": f32(B, E),
                 "dh0": f32(B, H), "dc0": f32(B, H),
             }
             if len(self._bufs) > 8:
@@ -310,10 +335,7 @@ class DataParallelTrainer:
                     self.reducer.events[i].record()
                     self.reducer.on_ready(i)
             self.reducer.finish()
-            loss = b["loss"]
-            if self.world > 1:
-                loss = loss.clone()
-                dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+            loss = b["loss"]      # (summed over ranks by the tail collective)
         for p, g in zip(self.weights, self.buckets.ordered()):
             p.grad = g
         self.input_grads = {"V": b["dV"], "v_g": b["dvg"], "h0": b["dh0"] if h0 is not None else None,

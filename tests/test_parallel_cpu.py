@@ -77,11 +77,14 @@ def _worker(rank, world, port, out):
         g = torch.Generator().manual_seed(100 + rank)
         local = {f: torch.randn(v.shape, generator=g) for f, v in gb.views.items()}
         red.start()
+        gb.loss.fill_(rank + 1.0)                            # the loss scalar rides in the last collective
         for b, fields in enumerate(par.BUCKETS):            # buckets become ready one by one, as in the backward
             for f in fields:
                 gb.views[f].copy_(local[f])
             red.on_ready(b)
+        n_coll = len(red.works)                              # LSTM + embedding + loss go through ONE all-reduce
         red.finish()
+        ok_loss = abs(float(gb.loss) - sum(r + 1.0 for r in range(world))) < 1e-6 and n_coll == len(par.BUCKETS) - 1
         # expected: sum over ranks of each rank's seeded gradients
         exp = {}
         for r in range(world):
@@ -99,7 +102,7 @@ def _worker(rank, world, port, out):
         ids_local = (torch.arange(lo, hi).view(-1, 1) * 10 + torch.arange(3).view(1, -1)).long()
         ids_all = par.gather_rows(ids_local, n_img)
         exp_ids = (torch.arange(n_img).view(-1, 1) * 10 + torch.arange(3).view(1, -1)).long()
-        out[rank] = (ok_sum, red.order == [0, 1, 2, 3], n_glob, n_glob2, torch.equal(ids_all, exp_ids))
+        out[rank] = (ok_sum and ok_loss, red.order == [0, 1, 2, 3], n_glob, n_glob2, torch.equal(ids_all, exp_ids))
     finally:
         dist.destroy_process_group()
 

@@ -17,7 +17,15 @@ from adaptive_b200.synth import CFG_A, make_inputs, make_lengths, make_weights  
 
 B, T = 80, 18
 dims = CFG_A
-dev = torch.device("cuda", 0)
+world = int(os.environ.get("WORLD_SIZE", "1"))      # under torchrun: the data-parallel step (rank 0 prints)
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
 
 
 class Cf:
@@ -32,7 +40,11 @@ lengths = make_lengths(B, T, seed=1234)
 inp = make_inputs(dims, B, T, seed=1234)
 b = {k: torch.from_numpy(v).to(dev) for k, v in inp.items()}
 b["tgt"] = torch.from_numpy(np.ascontiguousarray(F_aa.packed_targets(inp["captions"], lengths))).to(dev)
-step = GraphedTrainStep(model, b, lengths)
+if world > 1:
+    from adaptive_b200.parallel import DataParallelTrainer, GraphedDPStep
+    step = GraphedDPStep(DataParallelTrainer(model, overlap=True), b, lengths)
+else:
+    step = GraphedTrainStep(model, b, lengths)
 for _ in range(10):
     step(b)
 torch.cuda.synchronize()
@@ -42,6 +54,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         step(b)
     torch.cuda.synchronize()
+if rank != 0:
+    torch.cuda.synchronize()
+    os._exit(0)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 # split into replays at gaps > 20 us
@@ -66,3 +81,7 @@ for e in g:
         sid = getattr(e, "device_resource_id", -1)
     lane = streams.setdefault(sid, len(streams))
     print("%11.1f %9.1f %9.1f  %4d  %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, e.time_range.end - t0, lane, e.name[:110]))
+
+sys.stdout.flush()
+if world > 1:
+    os._exit(0)
