@@ -88,13 +88,14 @@ SIGNATURES = {
                                            c_size_t, P, POINTER(c_void_p), c_void_p, c_void_p]),
     "aa_decoder_forward_packed": (c_int, [_D, _W, P, P, P, P, P, P, c_int64, P, P, P, P, P, P, c_size_t, P]),
     "aa_decoder_backward_packed": (c_int, [_D, _W, P, P, P, P, P, P, P, P, c_size_t, P, c_int64, P, P, P, P, P, _G, P, P, P, P, P,
-                                           c_size_t, P, POINTER(c_void_p), c_void_p, c_void_p]),
+                                           c_size_t, P, POINTER(c_void_p), c_void_p, c_void_p, P]),
     "aa_clip_adam_step": (c_int, [P, c_int, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                   ctypes.c_float, c_int, P, P, P]),
     "aa_pack_rows": (c_int, [P, c_int64, P, c_int64, P, P]),
     "aa_unpack_rows": (c_int, [P, c_int64, P, c_int64, c_int64, P, P]),
     "aa_cross_entropy": (c_int, [P, c_int64, c_int64, P, P, P, P]),
-    "aa_scale_unless_one": (c_int, [P, P, c_int64, P]),
+    "aa_scale_unless_one": (c_int, [P, P, c_int64, P, P]),
+    "aa_cross_entropy_mirror": (c_int, [P, c_int64, c_int64, P, c_int64, P, P, P, POINTER(c_int), P]),
     "aa_copy_multi": (c_int, [c_int, P, P, P, P]),
     "aa_cross_entropy_denom": (c_int, [P, c_int64, c_int64, P, c_int64, P, P, P]),
     "aa_decode_workspace_bytes": (c_size_t, [_D, c_int]),

@@ -721,21 +721,22 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
                                  size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
                                  const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
                                  float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
-                                 aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows);
+                                 aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows, const bf16* dS16_in);
 
 static int decoder_backward_impl(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
                                  const float* h0, const float* c0, const float* alpha, const float* beta, const void* saved,
                                  size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
                                  const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
                                  float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
-                                 aa_grad_ready_fn on_ready, void* user, const int64_t* row_index = nullptr, int64_t n_rows = 0) {
+                                 aa_grad_ready_fn on_ready, void* user, const int64_t* row_index = nullptr, int64_t n_rows = 0,
+                                 const bf16* dS16_in = nullptr) {
   SideCtx* side = nullptr;
   AA_TRY(get_side(&side));
   cudaStream_t caller = (cudaStream_t)stream;
   cudaStream_t st = side ? side->crit : caller;
   AA_TRY(stream_dep(side, SIDE_EVENTS - 4, caller, st));
   AA_TRY(decoder_backward_body(d, w, V, v_g, captions, h0, c0, alpha, beta, saved, saved_bytes, d_scores, d_alpha, d_beta, d_hT, d_cT, gw, dV,
-                               dv_g, dh0, dc0, scratch, scratch_bytes, (void*)st, ready_events, on_ready, user, side, row_index, n_rows));
+                               dv_g, dh0, dc0, scratch, scratch_bytes, (void*)st, ready_events, on_ready, user, side, row_index, n_rows, dS16_in));
   return stream_dep(side, SIDE_EVENTS - 6, st, caller);
 }
 
@@ -744,7 +745,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
                                  size_t saved_bytes, const float* d_scores, const float* d_alpha, const float* d_beta,
                                  const float* d_hT, const float* d_cT, const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0,
                                  float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
-                                 aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows) {
+                                 aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows, const bf16* dS16_in) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && alpha && beta && d_scores && gw, "aa_decoder_backward: null pointer");
   AA_REQUIRE(gw->embed && gw->w_ih && gw->w_hh && gw->b_ih && gw->b_hh && gw->sen_wx && gw->sen_wh && gw->att_wv &&
@@ -820,9 +821,13 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_late], sl));
   // db_p = column sums of dS, fused with the bf16 cast of dS                     adaptive_attention.py:132
   // (packed entry point: d_scores holds the NR = n_rows packed rows only; the other positions have no gradient)
-  if (NR > 0) AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
+  // When the caller hands the bf16 mirror of dS along (aa_cross_entropy_mirror writes it in the loss kernel's own pass), nothing
+  // of this is on the critical path: the column sums only feed the bias gradient and move to lane A.
+  const bool have16 = tc && dS16_in != nullptr && NR > 0;
+  if (have16) {}
+  else if (NR > 0) AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
   else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_b, 0, sizeof(float) * Vc, st));
-  const Mat dS = M2(d_scores, Vc, sc.dS16, Vc);
+  const Mat dS = M2(d_scores, Vc, have16 ? dS16_in : sc.dS16, Vc);
 
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
   // (du is on the critical path: its contraction is enqueued before the weight gradient's so that it gets the SMs first)
@@ -833,6 +838,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   } else {
     AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, pre_dx ? sc.du : nullptr, H));
   }
+  if (have16) AA_PROF("colsum_cast_dS", sd, launch_colsum(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, sd));
   if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
   else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
   AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));
@@ -881,6 +887,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   if (side) AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_du], 0));   // the BPTT reads dh
   // BPTT                                                        baseline_attention.py:167-178
   const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
+  bool t0_rows_copied = seq;      // the cluster kernel stores the step-0 rows of dgates16 a second time behind the array
   if (seq) {
     LstmSeqBwd ls{};
     ls.B = B; ls.T = T; ls.H = H; ls.w_hh = w->w_hh;
@@ -888,10 +895,14 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
     ls.acts = sv.acts; ls.cells = sv.cells; ls.c0 = c0; ls.dgates = sc.dgates; ls.dgates16 = sc.dgates16;
     ls.dh0 = dh0; ls.dc0 = dc0; ls.whhT16 = sc.whhT16; ls.counters = sc.counters;
     ls.whh16 = sv.w16.w_hh;
+    ls.dgates16_t0 = (tc && h0) ? sc.dgates16 + (size_t)N * 4 * H : nullptr;   // (K-tail rows of the dW_hh contraction, see below)
     {
       aa::ProfScope ps("lstm_seq_bwd", st);
       int rc = launch_lstm_cluster_bwd(ls, st);
-      if (rc == AA_ERR_UNSUPPORTED) rc = launch_lstm_seq_bwd(ls, st);
+      if (rc == AA_ERR_UNSUPPORTED) {
+        rc = launch_lstm_seq_bwd(ls, st);
+        t0_rows_copied = false;
+      }
       if (rc != AA_OK) return rc;
     }
   }
@@ -928,7 +939,8 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
     // rides along as B extra K rows: h0 behind the rows of h~ and the step-0 rows of dgates behind the rows of dgates
     AA_TRY(mm_tn(cs, "gemm_lstm_dw", 4 * H, 2 * E, N, dG, X, gw->w_ih, 2 * E, true));
     int Kh = N;
-    if (h0) {
+    if (h0 && t0_rows_copied) Kh = N + B;
+    else if (h0) {
       AA_CHECK_CUDA(cudaMemcpy2DAsync(sc.dgates16 + (size_t)N * 4 * H, sizeof(bf16) * (size_t)4 * H, sc.dgates16, sizeof(bf16) * (size_t)T * 4 * H,
                                       sizeof(bf16) * (size_t)4 * H, (size_t)B, cudaMemcpyDeviceToDevice, sb));
       Kh = N + B;
@@ -978,11 +990,12 @@ int aa_decoder_backward_packed(const aa_dims* d, const aa_weights* w, const floa
                                size_t saved_bytes, const int64_t* row_index, int64_t n_rows, const float* d_scores_packed,
                                const float* d_alpha, const float* d_beta, const float* d_hT, const float* d_cT,
                                const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0, float* dc0, void* scratch,
-                               size_t scratch_bytes, void* stream, void* const* ready_events, aa_grad_ready_fn on_ready, void* user) {
+                               size_t scratch_bytes, void* stream, void* const* ready_events, aa_grad_ready_fn on_ready, void* user,
+                               const void* d_scores_packed_bf16) {
   AA_REQUIRE(row_index && d && n_rows >= 0 && n_rows <= (int64_t)d->B * d->T, "aa_decoder_backward_packed: bad row index / count");
   return decoder_backward_impl(d, w, V, v_g, captions, h0, c0, alpha, beta, saved, saved_bytes, d_scores_packed, d_alpha, d_beta, d_hT,
                                d_cT, gw, dV, dv_g, dh0, dc0, scratch, scratch_bytes, stream, ready_events, on_ready, user, row_index,
-                               n_rows);
+                               n_rows, static_cast<const bf16*>(d_scores_packed_bf16));
 }
 
 int aa_pack_rows(const float* scores, int64_t n_cols, const int64_t* row_index, int64_t n_rows, float* packed, void* stream) {
@@ -1006,14 +1019,24 @@ int aa_unpack_rows(const float* d_packed, int64_t n_cols, const int64_t* row_ind
   return AA_OK;
 }
 
-int aa_cross_entropy_denom(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom, float* loss,
-                           float* dlogits, void* stream) {
+int aa_cross_entropy_mirror(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom, float* loss,
+                            float* dlogits, void* dlogits_bf16, int* mirror_written, void* stream) {
+  if (mirror_written) *mirror_written = 0;
   AA_REQUIRE(loss, "aa_cross_entropy: loss is NULL");
-  AA_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  {   // (a kernel, not a memset node: inside a captured graph the small memset in front of the loss kernel cost a ~9 us gap)
+    void* zp[1] = {loss};
+    const long long zb[1] = {(long long)sizeof(float)};
+    AA_TRY(launch_zero_multi(1, zp, zb, (cudaStream_t)stream));
+  }
   if (n_rows == 0) return AA_OK;
   AA_REQUIRE(logits && targets, "aa_cross_entropy: null pointer");
   return launch_ce_fwd_bwd(logits, Vc, reinterpret_cast<const long long*>(targets), (int)n_rows, (int)Vc, loss, dlogits, Vc, denom,
-                           (cudaStream_t)stream);
+                           (cudaStream_t)stream, static_cast<bf16*>(dlogits_bf16), mirror_written);
+}
+
+int aa_cross_entropy_denom(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom, float* loss,
+                           float* dlogits, void* stream) {
+  return aa_cross_entropy_mirror(logits, n_rows, Vc, targets, denom, loss, dlogits, nullptr, nullptr, stream);
 }
 
 int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, float* loss, float* dlogits,
@@ -1021,9 +1044,9 @@ int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int6
   return aa_cross_entropy_denom(logits, n_rows, Vc, targets, n_rows, loss, dlogits, stream);
 }
 
-int aa_scale_unless_one(float* x, const float* g, int64_t n, void* stream) {
+int aa_scale_unless_one(float* x, const float* g, int64_t n, void* x_bf16, void* stream) {
   AA_REQUIRE(n >= 0 && (n == 0 || (x && g)), "aa_scale_unless_one: bad argument");
-  return launch_scale_unless_one(x, g, (long long)n, (cudaStream_t)stream);
+  return launch_scale_unless_one(x, g, (long long)n, (cudaStream_t)stream, static_cast<bf16*>(x_bf16));
 }
 
 int aa_copy_multi(int n_segments, const void* const* src, void* const* dst, const int64_t* bytes, void* stream) {

@@ -62,10 +62,10 @@ int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s);
 // mean cross-entropy over rows + gradient: loss += -log_softmax(logits[r])[tgt[r]] / denom ; dlogits = (softmax - onehot)/denom
 // (denom <= 0: the row count n)
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
-                      long long ldd, long long denom, cudaStream_t s);
+                      long long ldd, long long denom, cudaStream_t s, __nv_bfloat16* dlogits16 = nullptr, int* mirror_written = nullptr);
 
 // x[0:n] *= *g unless *g == 1 (device scalar)
-int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s);
+int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s, __nv_bfloat16* x16 = nullptr);
 // zero-fill of up to 8 buffers in one launch (null / empty entries are skipped)
 int launch_zero_multi(int nsegs, void* const* dst, const long long* bytes, cudaStream_t s);
 // up to 8 device-to-device copies in one launch
@@ -124,6 +124,7 @@ struct LstmSeqBwd {
   __nv_bfloat16* whhT16;              // scratch [H*4H]
   unsigned* counters;
   const __nv_bfloat16* whh16;         // optional: plain bf16 copy of w_hh [4H,H] (operand of the cluster kernels)
+  __nv_bfloat16* dgates16_t0;         // optional [B,4H]: second copy of the step-0 rows of dgates16 (cluster kernel only)
 };
 int launch_lstm_seq_bwd(const LstmSeqBwd& p, cudaStream_t s);
 int set_seq_trace_buffer(void* dev_ptr);

@@ -252,12 +252,13 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_fwd_kernel(const __gr
       tc_fence_after();
       if (elect_one()) {
         if (t + 1 < T) mbar_expect_tx(&full[p ^ 1u], step_bytes);            // arm the buffer h_t will be delivered into
-        for (int ks = 0; ks < 4 * KB; ++ks) {     // k-step = 16 units = half a row (32 B) of slice ks/2
-          // (inside a cluster the shared-window address of ranks >= 1 carries the rank in its upper bits: keep the 14-bit
-          //  start-address field clean)
-          const uint64_t db = desc0 + (((sB + (p * CL + (uint32_t)(ks >> 1)) * SLICE_BYTES + (uint32_t)(ks & 1) * 32u) & 0x3FFFFu) >> 4);
-          tc_mma_ts(tmem_base + D_COL + (uint32_t)((ks % NACC) * NB), tmem_base + (uint32_t)(ks * 8), db, IDESC, ks >= NACC ? 1u : 0u);
-        }
+        // k-step ks = 16 units = half a row (32 B) of slice ks/2: the descriptors differ from the parity's base only in the
+        // start-address field (16-byte units): + (ks/2) * 64 + (ks%2) * 2 -- one add per MMA in the unrolled loop
+        const uint64_t dbase = desc0 + (((sB + p * CL * SLICE_BYTES) & 0x3FFFFu) >> 4);
+#pragma unroll 8
+        for (int ks = 0; ks < 4 * KB; ++ks)
+          tc_mma_ts(tmem_base + D_COL + (uint32_t)((ks % NACC) * NB), tmem_base + (uint32_t)(ks * 8),
+                    dbase + (uint64_t)((ks >> 1) * (SLICE_BYTES / 16) + (ks & 1) * 2), IDESC, ks >= NACC ? 1u : 0u);
         tc_commit(tmem_full);
       }
       __syncwarp();
@@ -385,6 +386,7 @@ struct ClBwdArgs {
   const float *acts, *cells, *c0;         // saved forward state; c0 may be null (zeros)
   float* dgates; bf16* dgates16;          // [B,T,4H]
   float *dh0, *dc0;                       // [B,H] (may be null)
+  bf16* dg16_t0;                          // optional [B,4H]: second copy of the step-0 rows of dgates16
 };
 
 __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const ClBwdArgs a) {
@@ -588,6 +590,7 @@ __global__ void __launch_bounds__(CLK_THREADS, 1) lstm_clk_bwd_kernel(const __gr
           for (int g = 0; g < 4; ++g) {
             a.dgates[bt * 4 * H + (long long)g * H + j] = d[k][g];
             a.dgates16[bt * 4 * H + (long long)g * H + j] = __float2bfloat16(d[k][g]);
+            if (t == 0 && a.dg16_t0) a.dg16_t0[(long long)(m0 + b) * 4 * H + (long long)g * H + j] = __float2bfloat16(d[k][g]);
           }
         }
       }
@@ -756,6 +759,7 @@ int launch_lstm_cluster_bwd(const LstmSeqBwd& p, cudaStream_t st) {
   a.B = p.B; a.T = p.T; a.H = H; a.rpg = rpg; a.RP = RP;
   a.dh_attn = p.dh_attn; a.dhs = p.dhs; a.dcell = p.dcell; a.d_hT = p.d_hT; a.d_cT = p.d_cT;
   a.acts = p.acts; a.cells = p.cells; a.c0 = p.c0; a.dgates = p.dgates; a.dgates16 = p.dgates16; a.dh0 = p.dh0; a.dc0 = p.dc0;
+  a.dg16_t0 = p.dgates16_t0;
   void* args[] = {(void*)&tmW, (void*)&a};
   return launch_clk(kern, CL, groups, smem, st, args, false, nullptr);
 }

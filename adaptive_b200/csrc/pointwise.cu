@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(PW_THREADS) ce_fwd_bwd_kernel(const float* __r
 template <int NT, int Q4>
 __global__ void __launch_bounds__(NT) ce_fwd_bwd_reg_kernel(const float* __restrict__ logits, long long ld,
                                                             const long long* __restrict__ tgt, int Vc, float* __restrict__ loss,
-                                                            float* __restrict__ dlogits, long long ldd, float inv_n) {
+                                                            float* __restrict__ dlogits, long long ldd, float inv_n,
+                                                            bf16* __restrict__ dlogits16) {
   __shared__ float red[NT / 32];
   __shared__ float bcast[2];
   const int r = blockIdx.x;
@@ -355,6 +356,13 @@ __global__ void __launch_bounds__(NT) ce_fwd_bwd_reg_kernel(const float* __restr
           if ((t & 3) == 0) p.x -= inv_n; else if ((t & 3) == 1) p.y -= inv_n; else if ((t & 3) == 2) p.z -= inv_n; else p.w -= inv_n;
         }
         d[i] = p;
+        if (dlogits16) {   // bf16 mirror of the gradient (operand of the vocabulary projection's backward), same row stride
+          __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          reinterpret_cast<uint2*>(dlogits16 + r * ldd)[i] = pk;
+        }
       }
     }
   }
@@ -362,10 +370,14 @@ __global__ void __launch_bounds__(NT) ce_fwd_bwd_reg_kernel(const float* __restr
 
 // x *= *g unless *g == 1 (the upstream gradient of a loss that is the root of the backward pass): every CTA reads the device
 // scalar and leaves at once in the common case instead of a full read-modify-write pass over x
-__global__ void scale_unless_one_kernel(float* __restrict__ x, const float* __restrict__ g, long long n) {
+__global__ void scale_unless_one_kernel(float* __restrict__ x, const float* __restrict__ g, long long n, bf16* __restrict__ x16) {
   const float s = *g;
   if (s == 1.0f) return;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= s;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i] * s;
+    x[i] = v;
+    if (x16) x16[i] = __float2bfloat16(v);     // (keeps an optional bf16 mirror consistent)
+  }
 }
 
 // up to 8 device-to-device copies in one launch (the step's input tensors into a CUDA graph's static buffers)
@@ -611,17 +623,23 @@ int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s) {
 }
 
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,
-                      long long ldd, long long denom, cudaStream_t s) {
+                      long long ldd, long long denom, cudaStream_t s, __nv_bfloat16* dlogits16, int* mirror_written) {
+  if (mirror_written) *mirror_written = 0;
   if (n == 0) return AA_OK;
   const float inv_n = 1.f / (float)(denom > 0 ? denom : n);
   const bool vec = Vc % 4 == 0 && ld % 4 == 0 && ldd % 4 == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0;
   const int n4 = Vc / 4;
-  if (vec && n4 <= 256 * 4) ce_fwd_bwd_reg_kernel<256, 4><<<n, 256, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
-  else if (vec && n4 <= 256 * 10) ce_fwd_bwd_reg_kernel<256, 10><<<n, 256, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
-  else if (vec && n4 <= 512 * 10) ce_fwd_bwd_reg_kernel<512, 10><<<n, 512, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
-  else if (vec && n4 <= 1024 * 12) ce_fwd_bwd_reg_kernel<1024, 12><<<n, 1024, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n);
-  else ce_fwd_bwd_kernel<<<n, PW_THREADS, 0, s>>>(logits, ld, tgt, n, Vc, loss, dlogits, ldd, inv_n);
+  bf16* m16 = (vec && dlogits && (reinterpret_cast<uintptr_t>(dlogits16) & 7) == 0) ? dlogits16 : nullptr;
+  if (vec && n4 <= 256 * 4) ce_fwd_bwd_reg_kernel<256, 4><<<n, 256, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n, m16);
+  else if (vec && n4 <= 256 * 10) ce_fwd_bwd_reg_kernel<256, 10><<<n, 256, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n, m16);
+  else if (vec && n4 <= 512 * 10) ce_fwd_bwd_reg_kernel<512, 10><<<n, 512, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n, m16);
+  else if (vec && n4 <= 1024 * 12) ce_fwd_bwd_reg_kernel<1024, 12><<<n, 1024, 0, s>>>(logits, ld, tgt, Vc, loss, dlogits, ldd, inv_n, m16);
+  else {
+    m16 = nullptr;
+    ce_fwd_bwd_kernel<<<n, PW_THREADS, 0, s>>>(logits, ld, tgt, n, Vc, loss, dlogits, ldd, inv_n);
+  }
   AA_CHECK_LAUNCH("ce_fwd_bwd");
+  if (mirror_written) *mirror_written = m16 ? 1 : 0;
   return AA_OK;
 }
 
@@ -661,11 +679,11 @@ int launch_zero_multi(int nsegs, void* const* dst, const long long* bytes, cudaS
   return AA_OK;
 }
 
-int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s) {
+int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s, __nv_bfloat16* x16) {
   if (n == 0) return AA_OK;
   long long nb = (n + PW_THREADS * 8 - 1) / (PW_THREADS * 8);
   nb = nb > 1184 ? 1184 : nb;
-  scale_unless_one_kernel<<<(unsigned)nb, PW_THREADS, 0, s>>>(x, g, n);
+  scale_unless_one_kernel<<<(unsigned)nb, PW_THREADS, 0, s>>>(x, g, n, x16);
   AA_CHECK_LAUNCH("scale_unless_one");
   return AA_OK;
 }

@@ -215,7 +215,13 @@ class _DecoderPackedFn(torch.autograd.Function):
         d = make_dims(B, T, k, H, E, Vc, a, prec)
         if d_packed is None:
             d_packed = torch.zeros(n, Vc, device=dev, dtype=torch.float32)
+        # bf16 mirror of the incoming gradient, if the producer left one on the tensor (cross_entropy below does): valid only for
+        # this very tensor object, so anything autograd put in between (an accumulation, a copy) simply loses it
+        mirror = getattr(d_packed, "_aa_bf16_mirror", None)
         d_packed, d_alpha, d_beta, d_hT, d_cT = (_f32c(x) for x in (d_packed, d_alpha, d_beta, d_hT, d_cT))
+        if mirror is not None and not (mirror.shape == d_packed.shape and mirror.dtype == torch.bfloat16 and mirror.is_contiguous()
+                                       and getattr(d_packed, "_aa_bf16_mirror", None) is mirror):
+            mirror = None
         grads = [torch.empty_like(t) for t in w]
         gs = AAWeightGrads()
         for name, t in zip(WEIGHT_FIELDS, grads):
@@ -232,7 +238,7 @@ class _DecoderPackedFn(torch.autograd.Function):
                                                  _ptr(c0), _ptr(alpha), _ptr(beta), _ptr(saved), saved.numel(), _ptr(row_index), n,
                                                  _ptr(d_packed), _ptr(d_alpha), _ptr(d_beta), _ptr(d_hT), _ptr(d_cT), ctypes.byref(gs),
                                                  _ptr(dV), _ptr(dvg), _ptr(dh0), _ptr(dc0), _ptr(scratch), sbytes, _stream(dev), None, None,
-                                                 None), "aa_decoder_backward_packed")
+                                                 None, _ptr(mirror)), "aa_decoder_backward_packed")
         return (None, dV, dvg, None, dh0, dc0, None) + tuple(grads)
 
 
@@ -334,10 +340,13 @@ class _CrossEntropyFn(torch.autograd.Function):
         n, Vc = logits.shape
         loss = torch.empty((), device=logits.device, dtype=torch.float32)
         dlog = torch.empty_like(logits)
+        dlog16 = torch.empty(n, Vc, device=logits.device, dtype=torch.bfloat16)
+        written = ctypes.c_int(0)
         with torch.cuda.device(logits.device):
-            check(lib.aa_cross_entropy(_ptr(logits), n, Vc, _ptr(targets), _ptr(loss), _ptr(dlog), _stream(logits.device)),
-                  "aa_cross_entropy")
+            check(lib.aa_cross_entropy_mirror(_ptr(logits), n, Vc, _ptr(targets), n, _ptr(loss), _ptr(dlog), _ptr(dlog16),
+                                              ctypes.byref(written), _stream(logits.device)), "aa_cross_entropy_mirror")
         ctx.save_for_backward(dlog)
+        ctx.dlog16 = dlog16 if written.value else None
         return loss
 
     @staticmethod
@@ -347,7 +356,10 @@ class _CrossEntropyFn(torch.autograd.Function):
         # and is consumed once, so it is scaled in place, and only when g != 1 (decided on the device: no host sync)
         g = g.to(torch.float32).contiguous()
         with torch.cuda.device(dlog.device):
-            check(_lib.load().aa_scale_unless_one(_ptr(dlog), _ptr(g), dlog.numel(), _stream(dlog.device)), "aa_scale_unless_one")
+            check(_lib.load().aa_scale_unless_one(_ptr(dlog), _ptr(g), dlog.numel(), _ptr(ctx.dlog16), _stream(dlog.device)),
+                  "aa_scale_unless_one")
+        if ctx.dlog16 is not None:      # the vocabulary projection's backward contracts with the bf16 copy: hand it along
+            dlog._aa_bf16_mirror = ctx.dlog16
         return dlog, None
 
 

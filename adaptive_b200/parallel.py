@@ -281,6 +281,7 @@ class DataParallelTrainer:
                 "saved": u8(self.lib.aa_decoder_saved_bytes(ctypes.byref(d))),
                 "scratch": u8(self.lib.aa_decoder_bwd_scratch_bytes(ctypes.byref(d))),
                 "packed": f32(n_rows, Vc), "dpacked": f32(n_rows, Vc),
+                "dpacked16": torch.empty(n_rows, Vc, device=dev, dtype=torch.bfloat16),
                 "loss": self.buckets.loss, "dV": f32(B, k, H), "dvg": f32(B, E),
                 "dh0": f32(B, H), "dc0": f32(B, H),
             }
@@ -320,8 +321,9 @@ class DataParallelTrainer:
             check(lib.aa_decoder_forward_packed(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(row_index),
                                                 n_rows, P(b["packed"]), P(b["alpha"]), P(b["beta"]), P(b["hT"]), P(b["cT"]), P(b["saved"]),
                                                 b["saved"].numel(), st), "aa_decoder_forward_packed")
-            check(lib.aa_cross_entropy_denom(P(b["packed"]), n_rows, Vc, P(targets), denom, P(b["loss"]), P(b["dpacked"]), st),
-                  "aa_cross_entropy_denom")
+            written = ctypes.c_int(0)
+            check(lib.aa_cross_entropy_mirror(P(b["packed"]), n_rows, Vc, P(targets), denom, P(b["loss"]), P(b["dpacked"]), P(b["dpacked16"]),
+                                              ctypes.byref(written), st), "aa_cross_entropy_mirror")
             self.reducer.start()
             hooked = self.overlap and self.world > 1
             check(lib.aa_decoder_backward_packed(
@@ -329,7 +331,8 @@ class DataParallelTrainer:
                 b["saved"].numel(), P(row_index), n_rows, P(b["dpacked"]), None, None, None, None, ctypes.byref(gs), P(b["dV"]),
                 P(b["dvg"]), P(b["dh0"]) if h0 is not None else None, P(b["dc0"]) if c0 is not None else None, P(b["scratch"]),
                 b["scratch"].numel(), st, self.reducer.event_handles() if hooked else None,
-                ctypes.cast(self._cb, ctypes.c_void_p) if hooked else None, None), "aa_decoder_backward_packed")
+                ctypes.cast(self._cb, ctypes.c_void_p) if hooked else None, None, P(b["dpacked16"]) if written.value else None),
+                "aa_decoder_backward_packed")
             if self.world > 1 and not hooked:          # non-overlapped variant: same buckets, after the backward
                 for i in range(len(BUCKETS)):
                     self.reducer.events[i].record()

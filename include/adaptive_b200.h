@@ -256,7 +256,8 @@ int aa_decoder_backward_packed(const aa_dims* d, const aa_weights* w, const floa
                                size_t saved_bytes, const int64_t* row_index, int64_t n_rows, const float* d_scores_packed,
                                const float* d_alpha, const float* d_beta, const float* d_hT, const float* d_cT,
                                const aa_weight_grads* gw, float* dV, float* dv_g, float* dh0, float* dc0, void* scratch,
-                               size_t scratch_bytes, void* stream, void* const* ready_events, aa_grad_ready_fn on_ready, void* user);
+                               size_t scratch_bytes, void* stream, void* const* ready_events, aa_grad_ready_fn on_ready, void* user,
+                               const void* d_scores_packed_bf16 /* optional: bf16 mirror of d_scores_packed, see aa_cross_entropy_mirror */);
 
 /* pack_padded_sequence(scores, lengths, batch_first=True).data (baseline_attention.py:228):
  * gathers rows (b,t) with t < lengths[b] in time-major order.  row_index [n_rows] int64 holds
@@ -277,9 +278,15 @@ int aa_cross_entropy(const float* logits, int64_t n_rows, int64_t Vc, const int6
 int aa_cross_entropy_denom(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom,
                            float* loss, float* dlogits, void* stream);
 
-/* x[0:n] *= *g unless *g == 1 -- the backward of the loss above when it is not the root of the backward pass
+/* Same, and (optional) the bf16 mirror of dlogits written by the same pass -- the operand the vocabulary projection's backward
+ * contracts with; handed to aa_decoder_backward_packed as d_scores_packed_bf16 it takes the fp32 -> bf16 cast and the bias
+ * column sums off that call's critical path.  *mirror_written (host int, optional) says whether the mirror was produced (it
+ * needs Vc % 4 == 0 and 16-byte aligned rows; otherwise the backward makes its own copy as before). */
+int aa_cross_entropy_mirror(const float* logits, int64_t n_rows, int64_t Vc, const int64_t* targets, int64_t denom,
+                            float* loss, float* dlogits, void* dlogits_bf16, int* mirror_written, void* stream);
+/* x[0:n] *= *g unless *g == 1 (x_bf16: optional bf16 mirror kept consistent) -- the backward of the loss above when it is not the root of the backward pass
  * (torch.autograd hands the upstream gradient as a device scalar; `loss.backward()` at train.py:210 passes 1). */
-int aa_scale_unless_one(float* x, const float* g, int64_t n, void* stream);
+int aa_scale_unless_one(float* x, const float* g, int64_t n, void* x_bf16, void* stream);
 /* Up to 8 device-to-device copies in one launch (host-side plumbing with no reference counterpart: a step's input tensors
  * into the static buffers of a captured CUDA graph; six separate copies cost 27 us of a 500 us step). */
 int aa_copy_multi(int n_segments, const void* const* src, void* const* dst, const int64_t* bytes, void* stream);

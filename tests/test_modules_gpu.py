@@ -4,6 +4,7 @@ import pytest
 import torch
 
 import adaptive_b200
+from adaptive_b200 import functional as F_aa
 from adaptive_b200.synth import Dims, make_inputs, make_lengths, make_weights
 from oracle import adaptive_oracle as orc
 from tests.helpers import rel_err
@@ -125,3 +126,55 @@ def test_fused_clip_adam_matches_torch_clip_and_adam():
                     assert float(diff.max()) <= 1e-6, (step, i, float(diff.max()))
                 else:
                     assert float(diff.max()) <= 2e-5 and float(diff.median()) <= 2e-7, (step, i, float(diff.max()), float(diff.median()))
+
+
+@pytest.mark.parametrize("n,Vc", [(37, 10000), (5, 1000), (9, 20000), (3, 48000), (11, 1003), (1, 8)])
+def test_cross_entropy_variants_vs_torch(n, Vc):
+    """Mean CE + gradient (train.py:63,208): the register-resident kernels (one read of the logits, one exp per element) for
+    every row length class and the three-pass fallback (Vc % 4 != 0), against torch's fp64 cross_entropy; the upstream
+    gradient is applied on the device only when it is not 1."""
+    g = torch.Generator().manual_seed(n * 7 + Vc)
+    logits = (torch.randn(n, Vc, generator=g) * 3.0).cuda()
+    tgt = torch.randint(0, Vc, (n,), generator=g).cuda()
+    ref_in = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, tgt)
+    ref.backward()
+    for scale in (1.0, -2.5):
+        x = logits.clone().requires_grad_(True)
+        loss = F_aa.cross_entropy(x, tgt)
+        (loss * scale).backward()
+        assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+        err = (x.grad.double() - scale * ref_in.grad).abs().max() / ref_in.grad.abs().max()
+        assert float(err) < 1e-5, (scale, float(err))
+
+
+def test_copy_multi_and_scale_unless_one():
+    """One-launch multi-segment copy (inputs of a captured step) with mixed dtypes, odd sizes and unaligned views; in-place
+    scaling by a device scalar that is skipped bit-exactly when the scalar is 1."""
+    g = torch.Generator().manual_seed(5)
+    srcs = [torch.randn(80, 49, 512, generator=g).cuda(), torch.randn(80, 256, generator=g).cuda(),
+            torch.randint(0, 10000, (80, 18), generator=g).cuda(), torch.randn(1003, generator=g).cuda()[1:],        # 4-byte aligned only
+            torch.randint(0, 255, (77,), generator=g, dtype=torch.uint8).cuda()[3:], torch.randn(0).cuda(),
+            torch.randn(7, 3, generator=g).cuda().half(), torch.randn(2, 2, generator=g).cuda(),
+            torch.randn(33, generator=g).cuda().double(), torch.randn(5, generator=g).cuda()]                     # 10 pairs: two launches
+    dsts = [torch.zeros_like(s) for s in srcs]
+    dsts[3] = torch.zeros(1003, device="cuda")[1:]
+    dsts[4] = torch.zeros(77, dtype=torch.uint8, device="cuda")[3:]
+    F_aa.copy_multi(dsts, srcs)
+    torch.cuda.synchronize()
+    for d, s in zip(dsts, srcs):
+        assert torch.equal(d, s)
+    with pytest.raises(ValueError):
+        F_aa.copy_multi([torch.zeros(4, device="cuda")], [torch.zeros(5, device="cuda")])
+    from adaptive_b200 import _lib
+    lib = _lib.load()
+    x = torch.randn(100003, generator=g).cuda()
+    x0 = x.clone()
+    one, half = torch.ones((), device="cuda"), torch.full((), 0.5, device="cuda")
+    x16 = x.to(torch.bfloat16)
+    _lib.check(lib.aa_scale_unless_one(F_aa._ptr(x), F_aa._ptr(one), x.numel(), F_aa._ptr(x16), F_aa._stream(x.device)), "scale")
+    assert torch.equal(x, x0) and torch.equal(x16, x0.to(torch.bfloat16))
+    _lib.check(lib.aa_scale_unless_one(F_aa._ptr(x), F_aa._ptr(half), x.numel(), F_aa._ptr(x16), F_aa._stream(x.device)), "scale")
+    assert torch.equal(x, x0 * 0.5) and torch.equal(x16, (x0 * 0.5).to(torch.bfloat16))
+    _lib.check(lib.aa_scale_unless_one(F_aa._ptr(x), F_aa._ptr(half), x.numel(), None, F_aa._stream(x.device)), "scale")
+    assert torch.equal(x, x0 * 0.25)
