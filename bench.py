@@ -469,8 +469,9 @@ def run_ours(args):
     roof = {kk: k_train[dom][kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roof["kernel"] = dom
     if dom.startswith("lstm_seq"):
-        roof["note"] = ("latency-bound: %d dependent recurrence steps of a [%d x %d] x [%d x %d] contraction inside one cooperative launch; "
-                        "the HBM-bound kernels of this step and of decoding are listed under kernels" %
+        roof["note"] = ("latency-bound: %d dependent recurrence steps of a [%d x %d] x [%d x %d] contraction inside one launch (8 clusters "
+                        "of 16 CTAs, weights resident in tensor memory, state exchanged through distributed shared memory: nothing "
+                        "of a step touches HBM); the HBM-bound kernels of this step and of decoding are listed under kernels" %
                         (TRAIN_T, TRAIN_B, 4 * dims.H, 4 * dims.H, dims.H))
     roof["peak_source"] = peaks["source"]
     roof["share_of_step"] = k_train[dom]["ms_total"] / max(sum(v["ms_total"] for v in k_train.values()), 1e-9)
