@@ -178,3 +178,37 @@ def test_copy_multi_and_scale_unless_one():
     assert torch.equal(x, x0 * 0.5) and torch.equal(x16, (x0 * 0.5).to(torch.bfloat16))
     _lib.check(lib.aa_scale_unless_one(F_aa._ptr(x), F_aa._ptr(half), x.numel(), None, F_aa._stream(x.device)), "scale")
     assert torch.equal(x, x0 * 0.25)
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.25])
+def test_bf16_step_with_fused_loss_matches_torch_loss(scale):
+    """bf16 training step through the module surface: the library's loss (whose backward hands the bf16 mirror of its
+    gradient straight to the vocabulary projection's backward) against torch's own CrossEntropyLoss on the same packed scores
+    (plain autograd: the backward makes its own bf16 copy).  Same fp32 gradient, same bf16 rounding: every parameter gradient
+    must agree to fp32 accuracy, also when the loss is scaled before backward() (upstream gradient != 1)."""
+    dims = Dims(H=128, E=64, Vc=504, k=49)
+    B, T = 11, 9
+
+    class Cf2:
+        adaptive_word_embed_size, adaptive_lstm_hidden_size, vocab_length = dims.E, dims.H, dims.Vc
+
+    w = make_weights(dims, seed=71, bias_scale=0.1)
+    inp = make_inputs(dims, B, T, seed=72)
+    lengths = make_lengths(B, T, seed=73)
+    tgt = torch.from_numpy(orc.packed_targets(inp["captions"], lengths)).cuda()
+    grads = {}
+    for which in ("fused", "torch"):
+        m = adaptive_b200.Encoder2Decoder(Cf2()).cuda()
+        m.load_state_dict({"decoder." + k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+        m.decoder.precision = "bf16"
+        states = (torch.from_numpy(inp["h0"]).cuda()[:, None], torch.from_numpy(inp["c0"]).cuda()[:, None])
+        packed = m((torch.from_numpy(inp["V"]).cuda(), torch.from_numpy(inp["v_g"]).cuda(), states), torch.from_numpy(inp["captions"]).cuda(),
+                   lengths)
+        loss = F_aa.cross_entropy(packed.data, tgt) if which == "fused" else torch.nn.CrossEntropyLoss()(packed.data, tgt)
+        (loss * scale).backward()
+        grads[which] = {n: p.grad.detach().cpu().numpy() for n, p in m.decoder.named_parameters()}
+        grads[which]["loss"] = np.float64(float(loss))
+    assert abs(grads["fused"]["loss"] - grads["torch"]["loss"]) < 1e-5 * abs(grads["torch"]["loss"])
+    # (split-K contractions sum their partial tiles in a run-to-run varying order: 1e-4, not bit equality)
+    bad = {n: rel_err(grads["fused"][n], grads["torch"][n]) for n in grads["torch"] if n != "loss" and not rel_err(grads["fused"][n], grads["torch"][n]) < 1e-4}
+    assert not bad, bad
