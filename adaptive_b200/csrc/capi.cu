@@ -606,7 +606,7 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
   // Side lane, forked at once: what the recurrence does not need -- the bf16 copies of every weight but the LSTM's and of V,
   // P = V W_v^T and the sentinel gate's input half -- runs next to the main lane's casts, gate GEMM and recurrence.
   const Ctx cs{d->precision, side ? side->side : st};
-  AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
+  if (!tc) AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
   if (tc) {   // bf16 copies of the GEMM weights and of V, h0
     const float* srcs[8] = {w->w_ih, w->w_hh, w->sen_wx, w->sen_wh, w->att_wv, w->att_wg, w->att_ws, w->mlp_w};
     bf16* dsts[8] = {h.w_ih, h.w_hh, h.sen_wx, h.sen_wh, h.att_wv, h.att_wg, h.att_ws, h.mlp_w};
@@ -616,33 +616,35 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
     for (int i = 0; i < 2; ++i) { c_main.src[i] = srcs[i]; c_main.dst[i] = dsts[i]; c_main.n[i] = ns[i]; }
     for (int i = 2; i < 8; ++i) { c_side.src[i - 2] = srcs[i]; c_side.dst[i - 2] = dsts[i]; c_side.n[i - 2] = ns[i]; }
     AA_PROF("cast_weights", st, launch_cast_multi(c_main, 2, st));
-    AA_PROF("cast_weights", cs.st, launch_cast_multi(c_side, 6, cs.st));
+    // (the side lane forks behind the main lane's small cast: dispatched first, the 7000-CTA cast of the other weights kept
+    //  the main lane's first kernels waiting for ~12 us in some replays, profiles/r01_v54_timeline.txt)
+    AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
+    AA_PROF("cast_weights", cs.st, launch_cast_multi(c_side, 6, cs.st));   // (capping its grid at ~2 CTAs per SM made the step slower: 389 us)
     AA_PROF("cast_inputs", cs.st, launch_cast2d(V, H, sv.V16, H, (long long)B * d->k, H, cs.st));
-    if (h0) AA_PROF("cast_inputs", st, launch_cast2d(h0, H, sv.h016, H, B, H, st));
   }
-  // zero-fills (h~_0 = 0 rows, absent initial states): lane B, joined in front of the recurrence
-  const cudaStream_t so = side ? side->side2 : st;
-  AA_TRY(stream_dep(side, SIDE_EVENTS - 8, st, so));
-  if (tc) {
-    if (!h0) AA_CHECK_CUDA(cudaMemsetAsync(sv.h016, 0, sizeof(bf16) * (size_t)B * H, so));
-    AA_CHECK_CUDA(cudaMemset2DAsync(sv.hsprev16, (size_t)T * H * 2, 0, (size_t)H * 2, B, so));
-  }
-  if (!h0 || !c0) AA_CHECK_CUDA(cudaMemsetAsync(sv.zeros, 0, sizeof(float) * (size_t)B * H, so));
-  AA_CHECK_CUDA(cudaMemset2DAsync(sv.hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, B, so));   // h~_0 = 0 (Q2)
   const Mat Wih = M2(w->w_ih, 2 * E, h.w_ih, 2 * E), Whh = M2(w->w_hh, H, h.w_hh, H);
   const Mat Wx = M2(w->sen_wx, 2 * E, h.sen_wx, 2 * E), Wh = M2(w->sen_wh, H, h.sen_wh, H);
   const Mat Wv = M2(w->att_wv, H, h.att_wv, H), Wg = M2(w->att_wg, H, h.att_wg, H), Ws = M2(w->att_ws, H, h.att_ws, H);
   const Mat Wp = M2(w->mlp_w, H, h.mlp_w, H);
   const Mat X = M2(sv.x, 2 * E, sv.x16, 2 * E);
+  // Lane B, forked at once as well: x = [embed(w); v_g] (baseline_attention.py:151-154) next to the main lane's weight casts,
+  // then what only the recurrence needs -- the bf16 copy of h0 and the zero-fills (h~_0 = 0 rows, absent initial states)
+  const cudaStream_t so = side ? side->side2 : st;
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 8, st, so));
+  AA_TRY(launch_build_x(cap, w->embed, v_g, sv.x, sv.x16, B, T, E, d->Vc, so, sv.hs_prev, tc ? sv.hsprev16 : nullptr, H));   // (+ h~_0 = 0 rows, Q2)
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 3, so, st));          // (x is built: the gate contractions of both lanes wait for it)
+  if (side) AA_CHECK_CUDA(cudaStreamWaitEvent(cs.st, side->ev[SIDE_EVENTS - 3], 0));
+  if (tc) {
+    if (h0) AA_PROF("cast_inputs", so, launch_cast2d(h0, H, sv.h016, H, B, H, so));
+    else AA_CHECK_CUDA(cudaMemsetAsync(sv.h016, 0, sizeof(bf16) * (size_t)B * H, so));
+  }
+  if (!h0 || !c0) AA_CHECK_CUDA(cudaMemsetAsync(sv.zeros, 0, sizeof(float) * (size_t)B * H, so));
 
-  // x = [embed(w); v_g]                                        baseline_attention.py:151-154
-  AA_TRY(launch_build_x(cap, w->embed, v_g, sv.x, sv.x16, B, T, E, d->Vc, st));
-  AA_TRY(mm_nt(cs, "gemm_P", B * d->k, d->a, H, M2(V, H, sv.V16, H), Wv, sv.P, d->a, nullptr, 0, nullptr, nullptr));   // :34
-  AA_TRY(stream_dep(side, SIDE_EVENTS - 3, st, cs.st));       // (x is built)
   // input halves of the LSTM gates (main lane) and of the sentinel gate (side lane), batched over all T
   AA_TRY(mm_nt(cx, "gemm_gates_in", N, 4 * H, 2 * E, X, Wih, sv.xg, 4 * H, nullptr, 0, w->b_ih, w->b_hh));
+  AA_TRY(mm_nt(cs, "gemm_P", B * d->k, d->a, H, M2(V, H, sv.V16, H), Wv, sv.P, d->a, nullptr, 0, nullptr, nullptr));   // :34
   AA_TRY(mm_nt(cs, "gemm_gates_in", N, H, 2 * E, X, Wx, sv.g, H, nullptr, 0, nullptr, nullptr));
-  AA_TRY(stream_dep(side, SIDE_EVENTS - 9, so, st));          // (zero-fills done)
+  AA_TRY(stream_dep(side, SIDE_EVENTS - 9, so, st));          // (h0 cast and zero-fills done)
   // recurrence                                                 baseline_attention.py:167-178
   const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
   if (seq) {   // all T steps in one cooperative launch (lstm_seq.cu)
@@ -803,8 +805,15 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   AA_TRY(dep(st, sz));
   const int NR = row_index ? (int)n_rows : N;
   const bool pre_dx = tc && NR > 0;     // du's contraction adds onto a zero-filled output: no memset node in front of it
-  {   // ONE kernel per group (memset nodes carry no priority and are dispatched one by one)
-    void* zp[5] = {pre_dx ? (void*)(row_index ? sc.dup : sc.du) : nullptr, row_index ? (void*)sc.du : nullptr, (void*)gw->att_wh, (void*)sc.dP,
+  {   // ONE kernel per group (memset nodes carry no priority and are dispatched one by one).  The output of du's contraction
+      // is needed first and is small: the critical lane clears it itself instead of waiting for the whole group.
+    const bool own_dup = pre_dx && row_index;       // (unpacked: du itself is the output and is in the group anyway)
+    if (own_dup) {
+      void* zp1[1] = {(void*)sc.dup};
+      const long long zb1[1] = {(long long)sizeof(float) * NR * H};
+      AA_TRY(launch_zero_multi(1, zp1, zb1, st));
+    }
+    void* zp[5] = {(pre_dx && !own_dup) ? (void*)sc.du : nullptr, row_index ? (void*)sc.du : nullptr, (void*)gw->att_wh, (void*)sc.dP,
                    (void*)dVb};
     const long long zb[5] = {(long long)sizeof(float) * NR * H, (long long)sizeof(float) * N * H, (long long)sizeof(float) * a,
                              (long long)sizeof(float) * B * k * a, (long long)sizeof(float) * B * k * H};
@@ -832,7 +841,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   // vocabulary projection: u = c_hat + h                        adaptive_attention.py:132
   // (du is on the critical path: its contraction is enqueued before the weight gradient's so that it gets the SMs first)
   AA_TRY(to_side());
-  AA_TRY(dep(sz, st));                                         // the zero-fills of du, dV, dP, att_wh are done
+  if (!(pre_dx && row_index)) AA_TRY(dep(sz, st));             // (unpacked: du is zero-filled on the zero lane)
   if (row_index) {   // du rows of the packed positions, scattered back to [B,T,H] (zero elsewhere)
     if (NR > 0) AA_TRY(mm_nn(cx, "gemm_vocab_dx", NR, H, Vc, dS, Wp, sc.dup, H, pre_dx ? sc.dup : nullptr, H));
   } else {
@@ -842,6 +851,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
   else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
   AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));
+  if (pre_dx && row_index) AA_TRY(dep(sz, st));                // the zero-fills of du, dV, dP, att_wh are done
   if (row_index && NR > 0) {
     pack_rows_kernel<<<(unsigned)NR, 128, 0, st>>>(sc.dup, H, reinterpret_cast<const long long*>(row_index), sc.du, 0);
     AA_CHECK_LAUNCH("scatter_rows");

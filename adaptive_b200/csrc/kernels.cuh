@@ -9,7 +9,7 @@ namespace aa {
 // x[b,t,:] = [embed[cap[b,t]] ; v_g[b]]                      (baseline_attention.py:151-154)
 // (every *16 argument is an optional bf16 mirror of the fp32 output, same strides; null in fp32 mode)
 int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, __nv_bfloat16* x16, int B, int T, int E,
-                   int Vc, cudaStream_t s);
+                   int Vc, cudaStream_t s, float* zrow32 = nullptr, __nv_bfloat16* zrow16 = nullptr, int H = 0);   // zrow*: [B,T,H] arrays whose t = 0 rows are zero-filled on the way
 // one LSTM cell update from pre-activations (gate order i,f,g,o)   (baseline_attention.py:172)
 //   pre [B,4H] row stride ld_pre; c_prev [B,H] stride ld_cprev;
 //   writes acts[b, t, 4, H] (post-activation), cells[b,t,:], hiddens[b,t,:], hs_next (= h, may be null)
@@ -58,7 +58,8 @@ struct CastSegs {
   __nv_bfloat16* dst[8];
   long long n[8];
 };
-int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s);
+// (max_blocks_per_seg > 0 caps the grid: background casts that must not crowd the SMs a critical kernel is about to need)
+int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s, int max_blocks_per_seg = 0);
 // mean cross-entropy over rows + gradient: loss += -log_softmax(logits[r])[tgt[r]] / denom ; dlogits = (softmax - onehot)/denom
 // (denom <= 0: the row count n)
 int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, int n, int Vc, float* loss, float* dlogits,

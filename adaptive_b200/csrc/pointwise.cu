@@ -11,9 +11,13 @@ typedef __nv_bfloat16 bf16;
 
 __global__ void build_x_kernel(const long long* __restrict__ cap, const float* __restrict__ embed,
                                const float* __restrict__ v_g, float* __restrict__ x, bf16* __restrict__ x16, int B, int T, int E,
-                               int Vc) {
+                               int Vc, float* __restrict__ zrow32, bf16* __restrict__ zrow16, int H) {
   const int row = blockIdx.x;  // b*T + t
   const int b = row / T;
+  if (row == b * T) {   // optional side job of the t = 0 blocks: the h~_0 = 0 rows of the shifted hidden-state arrays [B,T,H]
+    if (zrow32) for (int j = threadIdx.x; j < H; j += blockDim.x) zrow32[(long long)row * H + j] = 0.f;
+    if (zrow16) for (int j = threadIdx.x; j < H; j += blockDim.x) zrow16[(long long)row * H + j] = __float2bfloat16(0.f);
+  }
   long long id = cap[row];
   id = id < 0 ? 0 : (id >= Vc ? Vc - 1 : id);
   const float* src = embed + id * (long long)E;
@@ -485,9 +489,9 @@ inline unsigned blocks_for(long long n) { return (unsigned)((n + PW_THREADS - 1)
 }  // namespace
 
 int launch_build_x(const long long* cap, const float* embed, const float* v_g, float* x, __nv_bfloat16* x16, int B, int T, int E,
-                   int Vc, cudaStream_t s) {
+                   int Vc, cudaStream_t s, float* zrow32, __nv_bfloat16* zrow16, int H) {
   if (B * T == 0) return AA_OK;
-  build_x_kernel<<<B * T, 128, 0, s>>>(cap, embed, v_g, x, x16, B, T, E, Vc);
+  build_x_kernel<<<B * T, 128, 0, s>>>(cap, embed, v_g, x, x16, B, T, E, Vc, zrow32, zrow16, H);
   AA_CHECK_LAUNCH("build_x");
   return AA_OK;
 }
@@ -611,12 +615,13 @@ int launch_cast2d(const float* src, long long ld_src, __nv_bfloat16* dst, long l
   return AA_OK;
 }
 
-int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s) {
+int launch_cast_multi(const CastSegs& segs, int nsegs, cudaStream_t s, int max_blocks_per_seg) {
   if (nsegs == 0) return AA_OK;
   long long nmax = 0;
   for (int i = 0; i < nsegs; ++i) nmax = segs.n[i] > nmax ? segs.n[i] : nmax;
   long long nb = (nmax / 4 + PW_THREADS * 4 - 1) / (PW_THREADS * 4);   // ~4 float4 per thread
-  nb = nb < 1 ? 1 : (nb > 1184 ? 1184 : nb);
+  const long long cap = max_blocks_per_seg > 0 ? max_blocks_per_seg : 1184;
+  nb = nb < 1 ? 1 : (nb > cap ? cap : nb);
   cast_multi_kernel<<<dim3((unsigned)nb, nsegs), PW_THREADS, 0, s>>>(segs);
   AA_CHECK_LAUNCH("cast_multi");
   return AA_OK;
