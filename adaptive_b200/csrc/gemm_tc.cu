@@ -8,6 +8,8 @@
 //
 // Descriptor encodings follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction
 // descriptor" tables (same bit layout as cute::UMMA::SmemDescriptor / InstrDescriptor).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tc_common.cuh"
 
@@ -447,6 +449,15 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
   const long long sms = num_sms();
   const long long mt = ceil_div(g.M, BM);
   const bool can_splitk = g_tc_splitk && g.D32 && !g.D16 && !g.pmax && ceil_div(g.K, 128 / ES) >= 8;
+  // bf16, 256-column tiles: one A k-block feeds twice the columns (48 KB per k-block for 2x the flops of a 128x128 tile's 32 KB)
+  // and a 128x256x16 MMA costs 128 cycles against 2 x 103.  Measured (tools/bench_gemm.py, r01_v58): the config-5 vocabulary
+  // projection (4608 x 20000 x 1024) 195 -> 168 us (1.12 PFLOP/s), but every K <= 512 contraction of config 2 a few per cent
+  // SLOWER (only three 48 KB stages fit next to the epilogue's transpose tiles, and a short K loop exposes the shallower
+  // pipeline): taken only for long-K problems with at least two full waves of the wide tiles.
+  if constexpr (ES == 2) {
+    static const bool bn256 = [] { const char* e = getenv("AA_GEMM_BN256"); return !e || e[0] != '0'; }();
+    if (bn256 && g.N >= 256 && !g.pmax && mt * ceil_div(g.N, 256) >= 2 * sms && ceil_div(g.K, 64) >= 16) return launch_major<256, ES, 3>(g, st);
+  }
   // widest tile the problem fills: the per-MMA cost does not depend on N, and split-K covers the SMs when it applies
   if (g.N > 64 && (can_splitk || mt * ceil_div(g.N, 128) >= sms || g.N > 2048)) return launch_major<128, ES, 5>(g, st);
   if (g.N > 32 && (can_splitk || mt * ceil_div(g.N, 64) >= sms || g.N > 512 || (g.b_mn && ES == 2))) return launch_major<64, ES, 6>(g, st);

@@ -24,6 +24,7 @@ with the ``gloo`` backend on CPU tensors and is tested that way (``tests/test_pa
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -130,7 +131,7 @@ class GradBuckets:
             for f, o, n in zip(fields, offs, sizes):
                 self.views[f] = self.all[o:o + n].view(*shapes[f])
         self.loss = self.all[total:total + 1].view(())           # summed over ranks together with ``tail``
-        self.tail_first = len(BUCKETS) - 2                        # first bucket of the merged range
+        self.tail_first = max(0, len(BUCKETS) - int(os.environ.get("AA_DP_TAIL_BUCKETS", "2")))   # first bucket of the merged range
         self.tail = self.all[layout[self.tail_first][3]:total + 64]
 
     def ordered(self) -> Tuple[torch.Tensor, ...]:
@@ -187,11 +188,12 @@ class BucketReducer:
         if self.world == 1:
             return
         last = len(BUCKETS) - 1
-        if bucket == self.buckets.tail_first:        # reduced together with the last bucket and the loss slot
+        tf = self.buckets.tail_first
+        if tf <= bucket < last:                      # reduced together with the last bucket and the loss slot
             self._deferred.append(bucket)
-        elif bucket == last and self._deferred == [self.buckets.tail_first]:
+        elif bucket == last and self._deferred == list(range(tf, last)):
             self._deferred = []
-            self._all_reduce(self.buckets.tail, (self.buckets.tail_first, last))
+            self._all_reduce(self.buckets.tail, tuple(range(tf, last + 1)))
         else:
             self._all_reduce(self.buckets.flat[bucket], (bucket,))
 

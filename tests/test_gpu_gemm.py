@@ -11,7 +11,8 @@ from adaptive_b200.functional import _ptr, _stream
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(128, 128, 64), (80, 2048, 512), (1440, 49, 512), (1360, 10000, 512), (49, 512, 3920), (257, 96, 40), (4096, 520, 776)]
+SHAPES = [(128, 128, 64), (80, 2048, 512), (1440, 49, 512), (1360, 10000, 512), (49, 512, 3920), (257, 96, 40), (4096, 520, 776),
+          (2304, 4352, 1024)]      # (the last one is large enough for the 256-column bf16 tiles)
 
 
 def _run(engine, M, N, K, a_k, b_k, with_c, with_bias, seed=0):
