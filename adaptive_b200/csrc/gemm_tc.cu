@@ -423,6 +423,10 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
     const int sms = num_sms();
     while (ksplit < 16 && num_tiles * (ksplit + 1) <= sms && nkb / (ksplit + 1) >= 4) ++ksplit;
   }
+  // fp32-accurate (3xTF32) mode serves decoding, whose results must not vary from run to run: at most TWO K ranges -- the sum of
+  // two partials onto a zero-filled output is order-independent (0 + a + b == 0 + b + a bit for bit).  The decode step's
+  // [q | r] contraction (4096 x 98 x 1024) has 32 tiles of 384 MMAs each; two ranges halve that chain.
+  if (SPLIT && g.D32 && !g.D16 && !g.pmax && !g.Cin && g_tc_splitk && nkb >= 16 && num_tiles * 2 <= num_sms()) ksplit = 2;
   e.kb_per = ceil_div(nkb, ksplit);
   ksplit = ceil_div(nkb, e.kb_per);            // no empty K ranges
   e.ksplit = ksplit;
