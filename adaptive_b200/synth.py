@@ -156,3 +156,39 @@ def make_inputs(dims: Dims, B: int, T: int, seed: int = 1234, dtype=np.float32) 
         "c0": np.ascontiguousarray(c0, dtype=dtype),
         "captions": cap,
     }
+
+
+# ---- sentinel-less baseline decoder (baseline_attention.py:66-194) --------------------------
+BASELINE_KEYS: Tuple[str, ...] = tuple(k for k in DECODER_KEYS if "sentinel" not in k and "affine_s" not in k)
+
+
+def baseline_weights(w: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """The subset of ``make_weights`` the baseline ``Decoder.state_dict()`` holds (no sentinel, no ``affine_s``)."""
+    return {k: w[k] for k in BASELINE_KEYS}
+
+
+# ---- encoder heads (baseline_attention.py:21-34; SURVEY.md §8f rank 2) --------------------------------------------
+ENCODER_KEYS: Tuple[str, ...] = ("affine_a.weight", "affine_a.bias", "affine_b.weight", "affine_b.bias",
+                                 "affine_h0.weight", "affine_h0.bias", "affine_c0.weight", "affine_c0.bias")
+
+
+def make_encoder_weights(dims: Dims, C: int = 2048, seed: int = 321, dtype=np.float32, bias_scale: float = 0.0):
+    """Head weights keyed like ``AttentiveCNN.state_dict()`` minus the trunk: kaiming-uniform(relu) for ``affine_a/b``
+    (``baseline_attention.py:29``), xavier-uniform(tanh) for ``affine_h0/c0`` (``:34``), zero biases (+ noise for tests)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w: Dict[str, np.ndarray] = {}
+    for name, rows in (("affine_a", dims.H), ("affine_b", dims.E)):
+        b = math.sqrt(2.0) * math.sqrt(3.0 / C)
+        w[name + ".weight"] = rng.uniform(-b, b, size=(rows, C))
+    for name in ("affine_h0", "affine_c0"):
+        w[name + ".weight"] = _xavier_uniform(rng, (dims.H, C), 5.0 / 3.0)
+    for name, rows in (("affine_a", dims.H), ("affine_b", dims.E), ("affine_h0", dims.H), ("affine_c0", dims.H)):
+        w[name + ".bias"] = bias_scale * rng.standard_normal(rows) if bias_scale else np.zeros(rows)
+    return {k: np.ascontiguousarray(w[k], dtype=dtype) for k in ENCODER_KEYS}
+
+
+def make_features(B: int, C: int = 2048, hw: Tuple[int, int] = (7, 7), seed: int = 4321, dtype=np.float32) -> np.ndarray:
+    """Synthetic last-conv feature maps ``[B,C,h,w]``: post-ReLU like the trunk's output, scaled so that the pooled
+    pre-activations stay O(1)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return np.ascontiguousarray(np.maximum(rng.standard_normal((B, C) + tuple(hw)), 0.0), dtype=dtype)

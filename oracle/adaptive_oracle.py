@@ -64,6 +64,12 @@ def lstm_step(W: Weights, x_t, h, c):
     return h2, c2, (i, f, g, o)
 
 
+def is_baseline(W: Weights) -> bool:
+    """True for the weights of the sentinel-less baseline decoder (``baseline_attention.py:66-194``): no sentinel,
+    no ``affine_s``."""
+    return "adaptive.sentinel.affine_x.weight" not in W
+
+
 def sentinel_forward(W: Weights, x, h_prev, cells):
     """``Sentinel.forward`` (``adaptive_attention.py:75-85``): s = σ(W_x x + W_h h̃) ⊙ tanh(c_t)."""
     ga = x @ W["adaptive.sentinel.affine_x.weight"].T + h_prev @ W["adaptive.sentinel.affine_h.weight"].T
@@ -74,9 +80,21 @@ def sentinel_forward(W: Weights, x, h_prev, cells):
 def atten_forward(W: Weights, V, h, s):
     """``Atten.forward`` (``adaptive_attention.py:26-58``).
 
-    V [B,k,H]; h,s [B,T,H] -> c_hat [B,T,H], alpha [B,T,k], beta [B,T,1] and a cache."""
+    V [B,k,H]; h,s [B,T,H] -> c_hat [B,T,H], alpha [B,T,k], beta [B,T,1] and a cache.
+
+    Without ``affine_s`` in ``W`` this is the sentinel-less ``Atten.forward`` of the baseline model
+    (``baseline_attention.py:79-100``): the same scores, softmax and context, c_hat = ctx (beta = 0)."""
     Wv = W["adaptive.atten.affine_v.weight"]
     Wg = W["adaptive.atten.affine_g.weight"]
+    if "adaptive.atten.affine_s.weight" not in W:
+        wh = W["adaptive.atten.affine_h.weight"][0]
+        P = V @ Wv.T                                                          # baseline_attention.py:88
+        q = h @ Wg.T                                                          # :89
+        tp = np.tanh(P[:, None, :, :] + q[:, :, None, :])
+        alpha = _softmax(tp @ wh)                                             # :92-93
+        ctx = alpha @ V                                                       # :96
+        beta = np.zeros(alpha.shape[:2] + (1,), dtype=alpha.dtype)
+        return ctx, alpha, beta, dict(P=P, q=q, tp=tp, alpha=alpha, ctx=ctx, tr=np.zeros_like(q), beta=beta)
     Ws = W["adaptive.atten.affine_s.weight"]
     wh = W["adaptive.atten.affine_h.weight"][0]
     P = V @ Wv.T                                  # [B,k,a]      :34
@@ -102,7 +120,10 @@ def adaptive_forward(W: Weights, x, hiddens, cells, V):
     hs_prev = np.zeros_like(hiddens)
     if T > 1:
         hs_prev[:, 1:] = hiddens[:, :-1]
-    s, g = sentinel_forward(W, x, hs_prev, cells)
+    if is_baseline(W):   # sentinel-less baseline block (baseline_attention.py:121-128): scores = mlp(c + h)
+        s, g = np.zeros_like(hiddens), np.zeros_like(hiddens)
+    else:
+        s, g = sentinel_forward(W, x, hs_prev, cells)
     c_hat, alpha, beta, cache = atten_forward(W, V, hiddens, s)
     u = c_hat + hiddens
     scores = u @ W["adaptive.mlp.weight"].T + W["adaptive.mlp.bias"]   # :132
@@ -182,11 +203,12 @@ def decoder_backward(W: Weights, cache, d_scores, d_alpha=None, d_beta=None, d_h
     E = W["embed.weight"].shape[1]
     Wv = W["adaptive.atten.affine_v.weight"]
     Wg = W["adaptive.atten.affine_g.weight"]
-    Ws = W["adaptive.atten.affine_s.weight"]
+    base = is_baseline(W)   # beta = 0: every sentinel term below vanishes
+    Ws = None if base else W["adaptive.atten.affine_s.weight"]
     wh = W["adaptive.atten.affine_h.weight"][0]
     Wp = W["adaptive.mlp.weight"]
-    Wx = W["adaptive.sentinel.affine_x.weight"]
-    Wh = W["adaptive.sentinel.affine_h.weight"]
+    Wx = None if base else W["adaptive.sentinel.affine_x.weight"]
+    Wh = None if base else W["adaptive.sentinel.affine_h.weight"]
     Wih, Whh = W["LSTM.weight_ih_l0"], W["LSTM.weight_hh_l0"]
     alpha, beta, ctx, tp, tr = cache["alpha"], cache["beta"], cache["ctx"], cache["tp"], cache["tr"]
     s, g, u, hs_prev = cache["s"], cache["g"], cache["u"], cache["hs_prev"]
@@ -220,22 +242,27 @@ def decoder_backward(W: Weights, cache, d_scores, d_alpha=None, d_beta=None, d_h
     G["adaptive.atten.affine_h.weight"] = ((dz[..., None] * tp).sum((0, 1, 2)) + (dzs[..., None] * tr).sum((0, 1)))[None, :]
     dP = dp.sum(1)                                                  # [B,k,a]
     dq = dp.sum(2) + dr                                             # [B,T,a]
-    ds = ds + dr @ Ws
-    G["adaptive.atten.affine_s.weight"] = dr.reshape(B * T, -1).T @ s.reshape(B * T, H)
+    if not base:
+        ds = ds + dr @ Ws
+        G["adaptive.atten.affine_s.weight"] = dr.reshape(B * T, -1).T @ s.reshape(B * T, H)
     dh += dq @ Wg
     G["adaptive.atten.affine_g.weight"] = dq.reshape(B * T, -1).T @ hiddens.reshape(B * T, H)
     dV = dV + dP @ Wv
     G["adaptive.atten.affine_v.weight"] = np.einsum("bka,bkh->ah", dP, V)
     # sentinel (:79-83)
     tc = np.tanh(cells)
-    dg = ds * tc
-    dcell = ds * g * (1 - tc * tc)
-    da = dg * g * (1 - g)
-    dx = da @ Wx
-    G["adaptive.sentinel.affine_x.weight"] = da.reshape(B * T, H).T @ x.reshape(B * T, -1)
-    G["adaptive.sentinel.affine_h.weight"] = da.reshape(B * T, H).T @ hs_prev.reshape(B * T, H)
-    if T > 1:
-        dh[:, :-1] += (da @ Wh)[:, 1:]                              # h̃_t = h_{t-1}, t >= 1 (Q2)
+    if base:
+        dcell = np.zeros_like(cells)
+        dx = np.zeros_like(x)
+    else:
+        dg = ds * tc
+        dcell = ds * g * (1 - tc * tc)
+        da = dg * g * (1 - g)
+        dx = da @ Wx
+        G["adaptive.sentinel.affine_x.weight"] = da.reshape(B * T, H).T @ x.reshape(B * T, -1)
+        G["adaptive.sentinel.affine_h.weight"] = da.reshape(B * T, H).T @ hs_prev.reshape(B * T, H)
+        if T > 1:
+            dh[:, :-1] += (da @ Wh)[:, 1:]                          # h̃_t = h_{t-1}, t >= 1 (Q2)
     # LSTM BPTT (baseline_attention.py:167-178)
     dWih = np.zeros_like(Wih)
     dWhh = np.zeros_like(Whh)
@@ -365,3 +392,44 @@ def beam_decode(W: Weights, V, v_g, h0, c0, beam: int = 3, max_len: int = 20):
         done = was_done | (word == END_ID)
         tok = word.reshape(-1)
     return ids[:, 0], att[:, 0], bet[:, 0][..., None], cum[:, 0]
+
+
+# --------------------------------------------------------------------------------------
+# encoder heads -- pinned by tests/golden/enc_*.npz (gen_golden.py runs the
+# reference's AttentiveCNN with its ResNet trunk replaced by nn.Identity)
+# --------------------------------------------------------------------------------------
+def encoder_forward(We: Weights, A, want_cache: bool = False):
+    """``AttentiveCNN.forward`` after the trunk (``baseline_attention.py:46-62``): A [B,C,h,w] last-conv
+    feature map -> V [B,h*w,H], v_g [B,E], h0 [B,H], c0 [B,H].  The average pool covers the whole map
+    (``AvgPool2d(7)`` on the reference's 7x7 maps, ``:46-47``)."""
+    B, C = A.shape[0], A.shape[1]
+    At = A.reshape(B, C, -1).transpose(0, 2, 1)                                   # :50
+    a_g = At.mean(axis=1)                                                         # :46-47
+    V = np.maximum(At @ We["affine_a.weight"].T + We["affine_a.bias"], 0)         # :51
+    v_g = np.maximum(a_g @ We["affine_b.weight"].T + We["affine_b.bias"], 0)      # :53
+    h0 = np.tanh(a_g @ We["affine_h0.weight"].T + We["affine_h0.bias"])           # :56
+    c0 = np.tanh(a_g @ We["affine_c0.weight"].T + We["affine_c0.bias"])           # :58
+    if want_cache:
+        return V, v_g, h0, c0, dict(At=At, a_g=a_g, V=V, v_g=v_g, h0=h0, c0=c0, shape=A.shape)
+    return V, v_g, h0, c0
+
+
+def encoder_backward(We: Weights, cache, dV, dv_g, dh0, dc0):
+    """Gradients of ``sum(dV*V) + sum(dv_g*v_g) + sum(dh0*h0) + sum(dc0*c0)`` w.r.t. the 8 head parameters and A."""
+    At, a_g = cache["At"], cache["a_g"]
+    B, hw, C = At.shape
+    G: Dict[str, np.ndarray] = {}
+    dVp = dV * (cache["V"] > 0)
+    G["affine_a.weight"] = dVp.reshape(B * hw, -1).T @ At.reshape(B * hw, C)
+    G["affine_a.bias"] = dVp.sum((0, 1))
+    dAt = dVp @ We["affine_a.weight"]
+    dag = np.zeros_like(a_g)
+    for name, up, act in (("affine_b", dv_g, "relu"), ("affine_h0", dh0, "tanh"), ("affine_c0", dc0, "tanh")):
+        out = cache[{"affine_b": "v_g", "affine_h0": "h0", "affine_c0": "c0"}[name]]
+        dp = up * (out > 0) if act == "relu" else up * (1 - out * out)
+        G[name + ".weight"] = dp.T @ a_g
+        G[name + ".bias"] = dp.sum(0)
+        dag = dag + dp @ We[name + ".weight"]
+    dAt = dAt + dag[:, None, :] / hw
+    G["A"] = dAt.transpose(0, 2, 1).reshape(cache["shape"])
+    return G

@@ -41,3 +41,29 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ---- encoder heads / baseline decoder fixtures (oracle/gen_golden.py: run_encoder_case, run_baseline_case) ----
+ENC_CASES = ("enc_tiny", "enc_odd", "enc_cfgA")
+BASE_CASES = ("base_tiny", "base_odd")
+
+
+def encoder_setup(name, dtype=np.float32):
+    from adaptive_b200.synth import make_encoder_weights, make_features
+
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    H, E, C, B, fh, fw = [int(x) for x in g["meta"]]
+    dims = Dims(H=H, E=E, Vc=8, k=fh * fw)
+    w = {k: v.astype(dtype) for k, v in make_encoder_weights(dims, C, seed=321, bias_scale=0.1).items()}
+    A = make_features(B, C, (fh, fw), seed=4321).astype(dtype)
+    rng = np.random.Generator(np.random.PCG64(77))
+    ups = [rng.standard_normal(s).astype(dtype) for s in ((B, fh * fw, H), (B, E), (B, 1, H), (B, 1, H))]
+    ups[2], ups[3] = ups[2][:, 0], ups[3][:, 0]
+    return g, dims, C, B, w, A, ups
+
+
+def baseline_setup(name, dtype=np.float32):
+    from adaptive_b200.synth import baseline_weights
+
+    g, dims, B, T, L, w, inp = golden_setup(name, dtype)
+    return g, dims, B, T, L, baseline_weights(w), inp

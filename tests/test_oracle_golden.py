@@ -107,3 +107,56 @@ def test_beam_width1_equals_greedy_and_basic_invariants():
         assert all(x == orc.END_ID for x in ids1[b][stop:])
     ids3, _, _, sc3 = orc.beam_decode(w, inp["V"], inp["v_g"], inp["h0"], inp["c0"], beam=3, max_len=L)
     assert (sc3 >= sc1 - 1e-12).all()       # a wider beam never returns a worse hypothesis here
+
+
+# ---- encoder heads; rank 4: sentinel-less baseline decoder --------------------------------
+from tests.helpers import BASE_CASES, ENC_CASES, baseline_setup, encoder_setup  # noqa: E402
+
+
+def check_grad(G, g, tag, key, tol, name=None):
+    name = name or key
+    if (tag + "_grad_" + name) in g.files:
+        assert rel_err(G[key], g[tag + "_grad_" + name]) < tol, key
+    else:
+        assert rel_err(G[key].reshape(-1)[::251], g[tag + "_grad_sub_" + name]) < tol, key
+        nrm = np.sqrt((G[key].astype(np.float64) ** 2).sum())
+        assert abs(nrm - float(g[tag + "_grad_norm_" + name])) < tol * max(nrm, 1e-30), key
+
+
+@pytest.mark.parametrize("case", ENC_CASES)
+@pytest.mark.parametrize("tag,dt,tol", [("f32", np.float32, 2e-5), ("f64", np.float64, 1e-12)])
+def test_encoder_heads_vs_reference(case, tag, dt, tol):
+    """oracle.encoder_forward/backward against the reference's AttentiveCNN (trunk = Identity)."""
+    g, dims, C, B, w, A, ups = encoder_setup(case, dt)
+    V, v_g, h0, c0, cache = orc.encoder_forward(w, A, want_cache=True)
+    for got, key in ((V, "V"), (v_g, "v_g"), (h0, "h0"), (c0, "c0")):
+        assert rel_err(got, g[tag + "_" + key]) < tol, key
+    G = orc.encoder_backward(w, cache, *ups)
+    for key in w:
+        check_grad(G, g, tag, key, tol * 20)
+    if (tag + "_grad_A") in g.files:
+        assert rel_err(G["A"], g[tag + "_grad_A"]) < tol * 20
+    else:
+        assert rel_err(G["A"].reshape(-1)[::251], g[tag + "_grad_A_sub"]) < tol * 20
+
+
+@pytest.mark.parametrize("case", BASE_CASES)
+@pytest.mark.parametrize("tag,dt,tol", [("f32", np.float32, 2e-5), ("f64", np.float64, 1e-12)])
+def test_baseline_decoder_vs_reference(case, tag, dt, tol):
+    """The oracle in sentinel-less mode against baseline_attention.Decoder (outputs, gradients, greedy ids)."""
+    g, dims, B, T, L, w, inp = baseline_setup(case, dt)
+    assert orc.is_baseline(w)
+    scores, alpha, beta, (hT, cT), cache = orc.decoder_forward(
+        w, inp["V"], inp["v_g"], inp["captions"], inp["h0"], inp["c0"], want_cache=True)
+    assert rel_err(scores, g[tag + "_scores"]) < tol
+    assert rel_err(alpha, g[tag + "_alpha"]) < tol
+    assert rel_err(hT, g[tag + "_hT"]) < tol and rel_err(cT, g[tag + "_cT"]) < tol
+    assert not beta.any()
+    dS, dA, _, _, _ = upstream(scores.shape, alpha.shape, beta.shape, hT.shape, dt)
+    G = orc.decoder_backward(w, cache, dS, dA)
+    for key in list(w) + ["V", "v_g", "h0", "c0"]:
+        assert rel_err(G[key], g[tag + "_grad_" + key]) < tol * 20, key
+    ids, att, _ = orc.greedy_decode(w, inp["V"], inp["v_g"], inp["h0"], inp["c0"], L)
+    if tag == "f64":
+        assert np.array_equal(ids, g[tag + "_greedy_ids"])
+        assert rel_err(att, g[tag + "_greedy_alpha"]) < 1e-11
