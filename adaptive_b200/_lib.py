@@ -51,8 +51,27 @@ class AAWeightGrads(Structure):
     _fields_ = [(n, P) for n in WEIGHT_FIELDS]
 
 
+class AAEncDims(Structure):
+    _fields_ = [(n, c_int32) for n in ("B", "C", "hw", "H", "E", "precision")]
+
+
+ENC_FIELDS = ("wa", "ba", "wb", "bb", "wh0", "bh0", "wc0", "bc0")
+# AttentiveCNN.state_dict() key -> aa_enc_weights field
+ENC_KEY_TO_FIELD = {"affine_a.weight": "wa", "affine_a.bias": "ba", "affine_b.weight": "wb", "affine_b.bias": "bb",
+                    "affine_h0.weight": "wh0", "affine_h0.bias": "bh0", "affine_c0.weight": "wc0", "affine_c0.bias": "bc0"}
+
+
+class AAEncWeights(Structure):
+    _fields_ = [(n, P) for n in ENC_FIELDS]
+
+
+class AAEncWeightGrads(Structure):
+    _fields_ = [(n, P) for n in ENC_FIELDS]
+
+
 # name -> (restype, argtypes); mirrors include/adaptive_b200.h one to one
 _D, _W, _G = POINTER(AADims), POINTER(AAWeights), POINTER(AAWeightGrads)
+_ED, _EW, _EG = POINTER(AAEncDims), POINTER(AAEncWeights), POINTER(AAEncWeightGrads)
 SIGNATURES = {
     "aa_version": (c_int, []),
     "aa_last_error": (c_char_p, []),
@@ -98,6 +117,10 @@ SIGNATURES = {
     "aa_cross_entropy_mirror": (c_int, [P, c_int64, c_int64, P, c_int64, P, P, P, POINTER(c_int), P]),
     "aa_copy_multi": (c_int, [c_int, P, P, P, P]),
     "aa_cross_entropy_denom": (c_int, [P, c_int64, c_int64, P, c_int64, P, P, P]),
+    "aa_encoder_saved_bytes": (c_size_t, [_ED]),
+    "aa_encoder_bwd_scratch_bytes": (c_size_t, [_ED, c_int]),
+    "aa_encoder_forward": (c_int, [_ED, _EW, P, P, P, P, P, P, c_size_t, P]),
+    "aa_encoder_backward": (c_int, [_ED, _EW, P, c_size_t, P, P, P, P, P, P, P, P, _EG, P, P, c_size_t, P]),
     "aa_decode_workspace_bytes": (c_size_t, [_D, c_int]),
     "aa_greedy_decode": (c_int, [_D, _W, P, P, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     "aa_beam_decode": (c_int, [_D, _W, P, P, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),

@@ -509,3 +509,70 @@ def adaptive_forward(w: Sequence[torch.Tensor], x, hiddens, cells, V):
                                       _ptr(scores), _ptr(alpha), _ptr(beta), _ptr(wsb), nbytes, _stream(dev)),
               "aa_adaptive_forward")
     return scores, alpha, beta
+
+
+# ---- encoder heads -------------------------------------------------------------------------
+class _EncoderFn(torch.autograd.Function):
+    """``AttentiveCNN.forward`` after the trunk (baseline_attention.py:46-62) + hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, prec, A, *w):
+        lib = _lib.load()
+        B, C, hw = A.shape
+        H, E = w[0].shape[0], w[2].shape[0]
+        shapes = [(H, C), (H,), (E, C), (E,), (H, C), (H,), (H, C), (H,)]
+        for name, t, s in zip(_lib.ENC_FIELDS, w, shapes):
+            if tuple(t.shape) != s or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("encoder weight %s must be contiguous float32 of shape %s (got %s)" % (name, s, tuple(t.shape)))
+            _need_cuda(t)
+        dev = A.device
+        d = _lib.AAEncDims(B=B, C=C, hw=hw, H=H, E=E, precision=prec)
+        V = torch.empty(B, hw, H, device=dev, dtype=torch.float32)
+        v_g = torch.empty(B, E, device=dev, dtype=torch.float32)
+        h0 = torch.empty(B, H, device=dev, dtype=torch.float32)
+        c0 = torch.empty(B, H, device=dev, dtype=torch.float32)
+        nbytes = lib.aa_encoder_saved_bytes(ctypes.byref(d))
+        saved = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        ws = _lib.AAEncWeights()
+        for name, t in zip(_lib.ENC_FIELDS, w):
+            setattr(ws, name, t.data_ptr())
+        with torch.cuda.device(dev):
+            check(lib.aa_encoder_forward(ctypes.byref(d), ctypes.byref(ws), _ptr(A), _ptr(V), _ptr(v_g), _ptr(h0), _ptr(c0),
+                                         _ptr(saved), nbytes, _stream(dev)), "aa_encoder_forward")
+        ctx.dims = (B, C, hw, H, E, prec)
+        ctx.save_for_backward(V, v_g, h0, c0, saved, *w)
+        return V, v_g, h0, c0
+
+    @staticmethod
+    def backward(ctx, dV, dv_g, dh0, dc0):
+        lib = _lib.load()
+        V, v_g, h0, c0, saved = ctx.saved_tensors[:5]
+        w = ctx.saved_tensors[5:]
+        B, C, hw, H, E, prec = ctx.dims
+        dev = V.device
+        d = _lib.AAEncDims(B=B, C=C, hw=hw, H=H, E=E, precision=prec)
+        dV, dv_g, dh0, dc0 = (_f32c(g) for g in (dV, dv_g, dh0, dc0))
+        want_dA = bool(ctx.needs_input_grad[1])
+        grads = [torch.empty_like(t) for t in w]
+        gs = _lib.AAEncWeightGrads()
+        ws = _lib.AAEncWeights()
+        for name, t, g in zip(_lib.ENC_FIELDS, w, grads):
+            setattr(ws, name, t.data_ptr())
+            setattr(gs, name, g.data_ptr())
+        dA = torch.empty(B, C, hw, device=dev, dtype=torch.float32) if want_dA else None
+        nbytes = lib.aa_encoder_bwd_scratch_bytes(ctypes.byref(d), 1 if want_dA else 0)
+        scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            check(lib.aa_encoder_backward(ctypes.byref(d), ctypes.byref(ws), _ptr(saved), saved.numel(), _ptr(V), _ptr(v_g), _ptr(h0),
+                                          _ptr(c0), _ptr(dV), _ptr(dv_g), _ptr(dh0), _ptr(dc0), ctypes.byref(gs), _ptr(dA),
+                                          _ptr(scratch), nbytes, _stream(dev)), "aa_encoder_backward")
+        return (None, dA, *grads)
+
+
+def encoder_forward(w: Sequence[torch.Tensor], A: torch.Tensor, precision: str = "fp32"):
+    """Encoder heads: ``w`` = (affine_a.weight, .bias, affine_b.weight, .bias, affine_h0.weight, .bias, affine_c0.weight, .bias),
+    ``A`` the last-conv feature map ``[B,C,h,w]`` or ``[B,C,hw]`` -> ``V [B,hw,H], v_g [B,E], h0 [B,H], c0 [B,H]``."""
+    _need_cuda(A)
+    if A.dim() == 4:
+        A = A.reshape(A.shape[0], A.shape[1], -1)
+    return _EncoderFn.apply(PRECISIONS[precision], _f32c(A), *w)

@@ -157,13 +157,15 @@ class Decoder(nn.Module):
 class AttentiveCNN(nn.Module):
     """Encoder heads of baseline_attention.py:11-62 WITHOUT the ResNet-152 trunk, which is out
     of scope (BASELINE.json north_star): ``images`` are the last-conv feature maps
-    ``[B, 2048, h, w]`` (7x7 or 14x14), synthetic in tests and benches.  The four tiny
-    ``nn.Linear`` heads run as plain library calls (not part of the measured hot path).
+    ``[B, 2048, h, w]`` (7x7 or 14x14), synthetic in tests and benches.  The four ``nn.Linear``
+    heads are parameter containers; transpose + average pool, the contractions, the activations and
+    their gradients run in ``aa_encoder_forward`` / ``aa_encoder_backward``.
     ``resnet_conv`` is an identity kept for attribute compatibility."""
 
     def __init__(self, embed_size, hidden_size, cf=None, feat_dim=2048):
         super().__init__()
         self.resnet_conv = nn.Identity()
+        self.avgpool = nn.AvgPool2d(7)          # attribute of the reference (:20); the operator pools the whole map
         self.affine_a = nn.Linear(feat_dim, hidden_size)
         self.affine_b = nn.Linear(feat_dim, embed_size)
         self.dropout = nn.Dropout(0)
@@ -171,16 +173,17 @@ class AttentiveCNN(nn.Module):
         self.affine_h0 = nn.Linear(feat_dim, hidden_size)
         self.affine_c0 = nn.Linear(feat_dim, hidden_size)
         _xavier_uniform("tanh", self.affine_h0, self.affine_c0)
+        self.precision = getattr(cf, "precision", "fp32") if cf is not None else "fp32"
+
+    def weights(self):
+        return (self.affine_a.weight, self.affine_a.bias, self.affine_b.weight, self.affine_b.bias,
+                self.affine_h0.weight, self.affine_h0.bias, self.affine_c0.weight, self.affine_c0.bias)
 
     def forward(self, images):
+        """-> V [B,hw,H], v_g [B,E], (h0, c0) each [B,1,H] (baseline_attention.py:46-62)."""
         A = self.resnet_conv(images)
-        a_g = A.mean(dim=(2, 3))                              # AvgPool2d over the whole map (:46-47)
-        V = A.view(A.size(0), A.size(1), -1).transpose(1, 2)
-        V = torch.relu(self.affine_a(V))                      # :51
-        v_g = torch.relu(self.affine_b(a_g))                  # :53
-        h0 = torch.tanh(self.affine_h0(a_g)).unsqueeze(1)     # :56-57
-        c0 = torch.tanh(self.affine_c0(a_g)).unsqueeze(1)     # :58-59
-        return V, v_g, (h0, c0)
+        V, v_g, h0, c0 = F_aa.encoder_forward(self.weights(), A, self.precision)
+        return V, v_g, (h0.unsqueeze(1), c0.unsqueeze(1))
 
 
 class _Cfg:

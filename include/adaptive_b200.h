@@ -291,6 +291,38 @@ int aa_scale_unless_one(float* x, const float* g, int64_t n, void* x_bf16, void*
  * into the static buffers of a captured CUDA graph; six separate copies cost 27 us of a 500 us step). */
 int aa_copy_multi(int n_segments, const void* const* src, void* const* dst, const int64_t* bytes, void* stream);
 
+/* ---- encoder heads: AttentiveCNN.forward after the (out-of-scope) ResNet trunk ------- */
+
+/* Shape of the heads: B images, C feature channels (2048), hw = h*w positions of the last-conv map (49 or 196),
+ * H LSTM hidden size, E word-embedding size; precision AA_PREC_FP32 (exact) or AA_PREC_BF16 (tcgen05). */
+typedef struct aa_enc_dims {
+  int32_t B, C, hw, H, E;
+  int32_t precision;
+} aa_enc_dims;
+
+/* encoder.{affine_a [H,C], affine_b [E,C], affine_h0 [H,C], affine_c0 [H,C]}.{weight, bias}   baseline_attention.py:21-34 */
+typedef struct aa_enc_weights {
+  const float *wa, *ba, *wb, *bb, *wh0, *bh0, *wc0, *bc0;
+} aa_enc_weights;
+typedef struct aa_enc_weight_grads {   /* same shapes; every buffer is OVERWRITTEN */
+  float *wa, *ba, *wb, *bb, *wh0, *bh0, *wc0, *bc0;
+} aa_enc_weight_grads;
+
+size_t aa_encoder_saved_bytes(const aa_enc_dims* d);
+size_t aa_encoder_bwd_scratch_bytes(const aa_enc_dims* d, int want_dA);
+
+/* AttentiveCNN.forward from the feature map on (baseline_attention.py:46-62):
+ *   A [B,C,hw] (the NCHW last-conv map) -> V = relu(affine_a(A^T)) [B,hw,H], v_g = relu(affine_b(a_g)) [B,E],
+ *   h0 = tanh(affine_h0(a_g)) [B,H], c0 = tanh(affine_c0(a_g)) [B,H], a_g = mean of A over the map (AvgPool2d(7) on 7x7).
+ * `saved` (aa_encoder_saved_bytes) keeps the transposed map, the pooled rows and the bf16 weight copies for the backward. */
+int aa_encoder_forward(const aa_enc_dims* d, const aa_enc_weights* w, const float* A, float* V, float* v_g, float* h0, float* c0,
+                       void* saved, size_t saved_bytes, void* stream);
+/* Gradient of the above (autograd in the reference, train.py:210): V, v_g, h0, c0 are the forward's outputs, dV ... dc0 the
+ * upstream gradients; writes the 8 parameter gradients and, when dA != NULL, the gradient towards the trunk [B,C,hw]. */
+int aa_encoder_backward(const aa_enc_dims* d, const aa_enc_weights* w, const void* saved, size_t saved_bytes, const float* V,
+                        const float* v_g, const float* h0, const float* c0, const float* dV, const float* dv_g, const float* dh0,
+                        const float* dc0, const aa_enc_weight_grads* gw, float* dA, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- decoding: Encoder2Decoder.sampler -------------------------------------------- */
 
 /* Workspace for decoding d->B images for d->T (= max_len) steps: beam = 0 -> aa_greedy_decode,
