@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(AT_THREADS) atten_fwd_kernel(const AttenFwdArg
       for (int i = lane; i < k; i += 32) sum1 += expf(zs[i] - m1);
       sum1 = warp_sum(sum1);
       const float es = expf(zsent - m1);
-      const float beta = es / (sum1 + es);
+      const float beta = p.no_sentinel ? 0.f : es / (sum1 + es);   // (sentinel-less baseline block: c_hat = ctx)
       if (lane == 0) {
         misc[0] = beta;
         p.beta[row] = beta;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(TP_THREADS) atten_fwd_tpar_kernel(const AttenF
     for (int i = lane; i < k; i += 32) sum1 += expf(z[i] - m1);
     sum1 = warp_sum(sum1);
     const float es = expf(zsent - m1);
-    const float beta = es / (sum1 + es);
+    const float beta = p.no_sentinel ? 0.f : es / (sum1 + es);   // (sentinel-less baseline block: c_hat = ctx)
     for (int i = lane; i < k; i += 32) {
       const float al = expf(z[i] - m) * inv;
       als[tl * k + i] = al;

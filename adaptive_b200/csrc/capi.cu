@@ -259,6 +259,15 @@ int check_dims(const aa_dims* d, bool need_T) {
   return AA_OK;
 }
 
+// The sentinel-less baseline model (baseline_attention.py:66-194) is the same operator with the three sentinel
+// weights absent: sen_wx, sen_wh and att_ws are NULL together.  beta is then 0 everywhere, c_hat = ctx, scores = mlp(ctx + h).
+int check_sentinel_weights(const aa_weights* w, bool* base) {
+  const int n = (w->sen_wx != nullptr) + (w->sen_wh != nullptr) + (w->att_ws != nullptr);
+  AA_REQUIRE(n == 0 || n == 3, "sen_wx, sen_wh and att_ws must be given together (adaptive model) or all be NULL (baseline model)");
+  *base = n == 0;
+  return AA_OK;
+}
+
 // dst[r, :] = src[row_index[r], :] (fp32 and, optionally, the bf16 mirror in the same launch); cols % 4 == 0
 __global__ void gather_rows2_kernel(const float* __restrict__ src, const bf16* __restrict__ src16, const long long* __restrict__ row_index,
                                     int cols, float* __restrict__ dst, bf16* __restrict__ dst16) {
@@ -288,15 +297,16 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, long long n_cols
 // attention sub-stage shared by aa_atten_forward / aa_adaptive_forward / aa_decoder_forward
 static int atten_stage(const Ctx& c, const aa_dims& d, Mat Wv, Mat Wg, Mat Ws, const float* att_wh, Mat V, Mat h, Mat s, float* P,
                        float* q, float* r, float* c_hat, float* ctx, float* u, bf16* u16, float* alpha, float* beta,
-                       bool have_P = false, bool have_q = false) {
+                       bool have_P = false, bool have_q = false, bool base = false) {
   const int N = d.B * d.T;
   if (!have_P) AA_TRY(mm_nt(c, "gemm_P", d.B * d.k, d.a, d.H, V, Wv, P, d.a, nullptr, 0, nullptr, nullptr));   // :34
   if (!have_q) AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, h, Wg, q, d.a, nullptr, 0, nullptr, nullptr));           // :35
-  AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, s, Ws, r, d.a, q, d.a, nullptr, nullptr));               // :45
+  if (!base) AA_TRY(mm_nt(c, "gemm_qr", N, d.a, d.H, s, Ws, r, d.a, q, d.a, nullptr, nullptr));    // :45   (baseline: r, s are zero-filled)
   AttenFwdArgs p{};
   p.B = d.B; p.T = d.T; p.k = d.k; p.a = d.a; p.H = d.H;
   p.P = P; p.q = q; p.r = r; p.s = s.f; p.h = h.f; p.V = V.f; p.wh = att_wh;
   p.alpha = alpha; p.beta = beta; p.ctx = ctx; p.u = u; p.c_hat = c_hat; p.u16 = u16;
+  p.no_sentinel = base ? 1 : 0;
   AA_PROF("atten_fwd", c.st, launch_atten_fwd(p, c.st));
   return AA_OK;
 }
@@ -439,7 +449,9 @@ int aa_atten_forward(const aa_dims* d, const float* att_wv, const float* att_wg,
                      const float* V, const float* h_t, const float* s_t, float* c_hat, float* alpha, float* beta,
                      void* workspace, size_t workspace_bytes, void* stream) {
   AA_TRY(check_dims(d, true));
-  AA_REQUIRE(att_wv && att_wg && att_ws && att_wh && V && h_t && s_t && c_hat && alpha && beta, "aa_atten_forward: null pointer");
+  AA_REQUIRE(att_wv && att_wg && att_wh && V && h_t && c_hat && alpha && beta, "aa_atten_forward: null pointer");
+  AA_REQUIRE((att_ws != nullptr) == (s_t != nullptr), "aa_atten_forward: att_ws and s_t go together (both NULL: baseline Atten.forward)");
+  const bool base = att_ws == nullptr;
   if (workspace_bytes < aa_atten_workspace_bytes(d) || !workspace) {
     set_error("aa_atten_forward: workspace too small (%zu < %zu)", workspace_bytes, aa_atten_workspace_bytes(d));
     return AA_ERR_WORKSPACE;
@@ -450,8 +462,12 @@ int aa_atten_forward(const aa_dims* d, const float* att_wv, const float* att_wg,
   float* q = c.take(N * d->a);
   float* r = c.take(N * d->a);
   const Ctx cx{AA_PREC_FP32, (cudaStream_t)stream};
+  if (base) {   // baseline_attention.py:79-100: the kernel still reads (finite) r and s rows -- r is cleared, h_t stands in for s_t
+    AA_CHECK_CUDA(cudaMemsetAsync(r, 0, sizeof(float) * N * d->a, cx.st));
+    s_t = h_t;
+  }
   return atten_stage(cx, *d, M32(att_wv, d->H), M32(att_wg, d->H), M32(att_ws, d->H), att_wh, M32(V, d->H), M32(h_t, d->H),
-                     M32(s_t, d->H), P, q, r, c_hat, nullptr, nullptr, nullptr, alpha, beta);
+                     M32(s_t, d->H), P, q, r, c_hat, nullptr, nullptr, nullptr, alpha, beta, false, false, base);
 }
 
 size_t aa_adaptive_workspace_bytes(const aa_dims* d) {
@@ -465,6 +481,8 @@ int aa_adaptive_forward(const aa_dims* d, const aa_weights* w, const float* x, c
                         void* stream) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && x && hiddens && cells && V && scores && alpha && beta, "aa_adaptive_forward: null pointer");
+  bool base = false;
+  AA_TRY(check_sentinel_weights(w, &base));
   if (workspace_bytes < aa_adaptive_workspace_bytes(d) || !workspace) {
     set_error("aa_adaptive_forward: workspace too small (%zu < %zu)", workspace_bytes, aa_adaptive_workspace_bytes(d));
     return AA_ERR_WORKSPACE;
@@ -480,17 +498,22 @@ int aa_adaptive_forward(const aa_dims* d, const aa_weights* w, const float* x, c
   float* g = c.take(N * H);
   float* s = c.take(N * H);
   float* u = c.take(N * H);
-  // h~: zero-h0 shift of adaptive_attention.py:116-122
-  AA_TRY(gemm_nt((int)N, H, 2 * d->E, x, 2 * d->E, w->sen_wx, 2 * d->E, g, H, nullptr, 0, nullptr, nullptr, st));
-  if (T > 1) {
-    AA_CHECK_CUDA(cudaMemset2DAsync(hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, d->B, st));
-    AA_TRY(launch_copy2d(hs_prev + H, (long long)T * H, hiddens, (long long)T * H, d->B, (T - 1) * H, st));
-    AA_TRY(gemm_nt((int)N, H, H, hs_prev, H, w->sen_wh, H, g, H, g, H, nullptr, nullptr, st));
+  if (base) {   // baseline block (baseline_attention.py:121-128): no sentinel; the attention kernel reads zero r and s rows
+    AA_CHECK_CUDA(cudaMemsetAsync(s, 0, sizeof(float) * N * H, st));
+    AA_CHECK_CUDA(cudaMemsetAsync(r, 0, sizeof(float) * N * d->a, st));
+  } else {
+    // h~: zero-h0 shift of adaptive_attention.py:116-122
+    AA_TRY(gemm_nt((int)N, H, 2 * d->E, x, 2 * d->E, w->sen_wx, 2 * d->E, g, H, nullptr, 0, nullptr, nullptr, st));
+    if (T > 1) {
+      AA_CHECK_CUDA(cudaMemset2DAsync(hs_prev, (size_t)T * H * 4, 0, (size_t)H * 4, d->B, st));
+      AA_TRY(launch_copy2d(hs_prev + H, (long long)T * H, hiddens, (long long)T * H, d->B, (T - 1) * H, st));
+      AA_TRY(gemm_nt((int)N, H, H, hs_prev, H, w->sen_wh, H, g, H, g, H, nullptr, nullptr, st));
+    }
+    AA_TRY(launch_sentinel_fwd(g, cells, g, s, nullptr, (long long)N * H, st));
   }
-  AA_TRY(launch_sentinel_fwd(g, cells, g, s, nullptr, (long long)N * H, st));
   const Ctx cx{AA_PREC_FP32, st};
   AA_TRY(atten_stage(cx, *d, M32(w->att_wv, H), M32(w->att_wg, H), M32(w->att_ws, H), w->att_wh, M32(V, H), M32(hiddens, H),
-                     M32(s, H), P, q, r, nullptr, nullptr, u, nullptr, alpha, beta));
+                     M32(s, H), P, q, r, nullptr, nullptr, u, nullptr, alpha, beta, false, false, base));
   return gemm_nt((int)N, d->Vc, H, u, H, w->mlp_w, H, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr, st);   // :132
 }
 
@@ -520,6 +543,8 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
                                 void* saved, size_t saved_bytes, void* stream, SideCtx* side, const int64_t* row_index, int64_t n_rows) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && scores && alpha && beta, "aa_decoder_forward: null pointer");
+  bool base = false;
+  AA_TRY(check_sentinel_weights(w, &base));
   if (d->B == 0) return AA_OK;
   if (!saved || saved_bytes < aa_decoder_saved_bytes(d)) {
     set_error("aa_decoder_forward: saved blob too small (%zu < %zu)", saved_bytes, aa_decoder_saved_bytes(d));
@@ -546,7 +571,7 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
                              (long long)d->a * H, (long long)d->a * H, (long long)d->Vc * H};
     CastSegs c_main{}, c_side{};
     for (int i = 0; i < 2; ++i) { c_main.src[i] = srcs[i]; c_main.dst[i] = dsts[i]; c_main.n[i] = ns[i]; }
-    for (int i = 2; i < 8; ++i) { c_side.src[i - 2] = srcs[i]; c_side.dst[i - 2] = dsts[i]; c_side.n[i - 2] = ns[i]; }
+    for (int i = 2; i < 8; ++i) { c_side.src[i - 2] = srcs[i]; c_side.dst[i - 2] = dsts[i]; c_side.n[i - 2] = srcs[i] ? ns[i] : 0; }   // (baseline: no sentinel weights)
     AA_PROF("cast_weights", st, launch_cast_multi(c_main, 2, st));
     // (the side lane forks behind the main lane's small cast: dispatched first, the 7000-CTA cast of the other weights kept
     //  the main lane's first kernels waiting for ~12 us in some replays, profiles/r01_v54_timeline.txt)
@@ -575,7 +600,12 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
   // input halves of the LSTM gates (main lane) and of the sentinel gate (side lane), batched over all T
   AA_TRY(mm_nt(cx, "gemm_gates_in", N, 4 * H, 2 * E, X, Wih, sv.xg, 4 * H, nullptr, 0, w->b_ih, w->b_hh));
   AA_TRY(mm_nt(cs, "gemm_P", B * d->k, d->a, H, M2(V, H, sv.V16, H), Wv, sv.P, d->a, nullptr, 0, nullptr, nullptr));   // :34
-  AA_TRY(mm_nt(cs, "gemm_gates_in", N, H, 2 * E, X, Wx, sv.g, H, nullptr, 0, nullptr, nullptr));
+  if (!base) AA_TRY(mm_nt(cs, "gemm_gates_in", N, H, 2 * E, X, Wx, sv.g, H, nullptr, 0, nullptr, nullptr));
+  if (base) {   // baseline model: the attention kernels (forward and backward) read s and r as zero rows, beta is forced to 0
+    void* zp[3] = {(void*)sv.s, (void*)sv.r, tc ? (void*)sv.s16 : nullptr};
+    const long long zb[3] = {(long long)sizeof(float) * N * H, (long long)sizeof(float) * N * d->a, (long long)sizeof(bf16) * N * H};
+    AA_TRY(launch_zero_multi(3, zp, zb, cs.st));
+  }
   AA_TRY(stream_dep(side, SIDE_EVENTS - 9, so, st));          // (h0 cast and zero-fills done)
   // recurrence                                                 baseline_attention.py:167-178
   const bool seq = tc && lstm_seq_supported(B, H, nullptr) && B <= 128 * 64;
@@ -617,12 +647,12 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
   AA_TRY(stream_dep(side, SIDE_EVENTS - 2, st, cs.st));
   AA_TRY(mm_nt(cs, "gemm_qr", N, d->a, H, M2(sv.hiddens, H, sv.hid16, H), Wg, sv.q, d->a, nullptr, 0, nullptr, nullptr));   // :35
   // sentinel                                                   adaptive_attention.py:116-125, 75-85
-  if (T > 1) AA_TRY(mm_nt(cx, "gemm_sentinel_h", N, H, H, M2(sv.hs_prev, H, sv.hsprev16, H), Wh, sv.g, H, sv.g, H, nullptr, nullptr));
-  AA_TRY(launch_sentinel_fwd(sv.g, sv.cells, sv.g, sv.s, sv.s16, (long long)N * H, st));
+  if (T > 1 && !base) AA_TRY(mm_nt(cx, "gemm_sentinel_h", N, H, H, M2(sv.hs_prev, H, sv.hsprev16, H), Wh, sv.g, H, sv.g, H, nullptr, nullptr));
+  if (!base) AA_TRY(launch_sentinel_fwd(sv.g, sv.cells, sv.g, sv.s, sv.s16, (long long)N * H, st));
   AA_TRY(stream_dep(side, SIDE_EVENTS - 1, cs.st, st));       // q is ready
   // attention + vocabulary projection                          adaptive_attention.py:128-132
   AA_TRY(atten_stage(cx, *d, Wv, Wg, Ws, w->att_wh, M2(V, H, sv.V16, H), M2(sv.hiddens, H, sv.hid16, H), M2(sv.s, H, sv.s16, H), sv.P,
-                     sv.q, sv.r, nullptr, sv.ctx, sv.u, sv.u16, alpha, beta, /*have_P=*/true, /*have_q=*/true));
+                     sv.q, sv.r, nullptr, sv.ctx, sv.u, sv.u16, alpha, beta, /*have_P=*/true, /*have_q=*/true, base));
   if (row_index) {   // only the rows pack_padded_sequence keeps, already in packed order (baseline_attention.py:228, Q13)
     if (n_rows == 0) return AA_OK;
     gather_rows2_kernel<<<(unsigned)n_rows, 128, 0, st>>>(sv.u, tc ? sv.u16 : nullptr, reinterpret_cast<const long long*>(row_index), H,
@@ -682,8 +712,10 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
                                  aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows, const bf16* dS16_in) {
   AA_TRY(check_dims(d, true));
   AA_REQUIRE(w && V && v_g && captions && alpha && beta && d_scores && gw, "aa_decoder_backward: null pointer");
-  AA_REQUIRE(gw->embed && gw->w_ih && gw->w_hh && gw->b_ih && gw->b_hh && gw->sen_wx && gw->sen_wh && gw->att_wv &&
-                 gw->att_wg && gw->att_ws && gw->att_wh && gw->mlp_w && gw->mlp_b,
+  bool base = false;
+  AA_TRY(check_sentinel_weights(w, &base));
+  AA_REQUIRE(gw->embed && gw->w_ih && gw->w_hh && gw->b_ih && gw->b_hh && gw->att_wv && gw->att_wg && gw->att_wh && gw->mlp_w && gw->mlp_b &&
+                 (base || (gw->sen_wx && gw->sen_wh && gw->att_ws)),
              "aa_decoder_backward: every parameter gradient buffer must be provided");
   if (d->B == 0) return AA_OK;
   if (!saved || saved_bytes < aa_decoder_saved_bytes(d)) {
@@ -803,11 +835,18 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   AA_TRY(mm_nn(cb, "gemm_att_dx", N, H, a, dQ, Wg, sc.du, H, sc.du, H));                              // dh = du + dq W_g  (lane B)
   const int ev_du = evi++;
   if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_du], sb));
-  AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, N, dR, M2(sv.s, H, sv.s16, H), gw->att_ws, H, false));
+  if (!base) AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, N, dR, M2(sv.s, H, sv.s16, H), gw->att_ws, H, false));
   AA_TRY(mm_tn(cs, "gemm_att_dw", a, H, N, dQ, M2(sv.hiddens, H, sv.hid16, H), gw->att_wg, H, false));
   if (tc) AA_PROF("cast_inputs", sb, launch_cast2d(sc.dP, a, sc.dP16, ap, (long long)B * k, a, sb));
   AA_TRY(mm_nn(cb, "gemm_att_dx", B * k, H, a, dPm, Wv, dVb, H, dVb, H));                             // dV += dP W_v
   AA_TRY(mm_tn(cb, "gemm_att_dw", a, H, B * k, dPm, M2(V, H, sv.V16, H), gw->att_wv, H, false));
+  const int ev_dx = evi++;
+  if (base) {   // baseline model: beta = 0 -> ds = 0 and dr = 0; no sentinel, so nothing reaches the cells or x from here
+    void* zp[1] = {(void*)sc.dcell};
+    const long long zb[1] = {(long long)sizeof(float) * N * H};
+    AA_TRY(launch_zero_multi(1, zp, zb, st));
+    if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_dx], sd));
+  } else {
   AA_TRY(mm_nn(cx, "gemm_att_dx", N, H, a, dR, Ws, sc.ds, H, sc.ds, H));                              // ds += dr W_s
   // sentinel                                                    adaptive_attention.py:79-83
   AA_TRY(launch_sentinel_bwd(sc.ds, sv.g, sv.cells, sc.da, sc.dcell, tc ? sc.da16 : nullptr, (long long)N * H, st));
@@ -815,7 +854,6 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   AA_TRY(to_side());
   AA_TRY(dep(st, sb));
   AA_TRY(mm_nn(cs, "gemm_sent_dx", N, 2 * E, H, dA, Wx, sc.dx, 2 * E, nullptr, 0));
-  const int ev_dx = evi++;
   if (side) AA_CHECK_CUDA(cudaEventRecord(side->ev[ev_dx], sd));
   AA_TRY(mm_tn(cs, "gemm_sent_dw", H, 2 * E, N, dA, X, gw->sen_wx, 2 * E, false));
   if (T > 1) {
@@ -823,6 +861,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
     AA_TRY(mm_tn(cb, "gemm_sent_dw", H, H, N, dA, M2(sv.hs_prev, H, sv.hsprev16, H), gw->sen_wh, H, false));
   } else {
     AA_CHECK_CUDA(cudaMemsetAsync(gw->sen_wh, 0, sizeof(float) * (size_t)H * H, sb));   // h~ = 0: no gradient (Q3)
+  }
   }
   AA_TRY(dep(sb, sd));
   AA_TRY(bucket_ready(AA_BUCKET_ATTEN, sd));   // (att_wh was finished by atten_bwd, which the side lanes have waited for)
@@ -833,7 +872,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   if (seq) {
     LstmSeqBwd ls{};
     ls.B = B; ls.T = T; ls.H = H; ls.w_hh = w->w_hh;
-    ls.dh_attn = sc.du; ls.dhs = T > 1 ? sc.dhs : nullptr; ls.dcell = sc.dcell; ls.d_hT = d_hT; ls.d_cT = d_cT;
+    ls.dh_attn = sc.du; ls.dhs = (T > 1 && !base) ? sc.dhs : nullptr; ls.dcell = sc.dcell; ls.d_hT = d_hT; ls.d_cT = d_cT;
     ls.acts = sv.acts; ls.cells = sv.cells; ls.c0 = c0; ls.dgates = sc.dgates; ls.dgates16 = sc.dgates16;
     ls.dh0 = dh0; ls.dc0 = dc0; ls.whhT16 = sc.whhT16; ls.counters = sc.counters;
     ls.whh16 = sv.w16.w_hh;
@@ -851,7 +890,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   for (int t = T - 1; t >= 0 && !seq; --t) {
     const float* dh_rec_in = t == T - 1 ? d_hT : sc.dh_rec;
     const float* dc_rec_in = t == T - 1 ? d_cT : sc.dc_rec;
-    const float* dhs_next = (T > 1 && t + 1 < T) ? sc.dhs + (size_t)(t + 1) * H : nullptr;
+    const float* dhs_next = (T > 1 && t + 1 < T && !base) ? sc.dhs + (size_t)(t + 1) * H : nullptr;
     const float* cp = t == 0 ? (c0 ? c0 : sv.zeros) : sv.cells + (size_t)(t - 1) * H;
     const long long ldcp = t == 0 ? H : (long long)T * H;
     AA_PROF("lstm_cell_bwd", st,
@@ -901,7 +940,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   AA_TRY(bucket_ready(AA_BUCKET_LSTM, sd));
   // dx += dgates W_ih needs the sentinel's dx from the side lane
   if (side) AA_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[ev_dx], 0));
-  AA_TRY(mm_nn(cx, "gemm_lstm_dx", N, 2 * E, 4 * H, dG, Wih, sc.dx, 2 * E, sc.dx, 2 * E));
+  AA_TRY(mm_nn(cx, "gemm_lstm_dx", N, 2 * E, 4 * H, dG, Wih, sc.dx, 2 * E, base ? nullptr : sc.dx, 2 * E));   // (baseline: no sentinel dx to add onto)
   // x = [embed(w); v_g]                                         baseline_attention.py:151-154   (gw->embed was zero-filled on lane C)
   AA_TRY(launch_embed_bwd(cap, sc.dx, gw->embed, dv_g, B, T, E, Vc, st));
   AA_TRY(bucket_ready(AA_BUCKET_EMBED, st));

@@ -73,6 +73,11 @@ __global__ void __launch_bounds__(DS_THREADS) decode_step_kernel(const DecodeSte
     for (int rrow = warp; rrow < 2 * a; rrow += DS_WARPS) {
       const bool is_s = rrow >= a;
       const int j = is_s ? rrow - a : rrow;
+      if (is_s && !p.Ws) {   // baseline model: no sentinel branch (r stays q, beta is forced to 0 below)
+        if (lane == 0)
+          for (int g = 0; g < G; ++g) rs[g * a + j] = 0.f;
+        continue;
+      }
       const float* wrow = (is_s ? p.Ws : p.Wg) + (long long)j * H;
       const float* act = is_s ? ss : hs;
       float acc[G];
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(DS_THREADS) decode_step_kernel(const DecodeSte
       for (int i = lane; i < k; i += 32) sum1 += expf(z[i] - m1);
       sum1 = warp_sum(sum1);
       const float es = expf(zsent - m1);
-      const float beta = es / (sum1 + es);
+      const float beta = p.Ws ? es / (sum1 + es) : 0.f;
       if (lane == 0) {
         bts[g] = beta;
         p.beta[b * p.ld_beta] = beta;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
     for (int i = lane; i < k; i += 32) sum1 += expf(zs[i] - m1);
     sum1 = warp_sum(sum1);
     const float es = expf(zsent - m1);
-    const float beta = es / (sum1 + es);
+    const float beta = p.no_sentinel ? 0.f : es / (sum1 + es);
     __syncwarp();
     for (int i = lane; i < k; i += 32) {
       const float al = expf(zs[i] - m) * inv;
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
       for (int i = lane; i < k; i += 32) sum1 += expf(z[i] - m1);
       sum1 = warp_sum(sum1);
       const float es = expf(zsent - m1);
-      const float beta = es / (sum1 + es);
+      const float beta = p.no_sentinel ? 0.f : es / (sum1 + es);
       for (int i = lane; i < k; i += 32) {
         const float al = expf(z[i] - m) * inv;
         als[j * k + i] = al;

@@ -100,7 +100,7 @@ __global__ void pack_wcat_kernel(const float* __restrict__ w_ih, const float* __
     float v = 0.f;
     if (c < K) {
       if (n < 4 * H) v = c < E ? w_ih[(long long)n * 2 * E + c] : w_hh[(long long)n * H + (c - E)];
-      else v = c < E ? sen_wx[(long long)(n - 4 * H) * 2 * E + c] : 0.f;
+      else v = (c < E && sen_wx) ? sen_wx[(long long)(n - 4 * H) * 2 * E + c] : 0.f;   // (sen_wx == null: baseline model, zero rows)
     }
     if (split) {
       float hi, lo;
@@ -122,7 +122,7 @@ __global__ void pack_wqr_kernel(const float* __restrict__ Wg, const float* __res
   for (int c = threadIdx.x; c < K2p; c += blockDim.x) {
     float v = 0.f;
     if (c < H) v = Wg[(long long)j * H + c];
-    else if (c < 2 * H && n >= a) v = Ws[(long long)j * H + (c - H)];
+    else if (c < 2 * H && n >= a && Ws) v = Ws[(long long)j * H + (c - H)];   // (Ws == null: baseline model)
     float hi, lo;
     split_tf32(v, hi, lo);
     dst[c] = hi;
@@ -327,6 +327,10 @@ __global__ void beam_backtrack_kernel(const int* __restrict__ rec_word, const in
 
 int check_decode(const aa_dims* d, const aa_weights* w, int max_len, int beam) {
   AA_REQUIRE(d && w, "decode: null dims/weights");
+  {   // the baseline model (no sentinel) passes sen_wx = sen_wh = att_ws = NULL, all three together
+    const int ns = (w->sen_wx != nullptr) + (w->sen_wh != nullptr) + (w->att_ws != nullptr);
+    AA_REQUIRE(ns == 0 || ns == 3, "decode: sen_wx, sen_wh and att_ws must be given together (adaptive) or all be NULL (baseline)");
+  }
   AA_REQUIRE(d->B >= 0 && d->k >= 1 && d->a >= 1 && d->a <= 128 && d->Vc >= 3, "decode: bad dims");
   AA_REQUIRE(d->H % 4 == 0 && d->E % 4 == 0 && d->H >= 4 && d->E >= 4, "decode: H and E must be multiples of 4");
   AA_REQUIRE(max_len >= 1, "decode: max_len must be >= 1");
@@ -377,7 +381,8 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
   // static (per image) gate terms: v_g half of x and the biases
   float* stat_img = beam > 1 ? ws.gates : ws.stat;   // [B,5H]; `gates` is free before the first step
   AA_TRY(gemm_nt(B, 4 * H, E, v_g, E, w.w_ih + E, 2 * E, stat_img, 5 * H, nullptr, 0, w.b_ih, w.b_hh, st));
-  AA_TRY(gemm_nt(B, H, E, v_g, E, w.sen_wx + E, 2 * E, stat_img + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
+  if (w.sen_wx) AA_TRY(gemm_nt(B, H, E, v_g, E, w.sen_wx + E, 2 * E, stat_img + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
+  else AA_CHECK_CUDA(cudaMemset2DAsync(stat_img + 4 * H, sizeof(float) * 5 * H, 0, sizeof(float) * H, (size_t)B, st));   // baseline model
   if (beam > 1) {
     expand_rows_kernel<<<R, 256, 0, st>>>(stat_img, ws.stat, 5 * H, beam);
     AA_CHECK_LAUNCH("expand_rows");
@@ -415,6 +420,7 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
   ap.R = R; ap.k = d.k; ap.a = d.a; ap.H = H; ap.beam = beam;
   ap.qr = ws.qr; ap.ld_qr = ws.ld_qr; ap.hs = ws.hs; ap.P = ws.P; ap.ldP = ws.ldP; ap.V = V; ap.wh = w.att_wh;
   ap.force_simple = g_force_simple_atten;
+  ap.no_sentinel = w.att_ws == nullptr;     // baseline model (baseline_attention.py:79-100): beta = 0
   ap.alpha = alpha; ap.ld_alpha = ld_alpha; ap.beta = beta; ap.ld_beta = ld_beta;
   ap.u = ws.u; ap.ld_u = ws.ldU; ap.u_lo_off = ws.Hp;
   AA_PROF("dec_step_fused", st, launch_decode_atten(ap, st));

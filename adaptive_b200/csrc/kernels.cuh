@@ -146,6 +146,8 @@ struct AttenFwdArgs {
   float *alpha, *beta, *ctx, *u;            // alpha[B,T,k] beta[B,T] ctx[B,T,H] (may be null) u[B,T,H] = c_hat + h
   float* c_hat;                             // optional [B,T,H]
   __nv_bfloat16* u16;                       // optional bf16 mirror of u
+  int no_sentinel;                          // != 0: the baseline model's block (baseline_attention.py:79-100): beta = 0, c_hat = ctx;
+                                            // r and s must still point at finite (zero-filled) rows
 };
 int launch_atten_fwd(const AttenFwdArgs& p, cudaStream_t s);
 
@@ -174,7 +176,7 @@ struct DecodeStepArgs {
   float* c;                   // [B,H]  in: c_{t-1}  out: c_t
   float* h_out; long long ld_h;   // h_t destination (A-operand of the next gate GEMM)
   const float *P, *V;         // [B/beam,k,a], [B/beam,k,H]
-  const float *Wg, *Ws, *wh;  // [a,H],[a,H],[a]
+  const float *Wg, *Ws, *wh;  // [a,H],[a,H],[a]   (Ws == null: baseline model without the sentinel, beta = 0)
   float* alpha; long long ld_alpha;   // alpha[b*ld_alpha + i]
   float* beta; long long ld_beta;
   float* u; long long ld_u;   // u = c_hat + h, row stride ld_u (0 = H)
@@ -202,6 +204,7 @@ struct DecodeAttenArgs {
   const float *P, *V, *wh;    // [R/beam,k,ldP >= a], [R/beam,k,H], [a]
   long long ldP;              // row stride of P (a multiple of 4 enables the bulk-copy pipeline)
   int force_simple;           // != 0: always take the register-staged kernel (tests)
+  int no_sentinel;            // != 0: baseline model (no sentinel): beta = 0, c_hat = ctx
   float* alpha; long long ld_alpha;
   float* beta; long long ld_beta;
   float* u; long long ld_u, u_lo_off;    // u = c_hat + h as tf32 (hi, lo): hi at [0,H), lo at [u_lo_off, u_lo_off+H)

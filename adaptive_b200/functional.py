@@ -16,6 +16,14 @@ from . import _lib
 from ._lib import AADims, AAWeightGrads, AAWeights, KEY_TO_FIELD, WEIGHT_FIELDS, check
 
 ATT_DIM = 49
+# aa_weights fields the baseline model (baseline_attention.py:66-194) does not have: passed as None / NULL
+SENTINEL_FIELDS = ("sen_wx", "sen_wh", "att_ws")
+
+
+def baseline_weights(w: Sequence[Optional[torch.Tensor]]) -> Tuple[Optional[torch.Tensor], ...]:
+    """13-tuple in ``aa_weights`` order with the three sentinel weights dropped (None): the baseline decoder."""
+    return tuple(None if name in SENTINEL_FIELDS else t for name, t in zip(WEIGHT_FIELDS, w))
+
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -68,7 +76,8 @@ def make_dims(B, T, k, H, E, Vc, a=ATT_DIM, precision=_lib.PREC_FP32) -> AADims:
 def weights_struct(w: Sequence[torch.Tensor]) -> AAWeights:
     s = AAWeights()
     for name, t in zip(WEIGHT_FIELDS, w):
-        setattr(s, name, t.data_ptr())
+        if t is not None:      # (None = NULL: the sentinel weights of the baseline model)
+            setattr(s, name, t.data_ptr())
     return s
 
 
@@ -81,7 +90,13 @@ def ordered_weights(named: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, ...]:
 def _check_weights(w: Sequence[torch.Tensor], H, E, Vc, a):
     shapes = [(Vc, E), (4 * H, 2 * E), (4 * H, H), (4 * H,), (4 * H,), (H, 2 * E), (H, H), (a, H), (a, H), (a, H),
               (1, a), (Vc, H), (Vc,)]
+    absent = [name for name, t in zip(WEIGHT_FIELDS, w) if t is None]
+    if absent and sorted(absent) != sorted(SENTINEL_FIELDS):
+        raise ValueError("weights %s are missing: only sen_wx, sen_wh and att_ws may be None, and only together "
+                         "(the sentinel-less baseline decoder)" % absent)
     for name, t, s in zip(WEIGHT_FIELDS, w, shapes):
+        if t is None:
+            continue
         if tuple(t.shape) != s:
             raise ValueError("weight %s has shape %s, expected %s" % (name, tuple(t.shape), s))
         if t.dtype != torch.float32 or not t.is_contiguous():
@@ -135,10 +150,11 @@ class _DecoderFn(torch.autograd.Function):
         if d_scores is None:
             d_scores = torch.zeros(B, T, Vc, device=dev, dtype=torch.float32)
         d_scores, d_alpha, d_beta, d_hT, d_cT = (_f32c(x) for x in (d_scores, d_alpha, d_beta, d_hT, d_cT))
-        grads = [torch.empty_like(t) for t in w]
+        grads = [torch.empty_like(t) if t is not None else None for t in w]
         gs = AAWeightGrads()
         for name, t in zip(WEIGHT_FIELDS, grads):
-            setattr(gs, name, t.data_ptr())
+            if t is not None:
+                setattr(gs, name, t.data_ptr())
         dV = torch.empty_like(V)
         dvg = torch.empty_like(v_g)
         dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if h0 is not None else None
@@ -222,10 +238,11 @@ class _DecoderPackedFn(torch.autograd.Function):
         if mirror is not None and not (mirror.shape == d_packed.shape and mirror.dtype == torch.bfloat16 and mirror.is_contiguous()
                                        and getattr(d_packed, "_aa_bf16_mirror", None) is mirror):
             mirror = None
-        grads = [torch.empty_like(t) for t in w]
+        grads = [torch.empty_like(t) if t is not None else None for t in w]
         gs = AAWeightGrads()
         for name, t in zip(WEIGHT_FIELDS, grads):
-            setattr(gs, name, t.data_ptr())
+            if t is not None:
+                setattr(gs, name, t.data_ptr())
         dV = torch.empty_like(V)
         dvg = torch.empty_like(v_g)
         dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if h0 is not None else None
