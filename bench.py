@@ -225,6 +225,111 @@ def rooflines(report, models, peaks):
     return out
 
 
+def measure_widened(torch, dev, dims, peaks, steps):
+    """SURVEY 8f rows built beyond the headline path, measured on one GPU at BASELINE config 2/3 sizes (N = 1 only):
+    the encoder heads (aa_encoder_forward / aa_encoder_backward, bf16) and the sentinel-less baseline decoder (train step
+    and greedy decode).  Each timed as a replayed CUDA graph (training) / as the plain call (decode), CUDA events."""
+    import adaptive_b200
+    from adaptive_b200 import _lib, baseline
+    from adaptive_b200 import functional as F_aa
+    from adaptive_b200.graphs import GraphedTrainStep
+    from adaptive_b200.synth import baseline_weights, make_encoder_weights, make_features
+
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # ---- encoder heads: B = 80 feature maps [2048, 7, 7] -> V, v_g, h0, c0 and back (all 8 parameter gradients + dA) ----
+    C, hw = 2048, (7, 7)
+    ew = make_encoder_weights(dims, C, seed=321)
+    W = tuple(torch.from_numpy(ew[k]).to(dev).requires_grad_(True) for k in
+              ("affine_a.weight", "affine_a.bias", "affine_b.weight", "affine_b.bias", "affine_h0.weight", "affine_h0.bias",
+               "affine_c0.weight", "affine_c0.bias"))
+    A = torch.from_numpy(make_features(TRAIN_B, C, hw, seed=4321)).to(dev).requires_grad_(True)
+    ups = None
+
+    def enc_step():
+        nonlocal ups
+        for t in W + (A,):
+            t.grad = None
+        outs = F_aa.encoder_forward(W, A, "bf16")
+        if ups is None:
+            ups = [torch.randn_like(o) for o in outs]
+        torch.autograd.backward(outs, ups)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            enc_step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        enc_step()
+    for _ in range(3):
+        g.replay()
+    ms = timed(g.replay, max(steps, 10))
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    for _ in range(5):
+        enc_step()
+    torch.cuda.synchronize()
+    _lib.profile_enable(False)
+    rep = _lib.profile_report()
+    _lib.profile_reset()
+    M, k = TRAIN_B * hw[0] * hw[1], hw[0] * hw[1]
+    fl = lambda m, n, kk: 2.0 * m * n * kk
+    models = {
+        # one pass over the NCHW map: fp32 in, bf16 transpose + pooled rows (fp32 + bf16) out
+        "enc_transpose_pool": ("hbm", float(TRAIN_B) * C * (k * 4 + k * 2 + 4 + 2)),
+        "enc_untranspose": ("hbm", float(TRAIN_B) * C * (k * 4 + k * 4 + 4)),
+        "enc_gemm_V": ("tensor", fl(M, dims.H, C)), "enc_gemm_dWa": ("tensor", fl(dims.H, C, M)), "enc_gemm_dA": ("tensor", fl(M, C, dims.H)),
+    }
+    out["encoder_heads"] = {
+        "workload": "AttentiveCNN heads fwd+bwd (affine_a/b/h0/c0 + average pool, incl. dA), batch %d, [2048,7,7] maps, bf16" % TRAIN_B,
+        "value": TRAIN_B / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "cuda_graph": True,
+        "algorithmic_tflops": (3 * fl(M, dims.H, C) + 3 * fl(TRAIN_B, dims.E + 2 * dims.H, C)) / (ms * 1e-3) / 1e12,
+        "kernels": rooflines(rep, models, peaks),
+    }
+
+    # ---- sentinel-less baseline decoder: same shapes as the headline (config 2) and as config 3 ----
+    class Cf:
+        base_word_embed_size, base_lstm_hidden_size, vocab_length = dims.E, dims.H, dims.Vc
+        precision = "bf16"
+
+    bm = baseline.Encoder2Decoder(Cf()).to(dev)
+    bw = baseline_weights(make_weights(dims, seed=123))
+    bm.decoder.load_state_dict({k: torch.from_numpy(v) for k, v in bw.items()}, strict=True)
+    lengths = make_lengths(TRAIN_B, TRAIN_T, seed=1234)
+    inp = make_inputs(dims, TRAIN_B, TRAIN_T, seed=1234)
+    b = {k: torch.from_numpy(v).to(dev) for k, v in inp.items()}
+    b["tgt"] = torch.from_numpy(np.ascontiguousarray(F_aa.packed_targets(inp["captions"], lengths))).to(dev)
+    stepper = GraphedTrainStep(bm, b, lengths)
+    for _ in range(3):
+        stepper(b)
+    ms = timed(lambda: stepper(b), max(steps, 10))
+    dinp = make_inputs(dims, DECODE_B, 1, seed=4321)
+    db = {k: torch.from_numpy(dinp[k]).to(dev) for k in ("V", "v_g", "h0", "c0")}
+    dec = lambda: bm.sampler((db["V"], db["v_g"], (db["h0"], db["c0"])), max_len=DECODE_L)
+    dec()
+    dms = timed(dec, 3)
+    out["baseline_decoder"] = {
+        "workload": "baseline_attention.py model (no sentinel), config 2 / config 3 shapes",
+        "train": {"value": TRAIN_B * TRAIN_T / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "cuda_graph": True, "dtype": "bf16"},
+        "decode": {"value": DECODE_B * DECODE_L / (dms * 1e-3), "unit": "tokens/s", "ms_per_step": dms, "precision": bm.decoder.decode_precision},
+    }
+    return out
+
+
 _T0 = time.time()
 
 
@@ -455,6 +560,11 @@ def run_ours(args):
     dec_report = _lib.profile_report()
     _lib.profile_reset()
 
+    widened = None
+    if world == 1 and not args.no_widened:
+        stage("widened rows (encoder heads, baseline decoder)")
+        widened = measure_widened(torch, dev, dims, peaks, args.steps)
+
     stage("report")
     if world > 1:
         dist.barrier()
@@ -495,6 +605,8 @@ def run_ours(args):
                    "precision": model.decoder.decode_precision,
                    "roofline_fused_step": k_dec.get("dec_step_fused")},
     }
+    if widened is not None:
+        out["widened"] = widened
     if n_gpus == 1:
         cores = os.cpu_count() or 1
         step = oracle_train_step_fn(TRAIN_B, TRAIN_T, dims)
@@ -536,6 +648,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="training path: bf16 tensor cores (BASELINE config 2) or exact fp32")
     ap.add_argument("--graph", type=int, default=1, help="replay the training step as one CUDA graph (1) or launch eagerly (0)")
     ap.add_argument("--overlap", type=int, default=1, help="N>1: start each gradient bucket's all-reduce as soon as the backward finishes it")
+    ap.add_argument("--no-widened", action="store_true", help="skip the extra measurements of the SURVEY 8f rows (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
