@@ -84,6 +84,8 @@ SIGNATURES = {
     "aa_debug_set_trace_buffer": (c_int, [P]),
     "aa_debug_set_decode_atten_simple": (c_int, [c_int]),
     "aa_debug_set_atten_sequential": (c_int, [c_int]),
+    "aa_debug_set_decode_argmax_refine": (c_int, [c_int]),
+    "aa_debug_refine_pairs": (ctypes.c_longlong, [c_int]),
     "aa_debug_set_gemm_splitk": (c_int, [c_int]),
     "aa_debug_set_bptt_ksplit": (c_int, [c_int]),
     "aa_debug_set_lstm_cluster": (c_int, [c_int, c_int]),

@@ -11,6 +11,15 @@ namespace aa {
 
 namespace {
 
+// bf16 mirror of four consecutive values (operand of the single-pass arg-max contraction, vocab_refine.cu)
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, const float4& v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&a);
+  pk.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dst) = pk;
+}
+
 constexpr int DS_THREADS = 256;
 constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int G = 4;  // images per group: W_g/W_s rows are read once per group
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
         split_tf32(o.x, hi.x, lo.x); split_tf32(o.y, hi.y, lo.y); split_tf32(o.z, hi.z, lo.z); split_tf32(o.w, hi.w, lo.w);
         *reinterpret_cast<float4*>(urow + c) = hi;
         *reinterpret_cast<float4*>(urow + p.u_lo_off + c) = lo;
+        if (p.u16) store_bf16x4(p.u16 + r * p.ld_u16 + c, o);
       }
     }
     __syncwarp();   // zs is reused by this warp's next row
@@ -642,6 +652,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
           float* urow = p.u + (r0 + j) * p.ld_u + vec * 4;
           *reinterpret_cast<float4*>(urow) = hi;
           *reinterpret_cast<float4*>(urow + p.u_lo_off) = lo;
+          if (p.u16) store_bf16x4(p.u16 + (r0 + j) * p.ld_u16 + vec * 4, o);
         }
       }
     }

@@ -2,6 +2,7 @@
 // Encoder2Decoder.sampler (adaptive_attention.py:186-216) runs on the device, four launches
 // per step (gate GEMM, fused step kernel, vocabulary GEMM, arg-max + next-token gather) and
 // no host round trip — the arg-max feeds the next step's A operand directly.
+#include <stdlib.h>
 #include "../../include/adaptive_b200.h"
 #include "kernels.cuh"
 
@@ -13,6 +14,10 @@ constexpr int START_ID = 1;  // adaptive_attention.py:188
 constexpr int END_ID = 2;    // build_vocab.py:48-51
 constexpr int MAX_BEAM = 8;
 int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
+// filter-and-refine arg-max of the greedy vocabulary projection (vocab_refine.cu); AA_DECODE_REFINE=0 / aa_debug_set_decode_argmax_refine(0)
+// keep the fp32-accurate 3xTF32 contraction over the whole vocabulary
+// (1 = tf32 first pass, 2 = bf16 first pass: half the operand bytes, 8x the error bound -> ~2 candidate tiles per row instead of ~1.3)
+int g_argmax_refine = [] { const char* e = getenv("AA_DECODE_REFINE"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }();
 
 struct Carver {
   char* base;
@@ -33,6 +38,9 @@ struct DecodeWs {
   // reads the [emb | h] window, the q/r GEMM the [h | s] window.  W2 = [[W_g, 0], [W_g, W_s]] gives [q | r] in one GEMM.
   float *Wp_s, *pmax, *W2, *hs, *qr; int* pidx;
   int split, bm, K, Kp, lo, K2p, Hp, ldA, ldU, tiles_n;
+  // filter-and-refine arg-max (vocab_refine.cu): 64-column partial tiles, per-tile weight norms and candidate row lists
+  int refine, tiles64; float* wnorm; int *counts, *list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
+  __nv_bfloat16 *u16, *Wp16;
   int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
   // beam only
   float *cum, *row_max, *row_lsum, *rec_alpha, *rec_beta;
@@ -57,6 +65,9 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.ldA = w.split ? 2 * w.lo : (int)K;
   w.ldU = w.split ? 2 * w.Hp : (int)H;
   w.tiles_n = ceil_div(d.Vc, gemm_tc_argmax_tile_n(d.Vc));
+  w.refine = (w.split && !bm && g_argmax_refine && argmax_refine_supported(d.Vc, d.H)) ? ((g_argmax_refine >= 2 && d.H % 8 == 0) ? 2 : 1) : 0;
+  w.tiles64 = ceil_div(d.Vc, gemm_tc_argmax_tile_n_plain(d.Vc));
+  const size_t ptiles = w.refine ? (size_t)w.tiles64 : (size_t)w.tiles_n;
   w.ldP = w.split ? (d.a + 3) / 4 * 4 : d.a;
   w.ld_qr = (2 * d.a + 3) / 4 * 4;
   w.Wcat = c.take<float>((size_t)5 * H * (w.split ? 2 * w.Kp : (int)K));
@@ -71,8 +82,13 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.u = c.take<float>(R * w.ldU);
   w.logits = c.take<float>((w.split && !bm) ? 0 : R * d.Vc);     // split greedy never materialises the logits
   w.Wp_s = c.take<float>(w.split ? (size_t)d.Vc * 2 * w.Hp : 0);
-  w.pmax = c.take<float>((w.split && !bm) ? R * w.tiles_n : 0);
-  w.pidx = c.take<int>((w.split && !bm) ? R * w.tiles_n : 0);
+  w.pmax = c.take<float>((w.split && !bm) ? R * ptiles : 0);
+  w.pidx = c.take<int>((w.split && !bm) ? R * ptiles : 0);
+  w.wnorm = c.take<float>(w.refine ? w.tiles64 : 0);
+  w.counts = c.take<int>(w.refine ? w.tiles64 + 1 : 0);      // (+ 1: finished-CTA ticket of the refinement kernel)
+  w.list = c.take<int>(w.refine ? (size_t)w.tiles64 * R : 0);
+  w.u16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? R * H : 0));
+  w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? (size_t)d.Vc * H : 0));
   w.Acat2 = c.take<float>(bm ? R * w.ldA : 0);
   w.c2 = c.take<float>(bm ? R * H : 0);
   w.cum = c.take<float>(bm ? R : 0);
@@ -365,6 +381,11 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
   AA_CHECK_LAUNCH("pack_wcat");
   if (ws.split) {
     AA_TRY(launch_split_tf32(w.mlp_w, H, d.Vc, H, ws.Wp_s, ws.Hp, st));
+    if (ws.refine) {
+      AA_TRY(launch_tile_wnorm(w.mlp_w, d.Vc, H, ws.wnorm, st));
+      if (ws.refine == 2) AA_TRY(launch_cast2d(w.mlp_w, H, ws.Wp16, H, d.Vc, H, st));
+      AA_CHECK_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)(ws.tiles64 + 1), st));
+    }
     pack_wqr_kernel<<<2 * d.a, 256, 0, st>>>(w.att_wg, w.att_ws, ws.W2, d.a, H, ws.K2p);
     AA_CHECK_LAUNCH("pack_wqr");
     // the operand windows read past the columns they need (up to a multiple of 32, against zero weight columns):
@@ -423,6 +444,7 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
   ap.no_sentinel = w.att_ws == nullptr;     // baseline model (baseline_attention.py:79-100): beta = 0
   ap.alpha = alpha; ap.ld_alpha = ld_alpha; ap.beta = beta; ap.ld_beta = ld_beta;
   ap.u = ws.u; ap.ld_u = ws.ldU; ap.u_lo_off = ws.Hp;
+  ap.u16 = ws.refine == 2 ? ws.u16 : nullptr; ap.ld_u16 = H;
   AA_PROF("dec_step_fused", st, launch_decode_atten(ap, st));
   return AA_OK;
 }
@@ -433,6 +455,13 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
 using namespace aa;
 
 extern "C" {
+
+long long aa_debug_refine_pairs(int reset) { return aa::refine_pairs(reset); }
+
+int aa_debug_set_decode_argmax_refine(int on) {
+  g_argmax_refine = on < 0 ? 0 : (on > 2 ? 2 : on);
+  return AA_OK;
+}
 
 int aa_debug_set_decode_atten_simple(int on) {
   g_force_simple_atten = on ? 1 : 0;
@@ -468,6 +497,28 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
       // logits = u W_p^T + b_p on tensor cores; the epilogue keeps a per-(row, column tile) arg-max, so the [B,Vc]
       // logits never touch HBM unless the caller asked for them                                          :132, :201
       float* lg = logits_out ? logits_out + (size_t)t * B * Vc : nullptr;
+      if (ws.refine && !lg) {
+        // arg-max only: ONE tf32 pass over the hi halves with per-64-column maxima, then exact fp32 logits for the few (row, tile)
+        // pairs that can hold the maximum (vocab_refine.cu).  c = 1.1 * 2^-10: two tf32 roundings per product (2^-11 each) and
+        // an allowance of 2^-13.3 for the fp32 accumulation of the tensor pipe, relative to ||u|| ||W_j||.
+        // (bf16 first pass: 2^-9 per rounding -> c = 1.1 * 2^-8, operands = the bf16 mirrors of u and W_p)
+        TcGemmArgs g{};
+        g.M = B; g.N = Vc;
+        if (ws.refine == 2) {
+          g.K = H; g.elem_size = 2; g.A = ws.u16; g.lda = H; g.B = ws.Wp16; g.ldb = H;
+        } else {
+          g.K = ws.Hp; g.elem_size = 4; g.A = ws.u; g.lda = ws.ldU; g.B = Wp; g.ldb = 2 * ws.Hp;
+        }
+        g.bias1 = w->mlp_b; g.pmax = ws.pmax; g.pidx = nullptr;     // (maxima only: the refinement writes the indices of the tiles that matter)
+        AA_PROF("dec_vocab_gemm1", st, launch_gemm_tc(g, st));
+        AA_PROF("dec_argmax_filter", st, launch_argmax_filter(ws.pmax, ws.tiles64, B, ws.u, ws.ldU, ws.Hp, H, ws.wnorm,
+                                                              ws.refine == 2 ? 1.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, st));
+        AA_PROF("dec_argmax_refine", st, launch_argmax_refine(w->mlp_w, w->mlp_b, Vc, H, ws.u, ws.ldU, ws.Hp, B, ws.counts, ws.list,
+                                                              ws.pmax, ws.pidx, ws.tiles64, st));
+        AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles64, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,
+                                                         ws.lo, st));
+        continue;
+      }
       AA_PROF("dec_vocab_gemm", st, dec_gemm(ws, B, Vc, H, ws.Hp, ws.u, ws.ldU, ws.Hp, ws.ldU, Wp, 2 * ws.Hp, lg, Vc, nullptr, 0, w->mlp_b,
                                              ws.pmax, ws.pidx, st));
       AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles_n, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,

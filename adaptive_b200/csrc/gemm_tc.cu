@@ -90,7 +90,9 @@ struct TcEpilogue {
 // lo*hi + hi*lo + hi*hi into the same fp32 accumulator (the lo*lo term, ~2^-22 relative, is dropped).  Loading
 // each sub-tile once and using it in two products gives 1.5x the arithmetic intensity against L2 of a plain
 // 3K-long tf32 contraction.
-template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT>
+// PM: arg-max partials of the epilogue -- 0 = none (every training contraction: the scan code and its registers stay out of those
+// instantiations), 1 = per-(row, part) maximum and its column index, 2 = maximum only
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT, int PM = 0>
 __global__ void __launch_bounds__(tc_threads(SPLIT), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m,
                int num_tiles, int num_units) {
@@ -273,7 +275,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int nb = n0 + c * 32;
         if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
-        if (e.pmax) {               // ascending column scan with a strict compare: the lowest index wins ties
+        if constexpr (PM == 2) {    // maximum only (the caller recomputes the tiles that matter itself: vocab_refine.cu).  The
+                                    // (value, index) scan below costs ~17 instructions per element and bounded the single-pass
+                                    // contraction at 6 us per tile (profiles/r01_v64_vocab_pass1_hot_lines.txt); this one ~2.5
+          if (nb + 32 <= e.N && e.bias1 && (reinterpret_cast<uintptr_t>(e.bias1) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias1 + nb + j));
+              best = fmaxf(fmaxf(best, __uint_as_float(r[j]) + b4.x), __uint_as_float(r[j + 1]) + b4.y);
+              best = fmaxf(fmaxf(best, __uint_as_float(r[j + 2]) + b4.z), __uint_as_float(r[j + 3]) + b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < e.N) best = fmaxf(best, __uint_as_float(r[j]) + (e.bias1 ? __ldg(e.bias1 + nb + j) : 0.f));
+          }
+          if (!e.D32 && !e.D16) continue;
+        } else if constexpr (PM == 1) {   // ascending column scan with a strict compare: the lowest index wins ties
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (nb + j < e.N) {
@@ -365,10 +383,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       // partial index = first column of this part / (CPP * 32): the layout [M, ceil(N / gemm_tc_argmax_tile_n(N))]
-      if (e.pmax && row0 + lane < e.M && n0 + part * CPP * 32 < e.N) {
-        const long long o = (long long)(row0 + lane) * e.tiles_n + (long long)(tile / tiles_m) * NPARTS + part;
-        e.pmax[o] = best;
-        e.pidx[o] = best_i;
+      if constexpr (PM != 0) {
+        if (row0 + lane < e.M && n0 + part * CPP * 32 < e.N) {
+          const long long o = (long long)(row0 + lane) * e.tiles_n + (long long)(tile / tiles_m) * NPARTS + part;
+          e.pmax[o] = best;
+          if constexpr (PM == 1) e.pidx[o] = best_i;
+        }
       }
     }
   }
@@ -380,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT = false>
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT = false, int PM = 0>
 int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int BK = 128 / ES;
   CUtensorMap tmA, tmB;
@@ -404,7 +424,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
   constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration exceeds shared memory");
-  auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN, SPLIT>;
+  auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN, SPLIT, PM>;
   static bool attr_done = false;
   if (!attr_done) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -453,6 +473,9 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
   const long long sms = num_sms();
   const long long mt = ceil_div(g.M, BM);
   const bool can_splitk = g_tc_splitk && g.D32 && !g.D16 && !g.pmax && ceil_div(g.K, 128 / ES) >= 8;
+  // arg-max partials of a plain (single-pass) contraction: the partial layout [M, ceil(N / 64)] is part of the contract
+  // (gemm_tc_argmax_tile_n_plain), so the tile shape is fixed: 128 columns, two 64-column parts
+  if (g.pmax) return launch_cfg<128, ES, 5, false, false, false, 2>(g, st);
   // bf16, 256-column tiles: one A k-block feeds twice the columns (48 KB per k-block for 2x the flops of a 128x128 tile's 32 KB)
   // and a 128x256x16 MMA costs 128 cycles against 2 x 103.  Measured (tools/bench_gemm.py, r01_v58): the config-5 vocabulary
   // projection (4608 x 20000 x 1024) 195 -> 168 us (1.12 PFLOP/s), but every K <= 512 contraction of config 2 a few per cent
@@ -477,18 +500,22 @@ int set_gemm_splitk(int on) {
 }
 
 int gemm_tc_argmax_tile_n(int N) { return N > 64 ? 128 : 64; }
+int gemm_tc_argmax_tile_n_plain(int) { return 64; }
 
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AA_OK;
   AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16 || g.pmax), "tcgen05 GEMM: bad arguments");
   AA_REQUIRE(g.elem_size == 2 || g.elem_size == 4, "tcgen05 GEMM: element size must be 2 (bf16) or 4 (tf32)");
-  AA_REQUIRE(!g.pmax || (g.pidx && g.split3 && !g.Cin), "tcgen05 GEMM: arg-max partials need pidx, split mode and no C input");
+  AA_REQUIRE(!g.pmax || (!g.Cin && (g.split3 || (!g.a_mn && !g.b_mn))), "tcgen05 GEMM: arg-max partials need K-major operands and no C input");
+  AA_REQUIRE(!g.pmax || (g.split3 ? g.pidx != nullptr : (g.pidx == nullptr && !g.bias2)),
+             "tcgen05 GEMM: split mode keeps (maximum, index) partials and needs pidx; a plain contraction keeps maxima only (pidx == NULL, one bias)");
   if (g.split3) {
     AA_REQUIRE(g.elem_size == 4 && !g.a_mn && !g.b_mn, "tcgen05 GEMM: split (3xTF32) mode needs K-major fp32 operands");
     AA_REQUIRE(g.K % 32 == 0, "tcgen05 GEMM: split mode needs K (per half) padded to a multiple of 32 (got %d)", g.K);
     // the arg-max partial layout [M, ceil(N / tile_n)] is part of the contract: tile_n = gemm_tc_argmax_tile_n(N)
     // (256-column tiles -- 128 cycles per MMA for twice the columns -- were measured SLOWER here: only two 96 KB stages fit
     //  and the TMA feed, ~50 B/clk per SM, becomes the bound: vocabulary GEMM 224 us against 205 us, r01_v33)
+    if (g.pmax) return g.N > 64 ? launch_cfg<128, 4, 3, false, false, true, 1>(g, st) : launch_cfg<64, 4, 4, false, false, true, 1>(g, st);
     if (g.N > 64) return launch_cfg<128, 4, 3, false, false, true>(g, st);
     return launch_cfg<64, 4, 4, false, false, true>(g, st);
   }

@@ -94,11 +94,26 @@ struct TcGemmArgs {
   int lo_a, lo_b; long long a_cols, b_cols;
   // optional (split3 only): per-(row, n-tile) arg-max partials of D incl. bias, layout [M, ceil(N / tile_n)] with
   // tile_n = gemm_tc_argmax_tile_n(N); D32/D16 may then both be null (the logits are never written).
+  // pidx == null: maxima only (cheaper epilogue; bias2 must be null)
   float* pmax; int* pidx;
 };
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
 int gemm_tc_argmax_tile_n(int N);
+int gemm_tc_argmax_tile_n_plain(int N);   // same for a plain (non-split) contraction with arg-max partials
 int set_gemm_splitk(int on);   // diagnostics: 0 = never split K (deterministic summation order)
+
+// ---- vocab_refine.cu (filter-and-refine arg-max of the vocabulary projection, greedy decoding) ----
+bool argmax_refine_supported(int Vc, int H);
+long long refine_pairs(int reset);   // diagnostics: (row, tile) pairs refined so far on the current device (synchronises)
+// wnorm[t] = max_j ||W[j,:]||_2 over the 64-column tile t of W [Vc,H]
+int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s);
+// pmax [R, tiles]: approximate per-tile maxima (single-pass tensor-core contraction, |error_j| <= c ||u|| ||W_j||).  Tiles that cannot
+// hold the row's exact arg-max are set to -inf, the others appended to list[t*R + counts[t]++]  (u rows: hi at [0,H), lo at +lo_off)
+int launch_argmax_filter(float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
+                         int* counts, int* list, cudaStream_t s);
+// exact fp32 (max, index) of every listed (row, tile) pair written back into pmax / pidx; resets counts
+int launch_argmax_refine(const float* W, const float* bias, int Vc, int H, const float* u, long long ldu, long long lo_off, int R, int* counts,
+                         const int* list, float* pmax, int* pidx, int tiles, cudaStream_t s);
 
 // ---- lstm_seq.cu (persistent recurrence, bf16 tensor-core mode) -----------------------------
 // true when the one-launch recurrence kernels can run this shape (H % 64 == 0 and the CTAs fit the chip)
@@ -208,6 +223,7 @@ struct DecodeAttenArgs {
   float* alpha; long long ld_alpha;
   float* beta; long long ld_beta;
   float* u; long long ld_u, u_lo_off;    // u = c_hat + h as tf32 (hi, lo): hi at [0,H), lo at [u_lo_off, u_lo_off+H)
+  __nv_bfloat16* u16; long long ld_u16;  // optional bf16 mirror of u (ld_u16 % 4 == 0)
 };
 int launch_decode_atten(const DecodeAttenArgs& p, cudaStream_t s);
 

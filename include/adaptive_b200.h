@@ -108,6 +108,13 @@ int aa_debug_set_trace_buffer(void* dev_ptr);
 /* Diagnostics: on != 0 makes the tensor-core decode pipeline use the register-staged attention kernel instead of the
  * bulk-copy (cp.async.bulk + mbarrier ring) one; both compute the same step (tests compare them). */
 int aa_debug_set_decode_atten_simple(int on);
+/* Diagnostics: on == 0 makes the greedy sampler compute every logit with the fp32-accurate 3xTF32 contraction instead of the
+ * filter-and-refine arg-max (one low-precision tensor-core pass + exact fp32 logits of the columns that can hold the maximum);
+ * 1 = tf32 first pass, 2 = bf16 first pass (default). */
+int aa_debug_set_decode_argmax_refine(int on);
+/* Diagnostics: number of (row, 64-column tile) pairs the filter has handed to the exact refinement on the current device since
+ * the last reset (synchronises the device); -1 on error. */
+long long aa_debug_refine_pairs(int reset);
 /* Diagnostics: on != 0 makes the training attention use the step-by-step kernels instead of the step-parallel ones. */
 int aa_debug_set_atten_sequential(int on);
 /* Diagnostics: on == 0 stops the tcgen05 GEMM from splitting K (partial tiles summed with red.global.add, i.e. a

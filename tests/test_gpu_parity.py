@@ -477,6 +477,42 @@ def test_stage_operators_vs_oracle():
     assert rel_err(sc.cpu().numpy(), sc_ref) < TOL and rel_err(al2.cpu().numpy(), a2) < TOL and rel_err(be2.cpu().numpy(), b2) < TOL
 
 
+@pytest.mark.parametrize("dims,B,L", [(CFG_A, 1024, 6), (Dims(H=128, E=64, Vc=1000, k=49), 300, 8), (Dims(H=48, E=20, Vc=77, k=10), 37, 7),
+                                      (Dims(H=256, E=64, Vc=4097, k=20), 129, 5)])
+def test_greedy_argmax_refine_matches_full_projection(dims, B, L):
+    """Filter-and-refine arg-max (one tf32 pass + exact fp32 logits of the candidate tiles, vocab_refine.cu) against the
+    fp32-accurate 3xTF32 projection of every logit: same ids, except where the two best logits are within the near-tie threshold."""
+    from adaptive_b200 import _lib
+    lib = _lib.load()
+    w = make_weights(dims, seed=21, bias_scale=0.1)
+    inp = make_inputs(dims, B, 1, seed=22)
+    W = dev_weights(w)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+    try:
+        lib.aa_debug_set_decode_argmax_refine(0)
+        ids_f, att_f, bet_f, logits = F_aa.greedy_decode(W, V, v_g, h0, c0, L, return_logits=True, precision="tf32x3")
+        ids_f2, _, _ = F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision="tf32x3")
+        assert torch.equal(ids_f, ids_f2)
+        top2 = torch.topk(logits, 2, dim=-1).values                      # [L,B,2]
+        gap = (top2[..., 0] - top2[..., 1]).transpose(0, 1).cpu().numpy()
+        for mode in (1, 2):                                              # first pass in tf32 / in bf16
+            lib.aa_debug_set_decode_argmax_refine(mode)
+            lib.aa_debug_refine_pairs(1)
+            ids_r, att_r, bet_r = F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision="tf32x3")
+            pairs = lib.aa_debug_refine_pairs(1) / float(B * L)
+            assert 1.0 <= pairs <= 0.5 * ((dims.Vc + 63) // 64) + 1.0, pairs     # every row refines at least its best tile, never most of them
+            hard, near = near_tie_report(ids_r.cpu().numpy(), ids_f.cpu().numpy(), gap, NEAR_TIE)
+            _log_near_ties("argmax_refine[%d,%d,mode %d] (%.2f tiles refined per row)" % (dims.Vc, B, mode, pairs), near)
+            assert not hard, (mode, hard)
+            same = (ids_r == ids_f).all(1)
+            assert float(same.float().mean()) > 0.95
+            assert torch.equal(att_r[same], att_f[same]) and torch.equal(bet_r[same], bet_f[same])
+            ids_r2, _, _ = F_aa.greedy_decode(W, V, v_g, h0, c0, L, precision="tf32x3")      # deterministic
+            assert torch.equal(ids_r, ids_r2)
+    finally:
+        lib.aa_debug_set_decode_argmax_refine(2)
+
+
 @pytest.mark.parametrize("prec", DECODE_PRECISIONS)
 def test_full_size_decode_properties(prec):
     """BASELINE config 3 size (B=4096, max_len 20): size-independent properties."""
