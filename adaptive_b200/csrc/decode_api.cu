@@ -38,8 +38,8 @@ struct DecodeWs {
   // reads the [emb | h] window, the q/r GEMM the [h | s] window.  W2 = [[W_g, 0], [W_g, W_s]] gives [q | r] in one GEMM.
   float *Wp_s, *pmax, *W2, *hs, *qr; int* pidx;
   int split, bm, K, Kp, lo, K2p, Hp, ldA, ldU, tiles_n;
-  // filter-and-refine arg-max (vocab_refine.cu): 64-column partial tiles, per-tile weight norms and candidate row lists
-  int refine, tiles64; float* wnorm; int *counts, *list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
+  // filter-and-refine arg-max (vocab_refine.cu): 16-column partial tiles (`tiles64` of them), per-tile weight norms and candidate row lists
+  int refine, tiles64; float* wnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
   __nv_bfloat16 *u16, *Wp16;
   int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
   // beam only
@@ -86,7 +86,8 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.pidx = c.take<int>((w.split && !bm) ? R * ptiles : 0);
   w.wnorm = c.take<float>(w.refine ? w.tiles64 : 0);
   w.counts = c.take<int>(w.refine ? w.tiles64 + 1 : 0);      // (+ 1: finished-CTA ticket of the refinement kernel)
-  w.list = c.take<int>(w.refine ? (size_t)w.tiles64 * R : 0);
+  w.list = c.take<unsigned>(w.refine ? (size_t)w.tiles64 * R : 0);
+  w.ncand = c.take<int>(w.refine ? R : 0);
   w.u16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? R * H : 0));
   w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? (size_t)d.Vc * H : 0));
   w.Acat2 = c.take<float>(bm ? R * w.ldA : 0);
@@ -512,11 +513,11 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
         g.bias1 = w->mlp_b; g.pmax = ws.pmax; g.pidx = nullptr;     // (maxima only: the refinement writes the indices of the tiles that matter)
         AA_PROF("dec_vocab_gemm1", st, launch_gemm_tc(g, st));
         AA_PROF("dec_argmax_filter", st, launch_argmax_filter(ws.pmax, ws.tiles64, B, ws.u, ws.ldU, ws.Hp, H, ws.wnorm,
-                                                              ws.refine == 2 ? 1.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, st));
+                                                              ws.refine == 2 ? 1.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, ws.ncand, st));
         AA_PROF("dec_argmax_refine", st, launch_argmax_refine(w->mlp_w, w->mlp_b, Vc, H, ws.u, ws.ldU, ws.Hp, B, ws.counts, ws.list,
                                                               ws.pmax, ws.pidx, ws.tiles64, st));
         AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles64, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,
-                                                         ws.lo, st));
+                                                         ws.lo, st, ws.ncand));
         continue;
       }
       AA_PROF("dec_vocab_gemm", st, dec_gemm(ws, B, Vc, H, ws.Hp, ws.u, ws.ldU, ws.Hp, ws.ldU, Wp, 2 * ws.Hp, lg, Vc, nullptr, 0, w->mlp_b,

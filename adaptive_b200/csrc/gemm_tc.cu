@@ -275,20 +275,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int nb = n0 + c * 32;
         if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
-        if constexpr (PM == 2) {    // maximum only (the caller recomputes the tiles that matter itself: vocab_refine.cu).  The
-                                    // (value, index) scan below costs ~17 instructions per element and bounded the single-pass
-                                    // contraction at 6 us per tile (profiles/r01_v64_vocab_pass1_hot_lines.txt); this one ~2.5
+        if constexpr (PM == 2) {    // maxima only, one per 16 columns: layout [M, ceil(N / 16)] (the caller recomputes the tiles that
+                                    // matter itself: vocab_refine.cu).  The (value, index) scan below costs ~17 instructions per
+                                    // element and bounded the single-pass contraction at 6 us per tile
+                                    // (profiles/r01_v64_vocab_pass1_hot_lines.txt); this one ~2.5
+          float mx[2] = {-INFINITY, -INFINITY};
           if (nb + 32 <= e.N && e.bias1 && (reinterpret_cast<uintptr_t>(e.bias1) & 15) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias1 + nb + j));
-              best = fmaxf(fmaxf(best, __uint_as_float(r[j]) + b4.x), __uint_as_float(r[j + 1]) + b4.y);
-              best = fmaxf(fmaxf(best, __uint_as_float(r[j + 2]) + b4.z), __uint_as_float(r[j + 3]) + b4.w);
+              mx[j >> 4] = fmaxf(fmaxf(mx[j >> 4], __uint_as_float(r[j]) + b4.x), __uint_as_float(r[j + 1]) + b4.y);
+              mx[j >> 4] = fmaxf(fmaxf(mx[j >> 4], __uint_as_float(r[j + 2]) + b4.z), __uint_as_float(r[j + 3]) + b4.w);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nb + j < e.N) best = fmaxf(best, __uint_as_float(r[j]) + (e.bias1 ? __ldg(e.bias1 + nb + j) : 0.f));
+              if (nb + j < e.N) mx[j >> 4] = fmaxf(mx[j >> 4], __uint_as_float(r[j]) + (e.bias1 ? __ldg(e.bias1 + nb + j) : 0.f));
+          }
+          if (row0 + lane < e.M) {
+            float* po = e.pmax + (long long)(row0 + lane) * e.tiles_n + (nb >> 4);
+            po[0] = mx[0];
+            if (nb + 16 < e.N) po[1] = mx[1];
           }
           if (!e.D32 && !e.D16) continue;
         } else if constexpr (PM == 1) {   // ascending column scan with a strict compare: the lowest index wins ties
@@ -383,11 +390,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       // partial index = first column of this part / (CPP * 32): the layout [M, ceil(N / gemm_tc_argmax_tile_n(N))]
-      if constexpr (PM != 0) {
+      if constexpr (PM == 1) {
         if (row0 + lane < e.M && n0 + part * CPP * 32 < e.N) {
           const long long o = (long long)(row0 + lane) * e.tiles_n + (long long)(tile / tiles_m) * NPARTS + part;
           e.pmax[o] = best;
-          if constexpr (PM == 1) e.pidx[o] = best_i;
+          e.pidx[o] = best_i;
         }
       }
     }
@@ -421,7 +428,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
   constexpr int EW = epi_warps(SPLIT);
   constexpr int NPARTS = (EW / 4) < (BN / 32) ? (EW / 4) : (BN / 32);
-  e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
+  e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = PM == 2 ? ceil_div(g.N, 16) : ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
   constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN, SPLIT, PM>;
@@ -473,8 +480,7 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
   const long long sms = num_sms();
   const long long mt = ceil_div(g.M, BM);
   const bool can_splitk = g_tc_splitk && g.D32 && !g.D16 && !g.pmax && ceil_div(g.K, 128 / ES) >= 8;
-  // arg-max partials of a plain (single-pass) contraction: the partial layout [M, ceil(N / 64)] is part of the contract
-  // (gemm_tc_argmax_tile_n_plain), so the tile shape is fixed: 128 columns, two 64-column parts
+  // maxima partials of a plain (single-pass) contraction: one per 16 columns, layout [M, ceil(N / 16)] (gemm_tc_argmax_tile_n_plain)
   if (g.pmax) return launch_cfg<128, ES, 5, false, false, false, 2>(g, st);
   // bf16, 256-column tiles: one A k-block feeds twice the columns (48 KB per k-block for 2x the flops of a 128x128 tile's 32 KB)
   // and a 128x256x16 MMA costs 128 cycles against 2 x 103.  Measured (tools/bench_gemm.py, r01_v58): the config-5 vocabulary
@@ -500,7 +506,7 @@ int set_gemm_splitk(int on) {
 }
 
 int gemm_tc_argmax_tile_n(int N) { return N > 64 ? 128 : 64; }
-int gemm_tc_argmax_tile_n_plain(int) { return 64; }
+int gemm_tc_argmax_tile_n_plain(int) { return 16; }
 
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AA_OK;

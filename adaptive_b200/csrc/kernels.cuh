@@ -43,8 +43,10 @@ int launch_argmax_gather(const float* logits, long long ld_logits, int B, int Vc
                          const float* embed, int E, float* emb_dst, long long ld_emb, cudaStream_t s);
 // reduce the vocabulary GEMM's arg-max partials [B, tiles_n] to ids and gather embed[id] into the next A operand
 // (split != 0: as tf32 hi at [0,E) and lo at [lo_off, lo_off+E) of the destination row)
+// (ncand != null: row b holds ncand[b] valid partials at the front of its tiles_n entries)
 int launch_argmax_finalize(const float* pmax, const int* pidx, int tiles_n, int B, long long* ids_out, long long ld_ids,
-                           const float* embed, int E, float* emb_dst, long long ld_emb, int split, long long lo_off, cudaStream_t s);
+                           const float* embed, int E, float* emb_dst, long long ld_emb, int split, long long lo_off, cudaStream_t s,
+                           const int* ncand = nullptr);
 // dst [rows, 2*Kp] = [tf32 hi | lo] of src [rows, cols] (zero padded to Kp, a multiple of 32)
 int launch_split_tf32(const float* src, long long ld_src, long long rows, int cols, float* dst, int Kp, cudaStream_t s);
 int launch_gather_rows(const long long* ids, long long ld_ids, const float* table, int E, int Vc, float* dst, long long ld_dst,
@@ -105,15 +107,16 @@ int set_gemm_splitk(int on);   // diagnostics: 0 = never split K (deterministic 
 // ---- vocab_refine.cu (filter-and-refine arg-max of the vocabulary projection, greedy decoding) ----
 bool argmax_refine_supported(int Vc, int H);
 long long refine_pairs(int reset);   // diagnostics: (row, tile) pairs refined so far on the current device (synchronises)
-// wnorm[t] = max_j ||W[j,:]||_2 over the 64-column tile t of W [Vc,H]
+// wnorm[t] = max_j ||W[j,:]||_2 over the 16-column tile t of W [Vc,H] (tile width = gemm_tc_argmax_tile_n_plain)
 int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s);
-// pmax [R, tiles]: approximate per-tile maxima (single-pass tensor-core contraction, |error_j| <= c ||u|| ||W_j||).  Tiles that cannot
-// hold the row's exact arg-max are set to -inf, the others appended to list[t*R + counts[t]++]  (u rows: hi at [0,H), lo at +lo_off)
-int launch_argmax_filter(float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
-                         int* counts, int* list, cudaStream_t s);
-// exact fp32 (max, index) of every listed (row, tile) pair written back into pmax / pidx; resets counts
+// pmax [R, tiles]: approximate per-tile maxima (single-pass tensor-core contraction, |error_j| <= c ||u|| ||W_j||).  Every (row, tile)
+// pair whose tile can hold the row's exact arg-max is appended to list[t*R + counts[t]++] as row | slot << 20, slot = rank among
+// the row's candidates; ncand[row] = number of candidates  (u rows: hi at [0,H), lo at +lo_off)
+int launch_argmax_filter(const float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
+                         int* counts, unsigned* list, int* ncand, cudaStream_t s);
+// exact fp32 (max, index) of every listed pair written to pmax / pidx[row * tiles + slot]; resets counts
 int launch_argmax_refine(const float* W, const float* bias, int Vc, int H, const float* u, long long ldu, long long lo_off, int R, int* counts,
-                         const int* list, float* pmax, int* pidx, int tiles, cudaStream_t s);
+                         const unsigned* list, float* pmax, int* pidx, int tiles, cudaStream_t s);
 
 // ---- lstm_seq.cu (persistent recurrence, bf16 tensor-core mode) -----------------------------
 // true when the one-launch recurrence kernels can run this shape (H % 64 == 0 and the CTAs fit the chip)

@@ -198,13 +198,14 @@ __global__ void __launch_bounds__(PW_THREADS) argmax_finalize_kernel(const float
                                                                      int tiles_n, int B, long long* __restrict__ ids_out,
                                                                      long long ld_ids, const float* __restrict__ embed, int E,
                                                                      float* __restrict__ emb_dst, long long ld_emb, int split,
-                                                                     long long lo_off) {
+                                                                     long long lo_off, const int* __restrict__ ncand) {
   const int b = blockIdx.x * (PW_THREADS / 32) + (threadIdx.x >> 5);
   const int l = threadIdx.x & 31;
   if (b >= B) return;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int j = l; j < tiles_n; j += 32) {
+  const int nv = ncand ? ncand[b] : tiles_n;
+  for (int j = l; j < nv; j += 32) {
     const float v = pmax[(long long)b * tiles_n + j];
     const int i = pidx[(long long)b * tiles_n + j];
     if (v > best || (v == best && i < bi)) { best = v; bi = i; }
@@ -573,10 +574,11 @@ int launch_argmax_gather(const float* logits, long long ld_logits, int B, int Vc
 }
 
 int launch_argmax_finalize(const float* pmax, const int* pidx, int tiles_n, int B, long long* ids_out, long long ld_ids,
-                           const float* embed, int E, float* emb_dst, long long ld_emb, int split, long long lo_off, cudaStream_t s) {
+                           const float* embed, int E, float* emb_dst, long long ld_emb, int split, long long lo_off, cudaStream_t s,
+                           const int* ncand) {
   if (B == 0) return AA_OK;
   argmax_finalize_kernel<<<ceil_div(B, PW_THREADS / 32), PW_THREADS, 0, s>>>(pmax, pidx, tiles_n, B, ids_out, ld_ids, embed, E, emb_dst,
-                                                                             ld_emb, split, lo_off);
+                                                                             ld_emb, split, lo_off, ncand);
   AA_CHECK_LAUNCH("argmax_finalize");
   return AA_OK;
 }

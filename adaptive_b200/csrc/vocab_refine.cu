@@ -4,15 +4,16 @@
 // The sampler only needs arg-max_j (u . W_j + b_j), exact in fp32.  A fp32-accurate (3xTF32) contraction spends three
 // tensor-core products and twice the operand traffic on every one of the Vc logits although all but a handful are
 // far below the row's maximum.  Instead:
-//   1. ONE single-pass tensor-core contraction over the tf32 "hi" halves of the operands, whose epilogue keeps only
-//      the per-(row, 64-column tile) maximum (gemm_tc.cu, arg-max partials);
+//   1. ONE single-pass tensor-core contraction over bf16 mirrors (or the tf32 "hi" halves) of the operands, whose epilogue
+//      keeps only the per-(row, 16-column tile) maximum (gemm_tc.cu, arg-max partials);
 //   2. argmax_filter: with the rigorous bound |approx_j - exact_j| <= c ||u||_2 ||W_j||_2 (Cauchy-Schwarz over the
 //      per-product rounding errors of the two tf32 roundings, plus the fp32 accumulation), a tile can hold the exact
 //      arg-max only if its approximate maximum + bound reaches the best (approximate maximum - bound) of the row;
-//      those (row, tile) pairs -- ~1.2 per row for tf32 -- are appended to the tile's row list, every other partial
-//      is set to -inf;
-//   3. argmax_refine: one CTA per tile with a non-empty list keeps the tile's 64 fp32 weight rows in shared memory and
-//      recomputes the listed rows' 64 logits in plain fp32 FMA arithmetic, writing the tile's exact (max, index) back;
+//      those (row, tile) pairs -- ~1.3 per row for tf32, ~2 for bf16 at config 3 -- are appended to the tile's row list, every
+//      other partial is set to -inf;
+//   3. argmax_refine: work units (tile, chunk of listed rows) dealt to a persistent grid; a unit keeps the tile's 16 fp32 weight
+//      rows in shared memory and recomputes the listed rows' 16 logits in plain fp32 FMA arithmetic, writing the tile's exact
+//      (max, index) back;
 //   4. the existing argmax_finalize reduces the partials (lowest index wins ties) and gathers the next embedding.
 // Every column that could be the exact arg-max is recomputed exactly, so the ids equal those of an exact fp32 projection
 // (up to fp32 summation order, like any fp32 implementation).
@@ -24,6 +25,7 @@ namespace {
 constexpr int RF_THREADS = 256;
 constexpr int RF_WARPS = RF_THREADS / 32;
 constexpr int RF_ROWS = 4;       // rows a warp carries through one pass over the tile's weights
+constexpr int RF_TN = 16;        // columns per tile = granularity of the first pass's maxima (gemm_tc_argmax_tile_n_plain)
 
 __device__ unsigned long long d_refine_pairs = 0;    // diagnostics: (row, tile) pairs handed to the refinement so far
 
@@ -49,59 +51,105 @@ __global__ void tile_wnorm_kernel(const float* __restrict__ W, int Vc, int H, in
   }
 }
 
-// one warp per row: row norm, row threshold, candidate lists
-__global__ void __launch_bounds__(RF_THREADS) argmax_filter_kernel(float* __restrict__ pmax, int tiles, int R, const float* __restrict__ u,
+// Row norms, row thresholds, candidate lists: one warp per row, the row's maxima staged in shared memory.  A listed
+// (row, tile) pair gets a SLOT = its rank among the row's candidates: the refinement writes the tile's exact (max, index) to
+// pmax / pidx[row * tiles + slot], so that the final reduction reads ncand[row] entries instead of every tile of the row.
+// The positions in a tile's list come from ONE global atomic per (CTA, tile): most rows of a batch list the same tile (the word
+// most of them favour), and 4096 same-address atomics cost ~10 us.
+constexpr int FL_THREADS = 256, FL_ROWS = FL_THREADS / 32;      // one warp per row
+__global__ void __launch_bounds__(FL_THREADS) argmax_filter_kernel(const float* __restrict__ pmax, int tiles, int R, const float* __restrict__ u,
                                                                    long long ldu, long long lo_off, int H, const float* __restrict__ wnorm,
-                                                                   float c, int* __restrict__ counts, int* __restrict__ list) {
-  const int r = blockIdx.x * RF_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= R) return;
-  const float* ur = u + (long long)r * ldu;
-  float ss = 0.f;
-  for (int k = lane * 4; k < H; k += 128) {
-    const float4 hi = *reinterpret_cast<const float4*>(ur + k), lo = *reinterpret_cast<const float4*>(ur + lo_off + k);
-    const float x0 = hi.x + lo.x, x1 = hi.y + lo.y, x2 = hi.z + lo.z, x3 = hi.w + lo.w;
-    ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+                                                                   float c, int* __restrict__ counts, unsigned* __restrict__ list,
+                                                                   int* __restrict__ ncand) {
+  extern __shared__ int fsm[];
+  int* scnt = fsm;                                              // [tiles] pairs this CTA lists per tile, then the running position inside the CTA's range
+  float* wn = reinterpret_cast<float*>(fsm + tiles);            // [tiles] weight norms
+  __shared__ int spairs;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* prow = wn + tiles + warp * tiles;                      // [tiles] this warp's row of maxima (read three times)
+  const int r = blockIdx.x * FL_ROWS + warp;
+  const bool live = r < R;
+  for (int t = tid; t < tiles; t += FL_THREADS) {
+    scnt[t] = 0;
+    wn[t] = __ldg(wnorm + t);
   }
-  const float cn = c * sqrtf(warp_sum(ss)) * (1.f + 1e-6f);
-  float* pr = pmax + (long long)r * tiles;
-  float L = -INFINITY;      // best lower bound of the row's exact maximum
-  for (int t = lane; t < tiles; t += 32) L = fmaxf(L, pr[t] - cn * wnorm[t]);
-  L = warp_max(L);
-  int mine = 0;
-  for (int t = lane; t < tiles; t += 32) {
-    const float p = pr[t];
-    if (p + cn * wnorm[t] >= L) {           // the tile's exact maximum may reach the row's: refine it
-      const int pos = atomicAdd(&counts[t], 1);
-      list[(long long)t * R + pos] = r;
-      ++mine;
-    } else {
-      pr[t] = -INFINITY;                    // cannot hold the arg-max
+  if (tid == 0) spairs = 0;
+  float cn = 0.f, L = INFINITY;
+  if (live) {
+    const float* pr = pmax + (long long)r * tiles;
+#pragma unroll 4
+    for (int t = lane; t < tiles; t += 32) prow[t] = __ldcg(pr + t);
+    const float* ur = u + (long long)r * ldu;
+    float ss = 0.f;
+    for (int k = lane * 4; k < H; k += 128) {
+      const float4 hi = __ldcg(reinterpret_cast<const float4*>(ur + k)), lo = __ldcg(reinterpret_cast<const float4*>(ur + lo_off + k));
+      const float x0 = hi.x + lo.x, x1 = hi.y + lo.y, x2 = hi.z + lo.z, x3 = hi.w + lo.w;
+      ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+    }
+    cn = c * sqrtf(warp_sum(ss)) * (1.f + 1e-6f);
+  }
+  __syncthreads();
+  if (live) {
+    float lo_best = -INFINITY;      // best lower bound of the row's exact maximum
+    for (int t = lane; t < tiles; t += 32) lo_best = fmaxf(lo_best, prow[t] - cn * wn[t]);
+    L = warp_max(lo_best);
+    int mine = 0;
+    for (int t = lane; t < tiles; t += 32)
+      if (prow[t] + cn * wn[t] >= L) {     // the tile's exact maximum may reach the row's: refine it
+        atomicAdd(&scnt[t], 1);
+        ++mine;
+      }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) {
+      ncand[r] = mine;
+      atomicAdd(&spairs, mine);
     }
   }
-  mine = __reduce_add_sync(0xffffffffu, mine);
-  if (lane == 0) atomicAdd(&d_refine_pairs, (unsigned long long)mine);
+  __syncthreads();
+  for (int t = tid; t < tiles; t += FL_THREADS) {
+    const int n = scnt[t];
+    scnt[t] = n > 0 ? atomicAdd(&counts[t], n) : 0;      // this CTA's range in the tile's list
+  }
+  if (tid == 0) atomicAdd(&d_refine_pairs, (unsigned long long)spairs);
+  __syncthreads();
+  if (live) {
+    int nrow = 0;
+    for (int t0 = 0; t0 < tiles; t0 += 32) {
+      const int t = t0 + lane;
+      const bool flag = t < tiles && prow[t] + cn * wn[t] >= L;
+      const unsigned m = __ballot_sync(0xffffffffu, flag);
+      if (flag) {
+        const int slot = nrow + __popc(m & ((1u << lane) - 1u));
+        const int pos = atomicAdd(&scnt[t], 1);
+        list[(long long)t * R + pos] = (unsigned)r | ((unsigned)slot << 20);
+      }
+      nrow += __popc(m);
+    }
+  }
 }
 
-// Exact fp32 logits of the listed rows.  Work unit = (64-column tile, chunk of up to 32 listed rows); the units are dealt round
-// robin to a persistent grid of one CTA per SM.  (One CTA per tile is not enough: at a given step most rows of a batch favour the
-// same few words -- with the synthetic weights nearly all 4096 rows list the same tile -- and that CTA would do all the work.)
-// A CTA keeps the unit's 64 weight rows in shared memory; each warp carries RF_ROWS rows through one pass over them.
-__global__ void __launch_bounds__(RF_THREADS, 1) argmax_refine_kernel(const float* __restrict__ W, const float* __restrict__ bias, int Vc, int H,
+// Exact fp32 logits of the listed rows.  Work unit = (16-column tile, chunk of up to 32 listed rows); the units are dealt round
+// robin to a persistent grid.  (One CTA per tile is not enough: at a given step most rows of a batch favour the same few words --
+// with the synthetic weights nearly all 4096 rows list the same tile -- and that CTA would do all the work.)
+// A CTA keeps the unit's 16 weight rows in shared memory; each warp carries RF_ROWS rows through one pass over them, lane =
+// (column, half of the reduction range).
+__global__ void __launch_bounds__(RF_THREADS, 2) argmax_refine_kernel(const float* __restrict__ W, const float* __restrict__ bias, int Vc, int H,
                                                                       const float* __restrict__ u, long long ldu, long long lo_off, int R,
-                                                                      int* __restrict__ counts, const int* __restrict__ list,
+                                                                      int* __restrict__ counts, const unsigned* __restrict__ list,
                                                                       float* __restrict__ pmax, int* __restrict__ pidx, int tiles) {
   extern __shared__ __align__(16) float sm[];
   constexpr int CH = RF_WARPS * RF_ROWS;               // listed rows per work unit
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ldw = H + 4;                               // (H % 32 == 0: 8 lanes x 16 B of one LDS.128 phase hit 32 distinct banks)
-  float* Ws = sm;                                      // [64][H + 4]
-  float* us = sm + 64 * ldw + warp * RF_ROWS * H;      // [RF_ROWS][H] per warp
-  int* pre = reinterpret_cast<int*>(sm + 64 * ldw + RF_WARPS * RF_ROWS * H);   // [tiles + 1] exclusive prefix of the units per tile
-  if (warp == 0) {     // blocked exclusive scan of the units per tile: lane l owns tiles [l * per, (l + 1) * per)
-    const int per = (tiles + 31) / 32;
+  float* Ws = sm;                                      // [RF_TN][H + 4]
+  float* us = sm + RF_TN * ldw + warp * RF_ROWS * H;   // [RF_ROWS][H] per warp
+  int* pre = reinterpret_cast<int*>(sm + RF_TN * ldw + RF_WARPS * RF_ROWS * H);   // [tiles + 1] exclusive prefix of the units per tile
+  {   // blocked exclusive scan of the units per tile: thread i owns tiles [i * per, (i + 1) * per)
+    __shared__ int wsum[RF_WARPS];
+    const int per = (tiles + RF_THREADS - 1) / RF_THREADS;
     int loc = 0;
     for (int i = 0; i < per; ++i) {
-      const int t = lane * per + i;
+      const int t = tid * per + i;
       const int c = t < tiles ? (__ldcg(counts + t) + CH - 1) / CH : 0;
       if (t < tiles) pre[t] = c;
       loc += c;
@@ -112,20 +160,25 @@ __global__ void __launch_bounds__(RF_THREADS, 1) argmax_refine_kernel(const floa
       const int v = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += v;
     }
-    int acc = inc - loc;
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w2 = 0; w2 < warp; ++w2) base += wsum[w2];
+    int acc = base + inc - loc;
     for (int i = 0; i < per; ++i) {
-      const int t = lane * per + i;
+      const int t = tid * per + i;
       if (t < tiles) {
         const int c = pre[t];
         pre[t] = acc;
         acc += c;
       }
     }
-    if (lane == 31) pre[tiles] = inc;
+    if (tid == RF_THREADS - 1) pre[tiles] = base + inc;
   }
   __syncthreads();
   const int total = pre[tiles];
-  const int h4 = H / 4;
+  const int h4 = H / 4, hh4 = H / 8;                   // float4s per row / per half row
+  const int col = lane & (RF_TN - 1), kh = lane >> 4;  // this lane's column of the tile and half of the reduction range
   int cur_tile = -1;
   for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
     int lo_t = 0, hi_t = tiles - 1;                    // largest t with pre[t] <= unit (tiles without units share the next one's prefix)
@@ -134,11 +187,11 @@ __global__ void __launch_bounds__(RF_THREADS, 1) argmax_refine_kernel(const floa
       if (pre[mid] <= unit) lo_t = mid; else hi_t = mid - 1;
     }
     const int t = lo_t, chunk = unit - pre[t];
-    const int n = counts[t];
-    const int j0 = t * 64, nc = min(64, Vc - j0);
+    const int n = __ldcg(counts + t);
+    const int j0 = t * RF_TN, nc = min(RF_TN, Vc - j0);
     if (t != cur_tile) {
       __syncthreads();                                 // every warp is done with the previous tile's weights
-      for (int i = tid; i < 64 * h4; i += RF_THREADS) {     // asynchronous copies: all of a thread's 16-byte pieces are in flight at once
+      for (int i = tid; i < RF_TN * h4; i += RF_THREADS) {     // asynchronous copies: all of a thread's 16-byte pieces are in flight at once
         const int j = i / h4, k4 = i - j * h4;
         float* dst = Ws + j * ldw + k4 * 4;
         if (j < nc) {
@@ -154,13 +207,15 @@ __global__ void __launch_bounds__(RF_THREADS, 1) argmax_refine_kernel(const floa
     }
     const int i0 = chunk * CH + warp * RF_ROWS;
     if (i0 >= n) continue;                             // (warp-uniform; the barriers above are reached by every warp of the CTA)
-    const float b0 = lane < nc ? (bias ? __ldg(bias + j0 + lane) : 0.f) : -INFINITY;
-    const float b1 = lane + 32 < nc ? (bias ? __ldg(bias + j0 + lane + 32) : 0.f) : -INFINITY;
-    const float4* w0 = reinterpret_cast<const float4*>(Ws + lane * ldw);
-    const float4* w1 = reinterpret_cast<const float4*>(Ws + (lane + 32) * ldw);
-    int rows[RF_ROWS];
+    const float bj = col < nc ? (bias ? __ldg(bias + j0 + col) : 0.f) : -INFINITY;
+    const float4* wp = reinterpret_cast<const float4*>(Ws + col * ldw) + kh * hh4;
+    int rows[RF_ROWS], slots[RF_ROWS];
 #pragma unroll
-    for (int m = 0; m < RF_ROWS; ++m) rows[m] = list[(long long)t * R + min(i0 + m, n - 1)];
+    for (int m = 0; m < RF_ROWS; ++m) {
+      const unsigned e = list[(long long)t * R + min(i0 + m, n - 1)];
+      rows[m] = (int)(e & 0xFFFFFu);
+      slots[m] = (int)(e >> 20);
+    }
     for (int k = lane * 4; k < H; k += 128) {            // (the RF_ROWS rows' loads of one k are issued together)
       float4 hi[RF_ROWS], lo[RF_ROWS];
 #pragma unroll
@@ -174,37 +229,35 @@ __global__ void __launch_bounds__(RF_THREADS, 1) argmax_refine_kernel(const floa
         *reinterpret_cast<float4*>(us + m * H + k) = make_float4(hi[m].x + lo[m].x, hi[m].y + lo[m].y, hi[m].z + lo[m].z, hi[m].w + lo[m].w);
     }
     __syncwarp();
-    float4 a0[RF_ROWS], a1[RF_ROWS];                    // four partial sums (k mod 4) per (row, column)
+    float4 a[RF_ROWS];                                   // four partial sums (k mod 4) per row, this lane's column and half range
 #pragma unroll
-    for (int m = 0; m < RF_ROWS; ++m) a0[m] = a1[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int k4 = 0; k4 < h4; ++k4) {
-      const float4 x0 = w0[k4], x1 = w1[k4];
+    for (int m = 0; m < RF_ROWS; ++m) a[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* up = reinterpret_cast<const float4*>(us) + kh * hh4;
+#pragma unroll 4
+    for (int k4 = 0; k4 < hh4; ++k4) {
+      const float4 x = wp[k4];
 #pragma unroll
       for (int m = 0; m < RF_ROWS; ++m) {
-        const float4 uv = *reinterpret_cast<const float4*>(us + m * H + k4 * 4);
-        a0[m].x = fmaf(uv.x, x0.x, a0[m].x); a0[m].y = fmaf(uv.y, x0.y, a0[m].y);
-        a0[m].z = fmaf(uv.z, x0.z, a0[m].z); a0[m].w = fmaf(uv.w, x0.w, a0[m].w);
-        a1[m].x = fmaf(uv.x, x1.x, a1[m].x); a1[m].y = fmaf(uv.y, x1.y, a1[m].y);
-        a1[m].z = fmaf(uv.z, x1.z, a1[m].z); a1[m].w = fmaf(uv.w, x1.w, a1[m].w);
+        const float4 uv = up[m * h4 + k4];
+        a[m].x = fmaf(uv.x, x.x, a[m].x); a[m].y = fmaf(uv.y, x.y, a[m].y);
+        a[m].z = fmaf(uv.z, x.z, a[m].z); a[m].w = fmaf(uv.w, x.w, a[m].w);
       }
     }
 #pragma unroll
     for (int m = 0; m < RF_ROWS; ++m) {
-      const float v0 = ((a0[m].x + a0[m].y) + (a0[m].z + a0[m].w)) + b0;
-      const float v1 = ((a1[m].x + a1[m].y) + (a1[m].z + a1[m].w)) + b1;
-      float best = v0;
-      int bi = j0 + lane;
-      if (v1 > best) { best = v1; bi = j0 + lane + 32; }      // (strict: the lower column wins a tie)
+      float v = (a[m].x + a[m].y) + (a[m].z + a[m].w);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);           // the two halves of the reduction range (same sum in both lanes)
+      float best = v + bj;
+      int bi = j0 + col;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = RF_TN / 2; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }   // (the lower column wins a tie)
       }
-      if (lane == 0 && i0 + m < n) {
-        pmax[(long long)rows[m] * tiles + t] = best;
-        pidx[(long long)rows[m] * tiles + t] = bi;
+      if (lane == 0 && i0 + m < n) {          // (compacted: the row's slot-th candidate)
+        pmax[(long long)rows[m] * tiles + slots[m]] = best;
+        pidx[(long long)rows[m] * tiles + slots[m]] = bi;
       }
     }
     __syncwarp();
@@ -220,7 +273,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) argmax_refine_kernel(const floa
   }
 }
 
-size_t refine_smem(int H, int tiles) { return sizeof(float) * ((size_t)64 * (H + 4) + (size_t)RF_WARPS * RF_ROWS * H + tiles + 1); }
+size_t refine_smem(int H, int tiles) { return sizeof(float) * ((size_t)RF_TN * (H + 4) + (size_t)RF_WARPS * RF_ROWS * H + tiles + 1); }
 
 }  // namespace
 
@@ -234,30 +287,34 @@ long long refine_pairs(int reset) {
   return (long long)v;
 }
 
-bool argmax_refine_supported(int Vc, int H) { return Vc > 64 && H % 4 == 0 && refine_smem(H, ceil_div(Vc, 64)) <= 220 * 1024; }
+bool argmax_refine_supported(int Vc, int H) {
+  // (12-bit slots in the list entries; the filter stages 10 arrays of one entry per tile in 48 KB of shared memory)
+  return Vc > 64 && Vc <= 1200 * RF_TN && H % 8 == 0 && refine_smem(H, ceil_div(Vc, RF_TN)) <= 110 * 1024;
+}
 
 int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s) {
-  tile_wnorm_kernel<<<ceil_div(Vc, 64), RF_THREADS, 0, s>>>(W, Vc, H, 64, wnorm);
+  tile_wnorm_kernel<<<ceil_div(Vc, RF_TN), RF_THREADS, 0, s>>>(W, Vc, H, RF_TN, wnorm);
   AA_CHECK_LAUNCH("tile_wnorm");
   return AA_OK;
 }
 
-int launch_argmax_filter(float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
-                         int* counts, int* list, cudaStream_t s) {
-  argmax_filter_kernel<<<ceil_div(R, RF_WARPS), RF_THREADS, 0, s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm, c, counts, list);
+int launch_argmax_filter(const float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
+                         int* counts, unsigned* list, int* ncand, cudaStream_t s) {
+  AA_REQUIRE(R <= (1 << 20) && tiles <= 4096, "argmax_filter: at most 2^20 rows and 4096 tiles (got %d, %d)", R, tiles);
+  argmax_filter_kernel<<<ceil_div(R, FL_ROWS), FL_THREADS, sizeof(int) * tiles * (2 + FL_ROWS), s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm, c, counts, list, ncand);
   AA_CHECK_LAUNCH("argmax_filter");
   return AA_OK;
 }
 
 int launch_argmax_refine(const float* W, const float* bias, int Vc, int H, const float* u, long long ldu, long long lo_off, int R, int* counts,
-                         const int* list, float* pmax, int* pidx, int tiles, cudaStream_t s) {
+                         const unsigned* list, float* pmax, int* pidx, int tiles, cudaStream_t s) {
   static size_t granted = 0;
   const size_t smem = refine_smem(H, tiles);
   if (smem > granted) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(argmax_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     granted = smem;
   }
-  argmax_refine_kernel<<<num_sms(), RF_THREADS, smem, s>>>(W, bias, Vc, H, u, ldu, lo_off, R, counts, list, pmax, pidx, tiles);
+  argmax_refine_kernel<<<2 * num_sms(), RF_THREADS, smem, s>>>(W, bias, Vc, H, u, ldu, lo_off, R, counts, list, pmax, pidx, tiles);
   AA_CHECK_LAUNCH("argmax_refine");
   return AA_OK;
 }

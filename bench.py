@@ -179,7 +179,7 @@ def kernel_models(dims, B, T, decode_B):
         "dec_cell": ("hbm", float(cell_bytes) * decode_B), "dec_qr_gemm": ("tf32x3", fl(decode_B, 2 * a, 2 * H)),
         "gemm_vocab_fwd": ("tensor", fl(N, Vc, H)), "gemm_vocab_dx": ("tensor", fl(N, H, Vc)), "gemm_vocab_dw": ("tensor", fl(Vc, H, N)),
         "lstm_rec_gemm": ("tensor", fl(B, 4 * H, H)), "bptt_rec_gemm": ("tensor", fl(B, H, 4 * H)),
-        "dec_vocab_gemm": ("tf32x3", fl(decode_B, Vc, H)), "dec_vocab_gemm1": ("tf32x1", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tf32x3", fl(decode_B, 5 * H, E + H)),
+        "dec_vocab_gemm": ("tf32x3", fl(decode_B, Vc, H)), "dec_vocab_gemm1": ("bf16x1", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tf32x3", fl(decode_B, 5 * H, E + H)),
         "dec_step_fused": ("hbm", float(step_bytes) * decode_B),
         "dec_argmax": ("hbm", float(decode_B) * ((Vc + 127) // 128) * 8),      # reduction of the GEMM epilogue's partials
         # training attention, per launch over the whole batch: V + P + per-step rows in, u/ctx/alpha/beta out
@@ -218,11 +218,11 @@ def rooflines(report, models, peaks):
             ach, peak, unit = 3.0 * work / per / 1e12, peaks["bf16_tflops"] / 2.0, "TFLOP/s"
             extra = {"engine": "tcgen05 kind::tf32 x3 (hi/lo split)", "algorithmic_tflops": work / per / 1e12,
                      "peak_note": "tf32 peak taken as measured bf16 peak / 2"}
-        elif bound == "tf32x1":
-            # single tf32 pass of the filter-and-refine arg-max (the exact logits of the candidate tiles come from dec_argmax_refine)
+        elif bound == "bf16x1":
+            # single bf16 pass of the filter-and-refine arg-max (the exact logits of the candidate tiles come from dec_argmax_refine)
             bound = "tensor"
-            ach, peak, unit = work / per / 1e12, peaks["bf16_tflops"] / 2.0, "TFLOP/s"
-            extra = {"engine": "tcgen05 kind::tf32, one pass over the hi halves", "peak_note": "tf32 peak taken as measured bf16 peak / 2"}
+            ach, peak, unit = work / per / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+            extra = {"engine": "tcgen05 kind::f16 over bf16 mirrors, maxima per 16 columns only (no logits written)"}
         else:
             ach, peak, unit = work / per / 1e12, peaks["bf16_tflops"], "TFLOP/s"
         out[tag] = dict({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": TRAFFIC.get(tag),
@@ -564,6 +564,11 @@ def run_ours(args):
     _lib.profile_enable(False)
     dec_report = _lib.profile_report()
     _lib.profile_reset()
+    # filter-and-refine arg-max: (row, 16-column tile) pairs recomputed exactly, per row and step
+    lib = _lib.load()
+    lib.aa_debug_refine_pairs(1)
+    decode_step(ddev)
+    refine_pairs = lib.aa_debug_refine_pairs(1) / float(DECODE_B * DECODE_L)
 
     widened = None
     if world == 1 and not args.no_widened:
@@ -608,6 +613,9 @@ def run_ours(args):
                    "e2e": {"value": DECODE_B * DECODE_L * n_gpus / e2e_dec_s, "unit": "tokens/s", "h2d_bytes_per_step": h2d_dec,
                            "d2h_bytes_per_step": d2h_dec, "ms_per_step": e2e_dec_s * 1e3},
                    "precision": model.decoder.decode_precision,
+                   "vocab_argmax": {"method": "one bf16 tensor-core pass (maxima per 16 columns) + exact fp32 recompute of the tiles that can "
+                                              "hold the row maximum under a rigorous error bound (vocab_refine.cu); ids equal an exact fp32 projection's",
+                                    "tiles_refined_per_row_and_step": refine_pairs, "tiles_per_row": (dims.Vc + 15) // 16},
                    "roofline_fused_step": k_dec.get("dec_step_fused")},
     }
     if widened is not None:
