@@ -41,6 +41,7 @@ struct DecodeWs {
   // filter-and-refine arg-max (vocab_refine.cu): 16-column partial tiles (`tiles64` of them), per-tile weight norms and candidate row lists
   int refine, tiles64; float* wnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
   __nv_bfloat16 *u16, *Wp16;
+  float *vg_s, *wx_s; int Ep;     // split pipeline: (hi | lo) copies of v_g [B, 2*Ep] and of the v_g columns of [W_ih; W_x] [5H, 2*Ep]
   int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
   // beam only
   float *cum, *row_max, *row_lsum, *rec_alpha, *rec_beta;
@@ -90,6 +91,9 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.ncand = c.take<int>(w.refine ? R : 0);
   w.u16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? R * H : 0));
   w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? (size_t)d.Vc * H : 0));
+  w.Ep = (int)((E + 31) / 32 * 32);
+  w.vg_s = c.take<float>(w.split ? B * 2 * w.Ep : 0);
+  w.wx_s = c.take<float>(w.split ? (size_t)5 * H * 2 * w.Ep : 0);
   w.Acat2 = c.take<float>(bm ? R * w.ldA : 0);
   w.c2 = c.take<float>(bm ? R * H : 0);
   w.cum = c.take<float>(bm ? R : 0);
@@ -402,9 +406,24 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
   AA_TRY(gemm_nt(B * d.k, d.a, H, V, H, w.att_wv, H, ws.P, ws.ldP, nullptr, 0, nullptr, nullptr, st));
   // static (per image) gate terms: v_g half of x and the biases
   float* stat_img = beam > 1 ? ws.gates : ws.stat;   // [B,5H]; `gates` is free before the first step
-  AA_TRY(gemm_nt(B, 4 * H, E, v_g, E, w.w_ih + E, 2 * E, stat_img, 5 * H, nullptr, 0, w.b_ih, w.b_hh, st));
-  if (w.sen_wx) AA_TRY(gemm_nt(B, H, E, v_g, E, w.sen_wx + E, 2 * E, stat_img + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
-  else AA_CHECK_CUDA(cudaMemset2DAsync(stat_img + 4 * H, sizeof(float) * 5 * H, 0, sizeof(float) * H, (size_t)B, st));   // baseline model
+  if (ws.split) {   // on tensor cores like the per-step contractions (fp32-accurate 3xTF32): 4096 x 2560 x 256 took 165 us on the SIMT path
+    AA_TRY(launch_split_tf32(v_g, E, B, E, ws.vg_s, ws.Ep, st));
+    AA_TRY(launch_split_tf32(w.w_ih + E, 2 * E, 4 * H, E, ws.wx_s, ws.Ep, st));
+    if (w.sen_wx) AA_TRY(launch_split_tf32(w.sen_wx + E, 2 * E, H, E, ws.wx_s + (size_t)4 * H * 2 * ws.Ep, ws.Ep, st));
+    TcGemmArgs g{};
+    g.M = B; g.N = 4 * H; g.K = ws.Ep; g.elem_size = 4; g.split3 = 1;
+    g.A = ws.vg_s; g.lda = 2 * ws.Ep; g.B = ws.wx_s; g.ldb = 2 * ws.Ep;
+    g.D32 = stat_img; g.ldd32 = 5 * H; g.bias1 = w.b_ih; g.bias2 = w.b_hh;
+    AA_TRY(launch_gemm_tc(g, st));
+    if (w.sen_wx) {
+      g.N = H; g.B = ws.wx_s + (size_t)4 * H * 2 * ws.Ep; g.D32 = stat_img + 4 * H; g.bias1 = nullptr; g.bias2 = nullptr;
+      AA_TRY(launch_gemm_tc(g, st));
+    }
+  } else {
+    AA_TRY(gemm_nt(B, 4 * H, E, v_g, E, w.w_ih + E, 2 * E, stat_img, 5 * H, nullptr, 0, w.b_ih, w.b_hh, st));
+    if (w.sen_wx) AA_TRY(gemm_nt(B, H, E, v_g, E, w.sen_wx + E, 2 * E, stat_img + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
+  }
+  if (!w.sen_wx) AA_CHECK_CUDA(cudaMemset2DAsync(stat_img + 4 * H, sizeof(float) * 5 * H, 0, sizeof(float) * H, (size_t)B, st));   // baseline model
   if (beam > 1) {
     expand_rows_kernel<<<R, 256, 0, st>>>(stat_img, ws.stat, 5 * H, beam);
     AA_CHECK_LAUNCH("expand_rows");

@@ -221,7 +221,8 @@ int launch_sgemm(const GemmArgs& gin, cudaStream_t stream) {
   const long long sms = num_sms();
   auto tiles = [&](int bm, int bn) { return (long long)ceil_div(g.M, bm) * ceil_div(g.N, bn); };
   // pick the largest tile that still fills the chip; fall back to split-K for long, thin reductions
-  if (tiles(128, 128) >= sms) return dispatch_layout<128, 128, 16, 8, 8>(g, stream);
+  // (a 128-column tile wastes most of its work on N <= 64 outputs -- P = V W_v^T has 49 -- when the 64-column tiles fill the chip too)
+  if (tiles(128, 128) >= sms && !(g.N <= 64 && tiles(64, 64) >= sms)) return dispatch_layout<128, 128, 16, 8, 8>(g, stream);
   if (tiles(64, 64) >= sms || g.M > 32) {
     if (g.splitk == 0) {  // auto split-K
       const long long t = tiles(64, 64);
