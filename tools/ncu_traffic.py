@@ -14,7 +14,10 @@ TAGS = [  # (kernel-name regex, bench tag)
     (r"lstm_clk_fwd_kernel|lstm_seq_fwd_kernel", "lstm_seq_fwd"), (r"lstm_clk_bwd_kernel|lstm_seq_bwd_kernel", "lstm_seq_bwd"),
     (r"atten_fwd_tpar_kernel", "atten_fwd"), (r"atten_bwd_tpar_kernel", "atten_bwd"), (r"dec_atten_tma_kernel", "dec_step_fused"),
     (r"dec_cell_kernel", "dec_cell"), (r"ce_fwd_bwd", "ce_fwd_bwd"),
+    (r"argmax_filter_kernel", "dec_argmax_filter"), (r"argmax_refine_kernel", "dec_argmax_refine"), (r"argmax_finalize_kernel", "dec_argmax"),
+    (r"gemm_tc_kernel<128, 2, 5, 0, 0, 0, 2>", "dec_vocab_gemm1"),
 ]
+DECODE_SPLIT_ORDER = ["dec_gate_gemm", "dec_qr_gemm"]   # the two 3xTF32 contractions of a decode step, in launch order (reports named *decode*)
 GEMM_ORDER = ["gemm_vocab_fwd", "gemm_vocab_dx", "gemm_vocab_dw", "gemm_gates_in", "gemm_lstm_dw", "gemm_lstm_dx"]   # tools/prof_gemm.py, 2 launches each
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
 
@@ -36,9 +39,14 @@ def main(reps):
     acc = {}
     for rep in reps:
         gemm_i = 0
+        split_i = 0
         seen = {}
         for name, rd, wr, us in rows(rep):
-            if "gemm_tc_kernel" in name and "gemm" in rep:
+            if "decode" in rep and re.search(r"gemm_tc_kernel<\d+, 4, \d+, 0, 0, 1", name):
+                tag = DECODE_SPLIT_ORDER[split_i % 2]
+                first = split_i < 2
+                split_i += 1
+            elif "gemm_tc_kernel" in name and "gemm" in rep and "decode" not in rep:
                 tag = GEMM_ORDER[gemm_i // 2] if gemm_i // 2 < len(GEMM_ORDER) else None
                 first = gemm_i % 2 == 0
                 gemm_i += 1
