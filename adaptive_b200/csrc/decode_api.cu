@@ -368,13 +368,14 @@ int check_decode(const aa_dims* d, const aa_weights* w, int max_len, int beam) {
 // [hi (Kp) | lo (Kp)])
 int dec_gemm(const DecodeWs& ws, int M, int N, int K, int Kp, const float* A, long long lda, int lo_a, long long a_cols, const float* W,
              long long ldw, float* D, long long ldd, const float* Cin, long long ldcin, const float* bias, float* pmax, int* pidx,
-             cudaStream_t st) {
+             cudaStream_t st, int kcut_n0 = 0, int kcut_cols = 0) {
   if (!ws.split) return gemm_nt(M, N, K, A, lda, W, ldw, D, ldd, Cin, ldcin, bias, nullptr, st);
   TcGemmArgs g{};
   g.M = M; g.N = N; g.K = Kp; g.elem_size = 4; g.split3 = 1;
   g.A = A; g.lda = lda; g.lo_a = lo_a; g.a_cols = a_cols; g.B = W; g.ldb = ldw;
   g.D32 = D; g.ldd32 = ldd; g.Cin = Cin; g.ldcin = ldcin; g.beta = 1.f; g.bias1 = bias;
   g.pmax = pmax; g.pidx = pidx;
+  g.kcut_n0 = kcut_n0; g.kcut_cols = kcut_cols;
   return launch_gemm_tc(g, st);
 }
 
@@ -439,8 +440,9 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
                      float* alpha, long long ld_alpha, float* beta, long long ld_beta, cudaStream_t st) {
   const int H = d.H, E = d.E, K = E + H;
   // gates = [emb(w_t) | h_{t-1}] Wcat^T + static              (LSTM + sentinel-x pre-activations)
+  // (the sentinel rows 4H..5H of Wcat are zero beyond the embedding columns -- decode-mode h~ = 0, Q3: their tiles stop the K loop at E)
   AA_PROF("dec_gate_gemm", st, dec_gemm(ws, R, 5 * H, K, ws.Kp, Acur, ws.ldA, ws.lo, ws.ldA, ws.Wcat, ws.split ? 2 * ws.Kp : K, ws.gates,
-                                        5 * H, ws.stat, 5 * H, nullptr, nullptr, nullptr, st));
+                                        5 * H, ws.stat, 5 * H, nullptr, nullptr, nullptr, st, 4 * H, E));
   if (!ws.split) {   // exact-fp32 path: one fused kernel incl. the q/r mat-vecs
     DecodeStepArgs p{};
     p.B = R; p.k = d.k; p.a = d.a; p.H = H; p.beam = beam;

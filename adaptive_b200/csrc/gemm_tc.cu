@@ -79,6 +79,7 @@ struct TcEpilogue {
   float* pmax; int* pidx; int tiles_n;      // optional per-(row, n-tile) arg-max partials of D (bias included)
   int lo_a, lo_b;                           // split mode: column offset of the lo half inside a row of A / B
   int ksplit, kb_per;                       // split-K: work unit = (tile, K range of kb_per k-blocks); partial tiles are added with red.global.add
+  int kcut_n0, kcut_nkb;                    // tiles whose first column is >= kcut_n0 stop after kcut_nkb k-blocks (their B rows are zero beyond)
 };
 
 // Tile geometry (bytes): every smem row is 128 B (the swizzle span).
@@ -157,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int tile = unit % num_tiles, sp = unit / num_tiles;
         const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-        const int kb0 = sp * e.kb_per, kb1 = min(nkb, kb0 + e.kb_per);
+        const int kb0 = sp * e.kb_per, kb1 = min(n0 >= e.kcut_n0 ? e.kcut_nkb : nkb, kb0 + e.kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -197,7 +198,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int it = 0, lt = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++lt) {
-        const int kb0 = (unit / num_tiles) * e.kb_per, kb1 = min(nkb, kb0 + e.kb_per);
+        const int n0 = ((unit % num_tiles) / tiles_m) * BN;
+        const int kb0 = (unit / num_tiles) * e.kb_per, kb1 = min(n0 >= e.kcut_n0 ? e.kcut_nkb : nkb, kb0 + e.kb_per);
         const int acc = lt & 1;
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
@@ -428,6 +430,11 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
   constexpr int EW = epi_warps(SPLIT);
   constexpr int NPARTS = (EW / 4) < (BN / 32) ? (EW / 4) : (BN / 32);
+  e.kcut_n0 = 0x7fffffff; e.kcut_nkb = 0;
+  if (g.kcut_cols > 0 && g.kcut_n0 % BN == 0 && g.kcut_n0 < g.N) {     // (only when the cut falls on a tile boundary of this configuration)
+    e.kcut_n0 = g.kcut_n0;
+    e.kcut_nkb = ceil_div(g.kcut_cols, 128 / ES);
+  }
   e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = PM == 2 ? ceil_div(g.N, 16) : ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
   constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration exceeds shared memory");
@@ -457,6 +464,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   e.kb_per = ceil_div(nkb, ksplit);
   ksplit = ceil_div(nkb, e.kb_per);            // no empty K ranges
   e.ksplit = ksplit;
+  if (ksplit > 1) e.kcut_n0 = 0x7fffffff;      // (a K range beyond the cut would be empty: its accumulator never written)
   if (ksplit > 1 && !(g.Cin == g.D32 && g.beta == 1.f))   // (in-place accumulate adds onto C itself: nothing to clear)
     AA_CHECK_CUDA(cudaMemset2DAsync(g.D32, sizeof(float) * (size_t)g.ldd32, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
   const int num_units = num_tiles * ksplit;

@@ -98,6 +98,9 @@ struct TcGemmArgs {
   // tile_n = gemm_tc_argmax_tile_n(N); D32/D16 may then both be null (the logits are never written).
   // pidx == null: maxima only (cheaper epilogue; bias2 must be null)
   float* pmax; int* pidx;
+  // optional: the rows n >= kcut_n0 of B are zero beyond their first kcut_cols reduction columns (per half in split mode): output
+  // tiles starting at or after kcut_n0 stop their K loop there.  Ignored unless kcut_n0 is a multiple of the tile width; no split-K.
+  int kcut_n0, kcut_cols;
 };
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
 int gemm_tc_argmax_tile_n(int N);
