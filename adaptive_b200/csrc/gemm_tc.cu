@@ -489,7 +489,15 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
   const long long mt = ceil_div(g.M, BM);
   const bool can_splitk = g_tc_splitk && g.D32 && !g.D16 && !g.pmax && ceil_div(g.K, 128 / ES) >= 8;
   // maxima partials of a plain (single-pass) contraction: one per 16 columns, layout [M, ceil(N / 16)] (gemm_tc_argmax_tile_n_plain)
-  if (g.pmax) return launch_cfg<128, ES, 5, false, false, false, 2>(g, st);
+  if (g.pmax) {
+    // (bf16, wide N: 256-column tiles pull 48 KB per k-block for twice the columns of a 32 KB 128-column k-block -- the pass is
+    //  bound by the operand feed; AA_ARGMAX_BN256=0 keeps the 128-column tiles)
+    if constexpr (ES == 2) {
+      static const bool wide = [] { const char* e = getenv("AA_ARGMAX_BN256"); return !e || e[0] != '0'; }();
+      if (wide && g.N >= 2048) return launch_cfg<256, 2, 3, false, false, false, 2>(g, st);
+    }
+    return launch_cfg<128, ES, 5, false, false, false, 2>(g, st);
+  }
   // bf16, 256-column tiles: one A k-block feeds twice the columns (48 KB per k-block for 2x the flops of a 128x128 tile's 32 KB)
   // and a 128x256x16 MMA costs 128 cycles against 2 x 103.  Measured (tools/bench_gemm.py, r01_v58): the config-5 vocabulary
   // projection (4608 x 20000 x 1024) 195 -> 168 us (1.12 PFLOP/s), but every K <= 512 contraction of config 2 a few per cent
