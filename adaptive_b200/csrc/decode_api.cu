@@ -38,8 +38,8 @@ struct DecodeWs {
   // reads the [emb | h] window, the q/r GEMM the [h | s] window.  W2 = [[W_g, 0], [W_g, W_s]] gives [q | r] in one GEMM.
   float *Wp_s, *pmax, *W2, *hs, *qr; int* pidx;
   int split, bm, K, Kp, lo, K2p, Hp, ldA, ldU, tiles_n;
-  // filter-and-refine arg-max (vocab_refine.cu): 16-column partial tiles (`tiles64` of them), per-tile weight norms and candidate row lists
-  int refine, tiles64; float* wnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
+  // filter-and-refine arg-max (vocab_refine.cu): 16-column partial tiles (`tiles16` of them), per-tile weight norms and candidate row lists
+  int refine, tiles16; float* wnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
   __nv_bfloat16 *u16, *Wp16;
   float *vg_s, *wx_s; int Ep;     // split pipeline: (hi | lo) copies of v_g [B, 2*Ep] and of the v_g columns of [W_ih; W_x] [5H, 2*Ep]
   int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
@@ -67,8 +67,8 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.ldU = w.split ? 2 * w.Hp : (int)H;
   w.tiles_n = ceil_div(d.Vc, gemm_tc_argmax_tile_n(d.Vc));
   w.refine = (w.split && !bm && g_argmax_refine && argmax_refine_supported(d.Vc, d.H)) ? ((g_argmax_refine >= 2 && d.H % 8 == 0) ? 2 : 1) : 0;
-  w.tiles64 = ceil_div(d.Vc, gemm_tc_argmax_tile_n_plain(d.Vc));
-  const size_t ptiles = w.refine ? (size_t)w.tiles64 : (size_t)w.tiles_n;
+  w.tiles16 = ceil_div(d.Vc, gemm_tc_argmax_tile_n_plain(d.Vc));
+  const size_t ptiles = w.refine ? (size_t)w.tiles16 : (size_t)w.tiles_n;
   w.ldP = w.split ? (d.a + 3) / 4 * 4 : d.a;
   w.ld_qr = (2 * d.a + 3) / 4 * 4;
   w.Wcat = c.take<float>((size_t)5 * H * (w.split ? 2 * w.Kp : (int)K));
@@ -85,9 +85,9 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.Wp_s = c.take<float>(w.split ? (size_t)d.Vc * 2 * w.Hp : 0);
   w.pmax = c.take<float>((w.split && !bm) ? R * ptiles : 0);
   w.pidx = c.take<int>((w.split && !bm) ? R * ptiles : 0);
-  w.wnorm = c.take<float>(w.refine ? w.tiles64 : 0);
-  w.counts = c.take<int>(w.refine ? w.tiles64 + 1 : 0);      // (+ 1: finished-CTA ticket of the refinement kernel)
-  w.list = c.take<unsigned>(w.refine ? (size_t)w.tiles64 * R : 0);
+  w.wnorm = c.take<float>(w.refine ? w.tiles16 : 0);
+  w.counts = c.take<int>(w.refine ? w.tiles16 + 1 : 0);      // (+ 1: finished-CTA ticket of the refinement kernel)
+  w.list = c.take<unsigned>(w.refine ? (size_t)w.tiles16 * R : 0);
   w.ncand = c.take<int>(w.refine ? R : 0);
   w.u16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? R * H : 0));
   w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? (size_t)d.Vc * H : 0));
@@ -390,7 +390,7 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
     if (ws.refine) {
       AA_TRY(launch_tile_wnorm(w.mlp_w, d.Vc, H, ws.wnorm, st));
       if (ws.refine == 2) AA_TRY(launch_cast2d(w.mlp_w, H, ws.Wp16, H, d.Vc, H, st));
-      AA_CHECK_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)(ws.tiles64 + 1), st));
+      AA_CHECK_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)(ws.tiles16 + 1), st));
     }
     pack_wqr_kernel<<<2 * d.a, 256, 0, st>>>(w.att_wg, w.att_ws, ws.W2, d.a, H, ws.K2p);
     AA_CHECK_LAUNCH("pack_wqr");
@@ -533,11 +533,11 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
         }
         g.bias1 = w->mlp_b; g.pmax = ws.pmax; g.pidx = nullptr;     // (maxima only: the refinement writes the indices of the tiles that matter)
         AA_PROF("dec_vocab_gemm1", st, launch_gemm_tc(g, st));
-        AA_PROF("dec_argmax_filter", st, launch_argmax_filter(ws.pmax, ws.tiles64, B, ws.u, ws.ldU, ws.Hp, H, ws.wnorm,
+        AA_PROF("dec_argmax_filter", st, launch_argmax_filter(ws.pmax, ws.tiles16, B, ws.u, ws.ldU, ws.Hp, H, ws.wnorm,
                                                               ws.refine == 2 ? 1.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, ws.ncand, st));
         AA_PROF("dec_argmax_refine", st, launch_argmax_refine(w->mlp_w, w->mlp_b, Vc, H, ws.u, ws.ldU, ws.Hp, B, ws.counts, ws.list,
-                                                              ws.pmax, ws.pidx, ws.tiles64, st));
-        AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles64, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,
+                                                              ws.pmax, ws.pidx, ws.tiles16, st));
+        AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles16, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,
                                                          ws.lo, st, ws.ncand));
         continue;
       }

@@ -181,7 +181,10 @@ def kernel_models(dims, B, T, decode_B):
         "lstm_rec_gemm": ("tensor", fl(B, 4 * H, H)), "bptt_rec_gemm": ("tensor", fl(B, H, 4 * H)),
         "dec_vocab_gemm": ("tf32x3", fl(decode_B, Vc, H)), "dec_vocab_gemm1": ("bf16x1", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tf32x3", fl(decode_B, 5 * H, E + H)),
         "dec_step_fused": ("hbm", float(step_bytes) * decode_B),
-        "dec_argmax": ("hbm", float(decode_B) * ((Vc + 127) // 128) * 8),      # reduction of the GEMM epilogue's partials
+        # final reduction over the row's refined candidates (~2 entries) + gather of the next word's embedding into the (hi | lo) A operand
+        "dec_argmax": ("hbm", float(decode_B) * (E * 4 + 2 * E * 4 + 8 + 4 + 3 * 8)),
+        # candidate filter: one pass over the first pass's maxima [B, Vc/16] and over u (hi | lo) for the row norms
+        "dec_argmax_filter": ("hbm", float(decode_B) * (((Vc + 15) // 16) * 4 + 2 * H * 4)),
         # training attention, per launch over the whole batch: V + P + per-step rows in, u/ctx/alpha/beta out
         "atten_fwd": ("hbm", float(B) * (k * H * 4 + k * a * 4 + T * (2 * a + 2 * H + 2 * H + k + 1) * 4)),
         "atten_bwd": ("hbm", float(B) * (2 * k * H * 4 + 2 * k * a * 4 + T * (2 * a + 3 * H + H + k + 1 + 2 * a) * 4)),
