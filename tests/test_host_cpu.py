@@ -101,3 +101,56 @@ def test_ids_to_captions_and_vocabulary_format():
     assert res[0] == {"image_id": 11, "caption": "a dog runs"} and [r["image_id"] for r in res] == [11, 12, 13]
     with pytest.raises(ValueError):
         caption_results([1, 2], ids, vocab)
+
+
+def test_baseline_model_surface_and_weight_tuples():
+    """the sentinel-less baseline classes keep the reference's state_dict keys (baseline_attention.py:66-194:
+    no sentinel, no affine_s) and travel to the C ABI as the 13-tuple with three NULL entries, all three together."""
+    from adaptive_b200 import baseline
+    from adaptive_b200.synth import BASELINE_KEYS, baseline_weights
+
+    m = baseline.Encoder2Decoder()
+    keys = tuple(k[len("decoder."):] for k in m.state_dict() if k.startswith("decoder."))
+    assert keys == BASELINE_KEYS and len(keys) == 10
+    assert not any("sentinel" in k or "affine_s" in k for k in keys)
+    w13 = m.decoder.weights()
+    assert len(w13) == 13 and [i for i, t in enumerate(w13) if t is None] == [5, 6, 9]      # sen_wx, sen_wh, att_ws
+    assert [_lib.WEIGHT_FIELDS[i] for i in (5, 6, 9)] == list(F_aa.SENTINEL_FIELDS)
+    s = F_aa.weights_struct(w13)
+    assert s.sen_wx is None and s.sen_wh is None and s.att_ws is None and s.att_wv is not None
+    dims = Dims(H=32, E=16, Vc=40, k=49)
+    w = make_weights(dims)
+    assert tuple(baseline_weights(w)) == BASELINE_KEYS
+    full = tuple(torch.from_numpy(w[k]) for k in DECODER_KEYS)
+    assert F_aa.baseline_weights(full)[5] is None and F_aa.baseline_weights(full)[7] is full[7]
+    partial = list(full)
+    partial[5] = None                                        # only sen_wx missing: neither model
+    inp = make_inputs(dims, 2, 3)
+    with pytest.raises(ValueError, match="only together"):
+        F_aa._check_weights(partial, dims.H, dims.E, dims.Vc, dims.a)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):                                   # baseline weights on the CPU: no fallback either
+        F_aa.decoder_forward(F_aa.baseline_weights(full), torch.from_numpy(inp["V"]), torch.from_numpy(inp["v_g"]),
+                             torch.from_numpy(inp["captions"]))
+
+
+def test_encoder_heads_surface_and_size_queries():
+    """AttentiveCNN's head parameters under the reference's names, the C-ABI structs in that order, workspace
+    queries without a GPU, and no CPU path."""
+    from adaptive_b200.modules import AttentiveCNN
+    from adaptive_b200.synth import ENCODER_KEYS, make_encoder_weights, make_features
+
+    enc = AttentiveCNN(16, 32, None, feat_dim=64)
+    assert tuple(k for k in enc.state_dict()) == ENCODER_KEYS
+    assert [_lib.ENC_KEY_TO_FIELD[k] for k in ENCODER_KEYS] == list(_lib.ENC_FIELDS)
+    assert [tuple(t.shape) for t in enc.weights()] == [(32, 64), (32,), (16, 64), (16,), (32, 64), (32,), (32, 64), (32,)]
+    lib = _lib.load()
+    d32 = _lib.AAEncDims(B=80, C=2048, hw=49, H=512, E=256, precision=_lib.PREC_FP32)
+    d16 = _lib.AAEncDims(B=80, C=2048, hw=49, H=512, E=256, precision=_lib.PREC_BF16)
+    assert lib.aa_encoder_saved_bytes(ctypes.byref(d32)) >= 80 * 49 * 2048 * 4             # the fp32 transpose of the map
+    assert lib.aa_encoder_saved_bytes(ctypes.byref(d16)) >= 80 * 49 * 2048 * 2 + (512 * 3 + 256) * 2048 * 2
+    assert lib.aa_encoder_bwd_scratch_bytes(ctypes.byref(d32), 1) > lib.aa_encoder_bwd_scratch_bytes(ctypes.byref(d32), 0)
+    w = make_encoder_weights(Dims(H=32, E=16, Vc=8, k=49), 64)
+    A = make_features(2, 64, (7, 7))
+    assert A.shape == (2, 64, 7, 7) and A.min() >= 0 and tuple(w) == ENCODER_KEYS
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.from_numpy(A))
