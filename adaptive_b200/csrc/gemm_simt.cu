@@ -2,6 +2,8 @@
 // shared-memory tiles, 128-bit global loads.  It is the exact-fp32 contraction engine of the
 // library (decode path, weight gradients in fp32 mode) and the on-device reference the
 // tcgen05 GEMMs are validated against.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aa {
@@ -222,6 +224,10 @@ int launch_sgemm(const GemmArgs& gin, cudaStream_t stream) {
   auto tiles = [&](int bm, int bn) { return (long long)ceil_div(g.M, bm) * ceil_div(g.N, bn); };
   // pick the largest tile that still fills the chip; fall back to split-K for long, thin reductions
   // (a 128-column tile wastes most of its work on N <= 64 outputs -- P = V W_v^T has 49 -- when the 64-column tiles fill the chip too)
+  if (g.N <= 64 && tiles(128, 64) >= sms) {   // tall and narrow (P): 128 x 64 tiles, 8 x 4 outputs per thread
+    static const bool tall = [] { const char* e = getenv("AA_SGEMM_128X64"); return !e || e[0] != '0'; }();
+    if (tall) return dispatch_layout<128, 64, 16, 8, 4>(g, stream);
+  }
   if (tiles(128, 128) >= sms && !(g.N <= 64 && tiles(64, 64) >= sms)) return dispatch_layout<128, 128, 16, 8, 8>(g, stream);
   if (tiles(64, 64) >= sms || g.M > 32) {
     if (g.splitk == 0) {  // auto split-K
