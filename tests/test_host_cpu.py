@@ -154,3 +154,53 @@ def test_encoder_heads_surface_and_size_queries():
     assert A.shape == (2, 64, 7, 7) and A.min() >= 0 and tuple(w) == ENCODER_KEYS
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         enc(torch.from_numpy(A))
+
+
+def _round_bf16(x):
+    """fp32 -> bf16 (round to nearest even) -> fp32, like __floats2bfloat162_rn."""
+    b = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000
+    return b.astype(np.uint32).view(np.float32)
+
+
+def _round_tf32(x):
+    """fp32 -> tf32 (round to nearest, ties away: cvt.rna.tf32.f32) -> fp32."""
+    b = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + 0x1000) & 0xFFFFE000
+    return b.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("rounder,c", [(_round_bf16, 1.1 / 256), (_round_tf32, 1.1 / 1024)])
+def test_argmax_filter_bound_never_drops_the_exact_argmax(rounder, c):
+    """The claim csrc/vocab_refine.cu rests on, checked in numpy: with |approx_j - exact_j| <= c ||u|| ||W_j|| (c = 1.1 * 2^-8 for a bf16
+    first pass, 1.1 * 2^-10 for tf32) the 16-column tile holding the exact arg-max always passes the filter
+    `tile max + bound >= max over tiles of (tile max - bound)`, also for rows built to have near-ties, and the filter keeps few tiles."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    H, Vc, R, TN = 256, 2000, 300, 16
+    W = (rng.standard_normal((Vc, H)) * np.sqrt(2.0 / H)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(Vc)).astype(np.float32)
+    u = (0.4 + rng.standard_normal((R, H))).astype(np.float32)                    # common-mode component like c_hat + h
+    # adversarial rows: make two far-apart columns (different tiles) tie to ~1e-6
+    exact0 = u.astype(np.float64) @ W.astype(np.float64).T + bias
+    for r in range(0, R, 3):
+        j1, j2 = np.argsort(exact0[r])[-2:]
+        if abs(j1 - j2) >= TN:
+            d = W[j2].astype(np.float64) - W[j1].astype(np.float64)
+            gap = exact0[r, j2] - exact0[r, j1]
+            u[r] = (u[r].astype(np.float64) - (gap - 1e-6) * d / (d @ d)).astype(np.float32)
+    exact = u.astype(np.float64) @ W.astype(np.float64).T + bias
+    approx = (rounder(u).astype(np.float64) @ rounder(W).astype(np.float64).T).astype(np.float32) + bias     # fp32 accumulate
+    assert np.abs(approx - exact).max() <= (c * np.linalg.norm(u, axis=1)[:, None] * np.linalg.norm(W, axis=1)[None, :]).max()
+    assert (np.abs(approx - exact) <= c * np.linalg.norm(u, axis=1)[:, None] * np.linalg.norm(W, axis=1)[None, :] + 1e-7).all()
+    tiles = Vc // TN
+    tmax = approx.reshape(R, tiles, TN).max(-1)
+    wn = np.linalg.norm(W, axis=1).reshape(tiles, TN).max(-1)
+    b = c * np.linalg.norm(u, axis=1)[:, None] * wn[None, :]
+    L = (tmax - b).max(1, keepdims=True)
+    keep = tmax + b >= L
+    win = exact.argmax(1) // TN
+    assert keep[np.arange(R), win].all()                                          # the exact winner's tile is always refined
+    # every tile holding a column within 1e-6 of the exact maximum is kept too (ties are resolved on exact values afterwards)
+    near = (exact >= exact.max(1, keepdims=True) - 1e-6).reshape(R, tiles, TN).any(-1)
+    assert (keep | ~near).all()
+    assert 1.0 <= keep.sum(1).mean() < 0.2 * tiles
