@@ -60,15 +60,17 @@ constexpr int FL_THREADS = 256, FL_ROWS = FL_THREADS / 32;      // one warp per 
 __global__ void __launch_bounds__(FL_THREADS) argmax_filter_kernel(const float* __restrict__ pmax, int tiles, int R, const float* __restrict__ u,
                                                                    long long ldu, long long lo_off, int H, const float* __restrict__ wnorm,
                                                                    float c, int* __restrict__ counts, unsigned* __restrict__ list,
-                                                                   int* __restrict__ ncand) {
+                                                                   int* __restrict__ ncand, int stage) {
   extern __shared__ int fsm[];
   int* scnt = fsm;                                              // [tiles] pairs this CTA lists per tile, then the running position inside the CTA's range
   float* wn = reinterpret_cast<float*>(fsm + tiles);            // [tiles] weight norms
   __shared__ int spairs;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* prow = wn + tiles + warp * tiles;                      // [tiles] this warp's row of maxima (read three times)
   const int r = blockIdx.x * FL_ROWS + warp;
   const bool live = r < R;
+  // this warp's row of maxima is read three times: staged in shared memory when it fits (stage != 0), else re-read from L2
+  float* srow = wn + tiles + warp * tiles;
+  const float* prow = stage ? srow : pmax + (long long)(live ? r : 0) * tiles;
   for (int t = tid; t < tiles; t += FL_THREADS) {
     scnt[t] = 0;
     wn[t] = __ldg(wnorm + t);
@@ -76,9 +78,11 @@ __global__ void __launch_bounds__(FL_THREADS) argmax_filter_kernel(const float* 
   if (tid == 0) spairs = 0;
   float cn = 0.f, L = INFINITY;
   if (live) {
-    const float* pr = pmax + (long long)r * tiles;
+    if (stage) {
+      const float* pr = pmax + (long long)r * tiles;
 #pragma unroll 4
-    for (int t = lane; t < tiles; t += 32) prow[t] = __ldcg(pr + t);
+      for (int t = lane; t < tiles; t += 32) srow[t] = __ldcg(pr + t);
+    }
     const float* ur = u + (long long)r * ldu;
     float ss = 0.f;
     for (int k = lane * 4; k < H; k += 128) {
@@ -288,8 +292,8 @@ long long refine_pairs(int reset) {
 }
 
 bool argmax_refine_supported(int Vc, int H) {
-  // (12-bit slots in the list entries; the filter stages 10 arrays of one entry per tile in 48 KB of shared memory)
-  return Vc > 64 && Vc <= 1200 * RF_TN && H % 8 == 0 && refine_smem(H, ceil_div(Vc, RF_TN)) <= 110 * 1024;
+  // (12-bit slots in the list entries: at most 4096 tiles; the refinement's shared memory -- 16 weight rows + 32 rows of u -- must fit one SM)
+  return Vc > 64 && Vc <= 4096 * RF_TN && H % 8 == 0 && refine_smem(H, ceil_div(Vc, RF_TN)) <= 220 * 1024;
 }
 
 int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s) {
@@ -301,7 +305,9 @@ int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t 
 int launch_argmax_filter(const float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
                          int* counts, unsigned* list, int* ncand, cudaStream_t s) {
   AA_REQUIRE(R <= (1 << 20) && tiles <= 4096, "argmax_filter: at most 2^20 rows and 4096 tiles (got %d, %d)", R, tiles);
-  argmax_filter_kernel<<<ceil_div(R, FL_ROWS), FL_THREADS, sizeof(int) * tiles * (2 + FL_ROWS), s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm, c, counts, list, ncand);
+  const int stage = tiles <= 1200 ? 1 : 0;      // (2 + 8 arrays of one entry per tile within the default 48 KB of shared memory)
+  argmax_filter_kernel<<<ceil_div(R, FL_ROWS), FL_THREADS, sizeof(int) * tiles * (2 + (stage ? FL_ROWS : 0)), s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm,
+                                                                                                            c, counts, list, ncand, stage);
   AA_CHECK_LAUNCH("argmax_filter");
   return AA_OK;
 }

@@ -478,7 +478,8 @@ def test_stage_operators_vs_oracle():
 
 
 @pytest.mark.parametrize("dims,B,L", [(CFG_A, 1024, 6), (Dims(H=128, E=64, Vc=1000, k=49), 300, 8), (Dims(H=48, E=20, Vc=77, k=10), 37, 7),
-                                      (Dims(H=256, E=64, Vc=4097, k=20), 129, 5)])
+                                      (Dims(H=256, E=64, Vc=4097, k=20), 129, 5),
+                                      (Dims(H=1024, E=128, Vc=20000, k=20), 40, 3)])      # BASELINE config 5's hidden size / vocabulary
 def test_greedy_argmax_refine_matches_full_projection(dims, B, L):
     """Filter-and-refine arg-max (one tf32 pass + exact fp32 logits of the candidate tiles, vocab_refine.cu) against the
     fp32-accurate 3xTF32 projection of every logit: same ids, except where the two best logits are within the near-tie threshold."""
