@@ -7,14 +7,15 @@
 //   1. ONE single-pass tensor-core contraction over bf16 mirrors (or the tf32 "hi" halves) of the operands, whose epilogue
 //      keeps only the per-(row, 16-column tile) maximum (gemm_tc.cu, arg-max partials);
 //   2. argmax_filter: with the rigorous bound |approx_j - exact_j| <= c ||u||_2 ||W_j||_2 (Cauchy-Schwarz over the
-//      per-product rounding errors of the two tf32 roundings, plus the fp32 accumulation), a tile can hold the exact
-//      arg-max only if its approximate maximum + bound reaches the best (approximate maximum - bound) of the row;
-//      those (row, tile) pairs -- ~1.3 per row for tf32, ~2 for bf16 at config 3 -- are appended to the tile's row list, every
-//      other partial is set to -inf;
+//      per-product rounding errors of the two operand roundings -- 2^-9 each for bf16, 2^-11 for tf32 -- plus an allowance for
+//      the fp32 accumulation: c = 1.1 * 2^-8 / 1.1 * 2^-10), a tile can hold the exact arg-max only if its approximate
+//      maximum + bound reaches the best (approximate maximum - bound) of the row; those (row, tile) pairs -- ~1.3 per row for
+//      tf32, ~2.2 for bf16 at config 3 (625 tiles) -- are appended to the tile's row list together with their rank ("slot")
+//      among the row's candidates (tests/test_host_cpu.py::test_argmax_filter_bound_never_drops_the_exact_argmax checks the bound in numpy);
 //   3. argmax_refine: work units (tile, chunk of listed rows) dealt to a persistent grid; a unit keeps the tile's 16 fp32 weight
 //      rows in shared memory and recomputes the listed rows' 16 logits in plain fp32 FMA arithmetic, writing the tile's exact
-//      (max, index) back;
-//   4. the existing argmax_finalize reduces the partials (lowest index wins ties) and gathers the next embedding.
+//      (max, index) to the row's slot;
+//   4. argmax_finalize reduces the row's ncand[row] refined candidates (lowest index wins ties) and gathers the next embedding.
 // Every column that could be the exact arg-max is recomputed exactly, so the ids equal those of an exact fp32 projection
 // (up to fp32 summation order, like any fp32 implementation).
 #include "kernels.cuh"
