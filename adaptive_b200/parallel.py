@@ -256,6 +256,10 @@ class DataParallelTrainer:
         self.model, self.group, self.overlap = model, group, overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.weights = model.decoder.weights()
+        if any(t is None for t in self.weights):
+            raise ValueError("DataParallelTrainer buckets the 13 gradients of the adaptive decoder; the sentinel-less baseline model "
+                             "(adaptive_b200.baseline) trains through Encoder2Decoder.forward on one GPU per process and all-reduces "
+                             "its p.grad tensors itself")
         dev = self.weights[0].device
         if dev.type != "cuda":
             raise RuntimeError("DataParallelTrainer needs the decoder on a CUDA device (no CPU fallback)")

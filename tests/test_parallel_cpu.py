@@ -117,3 +117,12 @@ def test_reducer_count_and_gather_over_gloo_world2():
         ok_sum, order_ok, n_glob, n_glob2, ids_ok = out[r]
         assert ok_sum and order_ok and ids_ok
         assert n_glob == n_glob2 == 10 + 13
+
+
+def test_dp_trainer_rejects_the_baseline_model_clearly():
+    """The gradient buckets are laid out for the adaptive decoder's 13 tensors; the baseline model says so instead of failing obscurely."""
+    from adaptive_b200 import baseline
+    from adaptive_b200.parallel import DataParallelTrainer
+
+    with pytest.raises(ValueError, match="baseline"):
+        DataParallelTrainer(baseline.Encoder2Decoder())
