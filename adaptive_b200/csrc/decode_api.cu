@@ -66,7 +66,9 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.ldA = w.split ? 2 * w.lo : (int)K;
   w.ldU = w.split ? 2 * w.Hp : (int)H;
   w.tiles_n = ceil_div(d.Vc, gemm_tc_argmax_tile_n(d.Vc));
-  w.refine = (w.split && !bm && g_argmax_refine && argmax_refine_supported(d.Vc, d.H)) ? ((g_argmax_refine >= 2 && d.H % 8 == 0) ? 2 : 1) : 0;
+  // (list entries pack the row into 20 bits: larger batches take the 3xTF32 projection of every logit)
+  w.refine = (w.split && !bm && g_argmax_refine && argmax_refine_supported(d.Vc, d.H) && R <= ((size_t)1 << 20))
+                 ? ((g_argmax_refine >= 2 && d.H % 8 == 0) ? 2 : 1) : 0;
   w.tiles16 = ceil_div(d.Vc, gemm_tc_argmax_tile_n_plain(d.Vc));
   const size_t ptiles = w.refine ? (size_t)w.tiles16 : (size_t)w.tiles_n;
   w.ldP = w.split ? (d.a + 3) / 4 * 4 : d.a;
