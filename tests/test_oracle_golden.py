@@ -160,3 +160,38 @@ def test_baseline_decoder_vs_reference(case, tag, dt, tol):
     if tag == "f64":
         assert np.array_equal(ids, g[tag + "_greedy_ids"])
         assert rel_err(att, g[tag + "_greedy_alpha"]) < 1e-11
+
+
+def test_beam_with_full_width_equals_exhaustive_search():
+    """Beam search has no reference (Q14): besides the width-1 == greedy check above, a beam as wide as the number of live prefixes
+    cannot prune anything, so its best hypothesis must be the best of ALL sequences (scored step by step with the reference's own
+    single-step decoder, a finished sequence padded with <end> at no cost) -- an independent restatement of the definition."""
+    import itertools
+
+    dims, B, L = Dims(H=16, E=8, Vc=5, k=6), 2, 3
+    w = {k: v.astype(np.float64) for k, v in make_weights(dims, seed=4, bias_scale=0.3).items()}
+    inp = make_inputs(dims, B, 1, seed=5)
+    V, v_g, h0, c0 = (inp[k].astype(np.float64) for k in ("V", "v_g", "h0", "c0"))
+    ids, _, _, score = orc.beam_decode(w, V, v_g, h0, c0, beam=dims.Vc ** (L - 1), max_len=L)
+    for b in range(B):
+        best, best_seq = -np.inf, None
+        for seq in itertools.product(range(dims.Vc), repeat=L):
+            # canonical form of a finished hypothesis: everything after the first <end> is <end>
+            if any(seq[t] != orc.END_ID for t in range(L) if orc.END_ID in seq[:t]):
+                continue
+            h, c, tok, tot = h0[b:b + 1], c0[b:b + 1], np.ones(1, dtype=np.int64), 0.0
+            for t in range(L):
+                if orc.END_ID in seq[:t]:
+                    break                                   # frozen: keeps its score
+                sc, _, _, h, c = orc.decode_step(w, V[b:b + 1], v_g[b:b + 1], tok, h, c)
+                lp = sc[0] - sc[0].max()
+                lp = lp - np.log(np.exp(lp).sum())
+                tot += lp[seq[t]]
+                tok = np.asarray([seq[t]], dtype=np.int64)
+            if tot > best + 1e-12:
+                best, best_seq = tot, seq
+        assert abs(score[b] - best) < 1e-10
+        assert tuple(ids[b]) == best_seq
+
+
+from adaptive_b200.synth import Dims, make_inputs, make_weights  # noqa: E402
