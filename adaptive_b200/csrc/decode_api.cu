@@ -16,7 +16,7 @@ constexpr int MAX_BEAM = 8;
 int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
 // filter-and-refine arg-max of the greedy vocabulary projection (vocab_refine.cu); AA_DECODE_REFINE=0 / aa_debug_set_decode_argmax_refine(0)
 // keep the fp32-accurate 3xTF32 contraction over the whole vocabulary
-// (1 = tf32 first pass, 2 = bf16 first pass: half the operand bytes, 8x the error bound -> ~2 candidate tiles per row instead of ~1.3)
+// (1 = tf32 first pass, 2 = bf16 first pass: half the operand bytes, ~8x the error bound -> a few candidate tiles per row instead of ~1.3)
 int g_argmax_refine = [] { const char* e = getenv("AA_DECODE_REFINE"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }();
 
 struct Carver {
@@ -525,7 +525,8 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
         // arg-max only: ONE tf32 pass over the hi halves with per-64-column maxima, then exact fp32 logits for the few (row, tile)
         // pairs that can hold the maximum (vocab_refine.cu).  c = 1.1 * 2^-10: two tf32 roundings per product (2^-11 each) and
         // an allowance of 2^-13.3 for the fp32 accumulation of the tensor pipe, relative to ||u|| ||W_j||.
-        // (bf16 first pass: 2^-9 per rounding -> c = 1.1 * 2^-8, operands = the bf16 mirrors of u and W_p)
+        // (bf16 first pass: 8 significant bits, round-to-nearest unit roundoff 2^-8 per operand -> two roundings per product
+        // 2^-7 (1 + 2^-9); c = 2.1 * 2^-8 leaves 5 % for the fp32 accumulation; operands = the bf16 mirrors of u and W_p)
         TcGemmArgs g{};
         g.M = B; g.N = Vc;
         if (ws.refine == 2) {
@@ -536,7 +537,7 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
         g.bias1 = w->mlp_b; g.pmax = ws.pmax; g.pidx = nullptr;     // (maxima only: the refinement writes the indices of the tiles that matter)
         AA_PROF("dec_vocab_gemm1", st, launch_gemm_tc(g, st));
         AA_PROF("dec_argmax_filter", st, launch_argmax_filter(ws.pmax, ws.tiles16, B, ws.u, ws.ldU, ws.Hp, H, ws.wnorm,
-                                                              ws.refine == 2 ? 1.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, ws.ncand, st));
+                                                              ws.refine == 2 ? 2.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, ws.ncand, st));
         AA_PROF("dec_argmax_refine", st, launch_argmax_refine(w->mlp_w, w->mlp_b, Vc, H, ws.u, ws.ldU, ws.Hp, B, ws.counts, ws.list,
                                                               ws.pmax, ws.pidx, ws.tiles16, st));
         AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles16, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,

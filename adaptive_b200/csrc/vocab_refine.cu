@@ -7,8 +7,9 @@
 //   1. ONE single-pass tensor-core contraction over bf16 mirrors (or the tf32 "hi" halves) of the operands, whose epilogue
 //      keeps only the per-(row, 16-column tile) maximum (gemm_tc.cu, arg-max partials);
 //   2. argmax_filter: with the rigorous bound |approx_j - exact_j| <= c ||u||_2 ||W_j||_2 (Cauchy-Schwarz over the
-//      per-product rounding errors of the two operand roundings -- 2^-9 each for bf16, 2^-11 for tf32 -- plus an allowance for
-//      the fp32 accumulation: c = 1.1 * 2^-8 / 1.1 * 2^-10), a tile can hold the exact arg-max only if its approximate
+//      per-product rounding errors of the two operand roundings -- unit roundoff 2^-8 each for bf16 (8 significant bits,
+//      round to nearest), 2^-11 for tf32 (cvt.rna) -- plus an allowance for the fp32 accumulation: c = 2.1 * 2^-8 /
+//      1.1 * 2^-10), a tile can hold the exact arg-max only if its approximate
 //      maximum + bound reaches the best (approximate maximum - bound) of the row; those (row, tile) pairs -- ~1.3 per row for
 //      tf32, ~2.2 for bf16 at config 3 (625 tiles) -- are appended to the tile's row list together with their rank ("slot")
 //      among the row's candidates (tests/test_host_cpu.py::test_argmax_filter_bound_never_drops_the_exact_argmax checks the bound in numpy);

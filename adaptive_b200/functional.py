@@ -236,7 +236,8 @@ class _DecoderPackedFn(torch.autograd.Function):
         mirror = getattr(d_packed, "_aa_bf16_mirror", None)
         d_packed, d_alpha, d_beta, d_hT, d_cT = (_f32c(x) for x in (d_packed, d_alpha, d_beta, d_hT, d_cT))
         if mirror is not None and not (mirror.shape == d_packed.shape and mirror.dtype == torch.bfloat16 and mirror.is_contiguous()
-                                       and getattr(d_packed, "_aa_bf16_mirror", None) is mirror):
+                                       and getattr(d_packed, "_aa_bf16_mirror", None) is mirror
+                                       and getattr(d_packed, "_aa_bf16_mirror_version", -1) == d_packed._version):
             mirror = None
         grads = [torch.empty_like(t) if t is not None else None for t in w]
         gs = AAWeightGrads()
@@ -364,11 +365,17 @@ class _CrossEntropyFn(torch.autograd.Function):
                                               ctypes.byref(written), _stream(logits.device)), "aa_cross_entropy_mirror")
         ctx.save_for_backward(dlog)
         ctx.dlog16 = dlog16 if written.value else None
+        ctx.consumed = False
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         (dlog,) = ctx.saved_tensors
+        if ctx.consumed:      # the saved gradient is scaled in place below: a second pass (retain_graph=True) would apply g twice
+            raise RuntimeError("adaptive_b200.cross_entropy: backward through the same loss twice is not supported "
+                               "(its gradient buffer is consumed in place); recompute the loss instead")
+        ctx.consumed = True
         # upstream gradient: a device scalar, 1 when the loss is the root (train.py:210).  dlog is this function's own buffer
         # and is consumed once, so it is scaled in place, and only when g != 1 (decided on the device: no host sync)
         g = g.to(torch.float32).contiguous()
@@ -377,6 +384,7 @@ class _CrossEntropyFn(torch.autograd.Function):
                   "aa_scale_unless_one")
         if ctx.dlog16 is not None:      # the vocabulary projection's backward contracts with the bf16 copy: hand it along
             dlog._aa_bf16_mirror = ctx.dlog16
+            dlog._aa_bf16_mirror_version = dlog._version      # an in-place edit of dlog after this point (a gradient hook) voids the mirror
         return dlog, None
 
 

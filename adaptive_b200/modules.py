@@ -2,9 +2,11 @@
 
 Same class names, constructor arguments, ``forward`` / ``sampler`` signatures, attribute
 paths and ``state_dict`` keys as ``code_src/models/adaptive_attention.py`` (+ the base
-``Decoder`` / ``Encoder2Decoder`` shells of ``baseline_attention.py``), so a reference
-checkpoint loads unchanged and ``train.py:205`` / ``tools/utils.py:171`` call sites work as
-they are.  All arithmetic of the decoder runs in ``libadaptive_sm100.so``; the modules only
+``Decoder`` / ``Encoder2Decoder`` shells of ``baseline_attention.py``), so the decoder and
+encoder-head tensors of a reference checkpoint load by key (``load_reference_state_dict`` drops the
+930 ``encoder.resnet_conv.*`` entries of the out-of-scope ResNet trunk; a plain
+``load_state_dict`` needs ``strict=False`` for the same reason) and the ``train.py:205`` /
+``tools/utils.py:171`` call sites work as they are.  All arithmetic of the decoder runs in ``libadaptive_sm100.so``; the modules only
 own the parameters.
 
 Reference quirks that are reproduced on purpose: Q1 attention dim fixed to
@@ -204,6 +206,13 @@ class Encoder2Decoder(nn.Module):
         self.encoder = AttentiveCNN(cf.adaptive_word_embed_size, cf.adaptive_lstm_hidden_size, cf)
         self.decoder = Decoder(cf.adaptive_word_embed_size, cf.vocab_length, cf.adaptive_lstm_hidden_size, cf)
         self.fused_pack = True
+
+    def load_reference_state_dict(self, state_dict):
+        """Load a ``state_dict`` saved from the reference's ``Encoder2Decoder`` (``train.py:177``): every decoder and
+        encoder-head tensor must be present and match; the ResNet-152 trunk's ``encoder.resnet_conv.*`` entries (out of scope
+        here, ``resnet_conv`` is an identity) are dropped.  Anything else unexpected or missing raises, as ``strict=True`` would."""
+        kept = {k: v for k, v in state_dict.items() if not k.startswith("encoder.resnet_conv.")}
+        return self.load_state_dict(kept, strict=True)
 
     def _encode(self, images):
         if isinstance(images, (tuple, list)):

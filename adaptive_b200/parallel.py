@@ -218,25 +218,19 @@ class BucketReducer:
         self.works = []
 
 
-_COUNT_CACHE: Dict[tuple, int] = {}
-
-
 def global_token_count(lengths: Sequence[int], group=None) -> int:
-    """Sum over ranks of this rank's packed-row count ``sum(lengths)`` (cached per lengths tuple, so
-    a steady-state training loop does no host-side collective)."""
+    """Sum over ranks of this rank's packed-row count ``sum(lengths)``: the denominator of the global mean CE.
+
+    One small host-side collective per call, entered by EVERY rank on EVERY call: the value depends on all ranks' lengths,
+    so nothing here may be cached under a rank-local key (a rank that hit such a cache would skip a collective its peers
+    enter).  A loop that cannot afford it (a captured CUDA graph) computes the count once for its frozen lengths and hands
+    it to ``DataParallelTrainer.step(..., denom=...)``, which is what ``GraphedDPStep`` does."""
     n_local = int(sum(int(x) for x in lengths))
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return n_local
-    key = (tuple(int(x) for x in lengths), id(group))
-    hit = _COUNT_CACHE.get(key)
-    if hit is None:
-        counts: List[Optional[int]] = [None] * dist.get_world_size(group)
-        dist.all_gather_object(counts, n_local, group=group)
-        hit = int(sum(counts))
-        if len(_COUNT_CACHE) > 256:
-            _COUNT_CACHE.clear()
-        _COUNT_CACHE[key] = hit
-    return hit
+    counts: List[Optional[int]] = [None] * dist.get_world_size(group)
+    dist.all_gather_object(counts, n_local, group=group)
+    return int(sum(counts))
 
 
 class DataParallelTrainer:
@@ -296,7 +290,10 @@ class DataParallelTrainer:
             self._bufs[key] = hit
         return hit
 
-    def step(self, encoded, captions: torch.Tensor, lengths: Sequence[int], targets: torch.Tensor) -> torch.Tensor:
+    def step(self, encoded, captions: torch.Tensor, lengths: Sequence[int], targets: torch.Tensor,
+             denom: Optional[int] = None) -> torch.Tensor:
+        """``denom``: the GLOBAL packed-row count if the caller already knows it (same value on every rank); by default it is
+        gathered from all ranks on every call (``global_token_count``)."""
         from . import functional as F_aa
         from ._lib import AAWeightGrads, check
 
@@ -315,7 +312,8 @@ class DataParallelTrainer:
         prec = F_aa.PRECISIONS[self.model.decoder.precision]
         row_index, _ = F_aa.cached_row_index(lengths, T, self.device)
         n_rows = row_index.numel()
-        denom = global_token_count(lengths, self.group)
+        if denom is None:
+            denom = global_token_count(lengths, self.group)
         b = self._buffers(B, T, k, H, E, Vc, a, n_rows, prec)
         d, st, P = b["d"], F_aa._stream(self.device), F_aa._ptr
         ws = F_aa.weights_struct(w)
@@ -364,6 +362,7 @@ class GraphedDPStep:
         self.trainer = trainer
         self.lengths = [int(x) for x in lengths]
         self.static = {k: example[k].clone() for k in self.KEYS}
+        self.denom = global_token_count(self.lengths, trainer.group)     # lengths are frozen: one collective, at construction
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -378,7 +377,7 @@ class GraphedDPStep:
 
     def _eager(self):
         b = self.static
-        return self.trainer.step((b["V"], b["v_g"], (b["h0"], b["c0"])), b["captions"], self.lengths, b["tgt"])
+        return self.trainer.step((b["V"], b["v_g"], (b["h0"], b["c0"])), b["captions"], self.lengths, b["tgt"], denom=self.denom)
 
     def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         from . import functional as F_aa

@@ -95,7 +95,10 @@ def _worker(rank, world, port, out):
         # loss normalisation: global packed-token count
         lengths = [5, 3, 2] if rank == 0 else [4, 4, 4, 1]
         n_glob = par.global_token_count(lengths)
-        n_glob2 = par.global_token_count(lengths)          # cached: no second collective needed
+        # second step: rank 0 sees the SAME lengths again while rank 1's batch changed (last batch of an epoch, a length-bucketed
+        # sampler): every rank must enter the collective again and get the new global count -- nothing may be cached per rank
+        lengths2 = lengths if rank == 0 else [2, 1]
+        n_glob2 = par.global_token_count(lengths2)
         # decode: every rank "decodes" its contiguous range; gathered ids are in image order
         n_img = 7
         lo, hi = par.shard_range(n_img, rank, world)
@@ -116,7 +119,7 @@ def test_reducer_count_and_gather_over_gloo_world2():
     for r in range(world):
         ok_sum, order_ok, n_glob, n_glob2, ids_ok = out[r]
         assert ok_sum and order_ok and ids_ok
-        assert n_glob == n_glob2 == 10 + 13
+        assert n_glob == 10 + 13 and n_glob2 == 10 + 3
 
 
 def test_dp_trainer_rejects_the_baseline_model_clearly():
