@@ -125,6 +125,9 @@ SIGNATURES = {
     "aa_encoder_backward": (c_int, [_ED, _EW, P, c_size_t, P, P, P, P, P, P, P, P, _EG, P, P, c_size_t, P]),
     "aa_decode_workspace_bytes": (c_size_t, [_D, c_int]),
     "aa_greedy_decode": (c_int, [_D, _W, P, P, P, P, c_int, P, P, P, P, P, c_size_t, P]),
+    "aa_decode_persistent_workspace_bytes": (c_size_t, [_D]),
+    "aa_decode_persistent_supported": (c_int, [_D]),
+    "aa_decode_persistent": (c_int, [_D, _W, P, P, P, P, c_int, P, P, P, c_int, P, P, c_size_t, P]),
     "aa_beam_decode": (c_int, [_D, _W, P, P, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
 }
 

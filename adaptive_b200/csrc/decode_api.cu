@@ -473,6 +473,42 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
   return AA_OK;
 }
 
+// ---- persistent variant (decode_persist.cu): workspace = [weight-derived region | per-call region] ----
+struct PersistWs {
+  // weight-derived (reusable across calls while the weights do not change)
+  float* Wcat; __nv_bfloat16* Wp16; float* wn;
+  // per call
+  float *P, *stat, *Acat, *c, *part1, *approx; __nv_bfloat16* u16; unsigned* bar; int* ncand;
+  int Kp, lo, ldA, ldP, ldv, ks_max;
+  size_t bytes;
+};
+
+PersistWs carve_persist(const aa_dims& d, void* base) {
+  const size_t B = d.B, H = d.H, E = d.E, K = E + H, L = d.T;
+  Carver c(base);
+  PersistWs w{};
+  w.Kp = (int)((K + 31) / 32 * 32);
+  w.lo = w.Kp;
+  w.ldA = 2 * w.lo;
+  w.ldP = (d.a + 3) / 4 * 4;
+  w.ldv = (d.Vc + 3) / 4 * 4;
+  w.ks_max = 8;
+  w.Wcat = c.take<float>((size_t)5 * H * 2 * w.Kp);
+  w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>((size_t)d.Vc * H));
+  w.wn = c.take<float>((size_t)w.ldv);
+  w.P = c.take<float>(B * d.k * w.ldP);
+  w.stat = c.take<float>(B * 5 * H);
+  w.Acat = c.take<float>(B * w.ldA);
+  w.c = c.take<float>(B * H);
+  w.part1 = c.take<float>((size_t)w.ks_max * B * 5 * H);
+  w.approx = c.take<float>(B * w.ldv);
+  w.u16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(B * H));
+  w.bar = c.take<unsigned>(64);
+  w.ncand = c.take<int>(B * L);
+  w.bytes = c.off;
+  return w;
+}
+
 }  // namespace
 }  // namespace aa
 
@@ -554,6 +590,63 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
       AA_PROF("dec_argmax", st, launch_argmax_gather(lg, Vc, B, Vc, ids_t, L, w->embed, E, ws.Acat, K, st));                // :201
     }
   }
+  return AA_OK;
+}
+
+size_t aa_decode_persistent_workspace_bytes(const aa_dims* d) {
+  if (!d) return 0;
+  return carve_persist(*d, nullptr).bytes;
+}
+
+int aa_decode_persistent_supported(const aa_dims* d) {
+  if (!d) return 0;
+  return decode_persist_supported(d->B, d->k, d->a, d->H, d->E, d->Vc) ? 1 : 0;
+}
+
+int aa_decode_persistent(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const float* h0, const float* c0,
+                         int max_len, int64_t* ids, float* attention, float* Beta, int flags, int* candidates_out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  AA_TRY(check_decode(d, w, max_len, 1));
+  AA_REQUIRE(V && v_g && ids && attention && Beta, "aa_decode_persistent: null pointer");
+  if (d->B == 0) return AA_OK;
+  if (!decode_persist_supported(d->B, d->k, d->a, d->H, d->E, d->Vc)) {
+    set_error("aa_decode_persistent: B=%d k=%d H=%d does not fit one image per SM with V resident in shared memory; use aa_greedy_decode",
+              d->B, d->k, d->H);
+    return AA_ERR_UNSUPPORTED;
+  }
+  aa_dims dd = *d;
+  dd.T = max_len;
+  const size_t need = carve_persist(dd, nullptr).bytes;
+  if (!workspace || workspace_bytes < need) {
+    set_error("aa_decode_persistent: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return AA_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  PersistWs ws = carve_persist(dd, workspace);
+  const int B = d->B, H = d->H, E = d->E, L = max_len;
+  if (!(flags & AA_DECODE_REUSE_PACKED_WEIGHTS)) {     // weight-derived operands: once per set of weights
+    pack_wcat_kernel<<<5 * H, 256, 0, st>>>(w->w_ih, w->w_hh, w->sen_wx, ws.Wcat, H, E, 1, ws.Kp, 2 * ws.Kp);
+    AA_CHECK_LAUNCH("pack_wcat");
+    AA_TRY(launch_cast2d(w->mlp_w, H, ws.Wp16, H, d->Vc, H, st));
+    AA_TRY(launch_row_norm(w->mlp_w, d->Vc, H, ws.wn, st));
+  }
+  // per call: P = V W_v^T, the static (v_g, bias) gate terms, the initial operand rows and cell state -- exact fp32
+  if (ws.ldP != d->a) AA_CHECK_CUDA(cudaMemsetAsync(ws.P, 0, sizeof(float) * (size_t)B * d->k * ws.ldP, st));
+  AA_TRY(gemm_nt(B * d->k, d->a, H, V, H, w->att_wv, H, ws.P, ws.ldP, nullptr, 0, nullptr, nullptr, st));
+  AA_TRY(gemm_nt(B, 4 * H, E, v_g, E, w->w_ih + E, 2 * E, ws.stat, 5 * H, nullptr, 0, w->b_ih, w->b_hh, st));
+  if (w->sen_wx) AA_TRY(gemm_nt(B, H, E, v_g, E, w->sen_wx + E, 2 * E, ws.stat + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
+  else AA_CHECK_CUDA(cudaMemset2DAsync(ws.stat + 4 * H, sizeof(float) * 5 * H, 0, sizeof(float) * H, (size_t)B, st));
+  AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat, 0, sizeof(float) * (size_t)B * ws.ldA, st));
+  init_state_kernel<<<B, 256, 0, st>>>(w->embed, h0, c0, ws.Acat, ws.c, H, E, 1, 1, ws.lo, ws.ldA);
+  AA_CHECK_LAUNCH("init_state");
+  DecodePersistArgs p{};
+  p.B = B; p.k = d->k; p.a = d->a; p.H = H; p.E = E; p.Vc = d->Vc; p.L = L;
+  p.K1p = ws.Kp; p.lo1 = ws.lo; p.ldA = ws.ldA; p.ldP = ws.ldP; p.ldv = ws.ldv; p.ks1_max = ws.ks_max;
+  p.V = V; p.P = ws.P; p.stat = ws.stat; p.c0 = ws.c; p.Acat = ws.Acat; p.part1 = ws.part1; p.u16 = ws.u16; p.approx = ws.approx;
+  p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh; p.Wp = w->mlp_w; p.bp = w->mlp_b; p.wn = ws.wn; p.embed = w->embed;
+  p.ids = reinterpret_cast<long long*>(ids); p.alpha = attention; p.beta = Beta; p.ncand_out = candidates_out; p.bar = ws.bar;
+  p.cbound = 2.1f / 256.f;      // bf16 first pass: see vocab_refine.cu
+  AA_PROF("dec_persistent", st, launch_decode_persist(p, ws.Wcat, ws.Wp16, st));
   return AA_OK;
 }
 

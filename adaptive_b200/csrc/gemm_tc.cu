@@ -35,8 +35,8 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 // 2-D tensor map over a row-major [rows, cols] array (cols contiguous, row stride ld elements):
-// box = {128 bytes of the contiguous dim, box_rows}, 128B swizzle, zero fill out of bounds.
-int make_map(CUtensorMap* map, const void* base, int es, long long rows, long long cols, long long ld, int box_rows) {
+// box = {swizzle_bytes (128 or 64) of the contiguous dim, box_rows}, matching swizzle, zero fill out of bounds.
+int make_map(CUtensorMap* map, const void* base, int es, long long rows, long long cols, long long ld, int box_rows, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -46,10 +46,13 @@ int make_map(CUtensorMap* map, const void* base, int es, long long rows, long lo
   AA_REQUIRE((ld * es) % 16 == 0, "tcgen05 GEMM: operand row stride must be a multiple of 16 bytes (ld=%lld, es=%d)", ld, es);
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)(ld * es)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  AA_REQUIRE(swizzle_bytes == 128 || swizzle_bytes == 64, "tcgen05 GEMM: swizzle span must be 128 or 64 bytes");
+  AA_REQUIRE(box_rows >= 1 && box_rows <= 256, "tcgen05 GEMM: TMA box rows must be in [1, 256] (got %d)", box_rows);
+  cuuint32_t box[2] = {(cuuint32_t)(swizzle_bytes / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim,
-                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld es=%d)", (int)r, rows, cols, ld, es);

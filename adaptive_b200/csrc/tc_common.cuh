@@ -7,8 +7,9 @@
 namespace aa {
 
 // 2-D TMA descriptor over a row-major [rows, cols] array (cols contiguous, row stride ld elements):
-// box = {128 bytes of the contiguous dim, box_rows}, 128B swizzle, zero fill out of bounds.  es = element size.
-int make_map(CUtensorMap* map, const void* base, int es, long long rows, long long cols, long long ld, int box_rows);
+// box = {swizzle_bytes of the contiguous dim, box_rows}, 128B (default) or 64B swizzle, zero fill out of bounds.  es = element size.
+int make_map(CUtensorMap* map, const void* base, int es, long long rows, long long cols, long long ld, int box_rows,
+             int swizzle_bytes = 128);
 
 namespace tc {
 

@@ -413,10 +413,19 @@ def cross_entropy(logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def greedy_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: int = 30, return_logits: bool = False,
-                  precision: str = "tf32x3"):
+                  precision: str = "tf32x3", engine: str = "pipeline"):
     """``Encoder2Decoder.sampler`` loop (adaptive_attention.py:186-216) on the device.
     Returns ids [B,L] int64, attention [B,L,k], Beta [B,L,1] (+ logits [L,B,Vc]).
-    ``precision``: "tf32x3" (per-step contractions on tensor cores, fp32-accurate) or "fp32" (exact SIMT)."""
+    ``precision``: "tf32x3" (per-step contractions on tensor cores, fp32-accurate) or "fp32" (exact SIMT).
+    ``engine``: "pipeline" (per-step launches, any batch), "persistent" (one cooperative launch, V resident on chip; raises if
+    the batch / shape does not fit) or "auto" (persistent when it fits and nothing else was asked for)."""
+    if engine not in ("pipeline", "persistent", "auto"):
+        raise ValueError("engine must be 'pipeline', 'persistent' or 'auto'")
+    if engine == "persistent" or (engine == "auto" and not return_logits and precision == "tf32x3" and V.shape[0] > 0
+                                  and persistent_decode_supported(w, V, v_g, max_len)):
+        if return_logits or precision != "tf32x3":
+            raise ValueError("the persistent engine returns no logits and runs the tf32x3 precision only")
+        return greedy_decode_persistent(w, V, v_g, h0, c0, max_len)
     lib = _lib.load()
     _need_cuda(V, v_g, h0, c0)
     V, v_g = _f32c(V), _f32c(v_g)
@@ -439,6 +448,60 @@ def greedy_decode(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: 
                                    _ptr(ids), _ptr(att), _ptr(bet), _ptr(logits), _ptr(wsb), nbytes, _stream(dev)),
               "aa_greedy_decode")
     return (ids, att, bet, logits) if return_logits else (ids, att, bet)
+
+
+_PERSIST_WS: Dict[tuple, tuple] = {}
+
+
+def persistent_decode_supported(w: Sequence[torch.Tensor], V, v_g, max_len: int = 30) -> bool:
+    """True when ``aa_decode_persistent`` can take this batch: at most one image per SM and V, P and the in-kernel
+    contraction stages fit in shared memory (the C ABI's ``aa_decode_persistent_supported``)."""
+    if not V.is_cuda:
+        return False
+    B, k, H = V.shape
+    d = make_dims(B, max_len, k, H, v_g.shape[1], w[0].shape[0], w[7].shape[0], _lib.PREC_TF32X3)
+    with torch.cuda.device(V.device):
+        return bool(_lib.load().aa_decode_persistent_supported(ctypes.byref(d)))
+
+
+@torch.no_grad()
+def greedy_decode_persistent(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None, max_len: int = 30, return_candidates: bool = False):
+    """The sampler loop as ONE cooperative launch with V, P and the cell state resident in shared memory (one image per SM):
+    ``aa_decode_persistent``.  Same outputs as ``greedy_decode``.  The weight-derived operands (packed gate weights, bf16
+    projection, row norms) live at the head of a cached workspace and are rebuilt only when a weight tensor changed
+    (``Tensor._version``) -- the per-call prologue is then P = V W_v^T, the static gate terms and the initial state."""
+    lib = _lib.load()
+    _need_cuda(V, v_g, h0, c0)
+    V, v_g = _f32c(V), _f32c(v_g)
+    B, k, H = V.shape
+    E = v_g.shape[1]
+    Vc, a = w[0].shape[0], w[7].shape[0]
+    _check_weights(w, H, E, Vc, a)
+    h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
+    dev = V.device
+    d = make_dims(B, max_len, k, H, E, Vc, a, _lib.PREC_TF32X3)
+    ids = torch.empty(B, max_len, device=dev, dtype=torch.int64)
+    att = torch.empty(B, max_len, k, device=dev, dtype=torch.float32)
+    bet = torch.empty(B, max_len, 1, device=dev, dtype=torch.float32)
+    cand = torch.empty(B, max_len, device=dev, dtype=torch.int32) if return_candidates else None
+    with torch.cuda.device(dev):
+        nbytes = lib.aa_decode_persistent_workspace_bytes(ctypes.byref(d))
+        key = (dev.index, B, max_len, k, H, E, Vc, a)
+        stamp = tuple((t.data_ptr(), t._version) if t is not None else None for t in w)
+        hit = _PERSIST_WS.get(key)
+        flags = 0
+        if hit is not None and hit[1] == stamp and hit[0].numel() >= nbytes and not torch.cuda.is_current_stream_capturing():
+            wsb, flags = hit[0], 1                      # AA_DECODE_REUSE_PACKED_WEIGHTS
+        else:
+            wsb = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            if not torch.cuda.is_current_stream_capturing():
+                if len(_PERSIST_WS) > 16:
+                    _PERSIST_WS.clear()
+                _PERSIST_WS[key] = (wsb, stamp)
+        ws = weights_struct(w)
+        check(lib.aa_decode_persistent(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(h0), _ptr(c0), max_len, _ptr(ids),
+                                       _ptr(att), _ptr(bet), flags, _ptr(cand), _ptr(wsb), nbytes, _stream(dev)), "aa_decode_persistent")
+    return (ids, att, bet, cand) if return_candidates else (ids, att, bet)
 
 
 @torch.no_grad()

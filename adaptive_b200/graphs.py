@@ -57,3 +57,48 @@ class GraphedTrainStep:
             p.grad = g
         self.graph.replay()
         return self.loss
+
+
+class GraphedSampler:
+    """``Encoder2Decoder.sampler`` (adaptive_attention.py:168-216) for a fixed batch shape, captured once as a CUDA graph.
+
+    ``aa_greedy_decode`` is a host loop that enqueues ~9 launches per step and never synchronises, so the whole
+    ``max_len``-step loop (prologue included) captures into one graph: one launch per batch instead of ~180, which is what
+    bounds small batches (the reference's evaluation batch is 400, ``cfg_wzn.py:84``).  ``beam >= 1`` captures
+    ``beam_sampler`` instead.  ``__call__(encoded) -> (ids, attention, Beta)`` copies the inputs into the static buffers and
+    replays; the returned tensors are the graph's static outputs (overwritten by the next call)."""
+
+    KEYS = ("V", "v_g", "h0", "c0")
+
+    def __init__(self, model, example: Dict[str, torch.Tensor], max_len: int = 30, beam: int = 0, warmup: int = 2):
+        self.model, self.max_len, self.beam = model, int(max_len), int(beam)
+        self.static = {k: example[k].clone() for k in self.KEYS}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._eager()
+
+    def _eager(self):
+        b = self.static
+        enc = (b["V"], b["v_g"], (b["h0"], b["c0"]))
+        if self.beam >= 1:
+            return self.model.beam_sampler(enc, beam=self.beam, max_len=self.max_len)
+        return self.model.sampler(enc, max_len=self.max_len)
+
+    def __call__(self, encoded):
+        if isinstance(encoded, dict):
+            src = [encoded[k] for k in self.KEYS]
+        else:
+            V, v_g, (h0, c0) = encoded
+            src = [V, v_g, h0, c0]
+        src = [s.reshape(d.shape) for s, d in zip(src, (self.static[k] for k in self.KEYS))]
+        F_aa.copy_multi([self.static[k] for k in self.KEYS], src)
+        self.graph.replay()
+        return self.out

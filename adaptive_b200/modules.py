@@ -17,6 +17,7 @@ stops at <end>.  Quirks that are *repaired*: Q9 (``sampler`` works for B > 1) an
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -143,6 +144,9 @@ class Decoder(nn.Module):
         self.precision = getattr(cf, "precision", "fp32") if cf is not None else "fp32"
         # decoding: "tf32x3" = per-step contractions on tensor cores (fp32-accurate 3xTF32), "fp32" = exact SIMT
         self.decode_precision = getattr(cf, "decode_precision", "tf32x3") if cf is not None else "tf32x3"
+        # greedy engine: "auto" = the persistent kernel (one cooperative launch, V resident in shared memory) for batches of at most one
+        # image per SM, the per-step pipeline otherwise; "pipeline" / "persistent" force one
+        self.decode_engine = getattr(cf, "decode_engine", None) or os.environ.get("AA_DECODE_ENGINE", "auto")
 
     def weights(self):
         return self.adaptive._weights13(self.embed, self.LSTM)
@@ -237,7 +241,8 @@ class Encoder2Decoder(nn.Module):
         """Greedy search -> sampled_ids [B,max_len], attention [B,max_len,k], Beta [B,max_len,1]."""
         V, v_g, states = self._encode(images)
         h0, c0 = states if states is not None else (None, None)
-        return F_aa.greedy_decode(self.decoder.weights(), V, v_g, h0, c0, max_len, precision=self.decoder.decode_precision)
+        return F_aa.greedy_decode(self.decoder.weights(), V, v_g, h0, c0, max_len, precision=self.decoder.decode_precision,
+                                  engine=self.decoder.decode_engine)
 
     def beam_sampler(self, images, beam=3, max_len=20):
         """Beam search (extension; the reference only has a TODO for it, `for_wzn:3`)."""

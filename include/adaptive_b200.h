@@ -344,6 +344,23 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
                      const float* c0, int max_len, int64_t* ids, float* attention, float* Beta, float* logits_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Persistent-kernel variant of the greedy sampler (same loop, adaptive_attention.py:186-216; same outputs as aa_greedy_decode)
+ * for batches of at most ONE IMAGE PER SM: the whole max_len-step loop is one cooperative launch; each image's V, P = V W_v^T
+ * and LSTM cell state stay in the shared memory of the SM that owns it for all steps (24 130 instead of
+ * 128 588 algorithmic bytes per image and step), the gate and vocabulary contractions run on tcgen05 inside the kernel
+ * (fp32-accurate 3xTF32 gates; bf16 first pass + exact fp32 recomputation of every column that can hold the row maximum), four
+ * grid barriers per step replace the per-step launches.  aa_decode_persistent_supported: 1 if d->B (<= SM count) and the shape
+ * fit the residency limits on the current device, else 0 -- callers fall back to aa_greedy_decode (aa_decode_persistent itself
+ * returns AA_ERR_UNSUPPORTED then).  flags: AA_DECODE_REUSE_PACKED_WEIGHTS = the weight-derived operands at the head of
+ * `workspace` (packed gate weights, bf16 projection, row norms) were written by an earlier call with the same weights, dims and
+ * workspace and are not rebuilt.  candidates_out (optional, int32 [B,max_len]): columns recomputed exactly per row and step. */
+#define AA_DECODE_REUSE_PACKED_WEIGHTS 1
+size_t aa_decode_persistent_workspace_bytes(const aa_dims* d);   /* d->T = max_len */
+int aa_decode_persistent_supported(const aa_dims* d);
+int aa_decode_persistent(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const float* h0,
+                         const float* c0, int max_len, int64_t* ids, float* attention, float* Beta, int flags,
+                         int* candidates_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Beam search (NOT in the reference; definition in SURVEY section 8c / oracle.beam_decode):
  * returns the best hypothesis per image: ids [B,max_len], attention [B,max_len,k], Beta [B,max_len],
  * score [B] (cumulative log-prob). */

@@ -88,7 +88,7 @@ def train_step_fn(dims, B: int, T: int, lengths: Sequence[int], device="cpu", se
             packed = pack_padded_sequence(scores, lengths, batch_first=True)
             loss = crit(packed.data.float(), tgt)
             loss.backward()
-        return float(loss) if ncuda == 0 else loss
+        return float(loss.detach()) if ncuda == 0 else loss.detach()
 
     return step
 
