@@ -229,6 +229,24 @@ int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const floa
                                void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
                                aa_grad_ready_fn on_ready, void* user);
 
+/* Sum all-reduce of one gradient bucket over the GPUs of one NVSwitch box, written against peer-mapped ("symmetric") memory
+ * instead of NCCL (the exchange step of data-parallel training).  Every rank holds one allocation of identical
+ * size, mapped into every peer: peer_bufs[p] (HOST array of `world` device pointers) is rank p's allocation as seen from this
+ * device, peer_bufs[rank] the local one; multicast_buf is the NVLS multicast mapping of the same allocation or NULL.  The bucket
+ * is elements [offset_elems, offset_elems + n_elems) of the allocation viewed as float (both multiples of 4), reduced IN PLACE on
+ * every rank.  flag_offset_bytes: start of aa_allreduce_flag_bytes() bytes inside the allocation, zero-filled once at allocation,
+ * that the kernels use for their cross-GPU flags.  channel in [0, AA_AR_CHANNELS): collectives that may be in flight at the
+ * same time must use different channels.  Every rank must make the same sequence of calls; the call is asynchronous on
+ * `stream`, capturable into a CUDA graph, and uses at most max_blocks (<= AA_AR_MAX_BLOCKS; 0 = default) CTAs.
+ * With multicast_buf: one multimem.ld_reduce + one multimem.st per 16 bytes of this rank's 1/world slice (the switch adds);
+ * without: two-shot over peer loads, summed in rank order (deterministic). */
+#define AA_AR_MAX_WORLD 8
+#define AA_AR_MAX_BLOCKS 32
+#define AA_AR_CHANNELS 4
+size_t aa_allreduce_flag_bytes(void);
+int aa_allreduce_sum_f32(void* const* peer_bufs, void* multicast_buf, long long flag_offset_bytes, int rank, int world,
+                         long long offset_elems, long long n_elems, int channel, int max_blocks, void* stream);
+
 /* ---- optimizer step next to the path --------------------------------------------------------------
  * clip_grad_norm_(model.decoder.LSTM.parameters(), clip_max_norm) (train.py:213-214) followed by torch.optim.Adam's update
  * (model_factory.py:69-77; defaults of the reference: lr 1e-3, betas 0.8 / 0.999, eps 1e-8, weight_decay 0) over up to
