@@ -476,37 +476,50 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
 // ---- persistent variant (decode_persist.cu): workspace = [weight-derived region | per-call region] ----
 struct PersistWs {
   // weight-derived (reusable across calls while the weights do not change)
-  float* Wcat; __nv_bfloat16* Wp16; float* wn;
+  float* Whh; __nv_bfloat16* Wp16; float* wn; float* EG;
   // per call
-  float *P, *stat, *Acat, *c, *part1, *approx; __nv_bfloat16* u16; unsigned* bar; int* ncand;
-  int Kp, lo, ldA, ldP, ldv, ks_max;
+  float *P, *stat, *hA, *c, *part1, *approx; __nv_bfloat16* u16; unsigned* bar;
+  int Kp, ldA, ldP, ldv, ks_max;
   size_t bytes;
 };
 
 PersistWs carve_persist(const aa_dims& d, void* base) {
-  const size_t B = d.B, H = d.H, E = d.E, K = E + H, L = d.T;
+  const size_t B = d.B, H = d.H;
   Carver c(base);
   PersistWs w{};
-  w.Kp = (int)((K + 31) / 32 * 32);
-  w.lo = w.Kp;
-  w.ldA = 2 * w.lo;
+  w.Kp = (int)((H + 31) / 32 * 32);
+  w.ldA = 2 * w.Kp;
   w.ldP = (d.a + 3) / 4 * 4;
   w.ldv = (d.Vc + 3) / 4 * 4;
   w.ks_max = 8;
-  w.Wcat = c.take<float>((size_t)5 * H * 2 * w.Kp);
+  w.Whh = c.take<float>((size_t)4 * H * 2 * w.Kp);
   w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>((size_t)d.Vc * H));
   w.wn = c.take<float>((size_t)w.ldv);
+  w.EG = c.take<float>((size_t)d.Vc * 5 * H);
   w.P = c.take<float>(B * d.k * w.ldP);
   w.stat = c.take<float>(B * 5 * H);
-  w.Acat = c.take<float>(B * w.ldA);
+  w.hA = c.take<float>(B * w.ldA);
   w.c = c.take<float>(B * H);
-  w.part1 = c.take<float>((size_t)w.ks_max * B * 5 * H);
+  w.part1 = c.take<float>((size_t)w.ks_max * B * 4 * H);
   w.approx = c.take<float>(B * w.ldv);
   w.u16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(B * H));
   w.bar = c.take<unsigned>(64);
-  w.ncand = c.take<int>(B * L);
   w.bytes = c.off;
   return w;
+}
+
+// hA[r] = tf32 (hi | lo) of h0[r] (zeros without an initial state; pad columns zero), c[r] = c0[r]
+__global__ void persist_init_kernel(const float* __restrict__ h0, const float* __restrict__ c0, float* __restrict__ hA, float* __restrict__ c,
+                                    int H, int Kp) {
+  const int r = blockIdx.x;
+  float* row = hA + (long long)r * 2 * Kp;
+  for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+    float hi = 0.f, lo = 0.f;
+    if (i < H && h0) split_tf32(h0[(long long)r * H + i], hi, lo);
+    row[i] = hi;
+    row[Kp + i] = lo;
+  }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) c[(long long)r * H + i] = c0 ? c0[(long long)r * H + i] : 0.f;
 }
 
 }  // namespace
@@ -625,10 +638,13 @@ int aa_decode_persistent(const aa_dims* d, const aa_weights* w, const float* V, 
   PersistWs ws = carve_persist(dd, workspace);
   const int B = d->B, H = d->H, E = d->E, L = max_len;
   if (!(flags & AA_DECODE_REUSE_PACKED_WEIGHTS)) {     // weight-derived operands: once per set of weights
-    pack_wcat_kernel<<<5 * H, 256, 0, st>>>(w->w_ih, w->w_hh, w->sen_wx, ws.Wcat, H, E, 1, ws.Kp, 2 * ws.Kp);
-    AA_CHECK_LAUNCH("pack_wcat");
+    AA_TRY(launch_split_tf32(w->w_hh, H, 4 * H, H, ws.Whh, ws.Kp, st));
     AA_TRY(launch_cast2d(w->mlp_w, H, ws.Wp16, H, d->Vc, H, st));
     AA_TRY(launch_row_norm(w->mlp_w, d->Vc, H, ws.wn, st));
+    // EG[v] = [W_ih[:, :E]; W_x[:, :E]] emb(v): the input half of the five gate blocks for every word, exact fp32
+    AA_TRY(gemm_nt(d->Vc, 4 * H, E, w->embed, E, w->w_ih, 2 * E, ws.EG, 5 * H, nullptr, 0, nullptr, nullptr, st));
+    if (w->sen_wx) AA_TRY(gemm_nt(d->Vc, H, E, w->embed, E, w->sen_wx, 2 * E, ws.EG + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
+    else AA_CHECK_CUDA(cudaMemset2DAsync(ws.EG + 4 * H, sizeof(float) * 5 * H, 0, sizeof(float) * H, (size_t)d->Vc, st));
   }
   // per call: P = V W_v^T, the static (v_g, bias) gate terms, the initial operand rows and cell state -- exact fp32
   if (ws.ldP != d->a) AA_CHECK_CUDA(cudaMemsetAsync(ws.P, 0, sizeof(float) * (size_t)B * d->k * ws.ldP, st));
@@ -636,17 +652,16 @@ int aa_decode_persistent(const aa_dims* d, const aa_weights* w, const float* V, 
   AA_TRY(gemm_nt(B, 4 * H, E, v_g, E, w->w_ih + E, 2 * E, ws.stat, 5 * H, nullptr, 0, w->b_ih, w->b_hh, st));
   if (w->sen_wx) AA_TRY(gemm_nt(B, H, E, v_g, E, w->sen_wx + E, 2 * E, ws.stat + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
   else AA_CHECK_CUDA(cudaMemset2DAsync(ws.stat + 4 * H, sizeof(float) * 5 * H, 0, sizeof(float) * H, (size_t)B, st));
-  AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat, 0, sizeof(float) * (size_t)B * ws.ldA, st));
-  init_state_kernel<<<B, 256, 0, st>>>(w->embed, h0, c0, ws.Acat, ws.c, H, E, 1, 1, ws.lo, ws.ldA);
-  AA_CHECK_LAUNCH("init_state");
+  persist_init_kernel<<<B, 256, 0, st>>>(h0, c0, ws.hA, ws.c, H, ws.Kp);
+  AA_CHECK_LAUNCH("persist_init");
   DecodePersistArgs p{};
   p.B = B; p.k = d->k; p.a = d->a; p.H = H; p.E = E; p.Vc = d->Vc; p.L = L;
-  p.K1p = ws.Kp; p.lo1 = ws.lo; p.ldA = ws.ldA; p.ldP = ws.ldP; p.ldv = ws.ldv; p.ks1_max = ws.ks_max;
-  p.V = V; p.P = ws.P; p.stat = ws.stat; p.c0 = ws.c; p.Acat = ws.Acat; p.part1 = ws.part1; p.u16 = ws.u16; p.approx = ws.approx;
-  p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh; p.Wp = w->mlp_w; p.bp = w->mlp_b; p.wn = ws.wn; p.embed = w->embed;
+  p.K1p = ws.Kp; p.lo1 = ws.Kp; p.ldA = ws.ldA; p.ldP = ws.ldP; p.ldv = ws.ldv; p.ks1_max = ws.ks_max; p.start_id = START_ID;
+  p.V = V; p.P = ws.P; p.stat = ws.stat; p.c0 = ws.c; p.EG = ws.EG; p.hA = ws.hA; p.part1 = ws.part1; p.u16 = ws.u16; p.approx = ws.approx;
+  p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh; p.Wp = w->mlp_w; p.bp = w->mlp_b; p.wn = ws.wn;
   p.ids = reinterpret_cast<long long*>(ids); p.alpha = attention; p.beta = Beta; p.ncand_out = candidates_out; p.bar = ws.bar;
   p.cbound = 2.1f / 256.f;      // bf16 first pass: see vocab_refine.cu
-  AA_PROF("dec_persistent", st, launch_decode_persist(p, ws.Wcat, ws.Wp16, st));
+  AA_PROF("dec_persistent", st, launch_decode_persist(p, ws.Whh, ws.Wp16, st));
   return AA_OK;
 }
 

@@ -236,16 +236,18 @@ int launch_decode_atten(const DecodeAttenArgs& p, cudaStream_t s);
 // ---- decode_persist.cu: the whole greedy loop in one cooperative launch, one image per SM, V / P / c resident on chip ----
 struct DecodePersistArgs {
   int B, NB, k, a, H, E, Vc, L;     // NB: batch padded to the MMA's N (filled by the launcher)
-  int K1p, lo1, ldA;                // G1: padded K of Wcat's halves, column of Acat's lo half, Acat row stride (floats)
+  int K1p, lo1, ldA;                // G1: padded K of W_hh's halves (= column of hA's lo half), hA row stride (floats)
   int ldP, ldv;                     // row strides of P and of the approximate logits
   int nkb1, ks1, kbper1, ks1_max, nkb2;   // tiling (filled by the launcher; ks1_max = K ranges the partial buffer has room for)
-  const float *V, *P, *stat, *c0;   // [B,k,H], [B,k,ldP], [B,5H] static gate terms, [B,H] (null = zeros)
-  float* Acat;                      // [B, ldA] operand rows [emb | h] as tf32 (hi | lo); initialised with <start> and h0
-  float* part1;                     // [ks1_max, B, 5H] K-split partials of G1
+  int start_id;                     // <start> token (adaptive_attention.py:188)
+  const float *V, *P, *stat, *c0;   // [B,k,H], [B,k,ldP], [B,5H] static gate terms (v_g half + biases), [B,H] (null = zeros)
+  const float* EG;                  // [Vc,5H] input-half gate table: embed . [W_ih[:, :E]; W_x[:, :E]]^T
+  float* hA;                        // [B, ldA] G1's operand rows: h as tf32 (hi | lo); initialised with h0
+  float* part1;                     // [ks1_max, B, 4H] K-split partials of G1
   __nv_bfloat16* u16;               // [B, H] bf16 mirror of u (G2's operand)
   float* approx;                    // [B, ldv] approximate logits (bias included)
   const float *Wg, *Ws, *wh;        // attention weights (Ws == null: baseline model, beta = 0)
-  const float *Wp, *bp, *wn, *embed;   // vocabulary projection (fp32), its bias, its row norms, the embedding table
+  const float *Wp, *bp, *wn;        // vocabulary projection (fp32), its bias, its row norms
   long long* ids; float* alpha; float* beta;   // [B,L], [B,L,k], [B,L]
   int* ncand_out;                   // optional [B,L]: columns recomputed exactly (diagnostics)
   unsigned* bar;                    // grid barrier counter
@@ -254,6 +256,6 @@ struct DecodePersistArgs {
 bool decode_persist_supported(int B, int k, int a, int H, int E, int Vc);
 int decode_persist_nb(int B);
 int launch_row_norm(const float* W, int rows, int cols, float* wn, cudaStream_t s);
-int launch_decode_persist(const DecodePersistArgs& p, const float* Wcat_split, const __nv_bfloat16* Wp16, cudaStream_t s);
+int launch_decode_persist(const DecodePersistArgs& p, const float* Whh_split, const __nv_bfloat16* Wp16, cudaStream_t s);
 
 }  // namespace aa

@@ -105,6 +105,80 @@ def sharded_sampler(model, encoded, max_len: int = 30, beam: int = 0, gather: bo
 # ---------------------------------------------------------------------------------------------
 # gradient buckets + reducer (training)
 # ---------------------------------------------------------------------------------------------
+class SymmetricBuffer:
+    """One fp32 allocation per rank of identical size, mapped into every peer of the group (and, where the fabric supports it,
+    behind one NVLS multicast address): the memory the hand-written all-reduce kernels (``csrc/allreduce.cu``) work on.
+    The mappings come from ``torch.distributed._symmetric_memory`` (cuMem allocation + handle exchange: plumbing); the tail of
+    the allocation holds the kernels' cross-GPU flags, zero-filled once here."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("peer-memory all-reduce is built for one NVSwitch box (<= 8 ranks)")
+        flag_floats = int(lib.aa_allreduce_flag_bytes()) // 4
+        self.n = (int(n_floats) + 63) // 64 * 64
+        self.flag_offset_bytes = self.n * 4
+        self.buf = symm.empty(self.n + flag_floats, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = getattr(self.handle, "multicast_ptr", 0) or 0
+        self.multicast_ptr = int(mc) if os.environ.get("AA_AR_MULTICAST", "1") != "0" else 0
+        self._peer_arr = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
+        self.lib = lib
+        self.max_blocks = int(os.environ.get("AA_AR_BLOCKS", "32"))
+        dist.barrier(self.group)          # every rank's flags are zero before anyone signals
+
+    @property
+    def payload(self) -> torch.Tensor:
+        return self.buf[: self.n]
+
+    def all_reduce_(self, view: torch.Tensor, channel: int, stream=None):
+        """In-place sum over the ranks of ``view`` (a contiguous slice of ``payload`` starting on a 4-element boundary),
+        asynchronous on ``stream`` (default: the current one)."""
+        from ._lib import check
+
+        off = (view.data_ptr() - self.buf.data_ptr()) // 4
+        n = (view.numel() + 3) // 4 * 4
+        if off % 4 or off < 0 or off + n > self.n:
+            raise ValueError("all_reduce_: view must be a 16-byte aligned slice of the symmetric payload")
+        st = stream if stream is not None else torch.cuda.current_stream(self.buf.device)
+        with torch.cuda.device(self.buf.device):
+            check(self.lib.aa_allreduce_sum_f32(self._peer_arr, ctypes.c_void_p(self.multicast_ptr) if self.multicast_ptr else None,
+                                                self.flag_offset_bytes, self.rank, self.world, off, n, channel, self.max_blocks,
+                                                ctypes.c_void_p(st.cuda_stream)), "aa_allreduce_sum_f32")
+
+    def link_bytes(self, n_floats: int) -> int:
+        """NVLink bytes one GPU sends (= receives) for one all-reduce of ``n_floats``: its (W-1)/W share of the bucket once for
+        the reduction and once for the broadcast."""
+        return int(2 * 4 * n_floats * (self.world - 1) / self.world)
+
+
+def try_symmetric_buffer(n_floats: int, device, group=None) -> Optional["SymmetricBuffer"]:
+    """``SymmetricBuffer`` if every rank of the group can build one (same answer on all ranks), else None (NCCL is used)."""
+    if not dist.is_initialized() or dist.get_world_size(group) < 2 or os.environ.get("AA_DP_P2P", "1") == "0":
+        return None
+    sb, ok = None, 1.0
+    try:
+        sb = SymmetricBuffer(n_floats, device, group)
+    except Exception as e:      # no symmetric-memory support in this build / container / fabric
+        import sys
+
+        sys.stderr.write("adaptive_b200.parallel: symmetric memory unavailable on rank %d (%s: %s); using NCCL\n"
+                         % (dist.get_rank(group), type(e).__name__, str(e)[:300]))
+        ok = 0.0
+    flag = torch.tensor([ok], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return sb if float(flag.item()) > 0 else None
+
+
 class GradBuckets:
     """One flat fp32 buffer per bucket with a view per parameter (``aa_weights`` field order).
 
@@ -113,8 +187,9 @@ class GradBuckets:
     then one contiguous range, ``tail``, and go through one collective instead of three -- each NCCL all-reduce of the
     captured step costs ~45 us whatever its size (``profiles/r01_v47_timeline_n2.txt``)."""
 
-    def __init__(self, shapes: Dict[str, Sequence[int]], device, dtype=torch.float32):
+    def __init__(self, shapes: Dict[str, Sequence[int]], device, dtype=torch.float32, symmetric_group=None, want_symmetric: bool = False):
         self.flat: List[torch.Tensor] = []
+        self.symm: Optional[SymmetricBuffer] = None
         self.views: Dict[str, torch.Tensor] = {}
         layout, total = [], 0
         for fields in BUCKETS:
@@ -125,7 +200,12 @@ class GradBuckets:
                 offs.append(total)
                 total += (n + 63) // 64 * 64
             layout.append((fields, sizes, offs, start, total))
-        self.all = torch.zeros(total + 64, device=device, dtype=dtype)
+        if want_symmetric and dtype == torch.float32:
+            self.symm = try_symmetric_buffer(total + 64, device, symmetric_group)
+        if self.symm is not None:
+            self.all = self.symm.payload[: total + 64]        # gradients are written straight into peer-mapped memory
+        else:
+            self.all = torch.zeros(total + 64, device=device, dtype=dtype)
         for fields, sizes, offs, start, end in layout:
             self.flat.append(self.all[start:end])
             for f, o, n in zip(fields, offs, sizes):
@@ -173,9 +253,17 @@ class BucketReducer:
     def start(self):
         self.works, self.order = [], []
         self._deferred: List[int] = []
+        self.bytes_reduced = 0
 
     def _all_reduce(self, flat: torch.Tensor, buckets: Sequence[int]):
-        if self.cuda:
+        self.bytes_reduced += flat.numel() * flat.element_size()
+        if self.cuda and self.buckets.symm is not None:
+            # hand-written all-reduce over peer-mapped memory (csrc/allreduce.cu), one channel per bucket
+            with torch.cuda.stream(self.comm_stream):
+                for b in buckets:
+                    self.comm_stream.wait_event(self.events[b])
+                self.buckets.symm.all_reduce_(flat, channel=buckets[0], stream=self.comm_stream)
+        elif self.cuda:
             with torch.cuda.stream(self.comm_stream):
                 for b in buckets:
                     self.comm_stream.wait_event(self.events[b])
@@ -258,7 +346,10 @@ class DataParallelTrainer:
         if dev.type != "cuda":
             raise RuntimeError("DataParallelTrainer needs the decoder on a CUDA device (no CPU fallback)")
         self.device = dev
-        self.buckets = GradBuckets({f: tuple(t.shape) for f, t in zip(WEIGHT_FIELDS, self.weights)}, dev)
+        self.buckets = GradBuckets({f: tuple(t.shape) for f, t in zip(WEIGHT_FIELDS, self.weights)}, dev, symmetric_group=group,
+                                   want_symmetric=self.world > 1)
+        self.engine = "peer-memory kernels (%s)" % ("NVLS multimem" if self.buckets.symm.multicast_ptr else "two-shot peer loads") \
+            if self.buckets.symm is not None else ("nccl" if self.world > 1 else "none")
         self.reducer = BucketReducer(self.buckets, group)
         for p, g in zip(self.weights, self.buckets.ordered()):
             p.grad = g

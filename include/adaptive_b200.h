@@ -241,7 +241,7 @@ int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const floa
  * With multicast_buf: one multimem.ld_reduce + one multimem.st per 16 bytes of this rank's 1/world slice (the switch adds);
  * without: two-shot over peer loads, summed in rank order (deterministic). */
 #define AA_AR_MAX_WORLD 8
-#define AA_AR_MAX_BLOCKS 32
+#define AA_AR_MAX_BLOCKS 64
 #define AA_AR_CHANNELS 4
 size_t aa_allreduce_flag_bytes(void);
 int aa_allreduce_sum_f32(void* const* peer_bufs, void* multicast_buf, long long flag_offset_bytes, int rank, int world,
