@@ -83,6 +83,7 @@ SIGNATURES = {
     "aa_profile_get": (c_int, [c_int, ctypes.c_char_p, c_int, POINTER(ctypes.c_double), POINTER(c_int)]),
     "aa_debug_set_trace_buffer": (c_int, [P]),
     "aa_debug_set_decode_atten_simple": (c_int, [c_int]),
+    "aa_debug_set_persist_trace": (c_int, [P]),
     "aa_debug_set_atten_sequential": (c_int, [c_int]),
     "aa_debug_set_decode_argmax_refine": (c_int, [c_int]),
     "aa_debug_refine_pairs": (ctypes.c_longlong, [c_int]),

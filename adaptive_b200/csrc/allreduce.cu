@@ -19,12 +19,14 @@
 // The number of barriers a CTA has been through lives next to the counter (device memory, touched only by that CTA), so the
 // kernels can be captured into a CUDA graph and replayed: no host-side epoch.  CTA b of every rank only ever talks to CTA b of
 // its peers; the grid (<= AA_AR_MAX_BLOCKS CTAs, far below the SM count) is co-resident by construction.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace aa {
 namespace {
 
-constexpr int AR_THREADS = 512;
+constexpr int AR_THREADS = 512;      // upper bound; the launch picks blockDim.x (AA_AR_THREADS)
 constexpr int AR_UNROLL = 8;
 constexpr int AR_SLOTS = AA_AR_CHANNELS * AA_AR_MAX_BLOCKS;      // flag words: [AR_SLOTS] arrival counters, then [AR_SLOTS] local barrier counts
 
@@ -37,9 +39,9 @@ struct ArArgs {
   int rank, world, slot_base;            // slot_base = channel * AA_AR_MAX_BLOCKS
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -60,10 +62,15 @@ __device__ __forceinline__ void ar_barrier(const ArArgs& a) {
     }
     const unsigned target = e * (unsigned)a.world;
     long long t0 = 0;
-    while ((int)(ld_acquire_sys(mine + slot) - target) < 0) {
+    // relaxed polls with a pause in between, ONE acquire fence at the end: an acquire per poll is a system-scope fence per
+    // iteration on an SM that the backward's kernels share with this CTA (measured: the BPTT kernel next to 32 such pollers
+    // took 112 us instead of 58, profiles/r02_timeline_n8_v1.txt)
+    while ((int)(ld_relaxed_sys(mine + slot) - target) < 0) {
+      __nanosleep(100);
       if (t0 == 0) t0 = clock64();
       else if (clock64() - t0 > 4000000000ll) __trap();      // a peer that never arrives must fault, not hang the GPU
     }
+    __threadfence_system();
   }
   __syncthreads();
 }
@@ -85,8 +92,8 @@ __global__ void __launch_bounds__(AR_THREADS) ar_multimem_kernel(const ArArgs a)
   const long long per = (n4 + W - 1) / W;             // float4 groups per rank slice
   const long long lo = per * r, hi = min(n4, lo + per);
   float* mc = a.mc + a.off;
-  const long long stride = (long long)gridDim.x * AR_THREADS;
-  long long i = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + (AR_UNROLL - 1) * stride < hi; i += AR_UNROLL * stride) {      // AR_UNROLL independent 16-byte reductions in flight per thread
     float4 v[AR_UNROLL];
 #pragma unroll
@@ -104,10 +111,10 @@ __global__ void __launch_bounds__(AR_THREADS) ar_twoshot_kernel(const ArArgs a) 
   const long long n4 = a.n / 4;
   const long long per = (n4 + W - 1) / W;
   const long long lo = per * r, hi = min(n4, lo + per);
-  const long long stride = (long long)gridDim.x * AR_THREADS;
+  const long long stride = (long long)gridDim.x * blockDim.x;
   float* mine = a.bufs[r] + a.off;
   // reduce-scatter: slice r = sum over ranks in rank order (the same order on every replay: deterministic)
-  for (long long i = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i < hi; i += stride) {
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
     float4 v[AA_AR_MAX_WORLD];
 #pragma unroll
     for (int p = 0; p < AA_AR_MAX_WORLD; ++p)
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(AR_THREADS) ar_twoshot_kernel(const ArArgs a) 
     const int p = (r + s) % W;
     const long long plo = per * p, phi = min(n4, plo + per);
     const float4* src = reinterpret_cast<const float4*>(a.bufs[p] + a.off);
-    long long i = plo + (long long)blockIdx.x * AR_THREADS + threadIdx.x;
+    long long i = plo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < phi; i += 4 * stride) {
       const float4 v0 = __ldcg(src + i), v1 = __ldcg(src + i + stride), v2 = __ldcg(src + i + 2 * stride), v3 = __ldcg(src + i + 3 * stride);
       reinterpret_cast<float4*>(mine)[i] = v0;
@@ -171,8 +178,13 @@ int aa_allreduce_sum_f32(void* const* peer_bufs, void* multicast_buf, long long 
   if (blocks < 1) blocks = 1;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a.mc) ar_multimem_kernel<<<blocks, AR_THREADS, 0, st>>>(a);
-  else ar_twoshot_kernel<<<blocks, AR_THREADS, 0, st>>>(a);
+  static const int threads = [] {
+    const char* e = getenv("AA_AR_THREADS");
+    const int t = e ? atoi(e) : 256;
+    return (t >= 32 && t <= AR_THREADS && t % 32 == 0) ? t : 256;
+  }();
+  if (a.mc) ar_multimem_kernel<<<blocks, threads, 0, st>>>(a);
+  else ar_twoshot_kernel<<<blocks, threads, 0, st>>>(a);
   AA_CHECK_LAUNCH("allreduce");
   return AA_OK;
 }

@@ -606,6 +606,8 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
   return AA_OK;
 }
 
+int aa_debug_set_persist_trace(void* dev_ptr) { return set_persist_trace_buffer(dev_ptr); }
+
 size_t aa_decode_persistent_workspace_bytes(const aa_dims* d) {
   if (!d) return 0;
   return carve_persist(*d, nullptr).bytes;

@@ -51,6 +51,18 @@ __device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {
   return d;
 }
 
+// optional per-step timeline of CTA 0 (aa_debug_set_persist_trace): 8 x uint64 globaltimer stamps per step --
+//   0 contraction phase entered   1 this CTA's units done   2 grid barrier passed   3 arg-max done (word known)
+//   4 next step's owner work done (u written)   5 second grid barrier passed
+__device__ unsigned long long* g_pd_trace = nullptr;
+__device__ __forceinline__ void pd_trace(int step, int ev) {
+  if (g_pd_trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_pd_trace[step * 8 + ev] = t;
+  }
+}
+
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ void pd_grid_wait(const unsigned* counter, unsigned target) {
@@ -271,7 +283,7 @@ dec_persist_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
                    const __grid_constant__ CUtensorMap tmB2, const DecodePersistArgs p) {
   extern __shared__ uint8_t pd_raw[];
   uint8_t* base = pd_raw + ((1024u - (smem_u32(pd_raw) & 1023u)) & 1023u);
-  const int k = p.k, a = p.a, H = p.H, E = p.E, NB = p.NB, B = p.B;
+  const int k = p.k, a = p.a, H = p.H, NB = p.NB, B = p.B;
   const int M1 = 4 * H, G5 = 5 * H;
   const uint32_t stage_bytes = PD_A_BYTES + (uint32_t)NB * 128u;
   PdSmem sm;
@@ -588,14 +600,21 @@ dec_persist_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   for (int t = 0; t < p.L; ++t) {
     // [ G2(t): approximate logits of u_t | G1(t+1): recurrent gate terms of h_t ]
     ph.g2 = true; ph.g1 = t + 1 < p.L;
+    pd_trace(t, 0);
     pd_gemm_phase(sm, p, ph, &tmA1, &tmB1, &tmA2, &tmB2, tmem_base, it, lt);
+    __syncthreads();
+    pd_trace(t, 1);
     pd_grid_sync(p.bar, epoch);
+    pd_trace(t, 2);
     // [ O2(t): the word | O1(t+1): the next step up to u ]
     if (owner) {
       const int word = owner_argmax(t);
+      pd_trace(t, 3);
       if (t + 1 < p.L) owner_step(t + 1, word);
+      pd_trace(t, 4);
     }
     if (t + 1 < p.L) pd_grid_sync(p.bar, epoch);
+    pd_trace(t, 5);
   }
 
   tc_fence_before();
@@ -640,6 +659,12 @@ bool decode_persist_supported(int B, int k, int a, int H, int E, int Vc) {
   const size_t ring = (size_t)PD_STAGES * (PD_A_BYTES + (size_t)NB * 128);
   (void)Vc;
   return scratch <= ring;
+}
+
+int set_persist_trace_buffer(void* dev_ptr) {
+  unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+  AA_CHECK_CUDA(cudaMemcpyToSymbol(g_pd_trace, &p, sizeof(p)));
+  return AA_OK;
 }
 
 int launch_row_norm(const float* W, int rows, int cols, float* wn, cudaStream_t st) {

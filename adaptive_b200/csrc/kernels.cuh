@@ -256,6 +256,7 @@ struct DecodePersistArgs {
 bool decode_persist_supported(int B, int k, int a, int H, int E, int Vc);
 int decode_persist_nb(int B);
 int launch_row_norm(const float* W, int rows, int cols, float* wn, cudaStream_t s);
+int set_persist_trace_buffer(void* dev_ptr);   // diagnostics: [steps][8] uint64 globaltimer stamps of CTA 0; null = off
 int launch_decode_persist(const DecodePersistArgs& p, const float* Whh_split, const __nv_bfloat16* Wp16, cudaStream_t s);
 
 }  // namespace aa

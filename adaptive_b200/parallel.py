@@ -133,7 +133,7 @@ class SymmetricBuffer:
         self.multicast_ptr = int(mc) if os.environ.get("AA_AR_MULTICAST", "1") != "0" else 0
         self._peer_arr = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
         self.lib = lib
-        self.max_blocks = int(os.environ.get("AA_AR_BLOCKS", "32"))
+        self.max_blocks = int(os.environ.get("AA_AR_BLOCKS", "8"))
         dist.barrier(self.group)          # every rank's flags are zero before anyone signals
 
     @property

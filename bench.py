@@ -580,7 +580,7 @@ def dp_check(torch, dist, dev, model, dims, world, rank):
                 l1 = F_aa.cross_entropy(packed.data, gt)
                 l1.backward()
                 torch.cuda.synchronize()
-                ref_loss = float(l1)
+                ref_loss = float(l1.detach())
                 for name, p, g in zip(WEIGHT_FIELDS, params, dp_grads):
                     err = float((p.grad - g).abs().max() / p.grad.abs().max().clamp_min(1e-30))
                     if err > worst:
@@ -1037,8 +1037,10 @@ def run_ours(args):
         "ms_per_step": train_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": workload_config(n_gpus),
         "cuda_graph": bool(stepper is not None),
-        **({"dp": "4 gradient buckets, NCCL sum all-reduce %s the backward (%s launches)" %
-            ("overlapped with" if args.overlap else "after", dp_mode)} if world > 1 else {}),
+        **({"dp": "4 gradient buckets, sum all-reduce by %s, %s the backward (%s launches)" %
+            (trainer.engine, "overlapped with" if args.overlap else "after", dp_mode),
+            "dp_env": {k: os.environ.get(k) for k in ("AA_AR_BLOCKS", "AA_AR_THREADS", "AA_DP_P2P", "AA_AR_MULTICAST", "AA_DP_TAIL_BUCKETS") if os.environ.get(k)}}
+           if world > 1 else {}),
         "timing": spread,
         "tokens_per_step": {"positions_B_x_T": TRAIN_B * TRAIN_T, "packed_rows_sum_lengths": n_real,
                             "value_over_packed_rows": n_real * n_gpus / (train_ms * 1e-3),

@@ -105,6 +105,9 @@ int aa_profile_get(int i, char* name, int name_len, double* total_ms, int* launc
 /* Diagnostics: device buffer [steps][8] of uint64 %globaltimer stamps written by CTA (0,0) of the persistent
  * LSTM kernels (see lstm_seq.cu); NULL switches tracing off. */
 int aa_debug_set_trace_buffer(void* dev_ptr);
+/* Diagnostics: device buffer [max_len][8] of uint64 %globaltimer stamps written by CTA 0 of the persistent decoder
+ * (decode_persist.cu lists the events); NULL switches tracing off. */
+int aa_debug_set_persist_trace(void* dev_ptr);
 /* Diagnostics: on != 0 makes the tensor-core decode pipeline use the register-staged attention kernel instead of the
  * bulk-copy (cp.async.bulk + mbarrier ring) one; both compute the same step (tests compare them). */
 int aa_debug_set_decode_atten_simple(int on);
