@@ -113,6 +113,8 @@ SIGNATURES = {
                                            c_size_t, P, POINTER(c_void_p), c_void_p, c_void_p, P]),
     "aa_allreduce_flag_bytes": (c_size_t, []),
     "aa_allreduce_sum_f32": (c_int, [POINTER(c_void_p), P, ctypes.c_longlong, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, P]),
+    "aa_allreduce_sum_bf16": (c_int, [POINTER(c_void_p), P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, ctypes.c_longlong,
+                                      ctypes.c_longlong, c_int, c_int, P]),
     "aa_clip_adam_step": (c_int, [P, c_int, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                   ctypes.c_float, c_int, P, P, P]),
     "aa_pack_rows": (c_int, [P, c_int64, P, c_int64, P, P]),

@@ -21,6 +21,8 @@
 // its peers; the grid (<= AA_AR_MAX_BLOCKS CTAs, far below the SM count) is co-resident by construction.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace aa {
@@ -144,6 +146,112 @@ __global__ void __launch_bounds__(AR_THREADS) ar_twoshot_kernel(const ArArgs a) 
   ar_barrier(a);                                      // nobody still reads a slice its owner is about to overwrite
 }
 
+// ---- bf16 exchange: the bucket travels as bf16 (half the NVLink bytes), the switch accumulates in fp32 ----
+struct uint4x { unsigned x, y, z, w; };
+__device__ __forceinline__ uint4x mm_ld_reduce_bf16(const void* p) {
+  uint4x v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st_bf16(void* p, const uint4x& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// a.off / a.n count 16-byte groups (8 bf16) of the staging region here; a.mc / a.bufs point at the allocation's base
+__global__ void __launch_bounds__(AR_THREADS) ar_multimem_bf16_kernel(const ArArgs a) {
+  const int W = a.world, r = a.rank;
+  ar_barrier(a);
+  const long long n4 = a.n;
+  const long long per = (n4 + W - 1) / W;
+  const long long lo = per * r, hi = min(n4, lo + per);
+  uint4* mc = reinterpret_cast<uint4*>(a.mc) + a.off;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (AR_UNROLL - 1) * stride < hi; i += AR_UNROLL * stride) {
+    uint4x v[AR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u) v[u] = mm_ld_reduce_bf16(mc + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL; ++u) mm_st_bf16(mc + i + u * stride, v[u]);
+  }
+  for (; i < hi; i += stride) mm_st_bf16(mc + i, mm_ld_reduce_bf16(mc + i));
+  ar_barrier(a);
+}
+
+__device__ __forceinline__ void bf16x8_accum(float (&acc)[8], const uint4& v) {
+  const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    acc[2 * j] += __uint_as_float(w[j] << 16);
+    acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(AR_THREADS) ar_twoshot_bf16_kernel(const ArArgs a) {
+  const int W = a.world, r = a.rank;
+  ar_barrier(a);
+  const long long n4 = a.n;
+  const long long per = (n4 + W - 1) / W;
+  const long long lo = per * r, hi = min(n4, lo + per);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  uint4* mine = reinterpret_cast<uint4*>(a.bufs[r]) + a.off;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < W; ++p) bf16x8_accum(acc, __ldcg(reinterpret_cast<const uint4*>(a.bufs[p]) + a.off + i));
+    uint4 o;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(acc[0], acc[1]); o.x = *reinterpret_cast<unsigned*>(&t);
+    t = __floats2bfloat162_rn(acc[2], acc[3]); o.y = *reinterpret_cast<unsigned*>(&t);
+    t = __floats2bfloat162_rn(acc[4], acc[5]); o.z = *reinterpret_cast<unsigned*>(&t);
+    t = __floats2bfloat162_rn(acc[6], acc[7]); o.w = *reinterpret_cast<unsigned*>(&t);
+    mine[i] = o;
+  }
+  ar_barrier(a);
+  for (int s = 1; s < W; ++s) {
+    const int p = (r + s) % W;
+    const long long plo = per * p, phi = min(n4, plo + per);
+    const uint4* src = reinterpret_cast<const uint4*>(a.bufs[p]) + a.off;
+    for (long long i = plo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < phi; i += stride) mine[i] = __ldcg(src + i);
+  }
+  ar_barrier(a);
+}
+
+// fp32 -> bf16 (round to nearest even) and back, 8 elements per thread and iteration
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    uint4 o;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(a.x, a.y); o.x = *reinterpret_cast<unsigned*>(&t);
+    t = __floats2bfloat162_rn(a.z, a.w); o.y = *reinterpret_cast<unsigned*>(&t);
+    t = __floats2bfloat162_rn(b.x, b.y); o.z = *reinterpret_cast<unsigned*>(&t);
+    t = __floats2bfloat162_rn(b.z, b.w); o.w = *reinterpret_cast<unsigned*>(&t);
+    dst[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const uint4* __restrict__ src, float* __restrict__ dst, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldcg(src + i);
+    float4 a, b;
+    a.x = __uint_as_float(v.x << 16); a.y = __uint_as_float(v.x & 0xffff0000u);
+    a.z = __uint_as_float(v.y << 16); a.w = __uint_as_float(v.y & 0xffff0000u);
+    b.x = __uint_as_float(v.z << 16); b.y = __uint_as_float(v.z & 0xffff0000u);
+    b.z = __uint_as_float(v.w << 16); b.w = __uint_as_float(v.w & 0xffff0000u);
+    reinterpret_cast<float4*>(dst)[2 * i] = a;
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = b;
+  }
+}
+
+int ar_threads() {
+  static const int threads = [] {
+    const char* e = getenv("AA_AR_THREADS");
+    const int t = e ? atoi(e) : 256;
+    return (t >= 32 && t <= AR_THREADS && t % 32 == 0) ? t : 256;
+  }();
+  return threads;
+}
+
 }  // namespace
 }  // namespace aa
 
@@ -178,14 +286,51 @@ int aa_allreduce_sum_f32(void* const* peer_bufs, void* multicast_buf, long long 
   if (blocks < 1) blocks = 1;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int threads = [] {
-    const char* e = getenv("AA_AR_THREADS");
-    const int t = e ? atoi(e) : 256;
-    return (t >= 32 && t <= AR_THREADS && t % 32 == 0) ? t : 256;
-  }();
+  const int threads = ar_threads();
   if (a.mc) ar_multimem_kernel<<<blocks, threads, 0, st>>>(a);
   else ar_twoshot_kernel<<<blocks, threads, 0, st>>>(a);
   AA_CHECK_LAUNCH("allreduce");
+  return AA_OK;
+}
+
+// bf16 variant: fp32 bucket [offset_elems, +n_elems) of the allocation -> cast into the bf16 staging region that starts
+// stage_offset_bytes into the allocation (same element index) -> summed over the ranks as bf16 with fp32 accumulation (in the
+// switch with multicast, in registers without) -> cast back into the fp32 bucket.  n_elems and offset_elems multiples of 8.
+int aa_allreduce_sum_bf16(void* const* peer_bufs, void* multicast_buf, long long flag_offset_bytes, long long stage_offset_bytes, int rank,
+                          int world, long long offset_elems, long long n_elems, int channel, int max_blocks, void* stream) {
+  AA_REQUIRE(peer_bufs && world >= 2 && world <= AA_AR_MAX_WORLD && rank >= 0 && rank < world, "aa_allreduce_sum_bf16: bad rank / world (%d / %d)", rank, world);
+  AA_REQUIRE(channel >= 0 && channel < AA_AR_CHANNELS, "aa_allreduce_sum_bf16: channel must be in [0, %d)", AA_AR_CHANNELS);
+  AA_REQUIRE(offset_elems % 8 == 0 && n_elems % 8 == 0 && n_elems >= 0 && flag_offset_bytes % 16 == 0 && stage_offset_bytes % 16 == 0,
+             "aa_allreduce_sum_bf16: offset and length must be multiples of 8 elements");
+  if (n_elems == 0) return AA_OK;
+  ArArgs a{};
+  for (int p = 0; p < world; ++p) {
+    AA_REQUIRE(peer_bufs[p], "aa_allreduce_sum_bf16: null peer mapping %d", p);
+    a.bufs[p] = reinterpret_cast<float*>(static_cast<char*>(peer_bufs[p]) + stage_offset_bytes);      // base of the bf16 staging region
+    a.flags[p] = reinterpret_cast<unsigned*>(static_cast<char*>(peer_bufs[p]) + flag_offset_bytes);
+  }
+  a.mc = multicast_buf ? reinterpret_cast<float*>(static_cast<char*>(multicast_buf) + stage_offset_bytes) : nullptr;
+  a.mc_flags = multicast_buf ? reinterpret_cast<unsigned*>(static_cast<char*>(multicast_buf) + flag_offset_bytes) : nullptr;
+  a.off = offset_elems / 8; a.n = n_elems / 8; a.rank = rank; a.world = world;
+  a.slot_base = channel * AA_AR_MAX_BLOCKS;
+  const long long slice_bytes = (n_elems * 2 + world - 1) / world;
+  int blocks = (int)((slice_bytes + 65535) / 65536);
+  const int cap = max_blocks > 0 && max_blocks < AA_AR_MAX_BLOCKS ? max_blocks : AA_AR_MAX_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* grads = static_cast<float*>(peer_bufs[rank]) + offset_elems;
+  uint4* stage = reinterpret_cast<uint4*>(static_cast<char*>(peer_bufs[rank]) + stage_offset_bytes) + offset_elems / 8;
+  const long long n8 = n_elems / 8;
+  const int cgrid = (int)std::min<long long>((n8 + 255) / 256, 4LL * num_sms());
+  cast_f32_bf16_kernel<<<cgrid, 256, 0, st>>>(grads, stage, n8);
+  AA_CHECK_LAUNCH("cast_f32_bf16");
+  const int threads = ar_threads();
+  if (a.mc) ar_multimem_bf16_kernel<<<blocks, threads, 0, st>>>(a);
+  else ar_twoshot_bf16_kernel<<<blocks, threads, 0, st>>>(a);
+  AA_CHECK_LAUNCH("allreduce_bf16");
+  cast_bf16_f32_kernel<<<cgrid, 256, 0, st>>>(stage, grads, n8);
+  AA_CHECK_LAUNCH("cast_bf16_f32");
   return AA_OK;
 }
 

@@ -123,8 +123,10 @@ class SymmetricBuffer:
             raise RuntimeError("peer-memory all-reduce is built for one NVSwitch box (<= 8 ranks)")
         flag_floats = int(lib.aa_allreduce_flag_bytes()) // 4
         self.n = (int(n_floats) + 63) // 64 * 64
-        self.flag_offset_bytes = self.n * 4
-        self.buf = symm.empty(self.n + flag_floats, dtype=torch.float32, device=device)
+        # layout: [fp32 payload (n) | bf16 staging of the payload (n/2 floats) | flags]
+        self.stage_offset_bytes = self.n * 4
+        self.flag_offset_bytes = self.n * 4 + self.n * 2
+        self.buf = symm.empty(self.n + self.n // 2 + flag_floats, dtype=torch.float32, device=device)
         self.buf.zero_()
         torch.cuda.synchronize(device)
         self.handle = symm.rendezvous(self.buf, self.group)
@@ -140,25 +142,31 @@ class SymmetricBuffer:
     def payload(self) -> torch.Tensor:
         return self.buf[: self.n]
 
-    def all_reduce_(self, view: torch.Tensor, channel: int, stream=None):
-        """In-place sum over the ranks of ``view`` (a contiguous slice of ``payload`` starting on a 4-element boundary),
-        asynchronous on ``stream`` (default: the current one)."""
+    def all_reduce_(self, view: torch.Tensor, channel: int, stream=None, bf16: bool = False):
+        """In-place sum over the ranks of ``view`` (a contiguous slice of ``payload`` starting on a 32-byte boundary),
+        asynchronous on ``stream`` (default: the current one).  ``bf16``: the bucket crosses NVLink as bf16 (fp32 accumulation),
+        half the bytes -- the exchange of the mixed-precision training path."""
         from ._lib import check
 
         off = (view.data_ptr() - self.buf.data_ptr()) // 4
-        n = (view.numel() + 3) // 4 * 4
-        if off % 4 or off < 0 or off + n > self.n:
-            raise ValueError("all_reduce_: view must be a 16-byte aligned slice of the symmetric payload")
+        n = (view.numel() + 7) // 8 * 8
+        if off % 8 or off < 0 or off + n > self.n:
+            raise ValueError("all_reduce_: view must be a 32-byte aligned slice of the symmetric payload")
         st = stream if stream is not None else torch.cuda.current_stream(self.buf.device)
+        mc = ctypes.c_void_p(self.multicast_ptr) if self.multicast_ptr else None
         with torch.cuda.device(self.buf.device):
-            check(self.lib.aa_allreduce_sum_f32(self._peer_arr, ctypes.c_void_p(self.multicast_ptr) if self.multicast_ptr else None,
-                                                self.flag_offset_bytes, self.rank, self.world, off, n, channel, self.max_blocks,
-                                                ctypes.c_void_p(st.cuda_stream)), "aa_allreduce_sum_f32")
+            if bf16:
+                check(self.lib.aa_allreduce_sum_bf16(self._peer_arr, mc, self.flag_offset_bytes, self.stage_offset_bytes, self.rank,
+                                                     self.world, off, n, channel, self.max_blocks, ctypes.c_void_p(st.cuda_stream)),
+                      "aa_allreduce_sum_bf16")
+            else:
+                check(self.lib.aa_allreduce_sum_f32(self._peer_arr, mc, self.flag_offset_bytes, self.rank, self.world, off, n, channel,
+                                                    self.max_blocks, ctypes.c_void_p(st.cuda_stream)), "aa_allreduce_sum_f32")
 
-    def link_bytes(self, n_floats: int) -> int:
-        """NVLink bytes one GPU sends (= receives) for one all-reduce of ``n_floats``: its (W-1)/W share of the bucket once for
+    def link_bytes(self, n_elems: int, elem_bytes: int = 4) -> int:
+        """NVLink bytes one GPU sends (= receives) for one all-reduce of ``n_elems``: its (W-1)/W share of the bucket once for
         the reduction and once for the broadcast."""
-        return int(2 * 4 * n_floats * (self.world - 1) / self.world)
+        return int(2 * elem_bytes * n_elems * (self.world - 1) / self.world)
 
 
 def try_symmetric_buffer(n_floats: int, device, group=None) -> Optional["SymmetricBuffer"]:
@@ -213,6 +221,8 @@ class GradBuckets:
         self.loss = self.all[total:total + 1].view(())           # summed over ranks together with ``tail``
         self.tail_first = max(0, len(BUCKETS) - int(os.environ.get("AA_DP_TAIL_BUCKETS", "2")))   # first bucket of the merged range
         self.tail = self.all[layout[self.tail_first][3]:total + 64]
+        self.tail_grads = self.all[layout[self.tail_first][3]:total]       # the same range without the loss slot
+        self.loss_slot = self.all[total:total + 64]
 
     def ordered(self) -> Tuple[torch.Tensor, ...]:
         return tuple(self.views[f] for f in WEIGHT_FIELDS)
@@ -229,14 +239,19 @@ class BucketReducer:
     bucket), so it overlaps the remaining backward kernels; ``finish`` makes the caller's
     current stream wait for all of them.  On CPU (gloo) it degenerates to async all-reduces."""
 
-    def __init__(self, buckets: GradBuckets, group=None, average: bool = False):
+    def __init__(self, buckets: GradBuckets, group=None, average: bool = False, bf16_exchange: bool = False):
         self.buckets, self.group, self.average = buckets, group, average
+        self.bf16_exchange = bool(bf16_exchange) and buckets.symm is not None
+        self.bytes_reduced = 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = buckets.flat[0].is_cuda
         self.works: List = []
         self.order: List[int] = []
         if self.cuda:
             self.comm_stream = torch.cuda.Stream(device=buckets.flat[0].device)
+            # the small attention / sentinel bucket gets a lane of its own: behind the 20 MB vocabulary bucket on ONE lane it waited
+            # ~50 us for a 25 us exchange (profiles/r02_timeline_n8_v2.txt)
+            self.comm_stream2 = torch.cuda.Stream(device=buckets.flat[0].device)
             self.events = [torch.cuda.Event() for _ in BUCKETS]
             for e in self.events:      # the raw cudaEvent_t exists only after a first record
                 e.record()
@@ -254,15 +269,18 @@ class BucketReducer:
         self.works, self.order = [], []
         self._deferred: List[int] = []
         self.bytes_reduced = 0
+        self._lanes_used = set()
 
     def _all_reduce(self, flat: torch.Tensor, buckets: Sequence[int]):
-        self.bytes_reduced += flat.numel() * flat.element_size()
+        self.bytes_reduced += flat.numel() * (2 if self.bf16_exchange else flat.element_size())
         if self.cuda and self.buckets.symm is not None:
             # hand-written all-reduce over peer-mapped memory (csrc/allreduce.cu), one channel per bucket
-            with torch.cuda.stream(self.comm_stream):
+            lane = self.comm_stream2 if tuple(buckets) == (1,) else self.comm_stream
+            self._lanes_used.add(lane)
+            with torch.cuda.stream(lane):
                 for b in buckets:
-                    self.comm_stream.wait_event(self.events[b])
-                self.buckets.symm.all_reduce_(flat, channel=buckets[0], stream=self.comm_stream)
+                    lane.wait_event(self.events[b])
+                self.buckets.symm.all_reduce_(flat, channel=buckets[0], stream=lane, bf16=self.bf16_exchange)
         elif self.cuda:
             with torch.cuda.stream(self.comm_stream):
                 for b in buckets:
@@ -281,9 +299,22 @@ class BucketReducer:
             self._deferred.append(bucket)
         elif bucket == last and self._deferred == list(range(tf, last)):
             self._deferred = []
-            self._all_reduce(self.buckets.tail, tuple(range(tf, last + 1)))
+            # (bf16 exchange: the loss scalar must not be rounded -- it went through reduce_loss() in fp32 right after the loss kernel)
+            self._all_reduce(self.buckets.tail_grads if self.bf16_exchange else self.buckets.tail, tuple(range(tf, last + 1)))
         else:
             self._all_reduce(self.buckets.flat[bucket], (bucket,))
+
+    def reduce_loss(self, ready_event=None):
+        """bf16 exchange only: sum the loss scalar over the ranks in fp32 on the second lane, as soon as the loss kernel is done
+        (long before the backward ends: fully hidden)."""
+        if not (self.bf16_exchange and self.world > 1):
+            return
+        lane = self.comm_stream2
+        self._lanes_used.add(lane)
+        with torch.cuda.stream(lane):
+            if ready_event is not None:
+                lane.wait_event(ready_event)
+            self.buckets.symm.all_reduce_(self.buckets.loss_slot, channel=3, stream=lane, bf16=False)
 
     def finish(self):
         for b in getattr(self, "_deferred", []):       # (a deferred bucket whose partner never came)
@@ -297,6 +328,9 @@ class BucketReducer:
                     for flat in self.buckets.flat:
                         flat.div_(self.world)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+            for lane in getattr(self, "_lanes_used", ()):
+                if lane is not self.comm_stream:
+                    torch.cuda.current_stream().wait_stream(lane)
         else:
             for w in self.works:
                 w.wait()
@@ -348,14 +382,18 @@ class DataParallelTrainer:
         self.device = dev
         self.buckets = GradBuckets({f: tuple(t.shape) for f, t in zip(WEIGHT_FIELDS, self.weights)}, dev, symmetric_group=group,
                                    want_symmetric=self.world > 1)
-        self.engine = "peer-memory kernels (%s)" % ("NVLS multimem" if self.buckets.symm.multicast_ptr else "two-shot peer loads") \
+        self.engine = "peer-memory kernels (%s, %s on the wire)" % ("NVLS multimem" if self.buckets.symm.multicast_ptr else "two-shot peer loads",
+                                                                     "bf16" if self.reducer.bf16_exchange else "fp32") \
             if self.buckets.symm is not None else ("nccl" if self.world > 1 else "none")
-        self.reducer = BucketReducer(self.buckets, group)
+        # the mixed-precision path exchanges its gradients as bf16 (fp32 accumulation); the exact path keeps fp32 on the wire
+        want16 = os.environ.get("AA_DP_BF16", "1") != "0" and getattr(model.decoder, "precision", "fp32") == "bf16"
+        self.reducer = BucketReducer(self.buckets, group, bf16_exchange=want16)
         for p, g in zip(self.weights, self.buckets.ordered()):
             p.grad = g
         self._cb_type = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)
         self._cb = self._cb_type(lambda bucket, _user: self.reducer.on_ready(int(bucket)))
         self._bufs: Dict[tuple, dict] = {}
+        self._loss_ready = torch.cuda.Event()
 
     def _buffers(self, B, T, k, H, E, Vc, a, n_rows, prec):
         from . import functional as F_aa
@@ -420,6 +458,9 @@ class DataParallelTrainer:
             check(lib.aa_cross_entropy_mirror(P(b["packed"]), n_rows, Vc, P(targets), denom, P(b["loss"]), P(b["dpacked"]), P(b["dpacked16"]),
                                               ctypes.byref(written), st), "aa_cross_entropy_mirror")
             self.reducer.start()
+            if self.reducer.bf16_exchange and self.world > 1:
+                self._loss_ready.record(torch.cuda.current_stream(self.device))
+                self.reducer.reduce_loss(self._loss_ready)
             hooked = self.overlap and self.world > 1
             check(lib.aa_decoder_backward_packed(
                 ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(b["alpha"]), P(b["beta"]), P(b["saved"]),

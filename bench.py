@@ -793,7 +793,7 @@ def run_ours(args):
 
     stage("building the stepper (graph=%d)" % args.graph)
     dp_mode = None
-    if world == 1:
+    if world == 1 and not args.dp_path:
         stepper = GraphedTrainStep(model, devb[0], lengths) if args.graph else None
 
         def train_step(b):
@@ -819,7 +819,8 @@ def run_ours(args):
                 sys.stderr.write("rank %d: CUDA-graph capture of the data-parallel step failed (%s); running eagerly\n" % (rank, e))
                 ok.zero_()
                 stepper = None
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if float(ok.item()) < 1:
                 stepper = None
             dp_mode = "graph" if stepper is not None else "eager"
@@ -1040,7 +1041,7 @@ def run_ours(args):
         **({"dp": "4 gradient buckets, sum all-reduce by %s, %s the backward (%s launches)" %
             (trainer.engine, "overlapped with" if args.overlap else "after", dp_mode),
             "dp_env": {k: os.environ.get(k) for k in ("AA_AR_BLOCKS", "AA_AR_THREADS", "AA_DP_P2P", "AA_AR_MULTICAST", "AA_DP_TAIL_BUCKETS") if os.environ.get(k)}}
-           if world > 1 else {}),
+           if dp_mode is not None else {}),
         "timing": spread,
         "tokens_per_step": {"positions_B_x_T": TRAIN_B * TRAIN_T, "packed_rows_sum_lengths": n_real,
                             "value_over_packed_rows": n_real * n_gpus / (train_ms * 1e-3),
@@ -1135,6 +1136,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, help="N>1: start each gradient bucket's all-reduce as soon as the backward finishes it")
     ap.add_argument("--blocks", type=int, default=0, help="timed blocks of --steps steps (0 = enough for >= 50 blocks and >= 1 s)")
     ap.add_argument("--quick", action="store_true", help="headline + decode only: skip the eager-GPU reference arm, small-batch decode, beam, config 5, widened rows")
+    ap.add_argument("--dp-path", action="store_true", help="N=1: run the data-parallel trainer's code path (no collectives) instead of the autograd one")
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 section")
     ap.add_argument("--no-widened", action="store_true", help="skip the extra measurements of the SURVEY 8f rows (N=1 only)")
     args = ap.parse_args()

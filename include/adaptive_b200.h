@@ -249,6 +249,14 @@ int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const floa
 size_t aa_allreduce_flag_bytes(void);
 int aa_allreduce_sum_f32(void* const* peer_bufs, void* multicast_buf, long long flag_offset_bytes, int rank, int world,
                          long long offset_elems, long long n_elems, int channel, int max_blocks, void* stream);
+/* Same reduction with the bucket travelling as bf16 (half the NVLink bytes; the mixed-precision training path): three launches
+ * on `stream` -- the fp32 bucket is rounded into a bf16 staging region of the same allocation (stage_offset_bytes from its
+ * start, indexed like the fp32 payload), summed over the ranks with fp32 accumulation (multimem.ld_reduce ... acc::f32 in the
+ * switch, or registers without multicast), and the bf16 sum is widened back into the fp32 bucket.  Every rank ends with the
+ * same values; they differ from the fp32 exchange by two bf16 roundings (<= 2^-8 relative each).  Multiples of 8 elements. */
+int aa_allreduce_sum_bf16(void* const* peer_bufs, void* multicast_buf, long long flag_offset_bytes, long long stage_offset_bytes,
+                          int rank, int world, long long offset_elems, long long n_elems, int channel, int max_blocks,
+                          void* stream);
 
 /* ---- optimizer step next to the path --------------------------------------------------------------
  * clip_grad_norm_(model.decoder.LSTM.parameters(), clip_max_norm) (train.py:213-214) followed by torch.optim.Adam's update

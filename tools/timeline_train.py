@@ -40,7 +40,7 @@ lengths = make_lengths(B, T, seed=1234)
 inp = make_inputs(dims, B, T, seed=1234)
 b = {k: torch.from_numpy(v).to(dev) for k, v in inp.items()}
 b["tgt"] = torch.from_numpy(np.ascontiguousarray(F_aa.packed_targets(inp["captions"], lengths))).to(dev)
-if world > 1:
+if world > 1 or os.environ.get('AA_TIMELINE_DP_PATH') == '1':
     from adaptive_b200.parallel import DataParallelTrainer, GraphedDPStep
     step = GraphedDPStep(DataParallelTrainer(model, overlap=True), b, lengths)
 else:
