@@ -905,6 +905,9 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   }
   if (dh0 && !seq) AA_TRY(launch_copy2d(dh0, H, sc.dh_rec, H, B, H, st));
   if (dc0 && !seq) AA_TRY(launch_copy2d(dc0, H, sc.dc_rec, H, B, H, st));
+  // the recurrence (the latency-critical kernel of the backward) is enqueued: a caller that wants its gradient exchange to stay
+  // off the SMs / memory system while it runs starts the exchange on this event instead of on the buckets' own
+  AA_TRY(bucket_ready(AA_EVENT_BPTT_DONE, st));
   // LSTM parameter gradients, batched over all steps: one lane each
   const Mat dG = M2(sc.dgates, 4 * H, sc.dgates16, 4 * H);
   AA_TRY(to_side());

@@ -40,6 +40,8 @@ BUCKETS: Tuple[Tuple[str, ...], ...] = (
     ("embed",),
 )
 BUCKET_OF: Dict[str, int] = {f: b for b, fs in enumerate(BUCKETS) for f in fs}
+EVENT_BPTT_DONE = len(BUCKETS)        # AA_EVENT_BPTT_DONE: index of the "recurrence enqueued" event / callback
+N_READY_EVENTS = len(BUCKETS) + 1     # AA_NUM_READY_EVENTS
 assert sorted(BUCKET_OF) == sorted(WEIGHT_FIELDS)
 
 
@@ -252,15 +254,18 @@ class BucketReducer:
             # the small attention / sentinel bucket gets a lane of its own: behind the 20 MB vocabulary bucket on ONE lane it waited
             # ~50 us for a 25 us exchange (profiles/r02_timeline_n8_v2.txt)
             self.comm_stream2 = torch.cuda.Stream(device=buckets.flat[0].device)
-            self.events = [torch.cuda.Event() for _ in BUCKETS]
+            self.events = [torch.cuda.Event() for _ in range(N_READY_EVENTS)]      # four buckets + "recurrence enqueued"
             for e in self.events:      # the raw cudaEvent_t exists only after a first record
                 e.record()
         else:
-            self.comm_stream, self.events = None, [None] * len(BUCKETS)
+            self.comm_stream, self.events = None, [None] * N_READY_EVENTS
+        # peer-memory engine: the first exchange (vocabulary + attention buckets, one launch) starts when the backward's recurrence
+        # has finished instead of next to it; "bucket" = start every bucket's exchange as soon as it is final
+        self.schedule = os.environ.get("AA_DP_SCHEDULE", "after_bptt" if (self.cuda and buckets.symm is not None) else "bucket")
 
     def event_handles(self):
-        """``void* ready_events[AA_NUM_BUCKETS]`` for ``aa_decoder_backward_hooked`` (CUDA only)."""
-        arr = (ctypes.c_void_p * len(BUCKETS))()
+        """``void* ready_events[AA_NUM_READY_EVENTS]`` for ``aa_decoder_backward_hooked`` (CUDA only)."""
+        arr = (ctypes.c_void_p * N_READY_EVENTS)()
         for i, e in enumerate(self.events):
             arr[i] = e.cuda_event
         return arr
@@ -268,19 +273,21 @@ class BucketReducer:
     def start(self):
         self.works, self.order = [], []
         self._deferred: List[int] = []
+        self._early: List[int] = []
         self.bytes_reduced = 0
         self._lanes_used = set()
 
-    def _all_reduce(self, flat: torch.Tensor, buckets: Sequence[int]):
+    def _all_reduce(self, flat: torch.Tensor, buckets: Sequence[int], lane=None):
         self.bytes_reduced += flat.numel() * (2 if self.bf16_exchange else flat.element_size())
         if self.cuda and self.buckets.symm is not None:
             # hand-written all-reduce over peer-mapped memory (csrc/allreduce.cu), one channel per bucket
-            lane = self.comm_stream2 if tuple(buckets) == (1,) else self.comm_stream
+            if lane is None:
+                lane = self.comm_stream2 if tuple(buckets) == (1,) else self.comm_stream
             self._lanes_used.add(lane)
             with torch.cuda.stream(lane):
                 for b in buckets:
                     lane.wait_event(self.events[b])
-                self.buckets.symm.all_reduce_(flat, channel=buckets[0], stream=lane, bf16=self.bf16_exchange)
+                self.buckets.symm.all_reduce_(flat, channel=min(buckets[0], 3), stream=lane, bf16=self.bf16_exchange)
         elif self.cuda:
             with torch.cuda.stream(self.comm_stream):
                 for b in buckets:
@@ -290,8 +297,21 @@ class BucketReducer:
             self.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def on_ready(self, bucket: int):
+        if bucket == EVENT_BPTT_DONE:
+            if self.world > 1 and self.schedule == "after_bptt" and self._early:
+                # buckets 0..1 are contiguous in the allocation: one exchange, started when the recurrence is done
+                first, last_b = min(self._early), max(self._early)
+                lo = self.buckets.flat[first].data_ptr()
+                hi = self.buckets.flat[last_b].data_ptr() + self.buckets.flat[last_b].numel() * 4
+                span = self.buckets.all[(lo - self.buckets.all.data_ptr()) // 4:(hi - self.buckets.all.data_ptr()) // 4]
+                early, self._early = tuple(self._early) + (EVENT_BPTT_DONE,), []
+                self._all_reduce(span, early, lane=self.comm_stream)
+            return
         self.order.append(bucket)
         if self.world == 1:
+            return
+        if self.schedule == "after_bptt" and self.cuda and self.buckets.symm is not None and bucket < self.buckets.tail_first:
+            self._early.append(bucket)
             return
         last = len(BUCKETS) - 1
         tf = self.buckets.tail_first
@@ -317,9 +337,9 @@ class BucketReducer:
             self.buckets.symm.all_reduce_(self.buckets.loss_slot, channel=3, stream=lane, bf16=False)
 
     def finish(self):
-        for b in getattr(self, "_deferred", []):       # (a deferred bucket whose partner never came)
+        for b in getattr(self, "_early", []) + getattr(self, "_deferred", []):       # (deferred buckets whose trigger never came)
             self._all_reduce(self.buckets.flat[b], (b,))
-        self._deferred = []
+        self._deferred, self._early = [], []
         if self.cuda and self.world > 1:
             with torch.cuda.stream(self.comm_stream):
                 for w in self.works:
@@ -382,12 +402,12 @@ class DataParallelTrainer:
         self.device = dev
         self.buckets = GradBuckets({f: tuple(t.shape) for f, t in zip(WEIGHT_FIELDS, self.weights)}, dev, symmetric_group=group,
                                    want_symmetric=self.world > 1)
-        self.engine = "peer-memory kernels (%s, %s on the wire)" % ("NVLS multimem" if self.buckets.symm.multicast_ptr else "two-shot peer loads",
-                                                                     "bf16" if self.reducer.bf16_exchange else "fp32") \
-            if self.buckets.symm is not None else ("nccl" if self.world > 1 else "none")
         # the mixed-precision path exchanges its gradients as bf16 (fp32 accumulation); the exact path keeps fp32 on the wire
         want16 = os.environ.get("AA_DP_BF16", "1") != "0" and getattr(model.decoder, "precision", "fp32") == "bf16"
         self.reducer = BucketReducer(self.buckets, group, bf16_exchange=want16)
+        self.engine = "peer-memory kernels (%s, %s on the wire)" % ("NVLS multimem" if self.buckets.symm.multicast_ptr else "two-shot peer loads",
+                                                                     "bf16" if self.reducer.bf16_exchange else "fp32") \
+            if self.buckets.symm is not None else ("nccl" if self.world > 1 else "none")
         for p, g in zip(self.weights, self.buckets.ordered()):
             p.grad = g
         self._cb_type = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)
@@ -469,10 +489,18 @@ class DataParallelTrainer:
                 b["scratch"].numel(), st, self.reducer.event_handles() if hooked else None,
                 ctypes.cast(self._cb, ctypes.c_void_p) if hooked else None, None, P(b["dpacked16"]) if written.value else None),
                 "aa_decoder_backward_packed")
-            if self.world > 1 and not hooked:          # non-overlapped variant: same buckets, after the backward
-                for i in range(len(BUCKETS)):
-                    self.reducer.events[i].record()
-                    self.reducer.on_ready(i)
+            if self.world > 1 and not hooked:          # non-overlapped variants, after the backward
+                if self.buckets.symm is not None and os.environ.get("AA_DP_SINGLE", "1") != "0":
+                    # ONE exchange of all four buckets (they are contiguous in the symmetric allocation)
+                    self.reducer.events[0].record()
+                    whole = self.buckets.all[: self.buckets.loss_slot.data_ptr() // 4 - self.buckets.all.data_ptr() // 4] \
+                        if self.reducer.bf16_exchange else self.buckets.all
+                    self.reducer._all_reduce(whole, (0,))
+                    self.reducer.order = list(range(len(BUCKETS)))
+                else:                                  # the same buckets as the overlapped schedule, one after the other
+                    for i in range(len(BUCKETS)):
+                        self.reducer.events[i].record()
+                        self.reducer.on_ready(i)
             self.reducer.finish()
             loss = b["loss"]      # (summed over ranks by the tail collective)
         for p, g in zip(self.weights, self.buckets.ordered()):

@@ -207,7 +207,7 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
                         void* scratch, size_t scratch_bytes, void* stream);
 
 /* Data-parallel hook (the reference's multi-GPU scheme is nn.DataParallel's reduce_add_coalesced after
- * backward, baseline_attention.py:184-187; here: one process per GPU, NCCL all-reduce overlapped with the
+ * backward, baseline_attention.py:184-187; here: one process per GPU, all-reduce overlapped with the
  * rest of the backward).  The parameter gradients become final in four buckets, in this order:
  *   AA_BUCKET_MLP      mlp_w, mlp_b                                      (first: half of all gradient bytes)
  *   AA_BUCKET_ATTEN    att_wv, att_wg, att_ws, att_wh, sen_wx, sen_wh
@@ -217,12 +217,18 @@ int aa_decoder_backward(const aa_dims* d, const aa_weights* w, const float* V, c
  * enqueued, it records ready_events[bucket] (cudaEvent_t passed as void*, may be NULL to skip recording) on the
  * stream that kernel ran on and calls on_ready(bucket, user) on the calling host thread, so that the caller
  * can make a communication stream wait on the event and launch the bucket's all-reduce while the remaining
- * backward kernels are still running.  on_ready may be NULL. */
+ * backward kernels are still running.  on_ready may be NULL.
+ * ready_events has AA_NUM_READY_EVENTS entries: the four buckets above and, at index AA_EVENT_BPTT_DONE, an event recorded (and
+ * reported through on_ready with that index) when the recurrence's backward -- the latency-critical kernel of the step, between
+ * the ATTEN and LSTM buckets -- has been enqueued: measured on 8 GPUs, an exchange running next to that kernel doubles its time
+ * (profiles/r02_timeline_n8_v2.txt), so the data-parallel driver starts the first exchange on this event. */
 #define AA_BUCKET_MLP 0
 #define AA_BUCKET_ATTEN 1
 #define AA_BUCKET_LSTM 2
 #define AA_BUCKET_EMBED 3
 #define AA_NUM_BUCKETS 4
+#define AA_EVENT_BPTT_DONE 4
+#define AA_NUM_READY_EVENTS 5
 typedef void (*aa_grad_ready_fn)(int bucket, void* user);
 int aa_decoder_backward_hooked(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g,
                                const int64_t* captions, const float* h0, const float* c0, const float* alpha,
