@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const uint4* __restr
 int ar_threads() {
   static const int threads = [] {
     const char* e = getenv("AA_AR_THREADS");
-    const int t = e ? atoi(e) : 256;
-    return (t >= 32 && t <= AR_THREADS && t % 32 == 0) ? t : 256;
+    const int t = e ? atoi(e) : 512;
+    return (t >= 32 && t <= AR_THREADS && t % 32 == 0) ? t : 512;
   }();
   return threads;
 }

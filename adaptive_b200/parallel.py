@@ -137,7 +137,7 @@ class SymmetricBuffer:
         self.multicast_ptr = int(mc) if os.environ.get("AA_AR_MULTICAST", "1") != "0" else 0
         self._peer_arr = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
         self.lib = lib
-        self.max_blocks = int(os.environ.get("AA_AR_BLOCKS", "8"))
+        self.max_blocks = int(os.environ.get("AA_AR_BLOCKS", "16"))
         dist.barrier(self.group)          # every rank's flags are zero before anyone signals
 
     @property
@@ -250,18 +250,23 @@ class BucketReducer:
         self.works: List = []
         self.order: List[int] = []
         if self.cuda:
-            self.comm_stream = torch.cuda.Stream(device=buckets.flat[0].device)
+            # HIGHEST priority: the exchange kernels are a handful of CTAs that every rank must have RUNNING before any of them can
+            # finish; on a default-priority lane they queue behind the pending CTAs of whatever large grid the backward launched
+            # before them (tools/probe_overlap.py: a 145 us exchange took 480 us next to a 345 us copy kernel -- it simply ran after it)
+            prio = int(os.environ.get("AA_DP_COMM_PRIORITY", "-100"))
+            self.comm_stream = torch.cuda.Stream(device=buckets.flat[0].device, priority=prio)
             # the small attention / sentinel bucket gets a lane of its own: behind the 20 MB vocabulary bucket on ONE lane it waited
             # ~50 us for a 25 us exchange (profiles/r02_timeline_n8_v2.txt)
-            self.comm_stream2 = torch.cuda.Stream(device=buckets.flat[0].device)
+            self.comm_stream2 = torch.cuda.Stream(device=buckets.flat[0].device, priority=prio)
             self.events = [torch.cuda.Event() for _ in range(N_READY_EVENTS)]      # four buckets + "recurrence enqueued"
             for e in self.events:      # the raw cudaEvent_t exists only after a first record
                 e.record()
         else:
             self.comm_stream, self.events = None, [None] * N_READY_EVENTS
-        # peer-memory engine: the first exchange (vocabulary + attention buckets, one launch) starts when the backward's recurrence
-        # has finished instead of next to it; "bucket" = start every bucket's exchange as soon as it is final
-        self.schedule = os.environ.get("AA_DP_SCHEDULE", "after_bptt" if (self.cuda and buckets.symm is not None) else "bucket")
+        # "bucket" = start every bucket's exchange as soon as it is final (default); "after_bptt" = the first exchange (vocabulary +
+        # attention buckets, one launch) starts when the backward's recurrence has finished instead of next to it (measured slower:
+        # 530 vs 495 us per step on 2 GPUs)
+        self.schedule = os.environ.get("AA_DP_SCHEDULE", "bucket")
 
     def event_handles(self):
         """``void* ready_events[AA_NUM_READY_EVENTS]`` for ``aa_decoder_backward_hooked`` (CUDA only)."""

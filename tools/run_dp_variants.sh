@@ -12,9 +12,7 @@ try:
 except Exception as e:
     print('$tag FAILED', e)"
 }
-run afterbptt_bf16_b8 "" AA_X=1
-run afterbptt_bf16_b16t512 "" AA_AR_BLOCKS=16 AA_AR_THREADS=512
-run afterbptt_bf16_b32t512 "" AA_AR_BLOCKS=32 AA_AR_THREADS=512
-run afterbptt_fp32_b16t512 "" AA_AR_BLOCKS=16 AA_AR_THREADS=512 AA_DP_BF16=0
-run bucket_bf16_b8 "" AA_DP_SCHEDULE=bucket
+run default_bucket_bf16_b16t512 "" AA_X=1
 run single_bf16_b32t512 "--overlap 0" AA_DP_SINGLE=1 AA_AR_BLOCKS=32 AA_AR_THREADS=512
+run bucket_bf16_b8t512 "" AA_AR_BLOCKS=8
+run afterbptt_bf16_b16t512 "" AA_DP_SCHEDULE=after_bptt
