@@ -215,11 +215,24 @@ __global__ void __launch_bounds__(256) dec_cell_kernel(const DecodeCellArgs p) {
     const long long r = item / H4;
     const int c = (int)(item % H4) * 4;
     const float* pre = p.gates + r * 5 * H;
-    const float4 pi = ldg4_stream(pre + c);
-    const float4 pf = ldg4_stream(pre + H + c);
-    const float4 pg = ldg4_stream(pre + 2 * H + c);
-    const float4 po = ldg4_stream(pre + 3 * H + c);
-    const float4 ps = ldg4_stream(pre + 4 * H + c);
+    float4 pi = ldg4_stream(pre + c);
+    float4 pf = ldg4_stream(pre + H + c);
+    float4 pg = ldg4_stream(pre + 2 * H + c);
+    float4 po = ldg4_stream(pre + 3 * H + c);
+    float4 ps;
+    if (p.EG) {
+      const long long word = p.prev_ids ? p.prev_ids[r * p.ld_ids] : (long long)p.start_id;
+      const float* eg = p.EG + word * 5 * H;
+      const float4 ei = ldg4(eg + c), ef = ldg4(eg + H + c), eg4 = ldg4(eg + 2 * H + c), eo = ldg4(eg + 3 * H + c), es = ldg4(eg + 4 * H + c);
+      pi.x += ei.x; pi.y += ei.y; pi.z += ei.z; pi.w += ei.w;
+      pf.x += ef.x; pf.y += ef.y; pf.z += ef.z; pf.w += ef.w;
+      pg.x += eg4.x; pg.y += eg4.y; pg.z += eg4.z; pg.w += eg4.w;
+      po.x += eo.x; po.y += eo.y; po.z += eo.z; po.w += eo.w;
+      const float4 ss = ldg4_stream(p.stat + r * 5 * H + 4 * H + c);
+      ps = make_float4(ss.x + es.x, ss.y + es.y, ss.z + es.z, ss.w + es.w);
+    } else {
+      ps = ldg4_stream(pre + 4 * H + c);
+    }
     const float4 cp = *reinterpret_cast<const float4*>(p.c + r * H + c);
     float4 cn, hn, sn;
 #define AA_CELL(X)                                                               \

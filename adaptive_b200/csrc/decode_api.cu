@@ -13,6 +13,8 @@ namespace {
 constexpr int START_ID = 1;  // adaptive_attention.py:188
 constexpr int END_ID = 2;    // build_vocab.py:48-51
 constexpr int MAX_BEAM = 8;
+int g_decode_table = [] { const char* e = getenv("AA_DECODE_TABLE"); return (e && e[0] == '0') ? 0 : 1; }();
+int g_decode_table_min_rows = [] { const char* e = getenv("AA_DECODE_TABLE_MIN_ROWS"); return e ? atoi(e) : 1024; }();
 int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
 // filter-and-refine arg-max of the greedy vocabulary projection (vocab_refine.cu); AA_DECODE_REFINE=0 / aa_debug_set_decode_argmax_refine(0)
 // keep the fp32-accurate 3xTF32 contraction over the whole vocabulary
@@ -41,6 +43,9 @@ struct DecodeWs {
   // filter-and-refine arg-max (vocab_refine.cu): 16-column partial tiles (`tiles16` of them), per-tile weight norms and candidate row lists
   int refine, tiles16; float* wnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
   __nv_bfloat16 *u16, *Wp16;
+  // table mode (greedy, tensor-core pipeline, large batches): EG [Vc,5H] = embed . [W_ih[:, :E]; W_x[:, :E]]^T takes the word's half of
+  // the gate contraction out of the loop (K = E+H -> H, N = 5H -> 4H: the sentinel block has no recurrent half in decode mode, Q3)
+  int table; float *EG, *Whh_s, *emb_s, *wxe_s;
   float *vg_s, *wx_s; int Ep;     // split pipeline: (hi | lo) copies of v_g [B, 2*Ep] and of the v_g columns of [W_ih; W_x] [5H, 2*Ep]
   int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
   // beam only
@@ -73,7 +78,14 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   const size_t ptiles = w.refine ? (size_t)w.tiles16 : (size_t)w.tiles_n;
   w.ldP = w.split ? (d.a + 3) / 4 * 4 : d.a;
   w.ld_qr = (2 * d.a + 3) / 4 * 4;
-  w.Wcat = c.take<float>((size_t)5 * H * (w.split ? 2 * w.Kp : (int)K));
+  // (building the table costs one [Vc x 5H x E] contraction per call: worth it from ~1k rows on)
+  w.table = (w.split && !bm && g_decode_table && R >= (size_t)g_decode_table_min_rows) ? 1 : 0;
+  w.Ep = (int)((E + 31) / 32 * 32);
+  w.Wcat = c.take<float>(w.table ? 0 : (size_t)5 * H * (w.split ? 2 * w.Kp : (int)K));
+  w.EG = c.take<float>(w.table ? (size_t)d.Vc * 5 * H : 0);
+  w.Whh_s = c.take<float>(w.table ? (size_t)4 * H * 2 * w.Hp : 0);
+  w.emb_s = c.take<float>(w.table ? (size_t)d.Vc * 2 * w.Ep : 0);
+  w.wxe_s = c.take<float>(w.table ? (size_t)5 * H * 2 * w.Ep : 0);
   w.W2 = c.take<float>(w.split ? (size_t)2 * d.a * 2 * w.K2p : 0);
   w.hs = c.take<float>(w.split ? R * 2 * H : 0);
   w.qr = c.take<float>(w.split ? R * w.ld_qr : 0);
@@ -93,7 +105,6 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.ncand = c.take<int>(w.refine ? R : 0);
   w.u16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? R * H : 0));
   w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? (size_t)d.Vc * H : 0));
-  w.Ep = (int)((E + 31) / 32 * 32);
   w.vg_s = c.take<float>(w.split ? B * 2 * w.Ep : 0);
   w.wx_s = c.take<float>(w.split ? (size_t)5 * H * 2 * w.Ep : 0);
   w.Acat2 = c.take<float>(bm ? R * w.ldA : 0);
@@ -385,8 +396,22 @@ int dec_gemm(const DecodeWs& ws, int M, int N, int K, int Kp, const float* A, lo
 int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const float* v_g, const float* h0, const float* c0,
                     int beam, DecodeWs& ws, cudaStream_t st) {
   const int B = d.B, H = d.H, E = d.E, R = B * beam, K = E + H;
-  pack_wcat_kernel<<<5 * H, 256, 0, st>>>(w.w_ih, w.w_hh, w.sen_wx, ws.Wcat, H, E, ws.split, ws.Kp, ws.split ? 2 * ws.Kp : K);
-  AA_CHECK_LAUNCH("pack_wcat");
+  if (ws.table) {
+    // recurrent weights alone, and the per-word table of the input half (fp32-accurate 3xTF32 like the per-step contractions)
+    AA_TRY(launch_split_tf32(w.w_hh, H, 4 * H, H, ws.Whh_s, ws.Hp, st));
+    AA_TRY(launch_split_tf32(w.embed, E, d.Vc, E, ws.emb_s, ws.Ep, st));
+    AA_TRY(launch_split_tf32(w.w_ih, 2 * E, 4 * H, E, ws.wxe_s, ws.Ep, st));
+    if (w.sen_wx) AA_TRY(launch_split_tf32(w.sen_wx, 2 * E, H, E, ws.wxe_s + (size_t)4 * H * 2 * ws.Ep, ws.Ep, st));
+    else AA_CHECK_CUDA(cudaMemsetAsync(ws.wxe_s + (size_t)4 * H * 2 * ws.Ep, 0, sizeof(float) * (size_t)H * 2 * ws.Ep, st));
+    TcGemmArgs g{};
+    g.M = d.Vc; g.N = 5 * H; g.K = ws.Ep; g.elem_size = 4; g.split3 = 1;
+    g.A = ws.emb_s; g.lda = 2 * ws.Ep; g.B = ws.wxe_s; g.ldb = 2 * ws.Ep;
+    g.D32 = ws.EG; g.ldd32 = 5 * H;
+    AA_PROF("dec_gate_table", st, launch_gemm_tc(g, st));
+  } else {
+    pack_wcat_kernel<<<5 * H, 256, 0, st>>>(w.w_ih, w.w_hh, w.sen_wx, ws.Wcat, H, E, ws.split, ws.Kp, ws.split ? 2 * ws.Kp : K);
+    AA_CHECK_LAUNCH("pack_wcat");
+  }
   if (ws.split) {
     AA_TRY(launch_split_tf32(w.mlp_w, H, d.Vc, H, ws.Wp_s, ws.Hp, st));
     if (ws.refine) {
@@ -439,12 +464,20 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
 
 // One decode step up to u = c_hat + h for R rows (R = B * beam) whose A operand is `Acur` and cell state `ccur`.
 int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, const float* V, float* Acur, float* ccur, int R, int beam,
-                     float* alpha, long long ld_alpha, float* beta, long long ld_beta, cudaStream_t st) {
+                     float* alpha, long long ld_alpha, float* beta, long long ld_beta, cudaStream_t st,
+                     const long long* prev_ids = nullptr, long long ld_ids = 0) {
   const int H = d.H, E = d.E, K = E + H;
+  if (ws.table) {
+    // gates[:, :4H] = h_{t-1} W_hh^T + static; the word's half comes from the table inside dec_cell
+    AA_PROF("dec_gate_gemm", st, dec_gemm(ws, R, 4 * H, H, ws.Hp, Acur + E, ws.ldA, ws.lo, ws.ldA - E, ws.Whh_s, 2 * ws.Hp, ws.gates, 5 * H,
+                                          ws.stat, 5 * H, nullptr, nullptr, nullptr, st));
+  } else
   // gates = [emb(w_t) | h_{t-1}] Wcat^T + static              (LSTM + sentinel-x pre-activations)
   // (the sentinel rows 4H..5H of Wcat are zero beyond the embedding columns -- decode-mode h~ = 0, Q3: their tiles stop the K loop at E)
-  AA_PROF("dec_gate_gemm", st, dec_gemm(ws, R, 5 * H, K, ws.Kp, Acur, ws.ldA, ws.lo, ws.ldA, ws.Wcat, ws.split ? 2 * ws.Kp : K, ws.gates,
-                                        5 * H, ws.stat, 5 * H, nullptr, nullptr, nullptr, st, 4 * H, E));
+  {
+    AA_PROF("dec_gate_gemm", st, dec_gemm(ws, R, 5 * H, K, ws.Kp, Acur, ws.ldA, ws.lo, ws.ldA, ws.Wcat, ws.split ? 2 * ws.Kp : K, ws.gates,
+                                          5 * H, ws.stat, 5 * H, nullptr, nullptr, nullptr, st, 4 * H, E));
+  }
   if (!ws.split) {   // exact-fp32 path: one fused kernel incl. the q/r mat-vecs
     DecodeStepArgs p{};
     p.B = R; p.k = d.k; p.a = d.a; p.H = H; p.beam = beam;
@@ -457,6 +490,7 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
   }
   DecodeCellArgs cp{};
   cp.R = R; cp.H = H; cp.gates = ws.gates; cp.c = ccur; cp.hs = ws.hs; cp.A = Acur; cp.ldA = ws.ldA; cp.h_off = E; cp.lo_off = ws.lo;
+  if (ws.table) { cp.EG = ws.EG; cp.stat = ws.stat; cp.prev_ids = prev_ids; cp.ld_ids = ld_ids; cp.start_id = START_ID; }
   AA_PROF("dec_cell", st, launch_decode_cell(cp, st));
   // [q | r] = [h | s] W2^T                                                              adaptive_attention.py:35,45
   AA_PROF("dec_qr_gemm", st, dec_gemm(ws, R, 2 * d.a, 2 * H, ws.K2p, Acur + E, ws.ldA, ws.lo, ws.ldA - E, ws.W2, 2 * ws.K2p, ws.qr,
@@ -564,8 +598,10 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
   AA_TRY(decode_prologue(dd, *w, V, v_g, h0, c0, 1, ws, st));
   const float* Wp = ws.split ? ws.Wp_s : w->mlp_w;
   for (int t = 0; t < L; ++t) {
-    AA_TRY(decode_step_body(dd, *w, ws, V, ws.Acat, ws.c, B, 1, attention + (size_t)t * k, (long long)L * k, Beta + t, L, st));
     long long* ids_t = reinterpret_cast<long long*>(ids) + t;
+    AA_TRY(decode_step_body(dd, *w, ws, V, ws.Acat, ws.c, B, 1, attention + (size_t)t * k, (long long)L * k, Beta + t, L, st,
+                            t > 0 ? ids_t - 1 : nullptr, L));
+    float* emb_dst = ws.table ? nullptr : ws.Acat;      // table mode: the next step reads the word's gate terms from EG, not its embedding
     if (ws.split) {
       // logits = u W_p^T + b_p on tensor cores; the epilogue keeps a per-(row, column tile) arg-max, so the [B,Vc]
       // logits never touch HBM unless the caller asked for them                                          :132, :201
@@ -589,13 +625,13 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
                                                               ws.refine == 2 ? 2.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, ws.ncand, st));
         AA_PROF("dec_argmax_refine", st, launch_argmax_refine(w->mlp_w, w->mlp_b, Vc, H, ws.u, ws.ldU, ws.Hp, B, ws.counts, ws.list,
                                                               ws.pmax, ws.pidx, ws.tiles16, st));
-        AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles16, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,
+        AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles16, B, ids_t, L, w->embed, E, emb_dst, ws.ldA, 1,
                                                          ws.lo, st, ws.ncand));
         continue;
       }
       AA_PROF("dec_vocab_gemm", st, dec_gemm(ws, B, Vc, H, ws.Hp, ws.u, ws.ldU, ws.Hp, ws.ldU, Wp, 2 * ws.Hp, lg, Vc, nullptr, 0, w->mlp_b,
                                              ws.pmax, ws.pidx, st));
-      AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles_n, B, ids_t, L, w->embed, E, ws.Acat, ws.ldA, 1,
+      AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles_n, B, ids_t, L, w->embed, E, emb_dst, ws.ldA, 1,
                                                        ws.lo, st));
     } else {
       float* lg = logits_out ? logits_out + (size_t)t * B * Vc : ws.logits;

@@ -215,6 +215,12 @@ struct DecodeCellArgs {
   float* hs;                  // [R,2H] fp32 [h_t | s_t]
   float* A; long long ldA;    // A-operand rows: h (hi) at [h_off, h_off+H), s (hi) at [h_off+H, h_off+2H), lo halves at +lo_off
   long long h_off, lo_off;
+  // table mode (EG != null): the input half of the gates is not in `gates` but a row of the per-word table
+  // EG [Vc,5H] = embed . [W_ih[:, :E]; W_x[:, :E]]^T; `gates` then holds the recurrent half + static term of the four LSTM blocks
+  // (columns [0,4H) of rows of 5H) and the sentinel block's pre-activation is stat[r, 4H:] + EG[word, 4H:]
+  const float* EG; const float* stat;
+  const long long* prev_ids; long long ld_ids;   // word fed at this step: prev_ids[r * ld_ids] (null: start_id for every row)
+  int start_id;
 };
 int launch_decode_cell(const DecodeCellArgs& p, cudaStream_t s);
 // ... and the attention stream: scores + both softmaxes + beta-gated context + (c_hat + h), one warp per row

@@ -484,6 +484,10 @@ def measure_decode_small(torch, dev, model, dims, peaks):
                 row["launches_persistent"] = _lib.launch_count() - l0
                 ms = time_fn(torch, lambda: model.sampler(enc, max_len=DECODE_L), 20, warm=3)
                 alg = B * DECODE_L * out["algorithmic_bytes_per_image_step"]["persistent"]
+                gp = GraphedSampler(model, b, max_len=DECODE_L)
+                msg = time_fn(torch, lambda: gp(b), 20, warm=3)
+                del gp
+                row["persistent_cuda_graph"] = {"tokens_per_s": B * DECODE_L / (msg * 1e-3), "ms": msg}
                 row["persistent"] = {"tokens_per_s": B * DECODE_L / (ms * 1e-3), "ms": ms, "us_per_step": ms * 1e3 / DECODE_L,
                                      "ids_equal_pipeline": float((ids_pers == ids_pipe).all(1).float().mean()),
                                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
