@@ -14,7 +14,7 @@ constexpr int START_ID = 1;  // adaptive_attention.py:188
 constexpr int END_ID = 2;    // build_vocab.py:48-51
 constexpr int MAX_BEAM = 8;
 int g_decode_table = [] { const char* e = getenv("AA_DECODE_TABLE"); return (e && e[0] == '0') ? 0 : 1; }();
-int g_decode_table_min_rows = [] { const char* e = getenv("AA_DECODE_TABLE_MIN_ROWS"); return e ? atoi(e) : 1024; }();
+int g_decode_table_min_rows = [] { const char* e = getenv("AA_DECODE_TABLE_MIN_ROWS"); return e ? atoi(e) : 0; }();
 int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
 // filter-and-refine arg-max of the greedy vocabulary projection (vocab_refine.cu); AA_DECODE_REFINE=0 / aa_debug_set_decode_argmax_refine(0)
 // keep the fp32-accurate 3xTF32 contraction over the whole vocabulary
@@ -78,7 +78,8 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   const size_t ptiles = w.refine ? (size_t)w.tiles16 : (size_t)w.tiles_n;
   w.ldP = w.split ? (d.a + 3) / 4 * 4 : d.a;
   w.ld_qr = (2 * d.a + 3) / 4 * 4;
-  // (building the table costs one [Vc x 5H x E] contraction per call: worth it from ~1k rows on)
+  // (building the table costs one [Vc x 5H x E] contraction per call, ~0.1 ms at cfgA: repaid from ~1k rows on; taken for every
+  //  batch size all the same, so that a shard of a batch decodes bit-identically to the whole -- AA_DECODE_TABLE_MIN_ROWS overrides)
   w.table = (w.split && !bm && g_decode_table && R >= (size_t)g_decode_table_min_rows) ? 1 : 0;
   w.Ep = (int)((E + 31) / 32 * 32);
   w.Wcat = c.take<float>(w.table ? 0 : (size_t)5 * H * (w.split ? 2 * w.Kp : (int)K));
