@@ -115,6 +115,8 @@ SIGNATURES = {
     "aa_allreduce_sum_f32": (c_int, [POINTER(c_void_p), P, ctypes.c_longlong, c_int, c_int, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, P]),
     "aa_allreduce_sum_bf16": (c_int, [POINTER(c_void_p), P, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, ctypes.c_longlong,
                                       ctypes.c_longlong, c_int, c_int, P]),
+    "aa_decoder_forward_loss": (c_int, [_D, _W, P, P, P, P, P, P, c_int64, P, c_int64, P, P, P, P, P, P, c_size_t, P]),
+    "aa_decoder_loss_grad_scale": (c_int, [_D, P, c_size_t, c_int64, P, P]),
     "aa_clip_adam_step": (c_int, [P, c_int, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                   ctypes.c_float, c_int, P, P, P]),
     "aa_pack_rows": (c_int, [P, c_int64, P, c_int64, P, P]),

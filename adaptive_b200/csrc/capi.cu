@@ -156,6 +156,9 @@ struct Saved {
   bf16 *x16, *hid16, *hsprev16, *s16, *V16, *u16, *h016, *whh_pack16, *up16;
   unsigned* counters;
   W16 w16;
+  // fused cross-entropy (aa_decoder_forward_loss, bf16 mode): exp pieces, then the bf16 gradient of the packed logits, in place; chunk
+  // partials (max, sum) and scales; the targets' logits; the bias gradient
+  bf16* ce_e16; float *ce_part, *ce_scale, *ce_xt, *ce_dbp; int ce_chunks;
   size_t bytes;
 };
 
@@ -198,6 +201,12 @@ Saved carve_saved(const aa_dims& d, void* base) {
     s.w16.mlp_w = h.take((size_t)d.Vc * H);
     s.whh_pack16 = h.take(4 * H * H);
     s.counters = reinterpret_cast<unsigned*>(c.take(64));
+    s.ce_chunks = (d.Vc + 31) / 32;
+    s.ce_e16 = h.take(N * d.Vc);
+    s.ce_part = c.take(N * s.ce_chunks * 2);
+    s.ce_scale = c.take(N * s.ce_chunks);
+    s.ce_xt = c.take(N);
+    s.ce_dbp = c.take((size_t)d.Vc);
   }
   s.bytes = c.off;
   return s;
@@ -520,29 +529,38 @@ int aa_adaptive_forward(const aa_dims* d, const aa_weights* w, const float* x, c
 size_t aa_decoder_saved_bytes(const aa_dims* d) { return d ? carve_saved(*d, nullptr).bytes : 0; }
 size_t aa_decoder_bwd_scratch_bytes(const aa_dims* d) { return d ? carve_bwd(*d, nullptr).bytes : 0; }
 
+struct CeFuse;
 static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
                                 const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
-                                void* saved, size_t saved_bytes, void* stream, SideCtx* side, const int64_t* row_index, int64_t n_rows);
+                                void* saved, size_t saved_bytes, void* stream, SideCtx* side, const int64_t* row_index, int64_t n_rows,
+                                const CeFuse* ce);
 
 // fork the call's critical lane from the caller's stream, run the body on it, join every lane back
+// fused loss (aa_decoder_forward_loss): packed targets, denominator of the mean, the loss scalar
+struct CeFuse {
+  const int64_t* targets; long long denom; float* loss;
+};
+
 static int decoder_forward_impl(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
                                 const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
-                                void* saved, size_t saved_bytes, void* stream, const int64_t* row_index, int64_t n_rows) {
+                                void* saved, size_t saved_bytes, void* stream, const int64_t* row_index, int64_t n_rows,
+                                const CeFuse* ce = nullptr) {
   SideCtx* side = nullptr;
   AA_TRY(get_side(&side));
   cudaStream_t caller = (cudaStream_t)stream;
   cudaStream_t st = side ? side->crit : caller;
   AA_TRY(stream_dep(side, SIDE_EVENTS - 4, caller, st));
-  AA_TRY(decoder_forward_body(d, w, V, v_g, captions, h0, c0, scores, alpha, beta, hT, cT, saved, saved_bytes, (void*)st, side, row_index, n_rows));
+  AA_TRY(decoder_forward_body(d, w, V, v_g, captions, h0, c0, scores, alpha, beta, hT, cT, saved, saved_bytes, (void*)st, side, row_index, n_rows, ce));
   if (side) AA_TRY(stream_dep(side, SIDE_EVENTS - 5, side->side2, st));   // (hT / cT copies)
   return stream_dep(side, SIDE_EVENTS - 6, st, caller);
 }
 
 static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
                                 const float* h0, const float* c0, float* scores, float* alpha, float* beta, float* hT, float* cT,
-                                void* saved, size_t saved_bytes, void* stream, SideCtx* side, const int64_t* row_index, int64_t n_rows) {
+                                void* saved, size_t saved_bytes, void* stream, SideCtx* side, const int64_t* row_index, int64_t n_rows,
+                                const CeFuse* ce) {
   AA_TRY(check_dims(d, true));
-  AA_REQUIRE(w && V && v_g && captions && scores && alpha && beta, "aa_decoder_forward: null pointer");
+  AA_REQUIRE(w && V && v_g && captions && (scores || ce) && alpha && beta, "aa_decoder_forward: null pointer");
   bool base = false;
   AA_TRY(check_sentinel_weights(w, &base));
   if (d->B == 0) return AA_OK;
@@ -658,6 +676,26 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
     gather_rows2_kernel<<<(unsigned)n_rows, 128, 0, st>>>(sv.u, tc ? sv.u16 : nullptr, reinterpret_cast<const long long*>(row_index), H,
                                                           sv.up, tc ? sv.up16 : nullptr);
     AA_CHECK_LAUNCH("gather_rows2");
+    if (ce) {
+      // vocabulary projection with the cross-entropy in its epilogue (train.py:63,208): per 32-column chunk the row's maximum, sum of
+      // exponentials and the exponentials as bf16; the [n_rows, Vc] logits are never written.  Then two small passes: chunk partials ->
+      // log-sum-exp, loss and per-chunk scales; exponentials -> bf16 gradient of the logits (in place) + bias gradient.
+      AA_CHECK_CUDA(cudaMemsetAsync(ce->loss, 0, sizeof(float), st));
+      AA_CHECK_CUDA(cudaMemsetAsync(sv.ce_dbp, 0, sizeof(float) * (size_t)d->Vc, st));
+      {
+        ProfScope ps("gemm_vocab_fwd", st);
+        TcGemmArgs g{};
+        g.M = (int)n_rows; g.N = d->Vc; g.K = H; g.elem_size = 2;
+        g.A = sv.up16; g.lda = H; g.B = Wp.h; g.ldb = Wp.ldh; g.bias1 = w->mlp_b;
+        g.ce_e16 = sv.ce_e16; g.ld_ce = d->Vc; g.ce_part = sv.ce_part; g.ce_chunks = sv.ce_chunks;
+        g.ce_tgt = reinterpret_cast<const long long*>(ce->targets); g.ce_xt = sv.ce_xt;
+        AA_TRY(launch_gemm_tc(g, st));
+      }
+      AA_PROF("ce_merge", st, launch_ce_merge(sv.ce_part, sv.ce_chunks, (int)n_rows, sv.ce_xt, ce->denom, ce->loss, sv.ce_scale, st));
+      AA_PROF("ce_fixup", st, launch_ce_fixup(sv.ce_e16, d->Vc, (int)n_rows, d->Vc, sv.ce_scale, sv.ce_chunks,
+                                              reinterpret_cast<const long long*>(ce->targets), ce->denom, sv.ce_dbp, st));
+      return AA_OK;
+    }
     AA_TRY(mm_nt(cx, "gemm_vocab_fwd", (int)n_rows, d->Vc, H, M2(sv.up, H, sv.up16, H), Wp, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr));
     return AA_OK;
   }
@@ -678,6 +716,31 @@ int aa_decoder_forward_packed(const aa_dims* d, const aa_weights* w, const float
   AA_REQUIRE(d->H % 4 == 0, "aa_decoder_forward_packed: H must be a multiple of 4");
   return decoder_forward_impl(d, w, V, v_g, captions, h0, c0, scores_packed, alpha, beta, hT, cT, saved, saved_bytes, stream, row_index,
                               n_rows);
+}
+
+int aa_decoder_forward_loss(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                            const float* h0, const float* c0, const int64_t* row_index, int64_t n_rows, const int64_t* targets,
+                            int64_t denom, float* loss, float* alpha, float* beta, float* hT, float* cT, void* saved, size_t saved_bytes,
+                            void* stream) {
+  AA_REQUIRE(row_index && d && n_rows >= 0 && n_rows <= (int64_t)d->B * d->T, "aa_decoder_forward_loss: bad row index / count");
+  AA_REQUIRE(targets && loss, "aa_decoder_forward_loss: null targets / loss");
+  if (d->precision != AA_PREC_BF16) {
+    set_error("aa_decoder_forward_loss: the loss is fused into the tcgen05 vocabulary contraction (AA_PREC_BF16); the exact path uses "
+              "aa_decoder_forward_packed + aa_cross_entropy");
+    return AA_ERR_UNSUPPORTED;
+  }
+  const CeFuse ce{targets, (long long)(denom > 0 ? denom : n_rows), loss};
+  if (n_rows == 0) AA_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  return decoder_forward_impl(d, w, V, v_g, captions, h0, c0, nullptr, alpha, beta, hT, cT, saved, saved_bytes, stream, row_index, n_rows, &ce);
+}
+
+int aa_decoder_loss_grad_scale(const aa_dims* d, void* saved, size_t saved_bytes, int64_t n_rows, const float* g, void* stream) {
+  AA_TRY(check_dims(d, true));
+  AA_REQUIRE(saved && g && d->precision == AA_PREC_BF16 && n_rows >= 0 && n_rows <= (int64_t)d->B * d->T, "aa_decoder_loss_grad_scale: bad arguments");
+  AA_REQUIRE(saved_bytes >= aa_decoder_saved_bytes(d), "aa_decoder_loss_grad_scale: saved blob too small");
+  Saved sv = carve_saved(*d, saved);
+  AA_TRY(launch_scale_bf16_unless_one(sv.ce_e16, g, n_rows * (long long)d->Vc, (cudaStream_t)stream));
+  return launch_scale_unless_one(sv.ce_dbp, g, d->Vc, (cudaStream_t)stream, nullptr);
 }
 
 static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
@@ -711,7 +774,10 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
                                  float* dc0, void* scratch, size_t scratch_bytes, void* stream, void* const* ready_events,
                                  aa_grad_ready_fn on_ready, void* user, SideCtx* side, const int64_t* row_index, int64_t n_rows, const bf16* dS16_in) {
   AA_TRY(check_dims(d, true));
-  AA_REQUIRE(w && V && v_g && captions && alpha && beta && d_scores && gw, "aa_decoder_backward: null pointer");
+  AA_REQUIRE(w && V && v_g && captions && alpha && beta && gw, "aa_decoder_backward: null pointer");
+  // d_scores == NULL: the gradient of the packed logits is the one aa_decoder_forward_loss left in `saved` (bf16) next to the bias gradient
+  const bool fused_ce = d_scores == nullptr;
+  AA_REQUIRE(!fused_ce || (row_index && d->precision == AA_PREC_BF16), "aa_decoder_backward: d_scores is NULL (only the packed bf16 path after aa_decoder_forward_loss may omit it)");
   bool base = false;
   AA_TRY(check_sentinel_weights(w, &base));
   AA_REQUIRE(gw->embed && gw->w_ih && gw->w_hh && gw->b_ih && gw->b_hh && gw->att_wv && gw->att_wg && gw->att_wh && gw->mlp_w && gw->mlp_b &&
@@ -796,6 +862,7 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   // (packed entry point: d_scores holds the NR = n_rows packed rows only; the other positions have no gradient)
   // When the caller hands the bf16 mirror of dS along (aa_cross_entropy_mirror writes it in the loss kernel's own pass), nothing
   // of this is on the critical path: the column sums only feed the bias gradient and move to lane A.
+  if (fused_ce) dS16_in = sv.ce_e16;
   const bool have16 = tc && dS16_in != nullptr && NR > 0;
   if (have16) {}
   else if (NR > 0) AA_PROF("colsum_cast_dS", st, launch_colsum_cast(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, tc ? sc.dS16 : nullptr, Vc, st));
@@ -811,7 +878,8 @@ static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const fl
   } else {
     AA_TRY(mm_nn(cx, "gemm_vocab_dx", N, H, Vc, dS, Wp, sc.du, H, pre_dx ? sc.du : nullptr, H));
   }
-  if (have16) AA_PROF("colsum_cast_dS", sd, launch_colsum(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, sd));
+  if (fused_ce) AA_CHECK_CUDA(cudaMemcpyAsync(gw->mlp_b, sv.ce_dbp, sizeof(float) * (size_t)Vc, cudaMemcpyDeviceToDevice, sd));
+  else if (have16) AA_PROF("colsum_cast_dS", sd, launch_colsum(d_scores, Vc, NR, Vc, gw->mlp_b, nullptr, sd));
   if (NR > 0) AA_TRY(mm_tn(cs, "gemm_vocab_dw", Vc, H, NR, dS, row_index ? M2(sv.up, H, sv.up16, H) : M2(sv.u, H, sv.u16, H), gw->mlp_w, H, false));
   else AA_CHECK_CUDA(cudaMemsetAsync(gw->mlp_w, 0, sizeof(float) * (size_t)Vc * H, sd));
   AA_TRY(bucket_ready(AA_BUCKET_MLP, sd));

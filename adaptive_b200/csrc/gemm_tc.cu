@@ -83,6 +83,7 @@ struct TcEpilogue {
   int lo_a, lo_b;                           // split mode: column offset of the lo half inside a row of A / B
   int ksplit, kb_per;                       // split-K: work unit = (tile, K range of kb_per k-blocks); partial tiles are added with red.global.add
   int kcut_n0, kcut_nkb;                    // tiles whose first column is >= kcut_n0 stop after kcut_nkb k-blocks (their B rows are zero beyond)
+  __nv_bfloat16* ce_e16; long long ld_ce; float* ce_part; int ce_chunks; const long long* ce_tgt; float* ce_xt;   // PM == 3 (TcGemmArgs::ce_*)
 };
 
 // Tile geometry (bytes): every smem row is 128 B (the swizzle span).
@@ -95,7 +96,8 @@ struct TcEpilogue {
 // each sub-tile once and using it in two products gives 1.5x the arithmetic intensity against L2 of a plain
 // 3K-long tf32 contraction.
 // PM: arg-max partials of the epilogue -- 0 = none (every training contraction: the scan code and its registers stay out of those
-// instantiations), 1 = per-(row, part) maximum and its column index, 2 = maximum only
+// instantiations), 1 = per-(row, part) maximum and its column index, 2 = maximum only, 3 = cross-entropy pieces per 32-column
+// chunk (maximum, sum of exponentials, exponentials as bf16, the target's logit) instead of the logits
 template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT, int PM = 0>
 __global__ void __launch_bounds__(tc_threads(SPLIT), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m,
@@ -280,7 +282,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int nb = n0 + c * 32;
         if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
-        if constexpr (PM == 2) {    // maxima only, one per 16 columns: layout [M, ceil(N / 16)] (the caller recomputes the tiles that
+        if constexpr (PM == 3) {
+          // online log-softmax of this thread's row over the chunk's 32 columns: nothing of size [M, N] leaves the SM in fp32
+          const long long row = row0 + lane;
+          const bool full = nb + 32 <= e.N;
+          float x[32];
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x[j] = (full || nb + j < e.N) ? __uint_as_float(r[j]) + __ldg(e.bias1 + (full ? nb + j : min(nb + j, e.N - 1))) : -INFINITY;
+            m = fmaxf(m, x[j]);
+          }
+          if (row < e.M) {
+            const long long t = e.ce_tgt[row];
+            if (t >= nb && t < nb + 32) {
+              float xt = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) xt = (t == nb + j) ? x[j] : xt;
+              e.ce_xt[row] = xt;
+            }
+          }
+          float ssum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x[j] = __expf(x[j] - m);          // (exp(-inf) = 0 past the last column)
+            ssum += x[j];
+          }
+          if (row < e.M) {
+            float* pp = e.ce_part + (row * e.ce_chunks + (nb >> 5)) * 2;
+            pp[0] = m;
+            pp[1] = ssum;
+            __nv_bfloat16* er = e.ce_e16 + row * e.ld_ce + nb;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 t2;
+                t2 = __floats2bfloat162_rn(x[j], x[j + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t2);
+                t2 = __floats2bfloat162_rn(x[j + 2], x[j + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
+                t2 = __floats2bfloat162_rn(x[j + 4], x[j + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                t2 = __floats2bfloat162_rn(x[j + 6], x[j + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
+                *reinterpret_cast<uint4*>(er + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < e.N) er[j] = __float2bfloat16(x[j]);
+            }
+          }
+          continue;
+        } else if constexpr (PM == 2) {    // maxima only, one per 16 columns: layout [M, ceil(N / 16)] (the caller recomputes the tiles that
                                     // matter itself: vocab_refine.cu).  The (value, index) scan below costs ~17 instructions per
                                     // element and bounded the single-pass contraction at 6 us per tile
                                     // (profiles/r01_v64_vocab_pass1_hot_lines.txt); this one ~2.5
@@ -438,6 +489,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
     e.kcut_n0 = g.kcut_n0;
     e.kcut_nkb = ceil_div(g.kcut_cols, 128 / ES);
   }
+  e.ce_e16 = g.ce_e16; e.ld_ce = g.ld_ce; e.ce_part = g.ce_part; e.ce_chunks = g.ce_chunks; e.ce_tgt = g.ce_tgt; e.ce_xt = g.ce_xt;
   e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = PM == 2 ? ceil_div(g.N, 16) : ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
   constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration exceeds shared memory");
@@ -456,7 +508,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   int ksplit = 1;
   // (a split needs the output zero-filled first: a memset node and its dependency edge cost ~2-3 us inside a graph, more than the
   //  ~0.9 us that halving an 8-k-block chain saves -- K <= 8 k-blocks is never split)
-  if (!SPLIT && g.D32 && !g.D16 && !g.pmax && g_tc_splitk && nkb > 8) {
+  if (!SPLIT && g.D32 && !g.D16 && !g.pmax && !g.ce_e16 && g_tc_splitk && nkb > 8) {
     const int sms = num_sms();
     while (ksplit < 16 && num_tiles * (ksplit + 1) <= sms && nkb / (ksplit + 1) >= 4) ++ksplit;
   }
@@ -491,6 +543,10 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
   const long long sms = num_sms();
   const long long mt = ceil_div(g.M, BM);
   const bool can_splitk = g_tc_splitk && g.D32 && !g.D16 && !g.pmax && ceil_div(g.K, 128 / ES) >= 8;
+  if (g.ce_e16) {      // cross-entropy epilogue: bf16 only (checked by the caller)
+    if constexpr (ES == 2) return launch_cfg<128, 2, 5, false, false, false, 3>(g, st);
+    else return AA_ERR_UNSUPPORTED;
+  }
   // maxima partials of a plain (single-pass) contraction: one per 16 columns, layout [M, ceil(N / 16)] (gemm_tc_argmax_tile_n_plain)
   if (g.pmax) {
     // (bf16, wide N: 256-column tiles pull 48 KB per k-block for twice the columns of a 32 KB 128-column k-block -- the pass is
@@ -529,7 +585,11 @@ int gemm_tc_argmax_tile_n_plain(int) { return 16; }
 
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AA_OK;
-  AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16 || g.pmax), "tcgen05 GEMM: bad arguments");
+  AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16 || g.pmax || g.ce_e16), "tcgen05 GEMM: bad arguments");
+  AA_REQUIRE(!g.ce_e16 || (g.elem_size == 2 && !g.split3 && !g.a_mn && !g.b_mn && !g.D32 && !g.D16 && !g.pmax && !g.Cin && g.bias1 && !g.bias2 &&
+                           g.ce_part && g.ce_tgt && g.ce_xt && g.ld_ce % 8 == 0 && g.ce_chunks == (g.N + 31) / 32 &&
+                           (reinterpret_cast<uintptr_t>(g.ce_e16) & 15) == 0),
+             "tcgen05 GEMM: the cross-entropy epilogue needs K-major bf16 operands, one bias, no other output and 16-byte aligned bf16 rows");
   AA_REQUIRE(g.elem_size == 2 || g.elem_size == 4, "tcgen05 GEMM: element size must be 2 (bf16) or 4 (tf32)");
   AA_REQUIRE(!g.pmax || (!g.Cin && (g.split3 || (!g.a_mn && !g.b_mn))), "tcgen05 GEMM: arg-max partials need K-major operands and no C input");
   AA_REQUIRE(!g.pmax || (g.split3 ? g.pidx != nullptr : (g.pidx == nullptr && !g.bias2)),

@@ -69,6 +69,13 @@ int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, i
 
 // x[0:n] *= *g unless *g == 1 (device scalar)
 int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s, __nv_bfloat16* x16 = nullptr);
+// fused cross-entropy (see TcGemmArgs::ce_*): merge the chunk partials of every row into its log-sum-exp, add the row's loss term
+// to *loss, and leave scale[row * chunks + chunk] = exp(m_chunk - lse) / denom ...
+int launch_scale_bf16_unless_one(__nv_bfloat16* x, const float* g, long long n, cudaStream_t s);
+int launch_ce_merge(const float* part, int chunks, int n_rows, const float* xt, long long denom, float* loss, float* scale, cudaStream_t s);
+// ... then dlogits (bf16, in place over e) = e * scale - onehot / denom, and the bias gradient dbp[j] = sum over rows (dbp pre-zeroed)
+int launch_ce_fixup(__nv_bfloat16* e16, long long ld, int n_rows, int Vc, const float* scale, int chunks, const long long* tgt, long long denom,
+                    float* dbp, cudaStream_t s);
 // zero-fill of up to 8 buffers in one launch (null / empty entries are skipped)
 int launch_zero_multi(int nsegs, void* const* dst, const long long* bytes, cudaStream_t s);
 // up to 8 device-to-device copies in one launch
@@ -101,6 +108,11 @@ struct TcGemmArgs {
   // optional: the rows n >= kcut_n0 of B are zero beyond their first kcut_cols reduction columns (per half in split mode): output
   // tiles starting at or after kcut_n0 stop their K loop there.  Ignored unless kcut_n0 is a multiple of the tile width; no split-K.
   int kcut_n0, kcut_cols;
+  // optional (plain bf16, K-major): cross-entropy pieces instead of the logits (train.py:63,208 fused into the vocabulary projection's
+  // epilogue; D32 / D16 null).  Per row and 32-column chunk of D (+ bias1): the chunk maximum m and s = sum exp(x - m) go to
+  // ce_part[(row * ce_chunks + chunk) * 2 + {0, 1}], e = exp(x - m) as bf16 to ce_e16[row * ld_ce + col], and the target column's
+  // logit x[ce_tgt[row]] to ce_xt[row].  ce_chunks = ceil(N / 32).
+  __nv_bfloat16* ce_e16; long long ld_ce; float* ce_part; int ce_chunks; const long long* ce_tgt; float* ce_xt;
 };
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
 int gemm_tc_argmax_tile_n(int N);

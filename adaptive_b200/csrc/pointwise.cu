@@ -650,6 +650,97 @@ int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, i
   return AA_OK;
 }
 
+// ---- cross-entropy fused into the vocabulary projection (gemm_tc.cu, PM == 3): the two small passes after the contraction ----
+namespace {
+// one warp per row: lse = M + log(sum_c s_c exp(m_c - M)); loss += (lse - x_t) / denom; scale[c] = exp(m_c - lse) / denom
+__global__ void __launch_bounds__(PW_THREADS) ce_merge_kernel(const float* __restrict__ part, int chunks, int n_rows, const float* __restrict__ xt,
+                                                              float inv_n, float* __restrict__ loss, float* __restrict__ scale) {
+  const int r = blockIdx.x * (PW_THREADS / 32) + (threadIdx.x >> 5);
+  const int l = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const float2* pr = reinterpret_cast<const float2*>(part) + (long long)r * chunks;
+  float M = -INFINITY;
+  for (int c = l; c < chunks; c += 32) M = fmaxf(M, pr[c].x);
+  M = warp_max(M);
+  float S = 0.f;
+  for (int c = l; c < chunks; c += 32) {
+    const float2 v = pr[c];
+    S += v.y * expf(v.x - M);
+  }
+  S = warp_sum(S);
+  const float lse = M + logf(S);
+  for (int c = l; c < chunks; c += 32) scale[(long long)r * chunks + c] = expf(pr[c].x - lse) * inv_n;
+  if (l == 0) atomicAdd(loss, (lse - xt[r]) * inv_n);
+}
+
+// dlogits = e * scale - onehot / denom (bf16, in place), dbp[j] += column sums.  CTA = (strip of 2 * PW_THREADS columns, block of
+// CE_RB rows); a thread owns two adjacent columns.
+constexpr int CE_RB = 32;
+__global__ void __launch_bounds__(PW_THREADS) ce_fixup_kernel(bf16* __restrict__ e16, long long ld, int n_rows, int Vc, const float* __restrict__ scale,
+                                                              int chunks, const long long* __restrict__ tgt, float inv_n, float* __restrict__ dbp) {
+  const int j = (blockIdx.x * PW_THREADS + threadIdx.x) * 2;
+  if (j >= Vc) return;
+  const int r0 = blockIdx.y * CE_RB, r1 = min(n_rows, r0 + CE_RB);
+  const int c = j >> 5;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(e16 + (long long)r * ld + j);
+    const float2 v = __bfloat1622float2(*p);
+    const float f = __ldg(scale + (long long)r * chunks + c);
+    const long long t = __ldg(tgt + r);
+    float d0 = v.x * f, d1 = v.y * f;
+    if (t == j) d0 -= inv_n;
+    if (t == j + 1) d1 -= inv_n;
+    if (j + 1 >= Vc) d1 = 0.f;
+    *p = __floats2bfloat162_rn(d0, d1);
+    s0 += d0;
+    s1 += d1;
+  }
+  atomicAdd(dbp + j, s0);
+  if (j + 1 < Vc) atomicAdd(dbp + j + 1, s1);
+}
+}  // namespace
+
+namespace {
+__global__ void scale_bf16_unless_one_kernel(bf16* __restrict__ x, const float* __restrict__ g, long long n2) {
+  const float f = *g;
+  if (f == 1.f) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(x) + i;
+    const float2 v = __bfloat1622float2(*p);
+    *p = __floats2bfloat162_rn(v.x * f, v.y * f);
+  }
+}
+}  // namespace
+
+int launch_scale_bf16_unless_one(__nv_bfloat16* x, const float* g, long long n, cudaStream_t s) {
+  if (n == 0) return AA_OK;
+  AA_REQUIRE(n % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0, "scale_bf16: even length and 4-byte alignment needed");
+  long long nb = (n / 2 + PW_THREADS * 4 - 1) / (PW_THREADS * 4);
+  nb = nb > 1184 ? 1184 : nb;
+  scale_bf16_unless_one_kernel<<<(unsigned)nb, PW_THREADS, 0, s>>>(x, g, n / 2);
+  AA_CHECK_LAUNCH("scale_bf16_unless_one");
+  return AA_OK;
+}
+
+int launch_ce_merge(const float* part, int chunks, int n_rows, const float* xt, long long denom, float* loss, float* scale, cudaStream_t s) {
+  if (n_rows == 0) return AA_OK;
+  const float inv_n = 1.f / (float)(denom > 0 ? denom : n_rows);
+  ce_merge_kernel<<<ceil_div(n_rows, PW_THREADS / 32), PW_THREADS, 0, s>>>(part, chunks, n_rows, xt, inv_n, loss, scale);
+  AA_CHECK_LAUNCH("ce_merge");
+  return AA_OK;
+}
+
+int launch_ce_fixup(__nv_bfloat16* e16, long long ld, int n_rows, int Vc, const float* scale, int chunks, const long long* tgt, long long denom,
+                    float* dbp, cudaStream_t s) {
+  if (n_rows == 0) return AA_OK;
+  AA_REQUIRE(ld % 2 == 0 && (reinterpret_cast<uintptr_t>(e16) & 3) == 0, "ce_fixup: bf16 rows must be 4-byte aligned");
+  const float inv_n = 1.f / (float)(denom > 0 ? denom : n_rows);
+  ce_fixup_kernel<<<dim3(ceil_div(Vc, 2 * PW_THREADS), ceil_div(n_rows, CE_RB)), PW_THREADS, 0, s>>>(e16, ld, n_rows, Vc, scale, chunks, tgt, inv_n, dbp);
+  AA_CHECK_LAUNCH("ce_fixup");
+  return AA_OK;
+}
+
 // zero-fill of up to 8 buffers in one launch (16-byte vector stores where the buffer allows)
 namespace {
 __global__ void zero_multi_kernel(const CopySegs segs) {

@@ -274,6 +274,108 @@ def decoder_forward_packed(w: Sequence[torch.Tensor], V, v_g, captions, lengths:
     return torch.nn.utils.rnn.PackedSequence(data, batch_sizes), alpha, beta, hT, cT
 
 
+class _DecoderLossFn(torch.autograd.Function):
+    """``Encoder2Decoder.forward`` + mean cross-entropy over the packed positions (``train.py:205-208``) in ONE operator, the loss
+    fused into the vocabulary projection's epilogue (``aa_decoder_forward_loss``): the ``[n_rows, Vc]`` logits are never written."""
+
+    @staticmethod
+    def forward(ctx, prec, denom, V, v_g, captions, h0, c0, row_index, targets, *w):
+        lib = _lib.load()
+        B, k, H = V.shape
+        T = captions.shape[1]
+        E = v_g.shape[1]
+        Vc = w[0].shape[0]
+        a = w[7].shape[0]
+        _check_weights(w, H, E, Vc, a)
+        dev = V.device
+        n = row_index.numel()
+        d = make_dims(B, T, k, H, E, Vc, a, prec)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        alpha = torch.empty(B, T, k, device=dev, dtype=torch.float32)
+        beta = torch.empty(B, T, 1, device=dev, dtype=torch.float32)
+        hT = torch.empty(B, H, device=dev, dtype=torch.float32)
+        cT = torch.empty(B, H, device=dev, dtype=torch.float32)
+        nbytes = lib.aa_decoder_saved_bytes(ctypes.byref(d))
+        saved = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        ws = weights_struct(w)
+        with torch.cuda.device(dev):
+            check(lib.aa_decoder_forward_loss(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(captions), _ptr(h0), _ptr(c0),
+                                              _ptr(row_index), n, _ptr(targets), int(denom), _ptr(loss), _ptr(alpha), _ptr(beta), _ptr(hT),
+                                              _ptr(cT), _ptr(saved), nbytes, _stream(dev)), "aa_decoder_forward_loss")
+        ctx.dims = (B, T, k, H, E, Vc, a, prec)
+        ctx.has_state = (h0 is not None, c0 is not None)
+        ctx.save_for_backward(V, v_g, captions, h0 if h0 is not None else V.new_empty(0),
+                              c0 if c0 is not None else V.new_empty(0), alpha, beta, saved, row_index, *w)
+        ctx.set_materialize_grads(False)
+        ctx.consumed = False
+        return loss, alpha, beta, hT, cT
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_loss, d_alpha, d_beta, d_hT, d_cT):
+        lib = _lib.load()
+        V, v_g, captions, h0, c0, alpha, beta, saved, row_index = ctx.saved_tensors[:9]
+        w = ctx.saved_tensors[9:]
+        B, T, k, H, E, Vc, a, prec = ctx.dims
+        if ctx.consumed:
+            raise RuntimeError("adaptive_b200.decoder_forward_loss: backward twice through the same loss is not supported "
+                               "(the stored gradient of the logits is consumed in place)")
+        ctx.consumed = True
+        h0 = h0 if ctx.has_state[0] else None
+        c0 = c0 if ctx.has_state[1] else None
+        dev = V.device
+        n = row_index.numel()
+        d = make_dims(B, T, k, H, E, Vc, a, prec)
+        d_alpha, d_beta, d_hT, d_cT = (_f32c(x) for x in (d_alpha, d_beta, d_hT, d_cT))
+        grads = [torch.empty_like(t) if t is not None else None for t in w]
+        gs = AAWeightGrads()
+        for name, t in zip(WEIGHT_FIELDS, grads):
+            if t is not None:
+                setattr(gs, name, t.data_ptr())
+        dV = torch.empty_like(V)
+        dvg = torch.empty_like(v_g)
+        dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if h0 is not None else None
+        dc0 = torch.empty(B, H, device=dev, dtype=torch.float32) if c0 is not None else None
+        sbytes = lib.aa_decoder_bwd_scratch_bytes(ctypes.byref(d))
+        scratch = torch.empty(sbytes, device=dev, dtype=torch.uint8)
+        ws = weights_struct(w)
+        with torch.cuda.device(dev):
+            if g_loss is None:
+                g_loss = torch.zeros((), device=dev, dtype=torch.float32)
+            g_loss = g_loss.to(torch.float32).contiguous()
+            check(lib.aa_decoder_loss_grad_scale(ctypes.byref(d), _ptr(saved), saved.numel(), n, _ptr(g_loss), _stream(dev)),
+                  "aa_decoder_loss_grad_scale")
+            check(lib.aa_decoder_backward_packed(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(captions), _ptr(h0),
+                                                 _ptr(c0), _ptr(alpha), _ptr(beta), _ptr(saved), saved.numel(), _ptr(row_index), n,
+                                                 None, _ptr(d_alpha), _ptr(d_beta), _ptr(d_hT), _ptr(d_cT), ctypes.byref(gs),
+                                                 _ptr(dV), _ptr(dvg), _ptr(dh0), _ptr(dc0), _ptr(scratch), sbytes, _stream(dev), None, None,
+                                                 None, None), "aa_decoder_backward_packed")
+        return (None, None, dV, dvg, None, dh0, dc0, None, None) + tuple(grads)
+
+
+def decoder_forward_loss(w: Sequence[torch.Tensor], V, v_g, captions, lengths: Sequence[int], targets=None, h0=None, c0=None,
+                         denom: int = 0):
+    """-> (mean cross-entropy over the packed positions, alpha, beta, hT, cT), differentiable; bf16 tensor-core path only.
+    Equal (to bf16 accuracy) to ``cross_entropy(decoder_forward_packed(...)[0].data, targets)`` without the logits ever reaching
+    memory.  ``targets`` defaults to the packed next words ``pack(captions[:, 1:], lengths)`` (``train.py:102``)."""
+    _need_cuda(V, v_g, captions, h0, c0)
+    V, v_g = _f32c(V), _f32c(v_g)
+    B, _, H = V.shape
+    captions = captions.to(torch.int64).contiguous()
+    h0, c0 = _states2d(h0, B, H), _states2d(c0, B, H)
+    T = captions.shape[1]
+    row_index, _ = cached_row_index(lengths, T, V.device)
+    if targets is None:
+        if max(int(x) for x in lengths) > T - 1:
+            raise ValueError("default targets are the next words captions[:, 1:]: lengths must not exceed T - 1")
+        tidx, _ = cached_row_index(lengths, T - 1, V.device)
+        targets = captions[:, 1:].reshape(-1)[tidx]
+    targets = targets.to(torch.int64).contiguous()
+    if targets.numel() != row_index.numel():
+        raise ValueError("targets has %d entries, the packed rows %d" % (targets.numel(), row_index.numel()))
+    return _DecoderLossFn.apply(PRECISIONS["bf16"], int(denom), V, v_g, captions, h0, c0, row_index, targets, *w)
+
+
 class _PackRowsFn(torch.autograd.Function):
     """``pack_padded_sequence(scores, lengths, batch_first=True).data`` (baseline_attention.py:228)."""
 

@@ -46,8 +46,8 @@ class GraphedTrainStep:
         b = self.static
         for p in self.params:
             p.grad = None
-        packed = self.model((b["V"], b["v_g"], (b["h0"], b["c0"])), b["captions"], self.lengths)
-        loss = F_aa.cross_entropy(packed.data, b["tgt"])
+        # (bf16 path: the loss is fused into the vocabulary projection's epilogue, the packed logits are never written)
+        loss = self.model.forward_loss((b["V"], b["v_g"], (b["h0"], b["c0"])), b["captions"], self.lengths, b["tgt"])
         loss.backward()
         return loss
 

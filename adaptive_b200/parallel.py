@@ -449,6 +449,7 @@ class DataParallelTrainer:
              denom: Optional[int] = None) -> torch.Tensor:
         """``denom``: the GLOBAL packed-row count if the caller already knows it (same value on every rank); by default it is
         gathered from all ranks on every call (``global_token_count``)."""
+        from . import _lib as _lib_mod
         from . import functional as F_aa
         from ._lib import AAWeightGrads, check
 
@@ -477,12 +478,18 @@ class DataParallelTrainer:
             setattr(gs, name, t.data_ptr())
         with torch.cuda.device(self.device):
             # forward over the packed rows only (pack_padded_sequence fused, Q13), loss + its gradient in one pass, backward
-            check(lib.aa_decoder_forward_packed(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(row_index),
-                                                n_rows, P(b["packed"]), P(b["alpha"]), P(b["beta"]), P(b["hT"]), P(b["cT"]), P(b["saved"]),
-                                                b["saved"].numel(), st), "aa_decoder_forward_packed")
+            fused = prec == _lib_mod.PREC_BF16 and os.environ.get("AA_FUSED_CE", "1") != "0"
             written = ctypes.c_int(0)
-            check(lib.aa_cross_entropy_mirror(P(b["packed"]), n_rows, Vc, P(targets), denom, P(b["loss"]), P(b["dpacked"]), P(b["dpacked16"]),
-                                              ctypes.byref(written), st), "aa_cross_entropy_mirror")
+            if fused:      # the loss rides in the vocabulary projection's epilogue; the gradient of the logits stays inside `saved` (bf16)
+                check(lib.aa_decoder_forward_loss(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(row_index),
+                                                  n_rows, P(targets), denom, P(b["loss"]), P(b["alpha"]), P(b["beta"]), P(b["hT"]), P(b["cT"]),
+                                                  P(b["saved"]), b["saved"].numel(), st), "aa_decoder_forward_loss")
+            else:
+                check(lib.aa_decoder_forward_packed(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(row_index),
+                                                    n_rows, P(b["packed"]), P(b["alpha"]), P(b["beta"]), P(b["hT"]), P(b["cT"]), P(b["saved"]),
+                                                    b["saved"].numel(), st), "aa_decoder_forward_packed")
+                check(lib.aa_cross_entropy_mirror(P(b["packed"]), n_rows, Vc, P(targets), denom, P(b["loss"]), P(b["dpacked"]), P(b["dpacked16"]),
+                                                  ctypes.byref(written), st), "aa_cross_entropy_mirror")
             self.reducer.start()
             if self.reducer.bf16_exchange and self.world > 1:
                 self._loss_ready.record(torch.cuda.current_stream(self.device))
@@ -490,7 +497,7 @@ class DataParallelTrainer:
             hooked = self.overlap and self.world > 1
             check(lib.aa_decoder_backward_packed(
                 ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(b["alpha"]), P(b["beta"]), P(b["saved"]),
-                b["saved"].numel(), P(row_index), n_rows, P(b["dpacked"]), None, None, None, None, ctypes.byref(gs), P(b["dV"]),
+                b["saved"].numel(), P(row_index), n_rows, None if fused else P(b["dpacked"]), None, None, None, None, ctypes.byref(gs), P(b["dV"]),
                 P(b["dvg"]), P(b["dh0"]) if h0 is not None else None, P(b["dc0"]) if c0 is not None else None, P(b["scratch"]),
                 b["scratch"].numel(), st, self.reducer.event_handles() if hooked else None,
                 ctypes.cast(self._cb, ctypes.c_void_p) if hooked else None, None, P(b["dpacked16"]) if written.value else None),

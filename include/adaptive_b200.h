@@ -301,6 +301,22 @@ int aa_decoder_backward_packed(const aa_dims* d, const aa_weights* w, const floa
                                size_t scratch_bytes, void* stream, void* const* ready_events, aa_grad_ready_fn on_ready, void* user,
                                const void* d_scores_packed_bf16 /* optional: bf16 mirror of d_scores_packed, see aa_cross_entropy_mirror */);
 
+/* Forward + loss in one operator: Encoder2Decoder.forward (baseline_attention.py:206-230) followed by the
+ * caller's mean cross-entropy over the packed positions (nn.CrossEntropyLoss at train.py:63,208) WITHOUT ever writing the
+ * [n_rows, Vc] logits: the vocabulary projection's tcgen05 epilogue keeps, per row and 32-column chunk, the maximum, the sum of
+ * exponentials and the exponentials themselves as bf16; two small passes turn them into the loss and into the bf16 gradient of the
+ * logits (kept inside `saved`, together with the bias gradient).  AA_PREC_BF16 only (AA_ERR_UNSUPPORTED otherwise: the exact
+ * path is aa_decoder_forward_packed + aa_cross_entropy).  targets [n_rows] int64 = the packed next words (train.py:102);
+ * denom = denominator of the mean (0 = n_rows; data-parallel training passes the global count); loss: device scalar.
+ * The matching backward is aa_decoder_backward_packed with d_scores_packed = NULL and d_scores_packed_bf16 = NULL: it takes the
+ * gradient of the logits from `saved`.  If the loss is not the root of the backward pass, aa_decoder_loss_grad_scale multiplies
+ * that stored gradient by the upstream scalar *g (device pointer; nothing is done when *g == 1) first. */
+int aa_decoder_forward_loss(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,
+                            const float* h0, const float* c0, const int64_t* row_index, int64_t n_rows, const int64_t* targets,
+                            int64_t denom, float* loss, float* alpha, float* beta, float* hT, float* cT, void* saved,
+                            size_t saved_bytes, void* stream);
+int aa_decoder_loss_grad_scale(const aa_dims* d, void* saved, size_t saved_bytes, int64_t n_rows, const float* g, void* stream);
+
 /* pack_padded_sequence(scores, lengths, batch_first=True).data (baseline_attention.py:228):
  * gathers rows (b,t) with t < lengths[b] in time-major order.  row_index [n_rows] int64 holds
  * b*T+t per packed row (host code builds it from `lengths`).  packed [n_rows,Vc]. */
