@@ -206,7 +206,7 @@ Saved carve_saved(const aa_dims& d, void* base) {
     s.ce_part = c.take(N * s.ce_chunks * 2);
     s.ce_scale = c.take(N * s.ce_chunks);
     s.ce_xt = c.take(N);
-    s.ce_dbp = c.take((size_t)d.Vc);
+    s.ce_dbp = c.take((size_t)d.Vc + 1);      // (+ 1: the loss accumulator)
   }
   s.bytes = c.off;
   return s;
@@ -278,8 +278,12 @@ int check_sentinel_weights(const aa_weights* w, bool* base) {
 }
 
 // dst[r, :] = src[row_index[r], :] (fp32 and, optionally, the bf16 mirror in the same launch); cols % 4 == 0
+// (zero / nzero: an fp32 array the same launch zero-fills on the way -- the fused loss's scalar and bias gradient: memset nodes in front
+//  of the vocabulary contraction cost ~13 us of dispatch inside the replayed graph, profiles/r02_timeline_n1_fusedce_v1.txt)
 __global__ void gather_rows2_kernel(const float* __restrict__ src, const bf16* __restrict__ src16, const long long* __restrict__ row_index,
-                                    int cols, float* __restrict__ dst, bf16* __restrict__ dst16) {
+                                    int cols, float* __restrict__ dst, bf16* __restrict__ dst16, float* __restrict__ zero = nullptr,
+                                    long long nzero = 0) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += (long long)gridDim.x * blockDim.x) zero[i] = 0.f;
   const long long r = blockIdx.x, sr = row_index[r];
   for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
     *reinterpret_cast<float4*>(dst + r * cols + c) = *reinterpret_cast<const float4*>(src + sr * cols + c);
@@ -673,15 +677,14 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
                      sv.q, sv.r, nullptr, sv.ctx, sv.u, sv.u16, alpha, beta, /*have_P=*/true, /*have_q=*/true, base));
   if (row_index) {   // only the rows pack_padded_sequence keeps, already in packed order (baseline_attention.py:228, Q13)
     if (n_rows == 0) return AA_OK;
+    // (fused loss: ce_dbp [Vc] and the loss accumulator behind it are zero-filled by the same launch)
     gather_rows2_kernel<<<(unsigned)n_rows, 128, 0, st>>>(sv.u, tc ? sv.u16 : nullptr, reinterpret_cast<const long long*>(row_index), H,
-                                                          sv.up, tc ? sv.up16 : nullptr);
+                                                          sv.up, tc ? sv.up16 : nullptr, ce ? sv.ce_dbp : nullptr, ce ? (long long)d->Vc + 1 : 0);
     AA_CHECK_LAUNCH("gather_rows2");
     if (ce) {
       // vocabulary projection with the cross-entropy in its epilogue (train.py:63,208): per 32-column chunk the row's maximum, sum of
       // exponentials and the exponentials as bf16; the [n_rows, Vc] logits are never written.  Then two small passes: chunk partials ->
       // log-sum-exp, loss and per-chunk scales; exponentials -> bf16 gradient of the logits (in place) + bias gradient.
-      AA_CHECK_CUDA(cudaMemsetAsync(ce->loss, 0, sizeof(float), st));
-      AA_CHECK_CUDA(cudaMemsetAsync(sv.ce_dbp, 0, sizeof(float) * (size_t)d->Vc, st));
       {
         ProfScope ps("gemm_vocab_fwd", st);
         TcGemmArgs g{};
@@ -691,9 +694,9 @@ static int decoder_forward_body(const aa_dims* d, const aa_weights* w, const flo
         g.ce_tgt = reinterpret_cast<const long long*>(ce->targets); g.ce_xt = sv.ce_xt;
         AA_TRY(launch_gemm_tc(g, st));
       }
-      AA_PROF("ce_merge", st, launch_ce_merge(sv.ce_part, sv.ce_chunks, (int)n_rows, sv.ce_xt, ce->denom, ce->loss, sv.ce_scale, st));
+      AA_PROF("ce_merge", st, launch_ce_merge(sv.ce_part, sv.ce_chunks, (int)n_rows, sv.ce_xt, ce->denom, sv.ce_dbp + d->Vc, sv.ce_scale, st));
       AA_PROF("ce_fixup", st, launch_ce_fixup(sv.ce_e16, d->Vc, (int)n_rows, d->Vc, sv.ce_scale, sv.ce_chunks,
-                                              reinterpret_cast<const long long*>(ce->targets), ce->denom, sv.ce_dbp, st));
+                                              reinterpret_cast<const long long*>(ce->targets), ce->denom, sv.ce_dbp, st, sv.ce_dbp + d->Vc, ce->loss));
       return AA_OK;
     }
     AA_TRY(mm_nt(cx, "gemm_vocab_fwd", (int)n_rows, d->Vc, H, M2(sv.up, H, sv.up16, H), Wp, scores, d->Vc, nullptr, 0, w->mlp_b, nullptr));
@@ -739,8 +742,7 @@ int aa_decoder_loss_grad_scale(const aa_dims* d, void* saved, size_t saved_bytes
   AA_REQUIRE(saved && g && d->precision == AA_PREC_BF16 && n_rows >= 0 && n_rows <= (int64_t)d->B * d->T, "aa_decoder_loss_grad_scale: bad arguments");
   AA_REQUIRE(saved_bytes >= aa_decoder_saved_bytes(d), "aa_decoder_loss_grad_scale: saved blob too small");
   Saved sv = carve_saved(*d, saved);
-  AA_TRY(launch_scale_bf16_unless_one(sv.ce_e16, g, n_rows * (long long)d->Vc, (cudaStream_t)stream));
-  return launch_scale_unless_one(sv.ce_dbp, g, d->Vc, (cudaStream_t)stream, nullptr);
+  return launch_scale_bf16_unless_one(sv.ce_e16, g, n_rows * (long long)d->Vc, sv.ce_dbp, d->Vc, (cudaStream_t)stream);
 }
 
 static int decoder_backward_body(const aa_dims* d, const aa_weights* w, const float* V, const float* v_g, const int64_t* captions,

@@ -288,10 +288,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool full = nb + 32 <= e.N;
           float x[32];
           float m = -INFINITY;
+          if (full && (reinterpret_cast<uintptr_t>(e.bias1) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x[j] = (full || nb + j < e.N) ? __uint_as_float(r[j]) + __ldg(e.bias1 + (full ? nb + j : min(nb + j, e.N - 1))) : -INFINITY;
-            m = fmaxf(m, x[j]);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias1 + nb + j));
+              x[j] = __uint_as_float(r[j]) + b4.x; x[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+              x[j + 2] = __uint_as_float(r[j + 2]) + b4.z; x[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+              m = fmaxf(fmaxf(m, fmaxf(x[j], x[j + 1])), fmaxf(x[j + 2], x[j + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              x[j] = (nb + j < e.N) ? __uint_as_float(r[j]) + __ldg(e.bias1 + min(nb + j, e.N - 1)) : -INFINITY;
+              m = fmaxf(m, x[j]);
+            }
           }
           if (row < e.M) {
             const long long t = e.ce_tgt[row];
@@ -312,25 +322,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* pp = e.ce_part + (row * e.ce_chunks + (nb >> 5)) * 2;
             pp[0] = m;
             pp[1] = ssum;
-            __nv_bfloat16* er = e.ce_e16 + row * e.ld_ce + nb;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 t2;
-                t2 = __floats2bfloat162_rn(x[j], x[j + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t2);
-                t2 = __floats2bfloat162_rn(x[j + 2], x[j + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
-                t2 = __floats2bfloat162_rn(x[j + 4], x[j + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                t2 = __floats2bfloat162_rn(x[j + 6], x[j + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
-                *reinterpret_cast<uint4*>(er + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < e.N) er[j] = __float2bfloat16(x[j]);
-            }
           }
-          continue;
+          // the exponentials leave through the common store path below (smem transpose -> coalesced bf16 rows of D16 = ce_e16):
+          // one 16-byte store per lane and 8 columns touched half a sector in 32 different rows per instruction
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(x[j]);
         } else if constexpr (PM == 2) {    // maxima only, one per 16 columns: layout [M, ceil(N / 16)] (the caller recomputes the tiles that
                                     // matter itself: vocab_refine.cu).  The (value, index) scan below costs ~17 instructions per
                                     // element and bounded the single-pass contraction at 6 us per tile
@@ -371,7 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         const int n = nb + c4;
         float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((e.bias1 || e.bias2) && first_split) {
+        if (PM != 3 && (e.bias1 || e.bias2) && first_split) {      // (PM == 3: the bias is already inside the exponentials)
           float bb[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -489,6 +485,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
     e.kcut_n0 = g.kcut_n0;
     e.kcut_nkb = ceil_div(g.kcut_cols, 128 / ES);
   }
+  if (PM == 3) { e.D16 = g.ce_e16; e.ldd16 = g.ld_ce; }      // the exponentials take the bf16 output path
   e.ce_e16 = g.ce_e16; e.ld_ce = g.ld_ce; e.ce_part = g.ce_part; e.ce_chunks = g.ce_chunks; e.ce_tgt = g.ce_tgt; e.ce_xt = g.ce_xt;
   e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = PM == 2 ? ceil_div(g.N, 16) : ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
   constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;

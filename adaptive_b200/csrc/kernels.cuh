@@ -71,11 +71,12 @@ int launch_ce_fwd_bwd(const float* logits, long long ld, const long long* tgt, i
 int launch_scale_unless_one(float* x, const float* g, long long n, cudaStream_t s, __nv_bfloat16* x16 = nullptr);
 // fused cross-entropy (see TcGemmArgs::ce_*): merge the chunk partials of every row into its log-sum-exp, add the row's loss term
 // to *loss, and leave scale[row * chunks + chunk] = exp(m_chunk - lse) / denom ...
-int launch_scale_bf16_unless_one(__nv_bfloat16* x, const float* g, long long n, cudaStream_t s);
+// x[0:n] (bf16) *= *g and y[0:ny] (fp32) *= *g unless *g == 1 (decided on the device)
+int launch_scale_bf16_unless_one(__nv_bfloat16* x, const float* g, long long n, float* y, long long ny, cudaStream_t s);
 int launch_ce_merge(const float* part, int chunks, int n_rows, const float* xt, long long denom, float* loss, float* scale, cudaStream_t s);
 // ... then dlogits (bf16, in place over e) = e * scale - onehot / denom, and the bias gradient dbp[j] = sum over rows (dbp pre-zeroed)
 int launch_ce_fixup(__nv_bfloat16* e16, long long ld, int n_rows, int Vc, const float* scale, int chunks, const long long* tgt, long long denom,
-                    float* dbp, cudaStream_t s);
+                    float* dbp, cudaStream_t s, const float* loss_acc = nullptr, float* loss_out = nullptr);   // (*loss_out = *loss_acc on the way)
 // zero-fill of up to 8 buffers in one launch (null / empty entries are skipped)
 int launch_zero_multi(int nsegs, void* const* dst, const long long* bytes, cudaStream_t s);
 // up to 8 device-to-device copies in one launch

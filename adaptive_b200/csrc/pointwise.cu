@@ -677,24 +677,39 @@ __global__ void __launch_bounds__(PW_THREADS) ce_merge_kernel(const float* __res
 // CE_RB rows); a thread owns two adjacent columns.
 constexpr int CE_RB = 32;
 __global__ void __launch_bounds__(PW_THREADS) ce_fixup_kernel(bf16* __restrict__ e16, long long ld, int n_rows, int Vc, const float* __restrict__ scale,
-                                                              int chunks, const long long* __restrict__ tgt, float inv_n, float* __restrict__ dbp) {
+                                                              int chunks, const long long* __restrict__ tgt, float inv_n, float* __restrict__ dbp,
+                                                              const float* __restrict__ loss_acc, float* __restrict__ loss_out) {
+  if (loss_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *loss_out = *loss_acc;      // (ce_merge finished before this launch)
   const int j = (blockIdx.x * PW_THREADS + threadIdx.x) * 2;
   if (j >= Vc) return;
   const int r0 = blockIdx.y * CE_RB, r1 = min(n_rows, r0 + CE_RB);
   const int c = j >> 5;
   float s0 = 0.f, s1 = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(e16 + (long long)r * ld + j);
-    const float2 v = __bfloat1622float2(*p);
-    const float f = __ldg(scale + (long long)r * chunks + c);
-    const long long t = __ldg(tgt + r);
-    float d0 = v.x * f, d1 = v.y * f;
-    if (t == j) d0 -= inv_n;
-    if (t == j + 1) d1 -= inv_n;
-    if (j + 1 >= Vc) d1 = 0.f;
-    *p = __floats2bfloat162_rn(d0, d1);
-    s0 += d0;
-    s1 += d1;
+  constexpr int U = 8;       // rows in flight per thread
+  for (int rb = r0; rb < r1; rb += U) {
+    __nv_bfloat162 v[U];
+    float f[U];
+    long long t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = min(rb + u, r1 - 1);
+      v[u] = *reinterpret_cast<const __nv_bfloat162*>(e16 + (long long)r * ld + j);
+      f[u] = __ldg(scale + (long long)r * chunks + c);
+      t[u] = __ldg(tgt + r);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (rb + u < r1) {
+        const float2 x = __bfloat1622float2(v[u]);
+        float d0 = x.x * f[u], d1 = x.y * f[u];
+        if (t[u] == j) d0 -= inv_n;
+        if (t[u] == j + 1) d1 -= inv_n;
+        if (j + 1 >= Vc) d1 = 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(e16 + (long long)(rb + u) * ld + j) = __floats2bfloat162_rn(d0, d1);
+        s0 += d0;
+        s1 += d1;
+      }
+    }
   }
   atomicAdd(dbp + j, s0);
   if (j + 1 < Vc) atomicAdd(dbp + j + 1, s1);
@@ -702,7 +717,7 @@ __global__ void __launch_bounds__(PW_THREADS) ce_fixup_kernel(bf16* __restrict__
 }  // namespace
 
 namespace {
-__global__ void scale_bf16_unless_one_kernel(bf16* __restrict__ x, const float* __restrict__ g, long long n2) {
+__global__ void scale_bf16_unless_one_kernel(bf16* __restrict__ x, const float* __restrict__ g, long long n2, float* __restrict__ y, long long ny) {
   const float f = *g;
   if (f == 1.f) return;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
@@ -710,15 +725,17 @@ __global__ void scale_bf16_unless_one_kernel(bf16* __restrict__ x, const float* 
     const float2 v = __bfloat1622float2(*p);
     *p = __floats2bfloat162_rn(v.x * f, v.y * f);
   }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ny; i += (long long)gridDim.x * blockDim.x) y[i] *= f;
 }
 }  // namespace
 
-int launch_scale_bf16_unless_one(__nv_bfloat16* x, const float* g, long long n, cudaStream_t s) {
-  if (n == 0) return AA_OK;
+int launch_scale_bf16_unless_one(__nv_bfloat16* x, const float* g, long long n, float* y, long long ny, cudaStream_t s) {
+  if (n == 0 && ny == 0) return AA_OK;
   AA_REQUIRE(n % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0, "scale_bf16: even length and 4-byte alignment needed");
   long long nb = (n / 2 + PW_THREADS * 4 - 1) / (PW_THREADS * 4);
   nb = nb > 1184 ? 1184 : nb;
-  scale_bf16_unless_one_kernel<<<(unsigned)nb, PW_THREADS, 0, s>>>(x, g, n / 2);
+  if (nb < 1) nb = 1;
+  scale_bf16_unless_one_kernel<<<(unsigned)nb, PW_THREADS, 0, s>>>(x, g, n / 2, y, ny);
   AA_CHECK_LAUNCH("scale_bf16_unless_one");
   return AA_OK;
 }
@@ -732,11 +749,11 @@ int launch_ce_merge(const float* part, int chunks, int n_rows, const float* xt, 
 }
 
 int launch_ce_fixup(__nv_bfloat16* e16, long long ld, int n_rows, int Vc, const float* scale, int chunks, const long long* tgt, long long denom,
-                    float* dbp, cudaStream_t s) {
+                    float* dbp, cudaStream_t s, const float* loss_acc, float* loss_out) {
   if (n_rows == 0) return AA_OK;
   AA_REQUIRE(ld % 2 == 0 && (reinterpret_cast<uintptr_t>(e16) & 3) == 0, "ce_fixup: bf16 rows must be 4-byte aligned");
   const float inv_n = 1.f / (float)(denom > 0 ? denom : n_rows);
-  ce_fixup_kernel<<<dim3(ceil_div(Vc, 2 * PW_THREADS), ceil_div(n_rows, CE_RB)), PW_THREADS, 0, s>>>(e16, ld, n_rows, Vc, scale, chunks, tgt, inv_n, dbp);
+  ce_fixup_kernel<<<dim3(ceil_div(Vc, 2 * PW_THREADS), ceil_div(n_rows, CE_RB)), PW_THREADS, 0, s>>>(e16, ld, n_rows, Vc, scale, chunks, tgt, inv_n, dbp, loss_acc, loss_out);
   AA_CHECK_LAUNCH("ce_fixup");
   return AA_OK;
 }

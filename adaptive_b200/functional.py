@@ -8,6 +8,7 @@ test infrastructure).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -351,6 +352,20 @@ class _DecoderLossFn(torch.autograd.Function):
                                                  _ptr(dV), _ptr(dvg), _ptr(dh0), _ptr(dc0), _ptr(scratch), sbytes, _stream(dev), None, None,
                                                  None, None), "aa_decoder_backward_packed")
         return (None, None, dV, dvg, None, dh0, dc0, None, None) + tuple(grads)
+
+
+L2_BYTES = 96 << 20      # what of the 126 MB L2 a [rows, Vc] fp32 tensor can count on next to the step's other operands
+
+
+def fused_loss_pays(n_rows: int, Vc: int) -> bool:
+    """Whether ``forward_loss`` takes the fused operator.  ``AA_FUSED_CE`` = 1 / 0 forces it on / off; by default it is taken
+    when the packed fp32 logits would not stay in L2: at config 2 (943 x 10 000 x 4 B = 38 MB) the two-step route's logits
+    never really leave the chip and its 13 us loss kernel beats the fused epilogue + merge + fix-up passes by ~10 us per step
+    (382.6 vs 371 us, profiles/r02_timeline_n1_fusedce_v2.txt); at config 5 (3 000 x 20 000 x 4 B = 240 MB) they do."""
+    mode = os.environ.get("AA_FUSED_CE", "auto")
+    if mode in ("0", "1"):
+        return mode == "1"
+    return int(n_rows) * int(Vc) * 4 > L2_BYTES
 
 
 def decoder_forward_loss(w: Sequence[torch.Tensor], V, v_g, captions, lengths: Sequence[int], targets=None, h0=None, c0=None,

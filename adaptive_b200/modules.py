@@ -239,12 +239,13 @@ class Encoder2Decoder(nn.Module):
 
     def forward_loss(self, images, captions, lengths, targets=None):
         """``criterion(self(images, captions, lengths).data, targets)`` of the reference's training loop (``train.py:205-208``,
-        ``nn.CrossEntropyLoss``) as ONE operator: on the bf16 tensor-core path the loss is fused into the vocabulary projection's
-        epilogue and the packed logits are never written; on the exact fp32 path it is the two-step route.
+        ``nn.CrossEntropyLoss``) as ONE operator: on the bf16 tensor-core path, when the packed logits would not stay in L2
+        (``functional.fused_loss_pays``), the loss is fused into the vocabulary projection's epilogue and the logits are never
+        written; otherwise, and on the exact fp32 path, it is the two-step route.
         ``targets`` defaults to the packed next words ``pack_padded_sequence(captions[:, 1:], lengths)`` (``train.py:102``)."""
         V, v_g, states = self._encode(images)
         h0, c0 = states if states is not None else (None, None)
-        if self.decoder.precision == "bf16" and V.shape[2] % 8 == 0:
+        if self.decoder.precision == "bf16" and V.shape[2] % 8 == 0 and F_aa.fused_loss_pays(sum(int(x) for x in lengths), self.decoder.embed.num_embeddings):
             return F_aa.decoder_forward_loss(self.decoder.weights(), V, v_g, captions, lengths, targets, h0, c0)[0]
         packed = self.forward((V, v_g, states), captions, lengths)
         if targets is None:

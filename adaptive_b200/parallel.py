@@ -478,7 +478,7 @@ class DataParallelTrainer:
             setattr(gs, name, t.data_ptr())
         with torch.cuda.device(self.device):
             # forward over the packed rows only (pack_padded_sequence fused, Q13), loss + its gradient in one pass, backward
-            fused = prec == _lib_mod.PREC_BF16 and os.environ.get("AA_FUSED_CE", "1") != "0"
+            fused = prec == _lib_mod.PREC_BF16 and F_aa.fused_loss_pays(n_rows, Vc)
             written = ctypes.c_int(0)
             if fused:      # the loss rides in the vocabulary projection's epilogue; the gradient of the logits stays inside `saved` (bf16)
                 check(lib.aa_decoder_forward_loss(ctypes.byref(d), ctypes.byref(ws), P(V), P(v_g), P(captions), P(h0), P(c0), P(row_index),

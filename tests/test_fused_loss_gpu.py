@@ -68,6 +68,16 @@ def test_fused_loss_vs_oracle_and_two_step_route(B, T, dims):
     assert not bad2, bad2
 
 
+def test_fused_route_is_chosen_by_size(monkeypatch):
+    monkeypatch.delenv("AA_FUSED_CE", raising=False)
+    assert not F_aa.fused_loss_pays(943, 10000)          # config 2: 38 MB of logits stay in L2
+    assert F_aa.fused_loss_pays(3000, 20000)             # config 5: 240 MB do not
+    monkeypatch.setenv("AA_FUSED_CE", "1")
+    assert F_aa.fused_loss_pays(10, 10)
+    monkeypatch.setenv("AA_FUSED_CE", "0")
+    assert not F_aa.fused_loss_pays(3000, 20000)
+
+
 def test_default_targets_upstream_scale_and_double_backward():
     dims, B, T = Dims(H=128, E=64, Vc=504, k=49), 9, 7
     w = make_weights(dims, seed=71, bias_scale=0.1)
@@ -78,9 +88,9 @@ def test_default_targets_upstream_scale_and_double_backward():
     l1 = F_aa.decoder_forward_loss(W1, V, v_g, cap, lengths, None, h0, c0)[0]                  # targets default to the packed next words
     tgt = torch.from_numpy(np.ascontiguousarray(F_aa.packed_targets(inp["captions"], lengths))).cuda()
     l2 = F_aa.decoder_forward_loss(W1, V, v_g, cap, lengths, tgt, h0, c0)[0]
-    assert torch.equal(l1, l2)
+    assert abs(l1.item() - l2.item()) < 1e-5 * abs(l2.item())      # (the row terms are summed with atomics: order varies)
     l1.backward()
-    with pytest.raises(RuntimeError, match="twice"):
+    with pytest.raises(RuntimeError, match="twice|second time"):
         l1.backward()
     # loss not the root: gradients scale with the upstream factor (decided on the device)
     W2 = dev_weights(w, requires_grad=True)
@@ -96,11 +106,12 @@ def test_default_targets_upstream_scale_and_double_backward():
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp32"])
-def test_module_forward_loss_and_graphed_step(prec):
+def test_module_forward_loss_and_graphed_step(prec, monkeypatch):
     """``Encoder2Decoder.forward_loss`` == criterion(forward(...).data, targets) of train.py:205-208 on both precisions, and the
     graphed training step (which goes through it) leaves the same gradients as the eager two-step route."""
     from adaptive_b200.graphs import GraphedTrainStep
 
+    monkeypatch.setenv("AA_FUSED_CE", "1")      # (by default small problems take the two-step route: functional.fused_loss_pays)
     dims, B, T = Dims(H=128, E=64, Vc=1000, k=49), 16, 8
 
     class Cf:
