@@ -302,10 +302,12 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_atten_kernel(const DecodeAt
     }
     {   // sentinel score z_s = w_h . tanh(r)
       float acc = 0.f;
-      if (j0 < a) acc = w0 * tanh_mufu(qr[a + j0]);
-      if (j1 < a) acc = fmaf(w1, tanh_mufu(qr[a + j1]), acc);
-      if (j2 < a) acc = fmaf(w2, tanh_mufu(qr[a + j2]), acc);
-      if (j3 < a) acc = fmaf(w3, tanh_mufu(qr[a + j3]), acc);
+      const float* rr = qr + (p.r_off ? p.r_off : a);
+      const float pq = p.r_partial ? 1.f : 0.f;       // r = r' + q when the row holds the sentinel's half alone
+      if (j0 < a) acc = w0 * tanh_mufu(rr[j0] + pq * q0);
+      if (j1 < a) acc = fmaf(w1, tanh_mufu(rr[j1] + pq * q1), acc);
+      if (j2 < a) acc = fmaf(w2, tanh_mufu(rr[j2] + pq * q2), acc);
+      if (j3 < a) acc = fmaf(w3, tanh_mufu(rr[j3] + pq * q3), acc);
       acc = warp_sum(acc);
       if (lane == 0) zs[k] = acc;
     }
@@ -561,9 +563,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dec_atten_tma_kernel(const Deco
 #pragma unroll 4
           for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanh_mufu(prow[jj] + qrow[jj]), acc);
         } else {              // z_s = w_h . tanh(r)                                      adaptive_attention.py:46-47
-          const float* rrow = qrow + a;
+          const float* rrow = qrow + (p.r_off ? p.r_off : a);
+          if (p.r_partial) {
 #pragma unroll 4
-          for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanh_mufu(rrow[jj]), acc);
+            for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanh_mufu(rrow[jj] + qrow[jj]), acc);
+          } else {
+#pragma unroll 4
+            for (int jj = sub; jj < a; jj += 4) acc = fmaf(whs[jj], tanh_mufu(rrow[jj]), acc);
+          }
         }
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -764,7 +771,7 @@ int launch_decode_atten(const DecodeAttenArgs& p, cudaStream_t s) {
   AA_REQUIRE(p.H % 4 == 0 && p.H <= 1024, "decode_atten: H must be a multiple of 4 and <= 1024 (got %d)", p.H);
   AA_REQUIRE(p.a <= 128 && p.k >= 1 && p.k <= 4096, "decode_atten: need a <= 128 and 1 <= k <= 4096");
   AA_REQUIRE(p.beam >= 1 && p.ld_u % 4 == 0 && p.u_lo_off % 4 == 0, "decode_atten: bad beam / u layout");
-  AA_REQUIRE(p.ldP >= p.a && p.ld_qr >= 2 * p.a && p.R % p.beam == 0, "decode_atten: bad P / qr strides or R not a multiple of beam");
+  AA_REQUIRE(p.ldP >= p.a && p.ld_qr >= (p.r_off ? p.r_off : p.a) + p.a && p.R % p.beam == 0, "decode_atten: bad P / qr strides or R not a multiple of beam");
   if (p.R == 0) return AA_OK;
   // bulk-copy pipeline whenever every streamed operand is 16-byte addressable and the shape fits shared memory
   const bool aligned = p.ldP % 4 == 0 && p.ld_qr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.V) & 15) == 0 &&

@@ -15,6 +15,7 @@ constexpr int END_ID = 2;    // build_vocab.py:48-51
 constexpr int MAX_BEAM = 8;
 int g_decode_table = [] { const char* e = getenv("AA_DECODE_TABLE"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_decode_table_min_rows = [] { const char* e = getenv("AA_DECODE_TABLE_MIN_ROWS"); return e ? atoi(e) : 0; }();
+int g_decode_qr_split = [] { const char* e = getenv("AA_DECODE_QR_SPLIT"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
 // filter-and-refine arg-max of the greedy vocabulary projection (vocab_refine.cu); AA_DECODE_REFINE=0 / aa_debug_set_decode_argmax_refine(0)
 // keep the fp32-accurate 3xTF32 contraction over the whole vocabulary
@@ -40,6 +41,7 @@ struct DecodeWs {
   // reads the [emb | h] window, the q/r GEMM the [h | s] window.  W2 = [[W_g, 0], [W_g, W_s]] gives [q | r] in one GEMM.
   float *Wp_s, *pmax, *W2, *hs, *qr; int* pidx;
   int split, bm, K, Kp, lo, K2p, Hp, ldA, ldU, tiles_n;
+  int qr_split;     // [q | r'] from two K = H tiles of one launch (needs a <= 64, H % 32 == 0)
   // filter-and-refine arg-max (vocab_refine.cu): 16-column partial tiles (`tiles16` of them), per-tile weight norms and candidate row lists
   int refine, tiles16; float* wnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
   __nv_bfloat16 *u16, *Wp16;
@@ -77,7 +79,8 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.tiles16 = ceil_div(d.Vc, gemm_tc_argmax_tile_n_plain(d.Vc));
   const size_t ptiles = w.refine ? (size_t)w.tiles16 : (size_t)w.tiles_n;
   w.ldP = w.split ? (d.a + 3) / 4 * 4 : d.a;
-  w.ld_qr = (2 * d.a + 3) / 4 * 4;
+  w.qr_split = (w.split && d.a <= 64 && H % 32 == 0 && g_decode_qr_split) ? 1 : 0;
+  w.ld_qr = w.qr_split ? 128 : (2 * d.a + 3) / 4 * 4;
   // (building the table costs one [Vc x 5H x E] contraction per call, ~0.1 ms at cfgA: repaid from ~1k rows on; taken for every
   //  batch size all the same, so that a shard of a batch decodes bit-identically to the whole -- AA_DECODE_TABLE_MIN_ROWS overrides)
   w.table = (w.split && !bm && g_decode_table && R >= (size_t)g_decode_table_min_rows) ? 1 : 0;
@@ -87,7 +90,7 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.Whh_s = c.take<float>(w.table ? (size_t)4 * H * 2 * w.Hp : 0);
   w.emb_s = c.take<float>(w.table ? (size_t)d.Vc * 2 * w.Ep : 0);
   w.wxe_s = c.take<float>(w.table ? (size_t)5 * H * 2 * w.Ep : 0);
-  w.W2 = c.take<float>(w.split ? (size_t)2 * d.a * 2 * w.K2p : 0);
+  w.W2 = c.take<float>(w.split ? (w.qr_split ? (size_t)(64 + d.a) * 2 * w.Hp : (size_t)2 * d.a * 2 * w.K2p) : 0);
   w.hs = c.take<float>(w.split ? R * 2 * H : 0);
   w.qr = c.take<float>(w.split ? R * w.ld_qr : 0);
   w.P = c.take<float>(B * d.k * w.ldP);
@@ -145,6 +148,21 @@ __global__ void pack_wcat_kernel(const float* __restrict__ w_ih, const float* __
     } else {
       dst[c] = v;
     }
+  }
+}
+
+// W2s [64 + a, 2*Hp] (tf32 hi | lo): row j < a = W_g[j], rows a..63 zero, row 64 + j = W_s[j]: with the A window of the second
+// 64-column tile shifted from h to s (TcGemmArgs::ashift_*) one launch gives [q | r'] = [h W_g^T | s W_s^T] with K = H per tile
+// instead of K = 2H against a zero block; the attention kernel adds q to r'
+__global__ void pack_wqr_split_kernel(const float* __restrict__ Wg, const float* __restrict__ Ws, float* __restrict__ W2, int a, int H, int Hp) {
+  const int n = blockIdx.x;                      // 0 .. 64 + a
+  const float* src = n < a ? Wg + (long long)n * H : (n >= 64 && Ws) ? Ws + (long long)(n - 64) * H : nullptr;
+  float* dst = W2 + (long long)n * 2 * Hp;
+  for (int c = threadIdx.x; c < Hp; c += blockDim.x) {
+    float hi = 0.f, lo = 0.f;
+    if (src && c < H) split_tf32(src[c], hi, lo);
+    dst[c] = hi;
+    dst[Hp + c] = lo;
   }
 }
 
@@ -420,7 +438,8 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
       if (ws.refine == 2) AA_TRY(launch_cast2d(w.mlp_w, H, ws.Wp16, H, d.Vc, H, st));
       AA_CHECK_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)(ws.tiles16 + 1), st));
     }
-    pack_wqr_kernel<<<2 * d.a, 256, 0, st>>>(w.att_wg, w.att_ws, ws.W2, d.a, H, ws.K2p);
+    if (ws.qr_split) pack_wqr_split_kernel<<<64 + d.a, 256, 0, st>>>(w.att_wg, w.att_ws, ws.W2, d.a, H, ws.Hp);
+    else pack_wqr_kernel<<<2 * d.a, 256, 0, st>>>(w.att_wg, w.att_ws, ws.W2, d.a, H, ws.K2p);
     AA_CHECK_LAUNCH("pack_wqr");
     // the operand windows read past the columns they need (up to a multiple of 32, against zero weight columns):
     // everything they can touch must be finite from the start, and the pad columns stay zero for the whole decode
@@ -428,7 +447,7 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
     if (ws.bm) AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat2, 0, sizeof(float) * (size_t)R * ws.ldA, st));
     if (ws.Hp != H) AA_CHECK_CUDA(cudaMemsetAsync(ws.u, 0, sizeof(float) * (size_t)R * ws.ldU, st));
   }
-  if (ws.split && (ws.ldP != d.a || ws.ld_qr != 2 * d.a)) {   // pad columns are streamed into shared memory with their rows (never read): keep them finite
+  if (ws.split && (ws.ldP != d.a || ws.ld_qr != 2 * d.a || ws.qr_split)) {   // pad columns are streamed into shared memory with their rows (never read): keep them finite
     AA_CHECK_CUDA(cudaMemsetAsync(ws.P, 0, sizeof(float) * (size_t)B * d.k * ws.ldP, st));
     AA_CHECK_CUDA(cudaMemsetAsync(ws.qr, 0, sizeof(float) * (size_t)R * ws.ld_qr, st));
   }
@@ -494,11 +513,21 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
   if (ws.table) { cp.EG = ws.EG; cp.stat = ws.stat; cp.prev_ids = prev_ids; cp.ld_ids = ld_ids; cp.start_id = START_ID; }
   AA_PROF("dec_cell", st, launch_decode_cell(cp, st));
   // [q | r] = [h | s] W2^T                                                              adaptive_attention.py:35,45
-  AA_PROF("dec_qr_gemm", st, dec_gemm(ws, R, 2 * d.a, 2 * H, ws.K2p, Acur + E, ws.ldA, ws.lo, ws.ldA - E, ws.W2, 2 * ws.K2p, ws.qr,
-                                      ws.ld_qr, nullptr, 0, nullptr, nullptr, nullptr, st));
+  if (ws.qr_split) {      // [q | r'] = [h W_g^T | s W_s^T]: two 64-column tiles, K = H each, the second one reading the s window of the rows
+    aa::ProfScope ps("dec_qr_gemm", st);
+    TcGemmArgs g{};
+    g.M = R; g.N = 64 + d.a; g.K = ws.Hp; g.elem_size = 4; g.split3 = 1;
+    g.A = Acur + E; g.lda = ws.ldA; g.lo_a = ws.lo; g.a_cols = ws.ldA - E; g.B = ws.W2; g.ldb = 2 * ws.Hp;
+    g.D32 = ws.qr; g.ldd32 = ws.ld_qr; g.beta = 1.f;
+    g.ashift_n0 = 64; g.ashift_cols = H;
+    AA_TRY(launch_gemm_tc(g, st));
+  } else {
+    AA_PROF("dec_qr_gemm", st, dec_gemm(ws, R, 2 * d.a, 2 * H, ws.K2p, Acur + E, ws.ldA, ws.lo, ws.ldA - E, ws.W2, 2 * ws.K2p, ws.qr,
+                                        ws.ld_qr, nullptr, 0, nullptr, nullptr, nullptr, st));
+  }
   DecodeAttenArgs ap{};
   ap.R = R; ap.k = d.k; ap.a = d.a; ap.H = H; ap.beam = beam;
-  ap.qr = ws.qr; ap.ld_qr = ws.ld_qr; ap.hs = ws.hs; ap.P = ws.P; ap.ldP = ws.ldP; ap.V = V; ap.wh = w.att_wh;
+  ap.qr = ws.qr; ap.ld_qr = ws.ld_qr; ap.r_off = ws.qr_split ? 64 : 0; ap.r_partial = ws.qr_split; ap.hs = ws.hs; ap.P = ws.P; ap.ldP = ws.ldP; ap.V = V; ap.wh = w.att_wh;
   ap.force_simple = g_force_simple_atten;
   ap.no_sentinel = w.att_ws == nullptr;     // baseline model (baseline_attention.py:79-100): beta = 0
   ap.alpha = alpha; ap.ld_alpha = ld_alpha; ap.beta = beta; ap.ld_beta = ld_beta;

@@ -83,6 +83,7 @@ struct TcEpilogue {
   int lo_a, lo_b;                           // split mode: column offset of the lo half inside a row of A / B
   int ksplit, kb_per;                       // split-K: work unit = (tile, K range of kb_per k-blocks); partial tiles are added with red.global.add
   int kcut_n0, kcut_nkb;                    // tiles whose first column is >= kcut_n0 stop after kcut_nkb k-blocks (their B rows are zero beyond)
+  int ashift_n0, ashift_cols;               // split mode: tiles whose first column is >= ashift_n0 read A ashift_cols columns further in
   __nv_bfloat16* ce_e16; long long ld_ce; float* ce_part; int ce_chunks; const long long* ce_tgt; float* ce_xt;   // PM == 3 (TcGemmArgs::ce_*)
 };
 
@@ -172,8 +173,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* a_dst = sA + s * A_STAGE;
           uint8_t* b_dst = sB + s * B_STAGE;
           if constexpr (SPLIT) {      // hi halves at column kb*BK, lo halves at column K + kb*BK of the same arrays
-            tma_load_2d(a_dst, &tmA, kb * BK, m0, &full_bar[s]);
-            tma_load_2d(a_dst + A_BYTES, &tmA, e.lo_a + kb * BK, m0, &full_bar[s]);
+            const int ash = n0 >= e.ashift_n0 ? e.ashift_cols : 0;
+            tma_load_2d(a_dst, &tmA, kb * BK + ash, m0, &full_bar[s]);
+            tma_load_2d(a_dst + A_BYTES, &tmA, e.lo_a + kb * BK + ash, m0, &full_bar[s]);
             tma_load_2d(b_dst, &tmB, kb * BK, n0, &full_bar[s]);
             tma_load_2d(b_dst + B_BYTES, &tmB, e.lo_b + kb * BK, n0, &full_bar[s]);
             continue;
@@ -481,6 +483,11 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int EW = epi_warps(SPLIT);
   constexpr int NPARTS = (EW / 4) < (BN / 32) ? (EW / 4) : (BN / 32);
   e.kcut_n0 = 0x7fffffff; e.kcut_nkb = 0;
+  e.ashift_n0 = 0x7fffffff; e.ashift_cols = 0;
+  if (SPLIT && g.ashift_cols > 0) {
+    AA_REQUIRE(g.ashift_n0 % BN == 0, "tcgen05 GEMM: the A-window shift must start on a tile boundary (%d %% %d)", g.ashift_n0, BN);
+    e.ashift_n0 = g.ashift_n0; e.ashift_cols = g.ashift_cols;
+  }
   if (g.kcut_cols > 0 && g.kcut_n0 % BN == 0 && g.kcut_n0 < g.N) {     // (only when the cut falls on a tile boundary of this configuration)
     e.kcut_n0 = g.kcut_n0;
     e.kcut_nkb = ceil_div(g.kcut_cols, 128 / ES);
@@ -598,6 +605,7 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
     // (256-column tiles -- 128 cycles per MMA for twice the columns -- were measured SLOWER here: only two 96 KB stages fit
     //  and the TMA feed, ~50 B/clk per SM, becomes the bound: vocabulary GEMM 224 us against 205 us, r01_v33)
     if (g.pmax) return g.N > 64 ? launch_cfg<128, 4, 3, false, false, true, 1>(g, st) : launch_cfg<64, 4, 4, false, false, true, 1>(g, st);
+    if (g.ashift_cols > 0) return launch_cfg<64, 4, 4, false, false, true>(g, st);
     if (g.N > 64) return launch_cfg<128, 4, 3, false, false, true>(g, st);
     return launch_cfg<64, 4, 4, false, false, true>(g, st);
   }

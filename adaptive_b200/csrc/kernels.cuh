@@ -109,6 +109,10 @@ struct TcGemmArgs {
   // optional: the rows n >= kcut_n0 of B are zero beyond their first kcut_cols reduction columns (per half in split mode): output
   // tiles starting at or after kcut_n0 stop their K loop there.  Ignored unless kcut_n0 is a multiple of the tile width; no split-K.
   int kcut_n0, kcut_cols;
+  // optional (split3 only): output tiles starting at or after column ashift_n0 read their A operand ashift_cols columns further into
+  // the row (both halves) -- two contractions over different column windows of the same operand rows in one launch, e.g.
+  // [q | r'] = [h W_g^T | s W_s^T] from rows [h | s].  Needs ashift_n0 to be a multiple of the tile width (forces 64-column tiles).
+  int ashift_n0, ashift_cols;
   // optional (plain bf16, K-major): cross-entropy pieces instead of the logits (train.py:63,208 fused into the vocabulary projection's
   // epilogue; D32 / D16 null).  Per row and 32-column chunk of D (+ bias1): the chunk maximum m and s = sum exp(x - m) go to
   // ce_part[(row * ce_chunks + chunk) * 2 + {0, 1}], e = exp(x - m) as bf16 to ce_e16[row * ld_ce + col], and the target column's
@@ -240,6 +244,7 @@ int launch_decode_cell(const DecodeCellArgs& p, cudaStream_t s);
 struct DecodeAttenArgs {
   int R, k, a, H, beam;       // R rows; V/P row = r / beam
   const float* qr; long long ld_qr;   // [R, ld_qr >= 2a] = [q | r]   (q = h W_g^T, r = s W_s^T + q)
+  int r_off, r_partial;               // r starts r_off columns into a row (0 = a); r_partial != 0: the row holds r' = s W_s^T, r = r' + q
   const float* hs;            // [R,2H] = [h | s]
   const float *P, *V, *wh;    // [R/beam,k,ldP >= a], [R/beam,k,H], [a]
   long long ldP;              // row stride of P (a multiple of 4 enables the bulk-copy pipeline)
