@@ -18,7 +18,11 @@ class GraphedTrainStep:
     """``step(batch) -> loss`` with gradients left in ``p.grad`` of ``model.decoder`` parameters.
 
     ``batch`` is a dict of device tensors ``V, v_g, h0, c0, captions, tgt`` (``tgt`` = packed
-    targets); its values are copied into static buffers before each replay."""
+    targets); its values are copied into static buffers before each replay.
+
+    Construct it while no autograd graph of an earlier EAGER step over the same parameters is still alive (a kept ``loss`` /
+    ``packed`` tensor): torch reuses such a graph's AccumulateGrad nodes, which stay bound to the stream they were created on,
+    and the capture (on its own stream) is then invalidated by the synchronisation with that stream."""
 
     KEYS = ("V", "v_g", "h0", "c0", "captions", "tgt")
 
