@@ -43,7 +43,7 @@ struct DecodeWs {
   int split, bm, K, Kp, lo, K2p, Hp, ldA, ldU, tiles_n;
   int qr_split;     // [q | r'] from two K = H tiles of one launch (needs a <= 64, H % 32 == 0)
   // filter-and-refine arg-max (vocab_refine.cu): 16-column partial tiles (`tiles16` of them), per-tile weight norms and candidate row lists
-  int refine, tiles16; float* wnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
+  int refine, tiles16; float *wnorm, *dwnorm; int *counts, *ncand; unsigned* list;   // refine: 0 = off, 1 = tf32 first pass, 2 = bf16 first pass
   __nv_bfloat16 *u16, *Wp16;
   // table mode (greedy, tensor-core pipeline, large batches): EG [Vc,5H] = embed . [W_ih[:, :E]; W_x[:, :E]]^T takes the word's half of
   // the gate contraction out of the loop (K = E+H -> H, N = 5H -> 4H: the sentinel block has no recurrent half in decode mode, Q3)
@@ -104,6 +104,7 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.pmax = c.take<float>((w.split && !bm) ? R * ptiles : 0);
   w.pidx = c.take<int>((w.split && !bm) ? R * ptiles : 0);
   w.wnorm = c.take<float>(w.refine ? w.tiles16 : 0);
+  w.dwnorm = c.take<float>(w.refine == 2 ? w.tiles16 : 0);
   w.counts = c.take<int>(w.refine ? w.tiles16 + 1 : 0);      // (+ 1: finished-CTA ticket of the refinement kernel)
   w.list = c.take<unsigned>(w.refine ? (size_t)w.tiles16 * R : 0);
   w.ncand = c.take<int>(w.refine ? R : 0);
@@ -434,7 +435,7 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
   if (ws.split) {
     AA_TRY(launch_split_tf32(w.mlp_w, H, d.Vc, H, ws.Wp_s, ws.Hp, st));
     if (ws.refine) {
-      AA_TRY(launch_tile_wnorm(w.mlp_w, d.Vc, H, ws.wnorm, st));
+      AA_TRY(launch_tile_wnorm(w.mlp_w, d.Vc, H, ws.wnorm, st, ws.refine == 2 ? ws.dwnorm : nullptr));
       if (ws.refine == 2) AA_TRY(launch_cast2d(w.mlp_w, H, ws.Wp16, H, d.Vc, H, st));
       AA_CHECK_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)(ws.tiles16 + 1), st));
     }
@@ -540,7 +541,7 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
 // ---- persistent variant (decode_persist.cu): workspace = [weight-derived region | per-call region] ----
 struct PersistWs {
   // weight-derived (reusable across calls while the weights do not change)
-  float* Whh; __nv_bfloat16* Wp16; float* wn; float* EG;
+  float* Whh; __nv_bfloat16* Wp16; float *wn, *dwn; float* EG;
   // per call
   float *P, *stat, *hA, *c, *part1, *approx; __nv_bfloat16* u16; unsigned* bar;
   int Kp, ldA, ldP, ldv, ks_max;
@@ -559,6 +560,7 @@ PersistWs carve_persist(const aa_dims& d, void* base) {
   w.Whh = c.take<float>((size_t)4 * H * 2 * w.Kp);
   w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>((size_t)d.Vc * H));
   w.wn = c.take<float>((size_t)w.ldv);
+  w.dwn = c.take<float>((size_t)w.ldv);
   w.EG = c.take<float>((size_t)d.Vc * 5 * H);
   w.P = c.take<float>(B * d.k * w.ldP);
   w.stat = c.take<float>(B * 5 * H);
@@ -640,8 +642,9 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
         // arg-max only: ONE tf32 pass over the hi halves with per-64-column maxima, then exact fp32 logits for the few (row, tile)
         // pairs that can hold the maximum (vocab_refine.cu).  c = 1.1 * 2^-10: two tf32 roundings per product (2^-11 each) and
         // an allowance of 2^-13.3 for the fp32 accumulation of the tensor pipe, relative to ||u|| ||W_j||.
-        // (bf16 first pass: 8 significant bits, round-to-nearest unit roundoff 2^-8 per operand -> two roundings per product
-        // 2^-7 (1 + 2^-9); c = 2.1 * 2^-8 leaves 5 % for the fp32 accumulation; operands = the bf16 mirrors of u and W_p)
+        // (bf16 first pass, operands = the bf16 mirrors of u and W_p: the worst-case relative bound would be 2.1 * 2^-8 -- 8 significant
+        // bits, unit roundoff 2^-8 per operand -- ; the filter uses the exact decomposition u.W - u^.W^ = u^.(W - W^) + (u - u^).W with
+        // the norms of the ACTUAL residuals instead, ~2.3x tighter on real data and just as rigorous: vocab_refine.cu)
         TcGemmArgs g{};
         g.M = B; g.N = Vc;
         if (ws.refine == 2) {
@@ -652,7 +655,8 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
         g.bias1 = w->mlp_b; g.pmax = ws.pmax; g.pidx = nullptr;     // (maxima only: the refinement writes the indices of the tiles that matter)
         AA_PROF("dec_vocab_gemm1", st, launch_gemm_tc(g, st));
         AA_PROF("dec_argmax_filter", st, launch_argmax_filter(ws.pmax, ws.tiles16, B, ws.u, ws.ldU, ws.Hp, H, ws.wnorm,
-                                                              ws.refine == 2 ? 2.1f / 256.f : 1.1f / 1024.f, ws.counts, ws.list, ws.ncand, st));
+                                                              1.1f / 1024.f, ws.counts, ws.list, ws.ncand, st,
+                                                              ws.refine == 2 ? ws.u16 : nullptr, H, ws.refine == 2 ? ws.dwnorm : nullptr));
         AA_PROF("dec_argmax_refine", st, launch_argmax_refine(w->mlp_w, w->mlp_b, Vc, H, ws.u, ws.ldU, ws.Hp, B, ws.counts, ws.list,
                                                               ws.pmax, ws.pidx, ws.tiles16, st));
         AA_PROF("dec_argmax", st, launch_argmax_finalize(ws.pmax, ws.pidx, ws.tiles16, B, ids_t, L, w->embed, E, emb_dst, ws.ldA, 1,
@@ -708,7 +712,7 @@ int aa_decode_persistent(const aa_dims* d, const aa_weights* w, const float* V, 
   if (!(flags & AA_DECODE_REUSE_PACKED_WEIGHTS)) {     // weight-derived operands: once per set of weights
     AA_TRY(launch_split_tf32(w->w_hh, H, 4 * H, H, ws.Whh, ws.Kp, st));
     AA_TRY(launch_cast2d(w->mlp_w, H, ws.Wp16, H, d->Vc, H, st));
-    AA_TRY(launch_row_norm(w->mlp_w, d->Vc, H, ws.wn, st));
+    AA_TRY(launch_row_norm(w->mlp_w, d->Vc, H, ws.wn, ws.dwn, st));
     // EG[v] = [W_ih[:, :E]; W_x[:, :E]] emb(v): the input half of the five gate blocks for every word, exact fp32
     AA_TRY(gemm_nt(d->Vc, 4 * H, E, w->embed, E, w->w_ih, 2 * E, ws.EG, 5 * H, nullptr, 0, nullptr, nullptr, st));
     if (w->sen_wx) AA_TRY(gemm_nt(d->Vc, H, E, w->embed, E, w->sen_wx, 2 * E, ws.EG + 4 * H, 5 * H, nullptr, 0, nullptr, nullptr, st));
@@ -726,9 +730,8 @@ int aa_decode_persistent(const aa_dims* d, const aa_weights* w, const float* V, 
   p.B = B; p.k = d->k; p.a = d->a; p.H = H; p.E = E; p.Vc = d->Vc; p.L = L;
   p.K1p = ws.Kp; p.lo1 = ws.Kp; p.ldA = ws.ldA; p.ldP = ws.ldP; p.ldv = ws.ldv; p.ks1_max = ws.ks_max; p.start_id = START_ID;
   p.V = V; p.P = ws.P; p.stat = ws.stat; p.c0 = ws.c; p.EG = ws.EG; p.hA = ws.hA; p.part1 = ws.part1; p.u16 = ws.u16; p.approx = ws.approx;
-  p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh; p.Wp = w->mlp_w; p.bp = w->mlp_b; p.wn = ws.wn;
+  p.Wg = w->att_wg; p.Ws = w->att_ws; p.wh = w->att_wh; p.Wp = w->mlp_w; p.bp = w->mlp_b; p.wn = ws.wn; p.dwn = ws.dwn;
   p.ids = reinterpret_cast<long long*>(ids); p.alpha = attention; p.beta = Beta; p.ncand_out = candidates_out; p.bar = ws.bar;
-  p.cbound = 2.1f / 256.f;      // bf16 first pass: see vocab_refine.cu
   AA_PROF("dec_persistent", st, launch_decode_persist(p, ws.Whh, ws.Wp16, st));
   return AA_OK;
 }

@@ -15,7 +15,8 @@
 //     is the per-image static term.  That removes the dependency of the gate contraction on the word just chosen: G1 of step
 //     t+1 only needs h_t and runs in the SAME phase as G2 of step t;
 //   * everything between is the owner CTA's business, in exact fp32 (FMA) arithmetic, one uninterrupted phase per step:
-//       O2(t)   filter-and-refine arg-max per COLUMN: with |approx_j - exact_j| <= c ||u|| ||W_j|| (vocab_refine.cu, c = 2.1 * 2^-8)
+//       O2(t)   filter-and-refine arg-max per COLUMN: with |approx_j - exact_j| <= ||u - u^|| ||W_j|| + ||u^|| ||W_j - W^_j|| (the exact
+//               decomposition of the two bf16 roundings, vocab_refine.cu)
 //               only columns with approx_j + bound_j >= max_j (approx_j - bound_j) can hold the maximum; those few are recomputed
 //               exactly from the fp32 u kept in shared memory, lowest index wins ties;
 //       O1(t+1) gates = EG[word] + static + K-split partials -> LSTM cell -> sentinel -> q / r mat-vecs -> scores, both softmaxes
@@ -493,24 +494,32 @@ dec_persist_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     // (g) c_hat = beta s + (1 - beta) ctx, u = c_hat + h                                          :54, :132
     {
       const float beta = z_s[k];
-      float ss = 0.f;
+      float ss = 0.f, sh = 0.f, sd = 0.f;
       for (int i = tid; i < H; i += PD_THREADS) {
         const float ctx = (cx_s[i] + cx_s[H + i]) + cx_s[2 * H + i];
         const float uu = beta * s_s[i] + (1.f - beta) * ctx + h_s[i];
+        const __nv_bfloat16 u16 = __float2bfloat16(uu);
+        const float uh = __bfloat162float(u16);
         sm.u[i] = uu;
-        p.u16[(size_t)b * H + i] = __float2bfloat16(uu);
+        p.u16[(size_t)b * H + i] = u16;
         ss = fmaf(uu, uu, ss);
+        sh = fmaf(uh, uh, sh);
+        sd = fmaf(uu - uh, uu - uh, sd);
       }
       ss = block_sum(ss, sm.red, tid);
-      if (tid == 0) sm.red[32] = sqrtf(ss) * (1.f + 1e-6f);      // ||u||, rounded up
+      sh = block_sum(sh, sm.red, tid);
+      sd = block_sum(sd, sm.red, tid);
+      if (tid == 0) {      // coefficients of the first pass's error bound  cw * ||W_j|| + cd * ||W_j - W^_j||  (vocab_refine.cu)
+        sm.red[32] = sqrtf(sd) * (1.f + 1e-5f) + 1.220703125e-4f * sqrtf(ss);      // ||u - u^|| + 2^-13 ||u||
+        sm.red[33] = sqrtf(sh) * (1.f + 1e-5f);                                      // ||u^||
+      }
     }
     __syncthreads();
   };
 
   // ---- O2: exact arg-max of the row by filter-and-refine; returns the chosen word (uniform over the CTA) ----
   auto owner_argmax = [&](int t) -> int {
-    const float unorm = sm.red[32];
-    const float cb = p.cbound * unorm;
+    const float cb = sm.red[32], cdb = sm.red[33];
     const float* arow = p.approx + (size_t)b * p.ldv;
     const int Vc = p.Vc;
     constexpr int NC = 8;                         // float4 groups a thread keeps in registers between the two passes
@@ -524,18 +533,18 @@ dec_persist_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       bv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j + 3 < Vc) {
         xv[c] = ldcg4(arow + j);
-        const float4 w = ldg4(p.wn + j);
-        bv[c] = make_float4(cb * w.x, cb * w.y, cb * w.z, cb * w.w);
+        const float4 w = ldg4(p.wn + j), dw = ldg4(p.dwn + j);
+        bv[c] = make_float4(cb * w.x + cdb * dw.x, cb * w.y + cdb * dw.y, cb * w.z + cdb * dw.z, cb * w.w + cdb * dw.w);
       } else if (j < Vc) {
         float xs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, ws[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int e = 0; e < 4 && j + e < Vc; ++e) { xs[e] = __ldcg(arow + j + e); ws[e] = cb * __ldg(p.wn + j + e); }
+        for (int e = 0; e < 4 && j + e < Vc; ++e) { xs[e] = __ldcg(arow + j + e); ws[e] = cb * __ldg(p.wn + j + e) + cdb * __ldg(p.dwn + j + e); }
         xv[c] = make_float4(xs[0], xs[1], xs[2], xs[3]);
         bv[c] = make_float4(ws[0], ws[1], ws[2], ws[3]);
       }
       lo = fmaxf(fmaxf(lo, xv[c].x - bv[c].x), fmaxf(xv[c].y - bv[c].y, fmaxf(xv[c].z - bv[c].z, xv[c].w - bv[c].w)));
     }
     for (int j = (NC * PD_THREADS + tid) * 4; j < Vc; j += PD_THREADS * 4)       // (vocabularies beyond NC * 1536 columns)
-      for (int e = 0; e < 4 && j + e < Vc; ++e) lo = fmaxf(lo, __ldcg(arow + j + e) - cb * __ldg(p.wn + j + e));
+      for (int e = 0; e < 4 && j + e < Vc; ++e) lo = fmaxf(lo, __ldcg(arow + j + e) - (cb * __ldg(p.wn + j + e) + cdb * __ldg(p.dwn + j + e)));
     if (tid == 0) *ncand = 0;
     const float Lb = block_max(lo, sm.red, tid);
     // pass 2: columns whose upper bound reaches L
@@ -553,7 +562,7 @@ dec_persist_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     }
     for (int j = (NC * PD_THREADS + tid) * 4; j < Vc; j += PD_THREADS * 4)
       for (int e = 0; e < 4 && j + e < Vc; ++e)
-        if (__ldcg(arow + j + e) + cb * __ldg(p.wn + j + e) >= Lb) {
+        if (__ldcg(arow + j + e) + (cb * __ldg(p.wn + j + e) + cdb * __ldg(p.dwn + j + e)) >= Lb) {
           const int slot = atomicAdd(ncand, 1);
           if (slot < PD_MAX_CAND) cand[slot] = j + e;
         }
@@ -625,18 +634,26 @@ dec_persist_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   }
 }
 
-// norms of the projection's rows, rounded up (once per set of weights): wn[j] = ||W_p[j, :]||_2
-__global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ wn) {
+// norms of the projection's rows and of their bf16 rounding residuals, rounded up (once per set of weights):
+// wn[j] = ||W_p[j, :]||_2, dwn[j] = ||W_p[j, :] - bf16(W_p[j, :])||_2 (the conversion of launch_cast2d)
+__global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ wn,
+                                                       float* __restrict__ dwn) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + warp;
   if (j >= rows) return;
-  float ss = 0.f;
+  float ss = 0.f, sd = 0.f;
   for (int c = lane; c < cols; c += 32) {
     const float x = __ldg(W + (size_t)j * cols + c);
+    const float dx = x - __bfloat162float(__float2bfloat16(x));
     ss = fmaf(x, x, ss);
+    sd = fmaf(dx, dx, sd);
   }
   ss = warp_sum(ss);
-  if (lane == 0) wn[j] = sqrtf(ss) * (1.f + 1e-6f);
+  sd = warp_sum(sd);
+  if (lane == 0) {
+    wn[j] = sqrtf(ss) * (1.f + 1e-5f);
+    dwn[j] = sqrtf(sd) * (1.f + 1e-5f);
+  }
 }
 
 size_t pd_smem_bytes(int NB, int k, int H, int ldP) {
@@ -667,8 +684,8 @@ int set_persist_trace_buffer(void* dev_ptr) {
   return AA_OK;
 }
 
-int launch_row_norm(const float* W, int rows, int cols, float* wn, cudaStream_t st) {
-  row_norm_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(W, rows, cols, wn);
+int launch_row_norm(const float* W, int rows, int cols, float* wn, float* dwn, cudaStream_t st) {
+  row_norm_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(W, rows, cols, wn, dwn);
   AA_CHECK_LAUNCH("row_norm");
   return AA_OK;
 }

@@ -128,12 +128,13 @@ int set_gemm_splitk(int on);   // diagnostics: 0 = never split K (deterministic 
 bool argmax_refine_supported(int Vc, int H);
 long long refine_pairs(int reset);   // diagnostics: (row, tile) pairs refined so far on the current device (synchronises)
 // wnorm[t] = max_j ||W[j,:]||_2 over the 16-column tile t of W [Vc,H] (tile width = gemm_tc_argmax_tile_n_plain)
-int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s);
+int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s, float* dwnorm = nullptr);   // dwnorm: norms of W - bf16(W) per tile
 // pmax [R, tiles]: approximate per-tile maxima (single-pass tensor-core contraction, |error_j| <= c ||u|| ||W_j||).  Every (row, tile)
 // pair whose tile can hold the row's exact arg-max is appended to list[t*R + counts[t]++] as row | slot << 20, slot = rank among
 // the row's candidates; ncand[row] = number of candidates  (u rows: hi at [0,H), lo at +lo_off)
 int launch_argmax_filter(const float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
-                         int* counts, unsigned* list, int* ncand, cudaStream_t s);
+                         int* counts, unsigned* list, int* ncand, cudaStream_t s, const __nv_bfloat16* u16 = nullptr, long long ld16 = 0,
+                         const float* dwnorm = nullptr);   // (u16, dwnorm: bf16 first pass -- exact-decomposition bound, see vocab_refine.cu)
 // exact fp32 (max, index) of every listed pair written to pmax / pidx[row * tiles + slot]; resets counts
 int launch_argmax_refine(const float* W, const float* bias, int Vc, int H, const float* u, long long ldu, long long lo_off, int R, int* counts,
                          const unsigned* list, float* pmax, int* pidx, int tiles, cudaStream_t s);
@@ -271,15 +272,14 @@ struct DecodePersistArgs {
   __nv_bfloat16* u16;               // [B, H] bf16 mirror of u (G2's operand)
   float* approx;                    // [B, ldv] approximate logits (bias included)
   const float *Wg, *Ws, *wh;        // attention weights (Ws == null: baseline model, beta = 0)
-  const float *Wp, *bp, *wn;        // vocabulary projection (fp32), its bias, its row norms
+  const float *Wp, *bp, *wn, *dwn;  // vocabulary projection (fp32), its bias, the norms of its rows and of their bf16 residuals
   long long* ids; float* alpha; float* beta;   // [B,L], [B,L,k], [B,L]
   int* ncand_out;                   // optional [B,L]: columns recomputed exactly (diagnostics)
   unsigned* bar;                    // grid barrier counter
-  float cbound;                     // c of |approx - exact| <= c ||u|| ||W_j||
 };
 bool decode_persist_supported(int B, int k, int a, int H, int E, int Vc);
 int decode_persist_nb(int B);
-int launch_row_norm(const float* W, int rows, int cols, float* wn, cudaStream_t s);
+int launch_row_norm(const float* W, int rows, int cols, float* wn, float* dwn, cudaStream_t s);   // row norms of W and of W - bf16(W)
 int set_persist_trace_buffer(void* dev_ptr);   // diagnostics: [steps][8] uint64 globaltimer stamps of CTA 0; null = off
 int launch_decode_persist(const DecodePersistArgs& p, const float* Whh_split, const __nv_bfloat16* Wp16, cudaStream_t s);
 

@@ -31,25 +31,31 @@ constexpr int RF_TN = 16;        // columns per tile = granularity of the first 
 
 __device__ unsigned long long d_refine_pairs = 0;    // diagnostics: (row, tile) pairs handed to the refinement so far
 
-// wnorm[t] = max_{j in tile t} ||W[j, :]||_2, rounded up   (once per decode call)
-__global__ void tile_wnorm_kernel(const float* __restrict__ W, int Vc, int H, int tile_n, float* __restrict__ wnorm) {
-  __shared__ float red[RF_WARPS];
+// wnorm[t] = max_{j in tile t} ||W[j, :]||_2 and (optional) dwnorm[t] = max_j ||W[j, :] - bf16(W[j, :])||_2, both rounded up
+// (once per decode call).  bf16() is the round-to-nearest-even conversion the bf16 mirror of W is made with (launch_cast2d).
+__global__ void tile_wnorm_kernel(const float* __restrict__ W, int Vc, int H, int tile_n, float* __restrict__ wnorm, float* __restrict__ dwnorm) {
+  __shared__ float red[RF_WARPS], redd[RF_WARPS];
   const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float best = 0.f;
+  float best = 0.f, bestd = 0.f;
   for (int j = t * tile_n + warp; j < min(Vc, (t + 1) * tile_n); j += RF_WARPS) {
-    float ss = 0.f;
+    float ss = 0.f, sd = 0.f;
     for (int k = lane; k < H; k += 32) {
       const float x = __ldg(W + (long long)j * H + k);
+      const float dx = x - __bfloat162float(__float2bfloat16(x));
       ss = fmaf(x, x, ss);
+      sd = fmaf(dx, dx, sd);
     }
     ss = warp_sum(ss);
+    sd = warp_sum(sd);
     best = fmaxf(best, ss);
+    bestd = fmaxf(bestd, sd);
   }
-  if (lane == 0) red[warp] = best;
+  if (lane == 0) { red[warp] = best; redd[warp] = bestd; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < RF_WARPS; ++i) best = fmaxf(best, red[i]);
-    wnorm[t] = sqrtf(best) * (1.f + 1e-6f);
+    for (int i = 1; i < RF_WARPS; ++i) { best = fmaxf(best, red[i]); bestd = fmaxf(bestd, redd[i]); }
+    wnorm[t] = sqrtf(best) * (1.f + 1e-5f);
+    if (dwnorm) dwnorm[t] = sqrtf(bestd) * (1.f + 1e-5f);
   }
 }
 
@@ -59,26 +65,36 @@ __global__ void tile_wnorm_kernel(const float* __restrict__ W, int Vc, int H, in
 // The positions in a tile's list come from ONE global atomic per (CTA, tile): most rows of a batch list the same tile (the word
 // most of them favour), and 4096 same-address atomics cost ~10 us.
 constexpr int FL_THREADS = 256, FL_ROWS = FL_THREADS / 32;      // one warp per row
+// Error bound of the first pass for row r and tile t:  cw[r] * wnorm[t] + cd[r] * dwnorm[t].
+//   tf32 first pass (u16 == null): cw = c ||u||, cd = 0 -- the relative bound of two tf32 roundings per product.
+//   bf16 first pass (u16, dwnorm given): the EXACT decomposition  u.W_j - u^.W^_j = u^.(W_j - W^_j) + (u - u^).W_j  with u^ = the bf16
+//   mirror the pass actually read and W^ = the bf16 mirror of the weights, bounded term by term with Cauchy-Schwarz:
+//   cd = ||u^||, cw = ||u - u^|| (+ 2^-13 ||u|| for the fp32 accumulation of the tensor pipe and the bias add).  Rigorous like the
+//   relative bound 2.1 * 2^-8 ||u|| ||W_j|| it replaces, but ~2.3x tighter on real data (rounding errors average to ulp / sqrt(12),
+//   they do not all sit at the half-ulp worst case).
 __global__ void __launch_bounds__(FL_THREADS) argmax_filter_kernel(const float* __restrict__ pmax, int tiles, int R, const float* __restrict__ u,
                                                                    long long ldu, long long lo_off, int H, const float* __restrict__ wnorm,
                                                                    float c, int* __restrict__ counts, unsigned* __restrict__ list,
-                                                                   int* __restrict__ ncand, int stage) {
+                                                                   int* __restrict__ ncand, int stage, const __nv_bfloat16* __restrict__ u16,
+                                                                   long long ld16, const float* __restrict__ dwnorm) {
   extern __shared__ int fsm[];
   int* scnt = fsm;                                              // [tiles] pairs this CTA lists per tile, then the running position inside the CTA's range
   float* wn = reinterpret_cast<float*>(fsm + tiles);            // [tiles] weight norms
+  float* dwn = wn + tiles;                                      // [tiles] norms of the weights' bf16 residuals (zero without dwnorm)
   __shared__ int spairs;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = blockIdx.x * FL_ROWS + warp;
   const bool live = r < R;
   // this warp's row of maxima is read three times: staged in shared memory when it fits (stage != 0), else re-read from L2
-  float* srow = wn + tiles + warp * tiles;
+  float* srow = dwn + tiles + warp * tiles;
   const float* prow = stage ? srow : pmax + (long long)(live ? r : 0) * tiles;
   for (int t = tid; t < tiles; t += FL_THREADS) {
     scnt[t] = 0;
     wn[t] = __ldg(wnorm + t);
+    dwn[t] = dwnorm ? __ldg(dwnorm + t) : 0.f;
   }
   if (tid == 0) spairs = 0;
-  float cn = 0.f, L = INFINITY;
+  float cn = 0.f, cd = 0.f, L = INFINITY;
   if (live) {
     if (stage) {
       const float* pr = pmax + (long long)r * tiles;
@@ -86,22 +102,36 @@ __global__ void __launch_bounds__(FL_THREADS) argmax_filter_kernel(const float* 
       for (int t = lane; t < tiles; t += 32) srow[t] = __ldcg(pr + t);
     }
     const float* ur = u + (long long)r * ldu;
-    float ss = 0.f;
+    float ss = 0.f, sh = 0.f, sd = 0.f;
     for (int k = lane * 4; k < H; k += 128) {
       const float4 hi = __ldcg(reinterpret_cast<const float4*>(ur + k)), lo = __ldcg(reinterpret_cast<const float4*>(ur + lo_off + k));
       const float x0 = hi.x + lo.x, x1 = hi.y + lo.y, x2 = hi.z + lo.z, x3 = hi.w + lo.w;
       ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+      if (u16) {      // the mirror the first pass actually contracted with (never re-derived: a second rounding could differ in the last place)
+        const uint2 pk = __ldcg(reinterpret_cast<const uint2*>(u16 + (long long)r * ld16 + k));
+        const float h0 = __uint_as_float(pk.x << 16), h1 = __uint_as_float(pk.x & 0xffff0000u);
+        const float h2 = __uint_as_float(pk.y << 16), h3 = __uint_as_float(pk.y & 0xffff0000u);
+        sh = fmaf(h0, h0, sh); sh = fmaf(h1, h1, sh); sh = fmaf(h2, h2, sh); sh = fmaf(h3, h3, sh);
+        const float d0 = x0 - h0, d1 = x1 - h1, d2 = x2 - h2, d3 = x3 - h3;
+        sd = fmaf(d0, d0, sd); sd = fmaf(d1, d1, sd); sd = fmaf(d2, d2, sd); sd = fmaf(d3, d3, sd);
+      }
     }
-    cn = c * sqrtf(warp_sum(ss)) * (1.f + 1e-6f);
+    const float nu = sqrtf(warp_sum(ss));
+    if (u16) {
+      cn = sqrtf(warp_sum(sd)) * (1.f + 1e-5f) + 1.220703125e-4f * nu;      // ||u - u^|| + 2^-13 ||u||
+      cd = sqrtf(warp_sum(sh)) * (1.f + 1e-5f);
+    } else {
+      cn = c * nu * (1.f + 1e-6f);
+    }
   }
   __syncthreads();
   if (live) {
     float lo_best = -INFINITY;      // best lower bound of the row's exact maximum
-    for (int t = lane; t < tiles; t += 32) lo_best = fmaxf(lo_best, prow[t] - cn * wn[t]);
+    for (int t = lane; t < tiles; t += 32) lo_best = fmaxf(lo_best, prow[t] - (cn * wn[t] + cd * dwn[t]));
     L = warp_max(lo_best);
     int mine = 0;
     for (int t = lane; t < tiles; t += 32)
-      if (prow[t] + cn * wn[t] >= L) {     // the tile's exact maximum may reach the row's: refine it
+      if (prow[t] + (cn * wn[t] + cd * dwn[t]) >= L) {     // the tile's exact maximum may reach the row's: refine it
         atomicAdd(&scnt[t], 1);
         ++mine;
       }
@@ -122,7 +152,7 @@ __global__ void __launch_bounds__(FL_THREADS) argmax_filter_kernel(const float* 
     int nrow = 0;
     for (int t0 = 0; t0 < tiles; t0 += 32) {
       const int t = t0 + lane;
-      const bool flag = t < tiles && prow[t] + cn * wn[t] >= L;
+      const bool flag = t < tiles && prow[t] + (cn * wn[t] + cd * dwn[t]) >= L;
       const unsigned m = __ballot_sync(0xffffffffu, flag);
       if (flag) {
         const int slot = nrow + __popc(m & ((1u << lane) - 1u));
@@ -298,18 +328,19 @@ bool argmax_refine_supported(int Vc, int H) {
   return Vc > 64 && Vc <= 4096 * RF_TN && H % 8 == 0 && refine_smem(H, ceil_div(Vc, RF_TN)) <= 220 * 1024;
 }
 
-int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s) {
-  tile_wnorm_kernel<<<ceil_div(Vc, RF_TN), RF_THREADS, 0, s>>>(W, Vc, H, RF_TN, wnorm);
+int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s, float* dwnorm) {
+  tile_wnorm_kernel<<<ceil_div(Vc, RF_TN), RF_THREADS, 0, s>>>(W, Vc, H, RF_TN, wnorm, dwnorm);
   AA_CHECK_LAUNCH("tile_wnorm");
   return AA_OK;
 }
 
 int launch_argmax_filter(const float* pmax, int tiles, int R, const float* u, long long ldu, long long lo_off, int H, const float* wnorm, float c,
-                         int* counts, unsigned* list, int* ncand, cudaStream_t s) {
-  AA_REQUIRE(R <= (1 << 20) && tiles <= 4096, "argmax_filter: at most 2^20 rows and 4096 tiles (got %d, %d)", R, tiles);
-  const int stage = tiles <= 1200 ? 1 : 0;      // (2 + 8 arrays of one entry per tile within the default 48 KB of shared memory)
-  argmax_filter_kernel<<<ceil_div(R, FL_ROWS), FL_THREADS, sizeof(int) * tiles * (2 + (stage ? FL_ROWS : 0)), s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm,
-                                                                                                            c, counts, list, ncand, stage);
+                         int* counts, unsigned* list, int* ncand, cudaStream_t s, const __nv_bfloat16* u16, long long ld16, const float* dwnorm) {
+  AA_REQUIRE(R <= (1 << 20) && tiles <= 3900, "argmax_filter: at most 2^20 rows and 3900 tiles (got %d, %d)", R, tiles);
+  AA_REQUIRE((u16 == nullptr) == (dwnorm == nullptr) && (!u16 || (ld16 % 4 == 0 && H % 4 == 0)), "argmax_filter: the bf16 mirror and the residual norms go together");
+  const int stage = tiles <= 1100 ? 1 : 0;      // (3 + 8 arrays of one entry per tile within the default 48 KB of shared memory)
+  argmax_filter_kernel<<<ceil_div(R, FL_ROWS), FL_THREADS, sizeof(int) * tiles * (3 + (stage ? FL_ROWS : 0)), s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm,
+                                                                                                            c, counts, list, ncand, stage, u16, ld16, dwnorm);
   AA_CHECK_LAUNCH("argmax_filter");
   return AA_OK;
 }

@@ -262,3 +262,48 @@ def test_argmax_filter_bound_holds_for_sparse_worst_case_vectors(rounder, c, ulp
     keep = tmax + b >= (tmax - b).max(1, keepdims=True)
     win = exact.argmax(1) // TN
     assert keep[np.arange(H), win].all()
+
+
+def test_argmax_filter_exact_decomposition_bound():
+    """The bound the bf16 first pass is filtered with (csrc/vocab_refine.cu, round 2):
+        u.W_j - u^.W^_j  =  u^.(W_j - W^_j) + (u - u^).W_j          (exact, u^ / W^ = the bf16 mirrors)
+        |approx_j - exact_j| <= ||u^|| ||W_j - W^_j|| + ||u - u^|| ||W_j|| + 2^-13 ||u|| ||W_j||   (Cauchy-Schwarz + fp32 accumulation)
+    checked in numpy on dense random data, on rows built to have near-ties across tiles and on the one-hot vectors that attain the
+    worst-case relative bound; it must hold everywhere, keep the exact winner's tile, and be about twice as tight as the
+    relative bound 2.1 * 2^-8 ||u|| ||W_j|| on dense data."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    H, Vc, R, TN = 256, 2000, 300, 16
+    W = (rng.standard_normal((Vc, H)) * np.sqrt(2.0 / H)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(Vc)).astype(np.float32)
+    u = (0.4 + rng.standard_normal((R, H))).astype(np.float32)
+    exact0 = u.astype(np.float64) @ W.astype(np.float64).T + bias
+    for r in range(0, R, 3):                                  # near-ties between far-apart columns
+        j1, j2 = np.argsort(exact0[r])[-2:]
+        if abs(j1 - j2) >= TN:
+            d = W[j2].astype(np.float64) - W[j1].astype(np.float64)
+            u[r] = (u[r].astype(np.float64) - (exact0[r, j2] - exact0[r, j1] - 1e-6) * d / (d @ d)).astype(np.float32)
+    x = np.float32(1.0 + 2.0 ** -8 * (1.0 - 2.0 ** -10))      # worst-case one-hot rows / columns (both operands round down by ~half an ulp)
+    for i in range(8):
+        u[i] = 0
+        u[i, i] = x
+        W[i] = 0
+        W[i, i] = x
+    uh, Wh = _round_bf16(u), _round_bf16(W)
+    exact = u.astype(np.float64) @ W.astype(np.float64).T + bias
+    approx = (uh.astype(np.float64) @ Wh.astype(np.float64).T).astype(np.float32) + bias
+    n = lambda a: np.linalg.norm(a.astype(np.float64), axis=1)
+    bound = n(uh)[:, None] * n(W - Wh)[None, :] + (n(u - uh) + 2.0 ** -13 * n(u))[:, None] * n(W)[None, :]
+    assert (np.abs(approx - exact) <= bound).all()
+    tiles = Vc // TN
+    tmax = approx.reshape(R, tiles, TN).max(-1)
+    b = (n(uh)[:, None] * n(W - Wh).reshape(tiles, TN).max(-1)[None, :]
+         + (n(u - uh) + 2.0 ** -13 * n(u))[:, None] * n(W).reshape(tiles, TN).max(-1)[None, :])
+    keep = tmax + b >= (tmax - b).max(1, keepdims=True)
+    assert keep[np.arange(R), exact.argmax(1) // TN].all()
+    near = (exact >= exact.max(1, keepdims=True) - 1e-6).reshape(R, tiles, TN).any(-1)
+    assert (keep | ~near).all()
+    rel = 2.1 / 256 * n(u)[:, None] * n(W).reshape(tiles, TN).max(-1)[None, :]
+    dense = slice(8, None)
+    assert (b[dense, 1:] < 0.6 * rel[dense, 1:]).all()        # ~2x tighter than the relative bound on dense rows and tiles ...
+    keep_rel = tmax + rel >= (tmax - rel).max(1, keepdims=True)
+    assert keep[dense].sum() < 0.85 * keep_rel[dense].sum()   # ... which shows in the number of tiles handed to the refinement
