@@ -15,6 +15,7 @@ constexpr int END_ID = 2;    // build_vocab.py:48-51
 constexpr int MAX_BEAM = 8;
 int g_decode_table = [] { const char* e = getenv("AA_DECODE_TABLE"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_decode_table_min_rows = [] { const char* e = getenv("AA_DECODE_TABLE_MIN_ROWS"); return e ? atoi(e) : 0; }();
+int g_decode_p_tc = [] { const char* e = getenv("AA_DECODE_P_TC"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_decode_qr_split = [] { const char* e = getenv("AA_DECODE_QR_SPLIT"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
 // filter-and-refine arg-max of the greedy vocabulary projection (vocab_refine.cu); AA_DECODE_REFINE=0 / aa_debug_set_decode_argmax_refine(0)
@@ -48,6 +49,7 @@ struct DecodeWs {
   // table mode (greedy, tensor-core pipeline, large batches): EG [Vc,5H] = embed . [W_ih[:, :E]; W_x[:, :E]]^T takes the word's half of
   // the gate contraction out of the loop (K = E+H -> H, N = 5H -> 4H: the sentinel block has no recurrent half in decode mode, Q3)
   int table; float *EG, *Whh_s, *emb_s, *wxe_s;
+  int p_tc; float* wv_s;     // P = V W_v^T on tcgen05 with V split into tf32 (hi, lo) on the fly (TcGemmArgs::a_raw); wv_s = W_v split
   float *vg_s, *wx_s; int Ep;     // split pipeline: (hi | lo) copies of v_g [B, 2*Ep] and of the v_g columns of [W_ih; W_x] [5H, 2*Ep]
   int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
   // beam only
@@ -90,6 +92,8 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.Whh_s = c.take<float>(w.table ? (size_t)4 * H * 2 * w.Hp : 0);
   w.emb_s = c.take<float>(w.table ? (size_t)d.Vc * 2 * w.Ep : 0);
   w.wxe_s = c.take<float>(w.table ? (size_t)5 * H * 2 * w.Ep : 0);
+  w.p_tc = (w.split && d.a <= 64 && H % 32 == 0 && g_decode_p_tc) ? 1 : 0;
+  w.wv_s = c.take<float>(w.p_tc ? (size_t)d.a * 2 * w.Hp : 0);
   w.W2 = c.take<float>(w.split ? (w.qr_split ? (size_t)(64 + d.a) * 2 * w.Hp : (size_t)2 * d.a * 2 * w.K2p) : 0);
   w.hs = c.take<float>(w.split ? R * 2 * H : 0);
   w.qr = c.take<float>(w.split ? R * w.ld_qr : 0);
@@ -452,7 +456,17 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
     AA_CHECK_CUDA(cudaMemsetAsync(ws.P, 0, sizeof(float) * (size_t)B * d.k * ws.ldP, st));
     AA_CHECK_CUDA(cudaMemsetAsync(ws.qr, 0, sizeof(float) * (size_t)R * ws.ld_qr, st));
   }
-  AA_TRY(gemm_nt(B * d.k, d.a, H, V, H, w.att_wv, H, ws.P, ws.ldP, nullptr, 0, nullptr, nullptr, st));
+  if (ws.p_tc) {      // fp32-accurate 3xTF32 on tcgen05; V is read once and split in shared memory by the kernel's converter warps
+    AA_TRY(launch_split_tf32(w.att_wv, H, d.a, H, ws.wv_s, ws.Hp, st));
+    aa::ProfScope ps("dec_prologue_P", st);
+    TcGemmArgs g{};
+    g.M = B * d.k; g.N = d.a; g.K = H; g.elem_size = 4; g.split3 = 1; g.a_raw = 1;
+    g.A = V; g.lda = H; g.B = ws.wv_s; g.ldb = 2 * ws.Hp;
+    g.D32 = ws.P; g.ldd32 = ws.ldP;
+    AA_TRY(launch_gemm_tc(g, st));
+  } else {
+    AA_PROF("dec_prologue_P", st, gemm_nt(B * d.k, d.a, H, V, H, w.att_wv, H, ws.P, ws.ldP, nullptr, 0, nullptr, nullptr, st));
+  }
   // static (per image) gate terms: v_g half of x and the biases
   float* stat_img = beam > 1 ? ws.gates : ws.stat;   // [B,5H]; `gates` is free before the first step
   if (ws.split) {   // on tensor cores like the per-step contractions (fp32-accurate 3xTF32): 4096 x 2560 x 256 took 165 us on the SIMT path

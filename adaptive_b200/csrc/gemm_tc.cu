@@ -71,7 +71,7 @@ int g_tc_splitk = 1;   // diagnostics (aa_debug_set_gemm_splitk)
 // lane quarter, each part draining a contiguous range of the tile's 32-column chunks: with 4 warps the TMEM -> smem
 // transpose -> global chain of one warp per quarter bounded the K=512 contractions (1.4 TB/s of output at 148 SMs).
 constexpr int epi_warps(bool split) { return split ? 4 : 8; }   // (split stages leave no room for 8 transpose tiles)
-constexpr int tc_threads(bool split) { return 64 + 32 * epi_warps(split); }
+constexpr int tc_threads(bool split, bool a_raw = false) { return 64 + 32 * epi_warps(split) + (a_raw ? 128 : 0); }   // a_raw: + 4 converter warps
 
 struct TcEpilogue {
   int M, N, K;
@@ -99,8 +99,12 @@ struct TcEpilogue {
 // PM: arg-max partials of the epilogue -- 0 = none (every training contraction: the scan code and its registers stay out of those
 // instantiations), 1 = per-(row, part) maximum and its column index, 2 = maximum only, 3 = cross-entropy pieces per 32-column
 // chunk (maximum, sum of exponentials, exponentials as bf16, the target's logit) instead of the logits
-template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT, int PM = 0>
-__global__ void __launch_bounds__(tc_threads(SPLIT), 1)
+// A_RAW (split mode only): the A operand is a PLAIN fp32 array -- one TMA box per stage lands in the hi slot and four converter warps
+// split it there into tf32 (hi, lo) sub-tiles (the split is elementwise, so the swizzled layout stays what the MMA expects).  The
+// operand is read from HBM once instead of being split into a 2x larger array first: P = V W_v^T of the decode prologue, whose
+// 411 MB of V took 317 us of exact-fp32 SIMT work per call.
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT, int PM = 0, bool A_RAW = false>
+__global__ void __launch_bounds__(tc_threads(SPLIT, A_RAW), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m,
                int num_tiles, int num_units) {
   // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... (m fastest, so neighbouring CTAs share the
@@ -128,7 +132,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* conv_bar = tmem_empty + 2;           // [STAGES] (A_RAW: the stage's A tile has been split)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + (A_RAW ? STAGES : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (e.K + BK - 1) / BK;
@@ -141,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      if constexpr (A_RAW) mbar_init(&conv_bar[s], 4);   // one arrive per converter warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -169,9 +175,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], A_STAGE + B_STAGE);
+          if constexpr (!(SPLIT && A_RAW)) mbar_expect_tx(&full_bar[s], A_STAGE + B_STAGE);
           uint8_t* a_dst = sA + s * A_STAGE;
           uint8_t* b_dst = sB + s * B_STAGE;
+          if constexpr (SPLIT && A_RAW) {      // plain fp32 A: one box into the hi slot (the converter warps fill the lo slot)
+            mbar_expect_tx(&full_bar[s], A_BYTES + B_STAGE);
+            tma_load_2d(a_dst, &tmA, kb * BK, m0, &full_bar[s]);
+            tma_load_2d(b_dst, &tmB, kb * BK, n0, &full_bar[s]);
+            tma_load_2d(b_dst + B_BYTES, &tmB, e.lo_b + kb * BK, n0, &full_bar[s]);
+            continue;
+          }
           if constexpr (SPLIT) {      // hi halves at column kb*BK, lo halves at column K + kb*BK of the same arrays
             const int ash = n0 >= e.ashift_n0 ? e.ashift_cols : 0;
             tma_load_2d(a_dst, &tmA, kb * BK + ash, m0, &full_bar[s]);
@@ -214,7 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if constexpr (A_RAW) mbar_wait(&conv_bar[s], ph);      // (implies the stage's TMA loads: the converters waited for them)
+          else mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
           const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
@@ -242,6 +256,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (elect_one()) tc_commit(&tmem_full[acc]);   // accumulator complete
         __syncwarp();
+      }
+    }
+  } else if (A_RAW && warp >= 2 + EW) {
+    // ===== converters (A_RAW): raw fp32 A tile -> tf32 (hi, lo) sub-tiles, in place + the lo slot =====
+    if constexpr (A_RAW) {
+      const int ct = threadIdx.x - (2 + EW) * 32;      // 0 .. 127
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int n0 = ((unit % num_tiles) / tiles_m) * BN;
+        const int kb0 = (unit / num_tiles) * e.kb_per, kb1 = min(n0 >= e.kcut_n0 ? e.kcut_nkb : nkb, kb0 + e.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          float4* hi4 = reinterpret_cast<float4*>(sA + s * A_STAGE);
+          float4* lo4 = reinterpret_cast<float4*>(sA + s * A_STAGE + A_BYTES);
+#pragma unroll
+          for (int i = 0; i < (int)(A_BYTES / 16 / 128); ++i) {      // consecutive threads, consecutive 16-byte chunks: conflict-free
+            const float4 x = hi4[i * 128 + ct];
+            float4 h, l;
+            split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+            hi4[i * 128 + ct] = h;
+            lo4[i * 128 + ct] = l;
+          }
+          fence_proxy_async_smem();      // generic-proxy writes -> the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&conv_bar[s]);
+        }
       }
     }
   } else {
@@ -461,7 +502,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT = false, int PM = 0>
+template <int BN, int ES, int STAGES, bool A_MN, bool B_MN, bool SPLIT = false, int PM = 0, bool A_RAW = false>
 int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int BK = 128 / ES;
   CUtensorMap tmA, tmB;
@@ -469,7 +510,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   // split operands: a row holds [hi (>= K columns) ... lo (>= K columns) ...]; the map spans what the row has left
   // from the operand's base column on (columns past it are zero-filled by TMA, never wrapped into the next row)
   const int lo_a = g.lo_a ? g.lo_a : g.K, lo_b = g.lo_b ? g.lo_b : g.K;
-  const long long acols = SPLIT ? (g.a_cols ? g.a_cols : (long long)lo_a + g.K) : g.K;
+  const long long acols = A_RAW ? g.K : SPLIT ? (g.a_cols ? g.a_cols : (long long)lo_a + g.K) : g.K;
   const long long bcols = SPLIT ? (g.b_cols ? g.b_cols : (long long)lo_b + g.K) : g.K;
   if (A_MN) AA_TRY(make_map(&tmA, g.A, ES, g.K, g.M, g.lda, BK));
   else      AA_TRY(make_map(&tmA, g.A, ES, g.M, acols, g.lda, BM));
@@ -495,9 +536,9 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   if (PM == 3) { e.D16 = g.ce_e16; e.ldd16 = g.ld_ce; }      // the exponentials take the bf16 output path
   e.ce_e16 = g.ce_e16; e.ld_ce = g.ld_ce; e.ce_part = g.ce_part; e.ce_chunks = g.ce_chunks; e.ce_tgt = g.ce_tgt; e.ce_xt = g.ce_xt;
   e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = PM == 2 ? ceil_div(g.N, 16) : ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
-  constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration exceeds shared memory");
-  auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN, SPLIT, PM>;
+  auto kern = gemm_tc_kernel<BN, ES, STAGES, A_MN, B_MN, SPLIT, PM, A_RAW>;
   static bool attr_done = false;
   if (!attr_done) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -528,7 +569,7 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
     AA_CHECK_CUDA(cudaMemset2DAsync(g.D32, sizeof(float) * (size_t)g.ldd32, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
   const int num_units = num_tiles * ksplit;
   const int grid = num_units < num_sms() ? num_units : num_sms();     // persistent: one CTA per SM
-  kern<<<grid, tc_threads(SPLIT), smem, st>>>(tmA, tmB, e, tiles_m, num_tiles, num_units);
+  kern<<<grid, tc_threads(SPLIT, A_RAW), smem, st>>>(tmA, tmB, e, tiles_m, num_tiles, num_units);
   AA_CHECK_LAUNCH("gemm_tc_kernel");
   return AA_OK;
 }
@@ -605,6 +646,10 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
     // (256-column tiles -- 128 cycles per MMA for twice the columns -- were measured SLOWER here: only two 96 KB stages fit
     //  and the TMA feed, ~50 B/clk per SM, becomes the bound: vocabulary GEMM 224 us against 205 us, r01_v33)
     if (g.pmax) return g.N > 64 ? launch_cfg<128, 4, 3, false, false, true, 1>(g, st) : launch_cfg<64, 4, 4, false, false, true, 1>(g, st);
+    if (g.a_raw) {      // plain fp32 A split on the fly (narrow outputs only: the decode prologue's P = V W_v^T, N = 49)
+      AA_REQUIRE(!g.pmax && !g.ashift_cols && g.N <= 64, "tcgen05 GEMM: the on-the-fly split of A serves outputs of at most 64 columns");
+      return launch_cfg<64, 4, 4, false, false, true, 0, true>(g, st);
+    }
     if (g.ashift_cols > 0) return launch_cfg<64, 4, 4, false, false, true>(g, st);
     if (g.N > 64) return launch_cfg<128, 4, 3, false, false, true>(g, st);
     return launch_cfg<64, 4, 4, false, false, true>(g, st);

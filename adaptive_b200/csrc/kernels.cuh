@@ -113,6 +113,9 @@ struct TcGemmArgs {
   // the row (both halves) -- two contractions over different column windows of the same operand rows in one launch, e.g.
   // [q | r'] = [h W_g^T | s W_s^T] from rows [h | s].  Needs ashift_n0 to be a multiple of the tile width (forces 64-column tiles).
   int ashift_n0, ashift_cols;
+  // optional (split3 only): A is a PLAIN fp32 array [M, K] (row stride lda) that the kernel splits into tf32 (hi, lo) on the fly in
+  // shared memory; B stays pre-split.  N <= 64.
+  int a_raw;
   // optional (plain bf16, K-major): cross-entropy pieces instead of the logits (train.py:63,208 fused into the vocabulary projection's
   // epilogue; D32 / D16 null).  Per row and 32-column chunk of D (+ bias1): the chunk maximum m and s = sum exp(x - m) go to
   // ce_part[(row * ce_chunks + chunk) * 2 + {0, 1}], e = exp(x - m) as bf16 to ce_e16[row * ld_ce + col], and the target column's

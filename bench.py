@@ -662,7 +662,7 @@ def measure_config5(torch, dist, dev, world, rank, barrier, max_over_ranks, peak
 
         trainer = DataParallelTrainer(model, overlap=True)
         stepper = GraphedDPStep(trainer, b, lengths)
-        mode = "graph+nccl"
+        mode = "graph+exchange"
     for _ in range(3):
         stepper(b)
     barrier()
@@ -678,7 +678,7 @@ def measure_config5(torch, dist, dev, world, rank, barrier, max_over_ranks, peak
     flops = 191e6 * B * T               # 191 MFLOP per token fwd+bwd at cfgB
     n_par = sum(p.numel() for p in model.decoder.parameters())
     out = {"workload": "BASELINE config 5: DP training, 196 regions, hidden 1024, embed 512, vocab 20000, batch %d per GPU, caption len %d, bf16" % (B, T),
-           "value": B * T * world / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "n_gpus": world, "mode": mode, "steps": n,
+           "value": B * T * world / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "n_gpus": world, "exchange": (trainer.engine if world > 1 else "none"), "mode": mode, "steps": n,
            "gradient_bytes_fp32": 4 * n_par,
            "whole_step_roofline": {"bound": "tensor", "algorithmic_tflops": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"],
                                    "frac": flops / (ms * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "unit": "TFLOP/s"}}
