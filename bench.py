@@ -213,18 +213,20 @@ def kernel_models(dims, B, T, decode_B):
     fl = lambda m, n, kk: 2.0 * m * n * kk
     # attention stream kernel of the tensor-core decode pipeline, per (row, step): reads V, P, [h|s], [q|r]; writes u, alpha, beta
     step_bytes = k * H * 4 + k * a * 4 + 2 * H * 4 + 2 * a * 4 + H * 4 + k * 4 + 4          # 116 692 B at cfgA
-    cell_bytes = (5 * H + H) * 4 + (H + 2 * H) * 4                                          # gates, c in; c, h, s out
+    # cell: recurrent gates (4H) + static sentinel block (H) + the word's EG row (5H, L2-resident) + c in; c, [h | s], tf32 (hi, lo) of h and s out
+    cell_bytes = (4 * H + H + 5 * H + H) * 4 + (H + 2 * H + 4 * H) * 4
     return {
         "lstm_seq_fwd": ("tensor", fl(B, 4 * H, H) * T), "lstm_seq_bwd": ("tensor", fl(B, H, 4 * H) * T),
-        "dec_cell": ("hbm", float(cell_bytes) * decode_B), "dec_qr_gemm": ("tf32x3", fl(decode_B, 2 * a, 2 * H)),
+        "dec_cell": ("hbm", float(cell_bytes) * decode_B), "dec_qr_gemm": ("tf32x3", fl(decode_B, 2 * a, H)),
+        "dec_prologue_P": ("tf32x3", fl(decode_B * k, a, H)), "dec_gate_table": ("tf32x3", fl(Vc, 5 * H, E)),
         "gemm_vocab_fwd": ("tensor", fl(N, Vc, H)), "gemm_vocab_dx": ("tensor", fl(N, H, Vc)), "gemm_vocab_dw": ("tensor", fl(Vc, H, N)),
         "lstm_rec_gemm": ("tensor", fl(B, 4 * H, H)), "bptt_rec_gemm": ("tensor", fl(B, H, 4 * H)),
-        "dec_vocab_gemm": ("tf32x3", fl(decode_B, Vc, H)), "dec_vocab_gemm1": ("bf16x1", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tf32x3", fl(decode_B, 5 * H, E + H)),
+        "dec_vocab_gemm": ("tf32x3", fl(decode_B, Vc, H)), "dec_vocab_gemm1": ("bf16x1", fl(decode_B, Vc, H)), "dec_gate_gemm": ("tf32x3", fl(decode_B, 4 * H, H)),
         "dec_step_fused": ("hbm", float(step_bytes) * decode_B),
         # final reduction over the row's refined candidates (~2 entries) + gather of the next word's embedding into the (hi | lo) A operand
         "dec_argmax": ("hbm", float(decode_B) * (E * 4 + 2 * E * 4 + 8 + 4 + 3 * 8)),
         # candidate filter: one pass over the first pass's maxima [B, Vc/16] and over u (hi | lo) for the row norms
-        "dec_argmax_filter": ("hbm", float(decode_B) * (((Vc + 15) // 16) * 4 + 2 * H * 4)),
+        "dec_argmax_filter": ("hbm", float(decode_B) * (((Vc + 15) // 16) * 4 + 2 * H * 4 + H * 2)),
         # the small contractions of the step, grouped by tag: (flops per step) / (launches per step)
         "gemm_att_dw": ("tensor", (fl(a, H, B * k) + 2 * fl(a, H, N)) / 3), "gemm_att_dx": ("tensor", (fl(B * k, H, a) + 2 * fl(N, H, a)) / 3),
         "gemm_sent_dw": ("tensor", (fl(H, 2 * E, N) + fl(H, H, N)) / 2), "gemm_sent_dx": ("tensor", (fl(N, 2 * E, H) + fl(N, H, H)) / 2),
