@@ -664,6 +664,8 @@ def measure_config5(torch, dist, dev, world, rank, barrier, max_over_ranks, peak
 
         trainer = DataParallelTrainer(model, overlap=True)
         stepper = GraphedDPStep(trainer, b, lengths)
+        if trainer.buckets.symm is None:
+            NCCL_CAPTURED[0] = True
         mode = "graph+exchange"
     for _ in range(3):
         stepper(b)
@@ -702,11 +704,16 @@ def stage(msg):
     faulthandler.dump_traceback_later(float(os.environ.get("AA_BENCH_STAGE_TIMEOUT", "240")), exit=True)
 
 
+NCCL_CAPTURED = [False]     # set when a CUDA graph holding NCCL collectives was built in this process
+
+
 def leave(world, rc=0):
-    """End of a rank's run: flush what was printed, then (N > 1) leave without tearing NCCL down.
-    ``destroy_process_group()`` after CUDA-graph-captured collectives blocked forever on the 2-GPU box (every stage done, the
-    JSON line still in the stdout buffer); a finished benchmark process has nothing left to release that process exit does
-    not release, so the ranks synchronise their devices and exit 0 directly."""
+    """End of a rank's run: flush what was printed, then (N > 1) tear the process group down.
+    Root cause of round 1's hang, re-examined in round 2 (``gpurun_out/r02_clean_exit*.err``): ``destroy_process_group()`` blocks
+    forever exactly when NCCL collectives were captured into a CUDA graph in this process (the fallback exchange engine); with the
+    exchange in our own peer-memory kernels nothing of NCCL is ever captured and the teardown returns.  So: clean teardown unless an
+    NCCL-holding graph exists -- then, as before, synchronise and leave through ``os._exit`` (a finished benchmark process has
+    nothing left to release that process exit does not release)."""
     import faulthandler
 
     faulthandler.cancel_dump_traceback_later()
@@ -714,8 +721,18 @@ def leave(world, rc=0):
     sys.stderr.flush()
     if world > 1:
         import torch
+        import torch.distributed as dist
 
         torch.cuda.synchronize()
+        if not NCCL_CAPTURED[0] and os.environ.get("AA_BENCH_CLEAN_EXIT", "1") == "1":
+            try:
+                dist.barrier()
+                dist.destroy_process_group()
+            except Exception as e:      # (a peer already gone after a failed check: nothing left to tear down together)
+                sys.stderr.write("[bench rank %s] destroy_process_group(): %s\n" % (os.environ.get("RANK", "0"), e))
+                os._exit(rc)
+            sys.stderr.flush()
+            sys.exit(rc)
         os._exit(rc)
     if rc:
         sys.exit(rc)
@@ -830,6 +847,8 @@ def run_ours(args):
             if float(ok.item()) < 1:
                 stepper = None
             dp_mode = "graph" if stepper is not None else "eager"
+            if stepper is not None and trainer.buckets.symm is None:
+                NCCL_CAPTURED[0] = True
 
         def train_step(b):
             return stepper(b) if stepper is not None else dp_eager(b)
