@@ -115,6 +115,19 @@ class Encoder2Decoder(nn.Module):
             return F_aa.decoder_forward_packed(self.decoder.weights(), V, v_g, captions, lengths, h0, c0, self.decoder.precision)[0]
         return F_aa.pack_scores(self.decoder(V, v_g, captions, states)[0], lengths)
 
+    def forward_loss(self, images, captions, lengths, targets=None):
+        """``criterion(self(images, captions, lengths).data, targets)`` (``train.py:205-208``) as one operator; same routes as the
+        adaptive model's ``forward_loss`` (the fused operator takes the sentinel-less weights like every other entry point)."""
+        V, v_g, states = self._encode(images)
+        h0, c0 = states if states is not None else (None, None)
+        if (self.decoder.precision == "bf16" and V.shape[2] % 8 == 0
+                and F_aa.fused_loss_pays(sum(int(x) for x in lengths), self.decoder.embed.num_embeddings)):
+            return F_aa.decoder_forward_loss(self.decoder.weights(), V, v_g, captions, lengths, targets, h0, c0)[0]
+        packed = self.forward((V, v_g, states), captions, lengths)
+        if targets is None:
+            targets = F_aa.packed_targets(captions, lengths)
+        return F_aa.cross_entropy(packed.data, targets)
+
     def sampler(self, images, max_len=30):
         """Greedy search (baseline_attention.py:233-283) -> sampled_ids [B,max_len], attention [B,max_len,k]."""
         V, v_g, states = self._encode(images)

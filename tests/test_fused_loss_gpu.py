@@ -149,3 +149,36 @@ def test_module_forward_loss_and_graphed_step(prec, monkeypatch):
     assert abs(l3.item() - ref_v) < 1e-3 * abs(ref_v)
     for p, g in zip(params, g_ref):
         assert rel_err(p.grad.cpu().numpy(), g.cpu().numpy()) < tol
+
+
+def test_fused_loss_sentinel_less_baseline_model(monkeypatch):
+    """The baseline decoder (baseline_attention.py:66-194: no sentinel, beta = 0) through the fused operator: NULL sentinel weights like
+    every other entry point; loss and gradients against the oracle's baseline mode, and ``baseline.Encoder2Decoder.forward_loss``."""
+    from adaptive_b200 import baseline
+    from adaptive_b200.synth import baseline_weights
+
+    monkeypatch.setenv("AA_FUSED_CE", "1")
+    dims, B, T = Dims(H=128, E=64, Vc=504, k=49), 10, 7
+    w_full = make_weights(dims, seed=91, bias_scale=0.1)
+    wb = baseline_weights(w_full)
+    inp = make_inputs(dims, B, T, seed=92)
+    lengths = make_lengths(B, T, seed=93)
+    loss_o, G, tgt_np = _oracle_step(wb, inp, lengths, B, T, dims)
+    tgt = torch.from_numpy(np.ascontiguousarray(tgt_np)).cuda()
+    W = F_aa.baseline_weights(dev_weights(w_full, requires_grad=True))
+    V, v_g, h0, c0, cap = dev_inputs(inp)
+    loss = F_aa.decoder_forward_loss(W, V, v_g, cap, lengths, tgt, h0, c0)[0]
+    loss.backward()
+    assert abs(loss.item() - loss_o) < 1e-3 * abs(loss_o)
+    for key, t in zip(grad_key_order(), W):
+        if t is not None:
+            assert rel_err(t.grad.cpu().numpy(), G[key]) < BF16_TOL, key
+
+    class Cf:
+        base_word_embed_size, base_lstm_hidden_size, vocab_length = dims.E, dims.H, dims.Vc
+        precision = "bf16"
+
+    m = baseline.Encoder2Decoder(Cf()).cuda()
+    m.decoder.load_state_dict({k: torch.from_numpy(v) for k, v in wb.items()}, strict=True)
+    l2 = m.forward_loss((V, v_g, (h0, c0)), cap, lengths, tgt)
+    assert abs(l2.item() - loss_o) < 1e-3 * abs(loss_o)
