@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -604,17 +605,21 @@ def greedy_decode_persistent(w: Sequence[torch.Tensor], V, v_g, h0=None, c0=None
     with torch.cuda.device(dev):
         nbytes = lib.aa_decode_persistent_workspace_bytes(ctypes.byref(d))
         key = (dev.index, B, max_len, k, H, E, Vc, a)
-        stamp = tuple((t.data_ptr(), t._version) if t is not None else None for t in w)
+        # the packed operands are valid for THESE tensor objects at THESE versions: weak references, not addresses (a reloaded model
+        # can land on the addresses of the one it replaced, at version 0 again)
+        stamp = tuple(t._version if t is not None else None for t in w)
         hit = _PERSIST_WS.get(key)
         flags = 0
-        if hit is not None and hit[1] == stamp and hit[0].numel() >= nbytes and not torch.cuda.is_current_stream_capturing():
+        same = hit is not None and hit[1] == stamp and len(hit[2]) == len(w) and all(
+            (r is None and t is None) or (r is not None and t is not None and r() is t) for r, t in zip(hit[2], w))
+        if same and hit[0].numel() >= nbytes and not torch.cuda.is_current_stream_capturing():
             wsb, flags = hit[0], 1                      # AA_DECODE_REUSE_PACKED_WEIGHTS
         else:
             wsb = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             if not torch.cuda.is_current_stream_capturing():
                 if len(_PERSIST_WS) > 16:
                     _PERSIST_WS.clear()
-                _PERSIST_WS[key] = (wsb, stamp)
+                _PERSIST_WS[key] = (wsb, stamp, tuple(weakref.ref(t) if t is not None else None for t in w))
         ws = weights_struct(w)
         check(lib.aa_decode_persistent(ctypes.byref(d), ctypes.byref(ws), _ptr(V), _ptr(v_g), _ptr(h0), _ptr(c0), max_len, _ptr(ids),
                                        _ptr(att), _ptr(bet), flags, _ptr(cand), _ptr(wsb), nbytes, _stream(dev)), "aa_decode_persistent")
