@@ -15,7 +15,6 @@ constexpr int END_ID = 2;    // build_vocab.py:48-51
 constexpr int MAX_BEAM = 8;
 int g_decode_table = [] { const char* e = getenv("AA_DECODE_TABLE"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_decode_table_min_rows = [] { const char* e = getenv("AA_DECODE_TABLE_MIN_ROWS"); return e ? atoi(e) : 0; }();
-int g_decode_cell_fused = [] { const char* e = getenv("AA_DECODE_CELL_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_decode_p_tc = [] { const char* e = getenv("AA_DECODE_P_TC"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_decode_qr_split = [] { const char* e = getenv("AA_DECODE_QR_SPLIT"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_force_simple_atten = 0;   // diagnostics (aa_debug_set_decode_atten_simple): register-staged attention kernel
@@ -50,8 +49,6 @@ struct DecodeWs {
   // table mode (greedy, tensor-core pipeline, large batches): EG [Vc,5H] = embed . [W_ih[:, :E]; W_x[:, :E]]^T takes the word's half of
   // the gate contraction out of the loop (K = E+H -> H, N = 5H -> 4H: the sentinel block has no recurrent half in decode mode, Q3)
   int table; float *EG, *Whh_s, *emb_s, *wxe_s;
-  int cell_fused;            // table mode: the LSTM cell runs in the gate contraction's epilogue (W_hh rows gate-interleaved by 8 units,
-                             // operand rows double-buffered: Acat / Acat2)
   int p_tc; float* wv_s;     // P = V W_v^T on tcgen05 with V split into tf32 (hi, lo) on the fly (TcGemmArgs::a_raw); wv_s = W_v split
   float *vg_s, *wx_s; int Ep;     // split pipeline: (hi | lo) copies of v_g [B, 2*Ep] and of the v_g columns of [W_ih; W_x] [5H, 2*Ep]
   int ldP, ld_qr;   // row strides of P and [q | r]: padded to 4 floats in the split pipeline (16-byte bulk copies)
@@ -119,8 +116,7 @@ DecodeWs carve_decode(const aa_dims& d, int beam, void* base) {
   w.Wp16 = reinterpret_cast<__nv_bfloat16*>(c.take<unsigned short>(w.refine == 2 ? (size_t)d.Vc * H : 0));
   w.vg_s = c.take<float>(w.split ? B * 2 * w.Ep : 0);
   w.wx_s = c.take<float>(w.split ? (size_t)5 * H * 2 * w.Ep : 0);
-  w.cell_fused = (w.table && H % 8 == 0 && g_decode_cell_fused) ? 1 : 0;
-  w.Acat2 = c.take<float>((bm || w.cell_fused) ? R * w.ldA : 0);
+  w.Acat2 = c.take<float>(bm ? R * w.ldA : 0);
   w.c2 = c.take<float>(bm ? R * H : 0);
   w.cum = c.take<float>(bm ? R : 0);
   w.row_max = c.take<float>(bm ? R : 0);
@@ -172,21 +168,6 @@ __global__ void pack_wqr_split_kernel(const float* __restrict__ Wg, const float*
     if (src && c < H) split_tf32(src[c], hi, lo);
     dst[c] = hi;
     dst[Hp + c] = lo;
-  }
-}
-
-// W_hh [4H, H] -> tf32 (hi | lo) rows [4H, 2*Hp] in GATE-INTERLEAVED order: row (u / 8) * 32 + g * 8 + u % 8 = gate g of unit u, so that
-// every 32-column chunk of the gate contraction's accumulator holds i, f, g, o of 8 units (cell epilogue, gemm_tc.cu PM = 4)
-__global__ void pack_whh_interleaved_kernel(const float* __restrict__ w_hh, float* __restrict__ dst, int H, int Hp) {
-  const int n = blockIdx.x;                       // destination row
-  const int g = (n & 31) >> 3, u = (n >> 5) * 8 + (n & 7);
-  const float* src = w_hh + ((long long)g * H + u) * H;
-  float* d = dst + (long long)n * 2 * Hp;
-  for (int c = threadIdx.x; c < Hp; c += blockDim.x) {
-    float hi = 0.f, lo = 0.f;
-    if (c < H) split_tf32(src[c], hi, lo);
-    d[c] = hi;
-    d[Hp + c] = lo;
   }
 }
 
@@ -441,12 +422,7 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
   const int B = d.B, H = d.H, E = d.E, R = B * beam, K = E + H;
   if (ws.table) {
     // recurrent weights alone, and the per-word table of the input half (fp32-accurate 3xTF32 like the per-step contractions)
-    if (ws.cell_fused) {
-      pack_whh_interleaved_kernel<<<4 * H, 256, 0, st>>>(w.w_hh, ws.Whh_s, H, ws.Hp);
-      AA_CHECK_LAUNCH("pack_whh_interleaved");
-    } else {
-      AA_TRY(launch_split_tf32(w.w_hh, H, 4 * H, H, ws.Whh_s, ws.Hp, st));
-    }
+    AA_TRY(launch_split_tf32(w.w_hh, H, 4 * H, H, ws.Whh_s, ws.Hp, st));
     AA_TRY(launch_split_tf32(w.embed, E, d.Vc, E, ws.emb_s, ws.Ep, st));
     AA_TRY(launch_split_tf32(w.w_ih, 2 * E, 4 * H, E, ws.wxe_s, ws.Ep, st));
     if (w.sen_wx) AA_TRY(launch_split_tf32(w.sen_wx, 2 * E, H, E, ws.wxe_s + (size_t)4 * H * 2 * ws.Ep, ws.Ep, st));
@@ -473,7 +449,7 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
     // the operand windows read past the columns they need (up to a multiple of 32, against zero weight columns):
     // everything they can touch must be finite from the start, and the pad columns stay zero for the whole decode
     AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat, 0, sizeof(float) * (size_t)R * ws.ldA, st));
-    if (ws.bm || ws.cell_fused) AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat2, 0, sizeof(float) * (size_t)R * ws.ldA, st));
+    if (ws.bm) AA_CHECK_CUDA(cudaMemsetAsync(ws.Acat2, 0, sizeof(float) * (size_t)R * ws.ldA, st));
     if (ws.Hp != H) AA_CHECK_CUDA(cudaMemsetAsync(ws.u, 0, sizeof(float) * (size_t)R * ws.ldU, st));
   }
   if (ws.split && (ws.ldP != d.a || ws.ld_qr != 2 * d.a || ws.qr_split)) {   // pad columns are streamed into shared memory with their rows (never read): keep them finite
@@ -524,24 +500,9 @@ int decode_prologue(const aa_dims& d, const aa_weights& w, const float* V, const
 // One decode step up to u = c_hat + h for R rows (R = B * beam) whose A operand is `Acur` and cell state `ccur`.
 int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, const float* V, float* Acur, float* ccur, int R, int beam,
                      float* alpha, long long ld_alpha, float* beta, long long ld_beta, cudaStream_t st,
-                     const long long* prev_ids = nullptr, long long ld_ids = 0, float* Anext = nullptr) {
+                     const long long* prev_ids = nullptr, long long ld_ids = 0) {
   const int H = d.H, E = d.E, K = E + H;
-  if (ws.cell_fused && Anext) {
-    // gate contraction with the LSTM cell + sentinel gate in its epilogue: reads h_{t-1} from Acur, writes c in place, [h | s] and the
-    // tf32 (hi, lo) operand rows of THIS step into Anext (never the array the contraction is still reading)
-    DecodeCellArgs cp{};
-    cp.R = R; cp.H = H; cp.c = ccur; cp.hs = ws.hs; cp.A = Anext; cp.ldA = ws.ldA; cp.h_off = E; cp.lo_off = ws.lo;
-    cp.EG = ws.EG; cp.stat = ws.stat; cp.prev_ids = prev_ids; cp.ld_ids = ld_ids; cp.start_id = START_ID;
-    {
-      aa::ProfScope ps("dec_gate_gemm", st);
-      TcGemmArgs g{};
-      g.M = R; g.N = 4 * H; g.K = ws.Hp; g.elem_size = 4; g.split3 = 1;
-      g.A = Acur + E; g.lda = ws.ldA; g.lo_a = ws.lo; g.a_cols = ws.ldA - E; g.B = ws.Whh_s; g.ldb = 2 * ws.Hp;
-      g.cell = &cp;
-      AA_TRY(launch_gemm_tc(g, st));
-    }
-    Acur = Anext;
-  } else if (ws.table) {
+  if (ws.table) {
     // gates[:, :4H] = h_{t-1} W_hh^T + static; the word's half comes from the table inside dec_cell
     AA_PROF("dec_gate_gemm", st, dec_gemm(ws, R, 4 * H, H, ws.Hp, Acur + E, ws.ldA, ws.lo, ws.ldA - E, ws.Whh_s, 2 * ws.Hp, ws.gates, 5 * H,
                                           ws.stat, 5 * H, nullptr, nullptr, nullptr, st));
@@ -562,12 +523,10 @@ int decode_step_body(const aa_dims& d, const aa_weights& w, const DecodeWs& ws, 
     AA_PROF("dec_step_fused", st, launch_decode_step(p, st));
     return AA_OK;
   }
-  if (!(ws.cell_fused && Anext)) {
-    DecodeCellArgs cp{};
-    cp.R = R; cp.H = H; cp.gates = ws.gates; cp.c = ccur; cp.hs = ws.hs; cp.A = Acur; cp.ldA = ws.ldA; cp.h_off = E; cp.lo_off = ws.lo;
-    if (ws.table) { cp.EG = ws.EG; cp.stat = ws.stat; cp.prev_ids = prev_ids; cp.ld_ids = ld_ids; cp.start_id = START_ID; }
-    AA_PROF("dec_cell", st, launch_decode_cell(cp, st));
-  }
+  DecodeCellArgs cp{};
+  cp.R = R; cp.H = H; cp.gates = ws.gates; cp.c = ccur; cp.hs = ws.hs; cp.A = Acur; cp.ldA = ws.ldA; cp.h_off = E; cp.lo_off = ws.lo;
+  if (ws.table) { cp.EG = ws.EG; cp.stat = ws.stat; cp.prev_ids = prev_ids; cp.ld_ids = ld_ids; cp.start_id = START_ID; }
+  AA_PROF("dec_cell", st, launch_decode_cell(cp, st));
   // [q | r] = [h | s] W2^T                                                              adaptive_attention.py:35,45
   if (ws.qr_split) {      // [q | r'] = [h W_g^T | s W_s^T]: two 64-column tiles, K = H each, the second one reading the s window of the rows
     aa::ProfScope ps("dec_qr_gemm", st);
@@ -686,10 +645,8 @@ int aa_greedy_decode(const aa_dims* d, const aa_weights* w, const float* V, cons
   const float* Wp = ws.split ? ws.Wp_s : w->mlp_w;
   for (int t = 0; t < L; ++t) {
     long long* ids_t = reinterpret_cast<long long*>(ids) + t;
-    float* Aread = (ws.cell_fused && (t & 1)) ? ws.Acat2 : ws.Acat;          // (cell in the epilogue: the operand rows alternate)
-    float* Awrite = ws.cell_fused ? ((t & 1) ? ws.Acat : ws.Acat2) : nullptr;
-    AA_TRY(decode_step_body(dd, *w, ws, V, Aread, ws.c, B, 1, attention + (size_t)t * k, (long long)L * k, Beta + t, L, st,
-                            t > 0 ? ids_t - 1 : nullptr, L, Awrite));
+    AA_TRY(decode_step_body(dd, *w, ws, V, ws.Acat, ws.c, B, 1, attention + (size_t)t * k, (long long)L * k, Beta + t, L, st,
+                            t > 0 ? ids_t - 1 : nullptr, L));
     float* emb_dst = ws.table ? nullptr : ws.Acat;      // table mode: the next step reads the word's gate terms from EG, not its embedding
     if (ws.split) {
       // logits = u W_p^T + b_p on tensor cores; the epilogue keeps a per-(row, column tile) arg-max, so the [B,Vc]

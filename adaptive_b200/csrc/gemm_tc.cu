@@ -85,7 +85,6 @@ struct TcEpilogue {
   int kcut_n0, kcut_nkb;                    // tiles whose first column is >= kcut_n0 stop after kcut_nkb k-blocks (their B rows are zero beyond)
   int ashift_n0, ashift_cols;               // split mode: tiles whose first column is >= ashift_n0 read A ashift_cols columns further in
   __nv_bfloat16* ce_e16; long long ld_ce; float* ce_part; int ce_chunks; const long long* ce_tgt; float* ce_xt;   // PM == 3 (TcGemmArgs::ce_*)
-  DecodeCellArgs cell;                                                                                             // PM == 4 (TcGemmArgs::cell)
 };
 
 // Tile geometry (bytes): every smem row is 128 B (the swizzle span).
@@ -99,8 +98,7 @@ struct TcEpilogue {
 // 3K-long tf32 contraction.
 // PM: arg-max partials of the epilogue -- 0 = none (every training contraction: the scan code and its registers stay out of those
 // instantiations), 1 = per-(row, part) maximum and its column index, 2 = maximum only, 3 = cross-entropy pieces per 32-column
-// chunk (maximum, sum of exponentials, exponentials as bf16, the target's logit) instead of the logits, 4 = the LSTM cell + sentinel gate
-// of a decode step on gate-interleaved columns (baseline_attention.py:172, adaptive_attention.py:79-83) instead of the pre-activations
+// chunk (maximum, sum of exponentials, exponentials as bf16, the target's logit) instead of the logits
 // A_RAW (split mode only): the A operand is a PLAIN fp32 array -- one TMA box per stage lands in the hi slot and four converter warps
 // split it there into tf32 (hi, lo) sub-tiles (the split is elementwise, so the swizzled layout stays what the MMA expects).  The
 // operand is read from HBM once instead of being split into a 2x larger array first: P = V W_v^T of the decode prologue, whose
@@ -327,54 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int nb = n0 + c * 32;
         if (row0 >= e.M || nb >= e.N) continue;      // warp-uniform
-        if constexpr (PM == 4) {
-          // this thread's row, 8 hidden units: columns [0,8) = i, [8,16) = f, [16,24) = g, [24,32) = o recurrent pre-activations
-          const DecodeCellArgs& cp = e.cell;
-          const long long row = row0 + lane;
-          const int H = cp.H, u0 = (nb >> 5) * 8;
-          if (row < e.M && u0 < H) {
-            const long long word = cp.prev_ids ? cp.prev_ids[row * cp.ld_ids] : (long long)cp.start_id;
-            const float* eg = cp.EG + word * 5 * H + u0;
-            const float* st = cp.stat + row * 5 * H + u0;
-            float pre[5][8];
-#pragma unroll
-            for (int g = 0; g < 5; ++g) {
-              const float4 e0 = ldg4(eg + g * H), e1 = ldg4(eg + g * H + 4);
-              const float4 s0 = ldg4_stream(st + g * H), s1 = ldg4_stream(st + g * H + 4);
-              pre[g][0] = e0.x + s0.x; pre[g][1] = e0.y + s0.y; pre[g][2] = e0.z + s0.z; pre[g][3] = e0.w + s0.w;
-              pre[g][4] = e1.x + s1.x; pre[g][5] = e1.y + s1.y; pre[g][6] = e1.z + s1.z; pre[g][7] = e1.w + s1.w;
-            }
-            float* crow = cp.c + row * H + u0;
-            const float4 c0 = *reinterpret_cast<const float4*>(crow), c1 = *reinterpret_cast<const float4*>(crow + 4);
-            const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            float cn[8], hn[8], sn[8], hh[8], hl[8], sh[8], sl[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float pi = pre[0][u] + __uint_as_float(r[u]), pf = pre[1][u] + __uint_as_float(r[8 + u]);
-              const float pg = pre[2][u] + __uint_as_float(r[16 + u]), po = pre[3][u] + __uint_as_float(r[24 + u]);
-              const float cc = sigmoidf_acc(pf) * cprev[u] + sigmoidf_acc(pi) * tanhf(pg);
-              const float tcc = tanhf(cc);
-              cn[u] = cc;
-              hn[u] = sigmoidf_acc(po) * tcc;
-              sn[u] = sigmoidf_acc(pre[4][u]) * tcc;
-              split_tf32(hn[u], hh[u], hl[u]);
-              split_tf32(sn[u], sh[u], sl[u]);
-            }
-            auto st8 = [](float* p, const float* v) {
-              *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            };
-            st8(crow, cn);
-            st8(cp.hs + row * 2 * H + u0, hn);
-            st8(cp.hs + row * 2 * H + H + u0, sn);
-            float* arow = cp.A + row * cp.ldA + cp.h_off + u0;
-            st8(arow, hh);
-            st8(arow + cp.lo_off, hl);
-            st8(arow + H, sh);
-            st8(arow + H + cp.lo_off, sl);
-          }
-          continue;
-        } else if constexpr (PM == 3) {
+        if constexpr (PM == 3) {
           // online log-softmax of this thread's row over the chunk's 32 columns: nothing of size [M, N] leaves the SM in fp32
           const long long row = row0 + lane;
           const bool full = nb + 32 <= e.N;
@@ -583,7 +534,6 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
     e.kcut_nkb = ceil_div(g.kcut_cols, 128 / ES);
   }
   if (PM == 3) { e.D16 = g.ce_e16; e.ldd16 = g.ld_ce; }      // the exponentials take the bf16 output path
-  if (PM == 4) e.cell = *g.cell;
   e.ce_e16 = g.ce_e16; e.ld_ce = g.ld_ce; e.ce_part = g.ce_part; e.ce_chunks = g.ce_chunks; e.ce_tgt = g.ce_tgt; e.ce_xt = g.ce_xt;
   e.pmax = g.pmax; e.pidx = g.pidx; e.tiles_n = PM == 2 ? ceil_div(g.N, 16) : ceil_div(g.N, BN / NPARTS); e.lo_a = lo_a; e.lo_b = lo_b;
   constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (BM * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + 32 + EW * 32 * 36 * 4 + 1024;
@@ -680,7 +630,7 @@ int gemm_tc_argmax_tile_n_plain(int) { return 16; }
 
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AA_OK;
-  AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16 || g.pmax || g.ce_e16 || g.cell), "tcgen05 GEMM: bad arguments");
+  AA_REQUIRE(g.K > 0 && g.A && g.B && (g.D32 || g.D16 || g.pmax || g.ce_e16), "tcgen05 GEMM: bad arguments");
   AA_REQUIRE(!g.ce_e16 || (g.elem_size == 2 && !g.split3 && !g.a_mn && !g.b_mn && !g.D32 && !g.D16 && !g.pmax && !g.Cin && g.bias1 && !g.bias2 &&
                            g.ce_part && g.ce_tgt && g.ce_xt && g.ld_ce % 8 == 0 && g.ce_chunks == (g.N + 31) / 32 &&
                            (reinterpret_cast<uintptr_t>(g.ce_e16) & 15) == 0),
@@ -696,12 +646,6 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
     // (256-column tiles -- 128 cycles per MMA for twice the columns -- were measured SLOWER here: only two 96 KB stages fit
     //  and the TMA feed, ~50 B/clk per SM, becomes the bound: vocabulary GEMM 224 us against 205 us, r01_v33)
     if (g.pmax) return g.N > 64 ? launch_cfg<128, 4, 3, false, false, true, 1>(g, st) : launch_cfg<64, 4, 4, false, false, true, 1>(g, st);
-    if (g.cell) {       // decode step: LSTM cell in the epilogue (gate-interleaved weight rows)
-      AA_REQUIRE(!g.pmax && !g.D32 && !g.D16 && !g.Cin && g.cell->H % 8 == 0 && g.N == 4 * g.cell->H && g.cell->EG && g.cell->stat && g.cell->c &&
-                     g.cell->hs && g.cell->A && g.cell->A != g.A,
-                 "tcgen05 GEMM: the cell epilogue needs N = 4H (H %% 8 == 0), the gate table, the static terms and an output operand array");
-      return launch_cfg<128, 4, 3, false, false, true, 4>(g, st);
-    }
     if (g.a_raw) {      // plain fp32 A split on the fly (narrow outputs only: the decode prologue's P = V W_v^T, N = 49)
       AA_REQUIRE(!g.pmax && !g.ashift_cols && g.N <= 64, "tcgen05 GEMM: the on-the-fly split of A serves outputs of at most 64 columns");
       return launch_cfg<64, 4, 4, false, false, true, 0, true>(g, st);

@@ -116,11 +116,6 @@ struct TcGemmArgs {
   // optional (split3 only): A is a PLAIN fp32 array [M, K] (row stride lda) that the kernel splits into tf32 (hi, lo) on the fly in
   // shared memory; B stays pre-split.  N <= 64.
   int a_raw;
-  // optional (split3 only, N = 4H): the LSTM cell + sentinel gate of a decode step in the epilogue instead of a [M, 4H] output
-  // (D32 / D16 null).  B's rows must be gate-interleaved in groups of 8 units -- row (u / 8) * 32 + g * 8 + u % 8 = gate g of unit u --
-  // so that every 32-column chunk of the accumulator holds i, f, g, o of 8 units.  *cell: see DecodeCellArgs (gates unused; `A` is
-  // the operand row array of the NEXT step -- never the one this contraction reads).
-  const struct DecodeCellArgs* cell;
   // optional (plain bf16, K-major): cross-entropy pieces instead of the logits (train.py:63,208 fused into the vocabulary projection's
   // epilogue; D32 / D16 null).  Per row and 32-column chunk of D (+ bias1): the chunk maximum m and s = sum exp(x - m) go to
   // ce_part[(row * ce_chunks + chunk) * 2 + {0, 1}], e = exp(x - m) as bf16 to ce_e16[row * ld_ce + col], and the target column's
