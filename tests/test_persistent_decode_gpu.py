@@ -105,17 +105,38 @@ def test_persistent_sharding_and_weight_updates():
     assert (ids_n == ids_ref).float().mean() > 0.95 and not torch.equal(ids_n, ids)
 
 
+def test_auto_engine_takes_two_persistent_launches_up_to_two_images_per_sm():
+    """B in (SMs, 2 SMs]: the auto engine decodes the batch as two persistent launches; same ids as the pipeline (near-ties excepted),
+    and row i of the result is image i (no reordering by the split)."""
+    dims, L = CFG_A, 10
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 2 * sms - 3
+    w = make_weights(dims, seed=123)
+    W = dev_weights(w)
+    inp = make_inputs(dims, B, 1, seed=17)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+    ids_a, att_a, bet_a = F_aa.greedy_decode(W, V, v_g, h0[None], c0[None], L, engine="auto")      # [1,B,H] states: cut along dim 1
+    ids_p, att_p, bet_p = F_aa.greedy_decode(W, V, v_g, h0, c0, L, engine="pipeline")
+    assert ids_a.shape == (B, L) and att_a.shape == (B, L, dims.k)
+    agree = (ids_a == ids_p).all(1)
+    assert agree.float().mean() > 0.9
+    assert rel_err(att_a[agree].cpu().numpy(), att_p[agree].cpu().numpy()) < 2e-5
+    half = (B + 1) // 2
+    lo = F_aa.greedy_decode_persistent(W, V[half:], v_g[half:], h0[half:], c0[half:], L)[0]
+    assert torch.equal(ids_a[half:], lo)
+
+
 def test_persistent_rejects_what_it_cannot_hold():
     dims = CFG_A
     w = make_weights(dims, seed=123)
     W = dev_weights(w)
-    B = torch.cuda.get_device_properties(0).multi_processor_count + 1
+    B = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 1
     inp = make_inputs(dims, B, 1, seed=3)
     V, v_g, h0, c0, _ = dev_inputs(inp)
     assert not F_aa.persistent_decode_supported(W, V, v_g, 5)
     with pytest.raises(RuntimeError, match="does not fit"):
         F_aa.greedy_decode(W, V, v_g, h0, c0, 5, engine="persistent")
-    ids_a = F_aa.greedy_decode(W, V, v_g, h0, c0, 5, engine="auto")[0]        # falls back to the pipeline
+    ids_a = F_aa.greedy_decode(W, V, v_g, h0, c0, 5, engine="auto")[0]        # more than two images per SM: falls back to the pipeline
     ids_p = F_aa.greedy_decode(W, V, v_g, h0, c0, 5, engine="pipeline")[0]
     assert torch.equal(ids_a, ids_p)
 
