@@ -498,6 +498,13 @@ def measure_decode_small(torch, dev, model, dims, peaks):
                                                           "charged with is V, P once per image + 18.6 KB per step"}}
             else:
                 row["persistent"] = None
+                if sms < B <= 2 * sms:
+                    # two persistent launches (functional.greedy_decode, engine "auto"): what model.sampler does by default here
+                    model.decoder.decode_engine = "auto"
+                    ids_auto = model.sampler(enc, max_len=DECODE_L)[0]
+                    ms = time_fn(torch, lambda: model.sampler(enc, max_len=DECODE_L), 20, warm=3)
+                    row["auto_two_persistent_launches"] = {"tokens_per_s": B * DECODE_L / (ms * 1e-3), "ms": ms,
+                                                           "ids_equal_pipeline": float((ids_auto == ids_pipe).all(1).float().mean())}
             rows.append(row)
     finally:
         model.decoder.decode_engine = eng0
