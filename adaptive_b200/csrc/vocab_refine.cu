@@ -13,9 +13,9 @@
 //      maximum + bound reaches the best (approximate maximum - bound) of the row; those (row, tile) pairs -- ~1.3 per row for
 //      tf32, ~2.2 for bf16 at config 3 (625 tiles) -- are appended to the tile's row list together with their rank ("slot")
 //      among the row's candidates (tests/test_host_cpu.py::test_argmax_filter_bound_never_drops_the_exact_argmax checks the bound in numpy);
-//   3. argmax_refine: work units (tile, chunk of listed rows) dealt to a persistent grid; a unit keeps the tile's 16 fp32 weight
-//      rows in shared memory and recomputes the listed rows' 16 logits in plain fp32 FMA arithmetic, writing the tile's exact
-//      (max, index) to the row's slot;
+//   3. argmax_refine: work units (tile, chunk of listed rows) dealt to a persistent grid -- per CTA with the tile's 16 fp32 weight
+//      rows in shared memory for the tiles many rows list, per warp straight from L2 for the others -- recompute the listed rows'
+//      16 logits in plain fp32 FMA arithmetic and write the tile's exact (max, index) to the row's slot;
 //   4. argmax_finalize reduces the row's ncand[row] refined candidates (lowest index wins ties) and gathers the next embedding.
 // Every column that could be the exact arg-max is recomputed exactly, so the ids equal those of an exact fp32 projection
 // (up to fp32 summation order, like any fp32 implementation).
@@ -164,65 +164,263 @@ __global__ void __launch_bounds__(FL_THREADS) argmax_filter_kernel(const float* 
   }
 }
 
-// Exact fp32 logits of the listed rows.  Work unit = (16-column tile, chunk of up to 32 listed rows); the units are dealt round
-// robin to a persistent grid.  (One CTA per tile is not enough: at a given step most rows of a batch favour the same few words --
-// with the synthetic weights nearly all 4096 rows list the same tile -- and that CTA would do all the work.)
-// A CTA keeps the unit's 16 weight rows in shared memory; each warp carries RF_ROWS rows through one pass over them, lane =
-// (column, half of the reduction range).
-__global__ void __launch_bounds__(RF_THREADS, 2) argmax_refine_kernel(const float* __restrict__ W, const float* __restrict__ bias, int Vc, int H,
-                                                                      const float* __restrict__ u, long long ldu, long long lo_off, int R,
-                                                                      int* __restrict__ counts, const unsigned* __restrict__ list,
-                                                                      float* __restrict__ pmax, int* __restrict__ pidx, int tiles) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int CH = RF_WARPS * RF_ROWS;               // listed rows per work unit
+// The same filter with the row's maxima and bounds held in REGISTERS (NT values per lane, tiles <= 32 NT): one read of the maxima,
+// one evaluation of the bounds, the candidates remembered as a bit mask per lane -- the staged kernel above reads its shared-memory copy
+// three times and re-evaluates every bound twice (1745 instructions per row at config 3, latency-bound at 19 us per step:
+// profiles/r02_decode_ncu_details.txt).  A candidate's slot is its rank in (lane, tile) order: any numbering 0 .. ncand - 1 serves, the
+// final reduction is order-independent (lowest index wins ties).
+template <int NT>
+__global__ void __launch_bounds__(FL_THREADS) argmax_filter_reg_kernel(const float* __restrict__ pmax, int tiles, int R, const float* __restrict__ u,
+                                                                       long long ldu, long long lo_off, int H, const float* __restrict__ wnorm,
+                                                                       float c, int* __restrict__ counts, unsigned* __restrict__ list,
+                                                                       int* __restrict__ ncand, const __nv_bfloat16* __restrict__ u16,
+                                                                       long long ld16, const float* __restrict__ dwnorm) {
+  extern __shared__ int fsm[];
+  int* scnt = fsm;                                              // [tiles]
+  float* wn = reinterpret_cast<float*>(fsm + tiles);            // [tiles]
+  float* dwn = wn + tiles;                                      // [tiles]
+  __shared__ int spairs;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ldw = H + 4;                               // (H % 32 == 0: 8 lanes x 16 B of one LDS.128 phase hit 32 distinct banks)
-  float* Ws = sm;                                      // [RF_TN][H + 4]
-  float* us = sm + RF_TN * ldw + warp * RF_ROWS * H;   // [RF_ROWS][H] per warp
-  int* pre = reinterpret_cast<int*>(sm + RF_TN * ldw + RF_WARPS * RF_ROWS * H);   // [tiles + 1] exclusive prefix of the units per tile
-  {   // blocked exclusive scan of the units per tile: thread i owns tiles [i * per, (i + 1) * per)
-    __shared__ int wsum[RF_WARPS];
-    const int per = (tiles + RF_THREADS - 1) / RF_THREADS;
-    int loc = 0;
-    for (int i = 0; i < per; ++i) {
-      const int t = tid * per + i;
-      const int c = t < tiles ? (__ldcg(counts + t) + CH - 1) / CH : 0;
-      if (t < tiles) pre[t] = c;
-      loc += c;
+  const int r = blockIdx.x * FL_ROWS + warp;
+  const bool live = r < R;
+  for (int t = tid; t < tiles; t += FL_THREADS) {
+    scnt[t] = 0;
+    wn[t] = __ldg(wnorm + t);
+    dwn[t] = dwnorm ? __ldg(dwnorm + t) : 0.f;
+  }
+  if (tid == 0) spairs = 0;
+  float p[NT];
+  float cn = 0.f, cd = 0.f;
+  if (live) {
+    const float* pr = pmax + (long long)r * tiles;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) p[i] = (i * 32 + lane < tiles) ? __ldcg(pr + i * 32 + lane) : -INFINITY;
+    const float* ur = u + (long long)r * ldu;
+    float ss = 0.f, sh = 0.f, sd = 0.f;
+    for (int k = lane * 4; k < H; k += 128) {
+      const float4 hi = __ldcg(reinterpret_cast<const float4*>(ur + k)), lo = __ldcg(reinterpret_cast<const float4*>(ur + lo_off + k));
+      const float x0 = hi.x + lo.x, x1 = hi.y + lo.y, x2 = hi.z + lo.z, x3 = hi.w + lo.w;
+      ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+      if (u16) {      // the mirror the first pass actually contracted with
+        const uint2 pk = __ldcg(reinterpret_cast<const uint2*>(u16 + (long long)r * ld16 + k));
+        const float h0 = __uint_as_float(pk.x << 16), h1 = __uint_as_float(pk.x & 0xffff0000u);
+        const float h2 = __uint_as_float(pk.y << 16), h3 = __uint_as_float(pk.y & 0xffff0000u);
+        sh = fmaf(h0, h0, sh); sh = fmaf(h1, h1, sh); sh = fmaf(h2, h2, sh); sh = fmaf(h3, h3, sh);
+        const float d0 = x0 - h0, d1 = x1 - h1, d2 = x2 - h2, d3 = x3 - h3;
+        sd = fmaf(d0, d0, sd); sd = fmaf(d1, d1, sd); sd = fmaf(d2, d2, sd); sd = fmaf(d3, d3, sd);
+      }
     }
-    int inc = loc;
+    const float nu = sqrtf(warp_sum(ss));
+    if (u16) {
+      cn = sqrtf(warp_sum(sd)) * (1.f + 1e-5f) + 1.220703125e-4f * nu;      // ||u - u^|| + 2^-13 ||u||
+      cd = sqrtf(warp_sum(sh)) * (1.f + 1e-5f);
+    } else {
+      cn = c * nu * (1.f + 1e-6f);
+    }
+  }
+  __syncthreads();
+  unsigned fm = 0;                  // bit i: tile i * 32 + lane is a candidate of this row
+  int slot0 = 0;
+  if (live) {
+    float b[NT];
+    float lo_best = -INFINITY;      // best lower bound of the row's exact maximum
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int t = min(i * 32 + lane, tiles - 1);
+      b[i] = cn * wn[t] + cd * dwn[t];
+      lo_best = fmaxf(lo_best, p[i] - b[i]);        // (p = -inf past the last tile)
+    }
+    const float L = warp_max(lo_best);
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+      if (i * 32 + lane < tiles && p[i] + b[i] >= L) {       // the tile's exact maximum may reach the row's: refine it
+        fm |= 1u << i;
+        atomicAdd(&scnt[i * 32 + lane], 1);
+      }
+    const int mine = __popc(fm);
+    int inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += v;
     }
-    if (lane == 31) wsum[warp] = inc;
+    slot0 = inc - mine;
+    if (lane == 31) {
+      ncand[r] = inc;
+      atomicAdd(&spairs, inc);
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < tiles; t += FL_THREADS) {
+    const int n = scnt[t];
+    scnt[t] = n > 0 ? atomicAdd(&counts[t], n) : 0;      // this CTA's range in the tile's list
+  }
+  if (tid == 0) atomicAdd(&d_refine_pairs, (unsigned long long)spairs);
+  __syncthreads();
+  while (fm) {
+    const int i = __ffs(fm) - 1;
+    fm &= fm - 1;
+    const int t = i * 32 + lane;
+    const int pos = atomicAdd(&scnt[t], 1);
+    list[(long long)t * R + pos] = (unsigned)r | ((unsigned)slot0++ << 20);
+  }
+}
+
+// Exact fp32 logits of the listed rows, two kinds of work units dealt to a persistent grid:
+//   HOT  tiles (listed by more than RF_COLD_MAX rows -- at a given step most rows of a batch favour the same few words; with the
+//        synthetic weights nearly all 4096 rows list the same tile): (tile, chunk of up to 32 listed rows) per CTA, the tile's 16 fp32
+//        weight rows staged in shared memory once per CTA and tile, RF_ROWS rows per warp;
+//   COLD tiles (a few rows each, several hundred of them per step): (tile, up to RF_COLD_ROWS rows) per WARP, the weights read straight
+//        from L2.  As CTA units each of them cost a whole CTA the fixed latency of a 32 KB tile load for one busy warp, and the
+//        kernel ran 2-3 such rounds deep (29 us at config 3, 60 % of the SMs idle at the end: profiles/r02_decode_ncu_details.txt).
+// Both kinds go through refine_rows(): lanes along the reduction dimension (coalesced 512-byte reads of u and W), rows x 16 accumulators
+// per lane, ONE fixed butterfly to reduce them -- the same summation order whichever kind of unit a (row, tile) pair lands in, so an
+// image's ids do not depend on how many batch mates list the same tile (the shard == slice property of the decode tests).
+constexpr int RF_COLD_MAX = 8;
+constexpr int RF_COLD_ROWS = 2;     // rows per cold (warp) unit: leaves the registers for 16 weight reads in flight
+
+template <bool W_SMEM, int NR>
+__device__ __forceinline__ void refine_rows(const float* __restrict__ Wt, long long ldw, int nc, const float* __restrict__ bias, int j0,
+                                            const float* __restrict__ u, long long ldu, long long lo_off, int H,
+                                            const unsigned* __restrict__ lst, int i0, int n, float* __restrict__ pmax, int* __restrict__ pidx,
+                                            int tiles, int lane) {
+  static_assert(NR == 2 || NR == 4, "2 or 4 rows per warp");
+  int rows[NR];
+#pragma unroll
+  for (int m = 0; m < NR; ++m) rows[m] = (int)(lst[min(i0 + m, n - 1)] & 0xFFFFFu);
+  float acc[NR * RF_TN];
+#pragma unroll
+  for (int i = 0; i < NR * RF_TN; ++i) acc[i] = 0.f;
+  for (int k = lane * 4; k < H; k += 128) {
+    float4 uv[NR];
+#pragma unroll
+    for (int m = 0; m < NR; ++m) {
+      const float* ur = u + (long long)rows[m] * ldu + k;
+      const float4 hi = __ldcg(reinterpret_cast<const float4*>(ur)), lo = __ldcg(reinterpret_cast<const float4*>(ur + lo_off));
+      uv[m] = make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
+    }
+    if constexpr (W_SMEM) {
+#pragma unroll
+      for (int j = 0; j < RF_TN; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(Wt + j * ldw + k);       // (rows past nc are zero-filled)
+#pragma unroll
+        for (int m = 0; m < NR; ++m) {
+          float a = acc[m * RF_TN + j];
+          a = fmaf(uv[m].x, x.x, a); a = fmaf(uv[m].y, x.y, a); a = fmaf(uv[m].z, x.z, a); a = fmaf(uv[m].w, x.w, a);
+          acc[m * RF_TN + j] = a;
+        }
+      }
+    } else {
+      float4 x[RF_TN];            // all 16 reads from L2 in flight before the first FMA (the point of carrying only NR = 2 rows here)
+#pragma unroll
+      for (int j = 0; j < RF_TN; ++j)
+        x[j] = j < nc ? __ldg(reinterpret_cast<const float4*>(Wt + j * ldw + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < RF_TN; ++j) {
+#pragma unroll
+        for (int m = 0; m < NR; ++m) {
+          float a = acc[m * RF_TN + j];
+          a = fmaf(uv[m].x, x[j].x, a); a = fmaf(uv[m].y, x[j].y, a); a = fmaf(uv[m].z, x[j].z, a); a = fmaf(uv[m].w, x[j].w, a);
+          acc[m * RF_TN + j] = a;
+        }
+      }
+    }
+  }
+  // NR * 16 sums x 32 lanes -> NR / 2 per lane: at every stage (lane bits 4, 3, 2, 1, 0 in this order -- the same reduction tree over
+  // the lanes' partial sums for every value and for either NR) a lane keeps the half of its values whose index bit matches its lane bit
+  // and hands the other half to its partner.
+#pragma unroll
+  for (int half = NR * RF_TN / 2, bit = 16; bit >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? acc[i] : acc[i + half];
+      const float keep = up ? acc[i + half] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  // NR == 4: lane l holds i = 2 l, 2 l + 1 (i = row * 16 + column): row l / 8, columns 2 (l % 8), + 1.   NR == 2: lane l holds i = l.
+  constexpr int LPR = 32 / NR;                     // lanes per row
+  constexpr int CPL = RF_TN / LPR;                 // columns per lane (2 or 1)
+  const int m = lane / LPR, c0 = (lane % LPR) * CPL;
+  float best = c0 < nc ? acc[0] + (bias ? __ldg(bias + j0 + c0) : 0.f) : -INFINITY;
+  int bi = j0 + c0;
+  if constexpr (CPL == 2) {
+    const float b1 = c0 + 1 < nc ? acc[1] + (bias ? __ldg(bias + j0 + c0 + 1) : 0.f) : -INFINITY;
+    if (b1 > best) { best = b1; bi = j0 + c0 + 1; }            // (the lower column wins a tie)
+  }
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane % LPR == 0 && i0 + m < n) {          // (compacted: the row's slot-th candidate)
+    const unsigned e = lst[i0 + m];
+    const long long o = (long long)(e & 0xFFFFFu) * tiles + (e >> 20);
+    pmax[o] = best;
+    pidx[o] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(RF_THREADS, 2) argmax_refine_kernel(const float* __restrict__ W, const float* __restrict__ bias, int Vc, int H,
+                                                                      const float* __restrict__ u, long long ldu, long long lo_off, int R,
+                                                                      int* __restrict__ counts, const unsigned* __restrict__ list,
+                                                                      float* __restrict__ pmax, int* __restrict__ pidx, int tiles) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int CH = RF_WARPS * RF_ROWS;               // listed rows per CTA unit
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ldw = H + 4;
+  float* Ws = sm;                                      // [RF_TN][H + 4]
+  int* preH = reinterpret_cast<int*>(sm + RF_TN * ldw);   // [tiles + 1] exclusive prefix of the CTA units per tile
+  int* preC = preH + tiles + 1;                           // [tiles + 1] exclusive prefix of the warp units per tile
+  {   // blocked exclusive scans: thread i owns tiles [i * per, (i + 1) * per)
+    __shared__ int wsumH[RF_WARPS], wsumC[RF_WARPS];
+    const int per = (tiles + RF_THREADS - 1) / RF_THREADS;
+    int locH = 0, locC = 0;
+    for (int i = 0; i < per; ++i) {
+      const int t = tid * per + i;
+      const int n = t < tiles ? __ldcg(counts + t) : 0;
+      const int cH = n > RF_COLD_MAX ? (n + CH - 1) / CH : 0, cC = n > RF_COLD_MAX ? 0 : (n + RF_COLD_ROWS - 1) / RF_COLD_ROWS;
+      if (t < tiles) { preH[t] = cH; preC[t] = cC; }
+      locH += cH;
+      locC += cC;
+    }
+    int incH = locH, incC = locC;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int vH = __shfl_up_sync(0xffffffffu, incH, o), vC = __shfl_up_sync(0xffffffffu, incC, o);
+      if (lane >= o) { incH += vH; incC += vC; }
+    }
+    if (lane == 31) { wsumH[warp] = incH; wsumC[warp] = incC; }
     __syncthreads();
-    int base = 0;
-    for (int w2 = 0; w2 < warp; ++w2) base += wsum[w2];
-    int acc = base + inc - loc;
+    int baseH = 0, baseC = 0;
+    for (int w2 = 0; w2 < warp; ++w2) { baseH += wsumH[w2]; baseC += wsumC[w2]; }
+    int accH = baseH + incH - locH, accC = baseC + incC - locC;
     for (int i = 0; i < per; ++i) {
       const int t = tid * per + i;
       if (t < tiles) {
-        const int c = pre[t];
-        pre[t] = acc;
-        acc += c;
+        const int cH = preH[t], cC = preC[t];
+        preH[t] = accH; preC[t] = accC;
+        accH += cH; accC += cC;
       }
     }
-    if (tid == RF_THREADS - 1) pre[tiles] = base + inc;
+    if (tid == RF_THREADS - 1) { preH[tiles] = baseH + incH; preC[tiles] = baseC + incC; }
   }
   __syncthreads();
-  const int total = pre[tiles];
-  const int h4 = H / 4, hh4 = H / 8;                   // float4s per row / per half row
-  const int col = lane & (RF_TN - 1), kh = lane >> 4;  // this lane's column of the tile and half of the reduction range
-  int cur_tile = -1;
-  for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
-    int lo_t = 0, hi_t = tiles - 1;                    // largest t with pre[t] <= unit (tiles without units share the next one's prefix)
+  auto find = [&](const int* pre, int unit) {          // largest t with pre[t] <= unit (tiles without units share the next one's prefix)
+    int lo_t = 0, hi_t = tiles - 1;
     while (lo_t < hi_t) {
       const int mid = (lo_t + hi_t + 1) >> 1;
       if (pre[mid] <= unit) lo_t = mid; else hi_t = mid - 1;
     }
-    const int t = lo_t, chunk = unit - pre[t];
+    return lo_t;
+  };
+  const int totalH = preH[tiles], totalC = preC[tiles];
+  const int h4 = H / 4;
+  int cur_tile = -1;
+  for (int unit = blockIdx.x; unit < totalH; unit += gridDim.x) {
+    const int t = find(preH, unit), chunk = unit - preH[t];
     const int n = __ldcg(counts + t);
     const int j0 = t * RF_TN, nc = min(RF_TN, Vc - j0);
     if (t != cur_tile) {
@@ -243,73 +441,26 @@ __global__ void __launch_bounds__(RF_THREADS, 2) argmax_refine_kernel(const floa
     }
     const int i0 = chunk * CH + warp * RF_ROWS;
     if (i0 >= n) continue;                             // (warp-uniform; the barriers above are reached by every warp of the CTA)
-    const float bj = col < nc ? (bias ? __ldg(bias + j0 + col) : 0.f) : -INFINITY;
-    const float4* wp = reinterpret_cast<const float4*>(Ws + col * ldw) + kh * hh4;
-    int rows[RF_ROWS], slots[RF_ROWS];
-#pragma unroll
-    for (int m = 0; m < RF_ROWS; ++m) {
-      const unsigned e = list[(long long)t * R + min(i0 + m, n - 1)];
-      rows[m] = (int)(e & 0xFFFFFu);
-      slots[m] = (int)(e >> 20);
-    }
-    for (int k = lane * 4; k < H; k += 128) {            // (the RF_ROWS rows' loads of one k are issued together)
-      float4 hi[RF_ROWS], lo[RF_ROWS];
-#pragma unroll
-      for (int m = 0; m < RF_ROWS; ++m) {
-        const float* ur = u + (long long)rows[m] * ldu;
-        hi[m] = __ldcg(reinterpret_cast<const float4*>(ur + k));
-        lo[m] = __ldcg(reinterpret_cast<const float4*>(ur + lo_off + k));
-      }
-#pragma unroll
-      for (int m = 0; m < RF_ROWS; ++m)
-        *reinterpret_cast<float4*>(us + m * H + k) = make_float4(hi[m].x + lo[m].x, hi[m].y + lo[m].y, hi[m].z + lo[m].z, hi[m].w + lo[m].w);
-    }
-    __syncwarp();
-    float4 a[RF_ROWS];                                   // four partial sums (k mod 4) per row, this lane's column and half range
-#pragma unroll
-    for (int m = 0; m < RF_ROWS; ++m) a[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* up = reinterpret_cast<const float4*>(us) + kh * hh4;
-#pragma unroll 4
-    for (int k4 = 0; k4 < hh4; ++k4) {
-      const float4 x = wp[k4];
-#pragma unroll
-      for (int m = 0; m < RF_ROWS; ++m) {
-        const float4 uv = up[m * h4 + k4];
-        a[m].x = fmaf(uv.x, x.x, a[m].x); a[m].y = fmaf(uv.y, x.y, a[m].y);
-        a[m].z = fmaf(uv.z, x.z, a[m].z); a[m].w = fmaf(uv.w, x.w, a[m].w);
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < RF_ROWS; ++m) {
-      float v = (a[m].x + a[m].y) + (a[m].z + a[m].w);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);           // the two halves of the reduction range (same sum in both lanes)
-      float best = v + bj;
-      int bi = j0 + col;
-#pragma unroll
-      for (int o = RF_TN / 2; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }   // (the lower column wins a tie)
-      }
-      if (lane == 0 && i0 + m < n) {          // (compacted: the row's slot-th candidate)
-        pmax[(long long)rows[m] * tiles + slots[m]] = best;
-        pidx[(long long)rows[m] * tiles + slots[m]] = bi;
-      }
-    }
-    __syncwarp();
+    refine_rows<true, RF_ROWS>(Ws, ldw, nc, bias, j0, u, ldu, lo_off, H, list + (long long)t * R, i0, n, pmax, pidx, tiles, lane);
+  }
+  // cold units, one per warp; dealt from the far end of the grid so that the CTAs without a hot unit start on them at once
+  for (int unit = ((int)gridDim.x - 1 - (int)blockIdx.x) * RF_WARPS + warp; unit < totalC; unit += gridDim.x * RF_WARPS) {
+    const int t = find(preC, unit), chunk = unit - preC[t];
+    const int n = __ldcg(counts + t);
+    const int j0 = t * RF_TN, nc = min(RF_TN, Vc - j0);
+    refine_rows<false, RF_COLD_ROWS>(W + (long long)j0 * H, H, nc, bias, j0, u, ldu, lo_off, H, list + (long long)t * R, chunk * RF_COLD_ROWS, n, pmax, pidx, tiles, lane);
   }
   // the CTA that finishes last clears the lists for the next step's filter (counts[tiles] = number of finished CTAs)
   __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    if (atomicAdd(&counts[tiles], 1) == (int)gridDim.x - 1) {
-      for (int t = 0; t <= tiles; ++t) counts[t] = 0;
-      __threadfence();
-    }
+  if (tid == 0) __threadfence();
+  int last = 0;
+  if (tid == 0) last = atomicAdd(&counts[tiles], 1) == (int)gridDim.x - 1;
+  if (__syncthreads_or(last)) {
+    for (int t = tid; t <= tiles; t += RF_THREADS) counts[t] = 0;
   }
 }
 
-size_t refine_smem(int H, int tiles) { return sizeof(float) * ((size_t)RF_TN * (H + 4) + (size_t)RF_WARPS * RF_ROWS * H + tiles + 1); }
+size_t refine_smem(int H, int tiles) { return sizeof(float) * ((size_t)RF_TN * (H + 4) + 2 * ((size_t)tiles + 1)); }
 
 }  // namespace
 
@@ -324,7 +475,7 @@ long long refine_pairs(int reset) {
 }
 
 bool argmax_refine_supported(int Vc, int H) {
-  // (12-bit slots in the list entries: at most 4096 tiles; the refinement's shared memory -- 16 weight rows + 32 rows of u -- must fit one SM)
+  // (12-bit slots in the list entries: at most 4096 tiles; the refinement's shared memory -- 16 weight rows + two prefix arrays -- must fit one SM)
   return Vc > 64 && Vc <= 4096 * RF_TN && H % 8 == 0 && refine_smem(H, ceil_div(Vc, RF_TN)) <= 220 * 1024;
 }
 
@@ -338,6 +489,15 @@ int launch_argmax_filter(const float* pmax, int tiles, int R, const float* u, lo
                          int* counts, unsigned* list, int* ncand, cudaStream_t s, const __nv_bfloat16* u16, long long ld16, const float* dwnorm) {
   AA_REQUIRE(R <= (1 << 20) && tiles <= 3900, "argmax_filter: at most 2^20 rows and 3900 tiles (got %d, %d)", R, tiles);
   AA_REQUIRE((u16 == nullptr) == (dwnorm == nullptr) && (!u16 || (ld16 % 4 == 0 && H % 4 == 0)), "argmax_filter: the bf16 mirror and the residual norms go together");
+  if (tiles <= 1024) {
+    const unsigned grid = ceil_div(R, FL_ROWS);
+    const size_t sm = sizeof(int) * tiles * 3;
+    if (tiles <= 256) argmax_filter_reg_kernel<8><<<grid, FL_THREADS, sm, s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm, c, counts, list, ncand, u16, ld16, dwnorm);
+    else if (tiles <= 640) argmax_filter_reg_kernel<20><<<grid, FL_THREADS, sm, s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm, c, counts, list, ncand, u16, ld16, dwnorm);
+    else argmax_filter_reg_kernel<32><<<grid, FL_THREADS, sm, s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm, c, counts, list, ncand, u16, ld16, dwnorm);
+    AA_CHECK_LAUNCH("argmax_filter");
+    return AA_OK;
+  }
   const int stage = tiles <= 1100 ? 1 : 0;      // (3 + 8 arrays of one entry per tile within the default 48 KB of shared memory)
   argmax_filter_kernel<<<ceil_div(R, FL_ROWS), FL_THREADS, sizeof(int) * tiles * (3 + (stage ? FL_ROWS : 0)), s>>>(pmax, tiles, R, u, ldu, lo_off, H, wnorm,
                                                                                                             c, counts, list, ncand, stage, u16, ld16, dwnorm);
