@@ -87,6 +87,7 @@ SIGNATURES = {
     "aa_debug_set_atten_sequential": (c_int, [c_int]),
     "aa_debug_set_decode_argmax_refine": (c_int, [c_int]),
     "aa_debug_refine_pairs": (ctypes.c_longlong, [c_int]),
+    "aa_debug_refine_units": (c_int, [ctypes.c_void_p, c_int]),
     "aa_debug_set_gemm_splitk": (c_int, [c_int]),
     "aa_debug_set_bptt_ksplit": (c_int, [c_int]),
     "aa_debug_set_lstm_cluster": (c_int, [c_int, c_int]),

@@ -610,6 +610,7 @@ using namespace aa;
 extern "C" {
 
 long long aa_debug_refine_pairs(int reset) { return aa::refine_pairs(reset); }
+int aa_debug_refine_units(long long* out4, int reset) { return out4 ? aa::refine_units(out4, reset) : AA_ERR_INVALID; }
 
 int aa_debug_set_decode_argmax_refine(int on) {
   g_argmax_refine = on < 0 ? 0 : (on > 2 ? 2 : on);

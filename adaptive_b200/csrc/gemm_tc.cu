@@ -574,6 +574,357 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
   return AA_OK;
 }
 
+// ---- CTA-pair contraction (tcgen05.mma.cta_group::2) ---------------------------------------------------------------------
+// Two CTAs on the two SMs of one TPC (cluster of 2) share a 256 x 256 output tile: each stages ITS 128 rows of A and ITS 128
+// rows of B per k-block, the leader's elected thread issues one M = 256, N = 256 MMA per k-step for both SMs (each tensor core
+// reads its own A half and both B halves), and each CTA's tensor memory receives its 128 rows x 256 columns of the accumulator.
+// Per SM and k-block the same 32 KB (bf16) / 64 KB (3xTF32) of operands as a 128 x 128 single-CTA tile -- for twice the output:
+// the K = 512 contractions of the decode step are bound by the operand feed from L2 (~50 B/clk per SM, ~6300 B/clk for the chip:
+// profiles/r02_* and DESIGN.md 4), not by the tensor pipe, and a 256-wide MMA costs 128 cycles against 103 for a 128-wide one.
+//   barriers: full[s] lives in the LEADER (both CTAs' TMA loads complete on it: cp.async.bulk.tensor ... .cta_group::2 with the
+//   peer bit of the barrier address cleared); empty[s] and tmem_full[a] exist in both CTAs and are signalled by ONE multicast
+//   tcgen05.commit; tmem_empty[a] lives in the leader and counts the epilogue warps of both CTAs (remote mbarrier.arrive).
+// K-major operands only; epilogue = the single-CTA kernel's (bias, C input, fp32 / bf16 stores, PM == 2 maxima per 16 columns).
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the even (leader) CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(leader_bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {      // arrives on `bar` of BOTH CTAs when the MMAs issued so far are done
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+template <int ES, int STAGES, bool SPLIT, int PM>
+__global__ void __launch_bounds__(tc_threads(SPLIT), 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m, int num_tiles) {
+  static_assert(PM == 0 || PM == 2, "pair kernel: no epilogue partials other than the maxima");
+  constexpr bool TF32 = (ES == 4);
+  constexpr int BH = 128;                  // rows of A and of B this CTA stages
+  constexpr int BN2 = 256;                 // columns of the pair's tile (= accumulator columns per CTA)
+  constexpr int BK = 128 / ES;
+  constexpr int UMMA_K = 32 / ES;
+  constexpr uint32_t A_BYTES = BH * 128, B_BYTES = BH * 128;
+  constexpr uint32_t A_STAGE = SPLIT ? 2 * A_BYTES : A_BYTES, B_STAGE = SPLIT ? 2 * B_BYTES : B_BYTES;
+  constexpr uint32_t TCOLS = 512;          // two accumulators of 256 columns
+  constexpr int EW = epi_warps(SPLIT);
+  constexpr int NCH = BN2 / 32;
+  constexpr int NPARTS = EW / 4;
+  constexpr int CPP = NCH / NPARTS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2] (the leader's are used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nkb = (e.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);        // the leader's producer arms it with the bytes of both CTAs
+      mbar_init(&empty_bar[s], 1);       // one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * EW); // the epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {      // the same warp of both CTAs, the same shared-memory offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs: this CTA's halves) =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int ma = (tile % tiles_m) * 256 + (int)rank * BH, nb = (tile / tiles_m) * BN2 + (int)rank * BH;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_STAGE + B_STAGE));
+          uint8_t* a_dst = sA + s * A_STAGE;
+          uint8_t* b_dst = sB + s * B_STAGE;
+          tma2_load_2d(a_dst, &tmA, kb * BK, ma, &full_bar[s]);
+          tma2_load_2d(b_dst, &tmB, kb * BK, nb, &full_bar[s]);
+          if constexpr (SPLIT) {
+            tma2_load_2d(a_dst + A_BYTES, &tmA, e.lo_a + kb * BK, ma, &full_bar[s]);
+            tma2_load_2d(b_dst + B_BYTES, &tmB, e.lo_b + kb * BK, nb, &full_bar[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA only =====
+    if (rank == 0) {
+      constexpr uint32_t fmt = TF32 ? 2u : 1u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN2);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if constexpr (SPLIT) {
+                const uint64_t ah = make_smem_desc(a_addr + k * 32, 16, 1024), al = make_smem_desc(a_addr + A_BYTES + k * 32, 16, 1024);
+                const uint64_t bh = make_smem_desc(b_addr + k * 32, 16, 1024), bl = make_smem_desc(b_addr + B_BYTES + k * 32, 16, 1024);
+                tc2_mma<true>(tmem_d, al, bh, idesc, (kb | k) != 0 ? 1u : 0u);
+                tc2_mma<true>(tmem_d, ah, bl, idesc, 1u);
+                tc2_mma<true>(tmem_d, ah, bh, idesc, 1u);
+              } else {
+                tc2_mma<TF32>(tmem_d, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            tc2_commit(&empty_bar[s]);   // frees the stage in both CTAs
+          }
+          __syncwarp();
+        }
+        if (elect_one()) tc2_commit(&tmem_full[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs: this CTA's 128 rows x 256 columns) =====
+    // launch_pair() guarantees: N % 16 == 0; 16-byte aligned bias, C input and output with row strides that are multiples of 4
+    // floats; no bf16 output -- no scalar fall-back paths here (they made this kernel 60 KB of code, and the MMA warp's
+    // instruction fetches missed: 45 -> 60 us per launch).
+    // Either form keeps the NEXT chunk's accumulator read (tensor memory) and global loads (bias / C input) in flight while the
+    // current chunk is worked on -- two register sets, two copies of the stage.  Done strictly in sequence a chunk cost a warp
+    // ~1800 cycles (maxima) / ~2.5 us (stores with a C input from HBM): 7200 cycles of epilogue per tile against 4100 cycles of
+    // MMAs in the vocabulary pass, and 20 us of exposed last-tile epilogue in the decode step's gate contraction
+    // (profiles/r02_pair_ncu_details.txt).
+    const int q = warp & 3;
+    constexpr int TS = 36;
+    uint8_t* tb0 = reinterpret_cast<uint8_t*>(tmem_slot + 1);
+    float* tbuf = reinterpret_cast<float*>(tb0 + ((16u - (smem_u32(tb0) & 15u)) & 15u)) + (warp - 2) * (32 * TS);   // (PM == 0 only)
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const int cfirst = ((warp - 2) >> 2) * CPP;
+    // The C input (the decode step's static gate terms: 34 MB per step, evicted from L2 by the 411 MB of V in between) is pulled into
+    // L2 two tiles ahead, one row of the tile per thread.
+    auto prefetch_cin = [&](int tile) {
+      if (tile >= num_tiles || !e.Cin || threadIdx.x >= 64 + BH) return;
+      const int pr = (tile % tiles_m) * 256 + (int)rank * BH + (int)threadIdx.x - 64, pn = (tile / tiles_m) * BN2;
+      if (pr >= e.M || pn >= e.N) return;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(e.Cin + (long long)pr * e.ldcin + pn), "r"(min(BN2, e.N - pn) * 4) : "memory");
+    };
+    if constexpr (PM == 0) {
+      prefetch_cin(pair);
+      prefetch_cin(pair + npairs);
+    }
+    uint32_t rr[2][32];
+    float4 gg[2][8];            // PM == 2: the chunk's 32 bias values;  PM == 0: this lane's 8 float4 of the C input
+    int lt = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++lt) {
+      const int m0 = (tile % tiles_m) * 256 + (int)rank * BH, n0 = (tile / tiles_m) * BN2;
+      const int acc = lt & 1;
+      const int row0 = m0 + q * 32;
+      if constexpr (PM == 0) prefetch_cin(tile + 2 * npairs);
+      auto issue = [&](uint32_t (&r)[32], float4 (&g)[8], int c) {
+        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2 + c * 32), r);
+        const int nb = n0 + c * 32;
+        if constexpr (PM == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)      // (N % 16 == 0: a chunk that starts inside N holds 16 or 32 columns)
+            g[j] = (nb + 4 * j < e.N) ? __ldg(reinterpret_cast<const float4*>(e.bias1 + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          const int n = nb + c4;
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const long long row = row0 + i8 * 4 + rsub;
+            g[i8] = (e.Cin && row < e.M && n < e.N) ? __ldcg(reinterpret_cast<const float4*>(e.Cin + row * e.ldcin + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      auto stage = [&](uint32_t (&r)[32], float4 (&g)[8], uint32_t (&rn)[32], float4 (&gn)[8], int i) {
+        tmem_wait_ld(r);
+        if (i + 1 < CPP) {
+          issue(rn, gn, cfirst + i + 1);
+        } else {      // this warp's share of the accumulator is read: hand it back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        }
+        const int nb = n0 + (cfirst + i) * 32;
+        if (row0 >= e.M || nb >= e.N) return;      // warp-uniform
+        if constexpr (PM == 2) {
+          float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = g[j >> 2];
+            mx[j >> 4] = fmaxf(fmaxf(mx[j >> 4], __uint_as_float(r[j]) + b4.x), __uint_as_float(r[j + 1]) + b4.y);
+            mx[j >> 4] = fmaxf(fmaxf(mx[j >> 4], __uint_as_float(r[j + 2]) + b4.z), __uint_as_float(r[j + 3]) + b4.w);
+          }
+          if (row0 + lane < e.M) {
+            float* po = e.pmax + (long long)(row0 + lane) * e.tiles_n + (nb >> 4);
+            po[0] = mx[0];
+            if (nb + 16 < e.N) po[1] = mx[1];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(&tbuf[lane * TS + j]) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          __syncwarp();
+          const int n = nb + c4;
+          float4 badd = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < e.N) {
+            if (e.bias1) badd = __ldg(reinterpret_cast<const float4*>(e.bias1 + n));
+            if (e.bias2) { const float4 b2 = __ldg(reinterpret_cast<const float4*>(e.bias2 + n)); badd.x += b2.x; badd.y += b2.y; badd.z += b2.z; badd.w += b2.w; }
+          }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const long long row = row0 + i8 * 4 + rsub;
+            float4 v = *reinterpret_cast<const float4*>(&tbuf[(i8 * 4 + rsub) * TS + c4]);
+            v.x += badd.x + e.beta * g[i8].x; v.y += badd.y + e.beta * g[i8].y; v.z += badd.z + e.beta * g[i8].z; v.w += badd.w + e.beta * g[i8].w;
+            if (row < e.M && n < e.N) *reinterpret_cast<float4*>(e.D32 + row * e.ldd32 + n) = v;
+          }
+          __syncwarp();
+        }
+      };
+      static_assert(CPP % 2 == 0, "pair epilogue: an even number of chunks per warp");
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      issue(rr[0], gg[0], cfirst);
+#pragma unroll 1
+      for (int i = 0; i < CPP; i += 2) {
+        stage(rr[0], gg[0], rr[1], gg[1], i);
+        stage(rr[1], gg[1], rr[0], gg[0], i + 1);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // neither CTA frees tensor memory (or exits: its barriers are the peer's targets) before both are done
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
+  }
+}
+
+// AA_GEMM_PAIR=0 keeps every contraction on the single-CTA kernel.
+bool pair_enabled() {
+  static const bool on = [] { const char* e = getenv("AA_GEMM_PAIR"); return !e || e[0] != '0'; }();
+  return on;
+}
+
+// The choice must not depend on M: a row's result may not change with the number of batch mates (decode sharding).
+bool pair_applies(const TcGemmArgs& g) {
+  if (!pair_enabled() || g.a_mn || g.b_mn || g.a_raw || g.ashift_cols > 0 || g.kcut_cols > 0 || g.ce_e16 || g.pidx) return false;
+  if (g.N < 1024 || g.N % 16 != 0) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(g.bias1) || !al16(g.bias2)) return false;
+  if (g.split3)        // plain fp32-accurate contraction with an fp32 output (the decode step's gates)
+    return g.elem_size == 4 && !g.pmax && g.D32 && !g.D16 && al16(g.D32) && g.ldd32 % 4 == 0 && (!g.Cin || (al16(g.Cin) && g.ldcin % 4 == 0));
+  return g.elem_size == 2 && g.pmax && g.bias1 && !g.D32 && !g.D16 && !g.Cin && !g.bias2;      // the bf16 maxima pass of the vocabulary arg-max
+}
+
+template <int ES, int STAGES, bool SPLIT, int PM>
+int launch_pair(const TcGemmArgs& g, cudaStream_t st) {
+  constexpr int BK = 128 / ES;
+  CUtensorMap tmA, tmB;
+  const int lo_a = g.lo_a ? g.lo_a : g.K, lo_b = g.lo_b ? g.lo_b : g.K;
+  const long long acols = SPLIT ? (g.a_cols ? g.a_cols : (long long)lo_a + g.K) : g.K;
+  const long long bcols = SPLIT ? (g.b_cols ? g.b_cols : (long long)lo_b + g.K) : g.K;
+  AA_TRY(make_map(&tmA, g.A, ES, g.M, acols, g.lda, 128));
+  AA_TRY(make_map(&tmB, g.B, ES, g.N, bcols, g.ldb, 128));
+  const int tiles_m = ceil_div(g.M, 256), tiles_n = ceil_div(g.N, 256);
+  TcEpilogue e{};
+  e.M = g.M; e.N = g.N; e.K = g.K;
+  e.D32 = g.D32; e.ldd32 = g.ldd32; e.D16 = g.D16; e.ldd16 = g.ldd16;
+  e.Cin = g.Cin; e.ldcin = g.ldcin; e.beta = g.beta; e.bias1 = g.bias1; e.bias2 = g.bias2;
+  e.pmax = g.pmax; e.pidx = nullptr; e.tiles_n = ceil_div(g.N, 16); e.lo_a = lo_a; e.lo_b = lo_b;
+  e.ksplit = 1; e.kb_per = ceil_div(g.K, BK);
+  constexpr int EW = epi_warps(SPLIT);
+  constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (128 * 128 + 128 * 128) + (2 * STAGES + 4) * 8 + 16 + 32 +
+                          (PM == 2 ? 0 : EW * 32 * 36 * 4) + 1024;      // (the maxima-only instantiation has no transpose tiles)
+  static_assert(smem <= 227 * 1024, "pair tile configuration exceeds shared memory");
+  auto kern = gemm_pair_kernel<ES, STAGES, SPLIT, PM>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(tc_threads(SPLIT));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  static int max_pairs = 0;
+  if (!max_pairs) {
+    AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.gridDim = dim3(2 * (num_sms() / 2));
+    int n = 0;
+    AA_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    AA_REQUIRE(n > 0, "tcgen05 pair GEMM: no CTA pair fits this device");
+    max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+  }
+  const int num_tiles = tiles_m * tiles_n;
+  cfg.gridDim = dim3(2 * (num_tiles < max_pairs ? num_tiles : max_pairs));
+  AA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, e, tiles_m, num_tiles));
+  return AA_OK;
+}
+
 template <int BN, int ES, int STAGES>
 int launch_major(const TcGemmArgs& g, cudaStream_t st) {
   if (!g.a_mn && !g.b_mn) return launch_cfg<BN, ES, STAGES, false, false>(g, st);
@@ -642,6 +993,7 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   if (g.split3) {
     AA_REQUIRE(g.elem_size == 4 && !g.a_mn && !g.b_mn, "tcgen05 GEMM: split (3xTF32) mode needs K-major fp32 operands");
     AA_REQUIRE(g.K % 32 == 0, "tcgen05 GEMM: split mode needs K (per half) padded to a multiple of 32 (got %d)", g.K);
+    if (pair_applies(g)) return launch_pair<4, 3, true, 0>(g, st);
     // the arg-max partial layout [M, ceil(N / tile_n)] is part of the contract: tile_n = gemm_tc_argmax_tile_n(N)
     // (256-column tiles -- 128 cycles per MMA for twice the columns -- were measured SLOWER here: only two 96 KB stages fit
     //  and the TMA feed, ~50 B/clk per SM, becomes the bound: vocabulary GEMM 224 us against 205 us, r01_v33)
@@ -659,6 +1011,7 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
     set_error("tcgen05 GEMM: tf32 operands must be K-major");
     return AA_ERR_UNSUPPORTED;
   }
+  if (pair_applies(g)) return launch_pair<2, 7, false, 2>(g, st);
   return g.elem_size == 2 ? launch_es<2>(g, st) : launch_es<4>(g, st);
 }
 

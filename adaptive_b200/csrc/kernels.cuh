@@ -129,6 +129,7 @@ int set_gemm_splitk(int on);   // diagnostics: 0 = never split K (deterministic 
 
 // ---- vocab_refine.cu (filter-and-refine arg-max of the vocabulary projection, greedy decoding) ----
 bool argmax_refine_supported(int Vc, int H);
+int refine_units(long long* out4, int reset);   // diagnostics: CTA units, warp units, tiles refined by CTAs, tiles refined by warps (accumulated)
 long long refine_pairs(int reset);   // diagnostics: (row, tile) pairs refined so far on the current device (synchronises)
 // wnorm[t] = max_j ||W[j,:]||_2 over the 16-column tile t of W [Vc,H] (tile width = gemm_tc_argmax_tile_n_plain)
 int launch_tile_wnorm(const float* W, int Vc, int H, float* wnorm, cudaStream_t s, float* dwnorm = nullptr);   // dwnorm: norms of W - bf16(W) per tile

@@ -30,6 +30,7 @@ constexpr int RF_ROWS = 4;       // rows a warp carries through one pass over th
 constexpr int RF_TN = 16;        // columns per tile = granularity of the first pass's maxima (gemm_tc_argmax_tile_n_plain)
 
 __device__ unsigned long long d_refine_pairs = 0;    // diagnostics: (row, tile) pairs handed to the refinement so far
+__device__ unsigned long long d_refine_units[4] = {0, 0, 0, 0};   // diagnostics: CTA units, warp units, tiles refined by CTAs, by warps
 
 // wnorm[t] = max_{j in tile t} ||W[j, :]||_2 and (optional) dwnorm[t] = max_j ||W[j, :] - bf16(W[j, :])||_2, both rounded up
 // (once per decode call).  bf16() is the round-to-nearest-even conversion the bf16 mirror of W is made with (launch_cast2d).
@@ -385,6 +386,7 @@ __global__ void __launch_bounds__(RF_THREADS, 2) argmax_refine_kernel(const floa
       if (t < tiles) { preH[t] = cH; preC[t] = cC; }
       locH += cH;
       locC += cC;
+      if (blockIdx.x == 0 && n > 0) atomicAdd(&d_refine_units[n > RF_COLD_MAX ? 2 : 3], 1ull);
     }
     int incH = locH, incC = locC;
 #pragma unroll
@@ -405,7 +407,13 @@ __global__ void __launch_bounds__(RF_THREADS, 2) argmax_refine_kernel(const floa
         accH += cH; accC += cC;
       }
     }
-    if (tid == RF_THREADS - 1) { preH[tiles] = baseH + incH; preC[tiles] = baseC + incC; }
+    if (tid == RF_THREADS - 1) {
+      preH[tiles] = baseH + incH; preC[tiles] = baseC + incC;
+      if (blockIdx.x == 0) {
+        atomicAdd(&d_refine_units[0], (unsigned long long)(baseH + incH));
+        atomicAdd(&d_refine_units[1], (unsigned long long)(baseC + incC));
+      }
+    }
   }
   __syncthreads();
   auto find = [&](const int* pre, int unit) {          // largest t with pre[t] <= unit (tiles without units share the next one's prefix)
@@ -472,6 +480,17 @@ long long refine_pairs(int reset) {
     cudaMemcpyToSymbol(d_refine_pairs, &z, sizeof(z));
   }
   return (long long)v;
+}
+
+int refine_units(long long* out4, int reset) {
+  unsigned long long v[4] = {0, 0, 0, 0};
+  AA_CHECK_CUDA(cudaMemcpyFromSymbol(v, d_refine_units, sizeof(v)));
+  for (int i = 0; i < 4; ++i) out4[i] = (long long)v[i];
+  if (reset) {
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    AA_CHECK_CUDA(cudaMemcpyToSymbol(d_refine_units, z, sizeof(z)));
+  }
+  return AA_OK;
 }
 
 bool argmax_refine_supported(int Vc, int H) {

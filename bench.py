@@ -18,6 +18,7 @@ threads) on the same workload, on rank 0 only.
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -981,8 +982,13 @@ def run_ours(args):
     # filter-and-refine arg-max: (row, 16-column tile) pairs recomputed exactly, per row and step
     lib = _lib.load()
     lib.aa_debug_refine_pairs(1)
+    ru = (ctypes.c_longlong * 4)()
+    lib.aa_debug_refine_units(ctypes.cast(ru, ctypes.c_void_p), 1)
     ids_refine = decode_step(ddev)[0]
     refine_pairs = lib.aa_debug_refine_pairs(1) / float(DECODE_B * DECODE_L)
+    lib.aa_debug_refine_units(ctypes.cast(ru, ctypes.c_void_p), 1)
+    refine_units = {"cta_units_per_step": ru[0] / float(DECODE_L), "warp_units_per_step": ru[1] / float(DECODE_L),
+                    "tiles_by_cta_units_per_step": ru[2] / float(DECODE_L), "tiles_by_warp_units_per_step": ru[3] / float(DECODE_L)}
     # near-ties of config 3, counted on the device: the 3xTF32 projection of EVERY logit (refinement off, logits returned) gives
     # the top-1 / top-2 gap of each (image, step); ids of the default path must equal its arg-max wherever the gap is not tiny
     near = None
@@ -1098,7 +1104,8 @@ def run_ours(args):
                    "precision": model.decoder.decode_precision,
                    "vocab_argmax": {"method": "one bf16 tensor-core pass (maxima per 16 columns) + exact fp32 recompute of the tiles that can "
                                               "hold the row maximum under a rigorous error bound (vocab_refine.cu); ids equal an exact fp32 projection's",
-                                    "tiles_refined_per_row_and_step": refine_pairs, "tiles_per_row": (dims.Vc + 15) // 16},
+                                    "tiles_refined_per_row_and_step": refine_pairs, "tiles_per_row": (dims.Vc + 15) // 16,
+                                    "refine_units": refine_units},
                    "near_ties": near,
                    "roofline_fused_step": k_dec.get("dec_step_fused"),
                    "roofline_whole_step": dec_whole},

@@ -115,9 +115,12 @@ int aa_debug_set_decode_atten_simple(int on);
  * filter-and-refine arg-max (one low-precision tensor-core pass + exact fp32 logits of the columns that can hold the maximum);
  * 1 = tf32 first pass, 2 = bf16 first pass (default). */
 int aa_debug_set_decode_argmax_refine(int on);
-/* Diagnostics: number of (row, 64-column tile) pairs the filter has handed to the exact refinement on the current device since
+/* Diagnostics: number of (row, 16-column tile) pairs the filter has handed to the exact refinement on the current device since
  * the last reset (synchronises the device); -1 on error. */
 long long aa_debug_refine_pairs(int reset);
+/* Diagnostics: how the refinement dealt its work since the last reset -- out4 = {CTA units (tile, <= 32 rows), warp units
+ * (tile, <= 2 rows), tiles refined by CTA units, tiles refined by warp units}, summed over its launches (synchronises). */
+int aa_debug_refine_units(long long* out4, int reset);
 /* Diagnostics: on != 0 makes the training attention use the step-by-step kernels instead of the step-parallel ones. */
 int aa_debug_set_atten_sequential(int on);
 /* Diagnostics: on == 0 stops the tcgen05 GEMM from splitting K (partial tiles summed with red.global.add, i.e. a

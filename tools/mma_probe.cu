@@ -27,8 +27,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // SW128, K-ma
   d |= (uint64_t)2 << 61;
   return d;
 }
+// TF32: kind::tf32 (K = 8 per instruction, same 32-byte k-step in shared memory)
+template <bool TF32>
 __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  if constexpr (TF32)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
 __device__ __forceinline__ uint32_t elect_one() {
@@ -39,6 +44,7 @@ __device__ __forceinline__ uint32_t elect_one() {
 
 // warp_wide = 0: `if (threadIdx.x == 0)` issues (what lstm_seq.cu / gemm_tc.cu do); 1: the whole warp runs the loop
 // converged and the MMA is issued under elect.sync (operands are warp-uniform)
+template <bool TF32>
 __global__ void __launch_bounds__(128) probe(int N, int M, int nacc, int iters, int commit_every, int warp_wide, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = raw + ((1024u - (s32(raw) & 1023u)) & 1023u);
@@ -58,7 +64,8 @@ __global__ void __launch_bounds__(128) probe(int N, int M, int nacc, int iters, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = slot;
   if (warp_wide ? threadIdx.x < 32 : threadIdx.x == 0) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint32_t fmt = TF32 ? 2u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     const uint64_t db0 = make_desc(s32(sB));
     long long t0 = clock64();
     int j = 0;
@@ -67,14 +74,14 @@ __global__ void __launch_bounds__(128) probe(int N, int M, int nacc, int iters, 
       if (warp_wide) {
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma(tmem + (uint32_t)(((j + k) % nacc) * N), da0 + 2 * k, db0 + 2 * k, idesc, (j + k) >= nacc ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) mma<TF32>(tmem + (uint32_t)(((j + k) % nacc) * N), da0 + 2 * k, db0 + 2 * k, idesc, (j + k) >= nacc ? 1u : 0u);
           if (commit_every) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar2)) : "memory");
         }
         j += 4;
         __syncwarp();
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k, ++j) mma(tmem + (uint32_t)((j % nacc) * N), da0 + 2 * k, db0 + 2 * k, idesc, j >= nacc ? 1u : 0u);
+        for (int k = 0; k < 4; ++k, ++j) mma<TF32>(tmem + (uint32_t)((j % nacc) * N), da0 + 2 * k, db0 + 2 * k, idesc, j >= nacc ? 1u : 0u);
         if (commit_every) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar2)) : "memory");
       }
     }
@@ -93,7 +100,8 @@ int main() {
   long long* d;
   CK(cudaMalloc(&d, 16));
   const size_t smem = 65536 + 32768 + 1024;
-  CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int iters = 256;   // x4 MMAs
   for (int M : {128})
     for (int N : {16, 32, 64, 128, 256})
@@ -103,7 +111,7 @@ int main() {
           if (N * nacc > 512) continue;
           long long best[2] = {1LL << 60, 1LL << 60};
           for (int rep = 0; rep < 3; ++rep) {
-            probe<<<1, 128, smem>>>(N, M, nacc, iters, ce, ww, d);
+            probe<false><<<1, 128, smem>>>(N, M, nacc, iters, ce, ww, d);
             CK(cudaDeviceSynchronize());
             long long h[2];
             CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
@@ -112,5 +120,21 @@ int main() {
           printf("{\"M\": %d, \"N\": %d, \"accumulators\": %d, \"commit_per_kblock\": %d, \"warp_wide_elect\": %d, \"issue_cycles_per_mma\": %.1f, \"total_cycles_per_mma\": %.1f}\n", M, N, nacc, ce, ww,
                  (double)best[0] / (iters * 4), (double)best[1] / (iters * 4));
         }
+  // kind::tf32 against kind::f16 at the tile widths the contractions use (converged warp, one accumulator)
+  for (int tf : {0, 1})
+    for (int N : {64, 128, 256}) {
+      long long best[2] = {1LL << 60, 1LL << 60};
+      for (int rep = 0; rep < 3; ++rep) {
+        if (tf) probe<true><<<1, 128, smem>>>(N, 128, 1, iters, 1, 1, d);
+        else probe<false><<<1, 128, smem>>>(N, 128, 1, iters, 1, 1, d);
+        CK(cudaDeviceSynchronize());
+        long long h[2];
+        CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+        if (h[1] < best[1]) { best[0] = h[0]; best[1] = h[1]; }
+      }
+      const double cyc = (double)best[1] / (iters * 4);
+      printf("{\"kind\": \"%s\", \"M\": 128, \"N\": %d, \"K_per_mma\": %d, \"total_cycles_per_mma\": %.1f, \"flop_per_clk\": %.0f}\n", tf ? "tf32" : "f16(bf16)", N,
+             tf ? 8 : 16, cyc, 2.0 * 128 * N * (tf ? 8 : 16) / cyc);
+    }
   return 0;
 }
