@@ -626,10 +626,21 @@ __device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t desc_a, uint64
   }
 }
 
-template <int ES, int STAGES, bool SPLIT, int PM>
+// ARES (A resident; plain operands, K <= ARES_KB k-blocks): the pair walks a CONTIGUOUS range of tiles in n-fastest order, so that its
+// 256 rows of A change at most once or twice per launch; they stay in shared memory (one 16 KB box per k-block and CTA) and only B is
+// streamed through the stage ring -- half the operand bytes per tile again.  The vocabulary maxima pass (K = 512: 128 KB of A per
+// CTA) moved 336 MB from L2 at 8.6 TB/s, its bound (profiles/r02_pair_ncu_details.txt); the MMAs need 19 us of its 39.
+constexpr int ARES_KB = 8;
+
+#ifdef AA_PAIR_TRACE      // development build only (tools/trace_pair.py): per-tile wait / work cycles of the MMA warp and of one epilogue warp
+__device__ long long g_pair_trace[148 * 16 * 8];
+#endif
+
+template <int ES, int STAGES, bool SPLIT, int PM, bool ARES = false>
 __global__ void __launch_bounds__(tc_threads(SPLIT), 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpilogue e, int tiles_m, int num_tiles) {
   static_assert(PM == 0 || PM == 2, "pair kernel: no epilogue partials other than the maxima");
+  static_assert(!ARES || !SPLIT, "the resident-A form takes plain operands");
   constexpr bool TF32 = (ES == 4);
   constexpr int BH = 128;                  // rows of A and of B this CTA stages
   constexpr int BN2 = 256;                 // columns of the pair's tile (= accumulator columns per CTA)
@@ -645,18 +656,34 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint8_t* sA = smem;                                                     // ARES: [ARES_KB] boxes of this CTA's 128 rows, one per k-block
+  uint8_t* sB = smem + (ARES ? ARES_KB * A_BYTES : STAGES * A_STAGE);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2] (the leader's are used)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;             // ARES: the resident A tile has landed (leader's) / may be overwritten (both CTAs)
+  uint64_t* a_empty = a_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef AA_PAIR_TRACE
+  if (threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_pair_trace[((long long)blockIdx.x * 16 + 0) * 8 + 7] = (long long)gt;
+  }
+#endif
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nkb = (e.K + BK - 1) / BK;
+  // tiles of this pair: round robin in m-fastest order, or (ARES) a contiguous range in n-fastest order
+  const int tiles_n = num_tiles / tiles_m;
+  const int u_begin = ARES ? (int)((long long)pair * num_tiles / npairs) : pair;
+  const int u_end = ARES ? (int)((long long)(pair + 1) * num_tiles / npairs) : num_tiles;
+  const int u_step = ARES ? 1 : npairs;
+  auto tile_m = [&](int u) { return ARES ? u / tiles_n : u % tiles_m; };
+  auto tile_n = [&](int u) { return ARES ? u % tiles_n : u / tiles_m; };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -671,6 +698,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * EW); // the epilogue warps of both CTAs
     }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {      // the same warp of both CTAs, the same shared-memory offset
@@ -682,21 +711,37 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef AA_PAIR_TRACE
+  if (threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_pair_trace[((long long)blockIdx.x * 16 + 1) * 8 + 7] = (long long)gt;
+  }
+#endif
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs: this CTA's halves) =====
     if (lane == 0) {
-      int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += npairs) {
-        const int ma = (tile % tiles_m) * 256 + (int)rank * BH, nb = (tile / tiles_m) * BN2 + (int)rank * BH;
+      int it = 0, cur_m = -1, a_loads = 0;
+      for (int tile = u_begin; tile < u_end; tile += u_step) {
+        const int ma = tile_m(tile) * 256 + (int)rank * BH, nb = tile_n(tile) * BN2 + (int)rank * BH;
+        if constexpr (ARES) {
+          if (tile_m(tile) != cur_m) {      // (re)load the resident rows of A -- once every MMA that reads the old ones is done
+            if (a_loads > 0) mbar_wait(a_empty, (a_loads - 1) & 1);
+            if (rank == 0) mbar_expect_tx(a_full, 2 * nkb * A_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma2_load_2d(sA + kb * A_BYTES, &tmA, kb * BK, ma, a_full);
+            cur_m = tile_m(tile);
+            ++a_loads;
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * (A_STAGE + B_STAGE));
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * ((ARES ? 0 : A_STAGE) + B_STAGE));
           uint8_t* a_dst = sA + s * A_STAGE;
           uint8_t* b_dst = sB + s * B_STAGE;
-          tma2_load_2d(a_dst, &tmA, kb * BK, ma, &full_bar[s]);
+          if constexpr (!ARES) tma2_load_2d(a_dst, &tmA, kb * BK, ma, &full_bar[s]);
           tma2_load_2d(b_dst, &tmB, kb * BK, nb, &full_bar[s]);
           if constexpr (SPLIT) {
             tma2_load_2d(a_dst + A_BYTES, &tmA, e.lo_a + kb * BK, ma, &full_bar[s]);
@@ -710,18 +755,38 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (rank == 0) {
       constexpr uint32_t fmt = TF32 ? 2u : 1u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      int it = 0, lt = 0;
-      for (int tile = pair; tile < num_tiles; tile += npairs, ++lt) {
+      int it = 0, lt = 0, cur_m = -1, a_loads = 0;
+      for (int tile = u_begin; tile < u_end; tile += u_step, ++lt) {
         const int acc = lt & 1;
+        if constexpr (ARES) {
+          if (tile_m(tile) != cur_m) {
+            mbar_wait(a_full, a_loads & 1);
+            ++a_loads;
+            cur_m = tile_m(tile);
+          }
+        }
+#ifdef AA_PAIR_TRACE
+        const long long tr0 = clock64();
+        long long trf = 0;
+#endif
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);     // both epilogues have drained this accumulator
         tc_fence_after();
+#ifdef AA_PAIR_TRACE
+        const long long tr1 = clock64();
+#endif
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN2);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
+#ifdef AA_PAIR_TRACE
+          const long long tra = clock64();
+#endif
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
+#ifdef AA_PAIR_TRACE
+          trf += clock64() - tra;
+#endif
+          const uint32_t a_addr = smem_u32(ARES ? sA + kb * A_BYTES : sA + s * A_STAGE);
           const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
           if (elect_one()) {
 #pragma unroll
@@ -741,7 +806,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         }
-        if (elect_one()) tc2_commit(&tmem_full[acc]);
+#ifdef AA_PAIR_TRACE
+        if (lane == 0 && lt < 16) {
+          long long* o = g_pair_trace + ((long long)blockIdx.x * 16 + lt) * 8;
+          o[0] = tr1 - tr0; o[1] = trf; o[2] = clock64() - tr1; o[3] = tile;
+        }
+#endif
+        if (elect_one()) {
+          tc2_commit(&tmem_full[acc]);
+          if constexpr (ARES) {      // last tile on these rows of A: the producers of both CTAs may overwrite them once the MMAs so far are done
+            if (tile + 1 < u_end && tile_m(tile + 1) != cur_m) tc2_commit(a_empty);
+          }
+        }
         __syncwarp();
       }
     }
@@ -765,7 +841,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // L2 two tiles ahead, one row of the tile per thread.
     auto prefetch_cin = [&](int tile) {
       if (tile >= num_tiles || !e.Cin || threadIdx.x >= 64 + BH) return;
-      const int pr = (tile % tiles_m) * 256 + (int)rank * BH + (int)threadIdx.x - 64, pn = (tile / tiles_m) * BN2;
+      const int pr = tile_m(tile) * 256 + (int)rank * BH + (int)threadIdx.x - 64, pn = tile_n(tile) * BN2;
       if (pr >= e.M || pn >= e.N) return;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(e.Cin + (long long)pr * e.ldcin + pn), "r"(min(BN2, e.N - pn) * 4) : "memory");
     };
@@ -776,8 +852,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t rr[2][32];
     float4 gg[2][8];            // PM == 2: the chunk's 32 bias values;  PM == 0: this lane's 8 float4 of the C input
     int lt = 0;
-    for (int tile = pair; tile < num_tiles; tile += npairs, ++lt) {
-      const int m0 = (tile % tiles_m) * 256 + (int)rank * BH, n0 = (tile / tiles_m) * BN2;
+    for (int tile = u_begin; tile < u_end; tile += u_step, ++lt) {
+      const int m0 = tile_m(tile) * 256 + (int)rank * BH, n0 = tile_n(tile) * BN2;
       const int acc = lt & 1;
       const int row0 = m0 + q * 32;
       if constexpr (PM == 0) prefetch_cin(tile + 2 * npairs);
@@ -844,23 +920,49 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
       static_assert(CPP % 2 == 0, "pair epilogue: an even number of chunks per warp");
+#ifdef AA_PAIR_TRACE
+      const long long te0 = clock64();
+#endif
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
+#ifdef AA_PAIR_TRACE
+      const long long te1 = clock64();
+#endif
       issue(rr[0], gg[0], cfirst);
 #pragma unroll 1
       for (int i = 0; i < CPP; i += 2) {
         stage(rr[0], gg[0], rr[1], gg[1], i);
         stage(rr[1], gg[1], rr[0], gg[0], i + 1);
       }
+#ifdef AA_PAIR_TRACE
+      if (warp == 2 && lane == 0 && lt < 16) {
+        long long* o = g_pair_trace + ((long long)blockIdx.x * 16 + lt) * 8;
+        o[4] = te1 - te0; o[5] = clock64() - te1; o[6] = tile;
+      }
+#endif
     }
   }
   tc_fence_before();
   __syncthreads();
+#ifdef AA_PAIR_TRACE
+  if (threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_pair_trace[((long long)blockIdx.x * 16 + 2) * 8 + 7] = (long long)gt;
+  }
+#endif
   cluster_sync_all();      // neither CTA frees tensor memory (or exits: its barriers are the peer's targets) before both are done
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
   }
+#ifdef AA_PAIR_TRACE
+  if (threadIdx.x == 64) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_pair_trace[((long long)blockIdx.x * 16 + 3) * 8 + 7] = (long long)gt;
+  }
+#endif
 }
 
 // AA_GEMM_PAIR=0 keeps every contraction on the single-CTA kernel.
@@ -880,7 +982,7 @@ bool pair_applies(const TcGemmArgs& g) {
   return g.elem_size == 2 && g.pmax && g.bias1 && !g.D32 && !g.D16 && !g.Cin && !g.bias2;      // the bf16 maxima pass of the vocabulary arg-max
 }
 
-template <int ES, int STAGES, bool SPLIT, int PM>
+template <int ES, int STAGES, bool SPLIT, int PM, bool ARES = false>
 int launch_pair(const TcGemmArgs& g, cudaStream_t st) {
   constexpr int BK = 128 / ES;
   CUtensorMap tmA, tmB;
@@ -897,10 +999,11 @@ int launch_pair(const TcGemmArgs& g, cudaStream_t st) {
   e.pmax = g.pmax; e.pidx = nullptr; e.tiles_n = ceil_div(g.N, 16); e.lo_a = lo_a; e.lo_b = lo_b;
   e.ksplit = 1; e.kb_per = ceil_div(g.K, BK);
   constexpr int EW = epi_warps(SPLIT);
-  constexpr size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * (128 * 128 + 128 * 128) + (2 * STAGES + 4) * 8 + 16 + 32 +
-                          (PM == 2 ? 0 : EW * 32 * 36 * 4) + 1024;      // (the maxima-only instantiation has no transpose tiles)
+  constexpr size_t smem = (ARES ? (size_t)ARES_KB * 128 * 128 + (size_t)STAGES * 128 * 128 : (size_t)STAGES * (SPLIT ? 2 : 1) * (128 * 128 + 128 * 128)) +
+                          (2 * STAGES + 6) * 8 + 16 + 32 + (PM == 2 ? 0 : EW * 32 * 36 * 4) + 1024;      // (the maxima-only instantiation has no transpose tiles)
+  if (ARES) AA_REQUIRE(ceil_div(g.K, BK) <= ARES_KB, "tcgen05 pair GEMM: the resident-A form holds at most %d k-blocks", ARES_KB);
   static_assert(smem <= 227 * 1024, "pair tile configuration exceeds shared memory");
-  auto kern = gemm_pair_kernel<ES, STAGES, SPLIT, PM>;
+  auto kern = gemm_pair_kernel<ES, STAGES, SPLIT, PM, ARES>;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1011,8 +1114,23 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
     set_error("tcgen05 GEMM: tf32 operands must be K-major");
     return AA_ERR_UNSUPPORTED;
   }
-  if (pair_applies(g)) return launch_pair<2, 7, false, 2>(g, st);
+  if (pair_applies(g)) {
+    static const bool ares = [] { const char* e = getenv("AA_GEMM_PAIR_ARES"); return !e || e[0] != '0'; }();
+    if (ares && g.K <= ARES_KB * 64) return launch_pair<2, 6, false, 2, true>(g, st);
+    return launch_pair<2, 7, false, 2>(g, st);
+  }
   return g.elem_size == 2 ? launch_es<2>(g, st) : launch_es<4>(g, st);
 }
 
 }  // namespace aa
+
+#ifdef AA_PAIR_TRACE
+extern "C" int aa_debug_pair_trace(long long* out, int n, int reset) {
+  if (cudaMemcpyFromSymbol(out, aa::g_pair_trace, sizeof(long long) * (size_t)n) != cudaSuccess) return 2;
+  if (reset) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, aa::g_pair_trace) != cudaSuccess || cudaMemset(p, 0, sizeof(aa::g_pair_trace)) != cudaSuccess) return 2;
+  }
+  return 0;
+}
+#endif
