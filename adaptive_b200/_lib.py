@@ -89,6 +89,7 @@ SIGNATURES = {
     "aa_debug_refine_pairs": (ctypes.c_longlong, [c_int]),
     "aa_debug_refine_units": (c_int, [ctypes.c_void_p, c_int]),
     "aa_debug_set_gemm_splitk": (c_int, [c_int]),
+    "aa_debug_set_gemm_pair": (c_int, [c_int]),
     "aa_debug_set_bptt_ksplit": (c_int, [c_int]),
     "aa_debug_set_lstm_cluster": (c_int, [c_int, c_int]),
     "aa_linear_forward": (c_int, [c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),

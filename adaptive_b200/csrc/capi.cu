@@ -331,6 +331,7 @@ using namespace aa;
 extern "C" {
 
 int aa_debug_set_gemm_splitk(int on) { return aa::set_gemm_splitk(on); }
+int aa_debug_set_gemm_pair(int on) { return aa::set_gemm_pair(on); }
 
 int aa_debug_set_bptt_ksplit(int ks) { return aa::set_bptt_ksplit_max(ks); }
 

@@ -965,10 +965,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #endif
 }
 
-// AA_GEMM_PAIR=0 keeps every contraction on the single-CTA kernel.
+// AA_GEMM_PAIR=0 keeps every contraction on the single-CTA kernel; so does a device on which no CTA pair can be made resident
+// (found out at the first launch: g_pair_unavailable).
+bool g_pair_unavailable = false;
+int g_pair_override = -1;      // diagnostics (aa_debug_set_gemm_pair): 0 / 1 overrides the environment
 bool pair_enabled() {
   static const bool on = [] { const char* e = getenv("AA_GEMM_PAIR"); return !e || e[0] != '0'; }();
-  return on;
+  return (g_pair_override >= 0 ? g_pair_override != 0 : on) && !g_pair_unavailable;
 }
 
 // The choice must not depend on M: a row's result may not change with the number of batch mates (decode sharding).
@@ -1018,8 +1021,11 @@ int launch_pair(const TcGemmArgs& g, cudaStream_t st) {
     AA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cfg.gridDim = dim3(2 * (num_sms() / 2));
     int n = 0;
-    AA_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-    AA_REQUIRE(n > 0, "tcgen05 pair GEMM: no CTA pair fits this device");
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {      // the caller takes the single-CTA kernel, from now on
+      cudaGetLastError();
+      g_pair_unavailable = true;
+      return AA_ERR_UNSUPPORTED;
+    }
     max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
   }
   const int num_tiles = tiles_m * tiles_n;
@@ -1074,6 +1080,11 @@ int launch_es(const TcGemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
+int set_gemm_pair(int on) {
+  g_pair_override = on < 0 ? -1 : (on ? 1 : 0);
+  return AA_OK;
+}
+
 int set_gemm_splitk(int on) {
   g_tc_splitk = on ? 1 : 0;
   return AA_OK;
@@ -1096,7 +1107,10 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   if (g.split3) {
     AA_REQUIRE(g.elem_size == 4 && !g.a_mn && !g.b_mn, "tcgen05 GEMM: split (3xTF32) mode needs K-major fp32 operands");
     AA_REQUIRE(g.K % 32 == 0, "tcgen05 GEMM: split mode needs K (per half) padded to a multiple of 32 (got %d)", g.K);
-    if (pair_applies(g)) return launch_pair<4, 3, true, 0>(g, st);
+    if (pair_applies(g)) {
+      const int rc = launch_pair<4, 3, true, 0>(g, st);
+      if (rc != AA_ERR_UNSUPPORTED) return rc;
+    }
     // the arg-max partial layout [M, ceil(N / tile_n)] is part of the contract: tile_n = gemm_tc_argmax_tile_n(N)
     // (256-column tiles -- 128 cycles per MMA for twice the columns -- were measured SLOWER here: only two 96 KB stages fit
     //  and the TMA feed, ~50 B/clk per SM, becomes the bound: vocabulary GEMM 224 us against 205 us, r01_v33)
@@ -1116,8 +1130,8 @@ int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t st) {
   }
   if (pair_applies(g)) {
     static const bool ares = [] { const char* e = getenv("AA_GEMM_PAIR_ARES"); return !e || e[0] != '0'; }();
-    if (ares && g.K <= ARES_KB * 64) return launch_pair<2, 6, false, 2, true>(g, st);
-    return launch_pair<2, 7, false, 2>(g, st);
+    const int rc = (ares && g.K <= ARES_KB * 64) ? launch_pair<2, 6, false, 2, true>(g, st) : launch_pair<2, 7, false, 2>(g, st);
+    if (rc != AA_ERR_UNSUPPORTED) return rc;
   }
   return g.elem_size == 2 ? launch_es<2>(g, st) : launch_es<4>(g, st);
 }

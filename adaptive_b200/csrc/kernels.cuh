@@ -125,6 +125,7 @@ struct TcGemmArgs {
 int launch_gemm_tc(const TcGemmArgs& g, cudaStream_t s);
 int gemm_tc_argmax_tile_n(int N);
 int gemm_tc_argmax_tile_n_plain(int N);   // same for a plain (non-split) contraction with arg-max partials
+int set_gemm_pair(int on);     // diagnostics: 0 = single-CTA kernels only, 1 = CTA-pair kernels where they apply, < 0 = the environment's choice (AA_GEMM_PAIR, default on)
 int set_gemm_splitk(int on);   // diagnostics: 0 = never split K (deterministic summation order)
 
 // ---- vocab_refine.cu (filter-and-refine arg-max of the vocabulary projection, greedy decoding) ----

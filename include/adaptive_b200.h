@@ -126,6 +126,10 @@ int aa_debug_set_atten_sequential(int on);
 /* Diagnostics: on == 0 stops the tcgen05 GEMM from splitting K (partial tiles summed with red.global.add, i.e. a
  * run-to-run varying fp32 summation order in the affected gradients); default on. */
 int aa_debug_set_gemm_splitk(int on);
+/* Diagnostics: the CTA-pair contraction kernels (tcgen05.mma.cta_group::2, 256 x 256 tiles over the two SMs of a TPC; they serve the
+ * decode step's gate contraction and the maxima pass of its vocabulary arg-max).  0 = single-CTA kernels only, 1 = pairs where they
+ * apply, < 0 = the environment's choice (AA_GEMM_PAIR, default on). */
+int aa_debug_set_gemm_pair(int on);
 /* Diagnostics: cap on the K-split (thread-block cluster size 1, 2 or 4) of the persistent BPTT kernel. */
 int aa_debug_set_bptt_ksplit(int ks);
 /* Diagnostics: on == 0 makes the bf16 recurrences always take the grid-barrier kernels (lstm_seq.cu) instead of the

@@ -121,3 +121,39 @@ def test_tcgen05_split3_is_fp32_accurate(M, N, K):
     # core adds into its fp32 accumulator with truncation, so the error grows linearly with the number of accumulation
     # steps (3 per 8 elements of K) instead of with its square root.  The decode contractions have K <= 1536.
     assert err < 1e-5 * max(1.0, K / 1024), (err, err_simt)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 2048, 512), (300, 2560, 256), (64, 10000, 512), (517, 1024, 800)])
+def test_cta_pair_split3_equals_single_cta(M, N, K):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles over two SMs) against the single-CTA kernel on the same
+    pre-split operands: the same fp32-accurate result (each output element is the same sequence of k-steps into one fp32
+    accumulator; the decode tests' shard == slice property must not depend on which kernel a batch size selects -- the selection
+    does not look at M, and this pins that even a different kernel would not move a logit by more than the last place)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(M, K, generator=g, device="cuda")
+    B = torch.randn(N, K, generator=g, device="cuda")
+    bias = torch.randn(N, generator=g, device="cuda")
+    Kp = (K + 31) // 32 * 32
+    As, Bs = torch.zeros(M, 2 * Kp, device="cuda"), torch.zeros(N, 2 * Kp, device="cuda")
+    lib = _lib.load()
+    st = _stream(A.device)
+    _lib.check(lib.aa_split_tf32(_ptr(A), K, M, K, _ptr(As), Kp, st), "aa_split_tf32")
+    _lib.check(lib.aa_split_tf32(_ptr(B), K, N, K, _ptr(Bs), Kp, st), "aa_split_tf32")
+    outs = []
+    try:
+        for pair in (0, 1):
+            lib.aa_debug_set_gemm_pair(pair)
+            D = torch.full((M, N), float("nan"), device="cuda")
+            _lib.check(lib.aa_gemm_split3(M, N, Kp, _ptr(As), _ptr(Bs), _ptr(bias), _ptr(D), N, st), "aa_gemm_split3")
+            torch.cuda.synchronize()
+            outs.append(D)
+    finally:
+        lib.aa_debug_set_gemm_pair(-1)
+    assert torch.isfinite(outs[1]).all()
+    ref = A.double() @ B.double().t() + bias.double()
+    scale = float(ref.abs().max())
+    assert float((outs[1].double() - ref).abs().max()) / scale < 1e-5
+    # bit for bit wherever the single-CTA kernel keeps one K range (measured on B200: the first three shapes); it cuts K = 800 of the
+    # last shape into two ranges summed with red.add, which moves the last places
+    assert float((outs[1] - outs[0]).abs().max()) / scale < (2e-7 if K <= 512 else 1e-5)
+    print("pair == single bit for bit:", bool(torch.equal(outs[0], outs[1])))
