@@ -595,6 +595,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution barrier only: at the end of the kernel nothing is communicated through memory -- the peer must merely be past its last use of
+// this CTA's barriers and tensor memory.  (The releasing form waits for the CTA's outstanding global stores: 33.5 MB of gate pre-activations.)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
@@ -951,7 +956,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     g_pair_trace[((long long)blockIdx.x * 16 + 2) * 8 + 7] = (long long)gt;
   }
 #endif
-  cluster_sync_all();      // neither CTA frees tensor memory (or exits: its barriers are the peer's targets) before both are done
+  cluster_sync_relaxed();      // neither CTA frees tensor memory (or exits: its barriers are the peer's targets) before both are done
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
