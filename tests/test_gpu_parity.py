@@ -477,6 +477,29 @@ def test_stage_operators_vs_oracle():
     assert rel_err(sc.cpu().numpy(), sc_ref) < TOL and rel_err(al2.cpu().numpy(), a2) < TOL and rel_err(be2.cpu().numpy(), b2) < TOL
 
 
+@pytest.mark.parametrize("dims,B,L", [(CFG_A, 333, 6), (Dims(H=1024, E=128, Vc=20000, k=20), 40, 3)])
+def test_greedy_does_not_depend_on_the_contraction_kernel(dims, B, L):
+    """The CTA-pair contractions (tcgen05.mma.cta_group::2: the step's gate contraction and the maxima pass of the arg-max) against the
+    single-CTA kernels they replace: same ids, attention and Beta bit for bit (one K range each: the same sequence of k-steps into
+    one fp32 accumulator per element; the filter's candidates depend on the maxima only through a rigorous bound)."""
+    from adaptive_b200 import _lib
+    lib = _lib.load()
+    w = make_weights(dims, seed=123)
+    inp = make_inputs(dims, B, 1, seed=99)
+    W = dev_weights(w)
+    V, v_g, h0, c0, _ = dev_inputs(inp)
+    outs = []
+    try:
+        for pair in (0, 1):
+            lib.aa_debug_set_gemm_pair(pair)
+            outs.append(F_aa.greedy_decode(W, V, v_g, h0, c0, L, engine="pipeline"))
+            torch.cuda.synchronize()
+    finally:
+        lib.aa_debug_set_gemm_pair(-1)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
 @pytest.mark.parametrize("dims,B,L", [(CFG_A, 1024, 6), (Dims(H=128, E=64, Vc=1000, k=49), 300, 8), (Dims(H=48, E=20, Vc=77, k=10), 37, 7),
                                       (Dims(H=256, E=64, Vc=4097, k=20), 129, 5),
                                       (Dims(H=1024, E=128, Vc=20000, k=20), 40, 3)])      # BASELINE config 5's hidden size / vocabulary
