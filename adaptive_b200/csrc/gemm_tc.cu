@@ -578,9 +578,10 @@ int launch_cfg(const TcGemmArgs& g, cudaStream_t st) {
 // Two CTAs on the two SMs of one TPC (cluster of 2) share a 256 x 256 output tile: each stages ITS 128 rows of A and ITS 128
 // rows of B per k-block, the leader's elected thread issues one M = 256, N = 256 MMA per k-step for both SMs (each tensor core
 // reads its own A half and both B halves), and each CTA's tensor memory receives its 128 rows x 256 columns of the accumulator.
-// Per SM and k-block the same 32 KB (bf16) / 64 KB (3xTF32) of operands as a 128 x 128 single-CTA tile -- for twice the output:
-// the K = 512 contractions of the decode step are bound by the operand feed from L2 (~50 B/clk per SM, ~6300 B/clk for the chip:
-// profiles/r02_* and DESIGN.md 4), not by the tensor pipe, and a 256-wide MMA costs 128 cycles against 103 for a 128-wide one.
+// Per SM and k-block the same 32 KB (bf16) / 64 KB (3xTF32) of operands as a 128 x 128 single-CTA tile -- for twice the output --
+// and 256-wide MMAs: an MMA costs 128 cycles at N = 256 against 104 for any N <= 128 (kind::tf32 at half the flops of kind::f16:
+// profiles/r02_mma_probe_tf32.jsonl), so only 256-wide tiles reach the tensor peak, and the single-CTA 3xTF32 kernel cannot hold them
+// (96 KB stages).  Measured history and what bounds each user now: DESIGN.md 4 item 17, profiles/r02_pair_trace.txt.
 //   barriers: full[s] lives in the LEADER (both CTAs' TMA loads complete on it: cp.async.bulk.tensor ... .cta_group::2 with the
 //   peer bit of the barrier address cleared); empty[s] and tmem_full[a] exist in both CTAs and are signalled by ONE multicast
 //   tcgen05.commit; tmem_empty[a] lives in the leader and counts the epilogue warps of both CTAs (remote mbarrier.arrive).
@@ -596,7 +597,7 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // Execution barrier only: at the end of the kernel nothing is communicated through memory -- the peer must merely be past its last use of
-// this CTA's barriers and tensor memory.  (The releasing form waits for the CTA's outstanding global stores: 33.5 MB of gate pre-activations.)
+// this CTA's barriers and tensor memory.  (Measured equal to the releasing form: the kernel's exit waits for its output stores either way.)
 __device__ __forceinline__ void cluster_sync_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
 }
@@ -633,8 +634,9 @@ __device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t desc_a, uint64
 
 // ARES (A resident; plain operands, K <= ARES_KB k-blocks): the pair walks a CONTIGUOUS range of tiles in n-fastest order, so that its
 // 256 rows of A change at most once or twice per launch; they stay in shared memory (one 16 KB box per k-block and CTA) and only B is
-// streamed through the stage ring -- half the operand bytes per tile again.  The vocabulary maxima pass (K = 512: 128 KB of A per
-// CTA) moved 336 MB from L2 at 8.6 TB/s, its bound (profiles/r02_pair_ncu_details.txt); the MMAs need 19 us of its 39.
+// streamed through the stage ring -- half the operand bytes per tile again (336 -> ~175 MB per vocabulary maxima pass, K = 512: 128 KB
+// of A per CTA).  With it the pass's tile period is 32 MMAs x 128 cycles: tensor-bound in its steady state (profiles/r02_pair_trace.txt);
+// the gain over the streamed form is small (39.3 -> 38.2 us) because set-up, the ninth round and the exit are 40 % of the launch.
 constexpr int ARES_KB = 8;
 
 #ifdef AA_PAIR_TRACE      // development build only (tools/trace_pair.py): per-tile wait / work cycles of the MMA warp and of one epilogue warp
