@@ -307,3 +307,50 @@ def test_argmax_filter_exact_decomposition_bound():
     assert (b[dense, 1:] < 0.6 * rel[dense, 1:]).all()        # ~2x tighter than the relative bound on dense rows and tiles ...
     keep_rel = tmax + rel >= (tmax - rel).max(1, keepdims=True)
     assert keep[dense].sum() < 0.85 * keep_rel[dense].sum()   # ... which shows in the number of tiles handed to the refinement
+
+
+def test_refine_butterfly_sums_do_not_depend_on_rows_per_warp():
+    """csrc/vocab_refine.cu ``refine_rows``: a warp reduces NR x 16 per-lane partial sums with a halving exchange (lane bits 4, 3, 2, 1, 0
+    in this order).  The claim the decode sharding rests on: the value a (row, column) pair ends up with is the same fp32 number whether
+    the pair was refined by a CTA unit (NR = 4 rows per warp) or a warp unit (NR = 2) -- the same reduction tree over the 32 lanes'
+    partials.  Emulated here in numpy with the kernel's exact order of fp32 additions."""
+    rng = np.random.default_rng(5)
+    TN = 16
+
+    def butterfly(acc):                      # acc [32 lanes, NR * 16] float32 -> {(row, col): value}, as the kernel leaves them
+        acc = acc.copy()
+        n = acc.shape[1]
+        half, bit = n // 2, 16
+        while bit >= 1:
+            new = acc.copy()
+            for lane in range(32):
+                up = (lane & bit) != 0
+                for i in range(half):
+                    keep = acc[lane, i + half] if up else acc[lane, i]
+                    partner_up = ((lane ^ bit) & bit) != 0      # the partner sends acc[i] if IT is `up`, else acc[i + half]
+                    recv = acc[lane ^ bit, i] if partner_up else acc[lane ^ bit, i + half]
+                    new[lane, i] = np.float32(keep) + np.float32(recv)
+            acc = new
+            half //= 2
+            bit //= 2
+        nr = n // TN
+        lpr, cpl = 32 // nr, TN // (32 // nr)
+        out = {}
+        for lane in range(32):
+            m, c0 = lane // lpr, (lane % lpr) * cpl
+            for e in range(cpl):
+                out[(m, c0 + e)] = acc[lane, e]
+        return out
+
+    part4 = (rng.standard_normal((32, 4 * TN)) * 3).astype(np.float32)          # rows 0..3 of a CTA unit
+    r4 = butterfly(part4)
+    for pair_of_rows in ((0, 1), (2, 3), (1, 3)):
+        part2 = np.concatenate([part4[:, m * TN:(m + 1) * TN] for m in pair_of_rows], axis=1)    # the same two rows as a warp unit
+        r2 = butterfly(part2)
+        for k, m in enumerate(pair_of_rows):
+            for j in range(TN):
+                assert r2[(k, j)].tobytes() == r4[(m, j)].tobytes(), (m, j)
+    # and the tree really sums all 32 lanes
+    ref = part4.astype(np.float64).sum(0)
+    got = np.array([r4[(m, j)] for m in range(4) for j in range(TN)], dtype=np.float64)
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-4)
